@@ -1,0 +1,420 @@
+"""ctypes bindings of the two C ABIs (include/en234gpu.h, include/en234host.h).
+
+Python is only glue here (tests, bench, torch.distributed plumbing): every numerical step runs inside
+liben234gpu.so on the device.  There is no CPU fallback — creating a GpuSystem without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+
+class Stats(C.Structure):
+    _fields_ = [("assemble_ms", C.c_double), ("bc_ms", C.c_double), ("solve_ms", C.c_double),
+                ("spmv_ms_avg", C.c_double), ("kernel_launches", C.c_longlong), ("last_cg_iterations", C.c_int),
+                ("last_cg_err", C.c_double)]
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_double_p)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(c_int_p)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+_gpu = None
+_host = None
+
+GPU_SYMBOLS = [
+    "en234gpu_last_error", "en234gpu_device_count", "en234gpu_create", "en234gpu_destroy", "en234gpu_set_stream",
+    "en234gpu_assemble", "en234gpu_apply_boundaryconditions", "en234gpu_solve", "en234gpu_set_operator_mode",
+    "en234gpu_upload_state", "en234gpu_assemble_dev", "en234gpu_apply_boundaryconditions_dev", "en234gpu_solve_dev",
+    "en234gpu_download_state", "en234gpu_zero_increment_dev", "en234gpu_element_batch", "en234gpu_get_svars",
+    "en234gpu_nnz_blocks", "en234gpu_get_csr", "en234gpu_get_rhs", "en234gpu_apply_operator",
+    "en234gpu_get_unique_id", "en234gpu_comm_init", "en234gpu_set_partition", "en234gpu_get_stats",
+]
+HOST_SYMBOLS = [
+    "en234host_model_read", "en234host_model_from_text", "en234host_model_free", "en234host_last_error",
+    "en234host_model_int", "en234host_model_double", "en234host_model_find_set", "en234host_model_set",
+    "en234host_model_write_text", "en234host_evaluate_loads", "en234host_gpu_create", "en234host_run_static",
+    "en234host_partition", "en234host_part_free", "en234host_part_int", "en234host_part_owned",
+    "en234host_part_gpu_create",
+]
+
+
+def gpu_lib():
+    """liben234gpu.so (raises if it was not built: the product never falls back to a CPU path)."""
+    global _gpu
+    if _gpu is None:
+        path = os.path.join(_CSRC, "liben234gpu.so")
+        if not os.path.exists(path):
+            raise RuntimeError("liben234gpu.so is not built (run python -c 'import __graft_entry__ as g; g.build()')")
+        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        L.en234gpu_last_error.restype = C.c_char_p
+        L.en234gpu_nnz_blocks.restype = C.c_longlong
+        L.en234gpu_nnz_blocks.argtypes = [C.c_void_p]
+        _gpu = L
+    return _gpu
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        gpu_lib()
+        path = os.path.join(_CSRC, "liben234host.so")
+        if not os.path.exists(path):
+            raise RuntimeError("liben234host.so is not built")
+        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        L.en234host_last_error.restype = C.c_char_p
+        L.en234host_model_read.restype = C.c_void_p
+        L.en234host_model_read.argtypes = [C.c_char_p]
+        L.en234host_model_from_text.restype = C.c_void_p
+        L.en234host_model_from_text.argtypes = [C.c_char_p]
+        L.en234host_model_free.argtypes = [C.c_void_p]
+        L.en234host_model_write_text.restype = C.c_long
+        L.en234host_model_write_text.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
+        L.en234host_partition.restype = C.c_void_p
+        L.en234host_partition.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.en234host_part_free.argtypes = [C.c_void_p]
+        L.en234host_part_owned.restype = C.POINTER(C.c_ubyte)
+        L.en234host_part_owned.argtypes = [C.c_void_p]
+        _host = L
+    return _host
+
+
+INT_ARRAYS = ["connectivity", "element_flag", "element_prop_index", "element_n_props", "element_n_states",
+              "history_ptr", "nodeset_ptr", "nodeset_nodes", "elementset_ptr", "elementset_elements",
+              "pdof_flag", "pdof_dof", "pdof_node", "pdof_nodeset", "pdof_history", "pdof_rate",
+              "pforce_flag", "pforce_dof", "pforce_node", "pforce_nodeset", "pforce_history",
+              "dload_flag", "dload_elset", "dload_face", "dload_history", "dload_val_ptr"]
+INT_SCALARS = ["n_nodes", "n_elements", "max_no_steps", "solvertype", "nonlinear", "max_newton_iterations",
+               "unsymmetric", "abaqusformat", "max_cg_iterations", "checkstiffness_flag"]
+DBL_ARRAYS = ["coords", "element_properties", "history_time", "history_value", "pdof_value", "pforce_value",
+              "dload_values"]
+DBL_SCALARS = ["timestep_initial", "timestep_min", "timestep_max", "max_total_time", "newtonraphson_tolerance",
+               "cg_tolerance"]
+
+
+class Model:
+    """A parsed EN234_FEA input file (reference: src/read_input_file.f90)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise ValueError("input error: " + host_lib().en234host_last_error().decode())
+        self.h = C.c_void_p(handle)
+
+    @classmethod
+    def read(cls, path):
+        return cls(host_lib().en234host_model_read(os.fsencode(path)))
+
+    @classmethod
+    def from_text(cls, text):
+        return cls(host_lib().en234host_model_from_text(text.encode()))
+
+    def close(self):
+        if self.h:
+            host_lib().en234host_model_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ints(self, name):
+        p, n = c_int_p(), C.c_long()
+        if host_lib().en234host_model_int(self.h, name.encode(), C.byref(p), C.byref(n)):
+            raise KeyError(name)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.int32)
+
+    def doubles(self, name):
+        p, n = c_double_p(), C.c_long()
+        if host_lib().en234host_model_double(self.h, name.encode(), C.byref(p), C.byref(n)):
+            raise KeyError(name)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.float64)
+
+    def set(self, name, value):
+        if host_lib().en234host_model_set(self.h, name.encode(), C.c_double(value)):
+            raise KeyError(name)
+
+    def arrays(self):
+        """All flat arrays/scalars as a dict of numpy arrays (the schema the oracle's or_model_set_* accepts)."""
+        d = {k: self.ints(k) for k in INT_ARRAYS + INT_SCALARS}
+        d.update({k: self.doubles(k) for k in DBL_ARRAYS + DBL_SCALARS})
+        return d
+
+    @property
+    def n_nodes(self):
+        return int(self.ints("n_nodes")[0])
+
+    @property
+    def n_elements(self):
+        return int(self.ints("n_elements")[0])
+
+    def text(self):
+        n = host_lib().en234host_model_write_text(self.h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        host_lib().en234host_model_write_text(self.h, buf, n + 1)
+        return buf.value.decode()
+
+    def find_set(self, name, element_set=False):
+        return host_lib().en234host_model_find_set(self.h, 1 if element_set else 0, name.encode())
+
+    def evaluate_loads(self, time, dtime, dof_total=None, dof_increment=None):
+        nd = 3 * self.n_nodes
+        ut = _f64(dof_total) if dof_total is not None else np.zeros(nd)
+        du = _f64(dof_increment) if dof_increment is not None else np.zeros(nd)
+        fe, fx = np.zeros(nd), np.zeros(nd)
+        cap = int(self.ints("nodeset_nodes").size + self.ints("pdof_flag").size + 16)
+        fd, fv, fc = np.zeros(cap, np.int32), np.zeros(cap), np.zeros(cap)
+        n = C.c_int()
+        rc = host_lib().en234host_evaluate_loads(self.h, C.c_double(time), C.c_double(dtime), _dp(ut), _dp(du), _dp(fe),
+                                                 _dp(fx), C.byref(n), _ip(fd), _dp(fv), _dp(fc), C.c_int(cap))
+        if rc:
+            raise RuntimeError(host_lib().en234host_last_error().decode())
+        return fe, fx, fd[:n.value].copy(), fv[:n.value].copy(), fc[:n.value].copy()
+
+
+class GpuSystem:
+    """One device handle (en234gpu_create ... en234gpu_destroy)."""
+
+    def __init__(self, model=None, device=0, arrays=None, part=None):
+        L = gpu_lib()
+        self.h = C.c_void_p()
+        self.model = model
+        if part is not None:
+            rc = host_lib().en234host_part_gpu_create(model.h, part.h, C.c_int(device), C.byref(self.h))
+            err = host_lib().en234host_last_error
+            self.n_nodes = part.n_nodes
+        elif arrays is not None:
+            co, cn = _f64(arrays["coords"]), _i32(arrays["connectivity"])
+            fl, pi, pr = _i32(arrays["element_flag"]), _i32(arrays["element_prop_index"]), _f64(arrays["element_properties"])
+            self.n_nodes = co.size // 3
+            rc = L.en234gpu_create(C.byref(self.h), C.c_int(device), C.c_int(self.n_nodes), C.c_int(fl.size), _dp(co), _ip(cn),
+                                   _ip(fl), _ip(pi), _dp(pr), C.c_int(pr.size))
+            err = L.en234gpu_last_error
+        else:
+            rc = host_lib().en234host_gpu_create(model.h, C.c_int(device), C.byref(self.h))
+            err = host_lib().en234host_last_error
+            self.n_nodes = model.n_nodes
+        if rc:
+            self.h = None
+            raise RuntimeError("en234gpu_create failed: " + err().decode())
+        self.ndof = 3 * self.n_nodes
+
+    def _ck(self, rc):
+        if rc:
+            raise RuntimeError(gpu_lib().en234gpu_last_error().decode())
+
+    def close(self):
+        if self.h:
+            gpu_lib().en234gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_operator_mode(self, method):
+        self._ck(gpu_lib().en234gpu_set_operator_mode(self.h, C.c_int(method)))
+
+    def set_stream(self, cuda_stream):
+        self._ck(gpu_lib().en234gpu_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    # ---- host-buffer entry points
+    def assemble(self, dof_total, dof_increment, f_element_ext=None, want_rforce=True):
+        ut, du, fe = _f64(dof_total), _f64(dof_increment), _f64(f_element_ext)
+        rf = np.zeros(self.ndof) if want_rforce else None
+        nrm, fail = C.c_double(), C.c_int()
+        self._ck(gpu_lib().en234gpu_assemble(self.h, _dp(ut), _dp(du), _dp(fe), _dp(rf), C.byref(nrm), C.byref(fail)))
+        return rf, nrm.value, fail.value
+
+    def apply_boundaryconditions(self, f_ext, fixed_dof, fixed_correction):
+        fx, fd, fc = _f64(f_ext), _i32(fixed_dof), _f64(fixed_correction)
+        nrm = C.c_double()
+        self._ck(gpu_lib().en234gpu_apply_boundaryconditions(self.h, _dp(fx), C.c_int(fd.size), _ip(fd), _dp(fc), C.byref(nrm)))
+        return nrm.value
+
+    def solve(self, dof_increment, method=0, cg_tolerance=1e-17, max_cg_iterations=1000):
+        du = _f64(dof_increment).copy()
+        nrm, its, fail = C.c_double(), C.c_int(), C.c_int()
+        self._ck(gpu_lib().en234gpu_solve(self.h, C.c_int(method), C.c_double(cg_tolerance), C.c_int(max_cg_iterations),
+                                          _dp(du), C.byref(nrm), C.byref(its), C.byref(fail)))
+        return du, nrm.value, its.value, fail.value
+
+    # ---- device-resident variants
+    def upload_state(self, dof_total, dof_increment, f_element_ext, f_ext, fixed_dof, fixed_value):
+        ut, du, fe, fx = _f64(dof_total), _f64(dof_increment), _f64(f_element_ext), _f64(f_ext)
+        fd, fv = _i32(fixed_dof), _f64(fixed_value)
+        self._ck(gpu_lib().en234gpu_upload_state(self.h, _dp(ut), _dp(du), _dp(fe), _dp(fx), C.c_int(fd.size), _ip(fd), _dp(fv)))
+
+    def assemble_dev(self):
+        nrm, fail = C.c_double(), C.c_int()
+        self._ck(gpu_lib().en234gpu_assemble_dev(self.h, C.byref(nrm), C.byref(fail)))
+        return nrm.value, fail.value
+
+    def apply_boundaryconditions_dev(self):
+        nrm = C.c_double()
+        self._ck(gpu_lib().en234gpu_apply_boundaryconditions_dev(self.h, C.byref(nrm)))
+        return nrm.value
+
+    def solve_dev(self, method=0, cg_tolerance=1e-17, max_cg_iterations=1000):
+        nrm, its, fail = C.c_double(), C.c_int(), C.c_int()
+        self._ck(gpu_lib().en234gpu_solve_dev(self.h, C.c_int(method), C.c_double(cg_tolerance), C.c_int(max_cg_iterations),
+                                              C.byref(nrm), C.byref(its), C.byref(fail)))
+        return nrm.value, its.value, fail.value
+
+    def download_state(self, out_du=None, out_rf=None):
+        du = out_du if out_du is not None else np.zeros(self.ndof)
+        rf = out_rf if out_rf is not None else np.zeros(self.ndof)
+        self._ck(gpu_lib().en234gpu_download_state(self.h, _dp(du), _dp(rf)))
+        return du, rf
+
+    def zero_increment_dev(self):
+        self._ck(gpu_lib().en234gpu_zero_increment_dev(self.h))
+
+    # ---- plugin surface / inspection
+    def element_batch(self, element_numbers, dof_total, dof_increment):
+        el = _i32(element_numbers)
+        K, R = np.zeros((el.size, 576)), np.zeros((el.size, 24))
+        fail = C.c_int()
+        self._ck(gpu_lib().en234gpu_element_batch(self.h, C.c_int(el.size), _ip(el), _dp(_f64(dof_total)), _dp(_f64(dof_increment)),
+                                                  _dp(K), _dp(R), C.byref(fail)))
+        # column-major (ROW,COL) -> K[e][row, col]
+        return K.reshape(el.size, 24, 24).transpose(0, 2, 1).copy(), R, fail.value
+
+    def svars(self, dof_total, dof_increment, n_elements):
+        sv = np.zeros(48 * n_elements)
+        self._ck(gpu_lib().en234gpu_get_svars(self.h, _dp(_f64(dof_total)), _dp(_f64(dof_increment)), _dp(sv)))
+        return sv.reshape(n_elements, 8, 6)
+
+    def nnz_blocks(self):
+        return gpu_lib().en234gpu_nnz_blocks(self.h)
+
+    def csr(self):
+        import scipy.sparse as sp
+        nnz = 9 * self.nnz_blocks()
+        rowptr, col, val = np.zeros(self.ndof + 1, np.int64), np.zeros(nnz, np.int32), np.zeros(nnz)
+        self._ck(gpu_lib().en234gpu_get_csr(self.h, rowptr.ctypes.data_as(C.POINTER(C.c_longlong)), _ip(col), _dp(val)))
+        return sp.csr_matrix((val, col, rowptr), shape=(self.ndof, self.ndof))
+
+    def rhs(self, want_diag=False):
+        r = np.zeros(self.ndof)
+        d = np.zeros(self.ndof) if want_diag else None
+        self._ck(gpu_lib().en234gpu_get_rhs(self.h, _dp(r), _dp(d)))
+        return (r, d) if want_diag else r
+
+    def apply_operator(self, x, method=0):
+        y = np.zeros(self.ndof)
+        self._ck(gpu_lib().en234gpu_apply_operator(self.h, C.c_int(method), _dp(_f64(x)), _dp(y)))
+        return y
+
+    def stats(self):
+        s = Stats()
+        self._ck(gpu_lib().en234gpu_get_stats(self.h, C.byref(s)))
+        return s
+
+    # ---- multi-GPU
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        if gpu_lib().en234gpu_get_unique_id(buf):
+            raise RuntimeError(gpu_lib().en234gpu_last_error().decode())
+        return buf.raw
+
+    def comm_init(self, n_ranks, rank, uid):
+        self._ck(gpu_lib().en234gpu_comm_init(self.h, C.c_int(n_ranks), C.c_int(rank), C.c_char_p(uid)))
+
+    # ---- whole static analysis through the host driver (src/staticstep.f90 loop)
+    def run_static(self, method=0, cg_tolerance=0.0, max_cg_iterations=0, check_linear_cg=True, use_host_api=False,
+                   log_path=None):
+        nd = self.ndof
+        u, rf = np.zeros(nd), np.zeros(nd)
+        newton, cg = np.zeros((4096, 8)), np.zeros(4096, np.int32)
+        info = (C.c_longlong * 8)()
+        self.set_operator_mode(method)
+        rc = host_lib().en234host_run_static(self.model.h, self.h, C.c_int(method), C.c_double(cg_tolerance),
+                                             C.c_int(max_cg_iterations), C.c_int(1 if check_linear_cg else 0),
+                                             C.c_int(1 if use_host_api else 0), _dp(u), _dp(rf), _dp(newton), C.c_int(4096),
+                                             _ip(cg), C.c_int(4096), info, os.fsencode(log_path) if log_path else None)
+        if rc:
+            raise RuntimeError("static step failed: " + host_lib().en234host_last_error().decode())
+        return {"dof_total": u, "rforce": rf, "newton": newton[:info[2]].copy(), "cg_iterations": cg[:info[3]].copy(),
+                "n_steps": int(info[0]), "n_cutbacks": int(info[1])}
+
+
+class Partition:
+    """Element partition of a model for one rank (en234host_partition)."""
+
+    def __init__(self, model, n_ranks, rank):
+        self.h = C.c_void_p(host_lib().en234host_partition(model.h, C.c_int(n_ranks), C.c_int(rank)))
+        if not self.h:
+            raise RuntimeError(host_lib().en234host_last_error().decode())
+        self.n_ranks, self.rank = n_ranks, rank
+
+    def ints(self, name):
+        p, n = c_int_p(), C.c_long()
+        if host_lib().en234host_part_int(self.h, name.encode(), C.byref(p), C.byref(n)):
+            raise KeyError(name)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.int32)
+
+    @property
+    def n_nodes(self):
+        return int(self.ints("n_nodes")[0])
+
+    def owned(self):
+        p = host_lib().en234host_part_owned(self.h)
+        return np.ctypeslib.as_array(p, shape=(self.n_nodes,)).copy()
+
+    def close(self):
+        if self.h:
+            host_lib().en234host_part_free(self.h)
+            self.h = None
+
+
+def synthetic_block_input(nx, ny=None, nz=None, jitter=0.2, seed=1234, element="1001", E=100.0, nu=0.3,
+                          solver="CONJUGATE GRADIENT", cg_tolerance=1e-17, cg_maxit=1000, load="traction",
+                          nonlinear=None, steps=1, props=None, dt=1.0):
+    """`.in` text of the synthetic structured hex8 blocks of BASELINE.json: face x=0 clamped,
+    face x=max loaded by the traction (0,0,-1) ("traction") or a prescribed u_x ramp ("stretch")."""
+    ny = nx if ny is None else ny
+    nz = nx if nz is None else nz
+    flag = int(element[1:]) + 99999 if element.upper().startswith("U") else int(element)
+    plist = props if props is not None else [E, nu]
+    t = ["MESH", " USER SUBROUTINE",
+         "  %d, %d, %d, %.17g, %d, %d, 0" % (nx, ny, nz, jitter, seed, flag),
+         "  " + ", ".join("%.17g" % p for p in plist), " END USER SUBROUTINE", "END MESH", "BOUNDARY CONDITIONS"]
+    if load == "stretch":
+        t += [" HISTORY, ramp", "  0.d0, 0.d0", "  %.17g, 0.2d0" % (steps * dt), " END HISTORY"]
+    t += [" DEGREES OF FREEDOM", "  xmin, 1, VALUE, 0.d0", "  xmin, 2, VALUE, 0.d0", "  xmin, 3, VALUE, 0.d0"]
+    if load == "stretch":
+        t += ["  xmax, 1, HISTORY, ramp"]
+    t += [" END DEGREES OF FREEDOM"]
+    if load == "traction":
+        t += [" DISTRIBUTED LOADS", "  xmax_el, 4, VALUE, 0.d0, 0.d0, -1.d0", " END DISTRIBUTED LOADS"]
+    t += ["END BOUNDARY CONDITIONS", "STATIC STEP", " INITIAL TIME STEP, %.17g" % dt, " MAX TIME STEP, %.17g" % dt,
+          " MIN TIME STEP, %.17g" % (dt / 1024.0), " MAX NUMBER OF STEPS, %d" % steps, " STOP TIME, %.17g" % (steps * dt)]
+    if nonlinear:
+        t += [" SOLVER, %s, NONLINEAR, %.17g, %d" % (solver, nonlinear[0], nonlinear[1])]
+    else:
+        t += [" SOLVER, %s, LINEAR" % solver]
+    t += [" CG TOLERANCE, %.17g" % cg_tolerance, " CG MAX ITERATIONS, %d" % cg_maxit, "END STATIC STEP", "STOP", ""]
+    return "\n".join(t)

@@ -1,0 +1,713 @@
+// liben234gpu.so — C ABI (include/en234gpu.h) over the sm_100a kernels.  Host code here only builds index
+// structures once per analysis and launches kernels; there is no CPU implementation of any numerical step.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/en234gpu.h"
+#include "en234gpu_asm.cuh"
+#include "en234gpu_aux.cuh"
+#include "en234gpu_cg.cuh"
+#include "en234gpu_mf.cuh"
+#include "en234gpu_comm.h"
+
+using namespace en234k;
+
+static thread_local std::string g_err;
+static int set_err(const std::string& s) { g_err = s; return 1; }
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            return set_err(std::string(#call) + ": " + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + \
+                           std::to_string(__LINE__));                                                \
+        }                                                                                            \
+    } while (0)
+
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+constexpr int CG_CHUNK = 16;   // PCG iterations per CUDA-graph launch (even: iteration parity is baked into the graph)
+
+struct en234gpu_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int N = 0, E = 0, ndof = 0, n_sm = 148;
+    long long nnzb = 0;
+    // mesh
+    DevBuf<double> x, y, z;
+    DevBuf<int> conn, mat, adj_ptr, adj, browptr, bcol;
+    DevBuf<uint8_t> slot;
+    DevBuf<Material> mats;
+    // system
+    DevBuf<double> val, rhs, rforce, minv, ut, du, felem, fext, cval, sol, r, p, Ap, part, part2, part3, tmpvec, tmpvec2;
+    DevBuf<uint8_t> cflag, owned;
+    DevBuf<int> fixdof;
+    DevBuf<double> fixval;
+    int n_fixed = 0;
+    bool have_felem = false, have_fext = false, have_owned = false;
+    DevBuf<CgScalars> S;
+    CgScalars* hS = nullptr;     // pinned mirror
+    // matrix-free
+    MfData mf;
+    // graphs
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    // launch geometry
+    int grid_rows = 0, grid_vec = 0;
+    size_t asm_smem = 0;
+    // host copies needed for inspection
+    std::vector<int> h_browptr, h_bcol;
+    // multi-GPU
+    Comm comm;
+    // stats
+    en234gpu_stats st{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool matrix_valid = false, rhs_valid = false;
+    int mode = EN234_SOLVE_PCG_BSR;   // operator mode: assembled block-CSR or matrix-free
+};
+
+static Mesh mesh_of(en234gpu_ctx* c) {
+    Mesh M;
+    M.N = c->N; M.E = c->E;
+    M.x = c->x.p; M.y = c->y.p; M.z = c->z.p;
+    M.conn = c->conn.p; M.mat = c->mat.p; M.mats = c->mats.p;
+    M.adj_ptr = c->adj_ptr.p; M.adj = c->adj.p; M.slot = c->slot.p;
+    M.browptr = c->browptr.p; M.bcol = c->bcol.p;
+    return M;
+}
+
+extern "C" {
+
+const char* en234gpu_last_error(void) { return g_err.c_str(); }
+
+int en234gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_elements, const double* coords,
+                    const int* connectivity, const int* element_flag, const int* element_prop_index,
+                    const double* element_properties, int n_element_properties) {
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err("en234gpu_create: no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return set_err("en234gpu_create: bad device index");
+    if (n_nodes <= 0 || n_elements <= 0) return set_err("en234gpu_create: empty mesh");
+    if ((long long)n_nodes * 3 >= 2147483647LL) return set_err("en234gpu_create: more than 2^31 DOFs per GPU");
+    CK(cudaSetDevice(device));
+    auto* c = new en234gpu_ctx();
+    c->device = device;
+    c->N = n_nodes; c->E = n_elements; c->ndof = 3 * n_nodes;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->n_sm = prop.multiProcessorCount;
+    const int N = n_nodes, E = n_elements;
+
+    // ---- materials: one table entry per distinct (flag, property offset)
+    std::map<std::pair<int, int>, int> matmap;
+    std::vector<Material> mats;
+    std::vector<int> mat(E);
+    for (int e = 0; e < E; ++e) {
+        const int flag = element_flag[e], pi = element_prop_index ? element_prop_index[e] : 0;
+        auto key = std::make_pair(flag, pi);
+        auto it = matmap.find(key);
+        if (it == matmap.end()) {
+            Material m{};
+            if (flag == EN234_ID_LINELAST || flag == EN234_FLAG_UEL_BASE + 1) {
+                if (pi + 2 > n_element_properties) { delete c; return set_err("element needs 2 properties (E, nu)"); }
+                const double Em = element_properties[pi], xnu = element_properties[pi + 1];
+                m.kind = 0;                                           // el_linelast_3Dbasic.f90:93-98
+                m.d44 = 0.5 * Em / (1 + xnu);
+                m.d11 = (1.0 - xnu) * Em / ((1 + xnu) * (1 - 2.0 * xnu));
+                m.d12 = xnu * Em / ((1 + xnu) * (1 - 2.0 * xnu));
+            } else if (flag == EN234_ID_NEOHOOKE || flag == EN234_FLAG_UEL_BASE + 2) {
+                if (pi + 2 > n_element_properties) { delete c; return set_err("element needs 2 properties (mu, K)"); }
+                m.kind = 1;
+                m.mu = element_properties[pi];
+                m.kappa = element_properties[pi + 1];
+            } else {
+                delete c;                                             // user_element.f90:83-86
+                return set_err("invalid element type " + std::to_string(flag) +
+                               " (device element types: 1001, 1002, U1, U2)");
+            }
+            it = matmap.emplace(key, (int)mats.size()).first;
+            mats.push_back(m);
+        }
+        mat[e] = it->second;
+    }
+    bool any_neo = false;
+    for (auto& m : mats) any_neo |= m.kind == 1;
+
+    // ---- SoA mesh, adjacency (ascending element order), block-CSR pattern, slot map
+    std::vector<double> xs(N), ys(N), zs(N);
+    for (int n = 0; n < N; ++n) { xs[n] = coords[3 * (size_t)n]; ys[n] = coords[3 * (size_t)n + 1]; zs[n] = coords[3 * (size_t)n + 2]; }
+    std::vector<int> conn((size_t)8 * E);
+    std::vector<int> adj_ptr(N + 1, 0);
+    for (int e = 0; e < E; ++e)
+        for (int a = 0; a < 8; ++a) {
+            const int n = connectivity[8 * (size_t)e + a] - 1;
+            if (n < 0 || n >= N) { delete c; return set_err("connectivity refers to a node that does not exist"); }
+            conn[(size_t)a * E + e] = n;
+            adj_ptr[n + 1]++;
+        }
+    for (int n = 0; n < N; ++n) adj_ptr[n + 1] += adj_ptr[n];
+    std::vector<int> adj((size_t)8 * E), fill(adj_ptr.begin(), adj_ptr.end() - 1);
+    for (int e = 0; e < E; ++e)
+        for (int a = 0; a < 8; ++a) adj[fill[conn[(size_t)a * E + e]]++] = e * 8 + a;
+    std::vector<int>& browptr = c->h_browptr;
+    std::vector<int>& bcol = c->h_bcol;
+    browptr.assign(N + 1, 0);
+    bcol.clear();
+    bcol.reserve((size_t)27 * N);
+    std::vector<uint8_t> slot((size_t)64 * E);
+    std::vector<int> cols;
+    for (int i = 0; i < N; ++i) {
+        cols.clear();
+        for (int k = adj_ptr[i]; k < adj_ptr[i + 1]; ++k) {
+            const int e = adj[k] >> 3;
+            for (int b = 0; b < 8; ++b) cols.push_back(conn[(size_t)b * E + e]);
+        }
+        if (cols.empty()) cols.push_back(i);          // isolated node: keep a diagonal block so 1/diag is defined
+        std::sort(cols.begin(), cols.end());
+        cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+        if (cols.size() > 255) { delete c; return set_err("a node couples to more than 255 nodes"); }
+        for (int k = adj_ptr[i]; k < adj_ptr[i + 1]; ++k) {
+            const int e = adj[k] >> 3;
+            for (int b = 0; b < 8; ++b) {
+                const int col = conn[(size_t)b * E + e];
+                slot[(size_t)k * 8 + b] = (uint8_t)(std::lower_bound(cols.begin(), cols.end(), col) - cols.begin());
+            }
+        }
+        bcol.insert(bcol.end(), cols.begin(), cols.end());
+        if (bcol.size() > 2000000000ULL) { delete c; return set_err("too many matrix blocks for one GPU"); }
+        browptr[i + 1] = (int)bcol.size();
+    }
+    c->nnzb = (long long)bcol.size();
+
+    // ---- device storage
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+#define UP(buf, vec)                                                                                  \
+    CK(c->buf.alloc((vec).size()));                                                                    \
+    CK(cudaMemcpy(c->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice))
+    UP(x, xs); UP(y, ys); UP(z, zs); UP(conn, conn); UP(mat, mat); UP(mats, mats);
+    UP(adj_ptr, adj_ptr); UP(adj, adj); UP(slot, slot); UP(browptr, browptr); UP(bcol, bcol);
+#undef UP
+    const size_t nd = (size_t)c->ndof;
+    CK(c->val.alloc(9 * (size_t)c->nnzb));
+    for (DevBuf<double>* b : {&c->rhs, &c->rforce, &c->minv, &c->ut, &c->du, &c->felem, &c->fext, &c->cval, &c->sol, &c->r,
+                              &c->p, &c->Ap, &c->tmpvec, &c->tmpvec2}) {
+        CK(b->alloc(nd));
+        CK(cudaMemset(b->p, 0, nd * sizeof(double)));
+    }
+    CK(c->cflag.alloc(nd));
+    CK(cudaMemset(c->cflag.p, 0, nd));
+    CK(c->part.alloc(MAX_PARTIALS)); CK(c->part2.alloc(MAX_PARTIALS)); CK(c->part3.alloc(MAX_PARTIALS));
+    CK(c->S.alloc(1));
+    CK(cudaMemset(c->S.p, 0, sizeof(CgScalars)));
+    CK(cudaMallocHost((void**)&c->hS, sizeof(CgScalars)));
+    std::memset(c->hS, 0, sizeof(CgScalars));
+
+    // ---- launch geometry: persistent grids sized from the SM count (148 on B200)
+    c->asm_smem = (size_t)WARPS * (GEOM_PER_WARP + ACC_PER_WARP) * sizeof(double);
+    CK(cudaFuncSetAttribute(k_assemble_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->asm_smem));
+    c->grid_rows = std::min(MAX_PARTIALS, std::max(1, std::min((N + WARPS - 1) / WARPS, c->n_sm * 8)));
+    c->grid_vec = std::min(MAX_PARTIALS, std::max(1, std::min((int)((nd + VEC_THREADS - 1) / VEC_THREADS), c->n_sm * 8)));
+    if (any_neo) { delete c; return set_err("neo-Hookean element: device kernel not built into this library yet"); }
+    int rc = mf_setup(c->mf, mesh_of(c), conn, N, E, c->n_sm, c->ndof);
+    if (rc) { delete c; return set_err("matrix-free set-up failed"); }
+    *out = c;
+    return 0;
+}
+
+int en234gpu_destroy(en234gpu_handle c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& g : c->graph) if (g) cudaGraphExecDestroy(g);
+    comm_destroy(c->comm);
+    mf_release(c->mf);
+    if (c->hS) cudaFreeHost(c->hS);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return 0;
+}
+
+int en234gpu_set_stream(en234gpu_handle c, void* s) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    for (auto& g : c->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static int read_scalars(en234gpu_ctx* c) {
+    CK(cudaMemcpyAsync(c->hS, c->S.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int phase_begin(en234gpu_ctx* c) { CK(cudaSetDevice(c->device)); CK(cudaEventRecord(c->ev0, c->stream)); return 0; }
+static int phase_end(en234gpu_ctx* c, double* ms) {
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    *ms = t;
+    return 0;
+}
+
+// sum a per-node-owned norm^2 partial array into S->norm2, all-reduce across ranks, return sqrt
+static int finish_norm(en234gpu_ctx* c, const double* part, int n, double* out) {
+    k_reduce_to<<<1, VEC_THREADS, 0, c->stream>>>(part, n, &c->S.p->norm2);
+    c->st.kernel_launches++;
+    if (c->comm.active && comm_allreduce_sum(c->comm, &c->S.p->norm2, 1, c->stream)) return set_err(comm_error());
+    if (read_scalars(c)) return 1;
+    *out = std::sqrt(c->hS->norm2);
+    return 0;
+}
+
+int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail) {
+    if (phase_begin(c)) return 1;
+    CK(cudaMemsetAsync(&c->S.p->nanflag, 0, sizeof(int), c->stream));
+    AsmArgs A;
+    A.M = mesh_of(c);
+    A.ut = c->ut.p; A.du = c->du.p;
+    A.felem = c->have_felem ? c->felem.p : nullptr;
+    A.val = c->val.p; A.rhs = c->rhs.p; A.rforce = c->rforce.p;
+    A.partials = c->part.p; A.S = c->S.p;
+    A.assemble_matrix = c->mode == EN234_SOLVE_PCG_BSR ? 1 : 0;
+    k_assemble_rows<<<c->grid_rows, THREADS, c->asm_smem, c->stream>>>(A);
+    c->st.kernel_launches++;
+    CK(cudaGetLastError());
+    c->matrix_valid = c->mode == EN234_SOLVE_PCG_BSR;
+    c->rhs_valid = true;
+    const double* part = c->part.p;
+    int npart = c->grid_rows;
+    if (c->comm.active) {
+        // interface nodes hold partial sums: halo-sum rhs (and rforce = -rhs), then an owned-only norm
+        if (comm_halo_sum(c->comm, c->rhs.p, c->stream)) return set_err(comm_error());
+        k_negate_norm<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(c->ndof, c->rhs.p, c->rforce.p, c->owned.p, c->part2.p);
+        c->st.kernel_launches += c->comm.launches_per_halo + 1;
+        part = c->part2.p; npart = c->grid_vec;
+    }
+    if (finish_norm(c, part, npart, nodal_force_norm)) return 1;
+    int bad = c->hS->nanflag;
+    if (c->comm.active && comm_host_max(c->comm, &bad)) return set_err(comm_error());
+    *fail = bad ? 1 : 0;
+    return phase_end(c, &c->st.assemble_ms);
+}
+
+static int upload_fixed(en234gpu_ctx* c, int n_fixed, const int* fixed_dof, const double* fixed_value) {
+    // a DOF listed twice keeps its last value (the reference applies fixdof in list order)
+    std::vector<int> last(n_fixed);
+    std::map<int, int> seen;
+    std::vector<int> d;
+    std::vector<double> v;
+    for (int i = 0; i < n_fixed; ++i) {
+        if (fixed_dof[i] < 0 || fixed_dof[i] >= c->ndof) return set_err("prescribed DOF index out of range");
+        auto it = seen.find(fixed_dof[i]);
+        if (it == seen.end()) { seen[fixed_dof[i]] = (int)d.size(); d.push_back(fixed_dof[i]); v.push_back(fixed_value[i]); }
+        else v[it->second] = fixed_value[i];
+    }
+    c->n_fixed = (int)d.size();
+    if (c->fixdof.n < d.size()) { CK(c->fixdof.alloc(d.size())); CK(c->fixval.alloc(d.size())); }
+    if (!d.empty()) {
+        CK(cudaMemcpyAsync(c->fixdof.p, d.data(), d.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->fixval.p, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+static int apply_bc_common(en234gpu_ctx* c, int values_are_corrections, double* unbalanced) {
+    if (!c->rhs_valid) return set_err("apply_boundaryconditions called before assemble");
+    CK(cudaMemsetAsync(c->cflag.p, 0, (size_t)c->ndof, c->stream));
+    if (c->n_fixed > 0) {
+        k_set_corrections<<<(c->n_fixed + 255) / 256, 256, 0, c->stream>>>(c->n_fixed, c->fixdof.p, c->fixval.p, c->ut.p,
+                                                                         c->du.p, c->cflag.p, c->cval.p,
+                                                                         values_are_corrections);
+        c->st.kernel_launches++;
+    }
+    BcArgs B;
+    B.N = c->N; B.browptr = c->browptr.p; B.bcol = c->bcol.p; B.val = c->val.p; B.rhs = c->rhs.p;
+    B.fext = c->have_fext ? c->fext.p : nullptr;
+    B.cflag = c->cflag.p; B.cval = c->cval.p; B.minv = c->minv.p; B.partials = c->part.p;
+    const double* part = c->part.p;
+    int npart = c->grid_rows;
+    if (c->mode == EN234_SOLVE_PCG_MATRIXFREE) {
+        // matrix-free: K[:,C] c is one application of the unmasked operator to the vector of prescribed corrections;
+        // the Jacobi diagonal is integrated element by element
+        const uint8_t* owned = c->have_owned ? c->owned.p : nullptr;
+        const int nb = (c->ndof + 255) / 256;
+        k_mask_values<<<nb, 256, 0, c->stream>>>(c->ndof, c->cflag.p, c->cval.p, c->tmpvec.p);
+        mf_apply(c->mf, mesh_of(c), c->ndof, nullptr, nullptr, c->tmpvec.p, c->tmpvec2.p, c->part3.p, nullptr, c->stream,
+                 &c->st.kernel_launches);
+        mf_diag(c->mf, mesh_of(c), c->ndof, c->tmpvec.p, c->Ap.p, c->stream, &c->st.kernel_launches);
+        if (c->comm.active) {
+            if (comm_halo_sum(c->comm, c->tmpvec2.p, c->stream)) return set_err(comm_error());
+            if (comm_halo_sum(c->comm, c->Ap.p, c->stream)) return set_err(comm_error());
+        }
+        k_fix_diag<<<nb, 256, 0, c->stream>>>(c->ndof, c->cflag.p, nullptr, c->Ap.p);
+        k_bc_finalize<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(c->ndof, c->rhs.p, B.fext, c->cflag.p, c->cval.p,
+                                                                   c->tmpvec2.p, c->Ap.p, c->minv.p, owned, c->part2.p);
+        c->st.kernel_launches += 3;
+        part = c->part2.p; npart = c->grid_vec;
+    } else if (c->comm.active) {
+        // the Jacobi diagonal and the rhs corrections of interface rows are partial sums on each rank:
+        // apply to local rows, then halo-sum what is additive (see k_apply_bc_partitioned)
+        if (bc_partitioned(c->comm, B, c->grid_rows, c->grid_vec, c->ndof, c->owned.p, c->tmpvec.p, c->tmpvec2.p, c->part2.p,
+                           c->stream, &c->st.kernel_launches)) return set_err(comm_error());
+        part = c->part2.p; npart = c->grid_vec;
+    } else {
+        k_apply_bc<<<c->grid_rows, THREADS, 0, c->stream>>>(B);
+        c->st.kernel_launches++;
+    }
+    CK(cudaGetLastError());
+    return finish_norm(c, part, npart, unbalanced);
+}
+
+int en234gpu_apply_boundaryconditions_dev(en234gpu_handle c, double* unbalanced_force_norm) {
+    if (phase_begin(c)) return 1;
+    if (apply_bc_common(c, 0, unbalanced_force_norm)) return 1;
+    return phase_end(c, &c->st.bc_ms);
+}
+
+// ---- PCG ------------------------------------------------------------------------------------------------
+static CgVecArgs vec_args(en234gpu_ctx* c, int method, int parity) {
+    CgVecArgs V{};
+    V.n = c->ndof; V.rhs = c->rhs.p; V.minv = c->minv.p;
+    V.owned = c->have_owned ? c->owned.p : nullptr;
+    V.sol = c->sol.p; V.r = c->r.p; V.p = c->p.p; V.Ap = c->Ap.p;
+    V.part_pAp = c->part.p;
+    V.n_part_pAp = c->comm.active ? 1 : (method == EN234_SOLVE_PCG_MATRIXFREE ? c->mf.n_partials : c->grid_rows);
+    V.part_a = c->part2.p; V.part_b = c->part3.p;
+    V.n_part = c->comm.active ? 1 : c->grid_vec;
+    V.S = c->S.p;
+    V.parity = parity;
+    return V;
+}
+
+static int launch_operator(en234gpu_ctx* c, int method, const double* x, double* y, int check_stop) {
+    if (method == EN234_SOLVE_PCG_MATRIXFREE) {
+        mf_apply(c->mf, mesh_of(c), c->ndof, c->cflag.p, c->have_owned ? c->owned.p : nullptr, x, y, c->part.p,
+                 check_stop ? c->S.p : nullptr, c->stream, &c->st.kernel_launches);
+    } else {
+        SpmvArgs A;
+        A.N = c->N; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
+        A.partials = c->part.p; A.S = c->S.p; A.check_stop = check_stop;
+        k_spmv<<<c->grid_rows, THREADS, 0, c->stream>>>(A);
+        c->st.kernel_launches++;
+    }
+    return 0;
+}
+
+// one PCG iteration on the stream (captured into the graph)
+static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
+    launch_operator(c, method, c->p.p, c->Ap.p, 1);
+    if (c->comm.active) {
+        // p.Ap: sum of local partial products over ALL local rows equals the global product (interface rows hold
+        // partial sums and p agrees on both sides), so the all-reduce does not wait for the halo exchange
+        const int np = method == EN234_SOLVE_PCG_MATRIXFREE ? c->mf.n_partials : c->grid_rows;
+        k_reduce_to<<<1, VEC_THREADS, 0, c->stream>>>(c->part.p, np, c->part.p);
+        if (comm_allreduce_sum(c->comm, c->part.p, 1, c->stream)) return 1;
+        if (comm_halo_sum(c->comm, c->Ap.p, c->stream)) return 1;
+        c->st.kernel_launches += 1 + c->comm.launches_per_halo;
+    }
+    CgVecArgs V = vec_args(c, method, parity);
+    k_cg_update<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+    c->st.kernel_launches++;
+    if (c->comm.active) {
+        k_reduce2_to<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, c->grid_vec, c->part2.p, c->part3.p);
+        // pack {rr, rz} in one 2-double message: part2[0], part2[1]
+        k_pack2<<<1, 1, 0, c->stream>>>(c->part2.p, c->part3.p);
+        if (comm_allreduce_sum(c->comm, c->part2.p, 2, c->stream)) return 1;
+        k_unpack2<<<1, 1, 0, c->stream>>>(c->part2.p, c->part3.p);
+        c->st.kernel_launches += 3;
+    }
+    k_cg_pupdate<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+    c->st.kernel_launches++;
+    return 0;
+}
+
+static int build_graph(en234gpu_ctx* c, int method) {
+    cudaGraph_t g = nullptr;
+    const long long before = c->st.kernel_launches;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    for (int it = 1; it <= CG_CHUNK && !rc; ++it) rc = enqueue_iteration(c, method, it & 1);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    c->st.kernel_launches = before;          // capture does not launch
+    if (rc) return set_err(std::string("graph capture: ") + comm_error());
+    if (e != cudaSuccess) return set_err(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    CK(cudaGraphInstantiate(&c->graph[method], g, 0));
+    CK(cudaGraphDestroy(g));
+    return 0;
+}
+
+int en234gpu_solve_dev(en234gpu_handle c, int method, double cg_tolerance, int max_cg_iterations,
+                       double* correction_norm, int* cg_iterations, int* fail) {
+    if (method != EN234_SOLVE_PCG_BSR && method != EN234_SOLVE_PCG_MATRIXFREE) return set_err("unknown solve method");
+    if (method == EN234_SOLVE_PCG_BSR && !c->matrix_valid) return set_err("solve called before assemble");
+    if (method != c->mode) return set_err("solve method differs from the operator mode (en234gpu_set_operator_mode)");
+    if (phase_begin(c)) return 1;
+    if (!c->graph[method] && build_graph(c, method)) return 1;
+    // tolerance / iteration cap are run-time values in device memory (compile-time in modules/Stiffness.f90:35-37)
+    CgScalars init{};
+    init.tol = cg_tolerance; init.maxit = max_cg_iterations;
+    CK(cudaMemcpyAsync(c->S.p, &init, sizeof(CgScalars), cudaMemcpyHostToDevice, c->stream));
+    CgVecArgs V = vec_args(c, method, 1);
+    V.n_part = c->grid_vec;
+    k_cg_init<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+    c->st.kernel_launches++;
+    if (c->comm.active) {
+        k_reduce2_to<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, c->grid_vec, c->part2.p, c->part3.p);
+        k_pack2<<<1, 1, 0, c->stream>>>(c->part2.p, c->part3.p);
+        if (comm_allreduce_sum(c->comm, c->part2.p, 2, c->stream)) return set_err(comm_error());
+        k_unpack2<<<1, 1, 0, c->stream>>>(c->part2.p, c->part3.p);
+        V.n_part = 1;
+        c->st.kernel_launches += 3;
+    }
+    k_cg_init_finish<<<1, VEC_THREADS, 0, c->stream>>>(V);
+    c->st.kernel_launches++;
+    CK(cudaGetLastError());
+    const long long per_graph = (long long)CG_CHUNK * (c->comm.active ? (3 + 1 + c->comm.launches_per_halo + 3) : 3) +
+                                (method == EN234_SOLVE_PCG_MATRIXFREE ? (long long)CG_CHUNK * (c->mf.launches_per_apply - 1) : 0);
+    // chunks of CG_CHUNK iterations; the stop flag is read back after each chunk (iterations after convergence
+    // inside a chunk return immediately)
+    for (;;) {
+        if (read_scalars(c)) return 1;
+        if (c->hS->stop || c->hS->iter >= max_cg_iterations) break;
+        CK(cudaGraphLaunch(c->graph[method], c->stream));
+        c->st.kernel_launches += per_graph;
+    }
+    *fail = c->hS->fail ? 1 : 0;
+    *cg_iterations = c->hS->iter;
+    c->st.last_cg_iterations = c->hS->iter;
+    c->st.last_cg_err = c->hS->err;
+    if (!*fail) {
+        k_add_solution<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(c->ndof, c->sol.p, c->du.p,
+                                                                  c->have_owned ? c->owned.p : nullptr, c->part2.p);
+        c->st.kernel_launches++;
+        if (finish_norm(c, c->part2.p, c->grid_vec, correction_norm)) return 1;
+    } else *correction_norm = 0.0;
+    if (phase_end(c, &c->st.solve_ms)) return 1;
+    c->st.spmv_ms_avg = c->hS->iter > 0 ? c->st.solve_ms / c->hS->iter : 0.0;
+    return 0;
+}
+
+// ---- state movement -------------------------------------------------------------------------------------
+int en234gpu_upload_state(en234gpu_handle c, const double* dof_total, const double* dof_increment,
+                          const double* f_element_ext, const double* f_ext, int n_fixed, const int* fixed_dof,
+                          const double* fixed_value) {
+    CK(cudaSetDevice(c->device));
+    const size_t b = (size_t)c->ndof * sizeof(double);
+    if (dof_total) CK(cudaMemcpyAsync(c->ut.p, dof_total, b, cudaMemcpyHostToDevice, c->stream));
+    if (dof_increment) CK(cudaMemcpyAsync(c->du.p, dof_increment, b, cudaMemcpyHostToDevice, c->stream));
+    c->have_felem = f_element_ext != nullptr;
+    c->have_fext = f_ext != nullptr;
+    if (f_element_ext) CK(cudaMemcpyAsync(c->felem.p, f_element_ext, b, cudaMemcpyHostToDevice, c->stream));
+    if (f_ext) CK(cudaMemcpyAsync(c->fext.p, f_ext, b, cudaMemcpyHostToDevice, c->stream));
+    if (n_fixed >= 0) return upload_fixed(c, n_fixed, fixed_dof, fixed_value);
+    return 0;
+}
+
+int en234gpu_download_state(en234gpu_handle c, double* dof_increment, double* rforce) {
+    CK(cudaSetDevice(c->device));
+    const size_t b = (size_t)c->ndof * sizeof(double);
+    if (dof_increment) CK(cudaMemcpyAsync(dof_increment, c->du.p, b, cudaMemcpyDeviceToHost, c->stream));
+    if (rforce) CK(cudaMemcpyAsync(rforce, c->rforce.p, b, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int en234gpu_zero_increment_dev(en234gpu_handle c) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->du.p, 0, (size_t)c->ndof * sizeof(double), c->stream));
+    return 0;
+}
+
+// ---- host-buffer entry points (what a Fortran driver binds) -------------------------------------------------
+int en234gpu_assemble(en234gpu_handle c, const double* dof_total, const double* dof_increment,
+                      const double* f_element_ext, double* rforce, double* nodal_force_norm, int* fail) {
+    if (!dof_total || !dof_increment) return set_err("en234gpu_assemble: null DOF arrays");
+    CK(cudaSetDevice(c->device));
+    const size_t b = (size_t)c->ndof * sizeof(double);
+    CK(cudaMemcpyAsync(c->ut.p, dof_total, b, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->du.p, dof_increment, b, cudaMemcpyHostToDevice, c->stream));
+    c->have_felem = f_element_ext != nullptr;
+    if (f_element_ext) CK(cudaMemcpyAsync(c->felem.p, f_element_ext, b, cudaMemcpyHostToDevice, c->stream));
+    if (en234gpu_assemble_dev(c, nodal_force_norm, fail)) return 1;
+    if (rforce) {
+        CK(cudaMemcpyAsync(rforce, c->rforce.p, b, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int en234gpu_apply_boundaryconditions(en234gpu_handle c, const double* f_ext, int n_fixed, const int* fixed_dof,
+                                      const double* fixed_correction, double* unbalanced_force_norm) {
+    CK(cudaSetDevice(c->device));
+    c->have_fext = f_ext != nullptr;
+    if (f_ext) CK(cudaMemcpyAsync(c->fext.p, f_ext, (size_t)c->ndof * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (upload_fixed(c, n_fixed, fixed_dof, fixed_correction)) return 1;
+    if (phase_begin(c)) return 1;
+    if (apply_bc_common(c, 1, unbalanced_force_norm)) return 1;
+    return phase_end(c, &c->st.bc_ms);
+}
+
+int en234gpu_solve(en234gpu_handle c, int method, double cg_tolerance, int max_cg_iterations, double* dof_increment,
+                   double* correction_norm, int* cg_iterations, int* fail) {
+    CK(cudaSetDevice(c->device));
+    const size_t b = (size_t)c->ndof * sizeof(double);
+    CK(cudaMemcpyAsync(c->du.p, dof_increment, b, cudaMemcpyHostToDevice, c->stream));
+    if (en234gpu_solve_dev(c, method, cg_tolerance, max_cg_iterations, correction_norm, cg_iterations, fail)) return 1;
+    CK(cudaMemcpyAsync(dof_increment, c->du.p, b, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- element plugin surface / inspection --------------------------------------------------------------------
+int en234gpu_element_batch(en234gpu_handle c, int n, const int* element_numbers, const double* dof_total,
+                           const double* dof_increment, double* element_stiffness, double* element_residual, int* fail) {
+    CK(cudaSetDevice(c->device));
+    std::vector<int> el(n);
+    for (int i = 0; i < n; ++i) {
+        el[i] = element_numbers[i] - 1;
+        if (el[i] < 0 || el[i] >= c->E) return set_err("element number out of range");
+    }
+    DevBuf<int> d_el;
+    DevBuf<double> d_K, d_R;
+    CK(d_el.alloc(n)); CK(d_K.alloc((size_t)n * 576)); CK(d_R.alloc((size_t)n * 24));
+    const size_t b = (size_t)c->ndof * sizeof(double);
+    CK(cudaMemcpyAsync(d_el.p, el.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->tmpvec.p, dof_total, b, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->tmpvec2.p, dof_increment, b, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(&c->S.p->nanflag, 0, sizeof(int), c->stream));
+    k_element_batch<<<n, 64, 0, c->stream>>>(mesh_of(c), n, d_el.p, c->tmpvec.p, c->tmpvec2.p, d_K.p, d_R.p, c->S.p);
+    c->st.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(element_stiffness, d_K.p, (size_t)n * 576 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(element_residual, d_R.p, (size_t)n * 24 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (read_scalars(c)) return 1;
+    if (fail) *fail = c->hS->nanflag ? 1 : 0;
+    return 0;
+}
+
+int en234gpu_get_svars(en234gpu_handle c, const double* dof_total, const double* dof_increment, double* svars) {
+    CK(cudaSetDevice(c->device));
+    DevBuf<double> d_sv;
+    CK(d_sv.alloc((size_t)c->E * 48));
+    const size_t b = (size_t)c->ndof * sizeof(double);
+    CK(cudaMemcpyAsync(c->tmpvec.p, dof_total, b, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->tmpvec2.p, dof_increment, b, cudaMemcpyHostToDevice, c->stream));
+    const long long nt = (long long)c->E * 8;
+    k_svars<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(mesh_of(c), c->tmpvec.p, c->tmpvec2.p, d_sv.p);
+    c->st.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(svars, d_sv.p, (size_t)c->E * 48 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+long long en234gpu_nnz_blocks(en234gpu_handle c) { return c->nnzb; }
+
+int en234gpu_get_csr(en234gpu_handle c, long long* rowptr, int* col, double* val) {
+    CK(cudaSetDevice(c->device));
+    // block row i stores [r][block][c]: scalar row 3i+r starts at 9*browptr[i] + r*3*nb
+    for (int i = 0; i < c->N; ++i) {
+        const long long rb = c->h_browptr[i], nb = c->h_browptr[i + 1] - rb;
+        for (int r = 0; r < 3; ++r) {
+            const long long start = 9 * rb + r * 3 * nb;
+            if (rowptr) rowptr[3 * (long long)i + r] = start;
+            if (col)
+                for (long long q = 0; q < 3 * nb; ++q) col[start + q] = 3 * c->h_bcol[rb + q / 3] + (int)(q % 3);
+        }
+    }
+    if (rowptr) rowptr[3 * (long long)c->N] = 9 * c->nnzb;
+    if (val) {
+        CK(cudaMemcpyAsync(val, c->val.p, 9 * (size_t)c->nnzb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int en234gpu_get_rhs(en234gpu_handle c, double* rhs, double* diag) {
+    CK(cudaSetDevice(c->device));
+    const size_t b = (size_t)c->ndof * sizeof(double);
+    if (rhs) CK(cudaMemcpyAsync(rhs, c->rhs.p, b, cudaMemcpyDeviceToHost, c->stream));
+    if (diag) {
+        CK(cudaMemcpyAsync(diag, c->minv.p, b, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int d = 0; d < c->ndof; ++d) diag[d] = 1.0 / diag[d];
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int en234gpu_apply_operator(en234gpu_handle c, int method, const double* x, double* y) {
+    CK(cudaSetDevice(c->device));
+    const size_t b = (size_t)c->ndof * sizeof(double);
+    CK(cudaMemcpyAsync(c->tmpvec.p, x, b, cudaMemcpyHostToDevice, c->stream));
+    if (launch_operator(c, method, c->tmpvec.p, c->tmpvec2.p, 0)) return 1;
+    CK(cudaGetLastError());
+    if (c->comm.active && comm_halo_sum(c->comm, c->tmpvec2.p, c->stream)) return set_err(comm_error());
+    CK(cudaMemcpyAsync(y, c->tmpvec2.p, b, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- multi-GPU ----------------------------------------------------------------------------------------------
+int en234gpu_get_unique_id(char* id128) { return comm_unique_id(id128) ? set_err(comm_error()) : 0; }
+
+int en234gpu_comm_init(en234gpu_handle c, int n_ranks, int rank, const char* id128) {
+    CK(cudaSetDevice(c->device));
+    if (comm_init(c->comm, n_ranks, rank, id128, c->stream)) return set_err(comm_error());
+    for (auto& g : c->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    return 0;
+}
+
+int en234gpu_set_partition(en234gpu_handle c, int n_neighbours, const int* neighbour_rank, const int* shared_ptr,
+                           const int* shared_nodes, const unsigned char* owned) {
+    CK(cudaSetDevice(c->device));
+    CK(c->owned.alloc(c->N));
+    CK(cudaMemcpy(c->owned.p, owned, c->N, cudaMemcpyHostToDevice));
+    c->have_owned = true;
+    if (comm_set_halo(c->comm, n_neighbours, neighbour_rank, shared_ptr, shared_nodes)) return set_err(comm_error());
+    return 0;
+}
+
+int en234gpu_set_operator_mode(en234gpu_handle c, int method) {
+    if (method != EN234_SOLVE_PCG_BSR && method != EN234_SOLVE_PCG_MATRIXFREE) return set_err("unknown operator mode");
+    c->mode = method;
+    c->matrix_valid = false;
+    c->rhs_valid = false;
+    return 0;
+}
+
+int en234gpu_get_stats(en234gpu_handle c, struct en234gpu_stats* s) { *s = c->st; return 0; }
+
+}  // extern "C"

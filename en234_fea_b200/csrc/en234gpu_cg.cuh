@@ -1,0 +1,189 @@
+// Jacobi-preconditioned conjugate gradient kernels: the recurrences of cg_iteration_loop
+// (src/solver_conjugate_gradient.f90:776-912) with the three global dot products fused into the kernels that
+// produce their operands.  One PCG iteration = k_spmv -> k_update -> k_pupdate; all scalars live in device
+// memory (CgScalars), per-CTA partial sums are reduced redundantly by every consumer CTA in a fixed order, so the
+// iteration has no host round trip, no atomics and is bitwise run-to-run deterministic.
+#pragma once
+#include "en234gpu_kernels.cuh"
+
+namespace en234k {
+
+struct SpmvArgs {
+    int N;
+    const int* browptr;
+    const int* bcol;
+    const double* val;
+    const double* x;        // p
+    double* y;              // A p
+    double* partials;       // per-CTA sum of p.(A p) over the CTA's rows (all local rows, see DESIGN.md multi-GPU)
+    const CgScalars* S;
+    int check_stop;
+};
+
+// y = A x for the 3x3-block CSR matrix stored per block row as [r][block][c]; one warp per block row.
+// Lane q < 3*nb owns scalar column q of the block row: it gathers x_q once and reuses it for the three scalar
+// rows, whose values are read as three fully coalesced streams (streaming loads: the matrix is read once per
+// iteration and must not evict the vectors from L2).
+__global__ void __launch_bounds__(THREADS) k_spmv(SpmvArgs A) {
+    __shared__ double red[WARPS + 1];
+    if (A.check_stop && A.S->stop) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double dot = 0.0;
+    for (int i = blockIdx.x * WARPS + warp; i < A.N; i += gridDim.x * WARPS) {
+        const int rb = A.browptr[i], nb = A.browptr[i + 1] - rb, L = 3 * nb;
+        const double* v = A.val + 9 * (size_t)rb;
+        double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+        if (L <= 96) {
+            // issue every load of the row before the first use (3 x-gathers + 9 streaming value loads per lane)
+            double xq[3], a0[3], a1[3], a2[3];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int q = lane + 32 * t;
+                if (q < L) {
+                    const int j = 3 * __ldg(A.bcol + rb + q / 3) + q % 3;
+                    xq[t] = __ldg(A.x + j);
+                    a0[t] = __ldcs(v + q);
+                    a1[t] = __ldcs(v + L + q);
+                    a2[t] = __ldcs(v + 2 * L + q);
+                } else { xq[t] = 0.0; a0[t] = 0.0; a1[t] = 0.0; a2[t] = 0.0; }
+            }
+#pragma unroll
+            for (int t = 0; t < 3; ++t) { y0 += a0[t] * xq[t]; y1 += a1[t] * xq[t]; y2 += a2[t] * xq[t]; }
+        } else {
+            for (int q = lane; q < L; q += 32) {
+                const int j = 3 * __ldg(A.bcol + rb + q / 3) + q % 3;
+                const double xv = __ldg(A.x + j);
+                y0 += __ldcs(v + q) * xv;
+                y1 += __ldcs(v + L + q) * xv;
+                y2 += __ldcs(v + 2 * L + q) * xv;
+            }
+        }
+        y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2);
+        if (lane < 3) {
+            const double yv = lane == 0 ? y0 : (lane == 1 ? y1 : y2);
+            A.y[3 * (size_t)i + lane] = yv;
+            dot += yv * A.x[3 * (size_t)i + lane];
+        }
+    }
+    const double t = block_sum<THREADS>(dot, red);
+    if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
+}
+
+struct CgVecArgs {
+    int n;                         // number of DOFs
+    const double* rhs;
+    const double* minv;
+    const uint8_t* owned;          // per NODE ownership mask for dot products (null = all owned)
+    double *sol, *r, *p, *Ap;
+    const double* part_pAp; int n_part_pAp;     // partials written by the operator kernel
+    double* part_a; double* part_b; int n_part; // partials written by this family (grid size of the vector kernels)
+    CgScalars* S;
+    int parity;                    // iteration parity (selects S->rz slot)
+    double pAp_allreduced;         // unused on one GPU
+};
+
+__device__ __forceinline__ bool dof_owned(const uint8_t* owned, int d) { return owned == nullptr || owned[d / 3] != 0; }
+
+// sol = 0, r = b, p = z = M^-1 r ; partials of b.b and r.z      (:802-847, iteration 1's p = z at :869-870)
+__global__ void __launch_bounds__(VEC_THREADS) k_cg_init(CgVecArgs A) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    double bb = 0.0, rz = 0.0;
+    for (int d = blockIdx.x * VEC_THREADS + threadIdx.x; d < A.n; d += gridDim.x * VEC_THREADS) {
+        const double b = A.rhs[d];
+        const double z = b * A.minv[d];
+        A.sol[d] = 0.0;
+        A.r[d] = b;
+        A.p[d] = z;
+        if (dof_owned(A.owned, d)) { bb += b * b; rz += z * b; }
+    }
+    const double s0 = block_sum<VEC_THREADS>(bb, red);
+    const double s1 = block_sum<VEC_THREADS>(rz, red);
+    if (threadIdx.x == 0) { A.part_a[blockIdx.x] = s0; A.part_b[blockIdx.x] = s1; }
+}
+// single CTA: bnrm, rz[1], zero-rhs exit (:805-814)
+__global__ void __launch_bounds__(VEC_THREADS) k_cg_init_finish(CgVecArgs A) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    const double bb = reduce_partials<VEC_THREADS>(A.part_a, A.n_part, red);
+    const double rz = reduce_partials<VEC_THREADS>(A.part_b, A.n_part, red);
+    if (threadIdx.x == 0) {
+        CgScalars* S = A.S;
+        S->bnrm = bb;
+        S->rz[1] = rz;
+        S->rz[0] = 0.0;
+        S->err = 1.0;
+        S->iter = 0;
+        S->fail = 0;
+        S->stop = (bb == 0.0) ? 1 : 0;
+    }
+}
+
+// ak = (z.r)/(p.Ap); sol += ak p; r -= ak Ap; partials of r.r and r.(M^-1 r)            (:885-900)
+__global__ void __launch_bounds__(VEC_THREADS) k_cg_update(CgVecArgs A) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    if (A.S->stop) return;
+    const double pAp = reduce_partials<VEC_THREADS>(A.part_pAp, A.n_part_pAp, red);
+    const double ak = A.S->rz[A.parity] / pAp;
+    double rr = 0.0, rz = 0.0;
+    for (int d = blockIdx.x * VEC_THREADS + threadIdx.x; d < A.n; d += gridDim.x * VEC_THREADS) {
+        const double pv = A.p[d];
+        A.sol[d] = A.sol[d] + ak * pv;
+        const double rv = A.r[d] - ak * A.Ap[d];
+        A.r[d] = rv;
+        if (dof_owned(A.owned, d)) { rr += rv * rv; rz += (rv * A.minv[d]) * rv; }
+    }
+    const double s0 = block_sum<VEC_THREADS>(rr, red);
+    const double s1 = block_sum<VEC_THREADS>(rz, red);
+    if (threadIdx.x == 0) { A.part_a[blockIdx.x] = s0; A.part_b[blockIdx.x] = s1; }
+}
+
+// err = r.r/b.b; stop if !(err > tol) (:849, :900) or after maxit iterations (:854-860);
+// else bk = (z.r)_new/(z.r)_old, p = z + bk p (:867-874)
+__global__ void __launch_bounds__(VEC_THREADS) k_cg_pupdate(CgVecArgs A) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    CgScalars* S = A.S;
+    if (S->stop) return;
+    const double rr = reduce_partials<VEC_THREADS>(A.part_a, A.n_part, red);
+    const double rz = reduce_partials<VEC_THREADS>(A.part_b, A.n_part, red);
+    const double err = rr / S->bnrm;
+    const bool more = err > S->tol;
+    const int iter = S->iter + 1;
+    const bool exhausted = more && iter >= S->maxit;
+    const double bk = rz / S->rz[A.parity];
+    if (more && !exhausted) {
+        for (int d = blockIdx.x * VEC_THREADS + threadIdx.x; d < A.n; d += gridDim.x * VEC_THREADS)
+            A.p[d] = bk * A.p[d] + A.r[d] * A.minv[d];
+    }
+    // bookkeeping by the LAST CTA to finish reading S (all CTAs read S->iter/stop above): use a grid-wide ticket
+    __shared__ unsigned ticket;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        ticket = atomicAdd((unsigned*)&S->pad0, 1u);
+    }
+    __syncthreads();
+    if (ticket == gridDim.x - 1 && threadIdx.x == 0) {
+        S->pad0 = 0;
+        S->rz[A.parity ^ 1] = rz;
+        S->err = err;
+        S->iter = iter;
+        if (!more) S->stop = 1;
+        if (exhausted) { S->stop = 1; S->fail = 1; }
+        __threadfence();
+    }
+}
+
+// dof_increment += sol ; partial of sol.sol        (solve_conjugategradient :760-771)
+__global__ void __launch_bounds__(VEC_THREADS) k_add_solution(int n, const double* sol, double* du, const uint8_t* owned,
+                                                               double* partials) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    double ss = 0.0;
+    for (int d = blockIdx.x * VEC_THREADS + threadIdx.x; d < n; d += gridDim.x * VEC_THREADS) {
+        const double s = sol[d];
+        du[d] = du[d] + s;
+        if (dof_owned(owned, d)) ss += s * s;
+    }
+    const double t = block_sum<VEC_THREADS>(ss, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+}  // namespace en234k

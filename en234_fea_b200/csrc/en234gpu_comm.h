@@ -1,0 +1,225 @@
+// Multi-GPU plumbing for element-partitioned runs: one process per GPU, NCCL over NVLink/NVSwitch.
+// The reference is strictly serial (no communication backend); everything here is new.
+//  * halo sum: interface (shared) nodes hold partial sums after a local operator application; each rank sends its
+//    partials to every neighbour and adds what it receives (ncclSend/ncclRecv grouped; 1-D slabs => <= 2 neighbours)
+//  * scalar all-reduces for the PCG dot products and norms (device-resident scalars, graph-capturable)
+// NCCL is loaded with dlopen at communicator creation so that the library still loads on a host without it.
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <string>
+#include <vector>
+
+#include "en234gpu_asm.cuh"
+
+namespace en234k {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+inline std::string& comm_err_ref() { static thread_local std::string e; return e; }
+inline const char* comm_error() { return comm_err_ref().c_str(); }
+
+inline NcclApi* nccl_api() {
+    static NcclApi api;
+    if (api.lib) return &api;
+    // torch bundles its own libnccl.so.2; if it is already loaded RTLD_NOLOAD finds it, otherwise use the system one
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { comm_err_ref() = std::string("cannot load libnccl.so.2: ") + dlerror(); return nullptr; }
+#define LD(field, name)                                                                   \
+    api.field = (decltype(api.field))dlsym(h, name);                                      \
+    if (!api.field) { comm_err_ref() = std::string("missing NCCL symbol ") + name; return nullptr; }
+    LD(GetUniqueId, "ncclGetUniqueId") LD(CommInitRank, "ncclCommInitRank") LD(CommDestroy, "ncclCommDestroy")
+    LD(AllReduce, "ncclAllReduce") LD(Send, "ncclSend") LD(Recv, "ncclRecv") LD(GroupStart, "ncclGroupStart")
+    LD(GroupEnd, "ncclGroupEnd") LD(GetErrorString, "ncclGetErrorString")
+#undef LD
+    api.lib = h;
+    return &api;
+}
+
+struct Comm {
+    bool active = false;             // communicator created (n_ranks > 1)
+    int n_ranks = 1, rank = 0;
+    ncclComm_t nccl = nullptr;
+    int n_nbr = 0;
+    std::vector<int> nbr_rank, shared_ptr;    // host copies
+    int* d_shared = nullptr;                  // device: local node index per shared entry (all neighbours concatenated)
+    double *sendbuf = nullptr, *recvbuf = nullptr;
+    int n_shared = 0;
+    int launches_per_halo = 0;                // kernels of one halo sum (pack + one unpack per neighbour)
+};
+
+#define NCK(call)                                                                                    \
+    do {                                                                                             \
+        ncclResult_t r_ = (call);                                                                    \
+        if (r_ != ncclSuccess) { comm_err_ref() = std::string(#call) + ": " + api->GetErrorString(r_); return 1; } \
+    } while (0)
+
+inline int comm_unique_id(char* id128) {
+    NcclApi* api = nccl_api();
+    if (!api) return 1;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCK(api->GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+inline int comm_init(Comm& c, int n_ranks, int rank, const char* id128, cudaStream_t) {
+    c.n_ranks = n_ranks; c.rank = rank;
+    if (n_ranks <= 1) { c.active = false; return 0; }
+    NcclApi* api = nccl_api();
+    if (!api) return 1;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NCK(api->CommInitRank(&c.nccl, n_ranks, id, rank));
+    c.active = true;
+    return 0;
+}
+
+inline void comm_destroy(Comm& c) {
+    if (c.nccl) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(c.nccl); c.nccl = nullptr; }
+    if (c.d_shared) cudaFree(c.d_shared);
+    if (c.sendbuf) cudaFree(c.sendbuf);
+    if (c.recvbuf) cudaFree(c.recvbuf);
+    c.d_shared = nullptr; c.sendbuf = c.recvbuf = nullptr; c.active = false;
+}
+
+inline int comm_set_halo(Comm& c, int n_nbr, const int* nbr_rank, const int* shared_ptr, const int* shared_nodes) {
+    c.n_nbr = n_nbr;
+    c.nbr_rank.assign(nbr_rank, nbr_rank + n_nbr);
+    c.shared_ptr.assign(shared_ptr, shared_ptr + n_nbr + 1);
+    c.n_shared = n_nbr > 0 ? shared_ptr[n_nbr] : 0;
+    c.launches_per_halo = n_nbr > 0 ? 1 + n_nbr : 0;
+    if (c.n_shared > 0) {
+        if (cudaMalloc((void**)&c.d_shared, c.n_shared * sizeof(int)) != cudaSuccess ||
+            cudaMalloc((void**)&c.sendbuf, 3 * (size_t)c.n_shared * sizeof(double)) != cudaSuccess ||
+            cudaMalloc((void**)&c.recvbuf, 3 * (size_t)c.n_shared * sizeof(double)) != cudaSuccess) {
+            comm_err_ref() = "cudaMalloc failed for halo buffers";
+            return 1;
+        }
+        cudaMemcpy(c.d_shared, shared_nodes, c.n_shared * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    return 0;
+}
+
+__global__ void k_halo_pack(int n, const int* nodes, const double* vec, double* buf) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * n) return;
+    buf[t] = vec[3 * (size_t)nodes[t / 3] + t % 3];
+}
+__global__ void k_halo_add(int n, const int* nodes, const double* buf, double* vec) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * n) return;
+    vec[3 * (size_t)nodes[t / 3] + t % 3] += buf[t];
+}
+
+// vec[shared nodes] += sum over neighbours of their partial values.  Both sides add the same two numbers
+// (a+b == b+a), so the copies of an interface value stay bitwise identical on 1-D slab partitions.
+inline int comm_halo_sum(Comm& c, double* vec, cudaStream_t s) {
+    if (!c.active || c.n_shared == 0) return 0;
+    NcclApi* api = nccl_api();
+    if (!api) return 1;
+    k_halo_pack<<<(3 * c.n_shared + 255) / 256, 256, 0, s>>>(c.n_shared, c.d_shared, vec, c.sendbuf);
+    NCK(api->GroupStart());
+    for (int k = 0; k < c.n_nbr; ++k) {
+        const size_t off = 3 * (size_t)c.shared_ptr[k], cnt = 3 * (size_t)(c.shared_ptr[k + 1] - c.shared_ptr[k]);
+        NCK(api->Send(c.sendbuf + off, cnt, ncclDouble, c.nbr_rank[k], c.nccl, s));
+        NCK(api->Recv(c.recvbuf + off, cnt, ncclDouble, c.nbr_rank[k], c.nccl, s));
+    }
+    NCK(api->GroupEnd());
+    for (int k = 0; k < c.n_nbr; ++k) {           // one launch per neighbour: a node shared with two neighbours is
+        const int off = c.shared_ptr[k], cnt = c.shared_ptr[k + 1] - off;   // updated in neighbour order, race-free
+        k_halo_add<<<(3 * cnt + 255) / 256, 256, 0, s>>>(cnt, c.d_shared + off, c.recvbuf + 3 * (size_t)off, vec);
+    }
+    return 0;
+}
+
+inline int comm_allreduce_sum(Comm& c, double* dev, int n, cudaStream_t s) {
+    if (!c.active) return 0;
+    NcclApi* api = nccl_api();
+    if (!api) return 1;
+    NCK(api->AllReduce(dev, dev, (size_t)n, ncclDouble, ncclSum, c.nccl, s));
+    return 0;
+}
+
+// host int max across ranks (fail flags); uses a tiny device buffer
+inline int comm_host_max(Comm& c, int* v) {
+    if (!c.active) return 0;
+    NcclApi* api = nccl_api();
+    if (!api) return 1;
+    int* d = nullptr;
+    cudaMalloc((void**)&d, sizeof(int));
+    cudaMemcpy(d, v, sizeof(int), cudaMemcpyHostToDevice);
+    NCK(api->AllReduce(d, d, 1, ncclInt, ncclMax, c.nccl, 0));
+    cudaMemcpy(v, d, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return 0;
+}
+
+// ---- small kernels used only by the partitioned path -----------------------------------------------------------
+__global__ void __launch_bounds__(VEC_THREADS) k_negate_norm(int n, const double* rhs, double* rforce, const uint8_t* owned,
+                                                              double* partials) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    double s = 0.0;
+    for (int d = blockIdx.x * VEC_THREADS + threadIdx.x; d < n; d += gridDim.x * VEC_THREADS) {
+        const double r = rhs[d];
+        rforce[d] = -r;
+        if (owned[d / 3]) s += r * r;
+    }
+    const double t = block_sum<VEC_THREADS>(s, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(VEC_THREADS) k_reduce2_to(const double* pa, const double* pb, int n, double* oa, double* ob) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    const double a = reduce_partials<VEC_THREADS>(pa, n, red);
+    const double b = reduce_partials<VEC_THREADS>(pb, n, red);
+    if (threadIdx.x == 0) { *oa = a; *ob = b; }
+}
+__global__ void k_pack2(double* a, const double* b) { a[1] = b[0]; }
+__global__ void k_unpack2(const double* a, double* b) { b[0] = a[1]; }
+
+// finalize the BC application after the halo sums of the correction and diagonal vectors
+__global__ void __launch_bounds__(VEC_THREADS) k_bc_finalize(int n, double* rhs, const double* fext, const uint8_t* cflag,
+                                                              const double* cval, const double* corr, const double* diag,
+                                                              double* minv, const uint8_t* owned, double* partials) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    double s = 0.0;
+    for (int d = blockIdx.x * VEC_THREADS + threadIdx.x; d < n; d += gridDim.x * VEC_THREADS) {
+        double r;
+        if (cflag[d]) r = cval[d];
+        else { r = rhs[d]; if (fext) r += fext[d]; r -= corr[d]; }
+        rhs[d] = r;
+        minv[d] = 1.0 / diag[d];
+        if (owned == nullptr || owned[d / 3]) s += r * r;
+    }
+    const double t = block_sum<VEC_THREADS>(s, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+// BC application on a partition: local pass, halo sums of the additive vectors, finalisation
+inline int bc_partitioned(Comm& c, BcArgs B, int grid_rows, int grid_vec, int ndof, const uint8_t* owned, double* corr,
+                          double* diag, double* partials, cudaStream_t s, long long* launches) {
+    B.corr_out = corr; B.diag_out = diag; B.owned = owned;
+    k_apply_bc<<<grid_rows, THREADS, 0, s>>>(B);
+    if (comm_halo_sum(c, corr, s)) return 1;
+    if (comm_halo_sum(c, diag, s)) return 1;
+    k_bc_finalize<<<grid_vec, VEC_THREADS, 0, s>>>(ndof, B.rhs, B.fext, B.cflag, B.cval, corr, diag, B.minv, owned, partials);
+    *launches += 2 + 2 * c.launches_per_halo;
+    return 0;
+}
+
+}  // namespace en234k

@@ -1,0 +1,320 @@
+// C ABI of the host driver (include/en234host.h).
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+
+#include "../../../include/en234host.h"
+#include "loads.h"
+#include "model.h"
+#include "staticstep.h"
+
+using namespace en234;
+
+struct en234host_model {
+    Model m;
+    std::map<std::string, std::vector<int>> I;
+    std::map<std::string, std::vector<double>> D;
+    bool flat = false;
+};
+
+struct en234host_part {
+    int n_ranks = 1, rank = 0;
+    std::map<std::string, std::vector<int>> I;
+    std::vector<unsigned char> owned;
+    std::vector<double> coords;
+};
+
+static thread_local std::string g_err;
+
+static void flatten(en234host_model& w) {
+    Model& m = w.m;
+    auto& I = w.I;
+    auto& D = w.D;
+    I.clear(); D.clear();
+    I["n_nodes"] = {m.n_nodes}; I["n_elements"] = {m.n_elements};
+    I["connectivity"] = m.connectivity; I["element_flag"] = m.element_flag;
+    I["element_prop_index"] = m.element_prop_index; I["element_n_props"] = m.element_n_props;
+    I["element_n_states"] = m.element_n_states;
+    D["coords"] = m.coords; D["element_properties"] = m.element_properties;
+    auto& hp = I["history_ptr"]; hp = {0};
+    for (auto& h : m.histories) {
+        D["history_time"].insert(D["history_time"].end(), h.t.begin(), h.t.end());
+        D["history_value"].insert(D["history_value"].end(), h.v.begin(), h.v.end());
+        hp.push_back((int)D["history_time"].size());
+    }
+    D["history_time"]; D["history_value"];
+    auto sets = [&](const std::vector<NamedSet>& v, const char* pn, const char* ln) {
+        auto& p = I[pn]; p = {0};
+        auto& l = I[ln];
+        for (auto& s : v) { l.insert(l.end(), s.items.begin(), s.items.end()); p.push_back((int)l.size()); }
+    };
+    sets(m.nodesets, "nodeset_ptr", "nodeset_nodes");
+    sets(m.elementsets, "elementset_ptr", "elementset_elements");
+    auto dofs = [&](const std::vector<PrescribedDof>& v, const std::string& pre, bool rate) {
+        for (const char* k : {"_flag", "_dof", "_node", "_nodeset", "_history"}) I[pre + k];
+        if (rate) I[pre + "_rate"];
+        D[pre + "_value"];
+        for (auto& p : v) {
+            I[pre + "_flag"].push_back(p.flag); I[pre + "_dof"].push_back(p.dof); I[pre + "_node"].push_back(p.node_number);
+            I[pre + "_nodeset"].push_back(p.node_set); I[pre + "_history"].push_back(p.history_number);
+            if (rate) I[pre + "_rate"].push_back(p.rate_flag);
+            D[pre + "_value"].push_back(p.value);
+        }
+    };
+    dofs(m.prescribed_dofs, "pdof", true);
+    dofs(m.prescribed_forces, "pforce", false);
+    for (const char* k : {"dload_flag", "dload_elset", "dload_face", "dload_history"}) I[k];
+    I["dload_val_ptr"] = {0};
+    D["dload_values"];
+    for (auto& d : m.distributed_loads) {
+        I["dload_flag"].push_back(d.flag); I["dload_elset"].push_back(d.element_set); I["dload_face"].push_back(d.face);
+        I["dload_history"].push_back(d.history_number);
+        D["dload_values"].insert(D["dload_values"].end(), d.values.begin(), d.values.end());
+        I["dload_val_ptr"].push_back((int)D["dload_values"].size());
+    }
+    I["max_no_steps"] = {m.max_no_steps}; I["solvertype"] = {m.solvertype}; I["nonlinear"] = {m.nonlinear ? 1 : 0};
+    I["max_newton_iterations"] = {m.max_newton_iterations}; I["unsymmetric"] = {m.unsymmetric_stiffness ? 1 : 0};
+    I["abaqusformat"] = {m.abaqusformat ? 1 : 0}; I["max_cg_iterations"] = {m.max_cg_iterations};
+    I["checkstiffness_flag"] = {m.checkstiffness_flag};
+    D["timestep_initial"] = {m.timestep_initial}; D["timestep_min"] = {m.timestep_min};
+    D["timestep_max"] = {m.timestep_max}; D["max_total_time"] = {m.max_total_time};
+    D["newtonraphson_tolerance"] = {m.newtonraphson_tolerance}; D["cg_tolerance"] = {m.cg_tolerance};
+    w.flat = true;
+}
+
+extern "C" {
+
+const char* en234host_last_error(void) { return g_err.c_str(); }
+
+en234host_model_t en234host_model_read(const char* path) {
+    auto* w = new en234host_model();
+    if (!read_input_file(path, w->m)) { g_err = w->m.error; delete w; return nullptr; }
+    return w;
+}
+en234host_model_t en234host_model_from_text(const char* text) {
+    auto* w = new en234host_model();
+    if (!read_input_text(text, w->m)) { g_err = w->m.error; delete w; return nullptr; }
+    return w;
+}
+void en234host_model_free(en234host_model_t m) { delete m; }
+
+int en234host_model_int(en234host_model_t w, const char* name, const int** p, long* n) {
+    if (!w->flat) flatten(*w);
+    auto it = w->I.find(name);
+    if (it == w->I.end()) { g_err = std::string("unknown int array ") + name; return 1; }
+    *p = it->second.data(); *n = (long)it->second.size();
+    return 0;
+}
+int en234host_model_double(en234host_model_t w, const char* name, const double** p, long* n) {
+    if (!w->flat) flatten(*w);
+    auto it = w->D.find(name);
+    if (it == w->D.end()) { g_err = std::string("unknown double array ") + name; return 1; }
+    *p = it->second.data(); *n = (long)it->second.size();
+    return 0;
+}
+int en234host_model_find_set(en234host_model_t w, int element_set, const char* name) {
+    const auto& v = element_set ? w->m.elementsets : w->m.nodesets;
+    for (size_t i = 0; i < v.size(); ++i) if (v[i].name == name) return (int)i + 1;
+    return 0;
+}
+int en234host_model_set(en234host_model_t w, const char* name, double value) {
+    Model& m = w->m;
+    std::string k(name);
+    w->flat = false;
+    if (k == "cg_tolerance") m.cg_tolerance = value;
+    else if (k == "max_cg_iterations") m.max_cg_iterations = (int)value;
+    else if (k == "solvertype") m.solvertype = (int)value;
+    else if (k == "nonlinear") m.nonlinear = value != 0;
+    else if (k == "newtonraphson_tolerance") m.newtonraphson_tolerance = value;
+    else if (k == "max_newton_iterations") m.max_newton_iterations = (int)value;
+    else if (k == "max_no_steps") m.max_no_steps = (int)value;
+    else if (k == "timestep_initial") m.timestep_initial = value;
+    else if (k == "timestep_min") m.timestep_min = value;
+    else if (k == "timestep_max") m.timestep_max = value;
+    else if (k == "max_total_time") m.max_total_time = value;
+    else { g_err = "unknown option " + k; return 1; }
+    return 0;
+}
+long en234host_model_write_text(en234host_model_t w, char* buf, long cap) {
+    std::string s = write_input_text(w->m);
+    if (buf && cap > (long)s.size()) std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (long)s.size() + 1;
+}
+
+int en234host_evaluate_loads(en234host_model_t w, double time, double dtime, const double* dof_total,
+                             const double* dof_increment, double* f_element_ext, double* f_ext, int* n_fixed,
+                             int* fixed_dof, double* fixed_value, double* fixed_correction, int fixed_cap) {
+    StepLoads L;
+    evaluate_loads(w->m, time, dtime, dof_total, dof_increment, L);
+    const size_t nd = (size_t)w->m.ndof();
+    if (f_element_ext) std::memcpy(f_element_ext, L.element_ext.data(), nd * sizeof(double));
+    if (f_ext) std::memcpy(f_ext, L.ext.data(), nd * sizeof(double));
+    *n_fixed = (int)L.fixed_dof.size();
+    if ((int)L.fixed_dof.size() > fixed_cap) { g_err = "fixed_cap too small"; return 1; }
+    for (size_t i = 0; i < L.fixed_dof.size(); ++i) {
+        if (fixed_dof) fixed_dof[i] = L.fixed_dof[i];
+        if (fixed_value) fixed_value[i] = L.fixed_value[i];
+        if (fixed_correction) fixed_correction[i] = L.fixed_correction[i];
+    }
+    return 0;
+}
+
+int en234host_gpu_create(en234host_model_t w, int device, en234gpu_handle* h) {
+    const Model& m = w->m;
+    int rc = en234gpu_create(h, device, m.n_nodes, m.n_elements, m.coords.data(), m.connectivity.data(),
+                             m.element_flag.data(), m.element_prop_index.data(), m.element_properties.data(),
+                             (int)m.element_properties.size());
+    if (rc) g_err = en234gpu_last_error();
+    return rc;
+}
+
+int en234host_run_static(en234host_model_t w, en234gpu_handle h, int method, double cg_tolerance,
+                         int max_cg_iterations, int check_linear_cg, int use_host_api, double* dof_total,
+                         double* rforce, double* newton, int max_rows, int* cg_iterations, int max_cg_rows,
+                         long long* info, const char* log_path) {
+    StepOptions o;
+    o.method = method; o.cg_tolerance = cg_tolerance; o.max_cg_iterations = max_cg_iterations;
+    o.check_linear_cg = check_linear_cg != 0; o.use_host_api = use_host_api != 0;
+    StepResult r;
+    FILE* log = log_path ? std::fopen(log_path, "w") : nullptr;
+    int rc = compute_static_step(w->m, h, o, r, log);
+    if (log) std::fclose(log);
+    if (rc) g_err = r.error;
+    const size_t nd = (size_t)w->m.ndof();
+    if (dof_total && r.dof_total.size() == nd) std::memcpy(dof_total, r.dof_total.data(), nd * sizeof(double));
+    if (rforce && r.rforce.size() == nd) std::memcpy(rforce, r.rforce.data(), nd * sizeof(double));
+    int nr = 0;
+    for (auto& q : r.newton) {
+        if (nr >= max_rows) break;
+        double* p = newton + 8 * nr++;
+        p[0] = q.step; p[1] = q.iteration; p[2] = q.correction_norm; p[3] = q.nodal_force_norm;
+        p[4] = q.unbalanced_force_norm; p[5] = q.ratio; p[6] = q.tolerance; p[7] = q.converged;
+    }
+    int nc = 0;
+    for (int it : r.cg_iterations) { if (nc >= max_cg_rows) break; cg_iterations[nc++] = it; }
+    if (info) { info[0] = r.n_steps_completed; info[1] = r.n_cutbacks; info[2] = nr; info[3] = nc; }
+    return rc;
+}
+
+// ---- element partition --------------------------------------------------------------------------------
+// Elements are split into n_ranks contiguous ranges of the element numbering (for the structured blocks of
+// user_mesh(), whose elements are numbered x-fastest then y then z, a range of whole z-layers is a slab).
+// Each rank keeps the closure of its elements' nodes; a node shared with other ranks is owned by the lowest
+// rank that has it.  Shared node lists are sorted by global node number so both sides agree on the order.
+en234host_part_t en234host_partition(en234host_model_t w, int n_ranks, int rank) {
+    const Model& m = w->m;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) { g_err = "bad rank"; return nullptr; }
+    auto* p = new en234host_part();
+    p->n_ranks = n_ranks; p->rank = rank;
+    const long long E = m.n_elements;
+    // split on whole z-layers when the model is a single structured block, else on plain ranges
+    auto first_of = [&](int r) -> long long {
+        long long layer = 1;
+        if (m.groups.size() == 1 && m.groups[0].zone == "block") {
+            // recover nx*ny from the node set sizes is fragile; use the connectivity stride instead:
+            // first element of layer k+1 has first node = first node of layer k + (nx+1)(ny+1)
+            const int nxny_nodes = m.connectivity[4] - m.connectivity[0];
+            // elements per layer = count of elements whose first node < 1 + nxny_nodes and 5th node <= 2*nxny_nodes
+            long long cnt = 0;
+            while (cnt < E && m.connectivity[8 * cnt] <= nxny_nodes) ++cnt;
+            if (cnt > 0 && E % cnt == 0) layer = cnt;
+        }
+        long long nl = E / layer;
+        long long lf = nl * r / n_ranks;
+        return lf * layer;
+    };
+    const long long e0 = first_of(rank), e1 = rank + 1 == n_ranks ? E : first_of(rank + 1);
+    // which ranks touch each node: since ranges are contiguous, compute min/max rank per node
+    std::vector<int> rmin(m.n_nodes, n_ranks), rmax(m.n_nodes, -1);
+    {
+        int r = 0;
+        long long next = n_ranks > 1 ? first_of(1) : E;
+        for (long long e = 0; e < E; ++e) {
+            while (r + 1 < n_ranks && e >= next) { ++r; next = r + 1 < n_ranks ? first_of(r + 1) : E; }
+            for (int a = 0; a < 8; ++a) {
+                int n = m.connectivity[8 * e + a] - 1;
+                rmin[n] = std::min(rmin[n], r);
+                rmax[n] = std::max(rmax[n], r);
+            }
+        }
+    }
+    // exact rank sets for shared nodes (a node may be shared by non-adjacent ranks on unstructured meshes)
+    std::vector<int> g2l(m.n_nodes, -1);
+    auto& l2g = p->I["local_to_global_node"];
+    auto& lel = p->I["local_elements"];
+    auto& conn = p->I["connectivity"];
+    for (long long e = e0; e < e1; ++e) {
+        lel.push_back((int)e);
+        for (int a = 0; a < 8; ++a) {
+            int n = m.connectivity[8 * e + a] - 1;
+            if (g2l[n] < 0) { g2l[n] = 0; }
+        }
+    }
+    // local numbering in ascending global order (keeps the structured locality)
+    for (int n = 0; n < m.n_nodes; ++n) if (g2l[n] == 0) { g2l[n] = (int)l2g.size(); l2g.push_back(n); }
+    for (long long e = e0; e < e1; ++e)
+        for (int a = 0; a < 8; ++a) conn.push_back(g2l[m.connectivity[8 * e + a] - 1] + 1);
+    // neighbours: ranks r != rank that also touch one of my nodes.  Build per-rank node marks lazily.
+    std::map<int, std::vector<int>> shared;   // neighbour rank -> local nodes (ascending global order)
+    {
+        std::vector<std::vector<int>> touch;  // only for nodes with rmin != rmax
+        int r = 0;
+        long long next = n_ranks > 1 ? first_of(1) : E;
+        std::vector<int> last_rank_seen(m.n_nodes, -1);
+        std::vector<std::pair<int, int>> pairs;   // (global node, rank) for multi-rank nodes that I hold
+        for (long long e = 0; e < E; ++e) {
+            while (r + 1 < n_ranks && e >= next) { ++r; next = r + 1 < n_ranks ? first_of(r + 1) : E; }
+            if (r == rank) continue;
+            for (int a = 0; a < 8; ++a) {
+                int n = m.connectivity[8 * e + a] - 1;
+                if (g2l[n] >= 0 && last_rank_seen[n] != r) { last_rank_seen[n] = r; pairs.emplace_back(n, r); }
+            }
+        }
+        std::sort(pairs.begin(), pairs.end());
+        pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+        for (auto& pr : pairs) shared[pr.second].push_back(g2l[pr.first]);
+    }
+    auto& nbr = p->I["neighbour_rank"];
+    auto& sp = p->I["shared_ptr"]; sp = {0};
+    auto& sn = p->I["shared_nodes"];
+    for (auto& kv : shared) {
+        nbr.push_back(kv.first);
+        sn.insert(sn.end(), kv.second.begin(), kv.second.end());
+        sp.push_back((int)sn.size());
+    }
+    p->owned.assign(l2g.size(), 1);
+    for (size_t i = 0; i < l2g.size(); ++i) p->owned[i] = rmin[l2g[i]] == rank ? 1 : 0;
+    p->I["n_nodes"] = {(int)l2g.size()};
+    p->I["n_elements"] = {(int)lel.size()};
+    p->I["n_neighbours"] = {(int)nbr.size()};
+    p->coords.resize(3 * l2g.size());
+    for (size_t i = 0; i < l2g.size(); ++i)
+        for (int c = 0; c < 3; ++c) p->coords[3 * i + c] = m.coords[3 * (size_t)l2g[i] + c];
+    (void)rmax;
+    return p;
+}
+void en234host_part_free(en234host_part_t p) { delete p; }
+int en234host_part_int(en234host_part_t p, const char* name, const int** ptr, long* n) {
+    auto it = p->I.find(name);
+    if (it == p->I.end()) { g_err = std::string("unknown partition array ") + name; return 1; }
+    *ptr = it->second.data(); *n = (long)it->second.size();
+    return 0;
+}
+const unsigned char* en234host_part_owned(en234host_part_t p) { return p->owned.data(); }
+
+int en234host_part_gpu_create(en234host_model_t w, en234host_part_t p, int device, en234gpu_handle* h) {
+    const Model& m = w->m;
+    const auto& lel = p->I["local_elements"];
+    std::vector<int> flag(lel.size()), pidx(lel.size());
+    for (size_t i = 0; i < lel.size(); ++i) { flag[i] = m.element_flag[lel[i]]; pidx[i] = m.element_prop_index[lel[i]]; }
+    int rc = en234gpu_create(h, device, p->I["n_nodes"][0], (int)lel.size(), p->coords.data(), p->I["connectivity"].data(),
+                             flag.data(), pidx.data(), m.element_properties.data(), (int)m.element_properties.size());
+    if (rc) { g_err = en234gpu_last_error(); return rc; }
+    rc = en234gpu_set_partition(*h, p->I["n_neighbours"][0], p->I["neighbour_rank"].data(), p->I["shared_ptr"].data(),
+                                p->I["shared_nodes"].data(), p->owned.data());
+    if (rc) g_err = en234gpu_last_error();
+    return rc;
+}
+
+}  // extern "C"

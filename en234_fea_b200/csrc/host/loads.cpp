@@ -1,0 +1,138 @@
+// Host-side evaluation of the boundary-condition data that feeds the device path each time the reference
+// would call its assembly / BC routines.  These are surface (O(n^2)) terms, kept on the host:
+//   * element_ext: ABAQUS-UEL distributed loads, which the reference's UEL adds to its own element residual
+//     (user_codes/src/abaqus_uel_linelastic_3d.for:207-238; magnitudes from generate_abaqus_dloads,
+//     src/solver_direct.f90:798-912)
+//   * ext: native-element tractions (src/solver_direct.f90:501-568 + src/traction_boundarycondition.f90:66-94)
+//     and prescribed nodal forces (src/solver_direct.f90:646-682)
+//   * prescribed DOFs -> (dof, value) list in application order (src/solver_direct.f90:685-734)
+#include <cmath>
+
+#include "loads.h"
+
+namespace en234 {
+namespace {
+
+// local node numbers (1-based) of the faces of an 8-node brick (Element_Utilities.f90:1102-1109)
+const int FACE[6][4] = {{1, 2, 3, 4}, {5, 8, 7, 6}, {1, 5, 6, 2}, {2, 6, 7, 3}, {3, 7, 8, 4}, {4, 8, 5, 1}};
+
+// 2x2 Gauss rule on a quadrilateral face; abscissa is a proper double here
+// (Element_Utilities.f90:486 / abaqus_uel_2D.for:190), point order (-,-),(+,-),(+,+),(-,+)
+const double CN = 0.5773502691896260;
+const int GX[4] = {-1, 1, 1, -1}, GY[4] = {-1, -1, 1, 1};
+
+struct FacePoint { double N[4]; double norm[3]; };
+
+// shape functions of the 4-node face (abaqus_uel_2D.for:311-334) and the (unnormalised) normal as the
+// reference forms it — including its sign convention for the second component (…linelastic_3d.for:228-230)
+void face_point(const double fc[4][3], int kint, FacePoint& fp) {
+    const double xi = GX[kint] * CN, eta = GY[kint] * CN;
+    const double g1 = 0.5 * (1.0 - xi), g2 = 0.5 * (1.0 + xi), h1 = 0.5 * (1.0 - eta), h2 = 0.5 * (1.0 + eta);
+    fp.N[0] = g1 * h1; fp.N[1] = g2 * h1; fp.N[2] = g2 * h2; fp.N[3] = g1 * h2;
+    const double d1[4] = {-0.5 * h1, 0.5 * h1, 0.5 * h2, -0.5 * h2};
+    const double d2[4] = {g1 * -0.5, g2 * -0.5, g2 * 0.5, g1 * 0.5};
+    double t1[3] = {0, 0, 0}, t2[3] = {0, 0, 0};
+    for (int i = 0; i < 3; ++i)
+        for (int a = 0; a < 4; ++a) { t1[i] += fc[a][i] * d1[a]; t2[i] += fc[a][i] * d2[a]; }
+    fp.norm[0] = t1[1] * t2[2] - t2[1] * t1[2];
+    fp.norm[1] = t1[0] * t2[2] - t2[0] * t1[2];
+    fp.norm[2] = t1[0] * t2[1] - t2[0] * t1[1];
+}
+
+void face_coords(const Model& m, int lmn, int face, int nodes[4], double fc[4][3]) {
+    for (int j = 0; j < 4; ++j) {
+        nodes[j] = m.connectivity[8 * (size_t)lmn + FACE[face - 1][j] - 1] - 1;
+        for (int i = 0; i < 3; ++i) fc[j][i] = m.coords[3 * (size_t)nodes[j] + i];
+    }
+}
+
+}  // namespace
+
+void evaluate_loads(const Model& m, double time, double dtime, const double* dof_total, const double* dof_increment,
+                    StepLoads& out) {
+    const size_t ndof = (size_t)m.ndof();
+    out.element_ext.assign(ndof, 0.0);
+    out.ext.assign(ndof, 0.0);
+    out.fixed_dof.clear();
+    out.fixed_value.clear();
+    out.fixed_correction.clear();
+    out.any_element_ext = out.any_ext = false;
+
+    for (const auto& d : m.distributed_loads) {
+        const NamedSet& es = m.elementsets[d.element_set - 1];
+        double hist = 1.0;
+        if (d.history_number > 0) hist = interpolate_history_table(m.histories[d.history_number - 1], time + dtime);
+        for (int e1 : es.items) {
+            const int lmn = e1 - 1;
+            const bool uel = m.element_flag[lmn] > 99999;
+            if (d.uel_format) {
+                if (!uel) break;                                      // solver_direct.f90:848,:876 `exit`
+                // pressure magnitude (:886-890): value * history(TIME+DTIME)
+                const double mag = d.history_number > 0 ? d.values[0] * hist : d.values[0];
+                int nodes[4];
+                double fc[4][3];
+                face_coords(m, lmn, d.flag < 0 ? -d.flag : d.flag, nodes, fc);
+                for (int kint = 0; kint < 4; ++kint) {
+                    FacePoint fp;
+                    face_point(fc, kint, fp);
+                    // abaqus_uel_linelastic_3d.for:232-236 as the compiler scalarises it: every face
+                    // node receives (N2(1) n1, N2(2) n2, N2(3) n3)
+                    for (int i = 0; i < 4; ++i)
+                        for (int c = 0; c < 3; ++c) out.element_ext[3 * (size_t)nodes[i] + c] -= fp.N[c] * mag * fp.norm[c];
+                }
+                out.any_element_ext = true;
+            } else {
+                if (uel) continue;                                    // solver_direct.f90:510
+                if (d.flag >= 4) continue;
+                double tr[3] = {0, 0, 0};
+                if (d.flag < 3) for (size_t i = 0; i < d.values.size() && i < 3; ++i) tr[i] = d.values[i];
+                else tr[0] = 1.0;
+                if (d.flag == 2) {
+                    double nr = std::sqrt(tr[0] * tr[0] + tr[1] * tr[1] + tr[2] * tr[2]);
+                    for (double& t : tr) t /= nr;
+                }
+                if (d.flag > 1) for (double& t : tr) t *= hist;
+                int nodes[4];
+                double fc[4][3];
+                face_coords(m, lmn, d.face, nodes, fc);
+                for (int kint = 0; kint < 4; ++kint) {
+                    FacePoint fp;
+                    face_point(fc, kint, fp);
+                    const double det = std::sqrt(fp.norm[0] * fp.norm[0] + fp.norm[1] * fp.norm[1] + fp.norm[2] * fp.norm[2]);
+                    for (int a = 0; a < 4; ++a)
+                        for (int c = 0; c < 3; ++c) {
+                            if (d.flag < 3) out.ext[3 * (size_t)nodes[a] + c] += fp.N[a] * tr[c] * det;
+                            else out.ext[3 * (size_t)nodes[a] + c] -= fp.N[a] * tr[0] * fp.norm[c];
+                        }
+                }
+                out.any_ext = true;
+            }
+        }
+    }
+
+    for (const auto& p : m.prescribed_forces) {
+        double fv = p.flag == 1 ? p.value : interpolate_history_table(m.histories[p.history_number - 1], time + dtime);
+        if (p.node_set == 0) out.ext[3 * (size_t)(p.node_number - 1) + p.dof - 1] += fv;
+        else for (int n : m.nodesets[p.node_set - 1].items) out.ext[3 * (size_t)(n - 1) + p.dof - 1] += fv;
+        out.any_ext = true;
+    }
+
+    for (const auto& p : m.prescribed_dofs) {
+        double v = p.flag == 1 ? p.value : interpolate_history_table(m.histories[p.history_number - 1], time + dtime);
+        auto one = [&](int n) {
+            const int d = 3 * (n - 1) + p.dof - 1;
+            double target = v;
+            // RATE: the value prescribes the increment (solver_direct.f90:706-708); expressed as a target for
+            // dof_total + dof_increment so the device forms one kind of correction
+            if (p.rate_flag) target = v + (dof_total ? dof_total[d] : 0.0);
+            out.fixed_dof.push_back(d);
+            out.fixed_value.push_back(target);
+            const double ucur = (dof_total ? dof_total[d] : 0.0) + (dof_increment ? dof_increment[d] : 0.0);
+            out.fixed_correction.push_back(target - ucur);
+        };
+        if (p.node_set == 0) one(p.node_number);
+        else for (int n : m.nodesets[p.node_set - 1].items) one(n);
+    }
+}
+
+}  // namespace en234

@@ -1,0 +1,82 @@
+// Host-side data model of the product: the subset of the reference's module-global arrays that the
+// static-step hot path reads (modules/Mesh.f90:51-107, modules/Boundaryconditions.f90:4-76,
+// modules/Staticstepparameters.f90:5-18), as plain vectors.  Filled by read_input_file() or user_mesh().
+#pragma once
+#include <string>
+#include <vector>
+
+namespace en234 {
+
+struct History { std::string name; std::vector<double> t, v; };
+struct NamedSet { std::string name; std::vector<int> items; };   // 1-based node / element numbers
+
+struct PrescribedDof {        // prescribeddof_list / prescribedforce_list (Boundaryconditions.f90:34-55)
+    int flag = 1;             // 1 VALUE, 2 HISTORY, 3 SUBROUTINE (unsupported)
+    int dof = 1;              // 1-based
+    int node_number = 0;      // single node, or
+    int node_set = 0;         // 1-based node set (0 = none)
+    int history_number = 0;   // 1-based
+    double value = 0.0;
+    int rate_flag = 0;
+};
+
+struct DistributedLoad {      // distributedload_list (Boundaryconditions.f90:57-66)
+    int flag = 0;             // native: 1 VALUE, 2 HISTORY, 3 NORMAL, 4 SUBROUTINE; ABAQUS UEL: face number n of "Un"
+    int element_set = 0;      // 1-based
+    int face = 0;             // native loads only
+    int history_number = 0;
+    std::vector<double> values;
+    bool uel_format = false;
+};
+
+struct ElementGroup {         // one PARAMETERS/PROPERTIES/CONNECTIVITY block of ELEMENTS, USER
+    int flag = 0, n_nodes = 8, n_states = 0;
+    int prop_index = 0, n_props = 0;
+    int first_element = 0, n_elements = 0;
+    std::string zone;
+};
+
+struct Model {
+    // mesh
+    int n_nodes = 0, n_elements = 0;
+    int n_coords = 3, n_dof = 3;
+    std::vector<double> coords;            // 3 per node
+    std::vector<int> connectivity;         // 8 per element, 1-based
+    std::vector<int> element_flag, element_prop_index, element_n_props, element_n_states;
+    std::vector<double> element_properties;
+    std::vector<ElementGroup> groups;
+    bool abaqusformat = false;             // set when any element id is "Un"/"VUn" (read_input_file.f90:546-555)
+    // boundary conditions
+    std::vector<History> histories;
+    std::vector<NamedSet> nodesets, elementsets;
+    std::vector<PrescribedDof> prescribed_dofs, prescribed_forces;
+    std::vector<DistributedLoad> distributed_loads;
+    // static step (defaults read_input_file.f90:120-129, :1735-1751)
+    bool staticstep = false;
+    double timestep_initial = 0, timestep_min = 0, timestep_max = 0, max_total_time = 0;
+    int max_no_steps = 1;
+    int solvertype = 1;                    // 1 direct, 2 conjugate gradient
+    bool nonlinear = true;
+    double newtonraphson_tolerance = 1e-8;
+    int max_newton_iterations = 1;
+    bool unsymmetric_stiffness = false;
+    int checkstiffness_flag = 0;           // element flag named by CHECK STIFFNESS (0 = none)
+    // run-time solver options that are compile-time parameters in modules/Stiffness.f90:35-37
+    double cg_tolerance = 1e-17;
+    int max_cg_iterations = 1000;
+    std::string error;
+
+    int ndof() const { return 3 * n_nodes; }
+};
+
+// src/read_input_file.f90 + src/parse.f90 — subset listed in SURVEY.md section 5
+bool read_input_file(const std::string& path, Model& m);
+bool read_input_text(const std::string& text, Model& m);
+// user_codes/src/user_mesh.f90 hook (MESH / USER SUBROUTINE): synthetic structured hex8 block
+bool user_mesh(const std::vector<double>& params, Model& m);
+// writes the same mesh/BCs as literal .in text (parser round-trip tests, n <= 16)
+std::string write_input_text(const Model& m);
+
+double interpolate_history_table(const History& h, double time);   // Boundaryconditions.f90:161-221
+
+}  // namespace en234

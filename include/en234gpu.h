@@ -1,0 +1,152 @@
+/* en234gpu.h — C ABI of the B200 (sm_100a) implementation of the EN234_FEA static-step hot path.
+ *
+ * Drop-in boundary: every entry point replaces one argument-less module-global subroutine call of the
+ * reference's static step driver (citations relative to /root/reference/EN234_FEA/).  All arguments are
+ * plain pointers and sizes in the reference's own array layouts (modules/Mesh.f90:51-107): a Fortran
+ * driver binds them with ISO_C_BINDING (fortran/en234_gpu_iface.f90).
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (message via
+ * en234gpu_last_error()); the library never calls exit().  Recoverable numerical failures (NaN in
+ * the residual, non-positive Jacobian, CG breakdown / non-convergence) are reported through *fail = 1 so
+ * the driver can cut the time step back exactly as src/staticstep.f90:46-54,109-117 does.
+ * Host arrays stay caller-owned and are only touched during a call.  One host thread per handle.
+ * There is no CPU fallback: without a CUDA device en234gpu_create() fails.
+ */
+#ifndef EN234GPU_H
+#define EN234GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct en234gpu_ctx* en234gpu_handle;
+
+/* Element identifiers understood on the device (element_list%flag, modules/Mesh.f90:16-29):
+ *   1001            native linear elastic hex8   (user_codes/src/el_linelast_3Dbasic.f90, user_element.f90:62)
+ *   99999 + 1 (U1)  ABAQUS UEL linear elastic hex8 (user_codes/src/abaqus_uel_linelastic_3d.for; flag = n+99999,
+ *                   src/read_input_file.f90:546-550)
+ *   1002 / U2       compressible neo-Hookean hex8 (new; props mu, K as input_files/Abaqus_uel_hyperelastic.in:44) */
+#define EN234_ID_LINELAST 1001
+#define EN234_ID_NEOHOOKE 1002
+#define EN234_FLAG_UEL_BASE 99999
+
+/* Solver methods for en234gpu_solve */
+#define EN234_SOLVE_PCG_BSR 0        /* Jacobi-PCG on the assembled 3x3-block CSR matrix               */
+#define EN234_SOLVE_PCG_MATRIXFREE 1 /* Jacobi-PCG with the element-by-element (matrix-free) operator  */
+
+const char* en234gpu_last_error(void);
+int en234gpu_device_count(void);
+
+/* Replaces initialize_cg_solver (src/solver_conjugate_gradient.f90:1039-1244; called at src/staticstep.f90:95)
+ * and, for the direct branch, generate_node_numbers/compute_profile/allocate_direct_stiffness
+ * (src/staticstep.f90:38-40): builds the sparsity pattern, the element-to-CSR slot maps and all device
+ * storage once per analysis.
+ *   coords[3*n_nodes]          xyz per node           (Mesh.f90:84 `coords`)
+ *   connectivity[8*n_elements] 1-based node numbers   (Mesh.f90:69 `connectivity`)
+ *   element_flag[n_elements]   element_list%flag
+ *   element_prop_index[n_elements] 0-based offset of the element's first property in element_properties
+ *   element_properties[n_element_properties]          (Mesh.f90:76 `element_properties`)
+ * Partitioned runs (one handle per GPU/process) pass the rank-local mesh and then call
+ * en234gpu_set_partition() before the first assemble. */
+int en234gpu_create(en234gpu_handle* h, int device, int n_nodes, int n_elements, const double* coords,
+                    const int* connectivity, const int* element_flag, const int* element_prop_index,
+                    const double* element_properties, int n_element_properties);
+int en234gpu_destroy(en234gpu_handle h);
+
+/* Run all work of this handle on an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's
+ * current stream, so that caller-side CUDA events bracket it. NULL = the handle's own stream. */
+int en234gpu_set_stream(en234gpu_handle h, void* cuda_stream);
+
+/* Replaces assemble_conjugate_gradient_stiffness (src/solver_conjugate_gradient.f90:1-414; call sites
+ * src/staticstep.f90:98,122) / assemble_direct_stiffness (src/solver_direct.f90:5-439; :44,:61):
+ * element loop (gather :104-121, element routine :129-258) + deterministic assembly (:264-287 semantics,
+ * contributions summed in ascending element order) + NaN scan (:402-415) + rforce = -rhs (:417-421) +
+ * nodal_force_norm = ||rhs||_2 (:423).
+ *   dof_total, dof_increment [3*n_nodes]   (Mesh.f90:85-86)
+ *   f_element_ext [3*n_nodes] or NULL      load vectors that the reference's element routines add to their
+ *                                          own residual (ABAQUS UEL DLOAD faces, abaqus_uel_linelastic_3d.for:207-238);
+ *                                          evaluated on the host (surface terms) and added before rforce/norm.
+ *   rforce [3*n_nodes] out or NULL         (Mesh.f90:91) */
+int en234gpu_assemble(en234gpu_handle h, const double* dof_total, const double* dof_increment,
+                      const double* f_element_ext, double* rforce, double* nodal_force_norm, int* fail);
+
+/* Replaces apply_cojugategradient_boundaryconditions (src/solver_conjugate_gradient.f90:417-671; :107,:127) /
+ * apply_direct_boundaryconditions (src/solver_direct.f90:444-738; :55,:65):
+ *   f_ext [3*n_nodes] or NULL   native-element tractions (:501-568) + prescribed nodal forces (:646-682), host-evaluated
+ *   fixed_dof[n_fixed]          0-based DOF indices (3*(node-1)+dof-1) of the prescribed DOFs, in application order
+ *   fixed_correction[n_fixed]   value - (dof_total+dof_increment)   (:709,:729)
+ * fixdof_* semantics (:742-792 / CG :673-713): rhs_j -= K_jn c_n, row and column n zeroed, diag_n = 1,
+ * rhs_n = c_n; a DOF listed twice keeps its last correction.  unbalanced_force_norm = ||rhs||_2 (:736). */
+int en234gpu_apply_boundaryconditions(en234gpu_handle h, const double* f_ext, int n_fixed, const int* fixed_dof,
+                                      const double* fixed_correction, double* unbalanced_force_norm);
+
+/* Replaces solve_conjugategradient + cg_iteration_loop (src/solver_conjugate_gradient.f90:717-912; :108,:130)
+ * and, for large meshes, solve_direct (src/solver_direct.f90:916-973; :56,:68).
+ * Jacobi-PCG with the reference's recurrences and stopping rule: x0 = 0, stop when
+ * (r.r)/(b.b) < cg_tolerance (reference value 1e-17, modules/Stiffness.f90:35), *fail = 1 after
+ * max_cg_iterations (reference 1000, Stiffness.f90:37); zero right-hand side returns x = 0 (:805-814).
+ *   dof_increment [3*n_nodes] inout: += solution (:760-765);  correction_norm = ||solution||_2 (:771) */
+int en234gpu_solve(en234gpu_handle h, int method, double cg_tolerance, int max_cg_iterations, double* dof_increment,
+                   double* correction_norm, int* cg_iterations, int* fail);
+
+/* Select the operator used by assemble / apply_boundaryconditions / solve: EN234_SOLVE_PCG_BSR (default) forms the
+ * block-CSR matrix; EN234_SOLVE_PCG_MATRIXFREE never forms it (assemble computes residuals only, the BC routine
+ * evaluates K[:,C]c and the Jacobi diagonal element by element).  Call before assemble. */
+int en234gpu_set_operator_mode(en234gpu_handle h, int method);
+
+/* ---- device-resident variants: same operations on the handle's device copies (no host<->device copies) */
+int en234gpu_upload_state(en234gpu_handle h, const double* dof_total, const double* dof_increment,
+                          const double* f_element_ext, const double* f_ext, int n_fixed, const int* fixed_dof,
+                          const double* fixed_value /* prescribed VALUES (not corrections) */);
+int en234gpu_assemble_dev(en234gpu_handle h, double* nodal_force_norm, int* fail);
+/* corrections are formed on the device as fixed_value - (dof_total + dof_increment) */
+int en234gpu_apply_boundaryconditions_dev(en234gpu_handle h, double* unbalanced_force_norm);
+int en234gpu_solve_dev(en234gpu_handle h, int method, double cg_tolerance, int max_cg_iterations,
+                       double* correction_norm, int* cg_iterations, int* fail);
+int en234gpu_download_state(en234gpu_handle h, double* dof_increment, double* rforce);
+int en234gpu_zero_increment_dev(en234gpu_handle h);
+
+/* ---- element plugin surface.  Batched device evaluation of the element routines for a list of elements:
+ * the device twin of user_element_static (user_codes/src/user_element.f90:5-49) / UEL
+ * (user_codes/src/abaqus_uel_linelastic_3d.for:16-28).  element_stiffness is returned per element as the
+ * reference's column-major (ROW,COL) 24x24 array, element_residual as 24 values.  Used by CHECK STIFFNESS
+ * style tests; not part of the timed path. */
+int en234gpu_element_batch(en234gpu_handle h, int n, const int* element_numbers /*1-based*/, const double* dof_total,
+                           const double* dof_increment, double* element_stiffness /*n*576*/,
+                           double* element_residual /*n*24*/, int* fail);
+/* Gauss-point state: Cauchy stress s11,s22,s33,s12,s13,s23 at the 8 integration points of every element
+ * (the 48 SVARS of abaqus_uel_linelastic_3d.for:193-195), for dof_total + dof_increment. */
+int en234gpu_get_svars(en234gpu_handle h, const double* dof_total, const double* dof_increment,
+                       double* svars /*48*n_elements*/);
+
+/* ---- inspection (parity tests, reports) */
+long long en234gpu_nnz_blocks(en234gpu_handle h);
+/* Scalar CSR view of the current system matrix: rowptr[3N+1] (64-bit), col[9*nnzb] (0-based), val[9*nnzb] */
+int en234gpu_get_csr(en234gpu_handle h, long long* rowptr, int* col, double* val);
+int en234gpu_get_rhs(en234gpu_handle h, double* rhs /*3N*/, double* diag /*3N or NULL*/);
+/* y = A x with the assembled (method 0) or matrix-free (method 1) operator, for tests */
+int en234gpu_apply_operator(en234gpu_handle h, int method, const double* x, double* y);
+
+/* ---- multi-GPU (one handle per process/GPU; element partitions with shared-node halo sums)
+ * neighbours: for each neighbour rank its shared nodes as LOCAL 0-based node indices, listed in the same
+ * (global-node-number) order on both sides.  owned[n_nodes]: 1 if this rank owns the node (exactly one
+ * owner per global node) — dot products and norms count owned DOFs only. */
+int en234gpu_get_unique_id(char* id128);
+int en234gpu_comm_init(en234gpu_handle h, int n_ranks, int rank, const char* id128);
+int en234gpu_set_partition(en234gpu_handle h, int n_neighbours, const int* neighbour_rank, const int* shared_ptr,
+                           const int* shared_nodes, const unsigned char* owned);
+
+/* ---- measurement: device time (ms, CUDA events on the handle's stream) of the last call of each phase,
+ * kernel-launch counter, and per-iteration SpMV time of the last solve */
+struct en234gpu_stats {
+    double assemble_ms, bc_ms, solve_ms, spmv_ms_avg;
+    long long kernel_launches;   /* cumulative number of kernels launched by this handle */
+    int last_cg_iterations;
+    double last_cg_err;          /* (r.r)/(b.b) at exit */
+};
+int en234gpu_get_stats(en234gpu_handle h, struct en234gpu_stats* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

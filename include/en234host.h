@@ -1,0 +1,79 @@
+/* en234host.h — C ABI of the host-side driver that sits above en234gpu.h: the `.in` parser
+ * (reference: src/read_input_file.f90 + src/parse.f90), the MESH/USER SUBROUTINE hook
+ * (user_codes/src/user_mesh.f90), boundary-condition evaluation (src/solver_direct.f90:501-734,798-912) and the
+ * static step loop (src/staticstep.f90).  Written in C++ because no Fortran compiler exists in this image; the
+ * Fortran binding of the same device entry points is shipped as source in fortran/ (see INTEGRATION.md).
+ * Every function returns 0 on success unless stated otherwise. */
+#ifndef EN234HOST_H
+#define EN234HOST_H
+
+#include "en234gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct en234host_model* en234host_model_t;
+
+/* parse an input file / literal text; on failure returns NULL and en234host_last_error() explains */
+en234host_model_t en234host_model_read(const char* path);
+en234host_model_t en234host_model_from_text(const char* text);
+void en234host_model_free(en234host_model_t m);
+const char* en234host_last_error(void);
+
+/* Flat views of the model (names as in modules/Mesh.f90 / Boundaryconditions.f90 where they exist):
+ * int arrays:  connectivity element_flag element_prop_index element_n_props element_n_states history_ptr nodeset_ptr
+ *              nodeset_nodes elementset_ptr elementset_elements pdof_flag pdof_dof pdof_node pdof_nodeset pdof_history
+ *              pdof_rate pforce_flag pforce_dof pforce_node pforce_nodeset pforce_history dload_flag dload_elset
+ *              dload_face dload_history dload_val_ptr
+ * int scalars (length 1): n_nodes n_elements max_no_steps solvertype nonlinear max_newton_iterations unsymmetric
+ *              abaqusformat max_cg_iterations checkstiffness_flag
+ * double arrays: coords element_properties history_time history_value pdof_value pforce_value dload_values
+ * double scalars: timestep_initial timestep_min timestep_max max_total_time newtonraphson_tolerance cg_tolerance
+ * The pointers stay valid until the model is freed or modified. */
+int en234host_model_int(en234host_model_t m, const char* name, const int** p, long* n);
+int en234host_model_double(en234host_model_t m, const char* name, const double** p, long* n);
+/* names of node/element sets: returns the 1-based index or 0 */
+int en234host_model_find_set(en234host_model_t m, int element_set, const char* name);
+/* run-time overrides: cg_tolerance max_cg_iterations solvertype nonlinear newtonraphson_tolerance
+ * max_newton_iterations max_no_steps timestep_initial timestep_min timestep_max max_total_time */
+int en234host_model_set(en234host_model_t m, const char* name, double value);
+/* literal `.in` text of the model; returns the number of bytes needed (call with cap = 0 to size the buffer) */
+long en234host_model_write_text(en234host_model_t m, char* buf, long cap);
+
+/* boundary-condition vectors at TIME, DTIME (see en234gpu_assemble / en234gpu_apply_boundaryconditions) */
+int en234host_evaluate_loads(en234host_model_t m, double time, double dtime, const double* dof_total,
+                             const double* dof_increment, double* f_element_ext, double* f_ext, int* n_fixed,
+                             int* fixed_dof /*cap = sum of set sizes*/, double* fixed_value, double* fixed_correction,
+                             int fixed_cap);
+
+/* device handle for the whole mesh of a model */
+int en234host_gpu_create(en234host_model_t m, int device, en234gpu_handle* h);
+
+/* compute_static_step (src/staticstep.f90:1-162) on the device path.
+ *   newton[8*max_rows]: step, iteration, correction, force, unbalanced, ratio, tolerance, converged per row
+ *   info[8]: n_steps_completed, n_cutbacks, n_newton_rows, n_cg_solves, 0...
+ *   log_path: optional file receiving the reference-format convergence lines (NULL = none) */
+int en234host_run_static(en234host_model_t m, en234gpu_handle h, int method, double cg_tolerance,
+                         int max_cg_iterations, int check_linear_cg, int use_host_api, double* dof_total,
+                         double* rforce, double* newton, int max_rows, int* cg_iterations, int max_cg_rows,
+                         long long* info, const char* log_path);
+
+/* Element partition of a model for multi-GPU runs (1-D slabs of whole elements along z for structured blocks,
+ * contiguous element ranges otherwise).  Produces the rank-local mesh and the halo description consumed by
+ * en234gpu_set_partition().  Query sizes first with the *_sizes call. */
+typedef struct en234host_part* en234host_part_t;
+en234host_part_t en234host_partition(en234host_model_t m, int n_ranks, int rank);
+void en234host_part_free(en234host_part_t p);
+/* int arrays: local_to_global_node (0-based global) local_elements (0-based global) connectivity (1-based LOCAL)
+ *             neighbour_rank shared_ptr shared_nodes ; unsigned char array `owned` via en234host_part_owned
+ * int scalars: n_nodes n_elements n_neighbours */
+int en234host_part_int(en234host_part_t p, const char* name, const int** ptr, long* n);
+const unsigned char* en234host_part_owned(en234host_part_t p);
+/* device handle for one partition (local mesh + halo already registered; call en234gpu_comm_init next) */
+int en234host_part_gpu_create(en234host_model_t m, en234host_part_t p, int device, en234gpu_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

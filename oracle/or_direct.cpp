@@ -1,0 +1,318 @@
+// ORACLE — test infrastructure only (see or_model.h).  Skyline ("profile") direct solver path:
+// restates src/solver_direct.f90 (assembly :5-439, BCs :444-738, fixdof :742-792, solve :916-973,
+// back-substitution :976-1032, LDU factorisation :1036-1192, profile :1196-1393) with 0-based arrays.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "or_model.h"
+
+namespace oracle {
+
+// Column j of the upper triangle holds rows j-h..j-1 at aupp[jp[j-1] .. jp[j]-1] (h = jp[j]-jp[j-1]).
+static inline long long colstart(const Skyline& s, int j) { return j == 0 ? 0 : s.jp[j - 1]; }
+static inline int colheight(const Skyline& s, int j) { return (int)(s.jp[j] - colstart(s, j)); }
+
+// compute_profile (solver_direct.f90:1252-1360): equations numbered in node_order, 3 per node;
+// column height = max over elements of (eq - smallest eq on the element).
+void compute_profile(const Model& m, const std::vector<int>& node_order, Skyline& s, StepLog* log) {
+    const int neq = m.ndof();
+    s.neq = neq;
+    s.ieqs.assign(neq, 0);
+    int e = 0;
+    for (int i = 0; i < m.n_nodes; ++i) {
+        int n = node_order[i];
+        for (int j = 0; j < 3; ++j) s.ieqs[3 * n + j] = e++;
+    }
+    std::vector<long long> h(neq, 0);
+    for (int lmn = 0; lmn < m.n_elements; ++lmn) {
+        int mineq = neq - 1;
+        for (int i = 0; i < 8; ++i) {
+            int n = m.connectivity[8 * lmn + i] - 1;
+            for (int j = 0; j < 3; ++j) mineq = std::min(mineq, s.ieqs[3 * n + j]);
+        }
+        for (int i = 0; i < 8; ++i) {
+            int n = m.connectivity[8 * lmn + i] - 1;
+            for (int j = 0; j < 3; ++j) {
+                int q = s.ieqs[3 * n + j];
+                h[q] = std::max<long long>(h[q], q - mineq);
+            }
+        }
+    }
+    // statistics exactly as :1339-1351 (first column excluded from max/mean/rms sums, divided by neq)
+    long long bwmax = 0;
+    double bwmn = 0.0, bwrms = 0.0;
+    s.jp.assign(neq, 0);
+    h[0] = 0;
+    for (int n = 1; n < neq; ++n) {
+        bwmax = std::max(bwmax, h[n]);
+        bwmn += (double)h[n];
+        bwrms += (double)h[n] * (double)h[n];
+    }
+    long long acc = 0;
+    for (int n = 0; n < neq; ++n) { acc += h[n]; s.jp[n] = acc; }
+    if (log) {
+        log->profile_neq = neq;
+        log->profile_bwmax = bwmax;
+        log->profile_bwmean = (long long)(bwmn / (double)neq + 0.5);
+        log->profile_bwrms = (long long)(std::sqrt(bwrms / (double)neq) + 0.5);
+        log->profile_size = s.jp[neq - 1];
+    }
+    s.aupp.assign((size_t)s.jp[neq - 1], 0.0);
+    s.diag.assign(neq, 0.0);
+    s.rhs.assign(neq, 0.0);
+}
+
+// assemble_direct_stiffness (solver_direct.f90:95-423)
+int assemble_direct_stiffness(const Model& m, Skyline& s, const double* dof_total, const double* dof_increment,
+                              double time, double dtime, std::vector<double>* svars, AsmOut& out) {
+    std::fill(s.aupp.begin(), s.aupp.end(), 0.0);
+    std::fill(s.rhs.begin(), s.rhs.end(), 0.0);
+    std::fill(s.diag.begin(), s.diag.end(), 0.0);
+    double K[576], R[24];
+    long long sv_off = 0;
+    for (int lmn = 0; lmn < m.n_elements; ++lmn) {
+        double* sv = nullptr;
+        if (svars && m.element_n_states[lmn] > 0) sv = svars->data() + sv_off;
+        sv_off += m.element_n_states[lmn];
+        if (element_static(m, lmn, dof_total, dof_increment, time, dtime, K, R, sv)) return 1;
+        // scatter :264-287
+        for (int i1 = 0; i1 < 8; ++i1) {
+            int node1 = m.connectivity[8 * lmn + i1] - 1;
+            for (int j1 = 0; j1 < 3; ++j1) {
+                int irow = s.ieqs[3 * node1 + j1], nsr = 3 * i1 + j1;
+                s.rhs[irow] += R[nsr];
+                for (int i2 = 0; i2 < 8; ++i2) {
+                    int node2 = m.connectivity[8 * lmn + i2] - 1;
+                    for (int j2 = 0; j2 < 3; ++j2) {
+                        int icol = s.ieqs[3 * node2 + j2], nsc = 3 * i2 + j2;
+                        if (icol == irow) s.diag[irow] += K[nsr + 24 * nsc];
+                        else if (icol > irow) s.aupp[(size_t)(s.jp[icol] - (icol - irow))] += K[nsr + 24 * nsc];
+                    }
+                }
+            }
+        }
+    }
+    // NaN scan :402-415
+    for (int n = 0; n < s.neq; ++n)
+        if (s.rhs[n] == s.rhs[n] + 1.0 || std::isnan(s.rhs[n])) return 1;
+    // rforce = -rhs, nodal_force_norm :417-423
+    out.rforce.assign(m.ndof(), 0.0);
+    double nn = 0.0;
+    for (int d = 0; d < m.ndof(); ++d) out.rforce[d] = -s.rhs[s.ieqs[d]];
+    for (int n = 0; n < s.neq; ++n) nn += s.rhs[n] * s.rhs[n];
+    out.nodal_force_norm = std::sqrt(nn);
+    return 0;
+}
+
+// fixdof_direct (solver_direct.f90:742-792), symmetric case
+static void fixdof_direct(Skyline& s, int n, double dofvalue) {
+    for (int ncol = n + 1; ncol < s.neq; ++ncol) {
+        int idis = ncol - n;
+        if (idis <= colheight(s, ncol)) {
+            size_t nn = (size_t)(s.jp[ncol] - idis);
+            s.rhs[ncol] -= s.aupp[nn] * dofvalue;
+            s.aupp[nn] = 0.0;
+        }
+    }
+    if (n > 0) {
+        int mod = n;
+        for (long long i = s.jp[n] - 1; i >= colstart(s, n); --i) {
+            --mod;
+            s.rhs[mod] -= s.aupp[(size_t)i] * dofvalue;
+            s.aupp[(size_t)i] = 0.0;
+        }
+    }
+    s.diag[n] = 1.0;
+    s.rhs[n] = dofvalue;
+}
+
+static double history_value(const Model& m, int h, double t) {
+    int o = m.history_ptr[h - 1], nh = m.history_ptr[h] - o;
+    return interpolate_history_table(&m.history_time[o], &m.history_value[o], nh, t);
+}
+
+// Shared by both solver paths: native-element tractions (solver_direct.f90:501-568) and prescribed
+// nodal forces (:646-682) added to rhs through `eq`; returns the list of (dof, correction) pairs of
+// the prescribed-DOF block (:685-734) in application order.
+static void bc_loads_and_corrections(const Model& m, const double* dof_total, const double* dof_increment,
+                                     double time, double dtime, bool nodal_forces, const int* ieqs,
+                                     std::vector<double>& rhs, std::vector<std::pair<int, double>>& fix) {
+    const int nloads = (int)m.dload_flag.size();
+    for (int load = 0; load < nloads; ++load) {
+        int flag = m.dload_flag[load], es = m.dload_elset[load] - 1, ifac = m.dload_face[load];
+        for (int k = m.elementset_ptr[es]; k < m.elementset_ptr[es + 1]; ++k) {
+            int lmn = m.elementset_elements[k] - 1;
+            if (m.element_flag[lmn] > FLAG_UEL_BASE) continue;    // :510 skip ABAQUS UEL
+            if (flag >= 4) continue;                               // user-subroutine loads: out of scope
+            double traction[3] = {0, 0, 0};
+            int ntract;
+            if (flag < 3) {
+                ntract = m.dload_val_ptr[load + 1] - m.dload_val_ptr[load];
+                for (int i = 0; i < ntract && i < 3; ++i) traction[i] = m.dload_values[m.dload_val_ptr[load] + i];
+            } else { ntract = 1; traction[0] = 1.0; }
+            if (flag == 2) {
+                double nr = std::sqrt(traction[0] * traction[0] + traction[1] * traction[1] + traction[2] * traction[2]);
+                for (double& t : traction) t = t / nr;
+            }
+            if (flag > 1) {
+                double v = history_value(m, m.dload_history[load], time + dtime);
+                for (double& t : traction) t = t * v;
+            }
+            int list[4];
+            facenodes_hex8(ifac, list);
+            double fc[12], R12[12];
+            for (int j = 0; j < 4; ++j) {
+                int n = m.connectivity[8 * lmn + list[j] - 1] - 1;
+                for (int i = 0; i < 3; ++i) fc[3 * j + i] = m.coords[3 * n + i];
+            }
+            traction_boundarycondition_static_3d(flag, fc, traction, ntract, R12);
+            for (int j = 0; j < 4; ++j) {
+                int n = m.connectivity[8 * lmn + list[j] - 1] - 1;
+                for (int i = 0; i < 3; ++i) rhs[ieqs[3 * n + i]] += R12[3 * j + i];
+            }
+        }
+    }
+    if (nodal_forces) {
+        for (size_t k = 0; k < m.pforce_flag.size(); ++k) {
+            double fv = 0.0;
+            if (m.pforce_flag[k] == 1) fv = m.pforce_value[k];
+            else if (m.pforce_flag[k] == 2) fv = history_value(m, m.pforce_history[k], time + dtime);
+            int idof = m.pforce_dof[k] - 1;
+            if (m.pforce_nodeset[k] == 0) rhs[ieqs[3 * (m.pforce_node[k] - 1) + idof]] += fv;
+            else {
+                int ns = m.pforce_nodeset[k] - 1;
+                for (int i = m.nodeset_ptr[ns]; i < m.nodeset_ptr[ns + 1]; ++i)
+                    rhs[ieqs[3 * (m.nodeset_nodes[i] - 1) + idof]] += fv;
+            }
+        }
+    }
+    for (size_t k = 0; k < m.pdof_flag.size(); ++k) {
+        double v = 0.0;
+        if (m.pdof_flag[k] == 1) v = m.pdof_value[k];
+        else if (m.pdof_flag[k] == 2) v = history_value(m, m.pdof_history[k], time + dtime);
+        int idof = m.pdof_dof[k] - 1;
+        auto one = [&](int n) {
+            int d = 3 * n + idof;
+            double ucur = m.pdof_rate[k] == 0 ? dof_increment[d] + dof_total[d] : dof_increment[d];
+            fix.emplace_back(d, v - ucur);
+        };
+        if (m.pdof_nodeset[k] == 0) one(m.pdof_node[k] - 1);
+        else {
+            int ns = m.pdof_nodeset[k] - 1;
+            for (int i = m.nodeset_ptr[ns]; i < m.nodeset_ptr[ns + 1]; ++i) one(m.nodeset_nodes[i] - 1);
+        }
+    }
+}
+// exported for or_cg.cpp
+void oracle_bc_loads_and_corrections(const Model& m, const double* dof_total, const double* dof_increment,
+                                     double time, double dtime, bool nodal_forces, const int* ieqs,
+                                     std::vector<double>& rhs, std::vector<std::pair<int, double>>& fix) {
+    bc_loads_and_corrections(m, dof_total, dof_increment, time, dtime, nodal_forces, ieqs, rhs, fix);
+}
+
+// apply_direct_boundaryconditions (solver_direct.f90:444-738)
+void apply_direct_boundaryconditions(const Model& m, Skyline& s, const double* dof_total,
+                                     const double* dof_increment, double time, double dtime, AsmOut& out) {
+    std::vector<std::pair<int, double>> fix;
+    bc_loads_and_corrections(m, dof_total, dof_increment, time, dtime, true, s.ieqs.data(), s.rhs, fix);
+    for (auto& f : fix) fixdof_direct(s, s.ieqs[f.first], f.second);
+    double nn = 0.0;
+    for (int n = 0; n < s.neq; ++n) nn += s.rhs[n] * s.rhs[n];
+    out.unbalanced_force_norm = std::sqrt(nn);                       // :736
+}
+
+// LU_decomposition + dredu (solver_direct.f90:1036-1192), symmetric case (alow aliases aupp):
+// Crout reduction column by column; the scaled column (U/d) replaces aupp, diag holds reciprocals.
+static void lu_decomposition(Skyline& s, StepLog* log) {
+    const double tol = 0.5e-7;
+    const int neq = s.neq;
+    double dimx = 0.0, dfig = 0.0, dimn = 0.0;
+    for (int i = 0; i < neq; ++i) dimn = std::max(dimn, std::fabs(s.diag[i]));
+    double* a = s.aupp.data();
+    for (int j = 0; j < neq; ++j) {
+        const long long c0 = colstart(s, j);
+        const int h = colheight(s, j);
+        const int is = j - h;                      // first stored row of column j
+        double daval = 0.0;
+        if (h > 1) {
+            if (s.diag[j] == 0.0)
+                for (int k = 0; k < h; ++k) daval += std::fabs(a[c0 + k]);   // :1100 (sum over jr..jr+jh)
+            for (int i = is + 1; i < j; ++i) {     // reduce entry (i,j) :1101-1111
+                const int hi = colheight(s, i);
+                const int ih = std::min(hi, i - is);
+                if (ih > 0) {
+                    const double* cj = a + c0 + (i - is) - ih;   // rows i-ih..i-1 of column j
+                    const double* ci = a + s.jp[i] - ih;          // rows i-ih..i-1 of column i
+                    double dot = 0.0;
+                    for (int k = 0; k < ih; ++k) dot += cj[k] * ci[k];
+                    a[c0 + (i - is)] -= dot;
+                }
+            }
+        }
+        const double dd = s.diag[j];
+        if (h >= 1) {                              // dredu :1164-1192
+            double dj = s.diag[j];
+            for (int k = 0; k < h; ++k) {
+                double ud = a[c0 + k] * s.diag[is + k];
+                dj = dj - a[c0 + k] * ud;
+                a[c0 + k] = ud;
+            }
+            s.diag[j] = dj;
+        }
+        if (s.diag[j] != 0.0) {                    // :1129-1137
+            dimx = std::max(dimx, std::fabs(s.diag[j]));
+            dimn = std::min(dimn, std::fabs(s.diag[j]));
+            dfig = std::max(dfig, std::fabs(dd / s.diag[j]));
+            s.diag[j] = 1.0 / s.diag[j];
+        } else {
+            s.diag[j] = 1.0 / (tol * dimn);
+        }
+        (void)daval;
+    }
+    if (log) {
+        log->lu_dimx.push_back(dimx);
+        log->lu_dimn.push_back(dimn);
+        log->lu_ifig.push_back((int)(std::log10(dfig) + 0.6));
+    }
+}
+
+// backsubstitution (solver_direct.f90:976-1032)
+static void backsubstitution(Skyline& s) {
+    const int neq = s.neq;
+    double* a = s.aupp.data();
+    double* rhs = s.rhs.data();
+    int is = 0;
+    while (is < neq && rhs[is] == 0.0) ++is;
+    if (is == neq) { std::fill(s.rhs.begin(), s.rhs.end(), 0.0); return; }
+    for (int j = is + 1; j < neq; ++j) {
+        const int h = colheight(s, j);
+        if (h > 0) {
+            const double* cj = a + colstart(s, j);
+            double dot = 0.0;
+            for (int k = 0; k < h; ++k) dot += cj[k] * rhs[j - h + k];
+            rhs[j] -= dot;
+        }
+    }
+    for (int j = is; j < neq; ++j) rhs[j] = rhs[j] * s.diag[j];
+    for (int j = neq - 1; j >= 1; --j) {
+        const int h = colheight(s, j);
+        if (h > 0) {
+            const double* cj = a + colstart(s, j);
+            const double rj = rhs[j];
+            for (int k = 0; k < h; ++k) rhs[j - h + k] -= rj * cj[k];
+        }
+    }
+}
+
+// solve_direct (solver_direct.f90:916-973)
+void solve_direct(const Model& m, Skyline& s, double* dof_increment, AsmOut& out, StepLog* log) {
+    lu_decomposition(s, log);
+    backsubstitution(s);
+    for (int d = 0; d < m.ndof(); ++d) dof_increment[d] += s.rhs[s.ieqs[d]];
+    double nn = 0.0;
+    for (int n = 0; n < s.neq; ++n) nn += s.rhs[n] * s.rhs[n];
+    out.correction_norm = std::sqrt(nn);
+}
+
+}  // namespace oracle

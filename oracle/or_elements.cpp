@@ -1,0 +1,451 @@
+// ORACLE — test infrastructure only (see or_model.h).  Element routines.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "or_model.h"
+
+namespace oracle {
+
+// Node sign table of the 8-node brick, ABAQUS C3D8 order
+// (user_codes/modules/Element_Utilities.f90:908-940 = abaqus_uel_linelastic_3d.for:424-456).
+static const double SGN[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1},
+                                 {-1, -1, 1},  {1, -1, 1},  {1, 1, 1},  {-1, 1, 1}};
+
+// Gauss abscissa: the reference assigns the *single precision* literal 0.5773502692 to a double
+// (Element_Utilities.f90:637-638, abaqus_uel_linelastic_3d.for:309-310) => 0.57735025882720947.
+static const double GP = (double)0.5773502692f;
+
+// 2x2x2 rule, point n = 4(k-1)+2(j-1)+i with i fastest over xi_1 (Element_Utilities.f90:639-648), w = 1.
+static void gauss_point(int n, double xi[3]) {
+    int i = n & 1, j = (n >> 1) & 1, k = (n >> 2) & 1;
+    xi[0] = i ? GP : -GP;
+    xi[1] = j ? GP : -GP;
+    xi[2] = k ? GP : -GP;
+}
+
+// dN/dxi for hex8 (Element_Utilities.f90:916-939).  (1 -/+ xi) products then /8, sign applied last:
+// bit-identical to the reference's "-(1.-xi(2))*(1.-xi(3))/8." forms.
+static void shape_hex8(const double xi[3], double N[8], double dNdxi[8][3]) {
+    for (int a = 0; a < 8; ++a) {
+        double f1 = 1.0 + SGN[a][0] * xi[0];
+        double f2 = 1.0 + SGN[a][1] * xi[1];
+        double f3 = 1.0 + SGN[a][2] * xi[2];
+        N[a] = f1 * f2 * f3 / 8.0;
+        dNdxi[a][0] = SGN[a][0] * (f2 * f3 / 8.0);
+        dNdxi[a][1] = SGN[a][1] * (f1 * f3 / 8.0);
+        dNdxi[a][2] = SGN[a][2] * (f1 * f2 / 8.0);
+    }
+}
+
+// Cofactor inverse + determinant (Element_Utilities.f90:99-123 / abq_UEL_invert3d :573-608).
+// A[i][j] row i, column j.  Returns 0 on a zero determinant (the reference stops).
+static int invert3(const double A[3][3], double Ai[3][3], double* det) {
+    double d = A[0][0] * A[1][1] * A[2][2] - A[0][0] * A[1][2] * A[2][1] - A[0][1] * A[1][0] * A[2][2] +
+               A[0][1] * A[1][2] * A[2][0] + A[0][2] * A[1][0] * A[2][1] - A[0][2] * A[1][1] * A[2][0];
+    *det = d;
+    if (d == 0.0) return 0;
+    double C[3][3];
+    C[0][0] = +(A[1][1] * A[2][2] - A[1][2] * A[2][1]);
+    C[0][1] = -(A[1][0] * A[2][2] - A[1][2] * A[2][0]);
+    C[0][2] = +(A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+    C[1][0] = -(A[0][1] * A[2][2] - A[0][2] * A[2][1]);
+    C[1][1] = +(A[0][0] * A[2][2] - A[0][2] * A[2][0]);
+    C[1][2] = -(A[0][0] * A[2][1] - A[0][1] * A[2][0]);
+    C[2][0] = +(A[0][1] * A[1][2] - A[0][2] * A[1][1]);
+    C[2][1] = -(A[0][0] * A[1][2] - A[0][2] * A[1][0]);
+    C[2][2] = +(A[0][0] * A[1][1] - A[0][1] * A[1][0]);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Ai[i][j] = C[j][i] / d;
+    return 1;
+}
+
+// Geometry at one Gauss point: dNdx(8,3) = dNdxi * dxidx with dxdxi = x(3x8)*dNdxi(8x3)
+// (el_linelast_3Dbasic.f90:109-112).
+static int geometry(const double* coords24, int kint, double dNdx[8][3], double* det, double N[8]) {
+    double xi[3], dNdxi[8][3], J[3][3], Ji[3][3];
+    gauss_point(kint, xi);
+    shape_hex8(xi, N, dNdxi);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0;
+            for (int a = 0; a < 8; ++a) s += coords24[3 * a + i] * dNdxi[a][j];
+            J[i][j] = s;
+        }
+    if (!invert3(J, Ji, det)) return 0;
+    for (int a = 0; a < 8; ++a)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k) s += dNdxi[a][k] * Ji[k][j];
+            dNdx[a][j] = s;
+        }
+    return 1;
+}
+
+// B(6x24): rows e11,e22,e33,2e12,2e13,2e23 (el_linelast_3Dbasic.f90:113-122)
+static void bmatrix(const double dNdx[8][3], double B[6][24]) {
+    std::memset(B, 0, sizeof(double) * 6 * 24);
+    for (int a = 0; a < 8; ++a) {
+        B[0][3 * a + 0] = dNdx[a][0];
+        B[1][3 * a + 1] = dNdx[a][1];
+        B[2][3 * a + 2] = dNdx[a][2];
+        B[3][3 * a + 0] = dNdx[a][1];
+        B[3][3 * a + 1] = dNdx[a][0];
+        B[4][3 * a + 0] = dNdx[a][2];
+        B[4][3 * a + 2] = dNdx[a][0];
+        B[5][3 * a + 1] = dNdx[a][2];
+        B[5][3 * a + 2] = dNdx[a][1];
+    }
+}
+
+static void dmatrix(const double* props, double D[6][6]) {
+    // el_linelast_3Dbasic.f90:93-105
+    double E = props[0], xnu = props[1];
+    double d44 = 0.5 * E / (1 + xnu);
+    double d11 = (1.0 - xnu) * E / ((1 + xnu) * (1 - 2.0 * xnu));
+    double d12 = xnu * E / ((1 + xnu) * (1 - 2.0 * xnu));
+    std::memset(D, 0, sizeof(double) * 36);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) D[i][j] = d12;
+    D[0][0] = D[1][1] = D[2][2] = d11;
+    D[3][3] = D[4][4] = D[5][5] = d44;
+}
+
+static void accumulate_KR(const double B[6][24], const double D[6][6], const double stress[6], double wdet_w,
+                          double det, double* K, double* R) {
+    // R -= matmul(B^T, stress)*w*det ; K += matmul(B^T, matmul(D,B))*w*det  (el_linelast_3Dbasic.f90:128-131)
+    double DB[6][24];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 24; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 6; ++k) s += D[i][k] * B[k][j];
+            DB[i][j] = s;
+        }
+    for (int i = 0; i < 24; ++i) {
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) s += B[k][i] * stress[k];
+        R[i] = R[i] - s * wdet_w * det;
+    }
+    for (int j = 0; j < 24; ++j)
+        for (int i = 0; i < 24; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < 6; ++k) s += B[k][i] * DB[k][j];
+            K[i + 24 * j] = K[i + 24 * j] + s * wdet_w * det;
+        }
+}
+
+// Native element id 1001 (user_codes/src/el_linelast_3Dbasic.f90:79-133), hex8 branch only.
+void el_linelast_3dbasic(const double* coords24, const double* du24, const double* utot24,
+                         const double* props, double* K, double* R) {
+    double D[6][6], B[6][24], dNdx[8][3], N[8], det;
+    std::memset(K, 0, sizeof(double) * 576);
+    std::memset(R, 0, sizeof(double) * 24);
+    dmatrix(props, D);
+    for (int kint = 0; kint < 8; ++kint) {
+        if (!geometry(coords24, kint, dNdx, &det, N)) {
+            std::fprintf(stderr, "oracle: zero Jacobian determinant (Element_Utilities.f90:108-112)\n");
+            return;
+        }
+        bmatrix(dNdx, B);
+        double strain[6], dstrain[6], stress[6];
+        for (int i = 0; i < 6; ++i) {
+            double s = 0.0, ds = 0.0;
+            for (int k = 0; k < 24; ++k) s += B[i][k] * utot24[k];
+            for (int k = 0; k < 24; ++k) ds += B[i][k] * du24[k];
+            strain[i] = s;
+            dstrain[i] = ds;
+        }
+        for (int i = 0; i < 6; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < 6; ++k) s += D[i][k] * (strain[k] + dstrain[k]);
+            stress[i] = s;
+        }
+        accumulate_KR(B, D, stress, 1.0, det, K, R);
+    }
+}
+
+// Face node table for hex8, 1-based local nodes (Element_Utilities.f90:1102-1109 =
+// abq_facenodes_3D abaqus_uel_linelastic_3d.for:645-651).
+void facenodes_hex8(int face, int list[4]) {
+    static const int T[6][4] = {{1, 2, 3, 4}, {5, 8, 7, 6}, {1, 5, 6, 2}, {2, 6, 7, 3}, {3, 7, 8, 4}, {4, 8, 5, 1}};
+    for (int i = 0; i < 4; ++i) list[i] = T[face - 1][i];
+}
+
+// 2x2 face rule with the *proper double* abscissa (abaqus_uel_2D.for:190 = Element_Utilities.f90:486)
+static void face_gauss(int k, double xi[2]) {
+    const double cn = 0.5773502691896260;
+    static const int sx[4] = {-1, 1, 1, -1}, sy[4] = {-1, -1, 1, 1};
+    xi[0] = sx[k] * cn;
+    xi[1] = sy[k] * cn;
+}
+// 4-node quad shape functions (abaqus_uel_2D.for:311-334)
+static void shape_quad4(const double xi[2], double f[4], double df[4][2]) {
+    double g1 = 0.5 * (1.0 - xi[0]), g2 = 0.5 * (1.0 + xi[0]);
+    double h1 = 0.5 * (1.0 - xi[1]), h2 = 0.5 * (1.0 + xi[1]);
+    f[0] = g1 * h1; f[1] = g2 * h1; f[2] = g2 * h2; f[3] = g1 * h2;
+    const double dg1 = -0.5, dg2 = 0.5, dh1 = -0.5, dh2 = 0.5;
+    df[0][0] = dg1 * h1; df[1][0] = dg2 * h1; df[2][0] = dg2 * h2; df[3][0] = dg1 * h2;
+    df[0][1] = g1 * dh1; df[1][1] = g2 * dh1; df[2][1] = g2 * dh2; df[3][1] = g1 * dh2;
+}
+static void face_normal(const double* fc12, const double df[4][2], double norm[3]) {
+    double dx[3][2];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 2; ++j) {
+            double s = 0.0;
+            for (int a = 0; a < 4; ++a) s += fc12[3 * a + i] * df[a][j];
+            dx[i][j] = s;
+        }
+    // sign of norm(2) as written in the reference (abaqus_uel_linelastic_3d.for:228-230, Q2)
+    norm[0] = (dx[1][0] * dx[2][1]) - (dx[1][1] * dx[2][0]);
+    norm[1] = (dx[0][0] * dx[2][1]) - (dx[0][1] * dx[2][0]);
+    norm[2] = (dx[0][0] * dx[1][1]) - (dx[0][1] * dx[1][0]);
+}
+
+// ABAQUS-format UEL "U1" (user_codes/src/abaqus_uel_linelastic_3d.for:129-238), hex8 branch.
+// U24 = u + du as passed at solver_direct.f90:234.
+void uel_linelastic_3d(const double* coords24, const double* U24, const double* props, int nsvars,
+                       int ndload, const int* jdltyp, const double* adlmag, double* K, double* R,
+                       double* svars, double* energy8, double* pnewdt) {
+    double D[6][6], B[6][24], dNdx[8][3], N[8], det;
+    std::memset(K, 0, sizeof(double) * 576);
+    std::memset(R, 0, sizeof(double) * 24);
+    if (energy8) std::memset(energy8, 0, sizeof(double) * 8);
+    dmatrix(props, D);
+    for (int kint = 0; kint < 8; ++kint) {
+        if (!geometry(coords24, kint, dNdx, &det, N)) {
+            std::fprintf(stderr, "oracle: zero Jacobian determinant (abaqus_uel_linelastic_3d.for:589-593)\n");
+            return;
+        }
+        bmatrix(dNdx, B);
+        double strain[6], stress[6];
+        for (int i = 0; i < 6; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < 24; ++k) s += B[i][k] * U24[k];
+            strain[i] = s;
+        }
+        for (int i = 0; i < 6; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < 6; ++k) s += D[i][k] * strain[k];
+            stress[i] = s;
+        }
+        accumulate_KR(B, D, stress, 1.0, det, K, R);
+        if (energy8) {
+            double e = 0.0;
+            for (int i = 0; i < 6; ++i) e += stress[i] * strain[i];
+            energy8[1] = energy8[1] + 0.5 * e * 1.0 * det;                     // :190-191
+        }
+        if (svars && nsvars >= 48)
+            for (int i = 0; i < 6; ++i) svars[6 * kint + i] = stress[i];       // :193-195
+    }
+    if (pnewdt) *pnewdt = 1.0;                                                  // :199
+    // Distributed (pressure) loads :207-238.  The update at :234-235 multiplies N2(1:nfacenodes) by
+    // norm(1:3); scalarised over the 3-element left-hand side every face node receives
+    // (N2(1) n1, N2(2) n2, N2(3) n3).  Reproduced literally.
+    for (int j = 0; j < ndload; ++j) {
+        int list[4];
+        facenodes_hex8(jdltyp[j] < 0 ? -jdltyp[j] : jdltyp[j], list);
+        double fc[12];
+        for (int i = 0; i < 4; ++i)
+            for (int c = 0; c < 3; ++c) fc[3 * i + c] = coords24[3 * (list[i] - 1) + c];
+        for (int kint = 0; kint < 4; ++kint) {
+            double xi2[2], N2[4], dN2[4][2], norm[3];
+            face_gauss(kint, xi2);
+            shape_quad4(xi2, N2, dN2);
+            face_normal(fc, dN2, norm);
+            for (int i = 0; i < 4; ++i) {
+                int ip = 3 * (list[i] - 1);
+                for (int c = 0; c < 3; ++c) R[ip + c] = R[ip + c] - N2[c] * adlmag[j] * norm[c] * 1.0;
+            }
+        }
+    }
+}
+
+// Surface traction on a native-element face (src/traction_boundarycondition.f90:66-94), 3-D, 4-node face.
+// flag 1/2: traction vector given; flag 3: normal pressure traction(1).
+void traction_boundarycondition_static_3d(int flag, const double* fc12, const double* traction, int ntract,
+                                          double* R12) {
+    std::memset(R12, 0, sizeof(double) * 12);
+    for (int kint = 0; kint < 4; ++kint) {
+        double xi2[2], N2[4], dN2[4][2], norm[3];
+        face_gauss(kint, xi2);
+        shape_quad4(xi2, N2, dN2);
+        face_normal(fc12, dN2, norm);
+        double det = std::sqrt(norm[0] * norm[0] + norm[1] * norm[1] + norm[2] * norm[2]);
+        if (flag < 3) {
+            for (int k = 0; k < 3; ++k) {
+                double t = k < ntract ? traction[k] : 0.0;
+                for (int a = 0; a < 4; ++a) R12[3 * a + k] = R12[3 * a + k] + N2[a] * t * 1.0 * det;
+            }
+        } else {
+            for (int a = 0; a < 4; ++a)
+                for (int k = 0; k < 3; ++k) R12[3 * a + k] = R12[3 * a + k] - N2[a] * traction[0] * norm[k] * 1.0;
+        }
+    }
+}
+
+// History table interpolation (modules/Boundaryconditions.f90:161-221)
+double interpolate_history_table(const double* t, const double* v, int n, double time) {
+    if (n == 1) return v[0];
+    if (time <= t[0]) return v[0];
+    if (time >= t[n - 1]) return v[n - 1];
+    int klo = 0, khi = n - 1;
+    while (khi - klo > 1) {
+        int k = (khi + klo + 2) / 2 - 1;   // same midpoint as the 1-based (khi+klo)/2
+        if (t[k] > time) khi = k; else klo = k;
+    }
+    if (t[khi] == t[klo]) return 0.5 * (v[khi] + v[klo]);
+    return ((t[khi] - time) * v[klo] + (time - t[klo]) * v[khi]) / (t[khi] - t[klo]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Compressible neo-Hookean hex8 (total Lagrangian), W = mu/2 (Ibar1 - 3) + K/2 (J - 1)^2,
+// Ibar1 = J^(-2/3) tr(F^T F).  props = (mu, K [, ignored...]) as in
+// input_files/Abaqus_uel_hyperelastic.in:44 (G11..G44 ignored).  NOT in the reference (no
+// hyperelastic code is shipped): parity unpinned by the reference; pinned by the FD stiffness check
+// (checkstiffness.f90:481-532 criterion) and patch tests.  Same Gauss rule/shape functions as above.
+//   P = dW/dF = mu J^(-2/3) (F - I1/3 F^-T) + K (J-1) J F^-T
+//   R_ai = - sum_gp P_iJ dN_a/dX_J w|J0| ;  K_ai,bk = sum_gp dN_a/dX_J A_iJkL dN_b/dX_L w|J0|
+void el_neohooke_3d(const double* coords24, const double* U24, const double* props, double* K,
+                    double* R, double* svars, int* fail) {
+    const double mu = props[0], Kb = props[1];
+    std::memset(K, 0, sizeof(double) * 576);
+    std::memset(R, 0, sizeof(double) * 24);
+    *fail = 0;
+    for (int kint = 0; kint < 8; ++kint) {
+        double dNdX[8][3], N[8], det0;
+        if (!geometry(coords24, kint, dNdX, &det0, N)) { *fail = 1; return; }
+        double F[3][3], Fi[3][3], J;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = (i == j) ? 1.0 : 0.0;
+                for (int a = 0; a < 8; ++a) s += U24[3 * a + i] * dNdX[a][j];
+                F[i][j] = s;
+            }
+        if (!invert3(F, Fi, &J) || !(J > 0.0)) { *fail = 1; return; }
+        double I1 = 0.0;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) I1 += F[i][j] * F[i][j];
+        const double Jm23 = std::pow(J, -2.0 / 3.0);
+        double P[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double FiT = Fi[j][i];
+                P[i][j] = mu * Jm23 * (F[i][j] - I1 / 3.0 * FiT) + Kb * (J - 1.0) * J * FiT;
+            }
+        if (svars) {
+            // store Cauchy stress sigma = P F^T / J (6 components s11,s22,s33,s12,s13,s23)
+            double sg[3][3];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    double s = 0.0;
+                    for (int k = 0; k < 3; ++k) s += P[i][k] * F[j][k];
+                    sg[i][j] = s / J;
+                }
+            double* sv = svars + 6 * kint;
+            sv[0] = sg[0][0]; sv[1] = sg[1][1]; sv[2] = sg[2][2]; sv[3] = sg[0][1]; sv[4] = sg[0][2]; sv[5] = sg[1][2];
+        }
+        const double w = 1.0 * det0;
+        for (int a = 0; a < 8; ++a)
+            for (int i = 0; i < 3; ++i) {
+                double s = 0.0;
+                for (int j = 0; j < 3; ++j) s += P[i][j] * dNdX[a][j];
+                R[3 * a + i] -= s * w;
+            }
+        // material tangent A_iJkL = dP_iJ/dF_kL
+        //  = mu Jm23 [ d_ik d_JL - (2/3) F_iJ Fi_Lk - (2/3) Fi_Ji F_kL + (2/9) I1 Fi_Ji Fi_Lk + (I1/3) Fi_Jk Fi_Li ]
+        //  + K [ (2J-1) J Fi_Ji Fi_Lk - (J-1) J Fi_Jk Fi_Li ]
+        const double c1 = mu * Jm23, cJ = Kb * (2.0 * J - 1.0) * J, cK = Kb * (J - 1.0) * J;
+        for (int a = 0; a < 8; ++a)
+            for (int b = 0; b < 8; ++b)
+                for (int i = 0; i < 3; ++i)
+                    for (int k = 0; k < 3; ++k) {
+                        double s = 0.0;
+                        for (int Jx = 0; Jx < 3; ++Jx)
+                            for (int L = 0; L < 3; ++L) {
+                                double A = c1 * (((i == k && Jx == L) ? 1.0 : 0.0) -
+                                                 (2.0 / 3.0) * F[i][Jx] * Fi[L][k] -
+                                                 (2.0 / 3.0) * Fi[Jx][i] * F[k][L] +
+                                                 (2.0 / 9.0) * I1 * Fi[Jx][i] * Fi[L][k] +
+                                                 (I1 / 3.0) * Fi[Jx][k] * Fi[L][i]) +
+                                           cJ * Fi[Jx][i] * Fi[L][k] - cK * Fi[Jx][k] * Fi[L][i];
+                                s += dNdX[a][Jx] * A * dNdX[b][L];
+                            }
+                        K[(3 * a + i) + 24 * (3 * b + k)] += s * w;
+                    }
+    }
+}
+
+// Element dispatch + gather, mirroring solver_direct.f90:104-258 (gather :104-121, UEL :174-247,
+// native :250-256).  UEL distributed loads are generated as in generate_abaqus_dloads :798-912.
+int element_static(const Model& m, int lmn, const double* dof_total, const double* dof_increment,
+                   double time, double dtime, double* K, double* R, double* svars) {
+    double xc[24], du[24], ut[24];
+    for (int j = 0; j < 8; ++j) {
+        int n = m.connectivity[8 * lmn + j] - 1;
+        for (int k = 0; k < 3; ++k) {
+            xc[3 * j + k] = m.coords[3 * n + k];
+            du[3 * j + k] = dof_increment[3 * n + k];
+            ut[3 * j + k] = dof_total[3 * n + k];
+        }
+    }
+    const int flag = m.element_flag[lmn];
+    const double* props = m.element_properties.data() + m.element_prop_index[lmn];
+    if (flag == FLAG_C3D8) {
+        int mat = m.element_material[lmn] - 1;
+        c3d8_bbar_static(xc, du, ut, m.material_properties.data() + m.material_prop_index[mat],
+                         m.material_n_props[mat], dtime, K, R, svars, m.element_n_states[lmn]);
+        return 0;
+    }
+    if (flag > FLAG_UEL_BASE) {
+        double U[24];
+        for (int k = 0; k < 24; ++k) U[k] = du[k] + ut[k];          // solver_direct.f90:234
+        // distributed loads on this element, in load order (generate_abaqus_dloads)
+        int jdl[16];
+        double adl[16];
+        int nd = 0;
+        const int nloads = (int)m.dload_flag.size();
+        for (int load = 0; load < nloads; ++load) {
+            int es = m.dload_elset[load] - 1;
+            for (int k = m.elementset_ptr[es]; k < m.elementset_ptr[es + 1]; ++k) {
+                int e = m.elementset_elements[k] - 1;
+                if (m.element_flag[e] < FLAG_UEL_BASE) break;       // :848, :876 "exit"
+                if (e != lmn) continue;
+                double bc_val = m.dload_values[m.dload_val_ptr[load]];
+                int h = m.dload_history[load];
+                if (h > 0) {
+                    int o = m.history_ptr[h - 1], nh = m.history_ptr[h] - o;
+                    double v1 = interpolate_history_table(&m.history_time[o], &m.history_value[o], nh, time + dtime);
+                    bc_val = bc_val * v1;                            // :886-890
+                }
+                if (nd < 16) { jdl[nd] = m.dload_flag[load]; adl[nd] = bc_val; ++nd; }
+            }
+        }
+        const int jtype = flag - FLAG_UEL_BASE;
+        if (jtype == 1) {
+            double energy[8], pnewdt;
+            uel_linelastic_3d(xc, U, props, m.element_n_states[lmn], nd, jdl, adl, K, R, svars, energy, &pnewdt);
+            return 0;
+        } else if (jtype == 2) {
+            int fail = 0;
+            el_neohooke_3d(xc, U, props, K, R, svars, &fail);
+            return fail;
+        }
+        std::fprintf(stderr, "oracle: unknown UEL type U%d\n", jtype);
+        return 1;
+    }
+    if (flag == ID_LINELAST) {                                       // user_element.f90:62-69
+        el_linelast_3dbasic(xc, du, ut, props, K, R);
+        return 0;
+    }
+    if (flag == ID_NEOHOOKE) {
+        double U[24];
+        int fail = 0;
+        for (int k = 0; k < 24; ++k) U[k] = du[k] + ut[k];
+        el_neohooke_3d(xc, U, props, K, R, svars, &fail);
+        return fail;
+    }
+    std::fprintf(stderr, "oracle: invalid element type %d (user_element.f90:83-86)\n", flag);
+    return 1;
+}
+
+}  // namespace oracle

@@ -1,0 +1,45 @@
+"""Generates the committed fixtures under tests/golden/ (run in the build container, where /root/reference exists):
+
+  linear_elastic_3d_uel.in   re-emission (by the product's own writer, 17 significant digits, no comments) of the
+  holeplate_3d_uel.in.gz     mesh/BC/step data parsed from input_files/Abaqus_uel_linear_elastic_3d.in and
+                             input_files/Abaqus_uel_holeplate_3d.in — data fixtures, the GPU box has no /root/reference
+  *_oracle.npz               displacements, reaction forces and Newton history of the CPU oracle (skyline direct
+                             solver path) on those inputs
+"""
+import gzip
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+REF = "/root/reference/EN234_FEA/input_files"
+
+from en234_fea_b200 import Model  # noqa: E402
+import oracle_binding as ob  # noqa: E402
+
+for src, dst in [("Abaqus_uel_linear_elastic_3d.in", "linear_elastic_3d_uel.in"),
+                 ("Abaqus_uel_holeplate_3d.in", "holeplate_3d_uel.in.gz")]:
+    m = Model.read(os.path.join(REF, src))
+    text = m.text()
+    path = os.path.join(HERE, dst)
+    if dst.endswith(".gz"):
+        with gzip.GzipFile(path, "wb", mtime=0) as f:
+            f.write(text.encode())
+    else:
+        open(path, "w").write(text)
+    m2 = Model.from_text(text)
+    a, b = m.arrays(), m2.arrays()
+    for k in a:
+        if k in ("cg_tolerance", "max_cg_iterations", "checkstiffness_flag"):
+            continue
+        assert np.array_equal(a[k], b[k]), k
+    om = ob.OracleModel(a)
+    res = om.run_static()
+    np.savez_compressed(os.path.join(HERE, dst.split(".")[0] + "_oracle.npz"), dof_total=res["dof_total"],
+                        rforce=res["rforce"], newton=res["newton"], profile=np.array(res["profile"]), lu=res["lu"])
+    print(dst, "nodes", m.n_nodes, "elements", m.n_elements, "steps", res["n_steps"], "newton rows", len(res["newton"]))
+    print(res["newton"])

@@ -1,0 +1,158 @@
+"""ctypes binding of the CPU oracle (oracle/liben234oracle.so).  TEST INFRASTRUCTURE: imported only by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_lib = None
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_ROOT, "oracle", "liben234oracle.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.check_call(["make", "-j8"], cwd=os.path.join(_ROOT, "oracle"), stdout=subprocess.DEVNULL)
+        L = C.CDLL(path)
+        L.or_model_new.restype = C.c_void_p
+        L.or_model_free.argtypes = [C.c_void_p]
+        L.or_model_set_int.argtypes = [C.c_void_p, C.c_char_p, ip, C.c_long]
+        L.or_model_set_double.argtypes = [C.c_void_p, C.c_char_p, dp, C.c_long]
+        L.or_model_finalize.argtypes = [C.c_void_p]
+        L.or_system_new.restype = C.c_void_p
+        L.or_system_new.argtypes = [C.c_void_p, C.c_int]
+        L.or_system_free.argtypes = [C.c_void_p]
+        L.or_system_nnz_upper.restype = C.c_long
+        L.or_system_nnz_upper.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(ip)
+
+
+class OracleModel:
+    def __init__(self, arrays, **overrides):
+        L = lib()
+        self.h = C.c_void_p(L.or_model_new())
+        self.arrays = dict(arrays)
+        self.arrays.update({k: np.atleast_1d(v) for k, v in overrides.items()})
+        self._keep = []
+        for k, v in self.arrays.items():
+            if k == "checkstiffness_flag":
+                continue
+            if v.dtype.kind in "iu":
+                a = np.ascontiguousarray(v, dtype=np.int32)
+                rc = L.or_model_set_int(self.h, k.encode(), _i(a), a.size)
+            else:
+                a = np.ascontiguousarray(v, dtype=np.float64)
+                rc = L.or_model_set_double(self.h, k.encode(), _d(a), a.size)
+            if rc:
+                raise KeyError("oracle does not know field " + k)
+            self._keep.append(a)
+        rc = L.or_model_finalize(self.h)
+        if rc:
+            raise ValueError("oracle model invalid: %d" % rc)
+        self.n_nodes = int(self.arrays["n_nodes"][0])
+        self.n_elements = int(self.arrays["n_elements"][0])
+        self.ndof = 3 * self.n_nodes
+
+    def close(self):
+        if self.h:
+            lib().or_model_free(self.h)
+            self.h = None
+
+    def run_static(self):
+        L = lib()
+        u, rf = np.zeros(self.ndof), np.zeros(self.ndof)
+        newton, cg = np.zeros((4096, 8)), np.zeros(4096, np.int32)
+        info = (C.c_longlong * 10)()
+        lu = np.zeros((256, 3))
+        rc = L.or_run_static(self.h, _d(u), _d(rf), None, _d(newton), C.c_int(4096), _i(cg), C.c_int(4096), info, _d(lu),
+                             C.c_int(256))
+        if rc:
+            raise RuntimeError("oracle static step failed rc=%d" % rc)
+        return {"dof_total": u, "rforce": rf, "newton": newton[:info[2]].copy(), "cg_iterations": cg[:info[3]].copy(),
+                "n_steps": int(info[0]), "n_cutbacks": int(info[1]),
+                "profile": [int(info[k]) for k in range(4, 9)], "lu": lu[:info[9]].copy()}
+
+
+class OracleSystem:
+    """kind 1 = skyline direct (solver_direct.f90), 2 = COO conjugate gradient (solver_conjugate_gradient.f90)"""
+
+    def __init__(self, model, kind=2):
+        self.m = model
+        self.kind = kind
+        self.h = C.c_void_p(lib().or_system_new(model.h, C.c_int(kind)))
+
+    def close(self):
+        if self.h:
+            lib().or_system_free(self.h)
+            self.h = None
+
+    def assemble(self, dof_total, dof_increment, time=0.0, dtime=1.0):
+        ut, du = np.ascontiguousarray(dof_total, float), np.ascontiguousarray(dof_increment, float)
+        rf, norms = np.zeros(self.m.ndof), np.zeros(3)
+        fail = lib().or_system_assemble(self.h, _d(ut), _d(du), C.c_double(time), C.c_double(dtime), _d(rf), _d(norms), None)
+        return rf, norms[0], fail
+
+    def apply_bc(self, dof_total, dof_increment, time=0.0, dtime=1.0):
+        ut, du = np.ascontiguousarray(dof_total, float), np.ascontiguousarray(dof_increment, float)
+        norms = np.zeros(3)
+        lib().or_system_apply_bc(self.h, _d(ut), _d(du), C.c_double(time), C.c_double(dtime), _d(norms))
+        return norms[1]
+
+    def matrix(self):
+        """assembled matrix as scipy CSR (full symmetric) + rhs"""
+        import scipy.sparse as sp
+        n = self.m.ndof
+        nz = lib().or_system_nnz_upper(self.h)
+        rows, cols, a = np.zeros(nz, np.int32), np.zeros(nz, np.int32), np.zeros(nz)
+        diag, rhs = np.zeros(n), np.zeros(n)
+        lib().or_system_get_coo(self.h, _i(rows), _i(cols), _d(a), _d(diag), _d(rhs))
+        A = sp.coo_matrix((a, (rows, cols)), shape=(n, n)).tocsr()
+        return (A + A.T + sp.diags(diag)).tocsr(), rhs
+
+    def rhs(self):
+        n = self.m.ndof
+        diag, rhs = np.zeros(n), np.zeros(n)
+        lib().or_system_get_coo(self.h, None, None, None, _d(diag), _d(rhs))
+        return rhs, diag
+
+    def solve(self, dof_increment, tol=1e-17, maxit=1000, fixed_iters=-1):
+        du = np.ascontiguousarray(dof_increment, float).copy()
+        norms, its = np.zeros(3), C.c_int()
+        fail = lib().or_system_solve(self.h, C.c_double(tol), C.c_int(maxit), C.c_int(fixed_iters), _d(du), _d(norms), C.byref(its))
+        return du, norms[2], its.value, fail
+
+
+def element(flag, coords24, dof_increment24, dof_total24, props, jdltyp=None, adlmag=None):
+    K, R, sv, en = np.zeros(576), np.zeros(24), np.zeros(48), np.zeros(8)
+    jd = np.ascontiguousarray(jdltyp if jdltyp is not None else [], np.int32)
+    ad = np.ascontiguousarray(adlmag if adlmag is not None else [], float)
+    rc = lib().or_element(C.c_int(flag), _d(np.ascontiguousarray(coords24, float)), _d(np.ascontiguousarray(dof_increment24, float)),
+                          _d(np.ascontiguousarray(dof_total24, float)), _d(np.ascontiguousarray(props, float)), C.c_int(jd.size),
+                          _i(jd), _d(ad), _d(K), _d(R), _d(sv), _d(en))
+    if rc < 0:
+        raise ValueError("unknown element flag")
+    return K.reshape(24, 24).T.copy(), R, sv.reshape(8, 6), en, rc
+
+
+def check_stiffness(flag, coords24, dof_increment24, dof_total24, props):
+    err, asym = C.c_double(), C.c_double()
+    rc = lib().or_check_stiffness(C.c_int(flag), _d(np.ascontiguousarray(coords24, float)),
+                                  _d(np.ascontiguousarray(dof_increment24, float)), _d(np.ascontiguousarray(dof_total24, float)),
+                                  _d(np.ascontiguousarray(props, float)), C.byref(err), C.byref(asym))
+    if rc:
+        raise RuntimeError("oracle element failed")
+    return err.value, asym.value

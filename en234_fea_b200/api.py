@@ -47,6 +47,7 @@ GPU_SYMBOLS = [
     "en234gpu_download_state", "en234gpu_zero_increment_dev", "en234gpu_element_batch", "en234gpu_get_svars",
     "en234gpu_nnz_blocks", "en234gpu_get_csr", "en234gpu_get_rhs", "en234gpu_apply_operator",
     "en234gpu_get_unique_id", "en234gpu_comm_init", "en234gpu_set_partition", "en234gpu_get_stats",
+    "en234gpu_bench_operator",
 ]
 HOST_SYMBOLS = [
     "en234host_model_read", "en234host_model_from_text", "en234host_model_free", "en234host_last_error",
@@ -331,6 +332,11 @@ class GpuSystem:
         s = Stats()
         self._ck(gpu_lib().en234gpu_get_stats(self.h, C.byref(s)))
         return s
+
+    def bench_operator(self, method=0, warm=3, reps=20):
+        ms = C.c_double()
+        self._ck(gpu_lib().en234gpu_bench_operator(self.h, C.c_int(method), C.c_int(warm), C.c_int(reps), C.byref(ms)))
+        return ms.value
 
     # ---- multi-GPU
     @staticmethod

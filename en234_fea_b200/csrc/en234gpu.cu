@@ -710,4 +710,19 @@ int en234gpu_set_operator_mode(en234gpu_handle c, int method) {
 
 int en234gpu_get_stats(en234gpu_handle c, struct en234gpu_stats* s) { *s = c->st; return 0; }
 
+int en234gpu_bench_operator(en234gpu_handle c, int method, int warm, int reps, double* ms_per_launch) {
+    CK(cudaSetDevice(c->device));
+    if (method == EN234_SOLVE_PCG_BSR && !c->matrix_valid) return set_err("bench_operator: no assembled matrix");
+    for (int i = 0; i < warm; ++i) launch_operator(c, method, c->p.p, c->Ap.p, 0);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i) launch_operator(c, method, c->p.p, c->Ap.p, 0);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaGetLastError());
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    *ms_per_launch = (double)t / reps;
+    return 0;
+}
+
 }  // extern "C"

@@ -145,6 +145,10 @@ struct en234gpu_stats {
     double last_cg_err;          /* (r.r)/(b.b) at exit */
 };
 int en234gpu_get_stats(en234gpu_handle h, struct en234gpu_stats* s);
+/* average device time (ms, CUDA events on the handle's stream) of `reps` back-to-back launches of the operator
+ * kernel y = A p (method 0: block-CSR SpMV; 1: matrix-free apply) after `warm` untimed ones — the per-launch
+ * duration the roofline figures are computed from */
+int en234gpu_bench_operator(en234gpu_handle h, int method, int warm, int reps, double* ms_per_launch);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — static-step benchmark of the EN234_FEA hot path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            the CUDA path (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithms (the C++ oracle port — the
+                                                           Fortran reference cannot be compiled in this image) on host cores
+
+A step = one static (linear) step of the synthetic hex8 block: assemble -> apply BCs -> Jacobi-PCG solve ->
+re-assemble -> apply BCs -> convergence check (src/staticstep.f90:44-70 loop body).
+metric  = MDOF-CG-iters/s = n_dof x CG iterations / step seconds / 1e6  (whole job, all ranks)
+value   : inputs resident in HBM (device-resident entry points);  e2e : host-buffer C-ABI entry points with pinned host
+          arrays, host<->device copies inside the timed region.
+Workloads: N=1 -> BASELINE configs[1] (64^3); N>1 -> weak family with 64^3 elements per GPU, slabs along z
+          (N=8 is configs[2], 128^3).  --workload c3 forces the 128^3 block at any N.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "MDOF-CG-iters/s"
+CG_TOL = 1e-20          # squared ratio (r.r)/(b.b): ||r||/||b|| <= 1e-10, the north_star residual
+CG_MAXIT = 20000
+
+
+def workload(n_gpus, name):
+    if name == "c3":
+        return (128, 128, 128), "c3: synthetic 128^3 hex8 linear-elastic block (BASELINE configs[2])"
+    if name == "c2" or n_gpus == 1:
+        return (64, 64, 64), "c2: synthetic 64^3 hex8 linear-elastic cube, Jacobi-PCG (BASELINE configs[1])"
+    dims = {2: (64, 64, 128), 4: (64, 128, 128), 8: (128, 128, 128)}.get(n_gpus, (64, 64, 64 * n_gpus))
+    return dims, "weak: %dx%dx%d hex8 block, 64^3 elements per GPU, z-slabs%s" % (
+        dims + (" (= BASELINE configs[2])" if n_gpus == 8 else "",))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 5]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        try:
+            sm = sorted(float(r[0]) for r in rows)
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = float(rows[0][1])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            out["reasons"] = [n for k, n in enumerate(names) if any("Active" in r[2 + k] and "Not" not in r[2 + k] for r in rows)]
+            out["samples"] = len(rows)
+        except ValueError:
+            pass
+        return out
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU algorithms (COO Jacobi-PCG of src/solver_conjugate_gradient.f90:776-912 on
+    the system assembled by its element loop), restated in C++ (oracle/) because no Fortran compiler exists here.
+    Serial, like the reference (no OpenMP/MPI; module-level scratch makes its element routines non-re-entrant)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_binding as ob
+    from en234_fea_b200 import Model, synthetic_block_input
+    dims, wname = workload(args.gpus, args.workload)
+    its_per_step = args.ref_iters
+    t0 = time.time()
+    m = Model.from_text(synthetic_block_input(*dims, jitter=0.2, cg_tolerance=CG_TOL, cg_maxit=CG_MAXIT))
+    om = ob.OracleModel(m.arrays())
+    s = ob.OracleSystem(om, 2)
+    n = om.ndof
+    z = np.zeros(n)
+    t1 = time.time()
+    s.assemble(z, z, 0.0, 1.0)
+    t_asm = time.time() - t1
+    t1 = time.time()
+    s.apply_bc(z, z, 0.0, 1.0)
+    t_bc = time.time() - t1
+    times = []
+    for k in range(args.warmup + args.steps):
+        t1 = time.time()
+        s.solve(z, CG_TOL, CG_MAXIT, fixed_iters=its_per_step)
+        if k >= args.warmup:
+            times.append(time.time() - t1)
+    t_step = float(np.mean(times))
+    value = n * its_per_step / t_step / 1e6
+    sample = ("%d PCG iterations per step on the assembled %dx%dx%d system (COO upper-triangle SpMV, 1 thread); assembly %.1f s "
+              "and BC %.2f s done once outside the timed steps" % (its_per_step, dims[0], dims[1], dims[2], t_asm, t_bc))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "MDOF-it/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wname, "n_dof": n, "cg_iterations_per_step": its_per_step},
+            "cpu_baseline": {"value": value, "unit": "MDOF-it/s", "cores": 1, "kind": "port", "sample": sample,
+                             "host_cores_available": os.cpu_count(), "assemble_s": t_asm, "bc_s": t_bc,
+                             "setup_s": t1 - t0},
+            "e2e": {"value": value, "unit": "MDOF-it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(dims, gpu_iters):
+    """Bounded CPU sample for the N=1 line: one assembly + BC + a fixed window of PCG iterations of the same workload."""
+    import oracle_binding as ob
+    from en234_fea_b200 import Model, synthetic_block_input
+    m = Model.from_text(synthetic_block_input(*dims, jitter=0.2, cg_tolerance=CG_TOL, cg_maxit=CG_MAXIT))
+    om = ob.OracleModel(m.arrays())
+    s = ob.OracleSystem(om, 2)
+    n = om.ndof
+    z = np.zeros(n)
+    t1 = time.time(); s.assemble(z, z, 0.0, 1.0); t_asm = time.time() - t1
+    t1 = time.time(); s.apply_bc(z, z, 0.0, 1.0); t_bc = time.time() - t1
+    win = 200
+    s.solve(z, CG_TOL, CG_MAXIT, fixed_iters=2)
+    t1 = time.time(); s.solve(z, CG_TOL, CG_MAXIT, fixed_iters=win); t_it = (time.time() - t1) / win
+    # same step definition as the GPU line: 2 assemblies + 2 BC passes + gpu_iters PCG iterations
+    t_step = 2 * (t_asm + t_bc) + gpu_iters * t_it
+    return {"value": n * gpu_iters / t_step / 1e6, "unit": "MDOF-it/s", "cores": 1, "kind": "port",
+            "sample": "oracle (C++ port of the reference, 1 thread): 1 assembly (%.1f s) + BC (%.2f s) + %d PCG iterations "
+                      "(%.3f s each) of the same %dx%dx%d workload; step time extrapolated to 2 assemblies + %d iterations"
+                      % (t_asm, t_bc, win, t_it, dims[0], dims[1], dims[2], gpu_iters),
+            "pcg_iteration_only": n / t_it / 1e6, "host_cores_available": os.cpu_count()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3"])
+    ap.add_argument("--method", type=int, default=0, help="0 assembled block-CSR PCG, 1 matrix-free PCG")
+    ap.add_argument("--ref-iters", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from en234_fea_b200 import GpuSystem, Model, Partition, synthetic_block_input
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dims, wname = workload(world, args.workload)
+    model = Model.from_text(synthetic_block_input(*dims, jitter=0.2, cg_tolerance=CG_TOL, cg_maxit=CG_MAXIT))
+    ndof_global = 3 * model.n_nodes
+    fe, fx, fd, fv, fc = model.evaluate_loads(0.0, 1.0)
+    if world > 1:
+        part = Partition(model, world, rank)
+        gpu = GpuSystem(model, device=local, part=part)
+        uid = [GpuSystem.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        gpu.comm_init(world, rank, uid[0])
+        l2g = part.ints("local_to_global_node").astype(np.int64)
+        ldof = (3 * l2g[:, None] + np.arange(3)).ravel()
+        g2l = -np.ones(ndof_global, np.int64)
+        g2l[ldof] = np.arange(ldof.size)
+        fx = fx[ldof]
+        keep = g2l[fd] >= 0
+        fd, fv, fc = g2l[fd[keep]].astype(np.int32), fv[keep], fc[keep]
+    else:
+        gpu = GpuSystem(model, device=local)
+    gpu.set_operator_mode(args.method)
+    stream = torch.cuda.current_stream()
+    gpu.set_stream(stream.cuda_stream)
+    n = gpu.ndof
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+
+    _t_ut, ut = pinned(np.zeros(n)); _t_du, du = pinned(np.zeros(n)); _t_fx, fxp = pinned(fx)
+    _t_fd, fdp = pinned(fd.astype(np.int32)); _t_fc, fcp = pinned(fc); _t_fv, fvp = pinned(fv)
+    _t_rf, rfp = pinned(np.zeros(n))
+
+    def step_device():
+        gpu.zero_increment_dev()
+        _, fail = gpu.assemble_dev()
+        gpu.apply_boundaryconditions_dev()
+        _, its, sfail = gpu.solve_dev(args.method, CG_TOL, CG_MAXIT)
+        nrm, fail2 = gpu.assemble_dev()
+        unb = gpu.apply_boundaryconditions_dev()
+        assert not (fail or sfail or fail2), "device step failed"
+        return its, unb / nrm if nrm > 0 else 0.0
+
+    def step_host():
+        du[:] = 0.0
+        _, _, fail = gpu.assemble(ut, du, None, out_rforce=rfp)
+        gpu.apply_boundaryconditions(fxp, fdp, fcp)
+        _, corr, its, sfail = gpu.solve(du, args.method, CG_TOL, CG_MAXIT, inplace=True)
+        _, nrm, fail2 = gpu.assemble(ut, du, None, out_rforce=rfp)
+        fcp[:] = fvp - du[fdp]
+        gpu.apply_boundaryconditions(fxp, fdp, fcp)
+        assert not (fail or sfail or fail2), "host-API step failed"
+        return its
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            out = fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = gpu.stats().kernel_launches
+        e0.record(stream)
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps, out, gpu.stats().kernel_launches - l0
+
+    gpu.upload_state(ut, du, None, fx, fd, fv)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, (its, ratio), launches = timed(step_device, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if sampler else {}
+    ms_e2e, its_h, _ = timed(step_host, args.steps, 1)
+    value = ndof_global * its / (ms_dev * 1e-3) / 1e6
+    e2e = ndof_global * its_h / (ms_e2e * 1e-3) / 1e6
+    nfix = int(fd.size)
+    h2d = 2 * (2 * n * 8) + 2 * (n * 8 + nfix * 12) + n * 8
+    d2h = 2 * n * 8 + n * 8
+
+    # roofline of the dominant kernel (operator application inside PCG), measured live with CUDA events
+    peak, peak_src = peaks()
+    N_loc = gpu.n_nodes
+    if args.method == 0:
+        ms_op = gpu.bench_operator(0, 5, 50)
+        nnzb = gpu.nnz_blocks()
+        alg = 8 * 9 * nnzb + 4 * nnzb + 4 * (N_loc + 1) + 16 * n
+        kern = "k_spmv (3x3-block CSR, FP64)"
+        extra = {"algorithmic_bytes_scalar_csr": 12 * 9 * nnzb + 20 * n}
+    else:
+        ms_op = gpu.bench_operator(1, 5, 50)
+        alg = 72 * N_loc + 32 * (dims[0] * dims[1] * dims[2] // world)
+        kern = "k_mf_color x colours + k_mf_finish (matrix-free, FP64-bound on a general mesh)"
+        extra = {}
+    ach = alg / (ms_op * 1e-3) / 1e9
+    st = gpu.stats()
+    it_ms = st.solve_ms / max(st.last_cg_iterations, 1)
+    b_iter = (alg + 104 * n) if args.method == 0 else (alg + 104 * n)
+    roof = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "peak_source": peak_src, "traffic": None, "ms_per_launch": ms_op, "algorithmic_bytes_per_launch": alg,
+            "cg_iteration": {"ms": it_ms, "algorithmic_bytes": b_iter, "achieved": b_iter / (it_ms * 1e-3) / 1e9,
+                             "frac": b_iter / (it_ms * 1e-3) / 1e9 / peak},
+            "phases_ms": {"assemble": st.assemble_ms, "bc": st.bc_ms, "solve": st.solve_ms}}
+    roof.update(extra)
+
+    line = {"metric": METRIC, "value": value, "unit": "MDOF-it/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wname, "n_dof": ndof_global, "elements": dims[0] * dims[1] * dims[2], "jitter": 0.2,
+                       "cg_iterations": int(its), "cg_rule": "(r.r)/(b.b) < 1e-20", "final_newton_ratio": ratio,
+                       "method": "assembled 3x3-block CSR" if args.method == 0 else "matrix-free",
+                       "l2": "matrix stream per PCG iteration (%.0f MB) exceeds the 126 MB L2" % (alg / 1e6),
+                       "step": "assemble+BC+PCG solve+re-assemble+BC (src/staticstep.f90:44-70)"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e, "unit": "MDOF-it/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "roofline": roof}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample(dims, int(its))
+        print(json.dumps(line), flush=True)
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -54,7 +54,7 @@ HOST_SYMBOLS = [
     "en234host_model_int", "en234host_model_double", "en234host_model_find_set", "en234host_model_set",
     "en234host_model_write_text", "en234host_evaluate_loads", "en234host_gpu_create", "en234host_run_static",
     "en234host_partition", "en234host_part_free", "en234host_part_int", "en234host_part_owned",
-    "en234host_part_gpu_create",
+    "en234host_part_gpu_create", "en234host_run_static_part",
 ]
 
 
@@ -199,6 +199,7 @@ class GpuSystem:
         L = gpu_lib()
         self.h = C.c_void_p()
         self.model = model
+        self.part = part
         if part is not None:
             rc = host_lib().en234host_part_gpu_create(model.h, part.h, C.c_int(device), C.byref(self.h))
             err = host_lib().en234host_last_error
@@ -241,9 +242,9 @@ class GpuSystem:
         self._ck(gpu_lib().en234gpu_set_stream(self.h, C.c_void_p(cuda_stream)))
 
     # ---- host-buffer entry points
-    def assemble(self, dof_total, dof_increment, f_element_ext=None, want_rforce=True):
+    def assemble(self, dof_total, dof_increment, f_element_ext=None, want_rforce=True, out_rforce=None):
         ut, du, fe = _f64(dof_total), _f64(dof_increment), _f64(f_element_ext)
-        rf = np.zeros(self.ndof) if want_rforce else None
+        rf = out_rforce if out_rforce is not None else (np.zeros(self.ndof) if want_rforce else None)
         nrm, fail = C.c_double(), C.c_int()
         self._ck(gpu_lib().en234gpu_assemble(self.h, _dp(ut), _dp(du), _dp(fe), _dp(rf), C.byref(nrm), C.byref(fail)))
         return rf, nrm.value, fail.value
@@ -254,8 +255,8 @@ class GpuSystem:
         self._ck(gpu_lib().en234gpu_apply_boundaryconditions(self.h, _dp(fx), C.c_int(fd.size), _ip(fd), _dp(fc), C.byref(nrm)))
         return nrm.value
 
-    def solve(self, dof_increment, method=0, cg_tolerance=1e-17, max_cg_iterations=1000):
-        du = _f64(dof_increment).copy()
+    def solve(self, dof_increment, method=0, cg_tolerance=1e-17, max_cg_iterations=1000, inplace=False):
+        du = _f64(dof_increment) if inplace else _f64(dof_increment).copy()
         nrm, its, fail = C.c_double(), C.c_int(), C.c_int()
         self._ck(gpu_lib().en234gpu_solve(self.h, C.c_int(method), C.c_double(cg_tolerance), C.c_int(max_cg_iterations),
                                           _dp(du), C.byref(nrm), C.byref(its), C.byref(fail)))
@@ -357,10 +358,17 @@ class GpuSystem:
         newton, cg = np.zeros((4096, 8)), np.zeros(4096, np.int32)
         info = (C.c_longlong * 8)()
         self.set_operator_mode(method)
-        rc = host_lib().en234host_run_static(self.model.h, self.h, C.c_int(method), C.c_double(cg_tolerance),
-                                             C.c_int(max_cg_iterations), C.c_int(1 if check_linear_cg else 0),
-                                             C.c_int(1 if use_host_api else 0), _dp(u), _dp(rf), _dp(newton), C.c_int(4096),
-                                             _ip(cg), C.c_int(4096), info, os.fsencode(log_path) if log_path else None)
+        if self.part is not None:      # rank-local arrays; collective over all ranks
+            rc = host_lib().en234host_run_static_part(self.model.h, self.part.h, self.h, C.c_int(method),
+                                                      C.c_double(cg_tolerance), C.c_int(max_cg_iterations),
+                                                      C.c_int(1 if check_linear_cg else 0), C.c_int(1 if use_host_api else 0),
+                                                      _dp(u), _dp(rf), _dp(newton), C.c_int(4096), _ip(cg), C.c_int(4096), info,
+                                                      os.fsencode(log_path) if log_path else None)
+        else:
+            rc = host_lib().en234host_run_static(self.model.h, self.h, C.c_int(method), C.c_double(cg_tolerance),
+                                                 C.c_int(max_cg_iterations), C.c_int(1 if check_linear_cg else 0),
+                                                 C.c_int(1 if use_host_api else 0), _dp(u), _dp(rf), _dp(newton), C.c_int(4096),
+                                                 _ip(cg), C.c_int(4096), info, os.fsencode(log_path) if log_path else None)
         if rc:
             raise RuntimeError("static step failed: " + host_lib().en234host_last_error().decode())
         return {"dof_total": u, "rforce": rf, "newton": newton[:info[2]].copy(), "cg_iterations": cg[:info[3]].copy(),

@@ -69,7 +69,7 @@ struct en234gpu_ctx {
     // graphs
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     // launch geometry
-    int grid_rows = 0, grid_vec = 0;
+    int grid_asm = 0, grid_bc = 0, grid_spmv = 0, grid_vec = 0;
     size_t asm_smem = 0;
     // host copies needed for inspection
     std::vector<int> h_browptr, h_bcol;
@@ -231,7 +231,17 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
     // ---- launch geometry: persistent grids sized from the SM count (148 on B200)
     c->asm_smem = (size_t)WARPS * (GEOM_PER_WARP + ACC_PER_WARP) * sizeof(double);
     CK(cudaFuncSetAttribute(k_assemble_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->asm_smem));
-    c->grid_rows = std::min(MAX_PARTIALS, std::max(1, std::min((N + WARPS - 1) / WARPS, c->n_sm * 8)));
+    // persistent single-wave grids: SM count x resident CTAs per SM (a partial last wave leaves most of the chip idle)
+    {
+        int oa = 1, ob = 1, os = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oa, k_assemble_rows, THREADS, c->asm_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob, k_apply_bc, THREADS, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&os, k_spmv, THREADS, 0));
+        const int need = (N + WARPS - 1) / WARPS;
+        c->grid_asm = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(oa, 1))));
+        c->grid_bc = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(ob, 1))));
+        c->grid_spmv = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(os, 1))));
+    }
     c->grid_vec = std::min(MAX_PARTIALS, std::max(1, std::min((int)((nd + VEC_THREADS - 1) / VEC_THREADS), c->n_sm * 8)));
     if (any_neo) { delete c; return set_err("neo-Hookean element: device kernel not built into this library yet"); }
     int rc = mf_setup(c->mf, mesh_of(c), conn, N, E, c->n_sm, c->ndof);
@@ -296,21 +306,23 @@ int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail
     AsmArgs A;
     A.M = mesh_of(c);
     A.ut = c->ut.p; A.du = c->du.p;
-    A.felem = c->have_felem ? c->felem.p : nullptr;
+    // partitioned runs add the (full-valued) element load vector after the halo sum of the partial residuals
+    A.felem = (c->have_felem && !c->comm.active) ? c->felem.p : nullptr;
     A.val = c->val.p; A.rhs = c->rhs.p; A.rforce = c->rforce.p;
     A.partials = c->part.p; A.S = c->S.p;
     A.assemble_matrix = c->mode == EN234_SOLVE_PCG_BSR ? 1 : 0;
-    k_assemble_rows<<<c->grid_rows, THREADS, c->asm_smem, c->stream>>>(A);
+    k_assemble_rows<<<c->grid_asm, THREADS, c->asm_smem, c->stream>>>(A);
     c->st.kernel_launches++;
     CK(cudaGetLastError());
     c->matrix_valid = c->mode == EN234_SOLVE_PCG_BSR;
     c->rhs_valid = true;
     const double* part = c->part.p;
-    int npart = c->grid_rows;
+    int npart = c->grid_asm;
     if (c->comm.active) {
         // interface nodes hold partial sums: halo-sum rhs (and rforce = -rhs), then an owned-only norm
         if (comm_halo_sum(c->comm, c->rhs.p, c->stream)) return set_err(comm_error());
-        k_negate_norm<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(c->ndof, c->rhs.p, c->rforce.p, c->owned.p, c->part2.p);
+        k_negate_norm<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(c->ndof, c->rhs.p, c->have_felem ? c->felem.p : nullptr,
+                                                                   c->rforce.p, c->owned.p, c->part2.p);
         c->st.kernel_launches += c->comm.launches_per_halo + 1;
         part = c->part2.p; npart = c->grid_vec;
     }
@@ -357,7 +369,7 @@ static int apply_bc_common(en234gpu_ctx* c, int values_are_corrections, double* 
     B.fext = c->have_fext ? c->fext.p : nullptr;
     B.cflag = c->cflag.p; B.cval = c->cval.p; B.minv = c->minv.p; B.partials = c->part.p;
     const double* part = c->part.p;
-    int npart = c->grid_rows;
+    int npart = c->grid_bc;
     if (c->mode == EN234_SOLVE_PCG_MATRIXFREE) {
         // matrix-free: K[:,C] c is one application of the unmasked operator to the vector of prescribed corrections;
         // the Jacobi diagonal is integrated element by element
@@ -379,11 +391,11 @@ static int apply_bc_common(en234gpu_ctx* c, int values_are_corrections, double* 
     } else if (c->comm.active) {
         // the Jacobi diagonal and the rhs corrections of interface rows are partial sums on each rank:
         // apply to local rows, then halo-sum what is additive (see k_apply_bc_partitioned)
-        if (bc_partitioned(c->comm, B, c->grid_rows, c->grid_vec, c->ndof, c->owned.p, c->tmpvec.p, c->tmpvec2.p, c->part2.p,
+        if (bc_partitioned(c->comm, B, c->grid_bc, c->grid_vec, c->ndof, c->owned.p, c->tmpvec.p, c->tmpvec2.p, c->part2.p,
                            c->stream, &c->st.kernel_launches)) return set_err(comm_error());
         part = c->part2.p; npart = c->grid_vec;
     } else {
-        k_apply_bc<<<c->grid_rows, THREADS, 0, c->stream>>>(B);
+        k_apply_bc<<<c->grid_bc, THREADS, 0, c->stream>>>(B);
         c->st.kernel_launches++;
     }
     CK(cudaGetLastError());
@@ -403,7 +415,7 @@ static CgVecArgs vec_args(en234gpu_ctx* c, int method, int parity) {
     V.owned = c->have_owned ? c->owned.p : nullptr;
     V.sol = c->sol.p; V.r = c->r.p; V.p = c->p.p; V.Ap = c->Ap.p;
     V.part_pAp = c->part.p;
-    V.n_part_pAp = c->comm.active ? 1 : (method == EN234_SOLVE_PCG_MATRIXFREE ? c->mf.n_partials : c->grid_rows);
+    V.n_part_pAp = c->comm.active ? 1 : (method == EN234_SOLVE_PCG_MATRIXFREE ? c->mf.n_partials : c->grid_spmv);
     V.part_a = c->part2.p; V.part_b = c->part3.p;
     V.n_part = c->comm.active ? 1 : c->grid_vec;
     V.S = c->S.p;
@@ -419,7 +431,7 @@ static int launch_operator(en234gpu_ctx* c, int method, const double* x, double*
         SpmvArgs A;
         A.N = c->N; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
         A.partials = c->part.p; A.S = c->S.p; A.check_stop = check_stop;
-        k_spmv<<<c->grid_rows, THREADS, 0, c->stream>>>(A);
+        k_spmv<<<c->grid_spmv, THREADS, 0, c->stream>>>(A);
         c->st.kernel_launches++;
     }
     return 0;
@@ -431,7 +443,7 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
     if (c->comm.active) {
         // p.Ap: sum of local partial products over ALL local rows equals the global product (interface rows hold
         // partial sums and p agrees on both sides), so the all-reduce does not wait for the halo exchange
-        const int np = method == EN234_SOLVE_PCG_MATRIXFREE ? c->mf.n_partials : c->grid_rows;
+        const int np = method == EN234_SOLVE_PCG_MATRIXFREE ? c->mf.n_partials : c->grid_spmv;
         k_reduce_to<<<1, VEC_THREADS, 0, c->stream>>>(c->part.p, np, c->part.p);
         if (comm_allreduce_sum(c->comm, c->part.p, 1, c->stream)) return 1;
         if (comm_halo_sum(c->comm, c->Ap.p, c->stream)) return 1;

@@ -24,7 +24,7 @@ struct AsmArgs {
 // zeros of B and D removed.  The four groups then add their blocks to the row accumulator one after the other, so every
 // entry is summed in ascending element order like the reference's serial loop (solver_direct.f90:102): bitwise
 // run-to-run deterministic, no atomics.
-__global__ void __launch_bounds__(THREADS) k_assemble_rows(AsmArgs A) {
+__global__ void __launch_bounds__(THREADS, 2) k_assemble_rows(AsmArgs A) {
     extern __shared__ double sm[];
     __shared__ double red[WARPS + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, b = lane & 7;

@@ -24,39 +24,55 @@ struct SpmvArgs {
 // Lane q < 3*nb owns scalar column q of the block row: it gathers x_q once and reuses it for the three scalar
 // rows, whose values are read as three fully coalesced streams (streaming loads: the matrix is read once per
 // iteration and must not evict the vectors from L2).
+// The index loads are software-pipelined across the warp's rows (row pointers two rows ahead, block columns one row
+// ahead), so every load issued for a row is independent of the others: one memory latency per row instead of the
+// pointer -> column -> x chain.  Rows are interleaved over all warps of the (single-wave, persistent) grid so that the
+// rows in flight at any time are neighbours and their x entries hit in L2/L1.
 __global__ void __launch_bounds__(THREADS) k_spmv(SpmvArgs A) {
     __shared__ double red[WARPS + 1];
     if (A.check_stop && A.S->stop) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = gridDim.x * WARPS, N = A.N;
+    const int d0 = lane / 3, m0 = lane % 3;                  // q = lane      -> block d0, component m0
+    const int d1 = (lane + 32) / 3, m1 = (lane + 32) % 3;    // q = lane + 32
+    const int d2 = (lane + 64) / 3, m2 = (lane + 64) % 3;    // q = lane + 64
     double dot = 0.0;
-    for (int i = blockIdx.x * WARPS + warp; i < A.N; i += gridDim.x * WARPS) {
-        const int rb = A.browptr[i], nb = A.browptr[i + 1] - rb, L = 3 * nb;
+    int i = blockIdx.x * WARPS + warp;
+    int rb = 0, re = 0, rbn = 0, ren = 0, c0 = 0, c1 = 0, c2 = 0;
+    if (i < N) { rb = __ldg(A.browptr + i); re = __ldg(A.browptr + i + 1); }
+    if (i + W < N) { rbn = __ldg(A.browptr + i + W); ren = __ldg(A.browptr + i + W + 1); }
+    {
+        const int nb = re - rb;
+        if (d0 < nb) c0 = __ldg(A.bcol + rb + d0);
+        if (d1 < nb) c1 = __ldg(A.bcol + rb + d1);
+        if (d2 < nb) c2 = __ldg(A.bcol + rb + d2);
+    }
+    for (; i < N; i += W) {
+        const int nb = re - rb, L = 3 * nb;
         const double* v = A.val + 9 * (size_t)rb;
         double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-        if (L <= 96) {
-            // issue every load of the row before the first use (3 x-gathers + 9 streaming value loads per lane)
-            double xq[3], a0[3], a1[3], a2[3];
-#pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const int q = lane + 32 * t;
-                if (q < L) {
-                    const int j = 3 * __ldg(A.bcol + rb + q / 3) + q % 3;
-                    xq[t] = __ldg(A.x + j);
-                    a0[t] = __ldcs(v + q);
-                    a1[t] = __ldcs(v + L + q);
-                    a2[t] = __ldcs(v + 2 * L + q);
-                } else { xq[t] = 0.0; a0[t] = 0.0; a1[t] = 0.0; a2[t] = 0.0; }
-            }
-#pragma unroll
-            for (int t = 0; t < 3; ++t) { y0 += a0[t] * xq[t]; y1 += a1[t] * xq[t]; y2 += a2[t] * xq[t]; }
-        } else {
-            for (int q = lane; q < L; q += 32) {
-                const int j = 3 * __ldg(A.bcol + rb + q / 3) + q % 3;
-                const double xv = __ldg(A.x + j);
-                y0 += __ldcs(v + q) * xv;
-                y1 += __ldcs(v + L + q) * xv;
-                y2 += __ldcs(v + 2 * L + q) * xv;
-            }
+        // ---- loads of this row: 3 x-gathers + 9 streaming value loads per lane, all independent
+        double x0 = 0.0, x1 = 0.0, x2 = 0.0, a00 = 0.0, a01 = 0.0, a02 = 0.0, a10 = 0.0, a11 = 0.0, a12 = 0.0, a20 = 0.0,
+               a21 = 0.0, a22 = 0.0;
+        if (d0 < nb) { x0 = __ldg(A.x + 3 * c0 + m0); a00 = __ldcs(v + lane); a10 = __ldcs(v + L + lane); a20 = __ldcs(v + 2 * L + lane); }
+        if (d1 < nb) { x1 = __ldg(A.x + 3 * c1 + m1); a01 = __ldcs(v + lane + 32); a11 = __ldcs(v + L + lane + 32); a21 = __ldcs(v + 2 * L + lane + 32); }
+        if (d2 < nb) { x2 = __ldg(A.x + 3 * c2 + m2); a02 = __ldcs(v + lane + 64); a12 = __ldcs(v + L + lane + 64); a22 = __ldcs(v + 2 * L + lane + 64); }
+        // ---- prefetch: columns of the next row, pointers of the row after it
+        const int nbn = ren - rbn;
+        int cn0 = 0, cn1 = 0, cn2 = 0, rb2 = 0, re2 = 0;
+        if (d0 < nbn) cn0 = __ldg(A.bcol + rbn + d0);
+        if (d1 < nbn) cn1 = __ldg(A.bcol + rbn + d1);
+        if (d2 < nbn) cn2 = __ldg(A.bcol + rbn + d2);
+        if (i + 2 * W < N) { rb2 = __ldg(A.browptr + i + 2 * W); re2 = __ldg(A.browptr + i + 2 * W + 1); }
+        y0 = a00 * x0 + a01 * x1 + a02 * x2;
+        y1 = a10 * x0 + a11 * x1 + a12 * x2;
+        y2 = a20 * x0 + a21 * x1 + a22 * x2;
+        for (int q = lane + 96; q < L; q += 32) {            // rows with more than 32 blocks (unstructured meshes)
+            const int j = 3 * __ldg(A.bcol + rb + q / 3) + q % 3;
+            const double xv = __ldg(A.x + j);
+            y0 += __ldcs(v + q) * xv;
+            y1 += __ldcs(v + L + q) * xv;
+            y2 += __ldcs(v + 2 * L + q) * xv;
         }
         y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2);
         if (lane < 3) {
@@ -64,6 +80,7 @@ __global__ void __launch_bounds__(THREADS) k_spmv(SpmvArgs A) {
             A.y[3 * (size_t)i + lane] = yv;
             dot += yv * A.x[3 * (size_t)i + lane];
         }
+        rb = rbn; re = ren; rbn = rb2; ren = re2; c0 = cn0; c1 = cn1; c2 = cn2;
     }
     const double t = block_sum<THREADS>(dot, red);
     if (threadIdx.x == 0) A.partials[blockIdx.x] = t;

@@ -171,12 +171,13 @@ inline int comm_host_max(Comm& c, int* v) {
 }
 
 // ---- small kernels used only by the partitioned path -----------------------------------------------------------
-__global__ void __launch_bounds__(VEC_THREADS) k_negate_norm(int n, const double* rhs, double* rforce, const uint8_t* owned,
-                                                              double* partials) {
+__global__ void __launch_bounds__(VEC_THREADS) k_negate_norm(int n, double* rhs, const double* felem, double* rforce,
+                                                              const uint8_t* owned, double* partials) {
     __shared__ double red[VEC_THREADS / 32 + 1];
     double s = 0.0;
     for (int d = blockIdx.x * VEC_THREADS + threadIdx.x; d < n; d += gridDim.x * VEC_THREADS) {
-        const double r = rhs[d];
+        double r = rhs[d];
+        if (felem) { r += felem[d]; rhs[d] = r; }
         rforce[d] = -r;
         if (owned[d / 3]) s += r * r;
     }

@@ -197,6 +197,39 @@ int en234host_run_static(en234host_model_t w, en234gpu_handle h, int method, dou
     return rc;
 }
 
+// same loop on one rank of a partitioned run: DOF arrays are rank-local (length 3 * part n_nodes)
+int en234host_run_static_part(en234host_model_t w, en234host_part_t p, en234gpu_handle h, int method, double cg_tolerance,
+                              int max_cg_iterations, int check_linear_cg, int use_host_api, double* dof_total_local,
+                              double* rforce_local, double* newton, int max_rows, int* cg_iterations, int max_cg_rows,
+                              long long* info, const char* log_path) {
+    StepOptions o;
+    o.method = method; o.cg_tolerance = cg_tolerance; o.max_cg_iterations = max_cg_iterations;
+    o.check_linear_cg = check_linear_cg != 0; o.use_host_api = use_host_api != 0;
+    const auto& l2g = p->I["local_to_global_node"];
+    std::vector<int> g2l((size_t)w->m.ndof(), -1);
+    for (size_t i = 0; i < l2g.size(); ++i)
+        for (int c = 0; c < 3; ++c) g2l[3 * (size_t)l2g[i] + c] = (int)(3 * i + c);
+    const size_t nd = 3 * l2g.size();
+    StepResult r;
+    FILE* log = (log_path && p->rank == 0) ? std::fopen(log_path, "w") : nullptr;
+    int rc = compute_static_step(w->m, h, o, r, log, &g2l, nd);
+    if (log) std::fclose(log);
+    if (rc) g_err = r.error;
+    if (dof_total_local && r.dof_total.size() == nd) std::memcpy(dof_total_local, r.dof_total.data(), nd * sizeof(double));
+    if (rforce_local && r.rforce.size() == nd) std::memcpy(rforce_local, r.rforce.data(), nd * sizeof(double));
+    int nr = 0;
+    for (auto& q : r.newton) {
+        if (nr >= max_rows) break;
+        double* s = newton + 8 * nr++;
+        s[0] = q.step; s[1] = q.iteration; s[2] = q.correction_norm; s[3] = q.nodal_force_norm;
+        s[4] = q.unbalanced_force_norm; s[5] = q.ratio; s[6] = q.tolerance; s[7] = q.converged;
+    }
+    int nc = 0;
+    for (int it : r.cg_iterations) { if (nc >= max_cg_rows) break; cg_iterations[nc++] = it; }
+    if (info) { info[0] = r.n_steps_completed; info[1] = r.n_cutbacks; info[2] = nr; info[3] = nc; }
+    return rc;
+}
+
 // ---- element partition --------------------------------------------------------------------------------
 // Elements are split into n_ranks contiguous ranges of the element numbering (for the structured blocks of
 // user_mesh(), whose elements are numbered x-fastest then y then z, a range of whole z-layers is a slab).

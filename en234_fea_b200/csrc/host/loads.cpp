@@ -49,8 +49,10 @@ void face_coords(const Model& m, int lmn, int face, int nodes[4], double fc[4][3
 }  // namespace
 
 void evaluate_loads(const Model& m, double time, double dtime, const double* dof_total, const double* dof_increment,
-                    StepLoads& out) {
-    const size_t ndof = (size_t)m.ndof();
+                    StepLoads& out, const std::vector<int>* g2l, size_t n_local) {
+    // g2l (partitioned runs): global DOF -> rank-local DOF or -1; all outputs and the DOF arrays are then rank-local
+    const size_t ndof = g2l ? n_local : (size_t)m.ndof();
+    auto loc = [&](size_t gd) -> long { return g2l ? (long)(*g2l)[gd] : (long)gd; };
     out.element_ext.assign(ndof, 0.0);
     out.ext.assign(ndof, 0.0);
     out.fixed_dof.clear();
@@ -78,7 +80,10 @@ void evaluate_loads(const Model& m, double time, double dtime, const double* dof
                     // abaqus_uel_linelastic_3d.for:232-236 as the compiler scalarises it: every face
                     // node receives (N2(1) n1, N2(2) n2, N2(3) n3)
                     for (int i = 0; i < 4; ++i)
-                        for (int c = 0; c < 3; ++c) out.element_ext[3 * (size_t)nodes[i] + c] -= fp.N[c] * mag * fp.norm[c];
+                        for (int c = 0; c < 3; ++c) {
+                            const long ld = loc(3 * (size_t)nodes[i] + c);
+                            if (ld >= 0) out.element_ext[ld] -= fp.N[c] * mag * fp.norm[c];
+                        }
                 }
                 out.any_element_ext = true;
             } else {
@@ -101,8 +106,10 @@ void evaluate_loads(const Model& m, double time, double dtime, const double* dof
                     const double det = std::sqrt(fp.norm[0] * fp.norm[0] + fp.norm[1] * fp.norm[1] + fp.norm[2] * fp.norm[2]);
                     for (int a = 0; a < 4; ++a)
                         for (int c = 0; c < 3; ++c) {
-                            if (d.flag < 3) out.ext[3 * (size_t)nodes[a] + c] += fp.N[a] * tr[c] * det;
-                            else out.ext[3 * (size_t)nodes[a] + c] -= fp.N[a] * tr[0] * fp.norm[c];
+                            const long ld = loc(3 * (size_t)nodes[a] + c);
+                            if (ld < 0) continue;
+                            if (d.flag < 3) out.ext[ld] += fp.N[a] * tr[c] * det;
+                            else out.ext[ld] -= fp.N[a] * tr[0] * fp.norm[c];
                         }
                 }
                 out.any_ext = true;
@@ -112,15 +119,18 @@ void evaluate_loads(const Model& m, double time, double dtime, const double* dof
 
     for (const auto& p : m.prescribed_forces) {
         double fv = p.flag == 1 ? p.value : interpolate_history_table(m.histories[p.history_number - 1], time + dtime);
-        if (p.node_set == 0) out.ext[3 * (size_t)(p.node_number - 1) + p.dof - 1] += fv;
-        else for (int n : m.nodesets[p.node_set - 1].items) out.ext[3 * (size_t)(n - 1) + p.dof - 1] += fv;
+        auto addf = [&](int n) { const long ld = loc(3 * (size_t)(n - 1) + p.dof - 1); if (ld >= 0) out.ext[ld] += fv; };
+        if (p.node_set == 0) addf(p.node_number);
+        else for (int n : m.nodesets[p.node_set - 1].items) addf(n);
         out.any_ext = true;
     }
 
     for (const auto& p : m.prescribed_dofs) {
         double v = p.flag == 1 ? p.value : interpolate_history_table(m.histories[p.history_number - 1], time + dtime);
         auto one = [&](int n) {
-            const int d = 3 * (n - 1) + p.dof - 1;
+            const long ld = loc(3 * (size_t)(n - 1) + p.dof - 1);
+            if (ld < 0) return;
+            const int d = (int)ld;
             double target = v;
             // RATE: the value prescribes the increment (solver_direct.f90:706-708); expressed as a target for
             // dof_total + dof_increment so the device forms one kind of correction

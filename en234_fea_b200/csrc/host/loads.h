@@ -14,7 +14,9 @@ struct StepLoads {
     bool any_element_ext = false, any_ext = false;
 };
 
+// g2l != null (partitioned runs): map global DOF -> rank-local DOF (-1 = not on this rank); outputs and the DOF
+// arrays are then rank-local with n_local entries
 void evaluate_loads(const Model& m, double time, double dtime, const double* dof_total, const double* dof_increment,
-                    StepLoads& out);
+                    StepLoads& out, const std::vector<int>* g2l = nullptr, size_t n_local = 0);
 
 }  // namespace en234

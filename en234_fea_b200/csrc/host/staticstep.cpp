@@ -90,8 +90,11 @@ static int assemble_and_bc(en234gpu_handle h, const Model& m, const StepOptions&
     return 0;
 }
 
-int compute_static_step(const Model& m, en234gpu_handle h, const StepOptions& opt, StepResult& res, FILE* log) {
-    const size_t ndof = (size_t)m.ndof();
+int compute_static_step(const Model& m, en234gpu_handle h, const StepOptions& opt, StepResult& res, FILE* log,
+                        const std::vector<int>* g2l, size_t n_local) {
+    // partitioned runs: every rank executes this same loop on its rank-local DOF arrays; the norms returned by the
+    // device entry points are global (all-reduced), so all ranks take identical step/cutback decisions
+    const size_t ndof = g2l ? n_local : (size_t)m.ndof();
     res.dof_total.assign(ndof, 0.0);
     res.rforce.assign(ndof, 0.0);
     std::vector<double> dof_increment(ndof, 0.0);
@@ -108,7 +111,7 @@ int compute_static_step(const Model& m, en234gpu_handle h, const StepOptions& op
     int guard = 0;
     while (cont) {
         if (++guard > 100000) { res.error = "time stepping did not terminate"; return 2; }
-        evaluate_loads(m, t.TIME, t.DTIME, res.dof_total.data(), dof_increment.data(), L);
+        evaluate_loads(m, t.TIME, t.DTIME, res.dof_total.data(), dof_increment.data(), L, g2l, n_local);
         if (!opt.use_host_api &&
             en234gpu_upload_state(h, res.dof_total.data(), dof_increment.data(), L.any_element_ext ? L.element_ext.data() : nullptr,
                                   L.any_ext ? L.ext.data() : nullptr, (int)L.fixed_dof.size(), L.fixed_dof.data(),

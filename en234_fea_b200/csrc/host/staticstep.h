@@ -32,6 +32,7 @@ struct StepResult {
     std::string error;
 };
 
-int compute_static_step(const Model& m, en234gpu_handle h, const StepOptions& opt, StepResult& res, FILE* log);
+int compute_static_step(const Model& m, en234gpu_handle h, const StepOptions& opt, StepResult& res, FILE* log,
+                        const std::vector<int>* g2l = nullptr, size_t n_local = 0);
 
 }  // namespace en234

@@ -72,6 +72,12 @@ int en234host_part_int(en234host_part_t p, const char* name, const int** ptr, lo
 const unsigned char* en234host_part_owned(en234host_part_t p);
 /* device handle for one partition (local mesh + halo already registered; call en234gpu_comm_init next) */
 int en234host_part_gpu_create(en234host_model_t m, en234host_part_t p, int device, en234gpu_handle* h);
+/* en234host_run_static on one rank of a partitioned run (all ranks call it collectively): dof_total / rforce are the
+ * rank-local arrays (3 * part n_nodes, local node order); norms, Newton records and CG counts are global */
+int en234host_run_static_part(en234host_model_t m, en234host_part_t p, en234gpu_handle h, int method,
+                              double cg_tolerance, int max_cg_iterations, int check_linear_cg, int use_host_api,
+                              double* dof_total_local, double* rforce_local, double* newton, int max_rows,
+                              int* cg_iterations, int max_cg_rows, long long* info, const char* log_path);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,67 @@
+"""Multi-GPU parity check, launched as one process per GPU:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
+Every rank runs the partitioned static step (NCCL halo sums + all-reduced dot products); rank 0 also solves the whole
+mesh on its own GPU and compares displacements / reaction forces (<= 1e-10 relative) and CG iteration counts."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from en234_fea_b200 import GpuSystem, Model, Partition, synthetic_block_input  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dims = tuple(int(x) for x in (sys.argv[1:4] if len(sys.argv) >= 4 else (12, 10, 8 * world)))
+    ok = True
+    for method in (0, 1):
+        for load in ("traction", "stretch"):
+            m = Model.from_text(synthetic_block_input(*dims, jitter=0.2, cg_tolerance=1e-26, cg_maxit=20000, load=load,
+                                                      steps=2 if load == "stretch" else 1))
+            part = Partition(m, world, rank)
+            g = GpuSystem(m, device=local, part=part)
+            uid = [GpuSystem.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            g.comm_init(world, rank, uid[0])
+            res = g.run_static(method=method, check_linear_cg=True)
+            l2g = part.ints("local_to_global_node").astype(np.int64)
+            ldof = (3 * l2g[:, None] + np.arange(3)).ravel()
+            # gather the distributed fields on rank 0 (owned entries win; shared copies must agree)
+            ug = torch.zeros(3 * m.n_nodes, dtype=torch.float64, device="cuda")
+            rg = torch.zeros_like(ug)
+            cnt = torch.zeros_like(ug)
+            idx = torch.from_numpy(ldof).cuda()
+            ug[idx] = torch.from_numpy(res["dof_total"]).cuda()
+            rg[idx] = torch.from_numpy(res["rforce"]).cuda()
+            cnt[idx] = 1.0
+            dist.all_reduce(ug); dist.all_reduce(rg); dist.all_reduce(cnt)
+            ug, rg = (ug / cnt).cpu().numpy(), (rg / cnt).cpu().numpy()
+            # shared copies agree bit for bit => dividing the sum by the count reproduces each copy
+            agree = np.array_equal(ug[ldof], res["dof_total"]) or np.abs(ug[ldof] - res["dof_total"]).max() <= 1e-15 * np.abs(ug).max()
+            if rank == 0:
+                g1 = GpuSystem(m, device=local)
+                ref = g1.run_static(method=0, check_linear_cg=True)
+                eu = np.abs(ug - ref["dof_total"]).max() / np.abs(ref["dof_total"]).max()
+                er = np.abs(rg - ref["rforce"]).max() / np.abs(ref["rforce"]).max()
+                its, its1 = res["cg_iterations"].tolist(), ref["cg_iterations"].tolist()
+                good = eu < 1e-10 and er < 1e-10 and all(abs(a - b) <= 2 for a, b in zip(its, its1)) and \
+                    res["newton"].shape == ref["newton"].shape and agree
+                print("mgpu_check world=%d mesh=%s method=%d load=%s: u err %.2e, rforce err %.2e, CG its %s vs %s, copies agree %s -> %s"
+                      % (world, dims, method, load, eu, er, its, its1, agree, "OK" if good else "FAIL"), flush=True)
+                ok = ok and good
+                g1.close()
+            g.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()

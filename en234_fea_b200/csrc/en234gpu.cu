@@ -71,6 +71,8 @@ struct en234gpu_ctx {
     // launch geometry
     int grid_asm = 0, grid_bc = 0, grid_spmv = 0, grid_vec = 0;
     size_t asm_smem = 0;
+    int asm_threads = THREADS;
+    bool any_neo = false;
     // host copies needed for inspection
     std::vector<int> h_browptr, h_bcol;
     // multi-GPU
@@ -229,21 +231,25 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
     std::memset(c->hS, 0, sizeof(CgScalars));
 
     // ---- launch geometry: persistent grids sized from the SM count (148 on B200)
-    c->asm_smem = (size_t)WARPS * (GEOM_PER_WARP + ACC_PER_WARP) * sizeof(double);
-    CK(cudaFuncSetAttribute(k_assemble_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->asm_smem));
+    c->any_neo = any_neo;
+    c->asm_smem = any_neo ? AsmCfg<true>::SMEM : AsmCfg<false>::SMEM;
+    c->asm_threads = (any_neo ? AsmCfg<true>::NW : AsmCfg<false>::NW) * 32;
+    if (any_neo) CK(cudaFuncSetAttribute(k_assemble_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->asm_smem));
+    else CK(cudaFuncSetAttribute(k_assemble_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->asm_smem));
     // persistent single-wave grids: SM count x resident CTAs per SM (a partial last wave leaves most of the chip idle)
     {
         int oa = 1, ob = 1, os = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oa, k_assemble_rows, THREADS, c->asm_smem));
+        if (any_neo) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oa, k_assemble_rows<true>, c->asm_threads, c->asm_smem));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oa, k_assemble_rows<false>, c->asm_threads, c->asm_smem));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob, k_apply_bc, THREADS, 0));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&os, k_spmv, THREADS, 0));
         const int need = (N + WARPS - 1) / WARPS;
-        c->grid_asm = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(oa, 1))));
+        const int need_asm = (N + c->asm_threads / 32 - 1) / (c->asm_threads / 32);
+        c->grid_asm = std::min(MAX_PARTIALS, std::max(1, std::min(need_asm, c->n_sm * std::max(oa, 1))));
         c->grid_bc = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(ob, 1))));
         c->grid_spmv = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(os, 1))));
     }
     c->grid_vec = std::min(MAX_PARTIALS, std::max(1, std::min((int)((nd + VEC_THREADS - 1) / VEC_THREADS), c->n_sm * 8)));
-    if (any_neo) { delete c; return set_err("neo-Hookean element: device kernel not built into this library yet"); }
     int rc = mf_setup(c->mf, mesh_of(c), conn, N, E, c->n_sm, c->ndof);
     if (rc) { delete c; return set_err("matrix-free set-up failed"); }
     *out = c;
@@ -311,7 +317,8 @@ int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail
     A.val = c->val.p; A.rhs = c->rhs.p; A.rforce = c->rforce.p;
     A.partials = c->part.p; A.S = c->S.p;
     A.assemble_matrix = c->mode == EN234_SOLVE_PCG_BSR ? 1 : 0;
-    k_assemble_rows<<<c->grid_asm, THREADS, c->asm_smem, c->stream>>>(A);
+    if (c->any_neo) k_assemble_rows<true><<<c->grid_asm, c->asm_threads, c->asm_smem, c->stream>>>(A);
+    else k_assemble_rows<false><<<c->grid_asm, c->asm_threads, c->asm_smem, c->stream>>>(A);
     c->st.kernel_launches++;
     CK(cudaGetLastError());
     c->matrix_valid = c->mode == EN234_SOLVE_PCG_BSR;
@@ -485,6 +492,8 @@ int en234gpu_solve_dev(en234gpu_handle c, int method, double cg_tolerance, int m
     if (method != EN234_SOLVE_PCG_BSR && method != EN234_SOLVE_PCG_MATRIXFREE) return set_err("unknown solve method");
     if (method == EN234_SOLVE_PCG_BSR && !c->matrix_valid) return set_err("solve called before assemble");
     if (method != c->mode) return set_err("solve method differs from the operator mode (en234gpu_set_operator_mode)");
+    if (method == EN234_SOLVE_PCG_MATRIXFREE && c->any_neo)
+        return set_err("the matrix-free operator covers the linear-elastic elements only (1001 / U1)");
     if (phase_begin(c)) return 1;
     if (!c->graph[method] && build_graph(c, method)) return 1;
     // tolerance / iteration cap are run-time values in device memory (compile-time in modules/Stiffness.f90:35-37)

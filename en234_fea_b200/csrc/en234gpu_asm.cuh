@@ -24,16 +24,28 @@ struct AsmArgs {
 // zeros of B and D removed.  The four groups then add their blocks to the row accumulator one after the other, so every
 // entry is summed in ascending element order like the reference's serial loop (solver_direct.f90:102): bitwise
 // run-to-run deterministic, no atomics.
-__global__ void __launch_bounds__(THREADS, 2) k_assemble_rows(AsmArgs A) {
+// NEO = true adds the compressible neo-Hookean element (material kind 1) with its larger per-point record; meshes
+// without such elements run the NEO = false instantiation.
+template <bool NEO>
+struct AsmCfg {
+    static constexpr int NW = NEO ? 4 : WARPS;                       // warps per CTA
+    static constexpr int GS = NEO ? GEOM_STRIDE_NEO : GEOM_STRIDE;   // doubles per Gauss point record
+    static constexpr int PER_WARP = 4 * 8 * GS + ACC_PER_WARP;
+    static constexpr size_t SMEM = (size_t)NW * PER_WARP * sizeof(double);
+};
+
+template <bool NEO>
+__global__ void __launch_bounds__(AsmCfg<NEO>::NW * 32, NEO ? 1 : 2) k_assemble_rows(AsmArgs A) {
+    constexpr int NW = AsmCfg<NEO>::NW, GS = AsmCfg<NEO>::GS;
     extern __shared__ double sm[];
-    __shared__ double red[WARPS + 1];
+    __shared__ double red[NW + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, b = lane & 7;
-    double* geom = sm + (size_t)warp * (GEOM_PER_WARP + ACC_PER_WARP);
-    double* accs = geom + GEOM_PER_WARP;
+    double* geom = sm + (size_t)warp * AsmCfg<NEO>::PER_WARP;
+    double* accs = geom + 4 * 8 * GS;
     const Mesh& M = A.M;
     double norm2 = 0.0;
     bool bad = false;
-    for (int i = blockIdx.x * WARPS + warp; i < M.N; i += gridDim.x * WARPS) {
+    for (int i = blockIdx.x * NW + warp; i < M.N; i += gridDim.x * NW) {
         const int k0 = M.adj_ptr[i], k1 = M.adj_ptr[i + 1];
         const int rb = M.browptr[i], nb = M.browptr[i + 1] - rb, L = 3 * nb;
         double* acc = (nb <= MAXNB) ? accs : A.val + 9 * (size_t)rb;
@@ -48,14 +60,23 @@ __global__ void __launch_bounds__(THREADS, 2) k_assemble_rows(AsmArgs A) {
             const int ea = M.adj[valid ? k : k0];
             const int e = ea >> 3, a = ea & 7;
             const Material mat = M.mats[M.mat[e]];
-            double* gg = geom + (g * 8 + b) * GEOM_STRIDE;
+            double* gg = geom + (g * 8 + b) * GS;
             GpOut gp;
             gauss_point_eval(M, e, b, LoadSum{A.ut, A.du}, gg, gp);
             if (valid && !(gp.det != 0.0)) bad = true;          // zero / NaN Jacobian (Element_Utilities.f90:108-112)
-            __syncwarp();
             // ---- residual of node a: -sum_gp w|J| sigma . grad N_a      (el_linelast_3Dbasic.f90:128)
             double s[9];
-            stress_linear(mat, gp.H, s);
+            if (NEO && mat.kind == 1) {
+                NeoPoint np;
+                neo_eval(mat, gp.H, gp.det, np);
+                neo_node_vectors(np, gg);
+                if (valid && !(np.J > 0.0)) bad = true;          // inverted element: cut the step back
+#pragma unroll
+                for (int q = 0; q < 9; ++q) s[q] = np.P[q];
+            } else {
+                stress_linear(mat, gp.H, s);
+            }
+            __syncwarp();
             const double da0 = gg[3 * a], da1 = gg[3 * a + 1], da2 = gg[3 * a + 2];
             double r0 = -(s[0] * da0 + s[1] * da1 + s[2] * da2) * gp.det;
             double r1 = -(s[3] * da0 + s[4] * da1 + s[5] * da2) * gp.det;
@@ -75,27 +96,34 @@ __global__ void __launch_bounds__(THREADS, 2) k_assemble_rows(AsmArgs A) {
             }
             if (A.assemble_matrix) {
                 // ---- block K_e[a][b]
-                double S[9];
-#pragma unroll
-                for (int q = 0; q < 9; ++q) S[q] = 0.0;
-                const double* ge = geom + g * 8 * GEOM_STRIDE;
-#pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const double* gq = ge + p * GEOM_STRIDE;
-                    const double w = gq[24];
-                    const double a0 = w * gq[3 * a], a1 = w * gq[3 * a + 1], a2 = w * gq[3 * a + 2];
-                    const double b0 = gq[3 * b], b1 = gq[3 * b + 1], b2 = gq[3 * b + 2];
-                    S[0] += a0 * b0; S[1] += a0 * b1; S[2] += a0 * b2;
-                    S[3] += a1 * b0; S[4] += a1 * b1; S[5] += a1 * b2;
-                    S[6] += a2 * b0; S[7] += a2 * b1; S[8] += a2 * b2;
-                }
-                const double lam = mat.d12, mu = mat.d44;
-                const double tr = mu * (S[0] + S[4] + S[8]);
                 double K[9];
+                const double* ge = geom + g * 8 * GS;
+                if (NEO && mat.kind == 1) {
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+                    for (int q = 0; q < 9; ++q) K[q] = 0.0;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) K[3 * r + c] = lam * S[3 * r + c] + mu * S[3 * c + r] + (r == c ? tr : 0.0);
+                    for (int p = 0; p < 8; ++p) neo_block_acc(ge + p * GS, a, b, K);
+                } else {
+                    double S[9];
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) S[q] = 0.0;
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        const double* gq = ge + p * GS;
+                        const double w = gq[G_W];
+                        const double a0 = w * gq[3 * a], a1 = w * gq[3 * a + 1], a2 = w * gq[3 * a + 2];
+                        const double b0 = gq[3 * b], b1 = gq[3 * b + 1], b2 = gq[3 * b + 2];
+                        S[0] += a0 * b0; S[1] += a0 * b1; S[2] += a0 * b2;
+                        S[3] += a1 * b0; S[4] += a1 * b1; S[5] += a1 * b2;
+                        S[6] += a2 * b0; S[7] += a2 * b1; S[8] += a2 * b2;
+                    }
+                    const double lam = mat.d12, mu = mat.d44;
+                    const double tr = mu * (S[0] + S[4] + S[8]);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) K[3 * r + c] = lam * S[3 * r + c] + mu * S[3 * c + r] + (r == c ? tr : 0.0);
+                }
                 const int sl = valid ? M.slot[(size_t)k * 8 + b] : 0;
 #pragma unroll
                 for (int gs = 0; gs < 4; ++gs) {
@@ -125,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_assemble_rows(AsmArgs A) {
         __syncwarp();
     }
     if (bad) atomicOr(&A.S->nanflag, 1);
-    const double t = block_sum<THREADS>(norm2, red);
+    const double t = block_sum<NW * 32>(norm2, red);
     if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
 }
 

@@ -1,4 +1,4 @@
-// Auxiliary kernels: batched element plugin evaluation (tests / CHECK STIFFNESS), Gauss-point state, layout helpers.
+// Auxiliary kernels: batched element plugin evaluation (tests / CHECK STIFFNESS), Gauss-point state.
 #pragma once
 #include "en234gpu_kernels.cuh"
 
@@ -9,7 +9,8 @@ namespace en234k {
 // point b.  Output in the reference's layout: element_stiffness(ROW,COL) column-major 24x24, element_residual(24).
 __global__ void __launch_bounds__(64) k_element_batch(Mesh M, int n, const int* elems /*0-based*/, const double* ut,
                                                       const double* du, double* Kout, double* Rout, CgScalars* S) {
-    __shared__ double geom[8 * GEOM_STRIDE];
+    constexpr int GS = GEOM_STRIDE_NEO;
+    __shared__ double geom[8 * GS];
     __shared__ double sig[8 * 9];
     const int idx = blockIdx.x;
     if (idx >= n) return;
@@ -18,42 +19,57 @@ __global__ void __launch_bounds__(64) k_element_batch(Mesh M, int n, const int* 
     const Material mat = M.mats[M.mat[e]];
     if (t < 8) {
         GpOut gp;
-        gauss_point_eval(M, e, t, LoadSum{ut, du}, geom + t * GEOM_STRIDE, gp);
+        double* gg = geom + t * GS;
+        gauss_point_eval(M, e, t, LoadSum{ut, du}, gg, gp);
         if (!(gp.det != 0.0)) atomicOr(&S->nanflag, 1);
         double s[9];
-        stress_linear(mat, gp.H, s);
+        if (mat.kind == 1) {
+            NeoPoint np;
+            neo_eval(mat, gp.H, gp.det, np);
+            neo_node_vectors(np, gg);
+            if (!(np.J > 0.0)) atomicOr(&S->nanflag, 1);
+            for (int q = 0; q < 9; ++q) s[q] = np.P[q];
+        } else stress_linear(mat, gp.H, s);
         for (int q = 0; q < 9; ++q) sig[t * 9 + q] = s[q];
     }
     __syncthreads();
-    double Sm[9];
-    for (int q = 0; q < 9; ++q) Sm[q] = 0.0;
-    for (int p = 0; p < 8; ++p) {
-        const double* gq = geom + p * GEOM_STRIDE;
-        const double w = gq[24];
-        const double a0 = w * gq[3 * a], a1 = w * gq[3 * a + 1], a2 = w * gq[3 * a + 2];
-        const double b0 = gq[3 * b], b1 = gq[3 * b + 1], b2 = gq[3 * b + 2];
-        Sm[0] += a0 * b0; Sm[1] += a0 * b1; Sm[2] += a0 * b2;
-        Sm[3] += a1 * b0; Sm[4] += a1 * b1; Sm[5] += a1 * b2;
-        Sm[6] += a2 * b0; Sm[7] += a2 * b1; Sm[8] += a2 * b2;
+    double K[9];
+    if (mat.kind == 1) {
+        for (int q = 0; q < 9; ++q) K[q] = 0.0;
+        for (int p = 0; p < 8; ++p) neo_block_acc(geom + p * GS, a, b, K);
+    } else {
+        double Sm[9];
+        for (int q = 0; q < 9; ++q) Sm[q] = 0.0;
+        for (int p = 0; p < 8; ++p) {
+            const double* gq = geom + p * GS;
+            const double w = gq[G_W];
+            const double a0 = w * gq[3 * a], a1 = w * gq[3 * a + 1], a2 = w * gq[3 * a + 2];
+            const double b0 = gq[3 * b], b1 = gq[3 * b + 1], b2 = gq[3 * b + 2];
+            Sm[0] += a0 * b0; Sm[1] += a0 * b1; Sm[2] += a0 * b2;
+            Sm[3] += a1 * b0; Sm[4] += a1 * b1; Sm[5] += a1 * b2;
+            Sm[6] += a2 * b0; Sm[7] += a2 * b1; Sm[8] += a2 * b2;
+        }
+        const double lam = mat.d12, mu = mat.d44, tr = mu * (Sm[0] + Sm[4] + Sm[8]);
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) K[3 * r + c] = lam * Sm[3 * r + c] + mu * Sm[3 * c + r] + (r == c ? tr : 0.0);
     }
-    const double lam = mat.d12, mu = mat.d44, tr = mu * (Sm[0] + Sm[4] + Sm[8]);
-    double* K = Kout + (size_t)idx * 576;
+    double* Ko = Kout + (size_t)idx * 576;
     for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c)
-            K[(3 * a + r) + 24 * (3 * b + c)] = lam * Sm[3 * r + c] + mu * Sm[3 * c + r] + (r == c ? tr : 0.0);
+        for (int c = 0; c < 3; ++c) Ko[(3 * a + r) + 24 * (3 * b + c)] = K[3 * r + c];
     if (t < 24) {
         const int na = t / 3, i = t % 3;
         double r = 0.0;
         for (int p = 0; p < 8; ++p) {
-            const double* gq = geom + p * GEOM_STRIDE;
+            const double* gq = geom + p * GS;
             const double* s = sig + p * 9;
-            r -= (s[3 * i] * gq[3 * na] + s[3 * i + 1] * gq[3 * na + 1] + s[3 * i + 2] * gq[3 * na + 2]) * gq[24];
+            r -= (s[3 * i] * gq[3 * na] + s[3 * i + 1] * gq[3 * na + 1] + s[3 * i + 2] * gq[3 * na + 2]) * gq[G_W];
         }
         Rout[(size_t)idx * 24 + t] = r;
     }
 }
 
-// SVARS: stress s11,s22,s33,s12,s13,s23 at the 8 Gauss points (abaqus_uel_linelastic_3d.for:193-195); thread per (e,gp)
+// SVARS: stress s11,s22,s33,s12,s13,s23 at the 8 Gauss points (abaqus_uel_linelastic_3d.for:193-195); for the
+// neo-Hookean element the Cauchy stress sigma = P F^T / J.  One thread per (element, Gauss point).
 __global__ void k_svars(Mesh M, const double* ut, const double* du, double* svars) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)M.E * 8) return;
@@ -61,8 +77,15 @@ __global__ void k_svars(Mesh M, const double* ut, const double* du, double* svar
     double g[GEOM_STRIDE];
     GpOut o;
     gauss_point_eval(M, e, gp, LoadSum{ut, du}, g, o);
+    const Material mat = M.mats[M.mat[e]];
     double s[9];
-    stress_linear(M.mats[M.mat[e]], o.H, s);
+    if (mat.kind == 1) {
+        NeoPoint np;
+        neo_eval(mat, o.H, o.det, np);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                s[3 * i + j] = (np.P[3 * i] * np.F[3 * j] + np.P[3 * i + 1] * np.F[3 * j + 1] + np.P[3 * i + 2] * np.F[3 * j + 2]) / np.J;
+    } else stress_linear(mat, o.H, s);
     double* sv = svars + (size_t)e * 48 + 6 * gp;
     sv[0] = s[0]; sv[1] = s[4]; sv[2] = s[8]; sv[3] = s[1]; sv[4] = s[2]; sv[5] = s[5];
 }

@@ -199,7 +199,69 @@ __device__ __forceinline__ void gauss_point_eval(const Mesh& M, int e, int gp, c
 // Cauchy/PK1-type stress measure at a Gauss point.
 //  linear elastic: sigma (symmetric 3x3 in s[0..8]) = D * strain(H)            (el_linelast_3Dbasic.f90:124-127)
 //  neo-Hookean:    first Piola-Kirchhoff P(F = I + H) and tangent scalars        (oracle/or_elements.cpp el_neohooke_3d)
-struct NeoCoef { double c1, cab, caa, cba; };   // see k_assemble_rows
+// Per-Gauss-point layout in shared memory (doubles): dN/dX of the 8 nodes, w|J0|, then (neo-Hookean only)
+// alpha_c = F^-T dN_c, f_c = F dN_c and four tangent scalars.
+constexpr int G_DN = 0, G_W = 24, G_AL = 25, G_FF = 49, G_SC = 73;
+constexpr int GEOM_STRIDE_NEO = 77;
+
+// Compressible neo-Hookean point quantities (oracle/or_elements.cpp el_neohooke_3d; W = mu/2 (Ibar1-3) + K/2 (J-1)^2):
+//   P_iJ = mu J^-2/3 (F_iJ - I1/3 F^-1_Ji) + K (J-1) J F^-1_Ji
+//   A_iJkL contracted with dN_a,J dN_b,L:
+//   K_ik = s0 d_ik (a.b) - s1 (fa_i beta_k + alpha_i fb_k) + s2 alpha_i beta_k + s3 alpha_k beta_i
+//   s0 = w c1, s1 = w 2/3 c1, s2 = w (2/9 I1 c1 + K(2J-1)J), s3 = w (c1 I1/3 - K(J-1)J),  c1 = mu J^-2/3
+struct NeoPoint { double F[9], Fi[9], P[9], sc[4], J; };
+
+__device__ __forceinline__ void neo_eval(const Material& m, const double* H, double w, NeoPoint& o) {
+#pragma unroll
+    for (int q = 0; q < 9; ++q) o.F[q] = H[q] + ((q == 0 || q == 4 || q == 8) ? 1.0 : 0.0);
+    Jac jc;
+    invert3(o.F, jc);
+    o.J = jc.det;
+    double I1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) { o.Fi[q] = jc.Ji[q]; I1 += o.F[q] * o.F[q]; }
+    const double t = rcbrt(o.J);
+    const double c1 = m.mu * t * t;
+    const double cJ = m.kappa * (2.0 * o.J - 1.0) * o.J, cK = m.kappa * (o.J - 1.0) * o.J;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o.P[3 * i + j] = c1 * (o.F[3 * i + j] - I1 / 3.0 * o.Fi[3 * j + i]) + cK * o.Fi[3 * j + i];
+    o.sc[0] = w * c1;
+    o.sc[1] = w * (2.0 / 3.0) * c1;
+    o.sc[2] = w * ((2.0 / 9.0) * I1 * c1 + cJ);
+    o.sc[3] = w * (c1 * I1 / 3.0 - cK);
+}
+// alpha_c, f_c for the 8 nodes from dN/dX stored at g[0..23]
+__device__ __forceinline__ void neo_node_vectors(const NeoPoint& p, double* g) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double d0 = g[3 * c], d1 = g[3 * c + 1], d2 = g[3 * c + 2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            g[G_AL + 3 * c + i] = p.Fi[i] * d0 + p.Fi[3 + i] * d1 + p.Fi[6 + i] * d2;
+            g[G_FF + 3 * c + i] = p.F[3 * i] * d0 + p.F[3 * i + 1] * d1 + p.F[3 * i + 2] * d2;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[G_SC + q] = p.sc[q];
+}
+// one Gauss point's contribution to the neo-Hookean block K[a][b]
+__device__ __forceinline__ void neo_block_acc(const double* gq, int a, int b, double* K) {
+    const double a0 = gq[3 * a], a1 = gq[3 * a + 1], a2 = gq[3 * a + 2];
+    const double b0 = gq[3 * b], b1 = gq[3 * b + 1], b2 = gq[3 * b + 2];
+    const double al[3] = {gq[G_AL + 3 * a], gq[G_AL + 3 * a + 1], gq[G_AL + 3 * a + 2]};
+    const double be[3] = {gq[G_AL + 3 * b], gq[G_AL + 3 * b + 1], gq[G_AL + 3 * b + 2]};
+    const double fa[3] = {gq[G_FF + 3 * a], gq[G_FF + 3 * a + 1], gq[G_FF + 3 * a + 2]};
+    const double fb[3] = {gq[G_FF + 3 * b], gq[G_FF + 3 * b + 1], gq[G_FF + 3 * b + 2]};
+    const double s0 = gq[G_SC], s1 = gq[G_SC + 1], s2 = gq[G_SC + 2], s3 = gq[G_SC + 3];
+    const double ab = s0 * (a0 * b0 + a1 * b1 + a2 * b2);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            K[3 * i + k] += s2 * al[i] * be[k] + s3 * al[k] * be[i] - s1 * (fa[i] * be[k] + al[i] * fb[k]) + (i == k ? ab : 0.0);
+}
 
 __device__ __forceinline__ void stress_linear(const Material& m, const double* H, double* s) {
     const double e11 = H[0], e22 = H[4], e33 = H[8];

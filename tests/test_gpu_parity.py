@@ -219,6 +219,52 @@ def test_prescribed_displacement_ramp_multi_step():
     g.close()
 
 
+def test_neohooke_element_and_newton_history():
+    # BASELINE configs[3] in small: neo-Hookean user element (mu = 1, K = 200 as input_files/Abaqus_uel_hyperelastic.in:44),
+    # prescribed stretch ramp over 4 increments, NONLINEAR 1e-5 / 15 with full re-assembly every Newton iteration.
+    # The reference ships no hyperelastic element: parity is against the repo's oracle twin, which is pinned by the FD
+    # stiffness check and patch tests in test_oracle_cpu.py (parity unpinned by reference outputs).
+    txt = synthetic_block_input(5, jitter=0.15, element="U2", props=[1.0, 200.0], load="stretch", steps=4,
+                                solver="DIRECT", nonlinear=(1e-5, 15))
+    m = Model.from_text(txt)
+    a = m.arrays()
+    assert a["nonlinear"][0] == 1 and a["element_flag"][0] == 100001
+    g = GpuSystem(m)
+    rng = np.random.default_rng(11)
+    ut, du = 2e-2 * rng.standard_normal(g.ndof), 5e-3 * rng.standard_normal(g.ndof)
+    els = np.arange(1, m.n_elements + 1, 9)
+    K, R, fail = g.element_batch(els, ut, du)
+    assert fail == 0
+    X = a["coords"].reshape(-1, 3); conn = a["connectivity"].reshape(-1, 8) - 1
+    for q, e in enumerate(els - 1):
+        dofs = (3 * conn[e][:, None] + np.arange(3)).ravel()
+        Ko, Ro, _, _, f = ob.element(1002, X[conn[e]].ravel(), du[dofs], ut[dofs], [1.0, 200.0])
+        assert f == 0
+        assert np.linalg.norm(K[q] - Ko) / np.linalg.norm(Ko) < 1e-12
+        assert np.abs(R[q] - Ro).max() <= 1e-12 * np.abs(Ro).max()
+    # assembled tangent and residual
+    s = ob.OracleSystem(ob.OracleModel(a), 2)
+    rf_o, nrm_o, _ = s.assemble(ut, du)
+    A_o, _ = s.matrix()
+    rf, nrm, fail = g.assemble(ut, du, None)
+    assert fail == 0 and abs(g.csr() - A_o).max() <= 1e-12 * abs(A_o).max() and relmax(rf, rf_o) < 1e-12
+    # whole analysis: same Newton convergence history, same displacements / reactions
+    res = g.run_static(method=0)
+    ref = ob.OracleModel(a).run_static()
+    assert res["n_steps"] == ref["n_steps"] == 4 and res["n_cutbacks"] == ref["n_cutbacks"] == 0
+    assert res["newton"].shape == ref["newton"].shape and res["newton"].shape[0] >= 8
+    assert np.array_equal(res["newton"][:, [0, 1, 7]], ref["newton"][:, [0, 1, 7]])
+    big = ref["newton"][:, 5] > 1e-7                       # ratios well above the linear-solver noise floor
+    assert np.allclose(res["newton"][big][:, 2:6], ref["newton"][big][:, 2:6], rtol=1e-6)
+    assert relmax(res["dof_total"], ref["dof_total"]) < TOL_U
+    assert relmax(res["rforce"], ref["rforce"]) < 1e-8
+    # an inverted element makes the assembly report fail (-> time step cutback in the driver)
+    bad = np.zeros(g.ndof); bad[0::3] = -3.0 * X[:, 0]
+    _, _, fail = g.assemble(bad, np.zeros(g.ndof), None)
+    assert fail == 1
+    g.close()
+
+
 def test_full_size_properties_64cubed():
     # BASELINE configs[1] at full size: properties that need no CPU solve — operator symmetry, residual of the
     # returned solution evaluated with an independent operator (matrix-free vs assembled), determinism

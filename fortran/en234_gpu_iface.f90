@@ -1,0 +1,102 @@
+!  ISO_C_BINDING interface to liben234gpu.so (include/en234gpu.h) for the EN234_FEA Fortran driver.
+!
+!  SOURCE ONLY: no Fortran compiler exists in the build image or on the GPU box, so this module and the patched
+!  static step below are shipped uncompiled; the functionally identical C++ driver (en234_fea_b200/csrc/host)
+!  carries the tests and measurements.  See INTEGRATION.md for how a maintainer adds these two files to the
+!  reference build (they replace nothing: solver type 3 is new, types 1 and 2 keep the reference's CPU paths).
+!
+!  Argument layouts are the reference's own module arrays (modules/Mesh.f90:51-107):
+!    coords(length_coords), connectivity(length_connectivity), dof_total/dof_increment/rforce(length_dofs)
+!
+module en234_gpu_iface
+    use, intrinsic :: iso_c_binding
+    implicit none
+
+    integer(c_int), parameter :: EN234_SOLVE_PCG_BSR = 0
+    integer(c_int), parameter :: EN234_SOLVE_PCG_MATRIXFREE = 1
+
+    type(c_ptr), save :: gpu_handle = c_null_ptr
+
+    interface
+        ! replaces initialize_cg_solver (src/solver_conjugate_gradient.f90:1039-1244; call site src/staticstep.f90:95)
+        function en234gpu_create(h, device, n_nodes, n_elements, coords, connectivity, element_flag, &
+                                 element_prop_index, element_properties, n_element_properties) bind(C, name='en234gpu_create')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), intent(out)          :: h
+            integer(c_int), value             :: device, n_nodes, n_elements, n_element_properties
+            real(c_double), intent(in)        :: coords(*), element_properties(*)
+            integer(c_int), intent(in)        :: connectivity(*), element_flag(*), element_prop_index(*)
+            integer(c_int)                    :: en234gpu_create
+        end function
+        function en234gpu_destroy(h) bind(C, name='en234gpu_destroy')
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h
+            integer(c_int)     :: en234gpu_destroy
+        end function
+        ! replaces assemble_conjugate_gradient_stiffness (src/staticstep.f90:98,122) / assemble_direct_stiffness (:44,:61)
+        function en234gpu_assemble(h, dof_total, dof_increment, f_element_ext, rforce, nodal_force_norm, fail) &
+                bind(C, name='en234gpu_assemble')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value          :: h
+            real(c_double), intent(in)  :: dof_total(*), dof_increment(*)
+            type(c_ptr), value          :: f_element_ext          ! c_loc(array) or c_null_ptr
+            real(c_double), intent(out) :: rforce(*), nodal_force_norm
+            integer(c_int), intent(out) :: fail
+            integer(c_int)              :: en234gpu_assemble
+        end function
+        ! replaces apply_cojugategradient_boundaryconditions (:107,:127) / apply_direct_boundaryconditions (:55,:65)
+        function en234gpu_apply_boundaryconditions(h, f_ext, n_fixed, fixed_dof, fixed_correction, &
+                                                   unbalanced_force_norm) bind(C, name='en234gpu_apply_boundaryconditions')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value          :: h
+            type(c_ptr), value          :: f_ext                  ! c_loc(array) or c_null_ptr
+            integer(c_int), value       :: n_fixed
+            integer(c_int), intent(in)  :: fixed_dof(*)           ! 0-based DOF indices
+            real(c_double), intent(in)  :: fixed_correction(*)
+            real(c_double), intent(out) :: unbalanced_force_norm
+            integer(c_int)              :: en234gpu_apply_boundaryconditions
+        end function
+        ! replaces solve_conjugategradient (:108,:130) / solve_direct (:56,:68)
+        function en234gpu_solve(h, method, cg_tolerance, max_cg_iterations, dof_increment, correction_norm, &
+                                cg_iterations, fail) bind(C, name='en234gpu_solve')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value            :: h
+            integer(c_int), value         :: method, max_cg_iterations
+            real(c_double), value         :: cg_tolerance
+            real(c_double), intent(inout) :: dof_increment(*)
+            real(c_double), intent(out)   :: correction_norm
+            integer(c_int), intent(out)   :: cg_iterations, fail
+            integer(c_int)                :: en234gpu_solve
+        end function
+        function en234gpu_last_error() bind(C, name='en234gpu_last_error')
+            import :: c_ptr
+            type(c_ptr) :: en234gpu_last_error
+        end function
+    end interface
+
+contains
+
+    ! Builds the element arrays the C ABI expects from module Mesh and creates the device handle.
+    ! Called once where the reference calls initialize_cg_solver (src/staticstep.f90:95).
+    subroutine initialize_gpu_solver
+        use Types
+        use ParamIO
+        use Mesh
+        implicit none
+        integer(c_int), allocatable :: flags(:), propidx(:)
+        integer :: lmn, status
+        allocate(flags(n_elements), propidx(n_elements))
+        do lmn = 1, n_elements
+            flags(lmn) = element_list(lmn)%flag
+            propidx(lmn) = element_list(lmn)%element_property_index - 1      ! 0-based offset
+        end do
+        status = en234gpu_create(gpu_handle, 0_c_int, int(n_nodes, c_int), int(n_elements, c_int), coords, connectivity, &
+                                 flags, propidx, element_properties, int(length_element_properties, c_int))
+        if (status /= 0) then
+            write(IOW, *) ' *** Error creating the GPU solver (en234gpu_create) *** '
+            stop
+        end if
+        deallocate(flags, propidx)
+    end subroutine initialize_gpu_solver
+
+end module en234_gpu_iface

@@ -172,6 +172,7 @@ def main():
     import torch.distributed as dist
     from en234_fea_b200 import GpuSystem, Model, Partition, synthetic_block_input
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the single JSON line
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -187,9 +188,7 @@ def main():
     if world > 1:
         part = Partition(model, world, rank)
         gpu = GpuSystem(model, device=local, part=part)
-        uid = [GpuSystem.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        gpu.comm_init(world, rank, uid[0])
+        comm_kind = gpu.setup_distributed()
         l2g = part.ints("local_to_global_node").astype(np.int64)
         ldof = (3 * l2g[:, None] + np.arange(3)).ravel()
         g2l = -np.ones(ndof_global, np.int64)
@@ -199,6 +198,7 @@ def main():
         fd, fv, fc = g2l[fd[keep]].astype(np.int32), fv[keep], fc[keep]
     else:
         gpu = GpuSystem(model, device=local)
+        comm_kind = "none"
     gpu.set_operator_mode(args.method)
     stream = torch.cuda.current_stream()
     gpu.set_stream(stream.cuda_stream)
@@ -297,7 +297,8 @@ def main():
                        "cg_iterations": int(its), "cg_rule": "(r.r)/(b.b) < 1e-20", "final_newton_ratio": ratio,
                        "method": "assembled 3x3-block CSR" if args.method == 0 else "matrix-free",
                        "l2": "matrix stream per PCG iteration (%.0f MB) exceeds the 126 MB L2" % (alg / 1e6),
-                       "step": "assemble+BC+PCG solve+re-assemble+BC (src/staticstep.f90:44-70)"},
+                       "step": "assemble+BC+PCG solve+re-assemble+BC (src/staticstep.f90:44-70)",
+                       "collectives": comm_kind},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e, "unit": "MDOF-it/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
@@ -306,6 +307,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(dims, int(its))
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
     gpu.close()
     if world > 1:
         dist.destroy_process_group()

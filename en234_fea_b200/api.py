@@ -47,7 +47,7 @@ GPU_SYMBOLS = [
     "en234gpu_download_state", "en234gpu_zero_increment_dev", "en234gpu_element_batch", "en234gpu_get_svars",
     "en234gpu_nnz_blocks", "en234gpu_get_csr", "en234gpu_get_rhs", "en234gpu_apply_operator",
     "en234gpu_get_unique_id", "en234gpu_comm_init", "en234gpu_set_partition", "en234gpu_get_stats",
-    "en234gpu_bench_operator",
+    "en234gpu_bench_operator", "en234gpu_comm_arena", "en234gpu_comm_connect",
 ]
 HOST_SYMBOLS = [
     "en234host_model_read", "en234host_model_from_text", "en234host_model_free", "en234host_last_error",
@@ -349,6 +349,35 @@ class GpuSystem:
 
     def comm_init(self, n_ranks, rank, uid):
         self._ck(gpu_lib().en234gpu_comm_init(self.h, C.c_int(n_ranks), C.c_int(rank), C.c_char_p(uid)))
+
+    def comm_arena(self, max_shared_nodes):
+        buf = C.create_string_buffer(64)
+        self._ck(gpu_lib().en234gpu_comm_arena(self.h, C.c_int(max_shared_nodes), buf))
+        return buf.raw
+
+    def comm_connect(self, handles):
+        self._ck(gpu_lib().en234gpu_comm_connect(self.h, C.c_char_p(b"".join(handles))))
+
+    def setup_distributed(self, use_peer_memory=True):
+        """torch.distributed plumbing for a partitioned handle: NCCL communicator from a broadcast unique id, then
+        (optionally) the peer-memory arena handles exchanged with an all-gather."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        uid = [GpuSystem.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        self.comm_init(world, rank, uid[0])
+        if not use_peer_memory or os.environ.get("EN234_COMM", "") == "nccl" or world > 16:
+            return "nccl"
+        sp = self.part.ints("shared_ptr")
+        mine = int(np.diff(sp).max()) if sp.size > 1 else 0
+        sizes = [None] * world
+        dist.all_gather_object(sizes, mine)
+        handle = self.comm_arena(max(sizes))
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        self.comm_connect(handles)
+        dist.barrier()
+        return "peer-memory"
 
     # ---- whole static analysis through the host driver (src/staticstep.f90 loop)
     def run_static(self, method=0, cg_tolerance=0.0, max_cg_iterations=0, check_linear_cg=True, use_host_api=False,

@@ -68,6 +68,7 @@ struct en234gpu_ctx {
     MfData mf;
     // graphs
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    long long graph_launches[2] = {0, 0};    // kernels inside one graph launch
     // launch geometry
     int grid_asm = 0, grid_bc = 0, grid_spmv = 0, grid_vec = 0;
     size_t asm_smem = 0;
@@ -416,13 +417,14 @@ int en234gpu_apply_boundaryconditions_dev(en234gpu_handle c, double* unbalanced_
 }
 
 // ---- PCG ------------------------------------------------------------------------------------------------
+static int operator_partials(en234gpu_ctx* c, int method);
 static CgVecArgs vec_args(en234gpu_ctx* c, int method, int parity) {
     CgVecArgs V{};
     V.n = c->ndof; V.rhs = c->rhs.p; V.minv = c->minv.p;
     V.owned = c->have_owned ? c->owned.p : nullptr;
     V.sol = c->sol.p; V.r = c->r.p; V.p = c->p.p; V.Ap = c->Ap.p;
     V.part_pAp = c->part.p;
-    V.n_part_pAp = c->comm.active ? 1 : (method == EN234_SOLVE_PCG_MATRIXFREE ? c->mf.n_partials : c->grid_spmv);
+    V.n_part_pAp = c->comm.active ? 1 : operator_partials(c, method);
     V.part_a = c->part2.p; V.part_b = c->part3.p;
     V.n_part = c->comm.active ? 1 : c->grid_vec;
     V.S = c->S.p;
@@ -430,27 +432,87 @@ static CgVecArgs vec_args(en234gpu_ctx* c, int method, int parity) {
     return V;
 }
 
+// y = A x on block rows [row0, row1) (assembled operator); partials are written at part[part_off ...]
+static int launch_spmv_rows(en234gpu_ctx* c, const double* x, double* y, int row0, int row1, int part_off, int check_stop,
+                            int* n_part) {
+    const int need = (row1 - row0 + WARPS - 1) / WARPS;
+    const int grid = std::max(1, std::min(need, c->grid_spmv));
+    SpmvArgs A;
+    A.row0 = row0; A.N = row1; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
+    A.partials = c->part.p + part_off; A.S = c->S.p; A.check_stop = check_stop;
+    k_spmv<<<grid, THREADS, 0, c->stream>>>(A);
+    c->st.kernel_launches++;
+    *n_part = grid;
+    return 0;
+}
+
 static int launch_operator(en234gpu_ctx* c, int method, const double* x, double* y, int check_stop) {
     if (method == EN234_SOLVE_PCG_MATRIXFREE) {
         mf_apply(c->mf, mesh_of(c), c->ndof, c->cflag.p, c->have_owned ? c->owned.p : nullptr, x, y, c->part.p,
                  check_stop ? c->S.p : nullptr, c->stream, &c->st.kernel_launches);
     } else {
-        SpmvArgs A;
-        A.N = c->N; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
-        A.partials = c->part.p; A.S = c->S.p; A.check_stop = check_stop;
-        k_spmv<<<c->grid_spmv, THREADS, 0, c->stream>>>(A);
-        c->st.kernel_launches++;
+        int np = 0;
+        launch_spmv_rows(c, x, y, 0, c->N, 0, check_stop, &np);
     }
     return 0;
 }
 
+// number of p.Ap partials the operator leaves in part[]
+static int operator_partials(en234gpu_ctx* c, int method) {
+    if (method == EN234_SOLVE_PCG_MATRIXFREE) return c->mf.n_partials;
+    return std::max(1, std::min((c->N + WARPS - 1) / WARPS, c->grid_spmv));
+}
+
+// peer-memory halo sum of `vec` on the side stream, forked from / joined to the main stream by events
+static void p2p_halo_fork(en234gpu_ctx* c, double* vec, int check_stop) {
+    Comm& cm = c->comm;
+    cudaEventRecord(cm.ev_fork, c->stream);
+    cudaStreamWaitEvent(cm.side, cm.ev_fork, 0);
+    if (cm.n_nbr > 0) {
+        int mx = 0;
+        for (int k = 0; k < cm.n_nbr; ++k) mx = std::max(mx, 3 * (cm.shared_ptr[k + 1] - cm.shared_ptr[k]));
+        const int nblk = std::max(1, std::min(32, (mx + 255) / 256));
+        k_halo_push<<<dim3(nblk, cm.n_nbr), 256, 0, cm.side>>>(cm.peers, cm.halo, vec, c->S.p, check_stop);
+        for (int k = 0; k < cm.n_nbr; ++k)
+            k_halo_wait_add<<<nblk, 256, 0, cm.side>>>(cm.peers, cm.halo, k, k == cm.n_nbr - 1 ? 1 : 0, vec, c->S.p, check_stop);
+        c->st.kernel_launches += 1 + cm.n_nbr;
+    }
+    cudaEventRecord(cm.ev_join, cm.side);
+}
+static void p2p_halo_join(en234gpu_ctx* c) { cudaStreamWaitEvent(c->stream, c->comm.ev_join, 0); }
+
 // one PCG iteration on the stream (captured into the graph)
 static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
+    Comm& cm = c->comm;
+    if (cm.active && cm.p2p) {
+        // interface rows first; their halo exchange (peer-memory stores + flags, side stream) overlaps the interior
+        // rows; p.Ap is the all-reduced sum of local partial products over ALL local rows, which needs no halo first
+        int np = 0;
+        if (method == EN234_SOLVE_PCG_BSR && cm.n_interface > 0 && cm.n_interface < c->N) {
+            int n1 = 0, n2 = 0;
+            launch_spmv_rows(c, c->p.p, c->Ap.p, 0, cm.n_interface, 0, 1, &n1);
+            p2p_halo_fork(c, c->Ap.p, 1);
+            launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2);
+            np = n1 + n2;
+        } else {
+            launch_operator(c, method, c->p.p, c->Ap.p, 1);
+            np = operator_partials(c, method);
+            p2p_halo_fork(c, c->Ap.p, 1);
+        }
+        k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(cm.peers, c->part.p, np, nullptr, 0, c->part.p, nullptr, c->S.p, 1);
+        p2p_halo_join(c);
+        CgVecArgs V = vec_args(c, method, parity);
+        k_cg_update<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+        k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(cm.peers, c->part2.p, c->grid_vec, c->part3.p, c->grid_vec,
+                                                          c->part2.p, c->part3.p, c->S.p, 1);
+        k_cg_pupdate<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+        c->st.kernel_launches += 4;
+        return 0;
+    }
     launch_operator(c, method, c->p.p, c->Ap.p, 1);
-    if (c->comm.active) {
-        // p.Ap: sum of local partial products over ALL local rows equals the global product (interface rows hold
-        // partial sums and p agrees on both sides), so the all-reduce does not wait for the halo exchange
-        const int np = method == EN234_SOLVE_PCG_MATRIXFREE ? c->mf.n_partials : c->grid_spmv;
+    if (cm.active) {
+        // NCCL path (EN234_COMM=nccl or no peer arena)
+        const int np = operator_partials(c, method);
         k_reduce_to<<<1, VEC_THREADS, 0, c->stream>>>(c->part.p, np, c->part.p);
         if (comm_allreduce_sum(c->comm, c->part.p, 1, c->stream)) return 1;
         if (comm_halo_sum(c->comm, c->Ap.p, c->stream)) return 1;
@@ -459,7 +521,7 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
     CgVecArgs V = vec_args(c, method, parity);
     k_cg_update<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
     c->st.kernel_launches++;
-    if (c->comm.active) {
+    if (cm.active) {
         k_reduce2_to<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, c->grid_vec, c->part2.p, c->part3.p);
         // pack {rr, rz} in one 2-double message: part2[0], part2[1]
         k_pack2<<<1, 1, 0, c->stream>>>(c->part2.p, c->part3.p);
@@ -479,6 +541,7 @@ static int build_graph(en234gpu_ctx* c, int method) {
     int rc = 0;
     for (int it = 1; it <= CG_CHUNK && !rc; ++it) rc = enqueue_iteration(c, method, it & 1);
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    c->graph_launches[method] = c->st.kernel_launches - before;
     c->st.kernel_launches = before;          // capture does not launch
     if (rc) return set_err(std::string("graph capture: ") + comm_error());
     if (e != cudaSuccess) return set_err(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
@@ -504,7 +567,12 @@ int en234gpu_solve_dev(en234gpu_handle c, int method, double cg_tolerance, int m
     V.n_part = c->grid_vec;
     k_cg_init<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
     c->st.kernel_launches++;
-    if (c->comm.active) {
+    if (c->comm.active && c->comm.p2p) {
+        k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(c->comm.peers, c->part2.p, c->grid_vec, c->part3.p, c->grid_vec,
+                                                          c->part2.p, c->part3.p, c->S.p, 0);
+        V.n_part = 1;
+        c->st.kernel_launches += 1;
+    } else if (c->comm.active) {
         k_reduce2_to<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, c->grid_vec, c->part2.p, c->part3.p);
         k_pack2<<<1, 1, 0, c->stream>>>(c->part2.p, c->part3.p);
         if (comm_allreduce_sum(c->comm, c->part2.p, 2, c->stream)) return set_err(comm_error());
@@ -515,8 +583,7 @@ int en234gpu_solve_dev(en234gpu_handle c, int method, double cg_tolerance, int m
     k_cg_init_finish<<<1, VEC_THREADS, 0, c->stream>>>(V);
     c->st.kernel_launches++;
     CK(cudaGetLastError());
-    const long long per_graph = (long long)CG_CHUNK * (c->comm.active ? (3 + 1 + c->comm.launches_per_halo + 3) : 3) +
-                                (method == EN234_SOLVE_PCG_MATRIXFREE ? (long long)CG_CHUNK * (c->mf.launches_per_apply - 1) : 0);
+    const long long per_graph = c->graph_launches[method];
     // chunks of CG_CHUNK iterations; the stop flag is read back after each chunk (iterations after convergence
     // inside a chunk return immediately)
     for (;;) {
@@ -525,6 +592,7 @@ int en234gpu_solve_dev(en234gpu_handle c, int method, double cg_tolerance, int m
         CK(cudaGraphLaunch(c->graph[method], c->stream));
         c->st.kernel_launches += per_graph;
     }
+    if (comm_p2p_error(c->comm)) return set_err("peer-memory collective timed out (a rank stopped responding)");
     *fail = c->hS->fail ? 1 : 0;
     *cg_iterations = c->hS->iter;
     c->st.last_cg_iterations = c->hS->iter;
@@ -695,7 +763,8 @@ int en234gpu_apply_operator(en234gpu_handle c, int method, const double* x, doub
     CK(cudaMemcpyAsync(c->tmpvec.p, x, b, cudaMemcpyHostToDevice, c->stream));
     if (launch_operator(c, method, c->tmpvec.p, c->tmpvec2.p, 0)) return 1;
     CK(cudaGetLastError());
-    if (c->comm.active && comm_halo_sum(c->comm, c->tmpvec2.p, c->stream)) return set_err(comm_error());
+    if (c->comm.active && c->comm.p2p) { p2p_halo_fork(c, c->tmpvec2.p, 0); p2p_halo_join(c); }
+    else if (c->comm.active && comm_halo_sum(c->comm, c->tmpvec2.p, c->stream)) return set_err(comm_error());
     CK(cudaMemcpyAsync(y, c->tmpvec2.p, b, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
@@ -718,6 +787,21 @@ int en234gpu_set_partition(en234gpu_handle c, int n_neighbours, const int* neigh
     CK(cudaMemcpy(c->owned.p, owned, c->N, cudaMemcpyHostToDevice));
     c->have_owned = true;
     if (comm_set_halo(c->comm, n_neighbours, neighbour_rank, shared_ptr, shared_nodes)) return set_err(comm_error());
+    return 0;
+}
+
+int en234gpu_comm_arena(en234gpu_handle c, int max_shared_nodes, char* handle64) {
+    CK(cudaSetDevice(c->device));
+    const char* env = getenv("EN234_COMM");
+    if (env && std::string(env) == "nccl") return set_err("peer-memory path disabled by EN234_COMM=nccl");
+    if (comm_arena_create(c->comm, max_shared_nodes, handle64)) return set_err(comm_error());
+    return 0;
+}
+
+int en234gpu_comm_connect(en234gpu_handle c, const char* handles) {
+    CK(cudaSetDevice(c->device));
+    if (comm_arena_connect(c->comm, handles)) return set_err(comm_error());
+    for (auto& g : c->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     return 0;
 }
 

@@ -9,7 +9,8 @@
 namespace en234k {
 
 struct SpmvArgs {
-    int N;
+    int row0 = 0;           // first block row of this launch (interface rows are launched first on partitioned runs)
+    int N;                  // one past the last block row of this launch
     const int* browptr;
     const int* bcol;
     const double* val;
@@ -32,12 +33,12 @@ __global__ void __launch_bounds__(THREADS) k_spmv(SpmvArgs A) {
     __shared__ double red[WARPS + 1];
     if (A.check_stop && A.S->stop) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int W = gridDim.x * WARPS, N = A.N;
+    const int W = gridDim.x * WARPS, N = A.N;          // rows [A.row0, A.N) are processed by this launch
     const int d0 = lane / 3, m0 = lane % 3;                  // q = lane      -> block d0, component m0
     const int d1 = (lane + 32) / 3, m1 = (lane + 32) % 3;    // q = lane + 32
     const int d2 = (lane + 64) / 3, m2 = (lane + 64) % 3;    // q = lane + 64
     double dot = 0.0;
-    int i = blockIdx.x * WARPS + warp;
+    int i = A.row0 + blockIdx.x * WARPS + warp;
     int rb = 0, re = 0, rbn = 0, ren = 0, c0 = 0, c1 = 0, c2 = 0;
     if (i < N) { rb = __ldg(A.browptr + i); re = __ldg(A.browptr + i + 1); }
     if (i + W < N) { rbn = __ldg(A.browptr + i + W); ren = __ldg(A.browptr + i + W + 1); }

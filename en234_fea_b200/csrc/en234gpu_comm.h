@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "en234gpu_asm.cuh"
+#include "en234gpu_p2p.cuh"
 
 namespace en234k {
 
@@ -60,7 +61,74 @@ struct Comm {
     double *sendbuf = nullptr, *recvbuf = nullptr;
     int n_shared = 0;
     int launches_per_halo = 0;                // kernels of one halo sum (pack + one unpack per neighbour)
+    int n_interface = 0;                      // interface nodes are local rows [0, n_interface) (0: not separable)
+    // peer-memory path (en234gpu_p2p.cuh): arena shared through CUDA IPC, side stream for the overlapped halo exchange
+    bool p2p = false;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    void* peer_base[P2P_MAXR] = {nullptr};
+    PeerSet peers{};
+    HaloSet halo{};
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
+
+constexpr size_t P2P_HDR_BYTES = (sizeof(ArenaHdr) + 255) / 256 * 256;
+
+inline int comm_arena_create(Comm& c, int max_shared_nodes, char* handle64) {
+    if (!c.active) { comm_err_ref() = "comm_arena_create: communicator not initialised"; return 1; }
+    if (c.n_ranks > P2P_MAXR) { comm_err_ref() = "peer-memory path supports at most 16 ranks"; return 1; }
+    c.peers.cap = 3LL * (max_shared_nodes > 0 ? max_shared_nodes : 1);
+    c.arena_bytes = P2P_HDR_BYTES + (size_t)c.n_ranks * 2 * (size_t)c.peers.cap * sizeof(double);
+    if (cudaMalloc(&c.arena, c.arena_bytes) != cudaSuccess) { comm_err_ref() = "cudaMalloc failed for the peer arena"; return 1; }
+    cudaMemset(c.arena, 0, c.arena_bytes);
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, c.arena);
+    if (e != cudaSuccess) { comm_err_ref() = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); return 1; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+inline int comm_arena_connect(Comm& c, const char* handles /* n_ranks x 64 */) {
+    if (!c.arena) { comm_err_ref() = "comm_arena_connect: no arena"; return 1; }
+    c.peers.n_ranks = c.n_ranks;
+    c.peers.me = c.rank;
+    for (int r = 0; r < c.n_ranks; ++r) {
+        void* base = c.arena;
+        if (r != c.rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + 64 * (size_t)r, 64);
+            cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { comm_err_ref() = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); return 1; }
+            c.peer_base[r] = base;
+        }
+        c.peers.arena[r] = (ArenaHdr*)base;
+        c.peers.halo[r] = (double*)((char*)base + P2P_HDR_BYTES);
+    }
+    if (c.n_nbr > P2P_MAXR) { comm_err_ref() = "too many neighbours"; return 1; }
+    c.halo.n_nbr = c.n_nbr;
+    for (int k = 0; k < c.n_nbr; ++k) { c.halo.nbr_rank[k] = c.nbr_rank[k]; c.halo.ptr[k] = c.shared_ptr[k]; }
+    c.halo.ptr[c.n_nbr] = c.n_nbr > 0 ? c.shared_ptr[c.n_nbr] : 0;
+    c.halo.nodes = c.d_shared;
+    for (int k = 0; k < c.n_nbr; ++k)
+        if (3LL * (c.shared_ptr[k + 1] - c.shared_ptr[k]) > c.peers.cap) { comm_err_ref() = "halo capacity too small"; return 1; }
+    if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        comm_err_ref() = "cannot create the side stream";
+        return 1;
+    }
+    c.p2p = true;
+    return 0;
+}
+
+inline int comm_p2p_error(Comm& c) {
+    if (!c.p2p) return 0;
+    int e = 0;
+    cudaMemcpy(&e, &((ArenaHdr*)c.arena)->error, sizeof(int), cudaMemcpyDeviceToHost);
+    return e;
+}
 
 #define NCK(call)                                                                                    \
     do {                                                                                             \
@@ -95,6 +163,12 @@ inline void comm_destroy(Comm& c) {
     if (c.d_shared) cudaFree(c.d_shared);
     if (c.sendbuf) cudaFree(c.sendbuf);
     if (c.recvbuf) cudaFree(c.recvbuf);
+    for (int r = 0; r < P2P_MAXR; ++r) if (c.peer_base[r]) { cudaIpcCloseMemHandle(c.peer_base[r]); c.peer_base[r] = nullptr; }
+    if (c.arena) cudaFree(c.arena);
+    if (c.side) cudaStreamDestroy(c.side);
+    if (c.ev_fork) cudaEventDestroy(c.ev_fork);
+    if (c.ev_join) cudaEventDestroy(c.ev_join);
+    c.arena = nullptr; c.side = nullptr; c.ev_fork = c.ev_join = nullptr; c.p2p = false;
     c.d_shared = nullptr; c.sendbuf = c.recvbuf = nullptr; c.active = false;
 }
 
@@ -104,6 +178,15 @@ inline int comm_set_halo(Comm& c, int n_nbr, const int* nbr_rank, const int* sha
     c.shared_ptr.assign(shared_ptr, shared_ptr + n_nbr + 1);
     c.n_shared = n_nbr > 0 ? shared_ptr[n_nbr] : 0;
     c.launches_per_halo = n_nbr > 0 ? 1 + n_nbr : 0;
+    // interface rows are separable when the shared nodes are exactly the local nodes [0, n_interface)
+    {
+        int mx = -1;
+        for (int i = 0; i < c.n_shared; ++i) mx = shared_nodes[i] > mx ? shared_nodes[i] : mx;
+        std::vector<char> seen(mx + 1, 0);
+        int distinct = 0;
+        for (int i = 0; i < c.n_shared; ++i) if (!seen[shared_nodes[i]]) { seen[shared_nodes[i]] = 1; ++distinct; }
+        c.n_interface = (distinct == mx + 1) ? mx + 1 : 0;
+    }
     if (c.n_shared > 0) {
         if (cudaMalloc((void**)&c.d_shared, c.n_shared * sizeof(int)) != cudaSuccess ||
             cudaMalloc((void**)&c.sendbuf, 3 * (size_t)c.n_shared * sizeof(double)) != cudaSuccess ||

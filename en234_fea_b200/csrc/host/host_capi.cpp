@@ -284,8 +284,13 @@ en234host_part_t en234host_partition(en234host_model_t w, int n_ranks, int rank)
             if (g2l[n] < 0) { g2l[n] = 0; }
         }
     }
-    // local numbering in ascending global order (keeps the structured locality)
-    for (int n = 0; n < m.n_nodes; ++n) if (g2l[n] == 0) { g2l[n] = (int)l2g.size(); l2g.push_back(n); }
+    // local numbering: interface nodes (touched by more than one rank) first, then the interior, each in ascending
+    // global order (keeps the structured locality).  Interface rows can then be computed first and their halo
+    // exchange overlapped with the interior rows.
+    for (int n = 0; n < m.n_nodes; ++n) if (g2l[n] == 0 && rmin[n] != rmax[n]) { g2l[n] = -2 - (int)l2g.size(); l2g.push_back(n); }
+    p->I["n_interface"] = {(int)l2g.size()};
+    for (int n = 0; n < m.n_nodes; ++n) if (g2l[n] == 0) { g2l[n] = -2 - (int)l2g.size(); l2g.push_back(n); }
+    for (size_t i = 0; i < l2g.size(); ++i) g2l[l2g[i]] = (int)i;
     for (long long e = e0; e < e1; ++e)
         for (int a = 0; a < 8; ++a) conn.push_back(g2l[m.connectivity[8 * e + a] - 1] + 1);
     // neighbours: ranks r != rank that also touch one of my nodes.  Build per-rank node marks lazily.

@@ -135,6 +135,14 @@ int en234gpu_get_unique_id(char* id128);
 int en234gpu_comm_init(en234gpu_handle h, int n_ranks, int rank, const char* id128);
 int en234gpu_set_partition(en234gpu_handle h, int n_neighbours, const int* neighbour_rank, const int* shared_ptr,
                            const int* shared_nodes, const unsigned char* owned);
+/* Optional peer-memory path for the collectives inside the PCG loop (CUDA IPC over NVLink): halo sums become direct
+ * stores into the neighbours' buffers overlapped with the interior rows of the SpMV, the dot-product all-reduces one
+ * single-CTA kernel each.  Call after comm_init + set_partition on every rank:
+ *   en234gpu_comm_arena(h, max over ranks of the largest shared-node list, handle64 out)
+ *   exchange the 64-byte handles (all-gather), then en234gpu_comm_connect(h, handles[n_ranks*64]).
+ * Without these calls (or with EN234_COMM=nccl) the loop uses ncclSend/ncclRecv/ncclAllReduce. */
+int en234gpu_comm_arena(en234gpu_handle h, int max_shared_nodes, char* handle64);
+int en234gpu_comm_connect(en234gpu_handle h, const char* handles);
 
 /* ---- measurement: device time (ms, CUDA events on the handle's stream) of the last call of each phase,
  * kernel-launch counter, and per-iteration SpMV time of the last solve */

@@ -26,9 +26,7 @@ def main():
                                                       steps=2 if load == "stretch" else 1))
             part = Partition(m, world, rank)
             g = GpuSystem(m, device=local, part=part)
-            uid = [GpuSystem.unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(uid, src=0)
-            g.comm_init(world, rank, uid[0])
+            comm_kind = g.setup_distributed()
             res = g.run_static(method=method, check_linear_cg=True)
             l2g = part.ints("local_to_global_node").astype(np.int64)
             ldof = (3 * l2g[:, None] + np.arange(3)).ravel()
@@ -52,10 +50,11 @@ def main():
                 its, its1 = res["cg_iterations"].tolist(), ref["cg_iterations"].tolist()
                 good = eu < 1e-10 and er < 1e-10 and all(abs(a - b) <= 2 for a, b in zip(its, its1)) and \
                     res["newton"].shape == ref["newton"].shape and agree
-                print("mgpu_check world=%d mesh=%s method=%d load=%s: u err %.2e, rforce err %.2e, CG its %s vs %s, copies agree %s -> %s"
-                      % (world, dims, method, load, eu, er, its, its1, agree, "OK" if good else "FAIL"), flush=True)
+                print("mgpu_check [%s] world=%d mesh=%s method=%d load=%s: u err %.2e, rforce err %.2e, CG its %s vs %s, copies agree %s -> %s"
+                      % (comm_kind, world, dims, method, load, eu, er, its, its1, agree, "OK" if good else "FAIL"), flush=True)
                 ok = ok and good
                 g1.close()
+            dist.barrier()
             g.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)

@@ -37,6 +37,11 @@ static void flatten(en234host_model& w) {
     I["element_prop_index"] = m.element_prop_index; I["element_n_props"] = m.element_n_props;
     I["element_n_states"] = m.element_n_states;
     D["coords"] = m.coords; D["element_properties"] = m.element_properties;
+    I["element_material"] = m.element_material;
+    I["element_material"].resize(m.n_elements, 0);
+    I["material_prop_index"]; I["material_n_props"];
+    for (auto& md : m.materials) { I["material_prop_index"].push_back(md.prop_index); I["material_n_props"].push_back(md.n_props); }
+    D["material_properties"] = m.material_properties;
     auto& hp = I["history_ptr"]; hp = {0};
     for (auto& h : m.histories) {
         D["history_time"].insert(D["history_time"].end(), h.t.begin(), h.t.end());

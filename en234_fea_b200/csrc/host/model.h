@@ -45,6 +45,12 @@ struct Model {
     std::vector<int> element_flag, element_prop_index, element_n_props, element_n_states;
     std::vector<double> element_properties;
     std::vector<ElementGroup> groups;
+    // MATERIAL blocks + ELEMENTS, INTERNAL (C3D8 + UMAT, element flag 10003): parsed so that the reference's golden
+    // input can be read, but not part of the GPU hot path — en234gpu_create rejects flag 10003.
+    struct MaterialDef { std::string name; int n_states = 0, prop_index = 0, n_props = 0; };
+    std::vector<MaterialDef> materials;
+    std::vector<double> material_properties;
+    std::vector<int> element_material;     // 1-based material per element (0 for user elements)
     bool abaqusformat = false;             // set when any element id is "Un"/"VUn" (read_input_file.f90:546-555)
     // boundary conditions
     std::vector<History> histories;

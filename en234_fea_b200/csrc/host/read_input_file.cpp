@@ -200,6 +200,80 @@ bool parse_elements_user(Reader& r) {
     return r.fail("ELEMENTS block not terminated");
 }
 
+// MATERIAL, name / STATE VARIABLES, n / PROPERTIES ... END PROPERTIES / END MATERIAL   (read_input_file.f90:433-509)
+bool parse_material(Reader& r, const Line& head) {
+    Model& m = r.m;
+    if (head.n() < 2) return r.fail("MATERIAL key must specify a name for the material", &head);
+    Model::MaterialDef md;
+    md.name = head.tok[1];
+    Line L;
+    while (r.next(L)) {
+        if (kw(L.tok[0], "STAT")) {
+            if (L.n() != 2 || L.typ[1] != 0) return r.fail("STATE VARIABLES key in a MATERIAL must specify no. state variables", &L);
+            md.n_states = to_int(L.tok[1]);
+        } else if (kw(L.tok[0], "PROP")) {
+            md.prop_index = (int)m.material_properties.size();
+            md.n_props = 0;
+            while (true) {
+                if (!r.next(L)) return r.fail("PROPERTIES not terminated");
+                if (kw(L.tok[0], "ENDPROP")) break;
+                for (int k = 0; k < L.n(); ++k) {
+                    if (L.typ[k] == 2) return r.fail("material properties must be real or integer values", &L);
+                    m.material_properties.push_back(to_real(L.tok[k]));
+                    md.n_props++;
+                }
+            }
+        } else if (kw(L.tok[0], "ENDMATE")) { m.materials.push_back(md); return true; }
+        else return r.fail("MATERIAL key must be terminated by an END MATERIAL", &L);
+    }
+    return r.fail("MATERIAL block not terminated");
+}
+
+// ELEMENTS, INTERNAL: TYPE, C3D8 / PROPERTIES, material name / CONNECTIVITY   (read_input_file.f90:756-960)
+bool parse_elements_internal(Reader& r) {
+    Model& m = r.m;
+    Line L;
+    int nnod = 0, nsvar = 0, n_int_pts = 0, material = 0;
+    while (r.next(L)) {
+        if (kw(L.tok[0], "TYPE")) {
+            if (L.n() != 2) return r.fail("TYPE key must specify the element type", &L);
+            if (kw(L.tok[1], "C3D8")) { nnod = 8; n_int_pts = 8; nsvar = 15; }
+            else return r.fail("only TYPE, C3D8 internal continuum elements are recognised", &L);
+        } else if (kw(L.tok[0], "DENS")) {
+        } else if (kw(L.tok[0], "PROP")) {
+            if (L.n() < 2) return r.fail("PROPERTIES of an internal element must name a material", &L);
+            material = 0;
+            for (size_t i = 0; i < m.materials.size(); ++i) if (m.materials[i].name == L.tok[1]) material = (int)i + 1;
+            if (!material) return r.fail("unknown material name", &L);
+            nsvar = 15 + m.materials[material - 1].n_states;
+        } else if (kw(L.tok[0], "INITIALS")) { if (!skip_block(r, "ENDINIT")) return false; }
+        else if (kw(L.tok[0], "CONN")) {
+            if (nnod == 0 || material == 0) return r.fail("TYPE and PROPERTIES must precede CONNECTIVITY", &L);
+            ElementGroup g;
+            g.flag = 10003; g.n_nodes = nnod; g.n_states = nsvar * n_int_pts; g.first_element = m.n_elements;
+            if (L.n() > 1 && L.typ[1] == 2) g.zone = L.tok[1];
+            while (true) {
+                if (!r.next(L)) return r.fail("CONNECTIVITY not terminated");
+                if (kw(L.tok[0], "ENDCONN")) break;
+                if (L.typ[0] == 2) return r.fail("CONNECTIVITY key must be terminated by an END CONNECTIVITY", &L);
+                if (L.n() < nnod || L.n() > nnod + 1) return r.fail("expecting element number (optional) and 8 nodes", &L);
+                for (int k = L.n() - nnod; k < L.n(); ++k) m.connectivity.push_back(to_int(L.tok[k]));
+                m.element_flag.push_back(10003);
+                m.element_prop_index.push_back(0);
+                m.element_n_props.push_back(0);
+                m.element_n_states.push_back(nsvar * n_int_pts);
+                m.element_material.resize(m.n_elements, 0);
+                m.element_material.push_back(material);
+                m.n_elements++;
+            }
+            g.n_elements = m.n_elements - g.first_element;
+            m.groups.push_back(g);
+        } else if (kw(L.tok[0], "ENDELEM")) return true;
+        else return r.fail("unknown key in ELEMENTS, INTERNAL block", &L);
+    }
+    return r.fail("ELEMENTS block not terminated");
+}
+
 bool parse_user_mesh(Reader& r) {
     Line L;
     std::vector<double> params;
@@ -218,12 +292,13 @@ bool parse_mesh(Reader& r) {
     while (r.next(L)) {
         if (kw(L.tok[0], "USERSUB")) { if (!parse_user_mesh(r)) return false; }
         else if (kw(L.tok[0], "NODE")) { if (!parse_nodes(r)) return false; }
-        else if (kw(L.tok[0], "MATE")) return r.fail("MATERIAL blocks (UMAT continuum elements) are outside the GPU hot path", &L);
+        else if (kw(L.tok[0], "MATE")) { if (!parse_material(r, L)) return false; }
         else if (kw(L.tok[0], "ELEM")) {
             if (L.n() < 2) return r.fail("ELEMENT key must be followed by USER or INTERNAL", &L);
-            if (!kw(L.tok[1], "USER")) return r.fail("ELEMENTS, INTERNAL (continuum + UMAT) is outside the GPU hot path", &L);
-            if (!parse_elements_user(r)) return false;
-        } else if (kw(L.tok[0], "ENDMESH")) return true;
+            if (kw(L.tok[1], "USER")) { if (!parse_elements_user(r)) return false; }
+            else if (kw(L.tok[1], "INTER")) { if (!parse_elements_internal(r)) return false; }
+            else return r.fail("ELEMENT key must be followed by USER or INTERNAL", &L);
+        } else if (kw(L.tok[0], "ENDMESH")) { r.m.element_material.resize(r.m.n_elements, 0); return true; }
         else return r.fail("expecting an END MESH statement", &L);
     }
     return r.fail("MESH block not terminated");

@@ -1,12 +1,7 @@
 mkdir -p gpurun_out
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py 2>&1 | grep "mgpu_check\|rror\|Traceback" | tail -8
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err; echo "rc=$?"; tail -2 gpurun_out/bench_n8.err | cut -c1-300
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 --steps 3 --warmup 3 > gpurun_out/bench_n4.json 2> gpurun_out/bench_n4.err; echo "rc=$?"
-python - <<'PY'
-import json
-for f in ('bench_n8','bench_n4'):
-    try:
-        d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1])
-        print(f, {k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['frac'], d['roofline']['ms_per_launch'], d['roofline']['cg_iteration']['ms'], d['config']['collectives'], d['config']['cg_iterations'], d['clocks'])
-    except Exception as e: print(f, 'ERR', e)
-PY
+python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3600 --csv --log-file gpurun_out/launches_b.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
+echo rc=$?
+python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'k_spmv|k_assemble_rows|k_cg_update|k_cg_pupdate|k_apply_bc' -c 8 -o gpurun_out/prof_r1b python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
+echo rc=$?

@@ -36,7 +36,7 @@ int or_model_set_int(void* h, const char* name, const int* p, long n) {
     VI(history_ptr) VI(nodeset_ptr) VI(nodeset_nodes) VI(elementset_ptr) VI(elementset_elements)
     VI(pdof_flag) VI(pdof_dof) VI(pdof_node) VI(pdof_nodeset) VI(pdof_history) VI(pdof_rate)
     VI(pforce_flag) VI(pforce_dof) VI(pforce_node) VI(pforce_nodeset) VI(pforce_history)
-    VI(dload_flag) VI(dload_elset) VI(dload_face) VI(dload_history) VI(dload_val_ptr)
+    VI(node_order) VI(dload_flag) VI(dload_elset) VI(dload_face) VI(dload_history) VI(dload_val_ptr)
     SI(n_nodes) SI(n_elements) SI(max_no_steps) SI(solvertype) SI(nonlinear) SI(max_newton_iterations)
     SI(unsymmetric) SI(abaqusformat) SI(max_cg_iterations) SI(gps_renumber) SI(cg_apply_nodal_forces)
     SI(cg_check_linear)
@@ -129,7 +129,7 @@ void* or_system_new(void* model, int kind) {
     s->kind = kind;
     if (kind == 1) {
         std::vector<int> order(s->m->n_nodes);
-        if (s->m->gps_renumber) gps_node_order(*s->m, order);
+        if ((int)s->m->node_order.size() == s->m->n_nodes) order = s->m->node_order;
         else for (int i = 0; i < s->m->n_nodes; ++i) order[i] = i;
         compute_profile(*s->m, order, s->sky, &s->log);
     } else initialize_cg_solver(*s->m, s->coo);

@@ -59,6 +59,8 @@ void compute_profile(const Model& m, const std::vector<int>& node_order, Skyline
         log->profile_size = s.jp[neq - 1];
     }
     s.aupp.assign((size_t)s.jp[neq - 1], 0.0);
+    s.unsym = m.unsymmetric != 0;
+    if (s.unsym) s.alow.assign((size_t)s.jp[neq - 1], 0.0); else s.alow.clear();
     s.diag.assign(neq, 0.0);
     s.rhs.assign(neq, 0.0);
 }
@@ -67,6 +69,7 @@ void compute_profile(const Model& m, const std::vector<int>& node_order, Skyline
 int assemble_direct_stiffness(const Model& m, Skyline& s, const double* dof_total, const double* dof_increment,
                               double time, double dtime, std::vector<double>* svars, AsmOut& out) {
     std::fill(s.aupp.begin(), s.aupp.end(), 0.0);
+    std::fill(s.alow.begin(), s.alow.end(), 0.0);
     std::fill(s.rhs.begin(), s.rhs.end(), 0.0);
     std::fill(s.diag.begin(), s.diag.end(), 0.0);
     double K[576], R[24];
@@ -87,7 +90,11 @@ int assemble_direct_stiffness(const Model& m, Skyline& s, const double* dof_tota
                     for (int j2 = 0; j2 < 3; ++j2) {
                         int icol = s.ieqs[3 * node2 + j2], nsc = 3 * i2 + j2;
                         if (icol == irow) s.diag[irow] += K[nsr + 24 * nsc];
-                        else if (icol > irow) s.aupp[(size_t)(s.jp[icol] - (icol - irow))] += K[nsr + 24 * nsc];
+                        else if (icol > irow) {
+                            const size_t nn = (size_t)(s.jp[icol] - (icol - irow));
+                            s.aupp[nn] += K[nsr + 24 * nsc];
+                            if (s.unsym) s.alow[nn] += K[nsc + 24 * nsr];          // :282
+                        }
                     }
                 }
             }
@@ -111,11 +118,13 @@ static void fixdof_direct(Skyline& s, int n, double dofvalue) {
         int idis = ncol - n;
         if (idis <= colheight(s, ncol)) {
             size_t nn = (size_t)(s.jp[ncol] - idis);
-            s.rhs[ncol] -= s.aupp[nn] * dofvalue;
+            if (!s.unsym) s.rhs[ncol] -= s.aupp[nn] * dofvalue;          // :767
             s.aupp[nn] = 0.0;
         }
     }
-    if (n > 0) {
+    if (s.unsym) {                                                       // :772-777: only row n is replaced
+        for (long long i = colstart(s, n); i < s.jp[n]; ++i) s.alow[(size_t)i] = 0.0;
+    } else if (n > 0) {
         int mod = n;
         for (long long i = s.jp[n] - 1; i >= colstart(s, n); --i) {
             --mod;
@@ -230,6 +239,7 @@ static void lu_decomposition(Skyline& s, StepLog* log) {
     double dimx = 0.0, dfig = 0.0, dimn = 0.0;
     for (int i = 0; i < neq; ++i) dimn = std::max(dimn, std::fabs(s.diag[i]));
     double* a = s.aupp.data();
+    double* l = s.unsym ? s.alow.data() : s.aupp.data();     // symmetric: alow aliases aupp (solve_direct :956-957)
     for (int j = 0; j < neq; ++j) {
         const long long c0 = colstart(s, j);
         const int h = colheight(s, j);
@@ -242,11 +252,16 @@ static void lu_decomposition(Skyline& s, StepLog* log) {
                 const int hi = colheight(s, i);
                 const int ih = std::min(hi, i - is);
                 if (ih > 0) {
-                    const double* cj = a + c0 + (i - is) - ih;   // rows i-ih..i-1 of column j
-                    const double* ci = a + s.jp[i] - ih;          // rows i-ih..i-1 of column i
+                    const long long oj = c0 + (i - is) - ih;     // rows i-ih..i-1 of column j / row j
+                    const long long oi = s.jp[i] - ih;            // rows i-ih..i-1 of column i / row i
                     double dot = 0.0;
-                    for (int k = 0; k < ih; ++k) dot += cj[k] * ci[k];
-                    a[c0 + (i - is)] -= dot;
+                    for (int k = 0; k < ih; ++k) dot += a[oj + k] * l[oi + k];
+                    if (s.unsym) {                                 // :1109
+                        double dl = 0.0;
+                        for (int k = 0; k < ih; ++k) dl += l[oj + k] * a[oi + k];
+                        a[c0 + (i - is)] -= dot;
+                        l[c0 + (i - is)] -= dl;
+                    } else a[c0 + (i - is)] -= dot;
                 }
             }
         }
@@ -255,9 +270,10 @@ static void lu_decomposition(Skyline& s, StepLog* log) {
             double dj = s.diag[j];
             for (int k = 0; k < h; ++k) {
                 double ud = a[c0 + k] * s.diag[is + k];
-                dj = dj - a[c0 + k] * ud;
+                dj = dj - l[c0 + k] * ud;
                 a[c0 + k] = ud;
             }
+            if (s.unsym) for (int k = 0; k < h; ++k) l[c0 + k] = l[c0 + k] * s.diag[is + k];   // :1186-1188
             s.diag[j] = dj;
         }
         if (s.diag[j] != 0.0) {                    // :1129-1137
@@ -281,6 +297,7 @@ static void lu_decomposition(Skyline& s, StepLog* log) {
 static void backsubstitution(Skyline& s) {
     const int neq = s.neq;
     double* a = s.aupp.data();
+    const double* l = s.unsym ? s.alow.data() : s.aupp.data();
     double* rhs = s.rhs.data();
     int is = 0;
     while (is < neq && rhs[is] == 0.0) ++is;
@@ -288,7 +305,7 @@ static void backsubstitution(Skyline& s) {
     for (int j = is + 1; j < neq; ++j) {
         const int h = colheight(s, j);
         if (h > 0) {
-            const double* cj = a + colstart(s, j);
+            const double* cj = l + colstart(s, j);
             double dot = 0.0;
             for (int k = 0; k < h; ++k) dot += cj[k] * rhs[j - h + k];
             rhs[j] -= dot;

@@ -392,8 +392,11 @@ int element_static(const Model& m, int lmn, const double* dof_total, const doubl
     const double* props = m.element_properties.data() + m.element_prop_index[lmn];
     if (flag == FLAG_C3D8) {
         int mat = m.element_material[lmn] - 1;
+        if (!svars) { std::fprintf(stderr, "oracle: C3D8 element needs state variable storage\n"); return 1; }
+        // svars holds the state at the start of the increment on entry and is updated in place (each integration
+        // point reads its initial state before writing the updated one)
         c3d8_bbar_static(xc, du, ut, m.material_properties.data() + m.material_prop_index[mat],
-                         m.material_n_props[mat], dtime, K, R, svars, m.element_n_states[lmn]);
+                         m.material_n_props[mat], dtime, svars, K, R, svars, m.element_n_states[lmn]);
         return 0;
     }
     if (flag > FLAG_UEL_BASE) {

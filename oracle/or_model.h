@@ -57,7 +57,9 @@ struct Model {
     double cg_tolerance = 1e-17;
     int max_cg_iterations = 1000;
     // Oracle options (deviations from the literal reference are opt-in and documented):
-    int gps_renumber = 0;            // 1: Gibbs-Poole-Stockmeyer node order for the skyline (staticstep.f90:38)
+    int gps_renumber = 0;            // reserved (Gibbs-Poole-Stockmeyer order, staticstep.f90:38, is not restated)
+    std::vector<int> node_order;     // optional bandwidth-reducing node order for the skyline (0-based nodes, position ->
+                                     // node); the tests pass a reverse Cuthill-McKee order from scipy.  Empty = identity.
     int cg_apply_nodal_forces = 1;   // 0: literal CG BC routine, which drops FORCES
     int cg_check_linear = 0;         // 1: run the re-assemble + convergencecheck loop for LINEAR+CG too (Q6)
 
@@ -93,7 +95,7 @@ void uel_linelastic_3d(const double* coords24, const double* U24, const double* 
 void el_neohooke_3d(const double* coords24, const double* U24, const double* props, double* K,
                     double* R, double* svars, int* fail);
 void c3d8_bbar_static(const double* coords24, const double* du24, const double* utot24,
-                      const double* matprops, int nprops, double dtime, double* K, double* R,
+                      const double* matprops, int nprops, double dtime, const double* svars_in, double* K, double* R,
                       double* svars_out, int nsv);
 // Dispatch on element flag exactly as solver_direct.f90:129-258 does.  Returns fail.
 int element_static(const Model& m, int lmn /*0-based*/, const double* dof_total,
@@ -112,6 +114,8 @@ struct Skyline {
     std::vector<int> ieqs;       // dof (0-based) -> equation (0-based)
     std::vector<long long> jp;   // jp[j] = number of stored entries in columns 0..j (cumulative heights)
     std::vector<double> aupp, diag, rhs;
+    std::vector<double> alow;    // lower triangle stored row-wise (unsymmetric_stiffness only, Stiffness.f90:17-28)
+    bool unsym = false;
 };
 void compute_profile(const Model& m, const std::vector<int>& node_order, Skyline& s, StepLog* log);
 void gps_node_order(const Model& m, std::vector<int>& node_order);   // bandwidth_minimizer.f90

@@ -71,7 +71,7 @@ int compute_static_step(const Model& m, std::vector<double>& dof_total, std::vec
     if (m.solvertype == 1) {                                           // direct :31-91
         Skyline s;
         std::vector<int> order(m.n_nodes);
-        if (m.gps_renumber) gps_node_order(m, order);
+        if ((int)m.node_order.size() == m.n_nodes) order = m.node_order;
         else for (int i = 0; i < m.n_nodes; ++i) order[i] = i;
         compute_profile(m, order, s, &log);
         while (cont) {

@@ -43,3 +43,9 @@ for src, dst in [("Abaqus_uel_linear_elastic_3d.in", "linear_elastic_3d_uel.in")
                         rforce=res["rforce"], newton=res["newton"], profile=np.array(res["profile"]), lu=res["lu"])
     print(dst, "nodes", m.n_nodes, "elements", m.n_elements, "steps", res["n_steps"], "newton rows", len(res["newton"]))
     print(res["newton"])
+
+# golden-log case (C3D8 + UMAT): the model arrays as parsed from input_files/Abaqus_umat_holeplate_3d.in; the expected
+# Newton history is the reference's own Output_Files/Abaqus_umat_holeplate_3d.out (hard-coded in test_oracle_cpu.py)
+mu = Model.read(os.path.join(REF, "Abaqus_umat_holeplate_3d.in"))
+np.savez_compressed(os.path.join(HERE, "holeplate_3d_umat_model.npz"), **mu.arrays())
+print("holeplate_3d_umat_model.npz", mu.n_nodes, mu.n_elements)

@@ -182,9 +182,51 @@ def test_parser_on_reference_files():
     m1 = Model.read(os.path.join(REF_INPUTS, "Abaqus_uel_linear_elastic_3d.in"))
     a1 = m1.arrays()
     assert a1["checkstiffness_flag"][0] == 100000 and a1["dload_flag"].tolist() == [4] and a1["abaqusformat"][0] == 1
+    # the golden-log input (C3D8 + UMAT) parses — flag 10003, 15 state variables x 8 points, material properties — and is
+    # exactly the committed model fixture; the device library rejects that element type (not on the GPU hot path)
+    mu = Model.read(os.path.join(REF_INPUTS, "Abaqus_umat_holeplate_3d.in"))
+    au = mu.arrays()
+    assert set(au["element_flag"]) == {10003} and set(au["element_n_states"]) == {120} and au["unsymmetric"][0] == 1
+    assert au["material_properties"].tolist() == [10000.0, 0.3] and au["abaqusformat"][0] == 0
+    fx = np.load(os.path.join(GOLDEN, "holeplate_3d_umat_model.npz"))
+    for k in au:
+        assert np.array_equal(au[k], fx[k]), k
     # unsupported paths are rejected with a message, never silently misread
     with pytest.raises(ValueError):
-        Model.read(os.path.join(REF_INPUTS, "Abaqus_umat_holeplate_3d.in"))
+        Model.read(os.path.join(REF_INPUTS, "Abaqus_vumat_linear_elastic_3d.in"))
+
+
+def test_golden_log_newton_history():
+    """The only golden output of the reference: Output_Files/Abaqus_umat_holeplate_3d.out (C3D8 B-bar + elastic UMAT,
+    SOLVER, DIRECT, NONLINEAR 1e-5/15, UNSYMMETRIC; 3 steps).  The oracle's driver, element gather, unsymmetric skyline
+    assembly, fixdof, LDU solve and convergence check must reproduce every printed Newton record to the 6 significant
+    digits of the log.  (Profile statistics and LU conditioning lines depend on the Gibbs-Poole-Stockmeyer numbering,
+    which is not restated: a reverse Cuthill-McKee order from scipy is used for speed; the solution does not depend on it.)"""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    a = dict(np.load(os.path.join(GOLDEN, "holeplate_3d_umat_model.npz")))
+    N = int(a["n_nodes"][0])
+    assert (int(a["n_elements"][0]), N, 3 * N) == (3075, 4104, 12312)              # .out:4-7
+    conn = a["connectivity"].reshape(-1, 8) - 1
+    G = sp.coo_matrix((np.ones(conn.size * 8), (np.repeat(conn, 8, axis=1).ravel(), np.tile(conn, (1, 8)).ravel())),
+                      shape=(N, N)).tocsr()
+    order = reverse_cuthill_mckee(G, symmetric_mode=True).astype(np.int32)
+    res = ob.OracleModel(a, node_order=order).run_static()
+    # step, iteration, correction norm, generalized force norm, out-of-balance norm, ratio   (.out:26-31,42-47,58-63,91-96,124-129)
+    golden = [(1, 1, 0.390615e+00, 0.568430e+01, 0.240174e-01, 0.395353e-02),
+              (1, 2, 0.124137e-03, 0.568438e+01, 0.601132e-04, 0.105749e-04),
+              (1, 3, 0.273510e-06, 0.568438e+01, 0.914709e-07, 0.160916e-07),
+              (2, 1, 0.322128e-03, 0.113544e+02, 0.109670e-03, 0.965856e-05),
+              (3, 1, 0.320594e-03, 0.170101e+02, 0.122905e-03, 0.722529e-05)]
+    assert res["n_steps"] == 3 and res["n_cutbacks"] == 0 and len(res["newton"]) == len(golden)
+    for row, g in zip(res["newton"], golden):
+        assert (int(row[0]), int(row[1])) == g[:2]
+        for got, want in zip(row[2:6], g[2:]):
+            ulp = 10.0 ** (np.floor(np.log10(abs(want))) + 1 - 6)                     # last printed digit of 0.dddddd D+ee
+            assert abs(got - want) <= 0.51 * ulp, (row, g)
+        assert row[6] == 1e-5
+    assert [int(r[7]) for r in res["newton"]] == [0, 0, 1, 1, 1]
+    assert res["profile"][0] == 12312                                               # .out:11
 
 
 def test_parser_rules():

@@ -73,6 +73,7 @@ struct en234gpu_ctx {
     int grid_asm = 0, grid_bc = 0, grid_spmv = 0, grid_vec = 0;
     size_t asm_smem = 0;
     int asm_threads = THREADS;
+    int spmv_occ = 4;
     bool any_neo = false;
     // host copies needed for inspection
     std::vector<int> h_browptr, h_bcol;
@@ -243,14 +244,18 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
         if (any_neo) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oa, k_assemble_rows<true>, c->asm_threads, c->asm_smem));
         else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oa, k_assemble_rows<false>, c->asm_threads, c->asm_smem));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob, k_apply_bc, THREADS, 0));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&os, k_spmv, THREADS, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&os, k_spmv<4>, THREADS, 0));
+        c->spmv_occ = 4;
+        if (const char* e = getenv("EN234_SPMV_OCC")) {
+            if (atoi(e) == 5) { c->spmv_occ = 5; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&os, k_spmv<5>, THREADS, 0)); }
+        }
         const int need = (N + WARPS - 1) / WARPS;
         const int need_asm = (N + c->asm_threads / 32 - 1) / (c->asm_threads / 32);
         c->grid_asm = std::min(MAX_PARTIALS, std::max(1, std::min(need_asm, c->n_sm * std::max(oa, 1))));
         c->grid_bc = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(ob, 1))));
         c->grid_spmv = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(os, 1))));
     }
-    c->grid_vec = std::min(MAX_PARTIALS, std::max(1, std::min((int)((nd + VEC_THREADS - 1) / VEC_THREADS), c->n_sm * 8)));
+    c->grid_vec = std::min(MAX_PARTIALS, std::max(1, std::min((int)((nd + VEC_THREADS - 1) / VEC_THREADS), c->n_sm * 4)));
     int rc = mf_setup(c->mf, mesh_of(c), conn, N, E, c->n_sm, c->ndof);
     if (rc) { delete c; return set_err("matrix-free set-up failed"); }
     *out = c;
@@ -440,7 +445,8 @@ static int launch_spmv_rows(en234gpu_ctx* c, const double* x, double* y, int row
     SpmvArgs A;
     A.row0 = row0; A.N = row1; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
     A.partials = c->part.p + part_off; A.S = c->S.p; A.check_stop = check_stop;
-    k_spmv<<<grid, THREADS, 0, c->stream>>>(A);
+    if (c->spmv_occ == 5) k_spmv<5><<<grid, THREADS, 0, c->stream>>>(A);
+    else k_spmv<4><<<grid, THREADS, 0, c->stream>>>(A);
     c->st.kernel_launches++;
     *n_part = grid;
     return 0;

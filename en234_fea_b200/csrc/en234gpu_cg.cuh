@@ -29,7 +29,8 @@ struct SpmvArgs {
 // ahead), so every load issued for a row is independent of the others: one memory latency per row instead of the
 // pointer -> column -> x chain.  Rows are interleaved over all warps of the (single-wave, persistent) grid so that the
 // rows in flight at any time are neighbours and their x entries hit in L2/L1.
-__global__ void __launch_bounds__(THREADS) k_spmv(SpmvArgs A) {
+template <int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A) {
     __shared__ double red[WARPS + 1];
     if (A.check_stop && A.S->stop) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,18 +137,33 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_init_finish(CgVecArgs A) {
 }
 
 // ak = (z.r)/(p.Ap); sol += ak p; r -= ak Ap; partials of r.r and r.(M^-1 r)            (:885-900)
+// Each thread handles VEC_ILP strided entries with all loads issued before the first use (the vectors are far smaller
+// than the matrix, so these kernels are latency-bound unless several loads per thread are in flight).
+constexpr int VEC_ILP = 4;
 __global__ void __launch_bounds__(VEC_THREADS) k_cg_update(CgVecArgs A) {
     __shared__ double red[VEC_THREADS / 32 + 1];
     if (A.S->stop) return;
     const double pAp = reduce_partials<VEC_THREADS>(A.part_pAp, A.n_part_pAp, red);
     const double ak = A.S->rz[A.parity] / pAp;
     double rr = 0.0, rz = 0.0;
-    for (int d = blockIdx.x * VEC_THREADS + threadIdx.x; d < A.n; d += gridDim.x * VEC_THREADS) {
-        const double pv = A.p[d];
-        A.sol[d] = A.sol[d] + ak * pv;
-        const double rv = A.r[d] - ak * A.Ap[d];
-        A.r[d] = rv;
-        if (dof_owned(A.owned, d)) { rr += rv * rv; rz += (rv * A.minv[d]) * rv; }
+    const int T = gridDim.x * VEC_THREADS;
+    for (int d0 = blockIdx.x * VEC_THREADS + threadIdx.x; d0 < A.n; d0 += VEC_ILP * T) {
+        double pv[VEC_ILP], sv[VEC_ILP], rv[VEC_ILP], av[VEC_ILP], mv[VEC_ILP];
+#pragma unroll
+        for (int k = 0; k < VEC_ILP; ++k) {
+            const int d = d0 + k * T;
+            if (d < A.n) { pv[k] = A.p[d]; sv[k] = A.sol[d]; rv[k] = A.r[d]; av[k] = A.Ap[d]; mv[k] = A.minv[d]; }
+        }
+#pragma unroll
+        for (int k = 0; k < VEC_ILP; ++k) {
+            const int d = d0 + k * T;
+            if (d < A.n) {
+                A.sol[d] = sv[k] + ak * pv[k];
+                const double r = rv[k] - ak * av[k];
+                A.r[d] = r;
+                if (dof_owned(A.owned, d)) { rr += r * r; rz += (r * mv[k]) * r; }
+            }
+        }
     }
     const double s0 = block_sum<VEC_THREADS>(rr, red);
     const double s1 = block_sum<VEC_THREADS>(rz, red);
@@ -160,6 +176,15 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_pupdate(CgVecArgs A) {
     __shared__ double red[VEC_THREADS / 32 + 1];
     CgScalars* S = A.S;
     if (S->stop) return;
+    // start the vector loads of the first chunk before the scalar reduction so their latency overlaps it
+    const int T = gridDim.x * VEC_THREADS;
+    const int dfirst = blockIdx.x * VEC_THREADS + threadIdx.x;
+    double pv[VEC_ILP], rv[VEC_ILP], mv[VEC_ILP];
+#pragma unroll
+    for (int k = 0; k < VEC_ILP; ++k) {
+        const int d = dfirst + k * T;
+        if (d < A.n) { pv[k] = A.p[d]; rv[k] = A.r[d]; mv[k] = A.minv[d]; }
+    }
     const double rr = reduce_partials<VEC_THREADS>(A.part_a, A.n_part, red);
     const double rz = reduce_partials<VEC_THREADS>(A.part_b, A.n_part, red);
     const double err = rr / S->bnrm;
@@ -168,8 +193,23 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_pupdate(CgVecArgs A) {
     const bool exhausted = more && iter >= S->maxit;
     const double bk = rz / S->rz[A.parity];
     if (more && !exhausted) {
-        for (int d = blockIdx.x * VEC_THREADS + threadIdx.x; d < A.n; d += gridDim.x * VEC_THREADS)
-            A.p[d] = bk * A.p[d] + A.r[d] * A.minv[d];
+#pragma unroll
+        for (int k = 0; k < VEC_ILP; ++k) {
+            const int d = dfirst + k * T;
+            if (d < A.n) A.p[d] = bk * pv[k] + rv[k] * mv[k];
+        }
+        for (int d0 = dfirst + VEC_ILP * T; d0 < A.n; d0 += VEC_ILP * T) {
+#pragma unroll
+            for (int k = 0; k < VEC_ILP; ++k) {
+                const int d = d0 + k * T;
+                if (d < A.n) { pv[k] = A.p[d]; rv[k] = A.r[d]; mv[k] = A.minv[d]; }
+            }
+#pragma unroll
+            for (int k = 0; k < VEC_ILP; ++k) {
+                const int d = d0 + k * T;
+                if (d < A.n) A.p[d] = bk * pv[k] + rv[k] * mv[k];
+            }
+        }
     }
     // bookkeeping by the LAST CTA to finish reading S (all CTAs read S->iter/stop above): use a grid-wide ticket
     __shared__ unsigned ticket;

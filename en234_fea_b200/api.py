@@ -44,7 +44,7 @@ GPU_SYMBOLS = [
     "en234gpu_last_error", "en234gpu_device_count", "en234gpu_create", "en234gpu_destroy", "en234gpu_set_stream",
     "en234gpu_assemble", "en234gpu_apply_boundaryconditions", "en234gpu_solve", "en234gpu_set_operator_mode",
     "en234gpu_upload_state", "en234gpu_assemble_dev", "en234gpu_apply_boundaryconditions_dev", "en234gpu_solve_dev",
-    "en234gpu_download_state", "en234gpu_zero_increment_dev", "en234gpu_element_batch", "en234gpu_get_svars",
+    "en234gpu_download_state", "en234gpu_zero_increment_dev", "en234gpu_element_batch", "en234gpu_element_single", "en234gpu_get_svars",
     "en234gpu_nnz_blocks", "en234gpu_get_csr", "en234gpu_get_rhs", "en234gpu_apply_operator",
     "en234gpu_get_unique_id", "en234gpu_comm_init", "en234gpu_set_partition", "en234gpu_get_stats",
     "en234gpu_bench_operator", "en234gpu_comm_arena", "en234gpu_comm_connect",
@@ -56,6 +56,8 @@ HOST_SYMBOLS = [
     "en234host_partition", "en234host_part_free", "en234host_part_int", "en234host_part_owned",
     "en234host_part_gpu_create", "en234host_run_static_part",
 ]
+# Fortran-linkage twins of the reference plugin entry points (include/en234host.h)
+PLUGIN_SYMBOLS = ["user_element_static_", "uel_"]
 
 
 def gpu_lib():
@@ -403,6 +405,53 @@ class GpuSystem:
             raise RuntimeError("static step failed: " + host_lib().en234host_last_error().decode())
         return {"dof_total": u, "rforce": rf, "newton": newton[:info[2]].copy(), "cg_iterations": cg[:info[3]].copy(),
                 "n_steps": int(info[0]), "n_cutbacks": int(info[1])}
+
+
+
+# ---- the reference's plugin entry points, called the way a gfortran-compiled driver would (everything by reference)
+def user_element_static(element_identifier, element_coords, dof_increment, dof_total, element_properties,
+                        initial_state_variables=None):
+    """user_element_static (user_codes/src/user_element.f90:5-49) through its Fortran-linkage twin.
+    Returns element_stiffness[row, col], element_residual, updated_state_variables, fail."""
+    L = host_lib()
+    ci = lambda v: C.byref(C.c_int(int(v)))
+    xc, du, ut, pr = _f64(element_coords), _f64(dof_increment), _f64(dof_total), _f64(element_properties)
+    n_nodes = xc.size // 3
+    sv0 = _f64(initial_state_variables if initial_state_variables is not None else [])
+    sv1 = np.zeros_like(sv0)
+    node = np.zeros((n_nodes, 7), np.int32)                      # type(node), modules/Mesh.f90:5-14
+    for k in range(n_nodes):
+        node[k] = (0, 3 * k + 1, 3, 3 * k + 1, 3, 0, 0)
+    iprops = np.zeros(1, np.int32)
+    K, R = np.zeros(du.size * du.size), np.zeros(du.size)
+    fail = C.c_int(-1)
+    L.user_element_static_(ci(1), ci(element_identifier), ci(n_nodes), _ip(node), ci(pr.size), _dp(pr), ci(0), _ip(iprops),
+                           _dp(xc), ci(xc.size), _dp(du), _dp(ut), ci(du.size), ci(sv0.size), _dp(sv0), _dp(sv1), _dp(K),
+                           _dp(R), C.byref(fail))
+    return K.reshape(du.size, du.size).T.copy(), R, sv1, fail.value
+
+
+def uel(jtype, coords, u, du, props, jdltyp=(), adlmag=(), nsvars=48):
+    """UEL (user_codes/src/abaqus_uel_linelastic_3d.for:16-28) through its Fortran-linkage twin, with the argument
+    values the reference's assembly passes (src/solver_direct.f90:231-240).  coords is (NNODE, 3) row-major, i.e. the
+    memory of Fortran's COORDS(MCRD, NNODE).  Returns AMATRX[row, col], RHS, SVARS, ENERGY, PNEWDT."""
+    L = host_lib()
+    ci = lambda v: C.byref(C.c_int(int(v)))
+    cd = lambda v: C.byref(C.c_double(float(v)))
+    xc, U, DU, pr = _f64(coords), _f64(u), _f64(du), _f64(props)
+    nnode, nd = xc.size // 3, U.size
+    jd, ad = _i32(list(jdltyp) or [0]), _f64(list(adlmag) or [0.0])
+    ndload = len(jdltyp)
+    mdload = max(ndload, 1)
+    A, RHS, SV, EN = np.zeros(nd * nd), np.zeros(nd), np.zeros(nsvars), np.zeros(8)
+    zeros, time2, lflags = np.zeros(nd), np.zeros(2), np.array([1, 0, 1, 0, 0], np.int32)
+    params, predef, ddl, jprops = np.zeros(3), np.zeros(2 * nnode), np.zeros(mdload), np.zeros(1, np.int32)
+    pnewdt = C.c_double(-1.0)
+    L.uel_(_dp(RHS), _dp(A), _dp(SV), _dp(EN), ci(nd), ci(1), ci(nsvars), _dp(pr), ci(pr.size), _dp(xc), ci(3), ci(nnode),
+           _dp(U), _dp(DU), _dp(zeros), _dp(zeros), ci(jtype), _dp(time2), cd(1.0), ci(1), ci(1), ci(1), _dp(params),
+           ci(ndload), _ip(jd), _dp(ad), _dp(predef), ci(1), _ip(lflags), ci(nd), _dp(ddl), ci(mdload),
+           C.byref(pnewdt), _ip(jprops), ci(0), cd(1.0))
+    return A.reshape(nd, nd).T.copy(), RHS, SV, EN, pnewdt.value
 
 
 class Partition:

@@ -728,6 +728,45 @@ int en234gpu_get_svars(en234gpu_handle c, const double* dof_total, const double*
     return 0;
 }
 
+// Single-element evaluation on the device for the host-callable twins of the reference's element routines
+// (user_element_static / UEL): an 8-node scratch mesh is kept on device 0 and refilled per call.
+int en234gpu_element_single(int element_flag, const double* coords24, const double* props, int n_props,
+                            const double* dof_total24, const double* dof_increment24, double* element_stiffness,
+                            double* element_residual, double* svars48, double* energy, int* fail) {
+    static en234gpu_handle scratch = nullptr;
+    static int s_flag = 0;
+    static double s_props[2] = {0, 0}, s_coords[24];
+    bool fresh = scratch == nullptr || s_flag != element_flag || n_props < 2 || s_props[0] != props[0] ||
+                 s_props[1] != props[1] || std::memcmp(s_coords, coords24, sizeof(s_coords)) != 0;
+    if (fresh) {
+        if (scratch) { en234gpu_destroy(scratch); scratch = nullptr; }
+        const int conn[8] = {1, 2, 3, 4, 5, 6, 7, 8}, pidx = 0;
+        if (en234gpu_create(&scratch, 0, 8, 1, coords24, conn, &element_flag, &pidx, props, n_props)) return 1;
+        s_flag = element_flag; s_props[0] = props[0]; s_props[1] = props[1];
+        std::memcpy(s_coords, coords24, sizeof(s_coords));
+    }
+    en234gpu_ctx* c = scratch;
+    CK(cudaSetDevice(c->device));
+    DevBuf<int> d_el;
+    DevBuf<double> d_K, d_R, d_sv, d_en;
+    const int zero = 0;
+    CK(d_el.alloc(1)); CK(d_K.alloc(576)); CK(d_R.alloc(24)); CK(d_sv.alloc(48)); CK(d_en.alloc(1));
+    CK(cudaMemcpyAsync(d_el.p, &zero, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->tmpvec.p, dof_total24, 24 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->tmpvec2.p, dof_increment24, 24 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(&c->S.p->nanflag, 0, sizeof(int), c->stream));
+    k_element_batch<<<1, 64, 0, c->stream>>>(mesh_of(c), 1, d_el.p, c->tmpvec.p, c->tmpvec2.p, d_K.p, d_R.p, c->S.p, d_sv.p, d_en.p);
+    c->st.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(element_stiffness, d_K.p, 576 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(element_residual, d_R.p, 24 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (svars48) CK(cudaMemcpyAsync(svars48, d_sv.p, 48 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (energy) CK(cudaMemcpyAsync(energy, d_en.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (read_scalars(c)) return 1;
+    if (fail) *fail = c->hS->nanflag ? 1 : 0;
+    return 0;
+}
+
 long long en234gpu_nnz_blocks(en234gpu_handle c) { return c->nnzb; }
 
 int en234gpu_get_csr(en234gpu_handle c, long long* rowptr, int* col, double* val) {

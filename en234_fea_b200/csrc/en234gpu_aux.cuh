@@ -8,10 +8,12 @@ namespace en234k {
 // one CTA of 64 threads per element, thread (a,b) forms the 3x3 block K_e[a][b]; thread b < 8 also evaluates Gauss
 // point b.  Output in the reference's layout: element_stiffness(ROW,COL) column-major 24x24, element_residual(24).
 __global__ void __launch_bounds__(64) k_element_batch(Mesh M, int n, const int* elems /*0-based*/, const double* ut,
-                                                      const double* du, double* Kout, double* Rout, CgScalars* S) {
+                                                      const double* du, double* Kout, double* Rout, CgScalars* S,
+                                                      double* svout = nullptr /*n*48*/, double* enout = nullptr /*n*/) {
     constexpr int GS = GEOM_STRIDE_NEO;
     __shared__ double geom[8 * GS];
     __shared__ double sig[8 * 9];
+    __shared__ double egp[8];
     const int idx = blockIdx.x;
     if (idx >= n) return;
     const int e = elems[idx];
@@ -31,8 +33,29 @@ __global__ void __launch_bounds__(64) k_element_batch(Mesh M, int n, const int* 
             for (int q = 0; q < 9; ++q) s[q] = np.P[q];
         } else stress_linear(mat, gp.H, s);
         for (int q = 0; q < 9; ++q) sig[t * 9 + q] = s[q];
+        // elastic strain energy density x volume at this point (abaqus_uel_linelastic_3d.for:190-191)
+        const double* H = gp.H;
+        egp[t] = 0.5 * (s[0] * H[0] + s[4] * H[4] + s[8] * H[8] + s[1] * (H[1] + H[3]) + s[2] * (H[2] + H[6]) +
+                        s[5] * (H[5] + H[7])) * gp.det;
+        if (svout) {                                              // SVARS(6*kint-5:6*kint) = stress (:193-195)
+            double* sv = svout + (size_t)idx * 48 + 6 * t;
+            if (mat.kind == 1) {
+                NeoPoint np;
+                neo_eval(mat, gp.H, gp.det, np);
+                double c[9];
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j)
+                        c[3 * i + j] = (np.P[3 * i] * np.F[3 * j] + np.P[3 * i + 1] * np.F[3 * j + 1] + np.P[3 * i + 2] * np.F[3 * j + 2]) / np.J;
+                sv[0] = c[0]; sv[1] = c[4]; sv[2] = c[8]; sv[3] = c[1]; sv[4] = c[2]; sv[5] = c[5];
+            } else { sv[0] = s[0]; sv[1] = s[4]; sv[2] = s[8]; sv[3] = s[1]; sv[4] = s[2]; sv[5] = s[5]; }
+        }
     }
     __syncthreads();
+    if (t == 0 && enout) {
+        double e = 0.0;
+        for (int p = 0; p < 8; ++p) e += egp[p];
+        enout[idx] = e;
+    }
     double K[9];
     if (mat.kind == 1) {
         for (int q = 0; q < 9; ++q) K[q] = 0.0;

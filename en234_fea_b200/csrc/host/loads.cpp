@@ -48,6 +48,23 @@ void face_coords(const Model& m, int lmn, int face, int nodes[4], double fc[4][3
 
 }  // namespace
 
+// DLOAD contribution of one ABAQUS-UEL face to the 24-entry element residual (abaqus_uel_linelastic_3d.for:207-238),
+// coords24 = xyz per element node
+void uel_face_load(const double* coords24, int face, double mag, double* R24) {
+    double fc[4][3];
+    int nodes[4];
+    for (int j = 0; j < 4; ++j) {
+        nodes[j] = FACE[face - 1][j] - 1;
+        for (int i = 0; i < 3; ++i) fc[j][i] = coords24[3 * nodes[j] + i];
+    }
+    for (int kint = 0; kint < 4; ++kint) {
+        FacePoint fp;
+        face_point(fc, kint, fp);
+        for (int i = 0; i < 4; ++i)
+            for (int c = 0; c < 3; ++c) R24[3 * nodes[i] + c] -= fp.N[c] * mag * fp.norm[c];
+    }
+}
+
 void evaluate_loads(const Model& m, double time, double dtime, const double* dof_total, const double* dof_increment,
                     StepLoads& out, const std::vector<int>* g2l, size_t n_local) {
     // g2l (partitioned runs): global DOF -> rank-local DOF or -1; all outputs and the DOF arrays are then rank-local

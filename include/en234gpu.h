@@ -114,6 +114,11 @@ int en234gpu_zero_increment_dev(en234gpu_handle h);
 int en234gpu_element_batch(en234gpu_handle h, int n, const int* element_numbers /*1-based*/, const double* dof_total,
                            const double* dof_increment, double* element_stiffness /*n*576*/,
                            double* element_residual /*n*24*/, int* fail);
+/* One element, host arrays in and out (24 coords xyz per node, 24+24 DOFs): what the Fortran-signature twins
+ * user_element_static_ / uel_ (include/en234host.h) call.  svars48 / energy may be NULL. */
+int en234gpu_element_single(int element_flag, const double* coords24, const double* props, int n_props,
+                            const double* dof_total24, const double* dof_increment24, double* element_stiffness,
+                            double* element_residual, double* svars48, double* energy, int* fail);
 /* Gauss-point state: Cauchy stress s11,s22,s33,s12,s13,s23 at the 8 integration points of every element
  * (the 48 SVARS of abaqus_uel_linelastic_3d.for:193-195), for dof_total + dof_increment. */
 int en234gpu_get_svars(en234gpu_handle h, const double* dof_total, const double* dof_increment,

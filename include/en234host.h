@@ -80,6 +80,27 @@ int en234host_run_static_part(en234host_model_t m, en234host_part_t p, en234gpu_
                               double* dof_total_local, double* rforce_local, double* newton, int max_rows,
                               int* cg_iterations, int max_cg_rows, long long* info, const char* log_path);
 
+/* ---- the reference's element plugin entry points with their own argument lists and gfortran linkage (all arguments
+ * by reference; default integer / logical = int32): user_codes/src/user_element.f90:5-49 and
+ * user_codes/src/abaqus_uel_linelastic_3d.for:16-28.  A Fortran driver links these in place of the CPU routines;
+ * each call evaluates one hex8 element on device 0 (diagnostics / CHECK STIFFNESS use; the timed path evaluates
+ * elements inside the assembly kernel).  element ids 1001, 1002 / JTYPE 1, 2 only: anything else sets fail (PNEWDT
+ * = 0.5 for UEL) instead of stopping the process. */
+void user_element_static_(const int* lmn, const int* element_identifier, const int* n_nodes,
+                          const int* node_property_list, const int* n_properties, const double* element_properties,
+                          const int* n_int_properties, const int* int_element_properties,
+                          const double* element_coords, const int* length_coord_array, const double* dof_increment,
+                          const double* dof_total, const int* length_dof_array, const int* n_state_variables,
+                          const double* initial_state_variables, double* updated_state_variables,
+                          double* element_stiffness, double* element_residual, int* fail);
+void uel_(double* RHS, double* AMATRX, double* SVARS, double* ENERGY, const int* NDOFEL, const int* NRHS,
+          const int* NSVARS, const double* PROPS, const int* NPROPS, const double* COORDS, const int* MCRD,
+          const int* NNODE, const double* U, const double* DU, const double* V, const double* A, const int* JTYPE,
+          const double* TIME, const double* DTIME, const int* KSTEP, const int* KINC, const int* JELEM,
+          const double* PARAMS, const int* NDLOAD, const int* JDLTYP, const double* ADLMAG, const double* PREDEF,
+          const int* NPREDF, const int* LFLAGS, const int* MLVARX, const double* DDLMAG, const int* MDLOAD,
+          double* PNEWDT, const int* JPROPS, const int* NJPROP, const double* PERIOD);
+
 #ifdef __cplusplus
 }
 #endif

@@ -291,3 +291,34 @@ def test_full_size_properties_64cubed():
     assert its2 == its and np.array_equal(du, du2)
     assert np.all(du[fd] == 0.0)
     g.close()
+
+
+def test_fortran_linkage_plugin_twins_match_oracle():
+    """user_element_static_ / uel_ (include/en234host.h) called the way a gfortran driver calls them
+    (user_codes/src/user_element.f90:5-49, abaqus_uel_linelastic_3d.for:16-28, call site solver_direct.f90:231-240)."""
+    from en234_fea_b200 import uel, user_element_static
+    rng = np.random.default_rng(5)
+    ref = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    for trial in range(3):
+        X = (ref * [1.0, 0.7, 1.3] + 0.1 * rng.standard_normal((8, 3))).ravel()
+        ut, du = 1e-2 * rng.standard_normal(24), 1e-3 * rng.standard_normal(24)
+        for ident, props in ((1001, [100.0, 0.3]), (1002, [1.0, 200.0])):
+            K, R, sv, fail = user_element_static(ident, X, du, ut, props, initial_state_variables=[1.0, 2.0])
+            Ko, Ro, _, _, _ = ob.element(ident, X, du, ut, props)
+            assert fail == 0 and np.array_equal(sv, [1.0, 2.0])           # state copied (user_element.f90:60)
+            assert np.linalg.norm(K - Ko) <= TOL_KE * np.linalg.norm(Ko)
+            assert np.abs(R - Ro).max() <= 1e-13 * np.abs(Ro).max()
+    # UEL on a box-shaped element (flat rectangular faces: SURVEY Q2) with a pressure on face 2 and on face 4
+    X = (ref * [1.0, 0.7, 1.3]).ravel()
+    u, du = 1e-2 * rng.standard_normal(24), 1e-3 * rng.standard_normal(24)
+    A, RHS, SV, EN, pnewdt = uel(1, X, u, du, [100.0, 0.3], jdltyp=[2, 4], adlmag=[3.0, -1.5])
+    Ko, Ro, svo, eno, _ = ob.element(100000, X, du, u - du, [100.0, 0.3], jdltyp=[2, 4], adlmag=[3.0, -1.5])
+    assert pnewdt == 1.0
+    assert np.linalg.norm(A - Ko) <= TOL_KE * np.linalg.norm(Ko)
+    assert np.abs(RHS - Ro).max() <= 1e-13 * np.abs(Ro).max()
+    assert np.abs(SV.reshape(8, 6) - svo).max() <= 1e-13 * np.abs(svo).max()
+    assert abs(EN[1] - eno[1]) <= 1e-13 * abs(eno[1]) and EN[0] == 0.0
+    # an element type the device path does not have: fail / PNEWDT < 1, never a process stop
+    _, _, _, fail = user_element_static(77, X, du, u, [1.0, 0.3])
+    assert fail == 1
+    assert uel(1, X[:12], u[:12], du[:12], [100.0, 0.3])[4] < 1.0

@@ -336,6 +336,9 @@ def test_c_abi_exports_every_declared_symbol():
         assert declared == set(expected), declared ^ set(expected)
         for s in declared:
             assert hasattr(lib, s), s
+    for s in api.PLUGIN_SYMBOLS:                                  # gfortran-linkage element plugin twins
+        assert s + "(" in open(os.path.join(ROOT, "include", "en234host.h")).read()
+        assert hasattr(api.host_lib(), s), s
 
 
 def test_no_device_means_loud_failure():

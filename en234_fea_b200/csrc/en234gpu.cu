@@ -13,6 +13,7 @@
 #include "../../include/en234gpu.h"
 #include "en234gpu_asm.cuh"
 #include "en234gpu_aux.cuh"
+#include "en234gpu_elem.cuh"
 #include "en234gpu_cg.cuh"
 #include "en234gpu_mf.cuh"
 #include "en234gpu_comm.h"
@@ -54,6 +55,7 @@ struct en234gpu_ctx {
     DevBuf<double> x, y, z;
     DevBuf<int> conn, mat, adj_ptr, adj, browptr, bcol;
     DevBuf<uint8_t> slot;
+    DevBuf<unsigned> inv;        // inverse slot map per block (k_gather_rows)
     DevBuf<Material> mats;
     // system
     DevBuf<double> val, rhs, rforce, minv, ut, du, felem, fext, cval, sol, r, p, Ap, part, part2, part3, tmpvec, tmpvec2;
@@ -70,9 +72,17 @@ struct en234gpu_ctx {
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     long long graph_launches[2] = {0, 0};    // kernels inside one graph launch
     // launch geometry
-    int grid_asm = 0, grid_bc = 0, grid_spmv = 0, grid_vec = 0;
-    size_t asm_smem = 0;
-    int asm_threads = THREADS;
+    int grid_asm = 0, grid_bc = 0, grid_spmv = 0, grid_vec = 0, grid_elem = 0, grid_gather = 0;
+    size_t asm_smem = 0, elem_smem = 0;
+    int asm_threads = THREADS, elem_threads = THREADS;
+    int asm_rows = 0;            // EN234_ASM=rows: single-kernel row-gather assembly (A/B and low-memory path)
+    DevBuf<double> Ke, Re;       // element scratch of the two-kernel assembly (allocated at the first assembly)
+    DevBuf<double> diag;         // assembled diagonal (written by k_gather_rows)
+    DevBuf<int> bc_rows;         // block rows touched by the prescribed DOFs (prescribed nodes and their neighbours)
+    DevBuf<uint8_t> bc_affected; // the same set as a per-node flag
+    int n_bc_rows = 0;
+    std::vector<int> h_fixdof;   // last prescribed-DOF list (the row subset is rebuilt only when it changes)
+    bool diag_valid = false;
     int spmv_occ = 4;
     bool any_neo = false;
     // host copies needed for inspection
@@ -205,6 +215,16 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
         browptr[i + 1] = (int)bcol.size();
     }
     c->nnzb = (long long)bcol.size();
+    // inverse slot map: for block (row i, slot s) nibble k = local node b of the row's k-th adjacent element on column s
+    std::vector<unsigned> inv(bcol.size(), 0xffffffffu);
+    for (int i = 0; i < N; ++i) {
+        const int cnt = std::min(8, adj_ptr[i + 1] - adj_ptr[i]);
+        for (int k = 0; k < cnt; ++k)
+            for (int b = 0; b < 8; ++b) {
+                unsigned& w = inv[(size_t)browptr[i] + slot[((size_t)adj_ptr[i] + k) * 8 + b]];
+                w = (w & ~(15u << (4 * k))) | ((unsigned)b << (4 * k));
+            }
+    }
 
     // ---- device storage
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
@@ -215,7 +235,7 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
     CK(c->buf.alloc((vec).size()));                                                                    \
     CK(cudaMemcpy(c->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice))
     UP(x, xs); UP(y, ys); UP(z, zs); UP(conn, conn); UP(mat, mat); UP(mats, mats);
-    UP(adj_ptr, adj_ptr); UP(adj, adj); UP(slot, slot); UP(browptr, browptr); UP(bcol, bcol);
+    UP(adj_ptr, adj_ptr); UP(adj, adj); UP(slot, slot); UP(browptr, browptr); UP(bcol, bcol); UP(inv, inv);
 #undef UP
     const size_t nd = (size_t)c->ndof;
     CK(c->val.alloc(9 * (size_t)c->nnzb));
@@ -256,6 +276,24 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
         c->grid_spmv = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(os, 1))));
     }
     c->grid_vec = std::min(MAX_PARTIALS, std::max(1, std::min((int)((nd + VEC_THREADS - 1) / VEC_THREADS), c->n_sm * 4)));
+    {
+        // two-kernel assembly: element kernel (one warp per four elements) + row gather
+        int oe = 1, og = 1;
+        c->elem_smem = any_neo ? ElemCfg<true>::SMEM : ElemCfg<false>::SMEM;
+        c->elem_threads = (any_neo ? ElemCfg<true>::NW : ElemCfg<false>::NW) * 32;
+        if (any_neo) {
+            CK(cudaFuncSetAttribute(k_element_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->elem_smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oe, k_element_blocks<true>, c->elem_threads, c->elem_smem));
+        } else {
+            CK(cudaFuncSetAttribute(k_element_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->elem_smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oe, k_element_blocks<false>, c->elem_threads, c->elem_smem));
+        }
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&og, k_gather_rows, THREADS, 0));
+        const int wpc = c->elem_threads / 32, groups = (E + 3) / 4;
+        c->grid_elem = std::max(1, std::min((groups + wpc - 1) / wpc, c->n_sm * std::max(oe, 1)));
+        c->grid_gather = std::min(MAX_PARTIALS, std::max(1, std::min((N + WARPS - 1) / WARPS, c->n_sm * std::max(og, 1))));
+        if (const char* e = getenv("EN234_ASM")) c->asm_rows = std::strcmp(e, "rows") == 0;
+    }
     int rc = mf_setup(c->mf, mesh_of(c), conn, N, E, c->n_sm, c->ndof);
     if (rc) { delete c; return set_err("matrix-free set-up failed"); }
     *out = c;
@@ -315,22 +353,52 @@ static int finish_norm(en234gpu_ctx* c, const double* part, int n, double* out) 
 int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail) {
     if (phase_begin(c)) return 1;
     CK(cudaMemsetAsync(&c->S.p->nanflag, 0, sizeof(int), c->stream));
-    AsmArgs A;
-    A.M = mesh_of(c);
-    A.ut = c->ut.p; A.du = c->du.p;
+    const int with_matrix = c->mode == EN234_SOLVE_PCG_BSR ? 1 : 0;
     // partitioned runs add the (full-valued) element load vector after the halo sum of the partial residuals
-    A.felem = (c->have_felem && !c->comm.active) ? c->felem.p : nullptr;
-    A.val = c->val.p; A.rhs = c->rhs.p; A.rforce = c->rforce.p;
-    A.partials = c->part.p; A.S = c->S.p;
-    A.assemble_matrix = c->mode == EN234_SOLVE_PCG_BSR ? 1 : 0;
-    if (c->any_neo) k_assemble_rows<true><<<c->grid_asm, c->asm_threads, c->asm_smem, c->stream>>>(A);
-    else k_assemble_rows<false><<<c->grid_asm, c->asm_threads, c->asm_smem, c->stream>>>(A);
-    c->st.kernel_launches++;
+    const double* felem = (c->have_felem && !c->comm.active) ? c->felem.p : nullptr;
+    int npart_asm = 0;
+    if (c->asm_rows) {
+        AsmArgs A;
+        A.M = mesh_of(c);
+        A.ut = c->ut.p; A.du = c->du.p;
+        A.felem = felem;
+        A.val = c->val.p; A.rhs = c->rhs.p; A.rforce = c->rforce.p;
+        A.partials = c->part.p; A.S = c->S.p;
+        A.assemble_matrix = with_matrix;
+        if (c->any_neo) k_assemble_rows<true><<<c->grid_asm, c->asm_threads, c->asm_smem, c->stream>>>(A);
+        else k_assemble_rows<false><<<c->grid_asm, c->asm_threads, c->asm_smem, c->stream>>>(A);
+        c->st.kernel_launches++;
+        npart_asm = c->grid_asm;
+    } else {
+        const size_t need_ke = with_matrix ? (size_t)((c->E + 3) / 4) * 4 * 576 : 0, need_re = (size_t)c->E * 24;
+        if (c->Ke.n < need_ke && c->Ke.alloc(need_ke) != cudaSuccess) {
+            cudaGetLastError();
+            return set_err("en234gpu_assemble: cannot allocate the element scratch (" + std::to_string(need_ke * 8 >> 20) +
+                           " MiB); set EN234_ASM=rows for the single-kernel row-gather assembly");
+        }
+        if (c->Re.n < need_re) CK(c->Re.alloc(need_re));
+        ElemArgs EA;
+        EA.M = mesh_of(c);
+        EA.ut = c->ut.p; EA.du = c->du.p; EA.Ke = c->Ke.p; EA.Re = c->Re.p; EA.S = c->S.p;
+        EA.assemble_matrix = with_matrix;
+        if (c->any_neo) k_element_blocks<true><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA);
+        else k_element_blocks<false><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA);
+        GatherArgs G;
+        G.M = EA.M; G.Ke = c->Ke.p; G.Re = c->Re.p; G.felem = felem;
+        G.val = c->val.p; G.rhs = c->rhs.p; G.rforce = c->rforce.p; G.partials = c->part.p; G.S = c->S.p;
+        G.assemble_matrix = with_matrix;
+        if (with_matrix && c->diag.n < (size_t)c->ndof) CK(c->diag.alloc((size_t)c->ndof));
+        G.diag = c->diag.p; G.inv = c->inv.p;
+        k_gather_rows<<<c->grid_gather, THREADS, 0, c->stream>>>(G);
+        c->st.kernel_launches += 2;
+        npart_asm = c->grid_gather;
+    }
     CK(cudaGetLastError());
+    c->diag_valid = with_matrix && !c->asm_rows;
     c->matrix_valid = c->mode == EN234_SOLVE_PCG_BSR;
     c->rhs_valid = true;
     const double* part = c->part.p;
-    int npart = c->grid_asm;
+    int npart = npart_asm;
     if (c->comm.active) {
         // interface nodes hold partial sums: halo-sum rhs (and rforce = -rhs), then an owned-only norm
         if (comm_halo_sum(c->comm, c->rhs.p, c->stream)) return set_err(comm_error());
@@ -359,6 +427,24 @@ static int upload_fixed(en234gpu_ctx* c, int n_fixed, const int* fixed_dof, cons
         else v[it->second] = fixed_value[i];
     }
     c->n_fixed = (int)d.size();
+    if (d != c->h_fixdof || c->bc_affected.n == 0) {
+        // rows changed by fixdof: the prescribed nodes and every node coupled to one (the pattern is symmetric)
+        std::vector<uint8_t> aff(c->N, 0);
+        for (int dof : d) {
+            const int n = dof / 3;
+            for (int k = c->h_browptr[n]; k < c->h_browptr[n + 1]; ++k) aff[c->h_bcol[k]] = 1;
+            aff[n] = 1;
+        }
+        std::vector<int> rows;
+        for (int i = 0; i < c->N; ++i) if (aff[i]) rows.push_back(i);
+        c->n_bc_rows = (int)rows.size();
+        if (c->bc_affected.n == 0) CK(c->bc_affected.alloc(c->N));
+        if (c->bc_rows.n < rows.size()) CK(c->bc_rows.alloc(rows.size()));
+        CK(cudaMemcpyAsync(c->bc_affected.p, aff.data(), aff.size(), cudaMemcpyHostToDevice, c->stream));
+        if (!rows.empty()) CK(cudaMemcpyAsync(c->bc_rows.p, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->h_fixdof = d;
+    }
     if (c->fixdof.n < d.size()) { CK(c->fixdof.alloc(d.size())); CK(c->fixval.alloc(d.size())); }
     if (!d.empty()) {
         CK(cudaMemcpyAsync(c->fixdof.p, d.data(), d.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -383,6 +469,12 @@ static int apply_bc_common(en234gpu_ctx* c, int values_are_corrections, double* 
     B.cflag = c->cflag.p; B.cval = c->cval.p; B.minv = c->minv.p; B.partials = c->part.p;
     const double* part = c->part.p;
     int npart = c->grid_bc;
+    const bool subset = c->mode == EN234_SOLVE_PCG_BSR && c->diag_valid && c->bc_affected.n > 0;
+    int grid_bc = c->grid_bc;
+    if (subset) {
+        B.rows = c->bc_rows.p; B.n_rows = c->n_bc_rows;
+        grid_bc = std::max(1, std::min(c->grid_bc, (c->n_bc_rows + WARPS - 1) / WARPS));
+    }
     if (c->mode == EN234_SOLVE_PCG_MATRIXFREE) {
         // matrix-free: K[:,C] c is one application of the unmasked operator to the vector of prescribed corrections;
         // the Jacobi diagonal is integrated element by element
@@ -404,9 +496,17 @@ static int apply_bc_common(en234gpu_ctx* c, int values_are_corrections, double* 
     } else if (c->comm.active) {
         // the Jacobi diagonal and the rhs corrections of interface rows are partial sums on each rank:
         // apply to local rows, then halo-sum what is additive (see k_apply_bc_partitioned)
-        if (bc_partitioned(c->comm, B, c->grid_bc, c->grid_vec, c->ndof, c->owned.p, c->tmpvec.p, c->tmpvec2.p, c->part2.p,
-                           c->stream, &c->st.kernel_launches)) return set_err(comm_error());
+        if (bc_partitioned(c->comm, B, grid_bc, c->grid_vec, c->ndof, c->owned.p, c->tmpvec.p, c->tmpvec2.p, c->diag.p,
+                           c->part2.p, c->stream, &c->st.kernel_launches)) return set_err(comm_error());
         part = c->part2.p; npart = c->grid_vec;
+    } else if (subset) {
+        // prescribed rows and their neighbours through the matrix; every other row from the assembled diagonal
+        B.partials = c->part.p + c->grid_vec;
+        k_bc_rest<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(c->ndof, c->bc_affected.p, c->rhs.p, B.fext, c->diag.p,
+                                                               c->minv.p, c->part.p);
+        if (c->n_bc_rows > 0) k_apply_bc<<<grid_bc, THREADS, 0, c->stream>>>(B);
+        c->st.kernel_launches += c->n_bc_rows > 0 ? 2 : 1;
+        npart = c->grid_vec + (c->n_bc_rows > 0 ? grid_bc : 0);
     } else {
         k_apply_bc<<<c->grid_bc, THREADS, 0, c->stream>>>(B);
         c->st.kernel_launches++;

@@ -173,6 +173,10 @@ struct BcArgs {
     double* corr_out = nullptr;
     double* diag_out = nullptr;
     const uint8_t* owned = nullptr;
+    // row subset: only rows that are prescribed or couple to a prescribed DOF change (null = every row); the other
+    // rows are finished by k_bc_rest from the diagonal the assembly left in `diag`
+    const int* rows = nullptr;
+    int n_rows = 0;
 };
 
 // fixdof semantics for all prescribed DOFs in one pass (solver_conjugate_gradient.f90:673-713):
@@ -181,7 +185,9 @@ __global__ void __launch_bounds__(THREADS) k_apply_bc(BcArgs B) {
     __shared__ double red[WARPS + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double norm2 = 0.0;
-    for (int i = blockIdx.x * WARPS + warp; i < B.N; i += gridDim.x * WARPS) {
+    const int count = B.rows ? B.n_rows : B.N;
+    for (int ii = blockIdx.x * WARPS + warp; ii < count; ii += gridDim.x * WARPS) {
+        const int i = B.rows ? B.rows[ii] : ii;
         const int rb = B.browptr[i], nb = B.browptr[i + 1] - rb, L = 3 * nb;
         double* v = B.val + 9 * (size_t)rb;
 #pragma unroll
@@ -224,6 +230,23 @@ __global__ void __launch_bounds__(THREADS) k_apply_bc(BcArgs B) {
     }
     const double t = block_sum<THREADS>(norm2, red);
     if (threadIdx.x == 0) B.partials[blockIdx.x] = t;
+}
+
+// rows outside the subset of k_apply_bc: rhs += f_ext, 1/diag from the assembled diagonal, ||rhs||^2 partials
+__global__ void __launch_bounds__(VEC_THREADS) k_bc_rest(int n, const uint8_t* affected /*per node*/, double* rhs,
+                                                          const double* fext, const double* diag, double* minv,
+                                                          double* partials) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    double s = 0.0;
+    for (int d = blockIdx.x * VEC_THREADS + threadIdx.x; d < n; d += gridDim.x * VEC_THREADS) {
+        if (affected[d / 3]) continue;
+        double r = rhs[d];
+        if (fext) { r += fext[d]; rhs[d] = r; }
+        minv[d] = 1.0 / diag[d];
+        s += r * r;
+    }
+    const double t = block_sum<VEC_THREADS>(s, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
 
 // corrections for the device-resident path: c = value - (dof_total + dof_increment)  (solver_direct.f90:705-709)

@@ -296,9 +296,14 @@ __global__ void __launch_bounds__(VEC_THREADS) k_bc_finalize(int n, double* rhs,
 
 // BC application on a partition: local pass, halo sums of the additive vectors, finalisation
 inline int bc_partitioned(Comm& c, BcArgs B, int grid_rows, int grid_vec, int ndof, const uint8_t* owned, double* corr,
-                          double* diag, double* partials, cudaStream_t s, long long* launches) {
+                          double* diag, const double* assembled_diag, double* partials, cudaStream_t s, long long* launches) {
     B.corr_out = corr; B.diag_out = diag; B.owned = owned;
-    k_apply_bc<<<grid_rows, THREADS, 0, s>>>(B);
+    if (B.rows) {
+        // rows outside the subset: no correction, assembled diagonal
+        if (cudaMemsetAsync(corr, 0, (size_t)ndof * sizeof(double), s) != cudaSuccess) return 1;
+        if (cudaMemcpyAsync(diag, assembled_diag, (size_t)ndof * sizeof(double), cudaMemcpyDeviceToDevice, s) != cudaSuccess) return 1;
+    }
+    if (!B.rows || B.n_rows > 0) k_apply_bc<<<grid_rows, THREADS, 0, s>>>(B);
     if (comm_halo_sum(c, corr, s)) return 1;
     if (comm_halo_sum(c, diag, s)) return 1;
     k_bc_finalize<<<grid_vec, VEC_THREADS, 0, s>>>(ndof, B.rhs, B.fext, B.cflag, B.cval, corr, diag, B.minv, owned, partials);

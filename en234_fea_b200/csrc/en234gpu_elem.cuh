@@ -1,0 +1,324 @@
+// Two-kernel assembly: (1) batched element kernel  (2) deterministic gather into the block-CSR rows.
+//
+//   k_element_blocks<NEO>   element loop of assemble_*_stiffness (src/solver_direct.f90:102-258): every element is
+//                           evaluated ONCE — Gauss-point geometry, stress, the 24-entry element residual and the 64
+//                           3x3 blocks of element_stiffness — and written to an element scratch array in HBM.
+//   k_gather_rows           the scatter of src/solver_direct.f90:264-287 turned into a gather: one warp per node row
+//                           sums the row's (element, local node) contributions in ASCENDING ELEMENT ORDER through the
+//                           precomputed element-to-CSR slot map, so every matrix entry and residual entry is summed
+//                           in the reference's serial order — no atomics, bitwise run-to-run deterministic.
+//
+// Element scratch layout (per pair of elements, 2 x 576 doubles): values j = 2jp, 2jp+1 (jp = 0..17) of lane l (0..31)
+// at [jp*64 + 2l .. +1], lane l = (e&1)*16 + tA*4 + tB holding the 2x2 tile of blocks {2tA, 2tA+1} x {2tB, 2tB+1},
+// j = (sa*2 + sb)*9 + 3r + c.  Kernel 1 therefore stores 512-byte rows with 16-byte stores (fully coalesced) and the
+// 72 values of one (element, local node) row are nine whole 64-byte chunks for kernel 2.
+#pragma once
+#include "en234gpu_kernels.cuh"
+
+namespace en234k {
+
+struct ElemArgs {
+    Mesh M;
+    const double* ut;       // dof_total      (AoS, 3 per node)
+    const double* du;       // dof_increment
+    double* Ke;             // element blocks, layout above; padded to a multiple of 4 elements
+    double* Re;             // element residuals [e][24]
+    CgScalars* S;           // nanflag
+    int assemble_matrix;    // 0: residual only (matrix-free solves)
+};
+
+template <bool NEO>
+struct ElemCfg {
+    static constexpr int NW = NEO ? 4 : 8;                                      // warps per CTA
+    static constexpr int GS = (NEO ? GEOM_STRIDE_NEO : GEOM_STRIDE) + 10;       // + 9 stress values, odd stride
+    static constexpr int G_SIG = NEO ? GEOM_STRIDE_NEO : GEOM_STRIDE;           // w * stress (9)
+    static constexpr int PER_WARP = 4 * 8 * GS;
+    static constexpr size_t SMEM = (size_t)NW * PER_WARP * sizeof(double);
+};
+
+// One warp per group of four elements.
+//  phase A  lane = 8*g + p : Gauss point p of element g — Jacobian, dN/dx, grad u, stress -> shared memory
+//  phase R  lane = 8*g + a : residual of local node a,  R_a = -sum_p w|J| sigma_p . grad N_a   (el_linelast_3Dbasic.f90:128)
+//  phase B  lane = 16*h + 4*tA + tB (two rounds, elements 2*round + h): the 2x2 tile of 3x3 blocks
+//           K_e[a][b] = sum_p w|J| (lam S + mu S^T + mu tr(S) I),  S = grad N_a (x) grad N_b
+//           — the integrand of B^T D B (el_linelast_3Dbasic.f90:130-131) with the zeros of B and D removed; the tile keeps
+//           36 accumulators in registers so every shared-memory operand is used three times.
+template <bool NEO>
+__global__ void __launch_bounds__(ElemCfg<NEO>::NW * 32, 2) k_element_blocks(ElemArgs A) {
+    constexpr int NW = ElemCfg<NEO>::NW, GS = ElemCfg<NEO>::GS, G_SIG = ElemCfg<NEO>::G_SIG;
+    extern __shared__ double sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* geom = sm + (size_t)warp * ElemCfg<NEO>::PER_WARP;
+    const Mesh& M = A.M;
+    const int ngroups = (M.E + 3) >> 2;
+    bool bad = false;
+    for (int grp = blockIdx.x * NW + warp; grp < ngroups; grp += gridDim.x * NW) {
+        // ---------------- phase A
+        {
+            const int g = lane >> 3, p = lane & 7;
+            const int e = min(4 * grp + g, M.E - 1);                 // padding lanes repeat the last element
+            const bool valid = 4 * grp + g < M.E;
+            const Material mat = M.mats[M.mat[e]];
+            double* gg = geom + (g * 8 + p) * GS;
+            GpOut gp;
+            gauss_point_eval(M, e, p, LoadSum{A.ut, A.du}, gg, gp);
+            if (valid && !(gp.det != 0.0)) bad = true;               // zero / NaN Jacobian (Element_Utilities.f90:108-112)
+            double s[9];
+            if (NEO && mat.kind == 1) {
+                NeoPoint np;
+                neo_eval(mat, gp.H, gp.det, np);
+                neo_node_vectors(np, gg);
+                if (valid && !(np.J > 0.0)) bad = true;              // inverted element: cut the step back
+#pragma unroll
+                for (int q = 0; q < 9; ++q) s[q] = np.P[q];
+            } else {
+                stress_linear(mat, gp.H, s);
+            }
+#pragma unroll
+            for (int q = 0; q < 9; ++q) gg[G_SIG + q] = s[q];
+        }
+        __syncwarp();
+        // ---------------- phase R
+        {
+            const int g = lane >> 3, a = lane & 7;
+            const int e = 4 * grp + g;
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const double* gq = geom + (g * 8 + p) * GS;
+                const double* s = gq + G_SIG;
+                const double w = gq[G_W];
+                const double d0 = gq[3 * a], d1 = gq[3 * a + 1], d2 = gq[3 * a + 2];
+                r0 -= (s[0] * d0 + s[1] * d1 + s[2] * d2) * w;
+                r1 -= (s[3] * d0 + s[4] * d1 + s[5] * d2) * w;
+                r2 -= (s[6] * d0 + s[7] * d1 + s[8] * d2) * w;
+            }
+            if (e < M.E) {
+                double* R = A.Re + (size_t)e * 24 + 3 * a;
+                R[0] = r0; R[1] = r1; R[2] = r2;
+            }
+        }
+        // ---------------- phase B
+        if (A.assemble_matrix) {
+            const int h = lane >> 4, tA = (lane >> 2) & 3, tB = lane & 3;
+#pragma unroll 1
+            for (int round = 0; round < 2; ++round) {
+                const int el = 2 * round + h;
+                const int e = min(4 * grp + el, M.E - 1);
+                const Material mat = M.mats[M.mat[e]];
+                const double* ge = geom + el * 8 * GS;
+                double K[4][9];
+                if (NEO && mat.kind == 1) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) K[t][q] = 0.0;
+#pragma unroll 1
+                    for (int p = 0; p < 8; ++p) {
+                        const double* gq = ge + p * GS;
+                        neo_block_acc(gq, 2 * tA, 2 * tB, K[0]);
+                        neo_block_acc(gq, 2 * tA, 2 * tB + 1, K[1]);
+                        neo_block_acc(gq, 2 * tA + 1, 2 * tB, K[2]);
+                        neo_block_acc(gq, 2 * tA + 1, 2 * tB + 1, K[3]);
+                    }
+                } else {
+                    double S[4][9];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) S[t][q] = 0.0;
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        const double* gq = ge + p * GS;
+                        const double w = gq[G_W];
+                        double av[6], bv[6];
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) { av[q] = w * gq[6 * tA + q]; bv[q] = gq[6 * tB + q]; }
+#pragma unroll
+                        for (int sa = 0; sa < 2; ++sa)
+#pragma unroll
+                            for (int sb = 0; sb < 2; ++sb)
+#pragma unroll
+                                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                                    for (int c = 0; c < 3; ++c) S[sa * 2 + sb][3 * r + c] += av[3 * sa + r] * bv[3 * sb + c];
+                    }
+                    const double lam = mat.d12, mu = mat.d44;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const double tr = mu * (S[t][0] + S[t][4] + S[t][8]);
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+                                K[t][3 * r + c] = lam * S[t][3 * r + c] + mu * S[t][3 * c + r] + (r == c ? tr : 0.0);
+                    }
+                }
+                // elements 4grp+2round, +1 form one scratch pair: 36 coalesced 256-byte rows
+                double2* dst = reinterpret_cast<double2*>(A.Ke + ((size_t)(2 * grp + round)) * 1152) + lane;
+#pragma unroll
+                for (int jp = 0; jp < 18; ++jp) {
+                    const int j0 = 2 * jp, j1 = 2 * jp + 1;
+                    __stcs(dst + jp * 32, make_double2(K[j0 / 9][j0 % 9], K[j1 / 9][j1 % 9]));
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (bad) atomicOr(&A.S->nanflag, 1);
+}
+
+struct GatherArgs {
+    Mesh M;
+    const double* Ke;
+    const double* Re;
+    const double* felem;    // element-level external loads added to the residual (may be null)
+    double* val;            // block-row values, layout per block row i: [r][block][c]  (= scalar CSR of rows 3i..3i+2)
+    double* rhs;            // pre-BC right-hand side (element residual sum + felem)
+    double* rforce;         // -rhs                                        (solver_direct.f90:417-421)
+    double* partials;       // per-CTA sum of rhs^2                        (:423)
+    CgScalars* S;           // nanflag                                     (:402-415)
+    double* diag;           // assembled diagonal per DOF (Jacobi preconditioner input, cg_iteration_loop :817-820)
+    const unsigned* inv;    // per block (row, slot): nibble k = local node b of adjacency entry k on that column, 15 = none
+    int assemble_matrix;
+};
+
+// One warp per node row, ONE LANE PER 3x3 BLOCK of the row (a hex8 row has <= 27 blocks).  `inv` holds, for every block
+// (row i, slot s), one nibble per adjacency entry k < 8 of the row: the local node b of that element whose column is s,
+// or 15 when the element does not touch the column.  A lane therefore knows statically-indexed where its up to 8
+// contributions live in the element scratch: 9 accumulators in registers, contributions added in ascending element
+// order (the reference's serial order), no shared memory, no atomics; all loads of a row are independent.
+// Row pointers are fetched two rows ahead and adjacency / inverse-map words one row ahead, so one row costs one
+// memory latency.  Rows with more than 8 adjacent elements or more than 32 blocks take the generic path.
+__device__ __forceinline__ void gather_row_generic(const GatherArgs& A, int i, int k0, int k1, int rb, int nb, int lane,
+                                                   double* accs, double& R) {
+    const Mesh& M = A.M;
+    const int L = 3 * nb;
+    double* acc = (nb <= MAXNB) ? accs : A.val + 9 * (size_t)rb;
+    if (A.assemble_matrix) {
+        for (int q = lane; q < 9 * nb; q += 32) acc[q] = 0.0;
+    }
+    __syncwarp();
+    for (int k = k0; k < k1; ++k) {
+        const int ea = M.adj[k];
+        const int e = ea >> 3, a = ea & 7;
+        if (lane < 3) R += A.Re[(size_t)e * 24 + 3 * a + lane];
+        if (A.assemble_matrix) {
+            for (int q = lane; q < 72; q += 32) {
+                const int b = q / 9, rc = q % 9, j = ((a & 1) * 2 + (b & 1)) * 9 + rc;
+                const double v = A.Ke[(size_t)(e >> 1) * 1152 + (j >> 1) * 64 + ((e & 1) * 16 + (a >> 1) * 4 + (b >> 1)) * 2 + (j & 1)];
+                acc[(rc / 3) * L + 3 * (int)M.slot[(size_t)k * 8 + b] + rc % 3] += v;
+            }
+        }
+        __syncwarp();
+    }
+    if (A.assemble_matrix) {
+        const int dslot = k0 < k1 ? M.slot[(size_t)k0 * 8 + (M.adj[k0] & 7)] : 0;
+        if (lane < 3) A.diag[3 * (size_t)i + lane] = acc[lane * L + 3 * dslot + lane];
+        if (nb <= MAXNB) {
+            double* out = A.val + 9 * (size_t)rb;
+            for (int q = lane; q < 9 * nb; q += 32) out[q] = acc[q];
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(THREADS, 2) k_gather_rows(GatherArgs A) {
+    __shared__ double accs[WARPS * ACC_PER_WARP];
+    __shared__ double red[WARPS + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Mesh& M = A.M;
+    const int W = gridDim.x * WARPS;
+    double norm2 = 0.0;
+    bool bad = false;
+    int i = blockIdx.x * WARPS + warp;
+    // software pipeline: (k0, k1, rb, re) of rows i and i + W, adjacency entry / inverse-map word of row i
+    int k0 = 0, k1 = 0, rb = 0, re = 0, k0n = 0, k1n = 0, rbn = 0, ren = 0, my_ea = -1;
+    unsigned my_inv = 0xffffffffu;
+    if (i < M.N) { k0 = M.adj_ptr[i]; k1 = M.adj_ptr[i + 1]; rb = M.browptr[i]; re = M.browptr[i + 1]; }
+    if (i + W < M.N) { k0n = M.adj_ptr[i + W]; k1n = M.adj_ptr[i + W + 1]; rbn = M.browptr[i + W]; ren = M.browptr[i + W + 1]; }
+    if (lane < 8 && k0 + lane < k1) my_ea = M.adj[k0 + lane];
+    if (A.assemble_matrix && rb + lane < re) my_inv = A.inv[rb + lane];
+    for (; i < M.N; i += W) {
+        const int nb = re - rb, cnt = k1 - k0, L = 3 * nb;
+        double R = 0.0;
+        // prefetch for the next row / the row after it
+        int ea_n = -1, k0f = 0, k1f = 0, rbf = 0, ref = 0;
+        unsigned inv_n = 0xffffffffu;
+        if (lane < 8 && k0n + lane < k1n) ea_n = M.adj[k0n + lane];
+        if (A.assemble_matrix && rbn + lane < ren) inv_n = A.inv[rbn + lane];
+        if (i + 2 * W < M.N) {
+            k0f = M.adj_ptr[i + 2 * W]; k1f = M.adj_ptr[i + 2 * W + 1]; rbf = M.browptr[i + 2 * W]; ref = M.browptr[i + 2 * W + 1];
+        }
+        if (cnt <= 8 && nb <= 32) {
+            double acc[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+            // two halves of four contributions: all loads of a half are issued before its (ordered) adds
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                double v[4][9], rv[4];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = 4 * half + u;
+                    const int ea = __shfl_sync(0xffffffffu, my_ea, k);
+                    const int e = ea >> 3, a = ea & 7;
+                    const int b = (my_inv >> (4 * k)) & 15;
+                    ok[u] = A.assemble_matrix && ea >= 0 && b != 15;
+                    rv[u] = 0.0;
+                    if (lane < 3 && ea >= 0) rv[u] = A.Re[(size_t)e * 24 + 3 * a + lane];
+                    if (ok[u]) {
+                        const double* src = A.Ke + (size_t)(e >> 1) * 1152 + ((e & 1) * 16 + (a >> 1) * 4 + (b >> 1)) * 2;
+                        const int j0 = ((a & 1) * 2 + (b & 1)) * 9;
+#pragma unroll
+                        for (int rc = 0; rc < 9; ++rc) {
+                            const int j = j0 + rc;
+                            v[u][rc] = __ldcs(src + (j >> 1) * 64 + (j & 1));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    R += rv[u];
+                    if (ok[u]) {
+#pragma unroll
+                        for (int rc = 0; rc < 9; ++rc) acc[rc] += v[u][rc];
+                    }
+                }
+                if (cnt <= 4) break;                                  // warp-uniform
+            }
+            if (A.assemble_matrix && lane < nb) {
+                double* out = A.val + 9 * (size_t)rb + 3 * lane;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) out[r * L + c] = acc[3 * r + c];
+                // the diagonal block is the one whose first contribution is (e, a) -> b == a
+                const int ea0 = __shfl_sync(__activemask(), my_ea, 0);
+                if (cnt > 0 && (int)(my_inv & 15) == (ea0 & 7)) {
+                    double* dg = A.diag + 3 * (size_t)i;
+                    dg[0] = acc[0]; dg[1] = acc[4]; dg[2] = acc[8];
+                }
+                if (cnt == 0 && lane == 0) { double* dg = A.diag + 3 * (size_t)i; dg[0] = dg[1] = dg[2] = 0.0; }
+            }
+        } else {
+            gather_row_generic(A, i, k0, k1, rb, nb, lane, accs + warp * ACC_PER_WARP, R);
+        }
+        if (lane < 3) {
+            double r = R;
+            if (A.felem) r += A.felem[3 * (size_t)i + lane];
+            A.rhs[3 * (size_t)i + lane] = r;
+            A.rforce[3 * (size_t)i + lane] = -r;
+            norm2 += r * r;
+            if (r != r || r == r + 1.0) bad = true;              // NaN / Inf scan (solver_direct.f90:402-415)
+        }
+        k0 = k0n; k1 = k1n; rb = rbn; re = ren; my_ea = ea_n; my_inv = inv_n;
+        k0n = k0f; k1n = k1f; rbn = rbf; ren = ref;
+    }
+    if (bad) atomicOr(&A.S->nanflag, 1);
+    const double t = block_sum<THREADS>(norm2, red);
+    if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
+}
+
+}  // namespace en234k

@@ -322,3 +322,27 @@ def test_fortran_linkage_plugin_twins_match_oracle():
     _, _, _, fail = user_element_static(77, X, du, u, [1.0, 0.3])
     assert fail == 1
     assert uel(1, X[:12], u[:12], du[:12], [100.0, 0.3])[4] < 1.0
+
+
+def test_two_kernel_assembly_equals_row_gather_assembly(monkeypatch):
+    """k_element_blocks + k_gather_rows (default) against the single-kernel row-gather assembly (EN234_ASM=rows): both sum
+    every entry in ascending element order, so the matrices are bitwise equal; residuals agree to rounding."""
+    for element, props in (("1001", None), ("1002", (1.0, 200.0))):
+        kw = dict(jitter=0.2, element=element)
+        if props:
+            kw.update(props=list(props))
+        m = Model.from_text(synthetic_block_input(5, 4, 3, **kw))
+        rng = np.random.default_rng(3)
+        ut, du = 1e-2 * rng.standard_normal(3 * m.n_nodes), 1e-3 * rng.standard_normal(3 * m.n_nodes)
+        out = []
+        for mode in ("", "rows"):
+            monkeypatch.setenv("EN234_ASM", mode)
+            g = GpuSystem(m)
+            rf, nrm, fail = g.assemble(ut, du)
+            assert fail == 0
+            out.append((np.asarray(g.csr().data).copy(), rf.copy(), nrm))
+            g.close()
+        monkeypatch.delenv("EN234_ASM")
+        assert np.array_equal(out[0][0], out[1][0])
+        assert np.abs(out[0][1] - out[1][1]).max() <= 1e-14 * np.abs(out[1][1]).max()
+        assert abs(out[0][2] - out[1][2]) <= 1e-14 * out[1][2]

@@ -18,7 +18,7 @@ c_int_p = C.POINTER(C.c_int)
 class Stats(C.Structure):
     _fields_ = [("assemble_ms", C.c_double), ("bc_ms", C.c_double), ("solve_ms", C.c_double),
                 ("spmv_ms_avg", C.c_double), ("kernel_launches", C.c_longlong), ("last_cg_iterations", C.c_int),
-                ("last_cg_err", C.c_double)]
+                ("last_cg_err", C.c_double), ("mf_congruent", C.c_int)]
 
 
 def _dp(a):

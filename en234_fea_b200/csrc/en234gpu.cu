@@ -72,7 +72,7 @@ struct en234gpu_ctx {
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     long long graph_launches[2] = {0, 0};    // kernels inside one graph launch
     // launch geometry
-    int grid_asm = 0, grid_bc = 0, grid_spmv = 0, grid_vec = 0, grid_elem = 0, grid_gather = 0;
+    int grid_asm = 0, grid_bc = 0, grid_spmv = 0, grid_vec = 0, grid_elem = 0, grid_elem0 = 0, grid_gather = 0;
     size_t asm_smem = 0, elem_smem = 0;
     int asm_threads = THREADS, elem_threads = THREADS;
     int asm_rows = 0;            // EN234_ASM=rows: single-kernel row-gather assembly (A/B and low-memory path)
@@ -278,24 +278,52 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
     c->grid_vec = std::min(MAX_PARTIALS, std::max(1, std::min((int)((nd + VEC_THREADS - 1) / VEC_THREADS), c->n_sm * 4)));
     {
         // two-kernel assembly: element kernel (one warp per four elements) + row gather
-        int oe = 1, og = 1;
+        int oe = 1, oe0 = 1, og = 1;
         c->elem_smem = any_neo ? ElemCfg<true>::SMEM : ElemCfg<false>::SMEM;
         c->elem_threads = (any_neo ? ElemCfg<true>::NW : ElemCfg<false>::NW) * 32;
         if (any_neo) {
-            CK(cudaFuncSetAttribute(k_element_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->elem_smem));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oe, k_element_blocks<true>, c->elem_threads, c->elem_smem));
+            CK(cudaFuncSetAttribute(k_element_blocks<true, true, LoadSum>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->elem_smem));
+            CK(cudaFuncSetAttribute(k_element_blocks<true, false, LoadSum>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->elem_smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oe, k_element_blocks<true, true, LoadSum>, c->elem_threads, c->elem_smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oe0, k_element_blocks<true, false, LoadSum>, c->elem_threads, c->elem_smem));
         } else {
-            CK(cudaFuncSetAttribute(k_element_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->elem_smem));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oe, k_element_blocks<false>, c->elem_threads, c->elem_smem));
+            CK(cudaFuncSetAttribute(k_element_blocks<false, true, LoadSum>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->elem_smem));
+            CK(cudaFuncSetAttribute(k_element_blocks<false, false, LoadSum>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->elem_smem));
+            CK(cudaFuncSetAttribute(k_element_blocks<false, false, LoadMasked>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->elem_smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oe, k_element_blocks<false, true, LoadSum>, c->elem_threads, c->elem_smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oe0, k_element_blocks<false, false, LoadSum>, c->elem_threads, c->elem_smem));
         }
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&og, k_gather_rows, THREADS, 0));
         const int wpc = c->elem_threads / 32, groups = (E + 3) / 4;
         c->grid_elem = std::max(1, std::min((groups + wpc - 1) / wpc, c->n_sm * std::max(oe, 1)));
+        c->grid_elem0 = std::max(1, std::min((groups + wpc - 1) / wpc, c->n_sm * std::max(oe0, 1)));
         c->grid_gather = std::min(MAX_PARTIALS, std::max(1, std::min((N + WARPS - 1) / WARPS, c->n_sm * std::max(og, 1))));
         if (const char* e = getenv("EN234_ASM")) c->asm_rows = std::strcmp(e, "rows") == 0;
     }
     int rc = mf_setup(c->mf, mesh_of(c), conn, N, E, c->n_sm, c->ndof);
     if (rc) { delete c; return set_err("matrix-free set-up failed"); }
+    // congruent mesh (every element a translate of element 0, one linear-elastic material): the matrix-free operator
+    // multiplies by the single K_e of element 0, evaluated once by the element kernel.  EN234_MF_GENERAL=1 disables it.
+    bool cong = !any_neo && mats.size() == 1 && E > 1 && getenv("EN234_MF_GENERAL") == nullptr;
+    for (int e = 1; e < E && cong; ++e)
+        for (int a = 1; a < 8 && cong; ++a) {
+            const int n0 = conn[e], na = conn[(size_t)a * E + e], m0 = conn[0], ma = conn[(size_t)a * E];
+            cong = xs[na] - xs[n0] == xs[ma] - xs[m0] && ys[na] - ys[n0] == ys[ma] - ys[m0] && zs[na] - zs[n0] == zs[ma] - zs[m0];
+        }
+    if (cong) {
+        DevBuf<int> d_el;
+        DevBuf<double> d_K, d_R;
+        const int zero = 0;
+        std::vector<double> K0(576);
+        CK(d_el.alloc(1)); CK(d_K.alloc(576)); CK(d_R.alloc(24));
+        CK(cudaMemcpy(d_el.p, &zero, sizeof(int), cudaMemcpyHostToDevice));
+        k_element_batch<<<1, 64, 0, c->stream>>>(mesh_of(c), 1, d_el.p, c->ut.p, c->du.p, d_K.p, d_R.p, c->S.p);
+        CK(cudaMemcpyAsync(K0.data(), d_K.p, 576 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemset(c->S.p, 0, sizeof(CgScalars)));
+        const int rcs = mf_set_congruent(c->mf, K0.data(), N, adj_ptr, adj, slot, browptr, bcol);
+        if (rcs == 1) { delete c; return set_err("matrix-free set-up failed (congruent mesh row table)"); }
+    }
     *out = c;
     return 0;
 }
@@ -379,19 +407,26 @@ int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail
         if (c->Re.n < need_re) CK(c->Re.alloc(need_re));
         ElemArgs EA;
         EA.M = mesh_of(c);
-        EA.ut = c->ut.p; EA.du = c->du.p; EA.Ke = c->Ke.p; EA.Re = c->Re.p; EA.S = c->S.p;
-        EA.assemble_matrix = with_matrix;
-        if (c->any_neo) k_element_blocks<true><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA);
-        else k_element_blocks<false><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA);
+        EA.Ke = c->Ke.p; EA.Re = c->Re.p; EA.S = c->S.p;
+        const LoadSum ld{c->ut.p, c->du.p};
+        if (c->any_neo && with_matrix) k_element_blocks<true, true, LoadSum><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
+        else if (c->any_neo) k_element_blocks<true, false, LoadSum><<<c->grid_elem0, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
+        else if (with_matrix) k_element_blocks<false, true, LoadSum><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
+        else k_element_blocks<false, false, LoadSum><<<c->grid_elem0, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
         GatherArgs G;
         G.M = EA.M; G.Ke = c->Ke.p; G.Re = c->Re.p; G.felem = felem;
         G.val = c->val.p; G.rhs = c->rhs.p; G.rforce = c->rforce.p; G.partials = c->part.p; G.S = c->S.p;
         G.assemble_matrix = with_matrix;
         if (with_matrix && c->diag.n < (size_t)c->ndof) CK(c->diag.alloc((size_t)c->ndof));
         G.diag = c->diag.p; G.inv = c->inv.p;
-        k_gather_rows<<<c->grid_gather, THREADS, 0, c->stream>>>(G);
+        if (with_matrix) {
+            k_gather_rows<<<c->grid_gather, THREADS, 0, c->stream>>>(G);
+            npart_asm = c->grid_gather;
+        } else {
+            npart_asm = std::min(MAX_PARTIALS, std::max(1, (c->N + VEC_THREADS - 1) / VEC_THREADS));
+            k_gather_residual<<<npart_asm, VEC_THREADS, 0, c->stream>>>(G);
+        }
         c->st.kernel_launches += 2;
-        npart_asm = c->grid_gather;
     }
     CK(cudaGetLastError());
     c->diag_valid = with_matrix && !c->asm_rows;
@@ -444,6 +479,7 @@ static int upload_fixed(en234gpu_ctx* c, int n_fixed, const int* fixed_dof, cons
         if (!rows.empty()) CK(cudaMemcpyAsync(c->bc_rows.p, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         c->h_fixdof = d;
+        c->mf.affected = c->bc_affected.p;
     }
     if (c->fixdof.n < d.size()) { CK(c->fixdof.alloc(d.size())); CK(c->fixval.alloc(d.size())); }
     if (!d.empty()) {
@@ -958,7 +994,7 @@ int en234gpu_set_operator_mode(en234gpu_handle c, int method) {
     return 0;
 }
 
-int en234gpu_get_stats(en234gpu_handle c, struct en234gpu_stats* s) { *s = c->st; return 0; }
+int en234gpu_get_stats(en234gpu_handle c, struct en234gpu_stats* s) { c->st.mf_congruent = c->mf.congruent ? 1 : 0; *s = c->st; return 0; }
 
 int en234gpu_bench_operator(en234gpu_handle c, int method, int warm, int reps, double* ms_per_launch) {
     CK(cudaSetDevice(c->device));

@@ -19,12 +19,9 @@ namespace en234k {
 
 struct ElemArgs {
     Mesh M;
-    const double* ut;       // dof_total      (AoS, 3 per node)
-    const double* du;       // dof_increment
     double* Ke;             // element blocks, layout above; padded to a multiple of 4 elements
     double* Re;             // element residuals [e][24]
-    CgScalars* S;           // nanflag
-    int assemble_matrix;    // 0: residual only (matrix-free solves)
+    CgScalars* S;           // nanflag (may be null)
 };
 
 template <bool NEO>
@@ -32,36 +29,114 @@ struct ElemCfg {
     static constexpr int NW = NEO ? 4 : 8;                                      // warps per CTA
     static constexpr int GS = (NEO ? GEOM_STRIDE_NEO : GEOM_STRIDE) + 10;       // + 9 stress values, odd stride
     static constexpr int G_SIG = NEO ? GEOM_STRIDE_NEO : GEOM_STRIDE;           // w * stress (9)
-    static constexpr int PER_WARP = 4 * 8 * GS;
+    static constexpr int NSTRIDE = 49;                                          // node buffer: 8 nodes x (xyz, u) + pad
+    static constexpr int PER_WARP = 4 * 8 * GS + 4 * NSTRIDE;
     static constexpr size_t SMEM = (size_t)NW * PER_WARP * sizeof(double);
 };
 
+// gauss_point_eval (en234gpu_kernels.cuh) with the element's node data (x, y, z, u1, u2, u3 per node) already staged in
+// shared memory: same operations in the same order, so the results are bitwise those of the global-memory version.
+template <int C>
+__device__ __forceinline__ void jac_acc_sm(const double* nb, const double fp[3], const double fm[3], double* J) {
+    const double xc = nb[6 * C], yc = nb[6 * C + 1], zc = nb[6 * C + 2];
+    double dn[3];
+    dshape<C>(fp, fm, dn);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        J[j] += xc * dn[j];
+        J[3 + j] += yc * dn[j];
+        J[6 + j] += zc * dn[j];
+    }
+}
+template <int C>
+__device__ __forceinline__ void grad_acc_sm(const double* nb, const double fp[3], const double fm[3], const double* Ji,
+                                            double* g, double* H) {
+    double dn[3], d[3];
+    dshape<C>(fp, fm, dn);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) d[j] = dn[0] * Ji[j] + dn[1] * Ji[3 + j] + dn[2] * Ji[6 + j];
+    g[3 * C] = d[0]; g[3 * C + 1] = d[1]; g[3 * C + 2] = d[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double u = nb[6 * C + 3 + i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) H[3 * i + j] += u * d[j];
+    }
+}
+__device__ __forceinline__ void gauss_point_eval_sm(const double* nb, int gp, double* g, GpOut& o) {
+    double fp[3], fm[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const double xi = ((gp >> j) & 1) ? EN234_GP : -EN234_GP;
+        fp[j] = 1.0 + xi;
+        fm[j] = 1.0 - xi;
+    }
+    double J[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) J[q] = 0.0;
+    jac_acc_sm<0>(nb, fp, fm, J); jac_acc_sm<1>(nb, fp, fm, J); jac_acc_sm<2>(nb, fp, fm, J); jac_acc_sm<3>(nb, fp, fm, J);
+    jac_acc_sm<4>(nb, fp, fm, J); jac_acc_sm<5>(nb, fp, fm, J); jac_acc_sm<6>(nb, fp, fm, J); jac_acc_sm<7>(nb, fp, fm, J);
+    Jac jc;
+    invert3(J, jc);
+    o.det = jc.det;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) o.H[q] = 0.0;
+    grad_acc_sm<0>(nb, fp, fm, jc.Ji, g, o.H); grad_acc_sm<1>(nb, fp, fm, jc.Ji, g, o.H);
+    grad_acc_sm<2>(nb, fp, fm, jc.Ji, g, o.H); grad_acc_sm<3>(nb, fp, fm, jc.Ji, g, o.H);
+    grad_acc_sm<4>(nb, fp, fm, jc.Ji, g, o.H); grad_acc_sm<5>(nb, fp, fm, jc.Ji, g, o.H);
+    grad_acc_sm<6>(nb, fp, fm, jc.Ji, g, o.H); grad_acc_sm<7>(nb, fp, fm, jc.Ji, g, o.H);
+    g[24] = jc.det;   // w = 1 for the 2x2x2 rule
+}
+
 // One warp per group of four elements.
+//  stage    lane = 8*g + p : coordinates and DOFs of node p of element g, loaded one group AHEAD into registers (the
+//           global-memory latency overlaps the arithmetic of the current group) and handed over through shared memory
 //  phase A  lane = 8*g + p : Gauss point p of element g — Jacobian, dN/dx, grad u, stress -> shared memory
 //  phase R  lane = 8*g + a : residual of local node a,  R_a = -sum_p w|J| sigma_p . grad N_a   (el_linelast_3Dbasic.f90:128)
 //  phase B  lane = 16*h + 4*tA + tB (two rounds, elements 2*round + h): the 2x2 tile of 3x3 blocks
 //           K_e[a][b] = sum_p w|J| (lam S + mu S^T + mu tr(S) I),  S = grad N_a (x) grad N_b
 //           — the integrand of B^T D B (el_linelast_3Dbasic.f90:130-131) with the zeros of B and D removed; the tile keeps
 //           36 accumulators in registers so every shared-memory operand is used three times.
-template <bool NEO>
-__global__ void __launch_bounds__(ElemCfg<NEO>::NW * 32, 2) k_element_blocks(ElemArgs A) {
+// BLOCKS = false: residual only (matrix-free residual assembly, and the matrix-free operator itself: with
+// Load = LoadMasked the "residual" of the displacement field x is -K_e x_e).
+template <bool NEO, bool BLOCKS, class Load>
+__global__ void __launch_bounds__(ElemCfg<NEO>::NW * 32, 2) k_element_blocks(ElemArgs A, Load ld) {
     constexpr int NW = ElemCfg<NEO>::NW, GS = ElemCfg<NEO>::GS, G_SIG = ElemCfg<NEO>::G_SIG;
     extern __shared__ double sm[];
+    if (ld.stopped()) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NS = ElemCfg<NEO>::NSTRIDE;
     double* geom = sm + (size_t)warp * ElemCfg<NEO>::PER_WARP;
+    double* nbuf = geom + 4 * 8 * GS;
     const Mesh& M = A.M;
     const int ngroups = (M.E + 3) >> 2;
     bool bad = false;
-    for (int grp = blockIdx.x * NW + warp; grp < ngroups; grp += gridDim.x * NW) {
+    double nd[6];
+    auto stage = [&](int grp) {                                      // node (lane & 7) of element 4 grp + (lane >> 3)
+        const int e = min(4 * grp + (lane >> 3), M.E - 1);           // padding lanes repeat the last element
+        const int n = M.conn[(size_t)(lane & 7) * M.E + e];
+        nd[0] = __ldg(M.x + n); nd[1] = __ldg(M.y + n); nd[2] = __ldg(M.z + n);
+        nd[3] = ld(3 * (size_t)n); nd[4] = ld(3 * (size_t)n + 1); nd[5] = ld(3 * (size_t)n + 2);
+    };
+    int grp = blockIdx.x * NW + warp;
+    if (grp < ngroups) stage(grp);
+    for (; grp < ngroups; grp += gridDim.x * NW) {
+        {
+            double* dst = nbuf + (lane >> 3) * NS + (lane & 7) * 6;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) dst[q] = nd[q];
+        }
+        __syncwarp();
+        if (grp + gridDim.x * NW < ngroups) stage(grp + gridDim.x * NW);
         // ---------------- phase A
         {
             const int g = lane >> 3, p = lane & 7;
-            const int e = min(4 * grp + g, M.E - 1);                 // padding lanes repeat the last element
+            const int e = min(4 * grp + g, M.E - 1);
             const bool valid = 4 * grp + g < M.E;
             const Material mat = M.mats[M.mat[e]];
             double* gg = geom + (g * 8 + p) * GS;
             GpOut gp;
-            gauss_point_eval(M, e, p, LoadSum{A.ut, A.du}, gg, gp);
+            gauss_point_eval_sm(nbuf + g * NS, p, gg, gp);
             if (valid && !(gp.det != 0.0)) bad = true;               // zero / NaN Jacobian (Element_Utilities.f90:108-112)
             double s[9];
             if (NEO && mat.kind == 1) {
@@ -99,7 +174,7 @@ __global__ void __launch_bounds__(ElemCfg<NEO>::NW * 32, 2) k_element_blocks(Ele
             }
         }
         // ---------------- phase B
-        if (A.assemble_matrix) {
+        if (BLOCKS) {
             const int h = lane >> 4, tA = (lane >> 2) & 3, tB = lane & 3;
 #pragma unroll 1
             for (int round = 0; round < 2; ++round) {
@@ -165,7 +240,7 @@ __global__ void __launch_bounds__(ElemCfg<NEO>::NW * 32, 2) k_element_blocks(Ele
         }
         __syncwarp();
     }
-    if (bad) atomicOr(&A.S->nanflag, 1);
+    if (bad && A.S) atomicOr(&A.S->nanflag, 1);
 }
 
 struct GatherArgs {
@@ -318,6 +393,37 @@ __global__ void __launch_bounds__(THREADS, 2) k_gather_rows(GatherArgs A) {
     }
     if (bad) atomicOr(&A.S->nanflag, 1);
     const double t = block_sum<THREADS>(norm2, red);
+    if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
+}
+
+// Residual-only assembly (matrix-free solves): one thread per node sums the node's element residual entries in
+// ascending element order; rhs, rforce = -rhs, ||rhs||^2 partials and the NaN scan as in k_gather_rows.
+__global__ void __launch_bounds__(VEC_THREADS) k_gather_residual(GatherArgs A) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    const Mesh& M = A.M;
+    double norm2 = 0.0;
+    bool bad = false;
+    for (int i = blockIdx.x * VEC_THREADS + threadIdx.x; i < M.N; i += gridDim.x * VEC_THREADS) {
+        const int k0 = M.adj_ptr[i], k1 = M.adj_ptr[i + 1];
+        double r[3] = {0.0, 0.0, 0.0};
+        for (int k = k0; k < k1; ++k) {
+            const int ea = M.adj[k];
+            const double* f = A.Re + (size_t)(ea >> 3) * 24 + 3 * (ea & 7);
+            r[0] += __ldcs(f); r[1] += __ldcs(f + 1); r[2] += __ldcs(f + 2);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const size_t d = 3 * (size_t)i + c;
+            double v = r[c];
+            if (A.felem) v += A.felem[d];
+            A.rhs[d] = v;
+            A.rforce[d] = -v;
+            norm2 += v * v;
+            if (v != v || v == v + 1.0) bad = true;
+        }
+    }
+    if (bad) atomicOr(&A.S->nanflag, 1);
+    const double t = block_sum<VEC_THREADS>(norm2, red);
     if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
 }
 

@@ -146,11 +146,14 @@ struct LoadSum {                       // u = dof_total + dof_increment         
     const double* __restrict__ ut;
     const double* __restrict__ du;
     __device__ __forceinline__ double operator()(size_t d) const { return ut[d] + du[d]; }
+    __device__ __forceinline__ bool stopped() const { return false; }
 };
 struct LoadMasked {                    // x with prescribed DOFs zeroed (operator P A P of the matrix-free solve)
     const double* __restrict__ x;
     const uint8_t* __restrict__ cflag; // may be null
+    const CgScalars* stop = nullptr;   // PCG stop flag: kernels of a captured iteration exit at once when set
     __device__ __forceinline__ double operator()(size_t d) const { return (cflag && cflag[d]) ? 0.0 : x[d]; }
+    __device__ __forceinline__ bool stopped() const { return stop != nullptr && stop->stop != 0; }
 };
 
 template <int C, class Load>

@@ -2,17 +2,50 @@
 // path — its CG SpMV, src/solver_conjugate_gradient.f90:877-883, always reads an assembled matrix).
 // K_e x_e is evaluated as the internal force of the linear-elastic element for the displacement field x
 // (the integrand of el_linelast_3Dbasic.f90:124-128 with u := x), never forming K_e.
-// Determinism without atomics: elements are greedily coloured so that no two elements of a colour share a node;
-// colours are processed by successive launches, each element of a colour read-modify-writes its 8 node rows.
+// Operator application (mf_apply): the batched element kernel of the assembly (k_element_blocks, residual-only
+// instantiation, reading the masked vector x instead of the DOFs) leaves f_e = -K_e x_e in the element scratch and
+// k_mf_gather sums every node's contributions in ascending element order — no atomics, no colouring, deterministic.
+// The Jacobi diagonal (mf_diag, once per boundary-condition pass) is still integrated colour by colour: elements are
+// greedily coloured so that no two elements of a colour share a node, colours are processed by successive launches.
 #pragma once
 #include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 
-#include "en234gpu_kernels.cuh"
+#include "en234gpu_cg.cuh"
+#include "en234gpu_elem.cuh"
 
 namespace en234k {
 
+// the dominant distinct row (27 blocks: an interior node of a hex mesh), passed BY VALUE: kernel parameters live in the
+// constant bank, so the fully unrolled fast path uses its 243 values as immediate constant operands of the FMAs —
+// no value loads at all
+struct DominantRow { double v[243]; };
+
 struct MfData {
+    double* d_fe = nullptr;         // element force scratch [e][24]
+    // congruent-mesh fast path: every element is a translate of element 0 (bitwise equal node offsets, same material),
+    // so one 24x24 K_e serves the whole mesh and a block row is determined by WHICH local nodes of its adjacent elements
+    // the node is (and where their columns sit in the row): a few dozen distinct rows on a structured block.  The
+    // operator is then a block-CSR SpMV whose values come from the table of distinct rows (k_stencil_nodes): no global
+    // matrix, HBM traffic = column indices + vectors.
+    bool congruent = false;
+    double* d_st_val = nullptr;     // concatenated distinct rows, [r][block][c] each
+    int* d_st_off = nullptr;        // start of each distinct row in d_st_val
+    int* d_st_pid = nullptr;        // distinct-row id of every block row
+    int* d_st_nb = nullptr;         // blocks per distinct row
+    int* d_perm = nullptr;          // pattern-sorted row order
+    int n_dom = 0;                  // rows of the dominant distinct row (first in the sorted order)
+    DominantRow dom;
+    int* d_bcolT = nullptr;         // ELL-transposed block columns in sorted order (coalesced for one thread per row)
+    double* d_xs = nullptr;         // masked, component-major copy of the operand
+    int n_patterns = 0;
+    int grid_spmv = 0;
+    const uint8_t* affected = nullptr;   // per node: prescribed or coupled to a prescribed DOF (set with the BC list)
+    int grid_elem = 0, elem_threads = 0, grid_gather = 0;
+    size_t elem_smem = 0;
     int n_colors = 0;
     std::vector<int> color_ptr;     // host
     int* d_elist = nullptr;         // elements grouped by colour, ascending within a colour
@@ -118,6 +151,168 @@ __global__ void k_fix_diag(int n, const uint8_t* cflag, const uint8_t* owned, do
     if (d < n && cflag[d]) diag[d] = (owned == nullptr || owned[d / 3]) ? 1.0 : 0.0;
 }
 
+struct StencilArgs {
+    int N;
+    int n_dom;                     // the first n_dom rows of the pattern-sorted order all have the dominant distinct row
+    const int* perm;               // pattern-sorted position t -> block row
+    const int* bcolT;              // ELL-transposed block columns in sorted order: bcolT[s * N + t] = s-th column of row perm[t]
+    const double* st_val;          // concatenated distinct rows, [r][block][c] each
+    const int* st_off;             // start of each distinct row
+    const int* st_nb;              // number of blocks of each distinct row
+    const int* st_pid;             // distinct-row id per sorted position
+    const uint8_t* cflag;          // per DOF: 1 = prescribed (null: none)
+    const uint8_t* affected;       // per node: row is prescribed or couples to a prescribed DOF (null: test cflag always)
+    const uint8_t* owned;
+    const double* x;
+    const double* xs;              // masked x, component-major: xs[c * N + node] (written by k_mask_soa)
+    double* y;
+    double* partials;
+    const CgScalars* S;
+};
+
+// xs[c][node] = P x: prescribed DOFs zeroed, AoS (u1 u2 u3 per node, the reference layout) -> component-major, so that
+// the per-thread gathers of k_stencil_nodes touch 8-byte-stride sectors instead of 24-byte-stride ones
+__global__ void k_mask_soa(int N, const uint8_t* cflag, const double* __restrict__ x, double* __restrict__ xs,
+                           const CgScalars* S) {
+    if (S && S->stop) return;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= 3 * N) return;
+    xs[(size_t)(d % 3) * N + d / 3] = (cflag && cflag[d]) ? 0.0 : x[d];
+}
+
+// y = (P A P + (I - P)) x for a congruent mesh, ONE THREAD PER NODE ROW, rows visited in pattern-sorted order so that a
+// warp's 32 rows share one distinct row.  (The warp-per-row SpMV spends ~170 warp instructions per row on index
+// pipelining and three warp reductions — fine while 2 kB of matrix values stream past per row, but that is all that is
+// left once the values come from a table.)  A thread walks its row's blocks: column index from the ELL-transposed index
+// array (coalesced across the warp), three x values, nine FMAs.  Dominant-row CTAs take the unrolled constant-operand
+// path; the others read their values from the table (same address for every lane of a warp: one L1 sector per load).
+#ifndef STENCIL_CHUNK
+#define STENCIL_CHUNK 9
+#endif
+#ifndef STENCIL_OCC
+#define STENCIL_OCC 3
+#endif
+__global__ void __launch_bounds__(VEC_THREADS, STENCIL_OCC) k_stencil_nodes(StencilArgs A, const __grid_constant__ DominantRow D) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    if (A.S && A.S->stop) return;
+    double dot = 0.0;
+    const int N = A.N;
+    for (int t0 = blockIdx.x * VEC_THREADS; t0 < N; t0 += gridDim.x * VEC_THREADS) {
+        const int t = t0 + threadIdx.x;
+        double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+        if (t0 + VEC_THREADS <= A.n_dom) {                       // CTA-uniform: 256 dominant rows
+            const int* bc = A.bcolT + t;
+            const double* xs0 = A.xs;
+            const double* xs1 = A.xs + (size_t)N;
+            const double* xs2 = A.xs + 2 * (size_t)N;
+            int col[27];                                         // all column indices first: one HBM latency per row
+#pragma unroll
+            for (int s = 0; s < 27; ++s) col[s] = __ldg(bc + (size_t)s * N);
+#pragma unroll
+            for (int s0 = 0; s0 < 27; s0 += STENCIL_CHUNK) {
+                double xv[STENCIL_CHUNK][3];
+#pragma unroll
+                for (int u = 0; u < STENCIL_CHUNK; ++u) {
+                    xv[u][0] = __ldg(xs0 + col[s0 + u]); xv[u][1] = __ldg(xs1 + col[s0 + u]); xv[u][2] = __ldg(xs2 + col[s0 + u]);
+                }
+#pragma unroll
+                for (int u = 0; u < STENCIL_CHUNK; ++u) {
+                    const int s = s0 + u;
+                    const double x0 = xv[u][0], x1 = xv[u][1], x2 = xv[u][2];
+                    y0 += D.v[3 * s] * x0;       y0 += D.v[3 * s + 1] * x1;       y0 += D.v[3 * s + 2] * x2;
+                    y1 += D.v[81 + 3 * s] * x0;  y1 += D.v[81 + 3 * s + 1] * x1;  y1 += D.v[81 + 3 * s + 2] * x2;
+                    y2 += D.v[162 + 3 * s] * x0; y2 += D.v[162 + 3 * s + 1] * x1; y2 += D.v[162 + 3 * s + 2] * x2;
+                }
+            }
+        } else if (t < N) {
+            const int pid = A.st_pid[t], nb = A.st_nb[pid], L = 3 * nb;
+            const double* v = A.st_val + A.st_off[pid];
+            for (int s0 = 0; s0 < nb; s0 += 9) {
+                int col[9];
+#pragma unroll
+                for (int u = 0; u < 9; ++u) col[u] = s0 + u < nb ? __ldg(A.bcolT + (size_t)(s0 + u) * N + t) : 0;
+                double xv[9][3];
+#pragma unroll
+                for (int u = 0; u < 9; ++u) {
+                    xv[u][0] = __ldg(A.xs + col[u]); xv[u][1] = __ldg(A.xs + (size_t)N + col[u]); xv[u][2] = __ldg(A.xs + 2 * (size_t)N + col[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 9; ++u) {
+                    if (s0 + u < nb) {
+                        const double* vs = v + 3 * (s0 + u);
+                        y0 += __ldg(vs) * xv[u][0];         y0 += __ldg(vs + 1) * xv[u][1];         y0 += __ldg(vs + 2) * xv[u][2];
+                        y1 += __ldg(vs + L) * xv[u][0];     y1 += __ldg(vs + L + 1) * xv[u][1];     y1 += __ldg(vs + L + 2) * xv[u][2];
+                        y2 += __ldg(vs + 2 * L) * xv[u][0]; y2 += __ldg(vs + 2 * L + 1) * xv[u][1]; y2 += __ldg(vs + 2 * L + 2) * xv[u][2];
+                    }
+                }
+            }
+        }
+        if (t < N) {
+            const int i = A.perm[t];
+            const bool aff = A.cflag != nullptr && (A.affected == nullptr || A.affected[i] != 0);
+            double yv[3] = {y0, y1, y2};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const size_t d = 3 * (size_t)i + c;
+                const double xv = A.x[d];
+                if (aff && A.cflag[d]) yv[c] = (A.owned == nullptr || A.owned[i]) ? xv : 0.0;
+                A.y[d] = yv[c];
+                dot += yv[c] * xv;
+            }
+        }
+    }
+    const double tsum = block_sum<VEC_THREADS>(dot, red);
+    if (threadIdx.x == 0) A.partials[blockIdx.x] = tsum;
+}
+
+// y_i = -sum over the node's (element, local node) entries of the element scratch, ascending element order;
+// y_row = x_row on prescribed rows (unit diagonal on the owner rank only); partial of x.y over all local rows.
+// Eight lanes per node: lane k fetches adjacency entry k (all fetches of a node in flight together), the three
+// components are then summed across the eight lanes in ascending k by a shuffle chain (fixed order: deterministic).
+__global__ void __launch_bounds__(VEC_THREADS) k_mf_gather(int N, const int* __restrict__ adj_ptr, const int* __restrict__ adj,
+                                                            const double* __restrict__ fe, const uint8_t* cflag,
+                                                            const uint8_t* owned, const double* __restrict__ x, double* y,
+                                                            double* partials, const CgScalars* S) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    if (S && S->stop) return;
+    double dot = 0.0;
+    const int lane = threadIdx.x & 31, k = lane & 7, base = lane & 24;
+    const int per_cta = VEC_THREADS / 8;
+    for (int i0 = blockIdx.x * per_cta; i0 < N; i0 += gridDim.x * per_cta) {
+        const int i = i0 + (threadIdx.x >> 3);
+        const bool live = i < N;
+        const int k0 = live ? adj_ptr[i] : 0, k1 = live ? adj_ptr[i + 1] : 0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        int kmax = k1 - k0;                                       // warp-uniform trip count: the longest of the 4 rows
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, 8));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, 16));
+        for (int kk = 0; kk < kmax; kk += 8) {
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            if (k0 + kk + k < k1) {
+                const int ea = adj[k0 + kk + k];
+                const double* f = fe + (size_t)(ea >> 3) * 24 + 3 * (ea & 7);
+                v0 = __ldcs(f); v1 = __ldcs(f + 1); v2 = __ldcs(f + 2);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {                         // padding entries add 0
+                s0 += __shfl_sync(0xffffffffu, v0, base + u);
+                s1 += __shfl_sync(0xffffffffu, v1, base + u);
+                s2 += __shfl_sync(0xffffffffu, v2, base + u);
+            }
+        }
+        if (live && k < 3) {
+            const size_t d = 3 * (size_t)i + k;
+            double v = -(k == 0 ? s0 : (k == 1 ? s1 : s2));
+            const double xv = x[d];
+            if (cflag && cflag[d]) v = (owned == nullptr || owned[i]) ? xv : 0.0;
+            y[d] = v;
+            dot += v * xv;
+        }
+    }
+    const double t = block_sum<VEC_THREADS>(dot, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
 inline int mf_setup(MfData& mf, const Mesh& M, const std::vector<int>& conn /*SoA, host*/, int N, int E, int n_sm, int ndof) {
     // greedy colouring in element order: colour = smallest not used by an earlier element sharing a node
     std::vector<unsigned long long> node_mask(N, 0ULL);
@@ -142,24 +337,136 @@ inline int mf_setup(MfData& mf, const Mesh& M, const std::vector<int>& conn /*So
     if (cudaMalloc((void**)&mf.d_elist, (size_t)E * sizeof(int)) != cudaSuccess) return 1;
     cudaMemcpy(mf.d_elist, elist.data(), (size_t)E * sizeof(int), cudaMemcpyHostToDevice);
     mf.grid_vec = std::min(MAX_PARTIALS, std::max(1, std::min((ndof + VEC_THREADS - 1) / VEC_THREADS, n_sm * 8)));
-    mf.n_partials = mf.grid_vec;
-    mf.launches_per_apply = ncol + 1;
+    // operator application: element kernel (one warp per four elements, persistent) + node gather
+    if (cudaMalloc((void**)&mf.d_fe, (size_t)E * 24 * sizeof(double)) != cudaSuccess) return 1;
+    mf.elem_smem = ElemCfg<false>::SMEM;
+    mf.elem_threads = ElemCfg<false>::NW * 32;
+    int occ = 1;
+    if (cudaFuncSetAttribute(k_element_blocks<false, false, LoadMasked>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)mf.elem_smem) != cudaSuccess) return 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_element_blocks<false, false, LoadMasked>, mf.elem_threads,
+                                                      mf.elem_smem) != cudaSuccess) return 1;
+    const int wpc = mf.elem_threads / 32, groups = (E + 3) / 4;
+    mf.grid_elem = std::max(1, std::min((groups + wpc - 1) / wpc, n_sm * std::max(occ, 1)));
+    mf.grid_gather = std::min(MAX_PARTIALS, std::max(1, (N + VEC_THREADS / 8 - 1) / (VEC_THREADS / 8)));
+    mf.n_partials = mf.grid_gather;
+    mf.launches_per_apply = 2;
     (void)M;
     return 0;
 }
-inline void mf_release(MfData& mf) { if (mf.d_elist) cudaFree(mf.d_elist); mf.d_elist = nullptr; }
+// Table of distinct block rows of a congruent mesh from the K_e of the representative element (reference layout
+// element_stiffness(ROW,COL), column-major 24x24).  Each row is summed over its adjacent elements in ascending element
+// order — exactly what the assembly produces when every element has this K_e.  Returns 1 on failure, 2 when the mesh
+// has too many distinct rows for the table to pay off (the caller then keeps the element-by-element operator).
+inline int mf_set_congruent(MfData& mf, const double* Ke_colmajor, int N, const std::vector<int>& adj_ptr,
+                            const std::vector<int>& adj, const std::vector<uint8_t>& slot, const std::vector<int>& browptr,
+                            const std::vector<int>& bcol) {
+    std::map<std::string, int> ids;
+    std::vector<int> pid(N), off;
+    std::vector<double> val;
+    std::string key;
+    for (int i = 0; i < N; ++i) {
+        const int k0 = adj_ptr[i], k1 = adj_ptr[i + 1], nb = browptr[i + 1] - browptr[i], L = 3 * nb;
+        if (nb > 32) return 2;                                   // k_spmv_stencil keeps at most 96 scalar columns per row
+        key.assign(1, (char)nb);
+        for (int k = k0; k < k1; ++k) {
+            key.push_back((char)(adj[k] & 7));
+            key.append(reinterpret_cast<const char*>(&slot[(size_t)k * 8]), 8);
+        }
+        auto it = ids.find(key);
+        if (it == ids.end()) {
+            if (ids.size() >= 4096) return 2;
+            it = ids.emplace(key, (int)ids.size()).first;
+            off.push_back((int)val.size());
+            val.resize(val.size() + (size_t)9 * nb, 0.0);
+            double* row = val.data() + off.back();
+            for (int k = k0; k < k1; ++k) {
+                const int a = adj[k] & 7;
+                for (int b = 0; b < 8; ++b) {
+                    const int sl = slot[(size_t)k * 8 + b];
+                    for (int r = 0; r < 3; ++r)
+                        for (int c = 0; c < 3; ++c) row[r * L + 3 * sl + c] += Ke_colmajor[(3 * a + r) + 24 * (3 * b + c)];
+                }
+            }
+        }
+        pid[i] = it->second;
+    }
+    mf.n_patterns = (int)ids.size();
+    // pattern-sorted row order: the most frequent distinct row with 27 blocks first (unrolled fast path), then by id
+    std::vector<long long> freq(ids.size(), 0);
+    for (int i = 0; i < N; ++i) freq[pid[i]]++;
+    std::vector<int> nbp(ids.size());
+    for (int i = 0; i < N; ++i) nbp[pid[i]] = browptr[i + 1] - browptr[i];
+    int dom = -1;
+    for (size_t q = 0; q < ids.size(); ++q)
+        if (nbp[q] == 27 && (dom < 0 || freq[q] > freq[dom])) dom = (int)q;
+    std::vector<int> perm(N);
+    for (int i = 0; i < N; ++i) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+        const int ka = pid[a] == dom ? -1 : pid[a], kb = pid[b] == dom ? -1 : pid[b];
+        return ka < kb;
+    });
+    mf.n_dom = dom >= 0 ? (int)freq[dom] : 0;
+    std::memset(mf.dom.v, 0, sizeof(mf.dom.v));
+    if (dom >= 0) std::memcpy(mf.dom.v, val.data() + off[dom], 243 * sizeof(double));
+    std::vector<int> pidp(N);
+    int width = 0;
+    for (int t = 0; t < N; ++t) { pidp[t] = pid[perm[t]]; width = std::max(width, nbp[pidp[t]]); }
+    std::vector<int> bt((size_t)width * N, 0);
+    for (int t = 0; t < N; ++t) {
+        const int i = perm[t];
+        for (int sidx = 0; sidx < browptr[i + 1] - browptr[i]; ++sidx) bt[(size_t)sidx * N + t] = bcol[(size_t)browptr[i] + sidx];
+    }
+    auto up = [](void** d, const void* h, size_t bytes) {
+        if (cudaMalloc(d, bytes) != cudaSuccess) return 1;
+        return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : 1;
+    };
+    if (up((void**)&mf.d_st_val, val.data(), val.size() * sizeof(double))) return 1;
+    if (up((void**)&mf.d_st_off, off.data(), off.size() * sizeof(int))) return 1;
+    if (up((void**)&mf.d_st_nb, nbp.data(), nbp.size() * sizeof(int))) return 1;
+    if (up((void**)&mf.d_st_pid, pidp.data(), (size_t)N * sizeof(int))) return 1;
+    if (up((void**)&mf.d_perm, perm.data(), (size_t)N * sizeof(int))) return 1;
+    if (up((void**)&mf.d_bcolT, bt.data(), bt.size() * sizeof(int))) return 1;
+    if (cudaMalloc((void**)&mf.d_xs, (size_t)3 * N * sizeof(double)) != cudaSuccess) return 1;
+    mf.grid_spmv = std::min(MAX_PARTIALS, std::max(1, (N + VEC_THREADS - 1) / VEC_THREADS));
+    mf.n_partials = mf.grid_spmv;
+    mf.launches_per_apply = 2;
+    mf.congruent = true;
+    return 0;
+}
+inline void mf_release(MfData& mf) {
+    if (mf.d_elist) cudaFree(mf.d_elist);
+    if (mf.d_fe) cudaFree(mf.d_fe);
+    if (mf.d_st_val) cudaFree(mf.d_st_val);
+    if (mf.d_st_off) cudaFree(mf.d_st_off);
+    if (mf.d_st_pid) cudaFree(mf.d_st_pid);
+    if (mf.d_bcolT) cudaFree(mf.d_bcolT);
+    if (mf.d_xs) cudaFree(mf.d_xs);
+    if (mf.d_st_nb) cudaFree(mf.d_st_nb);
+    if (mf.d_perm) cudaFree(mf.d_perm);
+    mf.d_bcolT = nullptr; mf.d_xs = nullptr; mf.d_st_nb = nullptr; mf.d_perm = nullptr;
+    mf.d_elist = nullptr; mf.d_fe = nullptr; mf.d_st_val = nullptr; mf.d_st_off = nullptr; mf.d_st_pid = nullptr;
+}
 
 // y = P A P x + (I-P) x ; partials of x.y.  (cflag == null: plain A x)
 inline void mf_apply(const MfData& mf, const Mesh& M, int ndof, const uint8_t* cflag, const uint8_t* owned, const double* x,
                      double* y, double* partials, const CgScalars* S, cudaStream_t s, long long* launches) {
-    cudaMemsetAsync(y, 0, (size_t)ndof * sizeof(double), s);
-    for (int c = 0; c < mf.n_colors; ++c) {
-        const int n = mf.color_ptr[c + 1] - mf.color_ptr[c];
-        if (n == 0) continue;
-        k_mf_color<0><<<(8 * n + 255) / 256, 256, 0, s>>>(M, n, mf.d_elist + mf.color_ptr[c], cflag, x, y, S);
+    (void)ndof;
+    ElemArgs EA;
+    EA.M = M; EA.Ke = nullptr; EA.Re = mf.d_fe; EA.S = nullptr;
+    if (mf.congruent) {
+        StencilArgs A;
+        A.N = M.N; A.n_dom = mf.n_dom; A.perm = mf.d_perm; A.bcolT = mf.d_bcolT; A.st_val = mf.d_st_val;
+        A.st_off = mf.d_st_off; A.st_nb = mf.d_st_nb; A.st_pid = mf.d_st_pid; A.cflag = cflag; A.affected = cflag ? mf.affected : nullptr; A.owned = owned;
+        A.x = x; A.xs = mf.d_xs; A.y = y; A.partials = partials; A.S = S;
+        k_mask_soa<<<(3 * M.N + 255) / 256, 256, 0, s>>>(M.N, cflag, x, mf.d_xs, S);
+        k_stencil_nodes<<<mf.grid_spmv, VEC_THREADS, 0, s>>>(A, mf.dom);
+        *launches += 2;
+        return;
     }
-    k_mf_finish<<<mf.grid_vec, VEC_THREADS, 0, s>>>(ndof, cflag, owned, x, y, partials, S);
-    *launches += mf.n_colors + 1;
+    k_element_blocks<false, false, LoadMasked><<<mf.grid_elem, mf.elem_threads, mf.elem_smem, s>>>(EA, LoadMasked{x, cflag, S});
+    k_mf_gather<<<mf.grid_gather, VEC_THREADS, 0, s>>>(M.N, M.adj_ptr, M.adj, mf.d_fe, cflag, owned, x, y, partials, S);
+    *launches += 2;
 }
 inline void mf_diag(const MfData& mf, const Mesh& M, int ndof, const double* any_vec, double* diag, cudaStream_t s,
                     long long* launches) {

@@ -1,5 +1,2 @@
-set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for n in 64 128; do python tools/phase_times.py $n; done
-python tools/phase_times.py 96 1002
-ncu --set full --import-source on --clock-control none -k regex:"k_element_blocks|k_gather_rows" -c 2 -o gpurun_out/asm2k_b -f python tools/phase_times.py 64 1001 1 > gpurun_out/ncu_asm.log 2>&1
+cd en234_fea_b200/csrc
+for v in c9o2 c3o4 c9o3; do cp liben234gpu_$v.so liben234gpu.so; echo $v; (cd ../..; python tools/mf_times.py 128 0.0; python tools/mf_times.py 64 0.0); done

@@ -156,6 +156,8 @@ struct en234gpu_stats {
     long long kernel_launches;   /* cumulative number of kernels launched by this handle */
     int last_cg_iterations;
     double last_cg_err;          /* (r.r)/(b.b) at exit */
+    int mf_congruent;            /* 1: every element is a translate of element 0 (bitwise) with one material, and the
+                                    matrix-free operator multiplies by that single K_e */
 };
 int en234gpu_get_stats(en234gpu_handle h, struct en234gpu_stats* s);
 /* average device time (ms, CUDA events on the handle's stream) of `reps` back-to-back launches of the operator

@@ -346,3 +346,27 @@ def test_two_kernel_assembly_equals_row_gather_assembly(monkeypatch):
         assert np.array_equal(out[0][0], out[1][0])
         assert np.abs(out[0][1] - out[1][1]).max() <= 1e-14 * np.abs(out[1][1]).max()
         assert abs(out[0][2] - out[1][2]) <= 1e-14 * out[1][2]
+
+
+def test_matrix_free_congruent_mesh_fast_path():
+    """Uniform block with power-of-two spacing: every element is a bitwise translate of element 0, the matrix-free
+    operator multiplies by the single K_e (k_mf_congruent).  Same operator as the assembled matrix, same solution."""
+    m = Model.from_text(synthetic_block_input(8, 4, 16, jitter=0.0, cg_tolerance=1e-26, cg_maxit=5000))
+    g = GpuSystem(m)
+    assert g.stats().mf_congruent == 1
+    n = g.ndof
+    x = np.random.default_rng(7).standard_normal(n)
+    g.assemble(np.zeros(n), np.zeros(n), None)
+    A = g.csr()
+    g.apply_boundaryconditions(None, np.zeros(0, np.int32), np.zeros(0))
+    assert relmax(g.apply_operator(x, 1), A @ x) < 1e-12
+    res_mf = g.run_static(method=1, check_linear_cg=True)
+    ref = ob.OracleModel(m.arrays(), solvertype=1).run_static()
+    assert relmax(res_mf["dof_total"], ref["dof_total"]) < TOL_U
+    assert relmax(res_mf["rforce"], ref["rforce"]) < TOL_U
+    g.close()
+    # a jittered mesh (and a non-dyadic spacing) must not take the fast path
+    for kw in (dict(jitter=0.2), dict(jitter=0.0)):
+        g2 = GpuSystem(Model.from_text(synthetic_block_input(3 if kw["jitter"] == 0.0 else 4, **kw)))
+        assert g2.stats().mf_congruent == 0
+        g2.close()

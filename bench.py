@@ -12,6 +12,10 @@ value   : inputs resident in HBM (device-resident entry points);  e2e : host-buf
           arrays, host<->device copies inside the timed region.
 Workloads: N=1 -> BASELINE configs[1] (64^3); N>1 -> weak family with 64^3 elements per GPU, slabs along z
           (N=8 is configs[2], 128^3).  --workload c3 forces the 128^3 block at any N.
+          --workload c4: configs[3], 96^3 neo-Hookean block, 4 increments of Newton-Raphson with re-assembly (1 GPU; a step
+                         is the whole 4-increment analysis through the host driver).
+          --workload c5: configs[4], matrix-free PCG on 256^3 at 8 GPUs (128^3 per GPU-equivalent at N=1: 128^3);
+                         --jitter 0 selects the uniform mesh (congruent-element operator), default 0.2 the general one.
 """
 import argparse
 import json
@@ -33,6 +37,12 @@ CG_MAXIT = 20000
 
 
 def workload(n_gpus, name):
+    if name == "c4":
+        return (96, 96, 96), "c4: synthetic 96^3 hex8 neo-Hookean block, 4 increments, Newton-Raphson with re-assembly (BASELINE configs[3])"
+    if name == "c5":
+        dims = {1: (128, 128, 128), 2: (128, 128, 256), 4: (128, 256, 256), 8: (256, 256, 256)}.get(n_gpus, (128, 128, 128 * n_gpus))
+        return dims, "c5: synthetic %dx%dx%d hex8 block, matrix-free PCG, 128^3 elements per GPU%s" % (
+            dims + (" (= BASELINE configs[4])" if n_gpus == 8 else "",))
     if name == "c3":
         return (128, 128, 128), "c3: synthetic 128^3 hex8 linear-elastic block (BASELINE configs[2])"
     if name == "c2" or n_gpus == 1:
@@ -85,6 +95,74 @@ class ClockSampler:
         except ValueError:
             pass
         return out
+
+
+def measured_traffic(kernel, elements_per_gpu):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture) of the
+    dominant kernel at this per-GPU size, from the committed profiles/traffic.json; None when that size was not captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    for row in json.load(open(p)):
+        if kernel.startswith(row["kernel"]) and row["elements_per_gpu"] == elements_per_gpu:
+            return row["dram_bytes_per_launch"]
+    return None
+
+
+def run_newton(args):
+    """configs[3]: neo-Hookean block, prescribed stretch ramp over 4 increments, NONLINEAR (tolerance 1e-5, <= 15
+    iterations), full re-assembly in every Newton iteration; the whole analysis runs through the host driver
+    (src/staticstep.f90 loop restated in csrc/host/staticstep.cpp).  value: device-resident state; e2e: host-buffer API."""
+    import torch
+    from en234_fea_b200 import GpuSystem, Model, synthetic_block_input
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py --workload c4 is a 1-GPU measurement")
+    dims, wname = workload(1, "c4")
+    model = Model.from_text(synthetic_block_input(*dims, jitter=args.jitter, element="U2", props=[1.0, 200.0], load="stretch",
+                                                  steps=4, nonlinear=(1e-5, 15), cg_tolerance=CG_TOL, cg_maxit=CG_MAXIT))
+    gpu = GpuSystem(model, device=0)
+    n = gpu.ndof
+    sampler = ClockSampler(0)
+    res = None
+    for _ in range(max(args.warmup, 1)):
+        res = gpu.run_static(method=0)
+    torch.cuda.synchronize()
+    l0 = gpu.stats().kernel_launches
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = gpu.run_static(method=0)
+    torch.cuda.synchronize()
+    ms_dev = (time.perf_counter() - t0) * 1e3 / args.steps
+    launches = gpu.stats().kernel_launches - l0
+    clocks = sampler.stop()
+    t0 = time.perf_counter()
+    res_h = gpu.run_static(method=0, use_host_api=True)
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    its = int(res["cg_iterations"].sum())
+    st = gpu.stats()
+    nnzb = gpu.nnz_blocks()
+    alg_it = 8 * 9 * nnzb + 4 * nnzb + 4 * (gpu.n_nodes + 1) + 16 * n + 104 * n
+    peak, peak_src = peaks()
+    n_solves = len(res["cg_iterations"])
+    line = {"metric": METRIC, "value": n * its / (ms_dev * 1e-3) / 1e6, "unit": "MDOF-it/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 1), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wname, "n_dof": n, "elements": dims[0] * dims[1] * dims[2], "jitter": args.jitter,
+                       "increments": res["n_steps"], "cutbacks": res["n_cutbacks"], "newton_iterations": int(res["newton"].shape[0]),
+                       "linear_solves": n_solves, "cg_iterations": its, "cg_rule": "(r.r)/(b.b) < 1e-20",
+                       "newton_ratios": [float("%.4e" % r) for r in res["newton"][:, 5]],
+                       "timing": "host wall clock around the whole analysis (device-synchronised)",
+                       "l2": "matrix stream per PCG iteration (%.0f MB) exceeds the 126 MB L2" % ((alg_it - 104 * n) / 1e6)},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": n * int(res_h["cg_iterations"].sum()) / (ms_e2e * 1e-3) / 1e6, "unit": "MDOF-it/s",
+                    "ms_per_step": ms_e2e, "h2d_bytes_per_step": int((3 * res["newton"].shape[0] + n_solves) * n * 8),
+                    "d2h_bytes_per_step": int((2 * res["newton"].shape[0] + n_solves) * n * 8)},
+            "roofline": {"bound": "hbm", "kernel": "PCG iteration (k_spmv + vector kernels) inside the Newton loop",
+                         "achieved": alg_it * its / (ms_dev * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg_it * its / (ms_dev * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                         "phases_ms_last_call": {"assemble": st.assemble_ms, "bc": st.bc_ms, "solve": st.solve_ms}}}
+    print(json.dumps(line), flush=True)
+    gpu.close()
 
 
 def run_reference(args):
@@ -160,13 +238,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--jitter", type=float, default=0.2)
     ap.add_argument("--method", type=int, default=0, help="0 assembled block-CSR PCG, 1 matrix-free PCG")
     ap.add_argument("--ref-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c5":
+        args.method = 1
+    if args.workload == "c4":
+        return run_newton(args)
 
     import torch
     import torch.distributed as dist
@@ -182,7 +265,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dims, wname = workload(world, args.workload)
-    model = Model.from_text(synthetic_block_input(*dims, jitter=0.2, cg_tolerance=CG_TOL, cg_maxit=CG_MAXIT))
+    model = Model.from_text(synthetic_block_input(*dims, jitter=args.jitter, cg_tolerance=CG_TOL, cg_maxit=CG_MAXIT))
     ndof_global = 3 * model.n_nodes
     fe, fx, fd, fv, fc = model.evaluate_loads(0.0, 1.0)
     if world > 1:
@@ -274,17 +357,26 @@ def main():
         alg = 8 * 9 * nnzb + 4 * nnzb + 4 * (N_loc + 1) + 16 * n
         kern = "k_spmv (3x3-block CSR, FP64)"
         extra = {"algorithmic_bytes_scalar_csr": 12 * 9 * nnzb + 20 * n}
+    elif gpu.stats().mf_congruent:
+        ms_op = gpu.bench_operator(1, 5, 50)
+        nnzb = gpu.nnz_blocks()
+        # column indices (ELL, one per block) + sorted-order maps + operand read / masked copy written and read / result
+        alg = 4 * nnzb + 8 * N_loc + (8 + 1 + 8 + 8 + 8) * n
+        kern = "k_mask_soa + k_stencil_nodes (matrix-free, congruent mesh: distinct block rows from a table)"
+        extra = {"note": "uniform mesh: every element a bitwise translate of element 0; no matrix values are read"}
     else:
         ms_op = gpu.bench_operator(1, 5, 50)
-        alg = 72 * N_loc + 32 * (dims[0] * dims[1] * dims[2] // world)
-        kern = "k_mf_color x colours + k_mf_finish (matrix-free, FP64-bound on a general mesh)"
-        extra = {}
+        alg = 72 * N_loc + 32 * (dims[0] * dims[1] * dims[2] // world) + 2 * 192 * (dims[0] * dims[1] * dims[2] // world)
+        kern = "k_element_blocks<residual> + k_mf_gather (matrix-free, element by element)"
+        extra = {"note": "FP64-bound on a general mesh (about 3.2 kflop-instructions per element against ~450 B); "
+                         "the HBM fraction is reported for completeness, the binding roof is the FP64 pipe"}
     ach = alg / (ms_op * 1e-3) / 1e9
     st = gpu.stats()
     it_ms = st.solve_ms / max(st.last_cg_iterations, 1)
     b_iter = (alg + 104 * n) if args.method == 0 else (alg + 104 * n)
     roof = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "peak_source": peak_src, "traffic": None, "ms_per_launch": ms_op, "algorithmic_bytes_per_launch": alg,
+            "peak_source": peak_src, "traffic": measured_traffic(kern, dims[0] * dims[1] * dims[2] // world),
+            "ms_per_launch": ms_op, "algorithmic_bytes_per_launch": alg,
             "cg_iteration": {"ms": it_ms, "algorithmic_bytes": b_iter, "achieved": b_iter / (it_ms * 1e-3) / 1e9,
                              "frac": b_iter / (it_ms * 1e-3) / 1e9 / peak},
             "phases_ms": {"assemble": st.assemble_ms, "bc": st.bc_ms, "solve": st.solve_ms}}
@@ -293,9 +385,10 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "MDOF-it/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wname, "n_dof": ndof_global, "elements": dims[0] * dims[1] * dims[2], "jitter": 0.2,
+            "config": {"workload": wname, "n_dof": ndof_global, "elements": dims[0] * dims[1] * dims[2], "jitter": args.jitter,
                        "cg_iterations": int(its), "cg_rule": "(r.r)/(b.b) < 1e-20", "final_newton_ratio": ratio,
-                       "method": "assembled 3x3-block CSR" if args.method == 0 else "matrix-free",
+                       "method": "assembled 3x3-block CSR" if args.method == 0 else
+                                 ("matrix-free (congruent-mesh row table)" if gpu.stats().mf_congruent else "matrix-free (element by element)"),
                        "l2": "matrix stream per PCG iteration (%.0f MB) exceeds the 126 MB L2" % (alg / 1e6),
                        "step": "assemble+BC+PCG solve+re-assemble+BC (src/staticstep.f90:44-70)",
                        "collectives": comm_kind},

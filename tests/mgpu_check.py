@@ -19,10 +19,11 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dims = tuple(int(x) for x in (sys.argv[1:4] if len(sys.argv) >= 4 else (12, 10, 8 * world)))
+    jitter = float(sys.argv[4]) if len(sys.argv) >= 5 else 0.2      # 0 with power-of-two dims: congruent-mesh operator
     ok = True
     for method in (0, 1):
         for load in ("traction", "stretch"):
-            m = Model.from_text(synthetic_block_input(*dims, jitter=0.2, cg_tolerance=1e-26, cg_maxit=20000, load=load,
+            m = Model.from_text(synthetic_block_input(*dims, jitter=jitter, cg_tolerance=1e-26, cg_maxit=20000, load=load,
                                                       steps=2 if load == "stretch" else 1))
             part = Partition(m, world, rank)
             g = GpuSystem(m, device=local, part=part)
@@ -50,8 +51,8 @@ def main():
                 its, its1 = res["cg_iterations"].tolist(), ref["cg_iterations"].tolist()
                 good = eu < 1e-10 and er < 1e-10 and all(abs(a - b) <= 2 for a, b in zip(its, its1)) and \
                     res["newton"].shape == ref["newton"].shape and agree
-                print("mgpu_check [%s] world=%d mesh=%s method=%d load=%s: u err %.2e, rforce err %.2e, CG its %s vs %s, copies agree %s -> %s"
-                      % (comm_kind, world, dims, method, load, eu, er, its, its1, agree, "OK" if good else "FAIL"), flush=True)
+                print("mgpu_check [%s] world=%d mesh=%s jitter=%g congruent=%d method=%d load=%s: u err %.2e, rforce err %.2e, CG its %s vs %s, copies agree %s -> %s"
+                      % (comm_kind, world, dims, jitter, g.stats().mf_congruent, method, load, eu, er, its, its1, agree, "OK" if good else "FAIL"), flush=True)
                 ok = ok and good
                 g1.close()
             dist.barrier()

@@ -48,6 +48,7 @@ GPU_SYMBOLS = [
     "en234gpu_nnz_blocks", "en234gpu_get_csr", "en234gpu_get_rhs", "en234gpu_apply_operator",
     "en234gpu_get_unique_id", "en234gpu_comm_init", "en234gpu_set_partition", "en234gpu_get_stats",
     "en234gpu_bench_operator", "en234gpu_comm_arena", "en234gpu_comm_connect",
+    "en234gpu_n_state_variables", "en234gpu_commit_state", "en234gpu_get_state_variables", "en234gpu_set_state_variables",
 ]
 HOST_SYMBOLS = [
     "en234host_model_read", "en234host_model_from_text", "en234host_model_free", "en234host_last_error",
@@ -313,6 +314,16 @@ class GpuSystem:
 
     def nnz_blocks(self):
         return gpu_lib().en234gpu_nnz_blocks(self.h)
+
+    def state_variables(self, updated=True):
+        L = gpu_lib()
+        L.en234gpu_n_state_variables.restype = C.c_longlong
+        sv = np.zeros(L.en234gpu_n_state_variables(self.h))
+        self._ck(L.en234gpu_get_state_variables(self.h, C.c_int(1 if updated else 0), _dp(sv)))
+        return sv
+
+    def commit_state(self):
+        self._ck(gpu_lib().en234gpu_commit_state(self.h))
 
     def csr(self):
         import scipy.sparse as sp

@@ -13,6 +13,8 @@
 #include "../../include/en234gpu.h"
 #include "en234gpu_asm.cuh"
 #include "en234gpu_aux.cuh"
+#include "en234gpu_bicg.cuh"
+#include "en234gpu_c3d8.cuh"
 #include "en234gpu_elem.cuh"
 #include "en234gpu_cg.cuh"
 #include "en234gpu_mf.cuh"
@@ -85,6 +87,9 @@ struct en234gpu_ctx {
     bool diag_valid = false;
     int spmv_occ = 4;
     bool any_neo = false;
+    bool any_c3d8 = false;       // built-in C3D8 continuum elements (all elements of the mesh)
+    DevBuf<double> sv0, sv1;     // initial / updated element state variables
+    DevBuf<double> bi_z, bi_t, bi_xt, bi_b;   // BiCGSTAB work vectors
     // host copies needed for inspection
     std::vector<int> h_browptr, h_bcol;
     // multi-GPU
@@ -157,18 +162,24 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
                 m.kind = 1;
                 m.mu = element_properties[pi];
                 m.kappa = element_properties[pi + 1];
+            } else if (flag == EN234_FLAG_C3D8) {
+                if (pi + 2 > n_element_properties) { delete c; return set_err("C3D8 element needs 2 material properties (E, nu)"); }
+                m.kind = 2;                                           // abaqus_umat_elastic.for:253-308
+                m.d11 = element_properties[pi];                       // E
+                m.d12 = element_properties[pi + 1];                   // nu
             } else {
                 delete c;                                             // user_element.f90:83-86
                 return set_err("invalid element type " + std::to_string(flag) +
-                               " (device element types: 1001, 1002, U1, U2)");
+                               " (device element types: 1001, 1002, U1, U2, C3D8)");
             }
             it = matmap.emplace(key, (int)mats.size()).first;
             mats.push_back(m);
         }
         mat[e] = it->second;
     }
-    bool any_neo = false;
-    for (auto& m : mats) any_neo |= m.kind == 1;
+    bool any_neo = false, any_c3d8 = false, any_user = false;
+    for (auto& m : mats) { any_neo |= m.kind == 1; any_c3d8 |= m.kind == 2; any_user |= m.kind != 2; }
+    if (any_c3d8 && any_user) { delete c; return set_err("a mesh mixing C3D8 and user elements is not supported on the device"); }
 
     // ---- SoA mesh, adjacency (ascending element order), block-CSR pattern, slot map
     std::vector<double> xs(N), ys(N), zs(N);
@@ -254,6 +265,12 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
 
     // ---- launch geometry: persistent grids sized from the SM count (148 on B200)
     c->any_neo = any_neo;
+    c->any_c3d8 = any_c3d8;
+    if (any_c3d8) {
+        CK(c->sv0.alloc((size_t)E * C3D8_NSV)); CK(c->sv1.alloc((size_t)E * C3D8_NSV));
+        CK(cudaMemset(c->sv0.p, 0, (size_t)E * C3D8_NSV * sizeof(double)));
+        CK(cudaMemset(c->sv1.p, 0, (size_t)E * C3D8_NSV * sizeof(double)));
+    }
     c->asm_smem = any_neo ? AsmCfg<true>::SMEM : AsmCfg<false>::SMEM;
     c->asm_threads = (any_neo ? AsmCfg<true>::NW : AsmCfg<false>::NW) * 32;
     if (any_neo) CK(cudaFuncSetAttribute(k_assemble_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->asm_smem));
@@ -304,7 +321,7 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
     if (rc) { delete c; return set_err("matrix-free set-up failed"); }
     // congruent mesh (every element a translate of element 0, one linear-elastic material): the matrix-free operator
     // multiplies by the single K_e of element 0, evaluated once by the element kernel.  EN234_MF_GENERAL=1 disables it.
-    bool cong = !any_neo && mats.size() == 1 && E > 1 && getenv("EN234_MF_GENERAL") == nullptr;
+    bool cong = !any_neo && !any_c3d8 && mats.size() == 1 && E > 1 && getenv("EN234_MF_GENERAL") == nullptr;
     for (int e = 1; e < E && cong; ++e)
         for (int a = 1; a < 8 && cong; ++a) {
             const int n0 = conn[e], na = conn[(size_t)a * E + e], m0 = conn[0], ma = conn[(size_t)a * E];
@@ -385,7 +402,7 @@ int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail
     // partitioned runs add the (full-valued) element load vector after the halo sum of the partial residuals
     const double* felem = (c->have_felem && !c->comm.active) ? c->felem.p : nullptr;
     int npart_asm = 0;
-    if (c->asm_rows) {
+    if (c->asm_rows && !c->any_c3d8) {
         AsmArgs A;
         A.M = mesh_of(c);
         A.ut = c->ut.p; A.du = c->du.p;
@@ -409,7 +426,12 @@ int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail
         EA.M = mesh_of(c);
         EA.Ke = c->Ke.p; EA.Re = c->Re.p; EA.S = c->S.p;
         const LoadSum ld{c->ut.p, c->du.p};
-        if (c->any_neo && with_matrix) k_element_blocks<true, true, LoadSum><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
+        if (c->any_c3d8) {
+            C3d8Args CA;
+            CA.M = EA.M; CA.ut = c->ut.p; CA.du = c->du.p; CA.sv0 = c->sv0.p; CA.sv1 = c->sv1.p;
+            CA.Ke = with_matrix ? c->Ke.p : nullptr; CA.Re = c->Re.p; CA.S = c->S.p;
+            k_element_c3d8<<<(c->E + 63) / 64, 64, 0, c->stream>>>(CA);
+        } else if (c->any_neo && with_matrix) k_element_blocks<true, true, LoadSum><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
         else if (c->any_neo) k_element_blocks<true, false, LoadSum><<<c->grid_elem0, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
         else if (with_matrix) k_element_blocks<false, true, LoadSum><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
         else k_element_blocks<false, false, LoadSum><<<c->grid_elem0, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
@@ -692,11 +714,109 @@ static int build_graph(en234gpu_ctx* c, int method) {
     return 0;
 }
 
+// ---- BiCGSTAB (unsymmetric stiffness) ---------------------------------------------------------------------
+// One BiCGSTAB run for A d = b from d = 0 (recurrence residual driven to (r.r)/(b.b) <= tol); returns iterations, or -1
+// on breakdown / iteration cap, -2 on a CUDA error.
+static int bicgstab_run(en234gpu_ctx* c, const double* b, double* x, double tol, int maxit) {
+    const int n = c->ndof, gv = c->grid_vec, nb = (n + 255) / 256;
+    double *r = c->r.p, *rhat = c->tmpvec.p, *p = c->p.p, *v = c->Ap.p, *y = c->tmpvec2.p, *z = c->bi_z.p, *t = c->bi_t.p;
+    double* two = &c->S.p->rz[0];                         // two reduced scalars, read back through the pinned mirror
+    auto read2 = [&](double& a, double& bb) -> int {
+        if (read_scalars(c)) return 1;
+        a = c->hS->rz[0]; bb = c->hS->rz[1];
+        return 0;
+    };
+    int np = 0;
+    k_bi_init<<<gv, VEC_THREADS, 0, c->stream>>>(n, b, x, r, rhat, p, v, c->part2.p);
+    k_bi_reduce2<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part2.p, gv, two);
+    c->st.kernel_launches += 2;
+    double bb = 0, dummy = 0;
+    if (read2(bb, dummy)) return -2;
+    if (!(bb > 0.0)) return bb == 0.0 ? 0 : -1;
+    double rho = bb, rho_old = 1.0, alpha = 1.0, omega = 1.0, rr = bb;
+    int it = 0;
+    while (rr / bb > tol) {
+        if (it >= maxit) return -1;
+        ++it;
+        const double beta = (rho / rho_old) * (alpha / omega);
+        k_bi_p<<<nb, 256, 0, c->stream>>>(n, it == 1 ? 0.0 : beta, omega, r, v, c->minv.p, p, y);
+        launch_spmv_rows(c, y, v, 0, c->N, 0, 0, &np);
+        k_bi_dot2<<<gv, VEC_THREADS, 0, c->stream>>>(n, rhat, v, rhat, v, c->part2.p, c->part3.p);
+        k_bi_reduce2<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, two);
+        double rv = 0;
+        if (read2(rv, dummy)) return -2;
+        if (rv == 0.0 || rv != rv) return -1;
+        alpha = rho / rv;
+        k_bi_s<<<nb, 256, 0, c->stream>>>(n, alpha, v, c->minv.p, r, z);
+        launch_spmv_rows(c, z, t, 0, c->N, 0, 0, &np);
+        k_bi_dot2<<<gv, VEC_THREADS, 0, c->stream>>>(n, t, r, t, t, c->part2.p, c->part3.p);
+        k_bi_reduce2<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, two);
+        double ts = 0, tt = 0;
+        if (read2(ts, tt)) return -2;
+        if (tt != tt) return -1;
+        omega = tt > 0.0 ? ts / tt : 0.0;
+        k_bi_x<<<gv, VEC_THREADS, 0, c->stream>>>(n, alpha, omega, y, z, t, rhat, x, r, c->part2.p, c->part3.p);
+        k_bi_reduce2<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, two);
+        c->st.kernel_launches += 10;
+        rho_old = rho;
+        if (read2(rr, rho)) return -2;
+        if (rr != rr) return -1;
+        if (rr / bb > tol && (omega == 0.0 || rho == 0.0)) return -1;             // breakdown
+    }
+    return it;
+}
+
+// A x = rhs to a TRUE residual (b - A x).(b - A x)/(b.b) <= tol: BiCGSTAB runs on the current true residual, the
+// corrections are accumulated (iterative refinement).  The Newton history of the reference's golden log needs solves of
+// direct-solver quality (6 printed digits of a 1e-4 second correction), which a single recurrence-residual stop misses.
+static int bicgstab_solve(en234gpu_ctx* c, double tol, int maxit, double* correction_norm, int* iterations, int* fail) {
+    if (c->mode != EN234_SOLVE_PCG_BSR || !c->matrix_valid) return set_err("BiCGSTAB needs the assembled matrix (solve called before assemble?)");
+    if (c->comm.active) return set_err("BiCGSTAB is a single-GPU solver");
+    if (phase_begin(c)) return 1;
+    const int n = c->ndof, gv = c->grid_vec, nb = (n + 255) / 256;
+    if (c->bi_z.n < (size_t)n) { CK(c->bi_z.alloc(n)); CK(c->bi_t.alloc(n)); CK(c->bi_xt.alloc(n)); CK(c->bi_b.alloc(n)); }
+    const double tol_run = std::max(tol, 1e-24);
+    int total = 0, np = 0;
+    *fail = 0;
+    double bb = 0.0, rr_prev = 0.0;
+    for (int pass = 0; pass < 6; ++pass) {
+        const double* b = pass == 0 ? c->rhs.p : c->bi_b.p;
+        const int it = bicgstab_run(c, b, c->sol.p, pass == 0 ? tol_run : 1e-12, maxit - total);
+        if (it == -2) return set_err("BiCGSTAB: CUDA error");
+        if (it < 0) { *fail = 1; break; }
+        total += it;
+        k_bi_accumulate<<<nb, 256, 0, c->stream>>>(n, c->sol.p, c->bi_xt.p, pass == 0);
+        launch_spmv_rows(c, c->bi_xt.p, c->bi_t.p, 0, c->N, 0, 0, &np);
+        k_bi_residual<<<gv, VEC_THREADS, 0, c->stream>>>(n, c->rhs.p, c->bi_t.p, c->bi_b.p, c->part2.p);
+        k_bi_dot2<<<gv, VEC_THREADS, 0, c->stream>>>(n, c->rhs.p, c->rhs.p, c->rhs.p, c->rhs.p, c->part3.p, c->part.p);
+        k_bi_reduce2<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, &c->S.p->rz[0]);
+        c->st.kernel_launches += 5;
+        if (read_scalars(c)) return 1;
+        const double rr = c->hS->rz[0];
+        bb = c->hS->rz[1];
+        c->st.last_cg_err = bb > 0.0 ? rr / bb : 0.0;
+        if (!(bb > 0.0) || rr / bb <= tol) break;
+        if (pass > 0 && rr > 0.25 * rr_prev) break;          // refinement has reached the rounding floor
+        rr_prev = rr;
+    }
+    CK(cudaGetLastError());
+    *iterations = total;
+    c->st.last_cg_iterations = total;
+    if (!*fail) {
+        k_add_solution<<<gv, VEC_THREADS, 0, c->stream>>>(n, c->bi_xt.p, c->du.p, nullptr, c->part2.p);
+        c->st.kernel_launches++;
+        if (finish_norm(c, c->part2.p, gv, correction_norm)) return 1;
+    } else *correction_norm = 0.0;
+    return phase_end(c, &c->st.solve_ms);
+}
+
 int en234gpu_solve_dev(en234gpu_handle c, int method, double cg_tolerance, int max_cg_iterations,
                        double* correction_norm, int* cg_iterations, int* fail) {
+    if (method == EN234_SOLVE_BICGSTAB_BSR) return bicgstab_solve(c, cg_tolerance, max_cg_iterations, correction_norm, cg_iterations, fail);
     if (method != EN234_SOLVE_PCG_BSR && method != EN234_SOLVE_PCG_MATRIXFREE) return set_err("unknown solve method");
     if (method == EN234_SOLVE_PCG_BSR && !c->matrix_valid) return set_err("solve called before assemble");
     if (method != c->mode) return set_err("solve method differs from the operator mode (en234gpu_set_operator_mode)");
+    if (c->any_c3d8) return set_err("C3D8 continuum elements have an unsymmetric tangent: use EN234_SOLVE_BICGSTAB_BSR");
     if (method == EN234_SOLVE_PCG_MATRIXFREE && c->any_neo)
         return set_err("the matrix-free operator covers the linear-elastic elements only (1001 / U1)");
     if (phase_begin(c)) return 1;
@@ -772,6 +892,32 @@ int en234gpu_download_state(en234gpu_handle c, double* dof_increment, double* rf
     if (dof_increment) CK(cudaMemcpyAsync(dof_increment, c->du.p, b, cudaMemcpyDeviceToHost, c->stream));
     if (rforce) CK(cudaMemcpyAsync(rforce, c->rforce.p, b, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+long long en234gpu_n_state_variables(en234gpu_handle c) { return (long long)c->sv0.n; }
+
+int en234gpu_commit_state(en234gpu_handle c) {
+    CK(cudaSetDevice(c->device));
+    if (c->sv0.n) CK(cudaMemcpyAsync(c->sv0.p, c->sv1.p, c->sv0.n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+int en234gpu_get_state_variables(en234gpu_handle c, int updated, double* out) {
+    CK(cudaSetDevice(c->device));
+    if (c->sv0.n) {
+        CK(cudaMemcpyAsync(out, updated ? c->sv1.p : c->sv0.p, c->sv0.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int en234gpu_set_state_variables(en234gpu_handle c, const double* initial) {
+    CK(cudaSetDevice(c->device));
+    if (c->sv0.n) {
+        CK(cudaMemcpyAsync(c->sv0.p, initial, c->sv0.n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     return 0;
 }
 

@@ -167,9 +167,19 @@ int en234host_evaluate_loads(en234host_model_t w, double time, double dtime, con
 
 int en234host_gpu_create(en234host_model_t w, int device, en234gpu_handle* h) {
     const Model& m = w->m;
+    // built-in continuum elements (flag 10003) take their properties from their MATERIAL (read_input_file.f90:433-509,
+    // :756-960): one combined property array, element property index pointing into the material's section
+    std::vector<double> props = m.element_properties;
+    std::vector<int> pidx = m.element_prop_index;
+    props.insert(props.end(), m.material_properties.begin(), m.material_properties.end());
+    for (int e = 0; e < m.n_elements; ++e)
+        if (m.element_flag[e] == EN234_FLAG_C3D8) {
+            const int mi = e < (int)m.element_material.size() ? m.element_material[e] : 0;
+            if (mi < 1 || mi > (int)m.materials.size()) { g_err = "C3D8 element without a MATERIAL"; return 1; }
+            pidx[e] = (int)m.element_properties.size() + m.materials[mi - 1].prop_index;
+        }
     int rc = en234gpu_create(h, device, m.n_nodes, m.n_elements, m.coords.data(), m.connectivity.data(),
-                             m.element_flag.data(), m.element_prop_index.data(), m.element_properties.data(),
-                             (int)m.element_properties.size());
+                             m.element_flag.data(), pidx.data(), props.data(), (int)props.size());
     if (rc) g_err = en234gpu_last_error();
     return rc;
 }

@@ -104,7 +104,10 @@ int compute_static_step(const Model& m, en234gpu_handle h, const StepOptions& op
     double newdt = 0.0;
     // SOLVER, DIRECT inputs are solved by PCG converged far below the Newton tolerance; CONJUGATE GRADIENT inputs
     // use the reference's rule and constants unless overridden at run time.
-    const double cg_tol = opt.cg_tolerance > 0 ? opt.cg_tolerance : (m.solvertype == 1 ? 1e-28 : m.cg_tolerance);
+    // UNSYMMETRIC stiffness (built-in continuum elements): Jacobi-BiCGSTAB on the assembled matrix
+    const int method = (m.unsymmetric_stiffness && opt.method == EN234_SOLVE_PCG_BSR) ? EN234_SOLVE_BICGSTAB_BSR : opt.method;
+    const bool bicg = method == EN234_SOLVE_BICGSTAB_BSR;
+    const double cg_tol = opt.cg_tolerance > 0 ? opt.cg_tolerance : (m.solvertype == 1 ? (bicg ? 1e-30 : 1e-28) : m.cg_tolerance);
     const int cg_maxit = opt.max_cg_iterations > 0 ? opt.max_cg_iterations : (m.solvertype == 1 ? 100000 : m.max_cg_iterations);
     const bool newton_loop = m.solvertype == 1 || m.nonlinear || opt.check_linear_cg;   // staticstep.f90:60-70 vs :120-132
     StepLoads L;
@@ -130,8 +133,8 @@ int compute_static_step(const Model& m, en234gpu_handle h, const StepOptions& op
         int its = 0, sfail = 0;
         auto solve = [&]() -> int {
             int rc = opt.use_host_api
-                         ? en234gpu_solve(h, opt.method, cg_tol, cg_maxit, dof_increment.data(), &correction, &its, &sfail)
-                         : en234gpu_solve_dev(h, opt.method, cg_tol, cg_maxit, &correction, &its, &sfail);
+                         ? en234gpu_solve(h, method, cg_tol, cg_maxit, dof_increment.data(), &correction, &its, &sfail)
+                         : en234gpu_solve_dev(h, method, cg_tol, cg_maxit, &correction, &its, &sfail);
             res.cg_iterations.push_back(its);
             if (rc) { res.error = en234gpu_last_error(); return -1; }
             return sfail;
@@ -164,6 +167,7 @@ int compute_static_step(const Model& m, en234gpu_handle h, const StepOptions& op
             en234gpu_download_state(h, dof_increment.data(), res.rforce.data())) { res.error = en234gpu_last_error(); return -1; }
         t.current_step_number++;
         for (size_t d = 0; d < ndof; ++d) res.dof_total[d] += dof_increment[d];
+        if (en234gpu_commit_state(h)) { res.error = en234gpu_last_error(); return -1; }   // staticstep.f90:87
         // NB: like the reference (staticstep.f90:81-89) dof_increment is NOT reset here — the next step starts
         // from the previous increment as its predictor.
         res.step_time.push_back(t.TIME + t.DTIME);

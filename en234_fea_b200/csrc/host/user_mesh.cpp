@@ -108,8 +108,32 @@ std::string write_input_text(const Model& m) {
     o << "MESH\n NODES\n  PARAMETERS, 3, 3, 1\n  DISPLACEMENT DOF, 1, 2, 3\n  COORDINATES\n";
     for (int n = 0; n < m.n_nodes; ++n)
         o << "   " << n + 1 << ", " << m.coords[3 * n] << ", " << m.coords[3 * n + 1] << ", " << m.coords[3 * n + 2] << "\n";
-    o << "  END COORDINATES\n END NODES\n ELEMENTS, USER\n";
+    o << "  END COORDINATES\n END NODES\n";
+    for (const auto& md : m.materials) {                              // MATERIAL blocks (read_input_file.f90:433-509)
+        o << " MATERIAL, " << md.name << "\n  STATE VARIABLES, " << md.n_states << "\n  PROPERTIES\n";
+        for (int k = 0; k < md.n_props; ++k) o << "   " << m.material_properties[md.prop_index + k] << "\n";
+        o << "  END PROPERTIES\n END MATERIAL\n";
+    }
+    bool any_internal = false, any_user = false;
+    for (const auto& g : m.groups) { any_internal |= g.flag == 10003; any_user |= g.flag != 10003; }
+    if (any_internal) {                                               // ELEMENTS, INTERNAL (read_input_file.f90:756-960)
+        o << " ELEMENTS, INTERNAL\n";
+        for (const auto& g : m.groups) {
+            if (g.flag != 10003) continue;
+            o << "  TYPE, C3D8\n  PROPERTIES, " << m.materials[m.element_material[g.first_element] - 1].name
+              << "\n  CONNECTIVITY, " << (g.zone.empty() ? "zone" : g.zone) << "\n";
+            for (int e = g.first_element; e < g.first_element + g.n_elements; ++e) {
+                o << "   " << e + 1;
+                for (int a = 0; a < 8; ++a) o << ", " << m.connectivity[8 * (size_t)e + a];
+                o << "\n";
+            }
+            o << "  END CONNECTIVITY\n";
+        }
+        o << " END ELEMENTS\n";
+    }
+    if (any_user || !any_internal) o << " ELEMENTS, USER\n";
     for (const auto& g : m.groups) {
+        if (g.flag == 10003) continue;
         o << "  PARAMETERS, 8, " << g.n_states << ", ";
         if (g.flag > 99999) o << "U" << g.flag - 99999; else o << g.flag;
         o << "\n  PROPERTIES\n";
@@ -122,7 +146,8 @@ std::string write_input_text(const Model& m) {
         }
         o << "  END CONNECTIVITY\n";
     }
-    o << " END ELEMENTS\nEND MESH\nBOUNDARY CONDITIONS\n";
+    if (any_user || !any_internal) o << " END ELEMENTS\n";
+    o << "END MESH\nBOUNDARY CONDITIONS\n";
     for (const auto& h : m.histories) {
         o << " HISTORY, " << h.name << "\n";
         for (size_t i = 0; i < h.t.size(); ++i) o << "  " << h.t[i] << ", " << h.v[i] << "\n";
@@ -179,6 +204,7 @@ std::string write_input_text(const Model& m) {
           << (m.solvertype == 1 ? "DIRECT" : "CONJUGATE GRADIENT") << ", ";
         if (m.nonlinear) o << "NONLINEAR, " << m.newtonraphson_tolerance << ", " << m.max_newton_iterations;
         else o << "LINEAR";
+        if (m.unsymmetric_stiffness) o << ", UNSYMMETRIC";
         o << "\n CG TOLERANCE, " << m.cg_tolerance << "\n CG MAX ITERATIONS, " << m.max_cg_iterations << "\nEND STATIC STEP\n";
     }
     o << "STOP\n";

@@ -1,3 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py 16 16 64 0.0 2>&1 | grep "mgpu_check" | tail -6
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 8 --steps 2 --workload c5 --jitter 0 > gpurun_out/bench_r1e_c5_uniform_n8.json 2> gpurun_out/bench_r1e_c5u_n8.err; tail -c 1500 gpurun_out/bench_r1e_c5_uniform_n8.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus 8 --steps 3 > gpurun_out/bench_r1e_n8.json 2> gpurun_out/bench_r1e_n8.err; tail -c 800 gpurun_out/bench_r1e_n8.json
+python -m pytest tests -m gpu -x -q 2>&1 | tail -25

@@ -29,10 +29,16 @@ typedef struct en234gpu_ctx* en234gpu_handle;
 #define EN234_ID_LINELAST 1001
 #define EN234_ID_NEOHOOKE 1002
 #define EN234_FLAG_UEL_BASE 99999
+/*   10003           built-in C3D8 continuum element (finite-strain B-bar hex8, src/continuum_elements.f90:368-761) with
+ *                   the linear-elastic ABAQUS UMAT (user_codes/src/abaqus_umat_elastic.for); props E, nu of its
+ *                   MATERIAL; 15 state variables per integration point; UNSYMMETRIC tangent -> EN234_SOLVE_BICGSTAB_BSR.
+ *                   A mesh is either all-C3D8 or all user elements. */
+#define EN234_FLAG_C3D8 10003
 
 /* Solver methods for en234gpu_solve */
 #define EN234_SOLVE_PCG_BSR 0        /* Jacobi-PCG on the assembled 3x3-block CSR matrix               */
 #define EN234_SOLVE_PCG_MATRIXFREE 1 /* Jacobi-PCG with the element-by-element (matrix-free) operator  */
+#define EN234_SOLVE_BICGSTAB_BSR 2   /* Jacobi-BiCGSTAB on the assembled matrix (unsymmetric stiffness; 1 GPU) */
 
 const char* en234gpu_last_error(void);
 int en234gpu_device_count(void);
@@ -105,6 +111,14 @@ int en234gpu_solve_dev(en234gpu_handle h, int method, double cg_tolerance, int m
                        double* correction_norm, int* cg_iterations, int* fail);
 int en234gpu_download_state(en234gpu_handle h, double* dof_increment, double* rforce);
 int en234gpu_zero_increment_dev(en234gpu_handle h);
+
+/* ---- element state variables (initial_state_variables / updated_state_variables, modules/Mesh.f90:92-93): owned by the
+ * handle, zero at creation; every assembly recomputes the updated set from the initial one; the driver commits at the
+ * end of a converged step (initial = updated, src/staticstep.f90:87).  n_state_variables = 120 per C3D8 element. */
+long long en234gpu_n_state_variables(en234gpu_handle h);
+int en234gpu_commit_state(en234gpu_handle h);
+int en234gpu_get_state_variables(en234gpu_handle h, int updated /*0 initial, 1 updated*/, double* out);
+int en234gpu_set_state_variables(en234gpu_handle h, const double* initial);
 
 /* ---- element plugin surface.  Batched device evaluation of the element routines for a list of elements:
  * the device twin of user_element_static (user_codes/src/user_element.f90:5-49) / UEL

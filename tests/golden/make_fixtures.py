@@ -3,6 +3,7 @@
   linear_elastic_3d_uel.in   re-emission (by the product's own writer, 17 significant digits, no comments) of the
   holeplate_3d_uel.in.gz     mesh/BC/step data parsed from input_files/Abaqus_uel_linear_elastic_3d.in and
                              input_files/Abaqus_uel_holeplate_3d.in — data fixtures, the GPU box has no /root/reference
+  holeplate_3d_umat.in.gz    the same for input_files/Abaqus_umat_holeplate_3d.in (C3D8 + UMAT, the golden-log case)
   *_oracle.npz               displacements, reaction forces and Newton history of the CPU oracle (skyline direct
                              solver path) on those inputs
 """
@@ -49,3 +50,13 @@ for src, dst in [("Abaqus_uel_linear_elastic_3d.in", "linear_elastic_3d_uel.in")
 mu = Model.read(os.path.join(REF, "Abaqus_umat_holeplate_3d.in"))
 np.savez_compressed(os.path.join(HERE, "holeplate_3d_umat_model.npz"), **mu.arrays())
 print("holeplate_3d_umat_model.npz", mu.n_nodes, mu.n_elements)
+# the same model re-emitted as .in text by the product's writer, for the GPU run of the golden-log case
+text = mu.text()
+with gzip.GzipFile(os.path.join(HERE, "holeplate_3d_umat.in.gz"), "wb", mtime=0) as f:
+    f.write(text.encode())
+a, b = mu.arrays(), Model.from_text(text).arrays()
+for k in a:
+    if k in ("cg_tolerance", "max_cg_iterations", "checkstiffness_flag"):
+        continue
+    assert np.array_equal(a[k], b[k]), k
+print("holeplate_3d_umat.in.gz round trip ok")

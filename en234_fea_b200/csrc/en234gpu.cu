@@ -658,6 +658,14 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
             p2p_halo_fork(c, c->Ap.p, 1);
             launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2);
             np = n1 + n2;
+        } else if (method == EN234_SOLVE_PCG_MATRIXFREE && c->mf.congruent) {
+            // congruent-mesh operator: the non-dominant rows (all interface rows among them) first, their halo
+            // exchange overlaps the dominant rows
+            const uint8_t* owned = c->have_owned ? c->owned.p : nullptr;
+            mf_stencil(c->mf, mesh_of(c), c->cflag.p, owned, c->p.p, c->Ap.p, c->part.p, c->S.p, c->stream, &c->st.kernel_launches, 0);
+            p2p_halo_fork(c, c->Ap.p, 1);
+            mf_stencil(c->mf, mesh_of(c), c->cflag.p, owned, c->p.p, c->Ap.p, c->part.p, c->S.p, c->stream, &c->st.kernel_launches, 1);
+            np = operator_partials(c, method);
         } else {
             launch_operator(c, method, c->p.p, c->Ap.p, 1);
             np = operator_partials(c, method);

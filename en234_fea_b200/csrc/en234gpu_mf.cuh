@@ -42,7 +42,7 @@ struct MfData {
     int* d_bcolT = nullptr;         // ELL-transposed block columns in sorted order (coalesced for one thread per row)
     double* d_xs = nullptr;         // masked, component-major copy of the operand
     int n_patterns = 0;
-    int grid_spmv = 0;
+    int t_split = 0, grid_tail = 0, grid_head = 0;
     const uint8_t* affected = nullptr;   // per node: prescribed or coupled to a prescribed DOF (set with the BC list)
     int grid_elem = 0, elem_threads = 0, grid_gather = 0;
     size_t elem_smem = 0;
@@ -153,6 +153,7 @@ __global__ void k_fix_diag(int n, const uint8_t* cflag, const uint8_t* owned, do
 
 struct StencilArgs {
     int N;
+    int t_begin, t_end;            // sorted positions handled by this launch
     int n_dom;                     // the first n_dom rows of the pattern-sorted order all have the dominant distinct row
     const int* perm;               // pattern-sorted position t -> block row
     const int* bcolT;              // ELL-transposed block columns in sorted order: bcolT[s * N + t] = s-th column of row perm[t]
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(VEC_THREADS, STENCIL_OCC) k_stencil_nodes(Sten
     if (A.S && A.S->stop) return;
     double dot = 0.0;
     const int N = A.N;
-    for (int t0 = blockIdx.x * VEC_THREADS; t0 < N; t0 += gridDim.x * VEC_THREADS) {
+    for (int t0 = A.t_begin + blockIdx.x * VEC_THREADS; t0 < A.t_end; t0 += gridDim.x * VEC_THREADS) {
         const int t = t0 + threadIdx.x;
         double y0 = 0.0, y1 = 0.0, y2 = 0.0;
         if (t0 + VEC_THREADS <= A.n_dom) {                       // CTA-uniform: 256 dominant rows
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(VEC_THREADS, STENCIL_OCC) k_stencil_nodes(Sten
                     y2 += D.v[162 + 3 * s] * x0; y2 += D.v[162 + 3 * s + 1] * x1; y2 += D.v[162 + 3 * s + 2] * x2;
                 }
             }
-        } else if (t < N) {
+        } else if (t < A.t_end) {
             const int pid = A.st_pid[t], nb = A.st_nb[pid], L = 3 * nb;
             const double* v = A.st_val + A.st_off[pid];
             for (int s0 = 0; s0 < nb; s0 += 9) {
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(VEC_THREADS, STENCIL_OCC) k_stencil_nodes(Sten
                 }
             }
         }
-        if (t < N) {
+        if (t < A.t_end) {
             const int i = A.perm[t];
             const bool aff = A.cflag != nullptr && (A.affected == nullptr || A.affected[i] != 0);
             double yv[3] = {y0, y1, y2};
@@ -428,9 +429,13 @@ inline int mf_set_congruent(MfData& mf, const double* Ke_colmajor, int N, const 
     if (up((void**)&mf.d_perm, perm.data(), (size_t)N * sizeof(int))) return 1;
     if (up((void**)&mf.d_bcolT, bt.data(), bt.size() * sizeof(int))) return 1;
     if (cudaMalloc((void**)&mf.d_xs, (size_t)3 * N * sizeof(double)) != cudaSuccess) return 1;
-    mf.grid_spmv = std::min(MAX_PARTIALS, std::max(1, (N + VEC_THREADS - 1) / VEC_THREADS));
-    mf.n_partials = mf.grid_spmv;
-    mf.launches_per_apply = 2;
+    // two launches per application: the rows after the dominant run first (they include every partition-interface row,
+    // whose halo exchange then overlaps the dominant rows), then the dominant run
+    mf.t_split = (mf.n_dom / VEC_THREADS) * VEC_THREADS;
+    mf.grid_tail = std::min(MAX_PARTIALS / 2, std::max(1, (N - mf.t_split + VEC_THREADS - 1) / VEC_THREADS));
+    mf.grid_head = mf.t_split > 0 ? std::min(MAX_PARTIALS / 2, mf.t_split / VEC_THREADS) : 0;
+    mf.n_partials = mf.grid_tail + mf.grid_head;
+    mf.launches_per_apply = 3;
     mf.congruent = true;
     return 0;
 }
@@ -448,6 +453,26 @@ inline void mf_release(MfData& mf) {
     mf.d_elist = nullptr; mf.d_fe = nullptr; mf.d_st_val = nullptr; mf.d_st_off = nullptr; mf.d_st_pid = nullptr;
 }
 
+// congruent-mesh operator in two phases: 0 = masked operand copy + the rows after the dominant run, 1 = the dominant run
+inline void mf_stencil(const MfData& mf, const Mesh& M, const uint8_t* cflag, const uint8_t* owned, const double* x, double* y,
+                       double* partials, const CgScalars* S, cudaStream_t s, long long* launches, int phase) {
+    StencilArgs A;
+    A.N = M.N; A.n_dom = mf.n_dom; A.perm = mf.d_perm; A.bcolT = mf.d_bcolT; A.st_val = mf.d_st_val;
+    A.st_off = mf.d_st_off; A.st_nb = mf.d_st_nb; A.st_pid = mf.d_st_pid; A.cflag = cflag;
+    A.affected = cflag ? mf.affected : nullptr; A.owned = owned;
+    A.x = x; A.xs = mf.d_xs; A.y = y; A.S = S;
+    if (phase == 0) {
+        k_mask_soa<<<(3 * M.N + 255) / 256, 256, 0, s>>>(M.N, cflag, x, mf.d_xs, S);
+        A.t_begin = mf.t_split; A.t_end = M.N; A.partials = partials;
+        k_stencil_nodes<<<mf.grid_tail, VEC_THREADS, 0, s>>>(A, mf.dom);
+        *launches += 2;
+    } else if (mf.grid_head > 0) {
+        A.t_begin = 0; A.t_end = mf.t_split; A.partials = partials + mf.grid_tail;
+        k_stencil_nodes<<<mf.grid_head, VEC_THREADS, 0, s>>>(A, mf.dom);
+        *launches += 1;
+    }
+}
+
 // y = P A P x + (I-P) x ; partials of x.y.  (cflag == null: plain A x)
 inline void mf_apply(const MfData& mf, const Mesh& M, int ndof, const uint8_t* cflag, const uint8_t* owned, const double* x,
                      double* y, double* partials, const CgScalars* S, cudaStream_t s, long long* launches) {
@@ -455,13 +480,8 @@ inline void mf_apply(const MfData& mf, const Mesh& M, int ndof, const uint8_t* c
     ElemArgs EA;
     EA.M = M; EA.Ke = nullptr; EA.Re = mf.d_fe; EA.S = nullptr;
     if (mf.congruent) {
-        StencilArgs A;
-        A.N = M.N; A.n_dom = mf.n_dom; A.perm = mf.d_perm; A.bcolT = mf.d_bcolT; A.st_val = mf.d_st_val;
-        A.st_off = mf.d_st_off; A.st_nb = mf.d_st_nb; A.st_pid = mf.d_st_pid; A.cflag = cflag; A.affected = cflag ? mf.affected : nullptr; A.owned = owned;
-        A.x = x; A.xs = mf.d_xs; A.y = y; A.partials = partials; A.S = S;
-        k_mask_soa<<<(3 * M.N + 255) / 256, 256, 0, s>>>(M.N, cflag, x, mf.d_xs, S);
-        k_stencil_nodes<<<mf.grid_spmv, VEC_THREADS, 0, s>>>(A, mf.dom);
-        *launches += 2;
+        mf_stencil(mf, M, cflag, owned, x, y, partials, S, s, launches, 0);
+        mf_stencil(mf, M, cflag, owned, x, y, partials, S, s, launches, 1);
         return;
     }
     k_element_blocks<false, false, LoadMasked><<<mf.grid_elem, mf.elem_threads, mf.elem_smem, s>>>(EA, LoadMasked{x, cflag, S});

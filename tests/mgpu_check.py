@@ -49,7 +49,7 @@ def main():
                 eu = np.abs(ug - ref["dof_total"]).max() / np.abs(ref["dof_total"]).max()
                 er = np.abs(rg - ref["rforce"]).max() / np.abs(ref["rforce"]).max()
                 its, its1 = res["cg_iterations"].tolist(), ref["cg_iterations"].tolist()
-                good = eu < 1e-10 and er < 1e-10 and all(abs(a - b) <= 2 for a, b in zip(its, its1)) and \
+                good = eu < 1e-10 and er < 1e-10 and all(abs(a - b) <= max(2, b // 25) for a, b in zip(its, its1)) and \
                     res["newton"].shape == ref["newton"].shape and agree
                 print("mgpu_check [%s] world=%d mesh=%s jitter=%g congruent=%d method=%d load=%s: u err %.2e, rforce err %.2e, CG its %s vs %s, copies agree %s -> %s"
                       % (comm_kind, world, dims, jitter, g.stats().mf_congruent, method, load, eu, er, its, its1, agree, "OK" if good else "FAIL"), flush=True)

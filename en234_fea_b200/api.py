@@ -48,7 +48,7 @@ GPU_SYMBOLS = [
     "en234gpu_nnz_blocks", "en234gpu_get_csr", "en234gpu_get_rhs", "en234gpu_apply_operator",
     "en234gpu_get_unique_id", "en234gpu_comm_init", "en234gpu_set_partition", "en234gpu_get_stats",
     "en234gpu_bench_operator", "en234gpu_comm_arena", "en234gpu_comm_connect",
-    "en234gpu_n_state_variables", "en234gpu_commit_state", "en234gpu_get_state_variables", "en234gpu_set_state_variables",
+    "en234gpu_measure_fp64_peak", "en234gpu_n_state_variables", "en234gpu_commit_state", "en234gpu_get_state_variables", "en234gpu_set_state_variables",
 ]
 HOST_SYMBOLS = [
     "en234host_model_read", "en234host_model_from_text", "en234host_model_free", "en234host_last_error",
@@ -347,6 +347,11 @@ class GpuSystem:
         s = Stats()
         self._ck(gpu_lib().en234gpu_get_stats(self.h, C.byref(s)))
         return s
+
+    def fp64_peak(self):
+        t = C.c_double()
+        self._ck(gpu_lib().en234gpu_measure_fp64_peak(self.h, C.byref(t)))
+        return t.value
 
     def bench_operator(self, method=0, warm=3, reps=20):
         ms = C.c_double()

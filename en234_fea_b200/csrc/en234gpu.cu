@@ -1150,6 +1150,24 @@ int en234gpu_set_operator_mode(en234gpu_handle c, int method) {
 
 int en234gpu_get_stats(en234gpu_handle c, struct en234gpu_stats* s) { c->st.mf_congruent = c->mf.congruent ? 1 : 0; *s = c->st; return 0; }
 
+int en234gpu_measure_fp64_peak(en234gpu_handle c, double* tflops) {
+    CK(cudaSetDevice(c->device));
+    const int iters = 4096, grid = c->n_sm * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(c->ev0, c->stream));
+        k_fp64_peak<<<grid, 256, 0, c->stream>>>(iters, 0.999999, c->tmpvec.p);
+        CK(cudaEventRecord(c->ev1, c->stream));
+        CK(cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->st.kernel_launches++;
+        if (rep > 0) best = std::max(best, 2.0 * 16.0 * iters * (double)grid * 256.0 / (ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
+    return 0;
+}
+
 int en234gpu_bench_operator(en234gpu_handle c, int method, int warm, int reps, double* ms_per_launch) {
     CK(cudaSetDevice(c->device));
     if (method == EN234_SOLVE_PCG_BSR && !c->matrix_valid) return set_err("bench_operator: no assembled matrix");

@@ -113,4 +113,20 @@ __global__ void k_svars(Mesh M, const double* ut, const double* du, double* svar
     sv[0] = s[0]; sv[1] = s[4]; sv[2] = s[8]; sv[3] = s[1]; sv[4] = s[2]; sv[5] = s[5];
 }
 
+// FP64 FMA throughput of the device (the roof of the element kernel and of the general-mesh matrix-free operator):
+// 16 independent FMA chains per thread, `iters` x 16 FMAs each, full occupancy.  flops = 2 * 16 * iters * threads.
+__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double a, double* out) {
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 1.0 + 1e-3 * (threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = fma(v[k], a, 1e-9);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += v[k];
+    if (s == 12345.678) out[0] = s;                              // keeps the chains alive
+}
+
 }  // namespace en234k

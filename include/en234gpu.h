@@ -178,6 +178,9 @@ int en234gpu_get_stats(en234gpu_handle h, struct en234gpu_stats* s);
  * kernel y = A p (method 0: block-CSR SpMV; 1: matrix-free apply) after `warm` untimed ones — the per-launch
  * duration the roofline figures are computed from */
 int en234gpu_bench_operator(en234gpu_handle h, int method, int warm, int reps, double* ms_per_launch);
+/* measured FP64 FMA throughput of the handle's device in TFLOP/s (an FMA micro-kernel, best of 5): the roof of the
+ * FP64-bound kernels (element kernel, general-mesh matrix-free operator), reported beside the HBM roof */
+int en234gpu_measure_fp64_peak(en234gpu_handle h, double* tflops);
 
 #ifdef __cplusplus
 }

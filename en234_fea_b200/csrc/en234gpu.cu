@@ -55,7 +55,7 @@ struct en234gpu_ctx {
     long long nnzb = 0;
     // mesh
     DevBuf<double> x, y, z;
-    DevBuf<int> conn, mat, adj_ptr, adj, browptr, bcol;
+    DevBuf<int> conn, mat, adj_ptr, adj, adj_pos, browptr, bcol;
     DevBuf<uint8_t> slot;
     DevBuf<unsigned> inv;        // inverse slot map per block (k_gather_rows)
     DevBuf<Material> mats;
@@ -105,8 +105,8 @@ static Mesh mesh_of(en234gpu_ctx* c) {
     Mesh M;
     M.N = c->N; M.E = c->E;
     M.x = c->x.p; M.y = c->y.p; M.z = c->z.p;
-    M.conn = c->conn.p; M.mat = c->mat.p; M.mats = c->mats.p;
-    M.adj_ptr = c->adj_ptr.p; M.adj = c->adj.p; M.slot = c->slot.p;
+    M.conn = c->conn.p; M.mat = c->mat.p; M.mats = c->mats.p; M.n_mats = (int)c->mats.n;
+    M.adj_ptr = c->adj_ptr.p; M.adj = c->adj.p; M.adj_pos = c->adj_pos.p; M.slot = c->slot.p;
     M.browptr = c->browptr.p; M.bcol = c->bcol.p;
     return M;
 }
@@ -246,6 +246,9 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
     CK(c->buf.alloc((vec).size()));                                                                    \
     CK(cudaMemcpy(c->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice))
     UP(x, xs); UP(y, ys); UP(z, zs); UP(conn, conn); UP(mat, mat); UP(mats, mats);
+    std::vector<int> adj_pos((size_t)8 * E);
+    for (size_t k = 0; k < adj.size(); ++k) adj_pos[adj[k]] = (int)k;
+    UP(adj_pos, adj_pos);
     UP(adj_ptr, adj_ptr); UP(adj, adj); UP(slot, slot); UP(browptr, browptr); UP(bcol, bcol); UP(inv, inv);
 #undef UP
     const size_t nd = (size_t)c->ndof;
@@ -305,10 +308,8 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oe0, k_element_blocks<true, false, LoadSum>, c->elem_threads, c->elem_smem));
         } else {
             CK(cudaFuncSetAttribute(k_element_blocks<false, true, LoadSum>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->elem_smem));
-            CK(cudaFuncSetAttribute(k_element_blocks<false, false, LoadSum>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->elem_smem));
-            CK(cudaFuncSetAttribute(k_element_blocks<false, false, LoadMasked>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->elem_smem));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oe, k_element_blocks<false, true, LoadSum>, c->elem_threads, c->elem_smem));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oe0, k_element_blocks<false, false, LoadSum>, c->elem_threads, c->elem_smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oe0, k_element_forces<LoadSum>, 256, 0));
         }
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&og, k_gather_rows, THREADS, 0));
         const int wpc = c->elem_threads / 32, groups = (E + 3) / 4;
@@ -434,7 +435,7 @@ int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail
         } else if (c->any_neo && with_matrix) k_element_blocks<true, true, LoadSum><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
         else if (c->any_neo) k_element_blocks<true, false, LoadSum><<<c->grid_elem0, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
         else if (with_matrix) k_element_blocks<false, true, LoadSum><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
-        else k_element_blocks<false, false, LoadSum><<<c->grid_elem0, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
+        else k_element_forces<LoadSum><<<c->grid_elem0, 256, 0, c->stream>>>(EA, ld);
         GatherArgs G;
         G.M = EA.M; G.Ke = c->Ke.p; G.Re = c->Re.p; G.felem = felem;
         G.val = c->val.p; G.rhs = c->rhs.p; G.rforce = c->rforce.p; G.partials = c->part.p; G.S = c->S.p;

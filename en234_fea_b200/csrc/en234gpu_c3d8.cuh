@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(64, 1) k_element_c3d8(C3d8Args A) {
         }
     }
     for (int q = 0; q < 24; ++q) {
-        A.Re[(size_t)e * 24 + q] = R[q];
+        A.Re[3 * (size_t)M.adj_pos[8 * (size_t)e + q / 3] + q % 3] = R[q];
         if (R[q] != R[q]) bad = true;
     }
     if (A.Ke) {

@@ -20,7 +20,8 @@ namespace en234k {
 struct ElemArgs {
     Mesh M;
     double* Ke;             // element blocks, layout above; padded to a multiple of 4 elements
-    double* Re;             // element residuals [e][24]
+    double* Re;             // element residual entries in NODE-MAJOR order: the three components of (element e, local node
+                            // a) at 3 * adj_pos[8e + a], so a node's contributions are contiguous, ascending element order
     CgScalars* S;           // nanflag (may be null)
 };
 
@@ -110,30 +111,36 @@ __global__ void __launch_bounds__(ElemCfg<NEO>::NW * 32, 2) k_element_blocks(Ele
     double* nbuf = geom + 4 * 8 * GS;
     const Mesh& M = A.M;
     const int ngroups = (M.E + 3) >> 2;
+    const Material mat0 = M.mats[0];
     bool bad = false;
     double nd[6];
-    auto stage = [&](int grp) {                                      // node (lane & 7) of element 4 grp + (lane >> 3)
-        const int e = min(4 * grp + (lane >> 3), M.E - 1);           // padding lanes repeat the last element
-        const int n = M.conn[(size_t)(lane & 7) * M.E + e];
+    const int W = gridDim.x * NW;
+    auto node_of = [&](int grp) -> int {                             // node (lane & 7) of element 4 grp + (lane >> 3)
+        if (grp >= ngroups) return 0;
+        return M.conn[(size_t)(lane & 7) * M.E + min(4 * grp + (lane >> 3), M.E - 1)];   // padding lanes repeat the last element
+    };
+    auto stage = [&](int n) {
         nd[0] = __ldg(M.x + n); nd[1] = __ldg(M.y + n); nd[2] = __ldg(M.z + n);
         nd[3] = ld(3 * (size_t)n); nd[4] = ld(3 * (size_t)n + 1); nd[5] = ld(3 * (size_t)n + 2);
     };
     int grp = blockIdx.x * NW + warp;
-    if (grp < ngroups) stage(grp);
-    for (; grp < ngroups; grp += gridDim.x * NW) {
+    stage(node_of(grp));
+    int n_next = node_of(grp + W);                                   // node index fetched two groups ahead of its use
+    for (; grp < ngroups; grp += W) {
         {
             double* dst = nbuf + (lane >> 3) * NS + (lane & 7) * 6;
 #pragma unroll
             for (int q = 0; q < 6; ++q) dst[q] = nd[q];
         }
         __syncwarp();
-        if (grp + gridDim.x * NW < ngroups) stage(grp + gridDim.x * NW);
+        stage(n_next);
+        n_next = node_of(grp + 2 * W);
         // ---------------- phase A
         {
             const int g = lane >> 3, p = lane & 7;
             const int e = min(4 * grp + g, M.E - 1);
             const bool valid = 4 * grp + g < M.E;
-            const Material mat = M.mats[M.mat[e]];
+            const Material mat = M.n_mats == 1 ? mat0 : M.mats[M.mat[e]];
             double* gg = geom + (g * 8 + p) * GS;
             GpOut gp;
             gauss_point_eval_sm(nbuf + g * NS, p, gg, gp);
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(ElemCfg<NEO>::NW * 32, 2) k_element_blocks(Ele
                 r2 -= (s[6] * d0 + s[7] * d1 + s[8] * d2) * w;
             }
             if (e < M.E) {
-                double* R = A.Re + (size_t)e * 24 + 3 * a;
+                double* R = A.Re + 3 * (size_t)M.adj_pos[8 * (size_t)e + a];
                 R[0] = r0; R[1] = r1; R[2] = r2;
             }
         }
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(ElemCfg<NEO>::NW * 32, 2) k_element_blocks(Ele
             for (int round = 0; round < 2; ++round) {
                 const int el = 2 * round + h;
                 const int e = min(4 * grp + el, M.E - 1);
-                const Material mat = M.mats[M.mat[e]];
+                const Material mat = M.n_mats == 1 ? mat0 : M.mats[M.mat[e]];
                 const double* ge = geom + el * 8 * GS;
                 double K[4][9];
                 if (NEO && mat.kind == 1) {
@@ -243,6 +250,99 @@ __global__ void __launch_bounds__(ElemCfg<NEO>::NW * 32, 2) k_element_blocks(Ele
     if (bad && A.S) atomicOr(&A.S->nanflag, 1);
 }
 
+// Residual-only element kernel for the linear-elastic elements (matrix-free residual assembly and the general-mesh
+// matrix-free operator, where the "residual" of the field x is -K_e x_e).  Same staging as k_element_blocks; each lane
+// keeps its Gauss point's dN/dx in registers, forms the 24 nodal force entries of that point and the eight points of an
+// element are summed by a halving butterfly over the eight lanes (lane a ends with node a) — no geometry in shared
+// memory, so three CTAs fit per SM.
+#ifndef FORCES_OCC
+#define FORCES_OCC 2
+#endif
+template <class Load>
+__global__ void __launch_bounds__(256, FORCES_OCC) k_element_forces(ElemArgs A, Load ld) {
+    constexpr int NW = 8, NS = ElemCfg<false>::NSTRIDE;
+    __shared__ double nbuf_all[NW * 4 * NS];
+    if (ld.stopped()) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, p = lane & 7;
+    double* nbuf = nbuf_all + warp * 4 * NS;
+    const Mesh& M = A.M;
+    const int ngroups = (M.E + 3) >> 2, W = gridDim.x * NW;
+    const Material mat0 = M.mats[0];
+    bool bad = false;
+    double nd[6];
+    auto node_of = [&](int grp) -> int {
+        if (grp >= ngroups) return 0;
+        return M.conn[(size_t)p * M.E + min(4 * grp + g, M.E - 1)];
+    };
+    auto stage = [&](int n) {
+        nd[0] = __ldg(M.x + n); nd[1] = __ldg(M.y + n); nd[2] = __ldg(M.z + n);
+        nd[3] = ld(3 * (size_t)n); nd[4] = ld(3 * (size_t)n + 1); nd[5] = ld(3 * (size_t)n + 2);
+    };
+    int grp = blockIdx.x * NW + warp;
+    stage(node_of(grp));
+    int n_next = node_of(grp + W);
+    for (; grp < ngroups; grp += W) {
+        {
+            double* dst = nbuf + g * NS + p * 6;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) dst[q] = nd[q];
+        }
+        __syncwarp();
+        stage(n_next);
+        n_next = node_of(grp + 2 * W);
+        const int e = 4 * grp + g;
+        const bool valid = e < M.E;
+        const Material mat = M.n_mats == 1 ? mat0 : M.mats[M.mat[valid ? e : M.E - 1]];
+        double gg[GEOM_STRIDE];
+        GpOut gp;
+        gauss_point_eval_sm(nbuf + g * NS, p, gg, gp);
+        if (valid && !(gp.det != 0.0)) bad = true;
+        double s[9];
+        stress_linear(mat, gp.H, s);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) s[q] *= -gp.det;                  // R = - sum_p w|J| sigma . grad N  (w = 1)
+        double f[24];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            f[3 * a] = s[0] * gg[3 * a] + s[1] * gg[3 * a + 1] + s[2] * gg[3 * a + 2];
+            f[3 * a + 1] = s[3] * gg[3 * a] + s[4] * gg[3 * a + 1] + s[5] * gg[3 * a + 2];
+            f[3 * a + 2] = s[6] * gg[3 * a] + s[7] * gg[3 * a + 1] + s[8] * gg[3 * a + 2];
+        }
+        // halving butterfly over the 8 Gauss-point lanes: lane a ends with the 3 components of node a
+        double h[12], q6[6], r3[3];
+        {
+            const bool up = p & 4;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const double send = up ? f[j] : f[12 + j], keep = up ? f[12 + j] : f[j];
+                h[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+        }
+        {
+            const bool up = p & 2;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const double send = up ? h[j] : h[6 + j], keep = up ? h[6 + j] : h[j];
+                q6[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+        }
+        {
+            const bool up = p & 1;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double send = up ? q6[j] : q6[3 + j], keep = up ? q6[3 + j] : q6[j];
+                r3[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+        }
+        if (valid) {
+            double* R = A.Re + 3 * (size_t)M.adj_pos[8 * (size_t)e + p];
+            R[0] = r3[0]; R[1] = r3[1]; R[2] = r3[2];
+        }
+        __syncwarp();
+    }
+    if (bad && A.S) atomicOr(&A.S->nanflag, 1);
+}
+
 struct GatherArgs {
     Mesh M;
     const double* Ke;
@@ -277,7 +377,7 @@ __device__ __forceinline__ void gather_row_generic(const GatherArgs& A, int i, i
     for (int k = k0; k < k1; ++k) {
         const int ea = M.adj[k];
         const int e = ea >> 3, a = ea & 7;
-        if (lane < 3) R += A.Re[(size_t)e * 24 + 3 * a + lane];
+        if (lane < 3) R += A.Re[3 * (size_t)k + lane];
         if (A.assemble_matrix) {
             for (int q = lane; q < 72; q += 32) {
                 const int b = q / 9, rc = q % 9, j = ((a & 1) * 2 + (b & 1)) * 9 + rc;
@@ -342,7 +442,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_gather_rows(GatherArgs A) {
                     const int b = (my_inv >> (4 * k)) & 15;
                     ok[u] = A.assemble_matrix && ea >= 0 && b != 15;
                     rv[u] = 0.0;
-                    if (lane < 3 && ea >= 0) rv[u] = A.Re[(size_t)e * 24 + 3 * a + lane];
+                    if (lane < 3 && ea >= 0) rv[u] = A.Re[3 * (size_t)(k0 + k) + lane];
                     if (ok[u]) {
                         const double* src = A.Ke + (size_t)(e >> 1) * 1152 + ((e & 1) * 16 + (a >> 1) * 4 + (b >> 1)) * 2;
                         const int j0 = ((a & 1) * 2 + (b & 1)) * 9;
@@ -407,8 +507,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_gather_residual(GatherArgs A) {
         const int k0 = M.adj_ptr[i], k1 = M.adj_ptr[i + 1];
         double r[3] = {0.0, 0.0, 0.0};
         for (int k = k0; k < k1; ++k) {
-            const int ea = M.adj[k];
-            const double* f = A.Re + (size_t)(ea >> 3) * 24 + 3 * (ea & 7);
+            const double* f = A.Re + 3 * (size_t)k;
             r[0] += __ldcs(f); r[1] += __ldcs(f + 1); r[2] += __ldcs(f + 2);
         }
 #pragma unroll

@@ -48,8 +48,10 @@ struct Mesh {
     const int* conn;                   // SoA connectivity conn[a*E + e], 0-based nodes
     const int* mat;                    // material index per element
     const Material* mats;
+    int n_mats;                        // 1: every element uses mats[0] (kernels then skip the per-element lookup)
     const int* adj_ptr;                // node -> (element, local node) adjacency, ascending element
     const int* adj;                    // e*8 + a
+    const int* adj_pos;                // inverse of adj: adjacency position of (element e, local node a) at [8e + a]
     const uint8_t* slot;               // 8 per adjacency entry: position of column conn[e][b] in the node's block row
     const int* browptr;                // block-row pointers (N+1)
     const int* bcol;                   // block columns, ascending within a row
@@ -152,7 +154,12 @@ struct LoadMasked {                    // x with prescribed DOFs zeroed (operato
     const double* __restrict__ x;
     const uint8_t* __restrict__ cflag; // may be null
     const CgScalars* stop = nullptr;   // PCG stop flag: kernels of a captured iteration exit at once when set
-    __device__ __forceinline__ double operator()(size_t d) const { return (cflag && cflag[d]) ? 0.0 : x[d]; }
+    // both loads are issued unconditionally: a load of x behind the branch on cflag would cost two memory latencies
+    __device__ __forceinline__ double operator()(size_t d) const {
+        const double v = x[d];
+        const uint8_t f = cflag ? cflag[d] : (uint8_t)0;
+        return f ? 0.0 : v;
+    }
     __device__ __forceinline__ bool stopped() const { return stop != nullptr && stop->stop != 0; }
 };
 

@@ -2,8 +2,8 @@
 // path — its CG SpMV, src/solver_conjugate_gradient.f90:877-883, always reads an assembled matrix).
 // K_e x_e is evaluated as the internal force of the linear-elastic element for the displacement field x
 // (the integrand of el_linelast_3Dbasic.f90:124-128 with u := x), never forming K_e.
-// Operator application (mf_apply): the batched element kernel of the assembly (k_element_blocks, residual-only
-// instantiation, reading the masked vector x instead of the DOFs) leaves f_e = -K_e x_e in the element scratch and
+// Operator application (mf_apply): the residual-only element kernel of the assembly (k_element_forces, reading the
+// masked vector x instead of the DOFs) leaves f_e = -K_e x_e in the node-major element scratch and
 // k_mf_gather sums every node's contributions in ascending element order — no atomics, no colouring, deterministic.
 // The Jacobi diagonal (mf_diag, once per boundary-condition pass) is still integrated colour by colour: elements are
 // greedily coloured so that no two elements of a colour share a node, colours are processed by successive launches.
@@ -25,7 +25,7 @@ namespace en234k {
 struct DominantRow { double v[243]; };
 
 struct MfData {
-    double* d_fe = nullptr;         // element force scratch [e][24]
+    double* d_fe = nullptr;         // element force scratch, node-major (3 per adjacency entry)
     // congruent-mesh fast path: every element is a translate of element 0 (bitwise equal node offsets, same material),
     // so one 24x24 K_e serves the whole mesh and a block row is determined by WHICH local nodes of its adjacent elements
     // the node is (and where their columns sit in the row): a few dozen distinct rows on a structured block.  The
@@ -290,8 +290,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_mf_gather(int N, const int* __r
         for (int kk = 0; kk < kmax; kk += 8) {
             double v0 = 0.0, v1 = 0.0, v2 = 0.0;
             if (k0 + kk + k < k1) {
-                const int ea = adj[k0 + kk + k];
-                const double* f = fe + (size_t)(ea >> 3) * 24 + 3 * (ea & 7);
+                const double* f = fe + 3 * (size_t)(k0 + kk + k);     // node-major scratch: contiguous per node
                 v0 = __ldcs(f); v1 = __ldcs(f + 1); v2 = __ldcs(f + 2);
             }
 #pragma unroll
@@ -340,13 +339,10 @@ inline int mf_setup(MfData& mf, const Mesh& M, const std::vector<int>& conn /*So
     mf.grid_vec = std::min(MAX_PARTIALS, std::max(1, std::min((ndof + VEC_THREADS - 1) / VEC_THREADS, n_sm * 8)));
     // operator application: element kernel (one warp per four elements, persistent) + node gather
     if (cudaMalloc((void**)&mf.d_fe, (size_t)E * 24 * sizeof(double)) != cudaSuccess) return 1;
-    mf.elem_smem = ElemCfg<false>::SMEM;
-    mf.elem_threads = ElemCfg<false>::NW * 32;
+    mf.elem_smem = 0;
+    mf.elem_threads = 256;
     int occ = 1;
-    if (cudaFuncSetAttribute(k_element_blocks<false, false, LoadMasked>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)mf.elem_smem) != cudaSuccess) return 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_element_blocks<false, false, LoadMasked>, mf.elem_threads,
-                                                      mf.elem_smem) != cudaSuccess) return 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_element_forces<LoadMasked>, mf.elem_threads, 0) != cudaSuccess) return 1;
     const int wpc = mf.elem_threads / 32, groups = (E + 3) / 4;
     mf.grid_elem = std::max(1, std::min((groups + wpc - 1) / wpc, n_sm * std::max(occ, 1)));
     mf.grid_gather = std::min(MAX_PARTIALS, std::max(1, (N + VEC_THREADS / 8 - 1) / (VEC_THREADS / 8)));
@@ -484,7 +480,7 @@ inline void mf_apply(const MfData& mf, const Mesh& M, int ndof, const uint8_t* c
         mf_stencil(mf, M, cflag, owned, x, y, partials, S, s, launches, 1);
         return;
     }
-    k_element_blocks<false, false, LoadMasked><<<mf.grid_elem, mf.elem_threads, mf.elem_smem, s>>>(EA, LoadMasked{x, cflag, S});
+    k_element_forces<LoadMasked><<<mf.grid_elem, mf.elem_threads, 0, s>>>(EA, LoadMasked{x, cflag, S});
     k_mf_gather<<<mf.grid_gather, VEC_THREADS, 0, s>>>(M.N, M.adj_ptr, M.adj, mf.d_fe, cflag, owned, x, y, partials, S);
     *launches += 2;
 }

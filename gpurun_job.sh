@@ -1,1 +1,3 @@
-python bench.py --workload c5 --steps 2 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['roofline']['fp64'], d['roofline']['ms_per_launch'])"
+python tools/mf_times.py 64 0.2; python tools/mf_times.py 128 0.2
+python tools/phase_times.py 96 1002 3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3

@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(ElemCfg<NEO>::NW * 32, 2) k_element_blocks(Ele
         __syncwarp();
         stage(n_next);
         n_next = node_of(grp + 2 * W);
+        // scratch position of this lane's phase-R output, fetched now and used after phase A
+        const int rpos = 4 * grp + (lane >> 3) < M.E ? M.adj_pos[8 * (size_t)(4 * grp + (lane >> 3)) + (lane & 7)] : 0;
         // ---------------- phase A
         {
             const int g = lane >> 3, p = lane & 7;
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(ElemCfg<NEO>::NW * 32, 2) k_element_blocks(Ele
                 r2 -= (s[6] * d0 + s[7] * d1 + s[8] * d2) * w;
             }
             if (e < M.E) {
-                double* R = A.Re + 3 * (size_t)M.adj_pos[8 * (size_t)e + a];
+                double* R = A.Re + 3 * (size_t)rpos;
                 R[0] = r0; R[1] = r1; R[2] = r2;
             }
         }
@@ -292,6 +294,7 @@ __global__ void __launch_bounds__(256, FORCES_OCC) k_element_forces(ElemArgs A, 
         n_next = node_of(grp + 2 * W);
         const int e = 4 * grp + g;
         const bool valid = e < M.E;
+        const int pos = valid ? M.adj_pos[8 * (size_t)e + p] : 0;     // fetched now, used after the arithmetic
         const Material mat = M.n_mats == 1 ? mat0 : M.mats[M.mat[valid ? e : M.E - 1]];
         double gg[GEOM_STRIDE];
         GpOut gp;
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(256, FORCES_OCC) k_element_forces(ElemArgs A, 
             }
         }
         if (valid) {
-            double* R = A.Re + 3 * (size_t)M.adj_pos[8 * (size_t)e + p];
+            double* R = A.Re + 3 * (size_t)pos;
             R[0] = r3[0]; R[1] = r3[1]; R[2] = r3[2];
         }
         __syncwarp();

@@ -452,7 +452,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_gather_rows(GatherArgs A) {
 #pragma unroll
                         for (int rc = 0; rc < 9; ++rc) {
                             const int j = j0 + rc;
-                            v[u][rc] = __ldcs(src + (j >> 1) * 64 + (j & 1));
+                            // default caching, not evict-first: the rest of each 64-byte chunk is wanted by the
+                            // neighbouring lanes' later loads (with __ldcs the scratch came from HBM 1.45 times)
+                            v[u][rc] = __ldg(src + (j >> 1) * 64 + (j & 1));
                         }
                     }
                 }

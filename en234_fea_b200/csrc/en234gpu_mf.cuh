@@ -54,7 +54,9 @@ struct MfData {
     int grid_vec = 0;
 };
 
-// 8 lanes = the 8 Gauss points of one element.  mode 0: y += K_e x (x masked by cflag);  mode 1: diag(K_e) into y.
+// 8 lanes = the 8 Gauss points of one element.  mode 1: diag(K_e) into y (the Jacobi diagonal of the matrix-free solve,
+// once per boundary-condition pass);  mode 0: y += K_e x — the colour-pass operator the element-kernel + gather form
+// replaced, kept for A/B.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_mf_color(Mesh M, int n, const int* __restrict__ elist, const uint8_t* cflag,
                                                   const double* __restrict__ x, double* __restrict__ y,
@@ -125,21 +127,6 @@ __global__ void __launch_bounds__(256) k_mf_color(Mesh M, int n, const int* __re
         double* yy = y + 3 * (size_t)node;
         yy[0] += r3[0]; yy[1] += r3[1]; yy[2] += r3[2];
     }
-}
-
-// y_row = x_row on prescribed rows (unit diagonal on the owner rank only), partial of x.y over all local rows
-__global__ void __launch_bounds__(VEC_THREADS) k_mf_finish(int n, const uint8_t* cflag, const uint8_t* owned, const double* x,
-                                                            double* y, double* partials, const CgScalars* S) {
-    __shared__ double red[VEC_THREADS / 32 + 1];
-    if (S && S->stop) return;
-    double dot = 0.0;
-    for (int d = blockIdx.x * VEC_THREADS + threadIdx.x; d < n; d += gridDim.x * VEC_THREADS) {
-        double v = y[d];
-        if (cflag && cflag[d]) { v = (owned == nullptr || owned[d / 3]) ? x[d] : 0.0; y[d] = v; }
-        dot += v * x[d];
-    }
-    const double t = block_sum<VEC_THREADS>(dot, red);
-    if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
 
 __global__ void k_mask_values(int n, const uint8_t* cflag, const double* cval, double* out) {

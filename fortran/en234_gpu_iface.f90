@@ -68,6 +68,12 @@ module en234_gpu_iface
             integer(c_int), intent(out)   :: cg_iterations, fail
             integer(c_int)                :: en234gpu_solve
         end function
+        ! initial_state_variables = updated_state_variables on the device (src/staticstep.f90:87); built-in C3D8 elements
+        function en234gpu_commit_state(h) bind(C, name='en234gpu_commit_state')
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h
+            integer(c_int)     :: en234gpu_commit_state
+        end function
         function en234gpu_last_error() bind(C, name='en234gpu_last_error')
             import :: c_ptr
             type(c_ptr) :: en234gpu_last_error

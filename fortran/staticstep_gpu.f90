@@ -94,6 +94,7 @@ subroutine compute_static_step_gpu
         current_step_number = current_step_number + 1
         dof_total = dof_total + dof_increment
         initial_state_variables = updated_state_variables
+        status = en234gpu_commit_state(gpu_handle)       ! the device copy of the element state (C3D8 elements)
         TIME = TIME + DTIME
         DTIME = new_time_increment
     end do

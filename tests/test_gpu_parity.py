@@ -410,3 +410,34 @@ def test_golden_log_newton_history_on_the_gpu():
     sv = g.state_variables(updated=False)
     assert sv.size == 3075 * 120 and np.abs(sv).max() > 0
     g.close()
+
+
+def test_edge_cases_isolated_node_zero_load_and_repeated_prescribed_dof():
+    """A node no element uses (kept as an identity block row), a step without any load (zero right-hand side: x = 0 without
+    iterating, solver_conjugate_gradient.f90:805-814), a prescribed DOF listed twice (the last value wins, as when the
+    reference applies fixdof in list order)."""
+    m = Model.from_text(synthetic_block_input(3, jitter=0.1))
+    a = m.arrays()
+    N = m.n_nodes
+    coords = np.concatenate([a["coords"], [5.0, 5.0, 5.0]])               # node N+1 is not referenced by any element
+    g = GpuSystem(arrays=dict(n_nodes=N + 1, n_elements=m.n_elements, coords=coords, connectivity=a["connectivity"],
+                              element_flag=a["element_flag"], element_prop_index=a["element_prop_index"],
+                              element_properties=a["element_properties"]))
+    n = g.ndof
+    rf, nrm, fail = g.assemble(np.zeros(n), np.zeros(n), None)
+    assert fail == 0 and nrm == 0.0
+    A = g.csr().toarray()
+    assert np.all(A[3 * N:, :] == 0.0) and np.all(A[:, 3 * N:] == 0.0)
+    fixed = np.array([0, 1, 2, 3 * N, 3 * N + 1, 3 * N + 2, 0], np.int32)   # DOF 0 twice
+    corr = np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.25])
+    g.apply_boundaryconditions(None, fixed, corr)
+    rhs = g.rhs()
+    assert rhs[0] == 0.25                                                 # the later entry wins
+    du, corr_norm, its, sfail = g.solve(np.zeros(n), 0, 1e-24, 5000)
+    assert sfail == 0 and its > 0 and abs(du[0] - 0.25) < 1e-12 and np.all(du[3 * N:] == 0.0)
+    # no load at all: zero rhs -> zero solution, zero iterations
+    g.assemble(np.zeros(n), np.zeros(n), None)
+    g.apply_boundaryconditions(None, fixed[:6], np.zeros(6))
+    du, corr_norm, its, sfail = g.solve(np.zeros(n), 0, 1e-24, 5000)
+    assert sfail == 0 and its == 0 and corr_norm == 0.0 and np.all(du == 0.0)
+    g.close()

@@ -229,6 +229,19 @@ def test_golden_log_newton_history():
     assert res["profile"][0] == 12312                                               # .out:11
 
 
+def test_golden_umat_input_fixture_matches_model_arrays():
+    """tests/golden/holeplate_3d_umat.in.gz (the product writer's re-emission of the golden-log input: MATERIAL, ELEMENTS,
+    INTERNAL / C3D8, SOLVER ... UNSYMMETRIC) parses back to exactly the arrays the oracle runs on."""
+    import gzip
+    a = dict(np.load(os.path.join(GOLDEN, "holeplate_3d_umat_model.npz")))
+    b = Model.from_text(gzip.open(os.path.join(GOLDEN, "holeplate_3d_umat.in.gz"), "rb").read().decode()).arrays()
+    for k in a:
+        if k in ("cg_tolerance", "max_cg_iterations", "checkstiffness_flag"):
+            continue
+        assert np.array_equal(a[k], b[k]), k
+    assert b["unsymmetric"][0] == 1 and set(b["element_flag"].tolist()) == {10003} and b["element_n_states"][0] == 120
+
+
 def test_parser_rules():
     # parse.f90: blanks stripped, case-insensitive prefix keywords, % comments, Fortran D exponents, 100-char lines
     txt = synthetic_block_input(2)

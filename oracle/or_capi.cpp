@@ -122,6 +122,24 @@ int or_check_stiffness(int flag, const double* coords24, const double* dof_incre
     return 0;
 }
 
+// Gibbs-Poole-Stockmeyer node order of the model (bandwidth_minimizer.f90): order[i] = 0-based node numbered i+1
+int or_gps_node_order(void* model, int* order) {
+    std::vector<int> o;
+    gps_node_order(*(Model*)model, o);
+    for (size_t i = 0; i < o.size(); ++i) order[i] = o[i];
+    return 0;
+}
+
+// conditioning line of the field-projection mass matrix LU (print_state): out = {max diag, min diag, digits lost}
+int or_projection_mass_lu(void* model, const int* order, double* out) {
+    Model* m = (Model*)model;
+    std::vector<int> o(order, order + m->n_nodes);
+    StepLog log;
+    projection_mass_lu(*m, o, &log);
+    out[0] = log.lu_dimx[0]; out[1] = log.lu_dimn[0]; out[2] = log.lu_ifig[0];
+    return 0;
+}
+
 // ---- assembled systems ------------------------------------------------------------------------
 void* or_system_new(void* model, int kind) {
     System* s = new System();

@@ -293,6 +293,72 @@ static void lu_decomposition(Skyline& s, StepLog* log) {
     }
 }
 
+// The consistent field-projection mass matrix of print_state (src/printing.f90:1214-1383, assemble_projection_mass_matrix,
+// hex8 branch: 27-point rule with the reference's literals, Element_Utilities.f90:651-656) in node-level skyline storage
+// with the node numbering given, factorised by the same LDU routine (printing.f90:475-488).  Only the conditioning line
+// the reference prints for it is of interest here: the golden log carries it once per printed step.
+void projection_mass_lu(const Model& m, const std::vector<int>& node_order, StepLog* log) {
+    const int N = m.n_nodes;
+    std::vector<int> num(N, 0);                       // node -> equation (0-based)
+    for (int i = 0; i < N; ++i) num[node_order[i]] = i;
+    Skyline s;
+    s.neq = N;
+    std::vector<long long> h(N, 0);
+    for (int lmn = 0; lmn < m.n_elements; ++lmn) {
+        int mineq = N - 1;
+        for (int i = 0; i < 8; ++i) mineq = std::min(mineq, num[m.connectivity[8 * (size_t)lmn + i] - 1]);
+        for (int i = 0; i < 8; ++i) {
+            const int q = num[m.connectivity[8 * (size_t)lmn + i] - 1];
+            h[q] = std::max<long long>(h[q], q - mineq);
+        }
+    }
+    h[0] = 0;
+    s.jp.assign(N, 0);
+    long long acc = 0;
+    for (int n = 0; n < N; ++n) { acc += h[n]; s.jp[n] = acc; }
+    s.aupp.assign((size_t)acc, 0.0);
+    s.diag.assign(N, 0.0);
+    s.unsym = false;
+    const double x1[3] = {(double)-0.7745966692f, 0.0, (double)0.7745966692f};
+    const double w1[3] = {0.5555555555, 0.888888888, 0.55555555555};
+    static const double SGN[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}};
+    for (int lmn = 0; lmn < m.n_elements; ++lmn) {
+        double x[8][3], em[8][8];
+        int nodes[8];
+        for (int a = 0; a < 8; ++a) {
+            nodes[a] = m.connectivity[8 * (size_t)lmn + a] - 1;
+            for (int i = 0; i < 3; ++i) x[a][i] = m.coords[3 * (size_t)nodes[a] + i];
+        }
+        for (int a = 0; a < 8; ++a) for (int b = 0; b < 8; ++b) em[a][b] = 0.0;
+        for (int k = 0; k < 3; ++k)
+            for (int j = 0; j < 3; ++j)
+                for (int i = 0; i < 3; ++i) {
+                    const double xi[3] = {x1[i], x1[j], x1[k]}, w = w1[i] * w1[j] * w1[k];
+                    double Nn[8], dN[8][3], J[3][3];
+                    for (int a = 0; a < 8; ++a) {                    // Element_Utilities.f90:908-940
+                        const double f1 = 1.0 + SGN[a][0] * xi[0], f2 = 1.0 + SGN[a][1] * xi[1], f3 = 1.0 + SGN[a][2] * xi[2];
+                        Nn[a] = f1 * f2 * f3 / 8.0;
+                        dN[a][0] = SGN[a][0] * (f2 * f3 / 8.0); dN[a][1] = SGN[a][1] * (f1 * f3 / 8.0); dN[a][2] = SGN[a][2] * (f1 * f2 / 8.0);
+                    }
+                    for (int r = 0; r < 3; ++r)
+                        for (int c = 0; c < 3; ++c) { double t = 0; for (int a = 0; a < 8; ++a) t += x[a][r] * dN[a][c]; J[r][c] = t; }
+                    const double det = J[0][0] * J[1][1] * J[2][2] - J[0][0] * J[1][2] * J[2][1] - J[0][1] * J[1][0] * J[2][2] +
+                                       J[0][1] * J[1][2] * J[2][0] + J[0][2] * J[1][0] * J[2][1] - J[0][2] * J[1][1] * J[2][0];
+                    for (int b = 0; b < 8; ++b)
+                        for (int a = 0; a < 8; ++a) em[a][b] = em[a][b] + Nn[b] * Nn[a] * det * w;
+                }
+        for (int j = 0; j < 8; ++j) {
+            const int irow = num[nodes[j]];
+            for (int i = 0; i < 8; ++i) {
+                const int icol = num[nodes[i]];
+                if (icol == irow) s.diag[irow] += em[i][i];
+                else if (icol > irow) s.aupp[(size_t)(s.jp[icol] - 1 - (icol - 1 - irow))] += em[j][i];
+            }
+        }
+    }
+    lu_decomposition(s, log);
+}
+
 // backsubstitution (solver_direct.f90:976-1032)
 static void backsubstitution(Skyline& s) {
     const int neq = s.neq;

@@ -119,6 +119,8 @@ struct Skyline {
 };
 void compute_profile(const Model& m, const std::vector<int>& node_order, Skyline& s, StepLog* log);
 void gps_node_order(const Model& m, std::vector<int>& node_order);   // bandwidth_minimizer.f90
+struct StepLog;
+void projection_mass_lu(const Model& m, const std::vector<int>& node_order, StepLog* log);   // printing.f90:1214-1383, :475-488
 struct AsmOut {
     std::vector<double> rforce;
     double nodal_force_norm = 0, unbalanced_force_norm = 0, correction_norm = 0;

@@ -4,6 +4,7 @@
 // reproducing that log pins the oracle's driver / assembly / BC / skyline-LDU / Newton logic with reference output.
 //   element: src/continuum_elements.f90:368-761 (continuum_element_static_3D), hex8 branch
 //   material: user_codes/src/abaqus_umat_elastic.for:253-308
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -245,11 +246,249 @@ void c3d8_bbar_static(const double* xc, const double* du, const double* ut, cons
     }
 }
 
-// Gibbs-Poole-Stockmeyer renumbering (src/bandwidth_minimizer.f90) is not restated: the skyline uses the identity
-// node order, which changes the profile statistics and LU conditioning lines of the golden log but not the solution.
+// ---------------------------------------------------------------------------------------------------------------
+// Gibbs-Poole-Stockmeyer node renumbering, src/bandwidth_minimizer.f90 (generate_node_numbers :2-128 and its helpers),
+// restated with the reference's tie-breaking so that the skyline profile of the golden log is reproduced exactly:
+// adjacency lists in insertion order (compute_adjacency :250-268; the linked 10-entry bins of
+// modules/Linkedlist_Handling.f90 only preserve insertion order, so plain vectors are equivalent), the heapsort index
+// routine isort :1084-1138 (its treatment of equal keys matters), level structures in insertion order (levgen
+// :1001-1082), pseudo-diameter search diam :335-484, level-width minimisation widmin :486-736, numbering numgen
+// :738-931 with lowfnd :933-999.  1-based node numbers inside, like the reference.  No constraints (n_constraints = 0).
+namespace {
+
+// isort :1084-1138 — index(1..n) lists the entries of `in` in increasing magnitude (heapsort on the index table)
+void isort(int n, const std::vector<int>& in /*1-based*/, std::vector<int>& index /*1-based*/) {
+    if ((int)index.size() < n + 2) index.resize(n + 2);
+    for (int j = 1; j <= n; ++j) index[j] = j;
+    if (n <= 1) return;
+    int l = n / 2 + 1, ir = n, indxt, k;
+    for (;;) {
+        if (l > 1) {
+            l = l - 1;
+            indxt = index[l];
+            k = in[indxt];
+        } else {
+            indxt = index[ir];
+            k = in[indxt];
+            index[ir] = index[1];
+            ir = ir - 1;
+            if (ir == 1) { index[1] = indxt; return; }
+        }
+        int i = l, j = l + l;
+        while (j <= ir) {
+            if (j < ir && in[index[j]] < in[index[j + 1]]) j = j + 1;
+            if (k < in[index[j]]) { index[i] = index[j]; i = j; j = j + j; }
+            else j = ir + 1;
+        }
+        index[i] = indxt;
+    }
+}
+
+struct Levels {
+    std::vector<int> node_level;                 // 1-based node -> level (0 = none)
+    std::vector<std::vector<int>> list;          // list[l], l = 1..n_levels, nodes in insertion order
+    int n_levels = 0, width = 0;
+    int w(int l) const { return l < (int)list.size() ? (int)list[l].size() : 0; }
+};
+
+struct Gps {
+    int nops = 0;
+    std::vector<int> ideg;                       // node_degree (1-based)
+    std::vector<std::vector<int>> adj;           // adjacency in insertion order (1-based nodes)
+
+    // levgen :1001-1082 with the degree array passed in (widmin calls it with the reduced degrees)
+    void levgen(const std::vector<int>& deg, int start, Levels& L) const {
+        L.node_level.assign(nops + 1, 0);
+        L.list.assign(2, {});
+        L.node_level[start] = 1;
+        L.list[1].push_back(start);
+        L.n_levels = 1;
+        for (;;) {
+            const int nl1 = L.n_levels;
+            L.n_levels++;
+            if (L.n_levels > nops) break;
+            L.list.emplace_back();
+            const std::vector<int> prev = L.list[nl1];
+            for (int node : prev)
+                for (int j = 0; j < deg[node]; ++j) {
+                    const int nbr = adj[node][j];
+                    if (L.node_level[nbr] == 0 && deg[nbr] > 0) {
+                        L.list[L.n_levels].push_back(nbr);
+                        L.node_level[nbr] = L.n_levels;
+                    }
+                }
+            if (L.list[L.n_levels].empty()) break;
+        }
+        L.n_levels--;
+        L.width = 0;
+        for (int l = 1; l <= L.n_levels; ++l) L.width = std::max(L.width, (int)L.list[l].size());
+    }
+};
+
+}  // namespace
+
 void gps_node_order(const Model& m, std::vector<int>& node_order) {
-    node_order.resize(m.n_nodes);
-    for (int i = 0; i < m.n_nodes; ++i) node_order[i] = i;
+    const int N = m.n_nodes;
+    Gps g;
+    g.nops = N;
+    g.ideg.assign(N + 1, 0);
+    g.adj.assign(N + 1, {});
+    // compute_adjacency :131-333 (elements only): adjacency in order of first appearance
+    for (int lmn = 0; lmn < m.n_elements; ++lmn)
+        for (int i = 0; i < 8; ++i) {
+            const int node1 = m.connectivity[8 * (size_t)lmn + i];
+            for (int j = 0; j < 8; ++j) {
+                const int node2 = m.connectivity[8 * (size_t)lmn + j];
+                if (node2 == node1) continue;
+                auto& a = g.adj[node1];
+                if (std::find(a.begin(), a.end(), node2) == a.end()) a.push_back(node2);
+            }
+        }
+    for (int n = 1; n <= N; ++n) g.ideg[n] = (int)g.adj[n].size();
+
+    // ---- diam :335-484
+    int mindeg = N, minnod = 1;
+    for (int i = 1; i <= N; ++i)
+        if (g.ideg[i] < mindeg && g.ideg[i] > 0) { mindeg = g.ideg[i]; minnod = i; }
+    int nv = minnod, nu = minnod;
+    Levels V, U, S;
+    g.levgen(g.ideg, nv, V);
+    std::vector<int> id, sidx;
+    bool swapped = true;
+    while (swapped) {
+        const std::vector<int> last = V.list[V.n_levels];
+        const int n = (int)last.size();
+        id.assign(n + 2, 0);
+        for (int i = 1; i <= n; ++i) id[i] = g.ideg[last[i - 1]];
+        isort(n, id, sidx);
+        int minrem = N;
+        swapped = false;
+        for (int i = 1; i <= n; ++i) {
+            const int ns = last[sidx[i] - 1];
+            g.levgen(g.ideg, ns, S);
+            swapped = false;
+            if (S.n_levels > V.n_levels) { nv = ns; V = S; swapped = true; break; }
+            if (S.width <= minrem) { minrem = S.width; nu = ns; U = S; }
+        }
+    }
+    const int iwvmax = V.width, iwumax = U.width;
+
+    // ---- widmin :486-736
+    Levels F;                                                   // final level structure
+    F.node_level.assign(N + 1, 0);
+    F.list.assign(N + 2, {});
+    int ipair = 0;
+    {
+        int icount = 0;
+        for (int i = 1; i <= N; ++i) if (g.ideg[i] > 0) icount++;
+        std::vector<int> ideg2 = g.ideg;
+        for (int i = 1; i <= N; ++i)
+            if (g.ideg[i] > 0 && V.node_level[i] == U.n_levels + 1 - U.node_level[i]) {
+                F.node_level[i] = V.node_level[i];
+                F.list[V.node_level[i]].push_back(i);
+                icount--;
+                ideg2[i] = 0;
+            }
+        if (icount != 0) {
+            std::vector<std::vector<int>> comp;
+            for (int i = 1; i <= N; ++i)
+                if (ideg2[i] != 0) {
+                    g.levgen(ideg2, i, S);
+                    comp.emplace_back();
+                    for (int l = 1; l <= S.n_levels; ++l)
+                        for (int node : S.list[l]) { comp.back().push_back(node); ideg2[node] = 0; }
+                }
+            const int ncon = (int)comp.size();
+            std::vector<int> nmem(ncon + 2, 0), index;
+            for (int c = 1; c <= ncon; ++c) nmem[c] = (int)comp[c - 1].size();
+            isort(ncon, nmem, index);
+            std::vector<int> levwh(N + 2), levwl(N + 2), lw(N + 2);
+            for (int i = 1; i <= ncon; ++i) {
+                const std::vector<int>& cn = comp[index[ncon + 1 - i] - 1];
+                for (int l = 1; l <= N; ++l) lw[l] = (int)F.list[l].size();
+                levwh = lw; levwl = lw;
+                for (int node : cn) { levwh[V.node_level[node]]++; levwl[U.n_levels + 1 - U.node_level[node]]++; }
+                int ihmax = 0, ilmax = 0;
+                for (int j = 1; j <= U.n_levels; ++j) {
+                    if (levwh[j] > ihmax && levwh[j] > lw[j]) ihmax = levwh[j];
+                    if (levwl[j] > ilmax && levwl[j] > lw[j]) ilmax = levwl[j];
+                }
+                const bool use_v = ilmax > ihmax ? true : (ilmax < ihmax ? false : iwvmax <= iwumax);
+                if (i == 1) ipair = use_v ? 1 : 2;
+                for (int node : cn) {
+                    const int ilev = use_v ? V.node_level[node] : U.n_levels + 1 - U.node_level[node];
+                    F.node_level[node] = ilev;
+                    F.list[ilev].push_back(node);
+                }
+            }
+        }
+    }
+    const int n_levels = V.n_levels;
+
+    // ---- numgen :738-931
+    std::vector<int> numnod(N + 1, 0), list(N + 2), ldeg(N + 2), sort_index;
+    int irev;
+    if (g.ideg[nv] <= g.ideg[nu]) { numnod[nv] = 1; irev = 0; } else { numnod[nu] = 1; irev = 1; }
+    int number = 1;
+    // lowfnd :933-999: lowest-numbered node of lev1 with unnumbered neighbours in lev2; their list in adjacency order
+    auto lowfnd = [&](const std::vector<int>& lev1, const std::vector<int>& lev2) -> int {
+        int low = N + 1, lcount = 0;
+        for (int node1 : lev1) {
+            if (numnod[node1] < low && numnod[node1] > 0) {
+                std::vector<int> tmp;
+                for (int nbr : g.adj[node1])
+                    if (numnod[nbr] == 0 && std::find(lev2.begin(), lev2.end(), nbr) != lev2.end()) tmp.push_back(nbr);
+                if (!tmp.empty()) {
+                    low = numnod[node1];
+                    lcount = (int)tmp.size();
+                    for (int j = 1; j <= lcount; ++j) { list[j] = tmp[j - 1]; ldeg[j] = g.ideg[list[j]]; }
+                }
+            }
+        }
+        return lcount;
+    };
+    auto number_list = [&](int lcount) {
+        isort(lcount, ldeg, sort_index);
+        for (int i = 1; i <= lcount; ++i) numnod[list[sort_index[i]]] = ++number;
+    };
+    {   // first (last) level
+        const int l = irev == 1 ? n_levels : 1;
+        const std::vector<int>& lev = F.list[l];
+        for (;;) {
+            const int lcount = lowfnd(lev, lev);
+            if (lcount > 0) { number_list(lcount); continue; }
+            int nodrem = 0, md = N;
+            for (int node : lev)
+                if (numnod[node] == 0 && g.ideg[node] < md && g.ideg[node] > 0) { md = g.ideg[node]; nodrem = node; }
+            if (nodrem > 0) { numnod[nodrem] = ++number; continue; }
+            break;
+        }
+    }
+    {
+        const int lstart = irev == 0 ? 2 : n_levels - 1, lend = irev == 0 ? n_levels : 1, linc = irev == 0 ? 1 : -1;
+        for (int l = lstart; irev == 0 ? l <= lend : l >= lend; l += linc) {
+            const std::vector<int>& lev1 = F.list[l - linc];
+            const std::vector<int>& lev2 = F.list[l];
+            for (;;) {
+                const int lcount = lowfnd(lev1, lev2);
+                if (lcount > 0) { number_list(lcount); continue; }
+                int nodrem = 0, md = N;
+                for (int node : lev2)
+                    if (numnod[node] == 0 && g.ideg[node] <= md && g.ideg[node] > 0) { md = g.ideg[node]; nodrem = node; }
+                if (nodrem > 0) { numnod[nodrem] = ++number; continue; }
+                break;
+            }
+        }
+    }
+    int nodrem = 0;
+    for (int i = 1; i <= N; ++i) if (g.ideg[i] > 0) nodrem++;
+    if ((irev == 1 && ipair == 2) || (irev == 0 && ipair == 1))
+        for (int i = 1; i <= N; ++i) if (g.ideg[i] > 0) numnod[i] = nodrem + 1 - numnod[i];
+    // node_order_index = isort(node_numbers) (:102): position -> node
+    std::vector<int> order_index;
+    isort(N, numnod, order_index);
+    node_order.resize(N);
+    for (int i = 1; i <= N; ++i) node_order[i - 1] = order_index[i] - 1;
 }
 
 }  // namespace oracle

@@ -72,6 +72,18 @@ class OracleModel:
             lib().or_model_free(self.h)
             self.h = None
 
+    def gps_node_order(self):
+        """The reference's Gibbs-Poole-Stockmeyer numbering (src/bandwidth_minimizer.f90): position -> 0-based node."""
+        order = np.zeros(self.n_nodes, np.int32)
+        lib().or_gps_node_order(self.h, _i(order))
+        return order
+
+    def projection_mass_lu(self, order):
+        """(max reduced diagonal, min reduced diagonal, digits lost) of the print_state projection mass matrix LU."""
+        out = np.zeros(3)
+        lib().or_projection_mass_lu(self.h, _i(np.ascontiguousarray(order, np.int32)), _d(out))
+        return out
+
     def run_static(self):
         L = lib()
         u, rf = np.zeros(self.ndof), np.zeros(self.ndof)

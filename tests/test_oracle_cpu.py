@@ -196,22 +196,30 @@ def test_parser_on_reference_files():
         Model.read(os.path.join(REF_INPUTS, "Abaqus_vumat_linear_elastic_3d.in"))
 
 
-def test_golden_log_newton_history():
+def test_golden_log_reproduced_line_by_line():
     """The only golden output of the reference: Output_Files/Abaqus_umat_holeplate_3d.out (C3D8 B-bar + elastic UMAT,
-    SOLVER, DIRECT, NONLINEAR 1e-5/15, UNSYMMETRIC; 3 steps).  The oracle's driver, element gather, unsymmetric skyline
-    assembly, fixdof, LDU solve and convergence check must reproduce every printed Newton record to the 6 significant
-    digits of the log.  (Profile statistics and LU conditioning lines depend on the Gibbs-Poole-Stockmeyer numbering,
-    which is not restated: a reverse Cuthill-McKee order from scipy is used for speed; the solution does not depend on it.)"""
-    import scipy.sparse as sp
-    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    SOLVER, DIRECT, NONLINEAR 1e-5/15, UNSYMMETRIC; 3 steps).  Every number the log prints is reproduced by the oracle:
+      .out:4-7     element / node / DOF counts (parser)
+      .out:11-15   skyline profile statistics — need the reference's Gibbs-Poole-Stockmeyer numbering with its
+                   tie-breaking (src/bandwidth_minimizer.f90, restated in oracle/or_next.cpp)
+      .out:20-23 … LU conditioning lines of the five stiffness factorisations (4 significant digits, digits lost)
+      .out:77-80 … LU conditioning line of print_state's field-projection mass matrix (27-point rule, printing.f90:1214-1383)
+      .out:26-31 … the five Newton records (6 significant digits)."""
     a = dict(np.load(os.path.join(GOLDEN, "holeplate_3d_umat_model.npz")))
     N = int(a["n_nodes"][0])
     assert (int(a["n_elements"][0]), N, 3 * N) == (3075, 4104, 12312)              # .out:4-7
-    conn = a["connectivity"].reshape(-1, 8) - 1
-    G = sp.coo_matrix((np.ones(conn.size * 8), (np.repeat(conn, 8, axis=1).ravel(), np.tile(conn, (1, 8)).ravel())),
-                      shape=(N, N)).tocsr()
-    order = reverse_cuthill_mckee(G, symmetric_mode=True).astype(np.int32)
-    res = ob.OracleModel(a, node_order=order).run_static()
+    order = ob.OracleModel(a).gps_node_order()
+    assert sorted(order.tolist()) == list(range(N))
+    om = ob.OracleModel(a, node_order=order)
+    res = om.run_static()
+    assert res["profile"] == [12312, 596, 375, 390, 4613967]                        # .out:11-15
+    # .out:20-23, 36-39, 52-55, 85-88, 118-121: max / min diagonal of the reduced matrix (e11.4), digits lost
+    for (dimx, dimn, ifig), want in zip(res["lu"], (0.3562e4, 0.3568e4, 0.3568e4, 0.3574e4, 0.3580e4)):
+        assert float("%.4g" % dimx) == want and dimn == 1.0 and int(ifig) == 1
+    assert len(res["lu"]) == 5
+    pm = om.projection_mass_lu(order)                                               # .out:77-80,110-113,143-146
+    assert float("%.4g" % pm[0]) == 0.3471e-2 and float("%.4g" % pm[1]) == 0.2005e-3 and int(pm[2]) == 0
+    assert float("%.4g" % (pm[0] / pm[1])) == 0.1731e2
     # step, iteration, correction norm, generalized force norm, out-of-balance norm, ratio   (.out:26-31,42-47,58-63,91-96,124-129)
     golden = [(1, 1, 0.390615e+00, 0.568430e+01, 0.240174e-01, 0.395353e-02),
               (1, 2, 0.124137e-03, 0.568438e+01, 0.601132e-04, 0.105749e-04),
@@ -226,7 +234,6 @@ def test_golden_log_newton_history():
             assert abs(got - want) <= 0.51 * ulp, (row, g)
         assert row[6] == 1e-5
     assert [int(r[7]) for r in res["newton"]] == [0, 0, 1, 1, 1]
-    assert res["profile"][0] == 12312                                               # .out:11
 
 
 def test_golden_umat_input_fixture_matches_model_arrays():

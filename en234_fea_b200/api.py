@@ -55,7 +55,7 @@ HOST_SYMBOLS = [
     "en234host_model_int", "en234host_model_double", "en234host_model_find_set", "en234host_model_set",
     "en234host_model_write_text", "en234host_evaluate_loads", "en234host_gpu_create", "en234host_run_static",
     "en234host_partition", "en234host_part_free", "en234host_part_int", "en234host_part_owned",
-    "en234host_part_gpu_create", "en234host_run_static_part",
+    "en234host_part_gpu_create", "en234host_run_static_part", "en234host_check_stiffness",
 ]
 # Fortran-linkage twins of the reference plugin entry points (include/en234host.h)
 PLUGIN_SYMBOLS = ["user_element_static_", "uel_"]
@@ -180,6 +180,16 @@ class Model:
 
     def find_set(self, name, element_set=False):
         return host_lib().en234host_model_find_set(self.h, 1 if element_set else 0, name.encode())
+
+    def check_stiffness(self, element_flag=None, dof_total=None, dof_increment=None, log_path=None):
+        """check_stiffness (src/checkstiffness.f90) on the device twins: returns (err, n_unsymmetric, n_numerical_unsymmetric)."""
+        flag = int(self.ints("checkstiffness_flag")[0]) if element_flag is None else int(element_flag)
+        err, nu, nnu = C.c_double(), C.c_int(), C.c_int()
+        rc = host_lib().en234host_check_stiffness(self.h, C.c_int(flag), _dp(_f64(dof_total)), _dp(_f64(dof_increment)),
+                                                  os.fsencode(log_path) if log_path else None, C.byref(err), C.byref(nu), C.byref(nnu))
+        if rc:
+            raise RuntimeError("check_stiffness failed: " + host_lib().en234host_last_error().decode())
+        return err.value, nu.value, nnu.value
 
     def evaluate_loads(self, time, dtime, dof_total=None, dof_increment=None):
         nd = 3 * self.n_nodes

@@ -11,6 +11,12 @@
 
 using namespace en234;
 
+namespace en234 {
+int check_stiffness(const Model& m, int element_flag, const double* dof_total, const double* dof_increment, FILE* log,
+                    double* err_out, int* n_unsymmetric, int* n_numerical_unsymmetric, std::string& error);
+}
+
+
 struct en234host_model {
     Model m;
     std::map<std::string, std::vector<int>> I;
@@ -163,6 +169,16 @@ int en234host_evaluate_loads(en234host_model_t w, double time, double dtime, con
         if (fixed_correction) fixed_correction[i] = L.fixed_correction[i];
     }
     return 0;
+}
+
+int en234host_check_stiffness(en234host_model_t w, int element_flag, const double* dof_total, const double* dof_increment,
+                              const char* log_path, double* err, int* n_unsymmetric, int* n_numerical_unsymmetric) {
+    FILE* log = log_path ? std::fopen(log_path, "w") : nullptr;
+    std::string e;
+    const int rc = check_stiffness(w->m, element_flag, dof_total, dof_increment, log, err, n_unsymmetric, n_numerical_unsymmetric, e);
+    if (log) std::fclose(log);
+    if (rc) g_err = e;
+    return rc;
 }
 
 int en234host_gpu_create(en234host_model_t w, int device, en234gpu_handle* h) {

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "../../../include/en234host.h"
@@ -31,6 +32,16 @@ int main(int argc, char** argv) {
     en234gpu_handle h;
     if (en234host_gpu_create(m, device, &h)) { std::fprintf(stderr, "device error: %s\n", en234host_last_error()); return 1; }
     if (en234gpu_set_operator_mode(h, method)) { std::fprintf(stderr, "%s\n", en234gpu_last_error()); return 1; }
+    en234host_model_int(m, "checkstiffness_flag", &p, &n);
+    if (p[0] != 0) {                                    // CHECK STIFFNESS key: main.f90:136, before the static step
+        double err = 0;
+        int nu = 0, nnu = 0;
+        if (en234host_check_stiffness(m, p[0], nullptr, nullptr, log ? (std::string(log) + ".checkstiffness").c_str() : nullptr, &err, &nu, &nnu))
+            std::fprintf(stderr, "check stiffness: %s\n", en234host_last_error());
+        else
+            std::printf(" STIFFNESS CHECK element %d: normalized difference %.3e (%s), unsymmetric entries %d / %d\n", p[0], err,
+                        err > 1e-6 ? "NOT consistent" : "consistent with residual", nu, nnu);
+    }
     std::vector<double> u(3 * (size_t)nn), rf(3 * (size_t)nn), newton(8 * 4096);
     std::vector<int> cg(4096);
     long long info[8] = {0};

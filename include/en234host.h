@@ -80,6 +80,14 @@ int en234host_run_static_part(en234host_model_t m, en234host_part_t p, en234gpu_
                               double* dof_total_local, double* rforce_local, double* newton, int max_rows,
                               int* cg_iterations, int max_cg_rows, long long* info, const char* log_path);
 
+/* check_stiffness (src/checkstiffness.f90): the reference's self-test of an element routine, run through the device twins
+ * below — coded stiffness against the numerical derivative of the residual (h = 1e-7), err = sum (K_num - K)^2 / sum K^2
+ * (consistent when <= 1e-6), plus the counts of entries the symmetry report flags.  element_flag: as parsed from the
+ * CHECK STIFFNESS key (model int scalar checkstiffness_flag), dof arrays may be NULL (zero), log_path receives the
+ * reference-format report (NULL = none). */
+int en234host_check_stiffness(en234host_model_t m, int element_flag, const double* dof_total, const double* dof_increment,
+                              const char* log_path, double* err, int* n_unsymmetric, int* n_numerical_unsymmetric);
+
 /* ---- the reference's element plugin entry points with their own argument lists and gfortran linkage (all arguments
  * by reference; default integer / logical = int32): user_codes/src/user_element.f90:5-49 and
  * user_codes/src/abaqus_uel_linelastic_3d.for:16-28.  A Fortran driver links these in place of the CPU routines;

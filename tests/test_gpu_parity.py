@@ -436,3 +436,28 @@ def test_edge_cases_isolated_node_zero_load_and_repeated_prescribed_dof():
     du, corr_norm, its, sfail = g.solve(np.zeros(n), 0, 1e-24, 5000)
     assert sfail == 0 and its == 0 and corr_norm == 0.0 and np.all(du == 0.0)
     g.close()
+
+
+def test_check_stiffness_through_the_device_twins(tmp_path):
+    """The reference's own element self-test (src/checkstiffness.f90, CHECK STIFFNESS key) run by the host driver on the
+    device twins of the element routines: coded stiffness vs numerical derivative of the residual, criterion 1e-6."""
+    rng = np.random.default_rng(17)
+    for element, props in (("1001", None), ("U1", None), ("1002", [1.0, 200.0]), ("U2", [1.0, 200.0])):
+        kw = dict(jitter=0.2, element=element)
+        if props:
+            kw["props"] = props
+        m = Model.from_text(synthetic_block_input(2, **kw))
+        flag = int(m.arrays()["element_flag"][0])
+        ut, du = 2e-2 * rng.standard_normal(3 * m.n_nodes), 5e-3 * rng.standard_normal(3 * m.n_nodes)
+        log = str(tmp_path / ("check_%s.log" % element))
+        err, nu, nnu = m.check_stiffness(flag, ut, du, log_path=log)
+        assert err < 1e-6 and nu == 0, (element, err, nu)
+        text = open(log).read()
+        assert "STIFFNESS CHECK" in text and "Stiffness matrix is consistent with residual" in text and text.count("Column") == 24
+        # same figure as the oracle's restatement of the routine on the same element and state
+        a = m.arrays()
+        conn = a["connectivity"][:8] - 1
+        dofs = (3 * conn[:, None] + np.arange(3)).ravel()
+        eo, _ = ob.check_stiffness(flag if flag < 99999 else 100000 + (flag - 100000), a["coords"].reshape(-1, 3)[conn].ravel(),
+                                   du[dofs], ut[dofs], props or [100.0, 0.3])
+        assert abs(err - eo) <= 0.05 * max(err, eo) + 1e-16, (element, err, eo)

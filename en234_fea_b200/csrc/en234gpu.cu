@@ -90,6 +90,10 @@ struct en234gpu_ctx {
     bool any_c3d8 = false;       // built-in C3D8 continuum elements (all elements of the mesh)
     DevBuf<double> sv0, sv1;     // initial / updated element state variables
     DevBuf<double> bi_z, bi_t, bi_xt, bi_b;   // BiCGSTAB work vectors
+    DevBuf<BiScalars> bi_S;                   // device-resident BiCGSTAB recurrence scalars
+    BiScalars* h_bi_S = nullptr;              // pinned mirror
+    cudaGraphExec_t bi_graph = nullptr;       // BI_CHUNK iterations
+    long long bi_graph_launches = 0;
     // host copies needed for inspection
     std::vector<int> h_browptr, h_bcol;
     // multi-GPU
@@ -351,6 +355,8 @@ int en234gpu_destroy(en234gpu_handle c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& g : c->graph) if (g) cudaGraphExecDestroy(g);
+    if (c->bi_graph) cudaGraphExecDestroy(c->bi_graph);
+    if (c->h_bi_S) cudaFreeHost(c->h_bi_S);
     comm_destroy(c->comm);
     mf_release(c->mf);
     if (c->hS) cudaFreeHost(c->hS);
@@ -366,6 +372,7 @@ int en234gpu_set_stream(en234gpu_handle c, void* s) {
     CK(cudaStreamSynchronize(c->stream));
     c->stream = s ? (cudaStream_t)s : c->own_stream;
     for (auto& g : c->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    if (c->bi_graph) { cudaGraphExecDestroy(c->bi_graph); c->bi_graph = nullptr; }
     return 0;
 }
 
@@ -724,55 +731,52 @@ static int build_graph(en234gpu_ctx* c, int method) {
 }
 
 // ---- BiCGSTAB (unsymmetric stiffness) ---------------------------------------------------------------------
-// One BiCGSTAB run for A d = b from d = 0 (recurrence residual driven to (r.r)/(b.b) <= tol); returns iterations, or -1
-// on breakdown / iteration cap, -2 on a CUDA error.
-static int bicgstab_run(en234gpu_ctx* c, const double* b, double* x, double tol, int maxit) {
+constexpr int BI_CHUNK = 8;     // BiCGSTAB iterations per CUDA-graph launch
+
+static void bicg_enqueue_iteration(en234gpu_ctx* c) {
     const int n = c->ndof, gv = c->grid_vec, nb = (n + 255) / 256;
-    double *r = c->r.p, *rhat = c->tmpvec.p, *p = c->p.p, *v = c->Ap.p, *y = c->tmpvec2.p, *z = c->bi_z.p, *t = c->bi_t.p;
-    double* two = &c->S.p->rz[0];                         // two reduced scalars, read back through the pinned mirror
-    auto read2 = [&](double& a, double& bb) -> int {
-        if (read_scalars(c)) return 1;
-        a = c->hS->rz[0]; bb = c->hS->rz[1];
-        return 0;
-    };
+    double *x = c->sol.p, *r = c->r.p, *rhat = c->tmpvec.p, *p = c->p.p, *v = c->Ap.p, *y = c->tmpvec2.p, *z = c->bi_z.p, *t = c->bi_t.p;
+    BiScalars* S = c->bi_S.p;
     int np = 0;
-    k_bi_init<<<gv, VEC_THREADS, 0, c->stream>>>(n, b, x, r, rhat, p, v, c->part2.p);
-    k_bi_reduce2<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part2.p, gv, two);
-    c->st.kernel_launches += 2;
-    double bb = 0, dummy = 0;
-    if (read2(bb, dummy)) return -2;
-    if (!(bb > 0.0)) return bb == 0.0 ? 0 : -1;
-    double rho = bb, rho_old = 1.0, alpha = 1.0, omega = 1.0, rr = bb;
-    int it = 0;
-    while (rr / bb > tol) {
-        if (it >= maxit) return -1;
-        ++it;
-        const double beta = (rho / rho_old) * (alpha / omega);
-        k_bi_p<<<nb, 256, 0, c->stream>>>(n, it == 1 ? 0.0 : beta, omega, r, v, c->minv.p, p, y);
-        launch_spmv_rows(c, y, v, 0, c->N, 0, 0, &np);
-        k_bi_dot2<<<gv, VEC_THREADS, 0, c->stream>>>(n, rhat, v, rhat, v, c->part2.p, c->part3.p);
-        k_bi_reduce2<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, two);
-        double rv = 0;
-        if (read2(rv, dummy)) return -2;
-        if (rv == 0.0 || rv != rv) return -1;
-        alpha = rho / rv;
-        k_bi_s<<<nb, 256, 0, c->stream>>>(n, alpha, v, c->minv.p, r, z);
-        launch_spmv_rows(c, z, t, 0, c->N, 0, 0, &np);
-        k_bi_dot2<<<gv, VEC_THREADS, 0, c->stream>>>(n, t, r, t, t, c->part2.p, c->part3.p);
-        k_bi_reduce2<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, two);
-        double ts = 0, tt = 0;
-        if (read2(ts, tt)) return -2;
-        if (tt != tt) return -1;
-        omega = tt > 0.0 ? ts / tt : 0.0;
-        k_bi_x<<<gv, VEC_THREADS, 0, c->stream>>>(n, alpha, omega, y, z, t, rhat, x, r, c->part2.p, c->part3.p);
-        k_bi_reduce2<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, two);
-        c->st.kernel_launches += 10;
-        rho_old = rho;
-        if (read2(rr, rho)) return -2;
-        if (rr != rr) return -1;
-        if (rr / bb > tol && (omega == 0.0 || rho == 0.0)) return -1;             // breakdown
+    k_bi_p<<<nb, 256, 0, c->stream>>>(n, S, r, v, c->minv.p, p, y);
+    launch_spmv_rows(c, y, v, 0, c->N, 0, 0, &np);
+    k_bi_dot2<<<gv, VEC_THREADS, 0, c->stream>>>(n, S, rhat, v, rhat, v, c->part2.p, c->part3.p);
+    k_bi_alpha<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, gv, S);
+    k_bi_s<<<nb, 256, 0, c->stream>>>(n, S, v, c->minv.p, r, z);
+    launch_spmv_rows(c, z, t, 0, c->N, 0, 0, &np);
+    k_bi_dot2<<<gv, VEC_THREADS, 0, c->stream>>>(n, S, t, r, t, t, c->part2.p, c->part3.p);
+    k_bi_omega<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, S);
+    k_bi_x<<<gv, VEC_THREADS, 0, c->stream>>>(n, S, y, z, t, rhat, x, r, c->part2.p, c->part3.p);
+    k_bi_finish<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, S);
+    c->st.kernel_launches += 8;
+}
+
+// One BiCGSTAB run for A d = b from d = 0 (recurrence residual driven to (r.r)/(b.b) <= tol), result in c->sol; returns
+// the iteration count, -1 on breakdown / iteration cap, -2 on a CUDA error
+static int bicgstab_run(en234gpu_ctx* c, const double* b, double tol, int maxit) {
+    const int n = c->ndof, gv = c->grid_vec;
+    if (!c->bi_graph) {
+        cudaGraph_t g = nullptr;
+        const long long before = c->st.kernel_launches;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return -2;
+        for (int it = 0; it < BI_CHUNK; ++it) bicg_enqueue_iteration(c);
+        if (cudaStreamEndCapture(c->stream, &g) != cudaSuccess) return -2;
+        c->bi_graph_launches = c->st.kernel_launches - before;
+        c->st.kernel_launches = before;
+        if (cudaGraphInstantiate(&c->bi_graph, g, 0) != cudaSuccess) return -2;
+        cudaGraphDestroy(g);
     }
-    return it;
+    k_bi_init<<<gv, VEC_THREADS, 0, c->stream>>>(n, b, c->sol.p, c->r.p, c->tmpvec.p, c->p.p, c->Ap.p, c->part2.p);
+    k_bi_init_finish<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, gv, c->bi_S.p, tol, maxit);
+    c->st.kernel_launches += 2;
+    for (;;) {
+        if (cudaMemcpyAsync(c->h_bi_S, c->bi_S.p, sizeof(BiScalars), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -2;
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -2;
+        if (c->h_bi_S->stop) break;
+        if (cudaGraphLaunch(c->bi_graph, c->stream) != cudaSuccess) return -2;
+        c->st.kernel_launches += c->bi_graph_launches;
+    }
+    return c->h_bi_S->fail ? -1 : c->h_bi_S->iter;
 }
 
 // A x = rhs to a TRUE residual (b - A x).(b - A x)/(b.b) <= tol: BiCGSTAB runs on the current true residual, the
@@ -783,23 +787,25 @@ static int bicgstab_solve(en234gpu_ctx* c, double tol, int maxit, double* correc
     if (c->comm.active) return set_err("BiCGSTAB is a single-GPU solver");
     if (phase_begin(c)) return 1;
     const int n = c->ndof, gv = c->grid_vec, nb = (n + 255) / 256;
-    if (c->bi_z.n < (size_t)n) { CK(c->bi_z.alloc(n)); CK(c->bi_t.alloc(n)); CK(c->bi_xt.alloc(n)); CK(c->bi_b.alloc(n)); }
+    if (c->bi_z.n < (size_t)n) {
+        CK(c->bi_z.alloc(n)); CK(c->bi_t.alloc(n)); CK(c->bi_xt.alloc(n)); CK(c->bi_b.alloc(n)); CK(c->bi_S.alloc(1));
+        CK(cudaMallocHost((void**)&c->h_bi_S, sizeof(BiScalars)));
+    }
     const double tol_run = std::max(tol, 1e-24);
     int total = 0, np = 0;
     *fail = 0;
     double bb = 0.0, rr_prev = 0.0;
     for (int pass = 0; pass < 6; ++pass) {
         const double* b = pass == 0 ? c->rhs.p : c->bi_b.p;
-        const int it = bicgstab_run(c, b, c->sol.p, pass == 0 ? tol_run : 1e-12, maxit - total);
+        const int it = bicgstab_run(c, b, pass == 0 ? tol_run : 1e-12, std::max(1, maxit - total));
         if (it == -2) return set_err("BiCGSTAB: CUDA error");
         if (it < 0) { *fail = 1; break; }
         total += it;
         k_bi_accumulate<<<nb, 256, 0, c->stream>>>(n, c->sol.p, c->bi_xt.p, pass == 0);
         launch_spmv_rows(c, c->bi_xt.p, c->bi_t.p, 0, c->N, 0, 0, &np);
-        k_bi_residual<<<gv, VEC_THREADS, 0, c->stream>>>(n, c->rhs.p, c->bi_t.p, c->bi_b.p, c->part2.p);
-        k_bi_dot2<<<gv, VEC_THREADS, 0, c->stream>>>(n, c->rhs.p, c->rhs.p, c->rhs.p, c->rhs.p, c->part3.p, c->part.p);
+        k_bi_residual<<<gv, VEC_THREADS, 0, c->stream>>>(n, c->rhs.p, c->bi_t.p, c->bi_b.p, c->part2.p, c->part3.p);
         k_bi_reduce2<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, &c->S.p->rz[0]);
-        c->st.kernel_launches += 5;
+        c->st.kernel_launches += 4;
         if (read_scalars(c)) return 1;
         const double rr = c->hS->rz[0];
         bb = c->hS->rz[1];

@@ -1,4 +1,10 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py 2>&1 | grep "mgpu_check" | tail -5
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 3 > gpurun_out/bench_r1f_n8.json 2> gpurun_out/bench_r1f_n8.err; tail -c 200 gpurun_out/bench_r1f_n8.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 8 --steps 2 --workload c5 --jitter 0 > gpurun_out/bench_r1f_c5_uniform_n8.json 2> gpurun_out/bench_r1f_c5u_n8.err; tail -c 200 gpurun_out/bench_r1f_c5_uniform_n8.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus 8 --steps 1 --workload c5 > gpurun_out/bench_r1f_c5_general_n8.json 2> gpurun_out/bench_r1f_c5g_n8.err; tail -c 200 gpurun_out/bench_r1f_c5_general_n8.json
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python - <<'P'
+import gzip, time, sys
+sys.path.insert(0, '.')
+from en234_fea_b200 import GpuSystem, Model
+m = Model.from_text(gzip.open('tests/golden/holeplate_3d_umat.in.gz','rb').read().decode())
+g = GpuSystem(m)
+t = time.time(); res = g.run_static(method=0); dt = time.time() - t
+print("holeplate C3D8 run: %.2f s, BiCGSTAB iterations per solve %s, phases ms %s" % (dt, res["cg_iterations"].tolist(), (g.stats().assemble_ms, g.stats().bc_ms, g.stats().solve_ms)))
+P

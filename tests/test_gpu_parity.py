@@ -461,3 +461,22 @@ def test_check_stiffness_through_the_device_twins(tmp_path):
         eo, _ = ob.check_stiffness(flag if flag < 99999 else 100000 + (flag - 100000), a["coords"].reshape(-1, 3)[conn].ravel(),
                                    du[dofs], ut[dofs], props or [100.0, 0.3])
         assert abs(err - eo) <= 0.05 * max(err, eo) + 1e-16, (element, err, eo)
+
+
+def test_c3d8_umat_two_element_reference_input():
+    """input_files/Abaqus_umat_linear_elastic_3d.in (two C3D8 + elastic UMAT elements, uniaxial tension by a NORMAL
+    distributed load ramped over 3 steps, NONLINEAR 1e-9 / 15, UNSYMMETRIC): device path against the oracle's skyline-LDU
+    run, and against the small-strain analytic values it must approach (sigma = 6, E = 1e4, nu = 0.3)."""
+    m = golden_model("linear_elastic_3d_umat.in")
+    g = GpuSystem(m)
+    res = g.run_static(method=0)
+    ref = ob.OracleModel(m.arrays()).run_static()
+    assert res["n_steps"] == ref["n_steps"] == 3 and res["n_cutbacks"] == ref["n_cutbacks"] == 0
+    assert res["newton"].shape == ref["newton"].shape
+    assert np.array_equal(res["newton"][:, [0, 1, 7]], ref["newton"][:, [0, 1, 7]])
+    big = ref["newton"][:, 5] > 1e-7
+    assert np.allclose(res["newton"][big][:, 2:6], ref["newton"][big][:, 2:6], rtol=1e-6)
+    assert relmax(res["dof_total"], ref["dof_total"]) < 1e-9
+    u = res["dof_total"].reshape(-1, 3)
+    assert abs(u[8, 0] - 2 * 6e-4) < 2e-6 and abs(u[6, 1] + 1.8e-4) < 1e-6 and abs(u[6, 2] + 1.8e-4) < 1e-6
+    g.close()

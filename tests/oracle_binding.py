@@ -90,13 +90,15 @@ class OracleModel:
         newton, cg = np.zeros((4096, 8)), np.zeros(4096, np.int32)
         info = (C.c_longlong * 10)()
         lu = np.zeros((256, 3))
-        rc = L.or_run_static(self.h, _d(u), _d(rf), None, _d(newton), C.c_int(4096), _i(cg), C.c_int(4096), info, _d(lu),
-                             C.c_int(256))
+        nsv = int(np.sum(self.arrays["element_n_states"])) if "element_n_states" in self.arrays else 0
+        sv = np.zeros(max(nsv, 1))                       # element state variables, zero initial state in, final state out
+        rc = L.or_run_static(self.h, _d(u), _d(rf), _d(sv) if nsv else None, _d(newton), C.c_int(4096), _i(cg), C.c_int(4096),
+                             info, _d(lu), C.c_int(256))
         if rc:
             raise RuntimeError("oracle static step failed rc=%d" % rc)
         return {"dof_total": u, "rforce": rf, "newton": newton[:info[2]].copy(), "cg_iterations": cg[:info[3]].copy(),
                 "n_steps": int(info[0]), "n_cutbacks": int(info[1]),
-                "profile": [int(info[k]) for k in range(4, 9)], "lu": lu[:info[9]].copy()}
+                "profile": [int(info[k]) for k in range(4, 9)], "lu": lu[:info[9]].copy(), "state_variables": sv[:nsv].copy()}
 
 
 class OracleSystem:

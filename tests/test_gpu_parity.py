@@ -480,3 +480,46 @@ def test_c3d8_umat_two_element_reference_input():
     u = res["dof_total"].reshape(-1, 3)
     assert abs(u[8, 0] - 2 * 6e-4) < 2e-6 and abs(u[6, 1] + 1.8e-4) < 1e-6 and abs(u[6, 2] + 1.8e-4) < 1e-6
     g.close()
+
+
+def test_c3d8_stretch_then_rigid_rotation_keeps_the_stress_state():
+    """The scenario of input_files/Abaqus_umat_stretch_rotate.in (a two-element C3D8 bar stretched 1 % and then rotated
+    rigidly by 90 degrees about axis 3 in 10 steps) with the end-face motion given as HISTORY tables instead of the
+    reference's SUBROUTINE-type BCs: the Hughes-Winget rotation of the stored stress (continuum_elements.f90:591-640)
+    must carry the axial stress from the 1-axis to the 2-axis.  Device path against the oracle, state variables included."""
+    X = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1],
+                  [2, 0, 0], [2, 1, 0], [2, 0, 1], [2, 1, 1]], float)
+    ends = [1, 4, 5, 8, 9, 10, 12, 11]
+    steps = 11
+    lam = 1.01
+    def position(n, t):                                   # t = 1: stretched; t = 2..11: rotated by 9 degrees per step
+        x = X[n - 1] * [lam if t >= 1 else 1.0 + (lam - 1.0) * t, 1.0, 1.0]
+        th = np.radians(9.0 * max(0.0, t - 1.0))
+        c, s = np.cos(th), np.sin(th)
+        return np.array([c * x[0] - s * x[1], s * x[0] + c * x[1], x[2]])
+    t = ["MESH", " NODES", "  PARAMETERS, 3, 3, 1", "  DISPLACEMENT DOF, 1, 2, 3", "  COORDINATES"]
+    t += ["   %d, %.17g, %.17g, %.17g" % (i + 1, *X[i]) for i in range(12)]
+    t += ["  END COORDINATES", " END NODES", " MATERIAL, mat", "  STATE VARIABLES, 0", "  PROPERTIES", "   10000.d0, 0.3d0",
+          "  END PROPERTIES", " END MATERIAL", " ELEMENTS, INTERNAL", "  TYPE, C3D8", "  PROPERTIES, mat", "  CONNECTIVITY, zone1",
+          "   1, 1, 2, 3, 4, 5, 6, 7, 8", "   2, 2, 9, 10, 3, 6, 11, 12, 7", "  END CONNECTIVITY", " END ELEMENTS", "END MESH",
+          "BOUNDARY CONDITIONS"]
+    for n in ends:
+        for d in range(3):
+            t += [" HISTORY, h%d_%d" % (n, d + 1)] + ["  %.17g, %.17g" % (k, position(n, k)[d] - X[n - 1][d]) for k in range(steps + 1)] + [" END HISTORY"]
+    t += [" DEGREES OF FREEDOM"] + ["  %d, %d, HISTORY, h%d_%d" % (n, d + 1, n, d + 1) for n in ends for d in range(3)] + [" END DEGREES OF FREEDOM",
+          "END BOUNDARY CONDITIONS", "STATIC STEP", " INITIAL TIME STEP, 1.d0", " MAX TIME STEP, 1.d0", " MIN TIME STEP, 0.001d0",
+          " MAX NUMBER OF STEPS, %d" % steps, " STOP TIME, %d.d0" % steps, " SOLVER, DIRECT, NONLINEAR, 1.d-08, 15, UNSYMMETRIC",
+          "END STATIC STEP", "STOP", ""]
+    m = Model.from_text("\n".join(t))
+    g = GpuSystem(m)
+    res = g.run_static(method=0)
+    ref = ob.OracleModel(m.arrays()).run_static()
+    assert res["n_steps"] == ref["n_steps"] == steps and res["n_cutbacks"] == ref["n_cutbacks"] == 0
+    assert res["newton"].shape == ref["newton"].shape
+    assert relmax(res["dof_total"], ref["dof_total"]) < 1e-9
+    sv = g.state_variables(updated=False).reshape(2, 8, 15)
+    svo = ref["state_variables"].reshape(2, 8, 15)
+    assert np.abs(sv - svo).max() <= 1e-8 * np.abs(svo).max()
+    # after the 90 degree rotation the bar axis is the 2-axis: s22 carries the axial stress (~ E x 1 %), larger than s11
+    assert np.all(sv[..., 1] > 80.0) and np.all(sv[..., 1] > 2.0 * np.abs(sv[..., 0]))
+    g.close()

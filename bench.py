@@ -382,6 +382,7 @@ def main():
     it_ms = st.solve_ms / max(st.last_cg_iterations, 1)
     b_iter = (alg + 104 * n) if args.method == 0 else (alg + 104 * n)
     roof = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "frac_of_nominal_8000": ach / 8000.0,
             "peak_source": peak_src, "traffic": measured_traffic(kern, dims[0] * dims[1] * dims[2] // world),
             "ms_per_launch": ms_op, "algorithmic_bytes_per_launch": alg,
             "cg_iteration": {"ms": it_ms, "algorithmic_bytes": b_iter, "achieved": b_iter / (it_ms * 1e-3) / 1e9,

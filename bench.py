@@ -119,7 +119,7 @@ def run_newton(args):
         raise SystemExit("bench.py --workload c4 is a 1-GPU measurement")
     dims, wname = workload(1, "c4")
     model = Model.from_text(synthetic_block_input(*dims, jitter=args.jitter, element="U2", props=[1.0, 200.0], load="stretch",
-                                                  steps=4, nonlinear=(1e-5, 15), cg_tolerance=CG_TOL, cg_maxit=CG_MAXIT))
+                                                  steps=4, nonlinear=(1e-5, 15), cg_tolerance=CG_TOL, cg_maxit=10 * CG_MAXIT))
     gpu = GpuSystem(model, device=0)
     n = gpu.ndof
     sampler = ClockSampler(0)
@@ -150,6 +150,7 @@ def run_newton(args):
             "config": {"workload": wname, "n_dof": n, "elements": dims[0] * dims[1] * dims[2], "jitter": args.jitter,
                        "increments": res["n_steps"], "cutbacks": res["n_cutbacks"], "newton_iterations": int(res["newton"].shape[0]),
                        "linear_solves": n_solves, "cg_iterations": its, "cg_rule": "(r.r)/(b.b) < 1e-20",
+                       "cg_iterations_per_solve": [int(x) for x in res["cg_iterations"]],
                        "newton_ratios": [float("%.4e" % r) for r in res["newton"][:, 5]],
                        "timing": "host wall clock around the whole analysis (device-synchronised)",
                        "l2": "matrix stream per PCG iteration (%.0f MB) exceeds the 126 MB L2" % ((alg_it - 104 * n) / 1e6)},

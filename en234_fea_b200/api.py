@@ -104,13 +104,13 @@ def host_lib():
 INT_ARRAYS = ["connectivity", "element_flag", "element_prop_index", "element_n_props", "element_n_states",
               "element_material", "material_prop_index", "material_n_props",
               "history_ptr", "nodeset_ptr", "nodeset_nodes", "elementset_ptr", "elementset_elements",
-              "pdof_flag", "pdof_dof", "pdof_node", "pdof_nodeset", "pdof_history", "pdof_rate",
+              "pdof_flag", "pdof_dof", "pdof_node", "pdof_nodeset", "pdof_history", "pdof_rate", "pdof_subparam", "subparam_ptr",
               "pforce_flag", "pforce_dof", "pforce_node", "pforce_nodeset", "pforce_history",
               "dload_flag", "dload_elset", "dload_face", "dload_history", "dload_val_ptr"]
 INT_SCALARS = ["n_nodes", "n_elements", "max_no_steps", "solvertype", "nonlinear", "max_newton_iterations",
                "unsymmetric", "abaqusformat", "max_cg_iterations", "checkstiffness_flag"]
 DBL_ARRAYS = ["coords", "element_properties", "material_properties", "history_time", "history_value", "pdof_value", "pforce_value",
-              "dload_values"]
+              "dload_values", "subparam_values"]
 DBL_SCALARS = ["timestep_initial", "timestep_min", "timestep_max", "max_total_time", "newtonraphson_tolerance",
                "cg_tolerance"]
 

@@ -75,6 +75,14 @@ static void flatten(en234host_model& w) {
     };
     dofs(m.prescribed_dofs, "pdof", true);
     dofs(m.prescribed_forces, "pforce", false);
+    I["pdof_subparam"];                                               // SUBROUTINE PARAMETERS block per prescribed DOF (0 = none)
+    for (auto& p : m.prescribed_dofs) I["pdof_subparam"].push_back(p.subroutine_parameter_number);
+    I["subparam_ptr"] = {0};
+    D["subparam_values"];
+    for (auto& sp : m.subroutine_parameters) {
+        D["subparam_values"].insert(D["subparam_values"].end(), sp.values.begin(), sp.values.end());
+        I["subparam_ptr"].push_back((int)D["subparam_values"].size());
+    }
     for (const char* k : {"dload_flag", "dload_elset", "dload_face", "dload_history"}) I[k];
     I["dload_val_ptr"] = {0};
     D["dload_values"];

@@ -65,6 +65,40 @@ void uel_face_load(const double* coords24, int face, double mag, double* R24) {
     }
 }
 
+// user_prescribeddof (user_codes/src/user_prescribeddof.f90:1-108) as shipped: uniaxial stretch of a bar over the first
+// n_extension_steps steps, then a rigid rotation in n_rotation_steps steps, driven by current_step_number.
+// xref / utot: reference coordinates and dof_total of the node (3 each).
+static void user_prescribeddof(const Model& m, int node_number, int idof, const std::vector<double>& par, const double* xref,
+                               const double* utot, double& dofvalue, bool& ignoredof) {
+    if (par.size() < 11) { ignoredof = true; return; }
+    const int tensile_dir = (int)par[0], n_ext = (int)par[2], rot_axis = (int)par[4], n_rot = (int)par[5];
+    const int n_base = (int)par[6], n_end = (int)par[7], base_fixed = (int)par[8], base_con = (int)par[9], base_con_dir = (int)par[10];
+    const double extension = par[1], rotation_angle = par[3];
+    const int step = m.current_step_number;
+    ignoredof = true;
+    if (step <= n_ext) {
+        for (int i = 11; i < 11 + n_base && i < (int)par.size(); ++i)
+            if (node_number == (int)par[i] && idof == tensile_dir) { dofvalue = 0.0; ignoredof = false; }
+        for (int i = 11 + n_base; i < 11 + n_base + n_end && i < (int)par.size(); ++i)
+            if (node_number == (int)par[i] && idof == tensile_dir) { dofvalue = extension * step / n_ext; ignoredof = false; }
+        if (node_number == base_fixed) { dofvalue = 0.0; ignoredof = false; }
+        if (node_number == base_con && idof == base_con_dir) { dofvalue = 0.0; ignoredof = false; }
+    } else if (step <= n_ext + n_rot) {
+        const double PI_D = 3.141592653589793238462643383279502884197;
+        double cur[3], axis[3] = {0, 0, 0}, cr[3];
+        for (int i = 0; i < 3; ++i) cur[i] = xref[i] + utot[i];
+        const double angle = PI_D * rotation_angle / (n_rot * 180.0);
+        axis[rot_axis - 1] = 1.0;
+        cr[0] = axis[1] * cur[2] - axis[2] * cur[1];                  // cross_product, Element_Utilities.f90:38-52
+        cr[1] = cur[0] * axis[2] - axis[0] * cur[2];
+        cr[2] = axis[0] * cur[1] - axis[1] * cur[0];
+        const double ad = axis[0] * cur[0] + axis[1] * cur[1] + axis[2] * cur[2];
+        const int i = idof - 1;
+        dofvalue = std::cos(angle) * cur[i] + (1.0 - std::cos(angle)) * ad * axis[i] + std::sin(angle) * cr[i] - xref[i];
+        ignoredof = false;
+    } else { dofvalue = 0.0; ignoredof = false; }
+}
+
 void evaluate_loads(const Model& m, double time, double dtime, const double* dof_total, const double* dof_increment,
                     StepLoads& out, const std::vector<int>* g2l, size_t n_local) {
     // g2l (partitioned runs): global DOF -> rank-local DOF or -1; all outputs and the DOF arrays are then rank-local
@@ -143,11 +177,20 @@ void evaluate_loads(const Model& m, double time, double dtime, const double* dof
     }
 
     for (const auto& p : m.prescribed_dofs) {
-        double v = p.flag == 1 ? p.value : interpolate_history_table(m.histories[p.history_number - 1], time + dtime);
+        double v = p.flag == 1 ? p.value
+                 : p.flag == 2 ? interpolate_history_table(m.histories[p.history_number - 1], time + dtime) : 0.0;
         auto one = [&](int n) {
             const long ld = loc(3 * (size_t)(n - 1) + p.dof - 1);
             if (ld < 0) return;
             const int d = (int)ld;
+            if (p.flag == 3) {                                        // solver_direct.f90:703-708, :723-728
+                double ut3[3] = {0, 0, 0};
+                for (int c = 0; c < 3; ++c) { const long lc = loc(3 * (size_t)(n - 1) + c); if (lc >= 0 && dof_total) ut3[c] = dof_total[lc]; }
+                bool ignoredof = false;
+                user_prescribeddof(m, n, p.dof, m.subroutine_parameters[p.subroutine_parameter_number - 1].values,
+                                   &m.coords[3 * (size_t)(n - 1)], ut3, v, ignoredof);
+                if (ignoredof) return;
+            }
             double target = v;
             // RATE: the value prescribes the increment (solver_direct.f90:706-708); expressed as a target for
             // dof_total + dof_increment so the device forms one kind of correction

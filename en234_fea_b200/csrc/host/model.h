@@ -11,7 +11,8 @@ struct History { std::string name; std::vector<double> t, v; };
 struct NamedSet { std::string name; std::vector<int> items; };   // 1-based node / element numbers
 
 struct PrescribedDof {        // prescribeddof_list / prescribedforce_list (Boundaryconditions.f90:34-55)
-    int flag = 1;             // 1 VALUE, 2 HISTORY, 3 SUBROUTINE (unsupported)
+    int flag = 1;             // 1 VALUE, 2 HISTORY, 3 SUBROUTINE (user_prescribeddof)
+    int subroutine_parameter_number = 0;   // 1-based SUBROUTINE PARAMETERS block (flag 3)
     int dof = 1;              // 1-based
     int node_number = 0;      // single node, or
     int node_set = 0;         // 1-based node set (0 = none)
@@ -19,6 +20,8 @@ struct PrescribedDof {        // prescribeddof_list / prescribedforce_list (Boun
     double value = 0.0;
     int rate_flag = 0;
 };
+
+struct SubroutineParameters { std::string name; std::vector<double> values; };   // SUBROUTINE PARAMETERS block
 
 struct DistributedLoad {      // distributedload_list (Boundaryconditions.f90:57-66)
     int flag = 0;             // native: 1 VALUE, 2 HISTORY, 3 NORMAL, 4 SUBROUTINE; ABAQUS UEL: face number n of "Un"
@@ -56,6 +59,10 @@ struct Model {
     std::vector<History> histories;
     std::vector<NamedSet> nodesets, elementsets;
     std::vector<PrescribedDof> prescribed_dofs, prescribed_forces;
+    std::vector<SubroutineParameters> subroutine_parameters;
+    // current_step_number of module Staticstepparameters: the reference's user hooks read it as a global
+    // (user_codes/src/user_prescribeddof.f90:7); set by compute_static_step before the loads are evaluated
+    mutable int current_step_number = 1;
     std::vector<DistributedLoad> distributed_loads;
     // static step (defaults read_input_file.f90:120-129, :1735-1751)
     bool staticstep = false;

@@ -322,8 +322,14 @@ bool parse_dof_like(Reader& r, Line& L, bool is_force, PrescribedDof& p) {
         p.flag = 2;
         p.history_number = find_name(m.histories, L.tok[3]);
         if (!p.history_number) return r.fail("unknown history name", &L);
-    } else if (kw(L.tok[2], "SUBRO")) return r.fail("SUBROUTINE-type boundary conditions are outside the supported subset", &L);
-    else return r.fail("expecting key VALUE, HISTORY, or SUBROUTINE in a dof definition", &L);
+    } else if (kw(L.tok[2], "SUBRO")) {                               // read_input_file.f90:1212-1225
+        if (is_force) return r.fail("SUBROUTINE-type nodal forces are outside the supported subset", &L);
+        p.flag = 3;
+        p.subroutine_parameter_number = 0;
+        for (size_t i = 0; i < m.subroutine_parameters.size(); ++i)
+            if (m.subroutine_parameters[i].name == L.tok[3]) p.subroutine_parameter_number = (int)i + 1;
+        if (!p.subroutine_parameter_number) return r.fail("unknown SUBROUTINE PARAMETERS name", &L);
+    } else return r.fail("expecting key VALUE, HISTORY, or SUBROUTINE in a dof definition", &L);
     p.rate_flag = (!is_force && kw(L.tok[L.n() - 1], "RATE")) ? 1 : 0;
     return true;
 }
@@ -432,8 +438,21 @@ bool parse_boundary(Reader& r) {
                 }
                 m.distributed_loads.push_back(d);
             }
-        } else if (kw(L.tok[0], "SUBROUTINEP") || kw(L.tok[0], "CONSTRA")) {
-            return r.fail("SUBROUTINE PARAMETERS / CONSTRAINTS are outside the supported subset", &L);
+        } else if (kw(L.tok[0], "SUBROUTINEP")) {                      // read_input_file.f90:1030-1065
+            if (L.n() < 2) return r.fail("SUBROUTINE PARAMETERS key was used without specifying a name for the parameters", &L);
+            SubroutineParameters sp;
+            sp.name = L.tok[1];
+            while (true) {
+                if (!r.next(L)) return r.fail("SUBROUTINE PARAMETERS not terminated");
+                if (kw(L.tok[0], "ENDSUBR")) break;
+                for (int k = 0; k < L.n(); ++k) {
+                    if (L.typ[k] == 2) return r.fail("SUBROUTINE PARAMETERS must be terminated with an END SUBROUTINE PARAMETERS", &L);
+                    sp.values.push_back(to_real(L.tok[k]));
+                }
+            }
+            m.subroutine_parameters.push_back(sp);
+        } else if (kw(L.tok[0], "CONSTRA")) {
+            return r.fail("CONSTRAINTS are outside the supported subset", &L);
         } else if (kw(L.tok[0], "ENDBOUN")) return true;
         else return r.fail("unknown key in BOUNDARY CONDITIONS block", &L);
     }

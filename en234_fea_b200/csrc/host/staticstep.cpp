@@ -114,6 +114,7 @@ int compute_static_step(const Model& m, en234gpu_handle h, const StepOptions& op
     int guard = 0;
     while (cont) {
         if (++guard > 100000) { res.error = "time stepping did not terminate"; return 2; }
+        m.current_step_number = t.current_step_number;
         evaluate_loads(m, t.TIME, t.DTIME, res.dof_total.data(), dof_increment.data(), L, g2l, n_local);
         if (!opt.use_host_api &&
             en234gpu_upload_state(h, res.dof_total.data(), dof_increment.data(), L.any_element_ext ? L.element_ext.data() : nullptr,

@@ -153,6 +153,11 @@ std::string write_input_text(const Model& m) {
         for (size_t i = 0; i < h.t.size(); ++i) o << "  " << h.t[i] << ", " << h.v[i] << "\n";
         o << " END HISTORY\n";
     }
+    for (const auto& sp : m.subroutine_parameters) {
+        o << " SUBROUTINE PARAMETERS, " << sp.name << "\n";
+        for (double v : sp.values) o << "  " << v << "\n";
+        o << " END SUBROUTINE PARAMETERS\n";
+    }
     auto put_set = [&](const char* key, const char* endkey, const NamedSet& s) {
         o << " " << key << ", " << s.name << "\n";
         for (size_t i = 0; i < s.items.size(); ++i) {
@@ -170,7 +175,9 @@ std::string write_input_text(const Model& m) {
             o << "  ";
             if (p.node_set) o << m.nodesets[p.node_set - 1].name; else o << p.node_number;
             o << ", " << p.dof << ", ";
-            if (p.flag == 1) o << "VALUE, " << p.value; else o << "HISTORY, " << m.histories[p.history_number - 1].name;
+            if (p.flag == 1) o << "VALUE, " << p.value;
+            else if (p.flag == 3) o << "SUBROUTINE, " << m.subroutine_parameters[p.subroutine_parameter_number - 1].name;
+            else o << "HISTORY, " << m.histories[p.history_number - 1].name;
             if (p.rate_flag) o << ", RATE";
             o << "\n";
         }

@@ -25,11 +25,12 @@ const char* en234host_last_error(void);
  * int arrays:  connectivity element_flag element_prop_index element_n_props element_n_states element_material
  *              material_prop_index material_n_props history_ptr nodeset_ptr
  *              nodeset_nodes elementset_ptr elementset_elements pdof_flag pdof_dof pdof_node pdof_nodeset pdof_history
- *              pdof_rate pforce_flag pforce_dof pforce_node pforce_nodeset pforce_history dload_flag dload_elset
+ *              pdof_rate pdof_subparam subparam_ptr pforce_flag pforce_dof pforce_node pforce_nodeset pforce_history dload_flag dload_elset
  *              dload_face dload_history dload_val_ptr
  * int scalars (length 1): n_nodes n_elements max_no_steps solvertype nonlinear max_newton_iterations unsymmetric
  *              abaqusformat max_cg_iterations checkstiffness_flag
  * double arrays: coords element_properties material_properties history_time history_value pdof_value pforce_value dload_values
+ *              subparam_values
  * double scalars: timestep_initial timestep_min timestep_max max_total_time newtonraphson_tolerance cg_tolerance
  * The pointers stay valid until the model is freed or modified. */
 int en234host_model_int(en234host_model_t m, const char* name, const int** p, long* n);

@@ -34,7 +34,7 @@ int or_model_set_int(void* h, const char* name, const int* p, long n) {
     VI(connectivity) VI(element_flag) VI(element_prop_index) VI(element_n_props) VI(element_n_states)
     VI(element_material) VI(material_prop_index) VI(material_n_props)
     VI(history_ptr) VI(nodeset_ptr) VI(nodeset_nodes) VI(elementset_ptr) VI(elementset_elements)
-    VI(pdof_flag) VI(pdof_dof) VI(pdof_node) VI(pdof_nodeset) VI(pdof_history) VI(pdof_rate)
+    VI(pdof_flag) VI(pdof_dof) VI(pdof_node) VI(pdof_nodeset) VI(pdof_history) VI(pdof_rate) VI(pdof_subparam) VI(subparam_ptr)
     VI(pforce_flag) VI(pforce_dof) VI(pforce_node) VI(pforce_nodeset) VI(pforce_history)
     VI(node_order) VI(dload_flag) VI(dload_elset) VI(dload_face) VI(dload_history) VI(dload_val_ptr)
     SI(n_nodes) SI(n_elements) SI(max_no_steps) SI(solvertype) SI(nonlinear) SI(max_newton_iterations)
@@ -51,7 +51,7 @@ int or_model_set_double(void* h, const char* name, const double* p, long n) {
 #define VD(f) if (k == #f) { assign(m.f, p, n); return 0; }
 #define SD(f) if (k == #f) { m.f = p[0]; return 0; }
     VD(coords) VD(element_properties) VD(material_properties) VD(history_time) VD(history_value)
-    VD(pdof_value) VD(pforce_value) VD(dload_values)
+    VD(pdof_value) VD(pforce_value) VD(dload_values) VD(subparam_values)
     SD(timestep_initial) SD(timestep_min) SD(timestep_max) SD(max_total_time) SD(newtonraphson_tolerance)
     SD(cg_tolerance)
 #undef VD

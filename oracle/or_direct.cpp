@@ -136,6 +136,40 @@ static void fixdof_direct(Skyline& s, int n, double dofvalue) {
     s.rhs[n] = dofvalue;
 }
 
+// user_prescribeddof as shipped (user_codes/src/user_prescribeddof.f90:48-103): a bar is stretched along tensile_dir over the
+// first n_extension_steps steps and then rotated rigidly about rotation_axis in n_rotation_steps steps.  Returns false when
+// the routine sets ignoredof.  Parameter list: :48-58; nodes on the base / end follow from entry 12 on.
+static bool oracle_user_prescribeddof(const Model& m, int node_number, int idof, int k, const double* dof_total, double* dofvalue) {
+    const int sp = k < (int)m.pdof_subparam.size() ? m.pdof_subparam[k] : 0;
+    if (sp < 1) return false;
+    const double* par = &m.subparam_values[m.subparam_ptr[sp - 1]];
+    const int npar = m.subparam_ptr[sp] - m.subparam_ptr[sp - 1];
+    if (npar < 11) return false;
+    const int tensile_dir = (int)par[0], n_ext = (int)par[2], axis_no = (int)par[4], n_rot = (int)par[5];
+    const int n_base = (int)par[6], n_end = (int)par[7];
+    bool ignoredof = true;
+    const int step = m.current_step_number;
+    if (step <= n_ext) {
+        for (int i = 12; i <= 12 + n_base - 1 && i <= npar; ++i)
+            if (node_number == (int)par[i - 1] && idof == tensile_dir) { *dofvalue = 0.0; ignoredof = false; }
+        for (int i = 12 + n_base; i <= 12 + n_base + n_end - 1 && i <= npar; ++i)
+            if (node_number == (int)par[i - 1] && idof == tensile_dir) { *dofvalue = par[1] * step / n_ext; ignoredof = false; }
+        if (node_number == (int)par[8]) { *dofvalue = 0.0; ignoredof = false; }
+        if (node_number == (int)par[9] && idof == (int)par[10]) { *dofvalue = 0.0; ignoredof = false; }
+    } else if (step <= n_ext + n_rot) {
+        double ref[3], cur[3], ax[3] = {0.0, 0.0, 0.0};
+        for (int i = 0; i < 3; ++i) { ref[i] = m.coords[3 * (size_t)(node_number - 1) + i]; cur[i] = ref[i] + dof_total[3 * (size_t)(node_number - 1) + i]; }
+        const double angle = 3.141592653589793238462643383279502884197 * par[3] / (n_rot * 180.0);
+        ax[axis_no - 1] = 1.0;
+        const double dot = ax[0] * cur[0] + ax[1] * cur[1] + ax[2] * cur[2];
+        const double cross[3] = {ax[1] * cur[2] - ax[2] * cur[1], cur[0] * ax[2] - ax[0] * cur[2], ax[0] * cur[1] - ax[1] * cur[0]};
+        const double newc = std::cos(angle) * cur[idof - 1] + (1.0 - std::cos(angle)) * dot * ax[idof - 1] + std::sin(angle) * cross[idof - 1];
+        *dofvalue = newc - ref[idof - 1];
+        ignoredof = false;
+    } else { *dofvalue = 0.0; ignoredof = false; }
+    return !ignoredof;
+}
+
 static double history_value(const Model& m, int h, double t) {
     int o = m.history_ptr[h - 1], nh = m.history_ptr[h] - o;
     return interpolate_history_table(&m.history_time[o], &m.history_value[o], nh, t);
@@ -204,6 +238,12 @@ static void bc_loads_and_corrections(const Model& m, const double* dof_total, co
         auto one = [&](int n) {
             int d = 3 * n + idof;
             double ucur = m.pdof_rate[k] == 0 ? dof_increment[d] + dof_total[d] : dof_increment[d];
+            if (m.pdof_flag[k] == 3) {                              // solver_direct.f90:703-708 / :723-728
+                double value = 0.0;
+                if (!oracle_user_prescribeddof(m, n + 1, idof + 1, (int)k, dof_total, &value)) return;    // ignoredof
+                fix.emplace_back(d, value - ucur);
+                return;
+            }
             fix.emplace_back(d, v - ucur);
         };
         if (m.pdof_nodeset[k] == 0) one(m.pdof_node[k] - 1);

@@ -43,6 +43,10 @@ struct Model {
     std::vector<int> elementset_ptr, elementset_elements; // 1-based element numbers
     std::vector<int> pdof_flag, pdof_dof, pdof_node, pdof_nodeset, pdof_history, pdof_rate;
     std::vector<double> pdof_value;
+    // SUBROUTINE-type prescribed DOFs (flag 3): parameter block per DOF entry (1-based, 0 = none), CSR of the blocks
+    std::vector<int> pdof_subparam, subparam_ptr;
+    std::vector<double> subparam_values;
+    mutable int current_step_number = 1;   // Staticstepparameters%current_step_number, read by user_prescribeddof
     std::vector<int> pforce_flag, pforce_dof, pforce_node, pforce_nodeset, pforce_history;
     std::vector<double> pforce_value;
     std::vector<int> dload_flag, dload_elset, dload_face, dload_history, dload_val_ptr;

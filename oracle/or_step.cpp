@@ -76,6 +76,7 @@ int compute_static_step(const Model& m, std::vector<double>& dof_total, std::vec
         compute_profile(m, order, s, &log);
         while (cont) {
             if (++guard > 100000) return 2;
+            m.current_step_number = t.current_step_number;
             updated = svars;
             int fail = assemble_direct_stiffness(m, s, dof_total.data(), dof_increment.data(), t.TIME, t.DTIME, &updated, a);
             if (fail) {
@@ -119,6 +120,7 @@ int compute_static_step(const Model& m, std::vector<double>& dof_total, std::vec
         initialize_cg_solver(m, c);
         while (cont) {
             if (++guard > 100000) return 2;
+            m.current_step_number = t.current_step_number;
             updated = svars;
             int fail = assemble_conjugate_gradient_stiffness(m, c, dof_total.data(), dof_increment.data(), t.TIME, t.DTIME, &updated, a);
             if (fail) {

@@ -3,6 +3,7 @@
   linear_elastic_3d_uel.in   re-emission (by the product's own writer, 17 significant digits, no comments) of the
   holeplate_3d_uel.in.gz     mesh/BC/step data parsed from input_files/Abaqus_uel_linear_elastic_3d.in and
                              input_files/Abaqus_uel_holeplate_3d.in — data fixtures, the GPU box has no /root/reference
+  stretch_rotate_3d_umat.in  the same for input_files/Abaqus_umat_stretch_rotate.in (SUBROUTINE-type prescribed DOFs)
   linear_elastic_3d_umat.in  the same for input_files/Abaqus_umat_linear_elastic_3d.in (two C3D8 + UMAT elements)
   holeplate_3d_umat.in.gz    the same for input_files/Abaqus_umat_holeplate_3d.in (C3D8 + UMAT, the golden-log case)
   *_oracle.npz               displacements, reaction forces and Newton history of the CPU oracle (skyline direct
@@ -64,3 +65,7 @@ print("holeplate_3d_umat.in.gz round trip ok")
 # the two-element C3D8 + UMAT input (uniaxial tension by a NORMAL distributed load, 3 steps, NONLINEAR 1e-9)
 m2 = Model.read(os.path.join(REF, "Abaqus_umat_linear_elastic_3d.in"))
 open(os.path.join(HERE, "linear_elastic_3d_umat.in"), "w").write(m2.text())
+# the same bar stretched 1 % and then rotated rigidly by 90 degrees through SUBROUTINE-type prescribed DOFs
+# (user_prescribeddof): input_files/Abaqus_umat_stretch_rotate.in
+m3 = Model.read(os.path.join(REF, "Abaqus_umat_stretch_rotate.in"))
+open(os.path.join(HERE, "stretch_rotate_3d_umat.in"), "w").write(m3.text())

@@ -523,3 +523,22 @@ def test_c3d8_stretch_then_rigid_rotation_keeps_the_stress_state():
     # after the 90 degree rotation the bar axis is the 2-axis: s22 carries the axial stress (~ E x 1 %), larger than s11
     assert np.all(sv[..., 1] > 80.0) and np.all(sv[..., 1] > 2.0 * np.abs(sv[..., 0]))
     g.close()
+
+
+def test_stretch_rotate_reference_input_with_subroutine_bcs():
+    """input_files/Abaqus_umat_stretch_rotate.in as shipped: SUBROUTINE-type prescribed DOFs (user_prescribeddof driven by
+    current_step_number) on the two-element C3D8 bar — device path against the oracle, and the objectivity result itself:
+    after the rigid 90 degree rotation the uniaxial stress sits on the 2-axis, magnitude unchanged."""
+    m = golden_model("stretch_rotate_3d_umat.in")
+    g = GpuSystem(m)
+    res = g.run_static(method=0)
+    ref = ob.OracleModel(m.arrays()).run_static()
+    assert res["n_steps"] == ref["n_steps"] == 11 and res["n_cutbacks"] == ref["n_cutbacks"] == 0
+    assert res["newton"].shape == ref["newton"].shape
+    assert np.array_equal(res["newton"][:, [0, 1, 7]], ref["newton"][:, [0, 1, 7]])
+    assert relmax(res["dof_total"], ref["dof_total"]) < 1e-9
+    sv = g.state_variables(updated=False).reshape(2, 8, 15)
+    svo = ref["state_variables"].reshape(2, 8, 15)
+    assert np.abs(sv - svo).max() <= 1e-8 * np.abs(svo).max()
+    assert np.allclose(sv[..., 1], 49.875, atol=1e-3) and np.abs(np.delete(sv[..., :6], 1, axis=-1)).max() < 1e-4
+    g.close()

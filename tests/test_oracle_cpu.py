@@ -249,6 +249,29 @@ def test_golden_umat_input_fixture_matches_model_arrays():
     assert b["unsymmetric"][0] == 1 and set(b["element_flag"].tolist()) == {10003} and b["element_n_states"][0] == 120
 
 
+def test_stretch_rotate_reference_input_on_the_oracle():
+    """input_files/Abaqus_umat_stretch_rotate.in as shipped (re-emitted fixture): SUBROUTINE-type prescribed DOFs evaluated
+    by user_prescribeddof (user_codes/src/user_prescribeddof.f90) from current_step_number — one 1 % stretch step, then a
+    rigid 90 degree rotation about axis 3 in ten steps.  Objectivity of the C3D8 stress update (Hughes-Winget rotation,
+    continuum_elements.f90:591-640): the uniaxial stress ends up on the 2-axis with its magnitude unchanged."""
+    m = Model.read(os.path.join(GOLDEN, "stretch_rotate_3d_umat.in"))
+    a = m.arrays()
+    assert a["pdof_flag"].tolist() == [3] * 6 and a["pdof_subparam"].tolist() == [1] * 6 and a["subparam_values"].size == 19
+    if HAVE_REF:
+        b = Model.read(os.path.join(REF_INPUTS, "Abaqus_umat_stretch_rotate.in")).arrays()
+        for k in b:
+            if k not in ("cg_tolerance", "max_cg_iterations", "checkstiffness_flag"):
+                assert np.array_equal(a[k], b[k]), k
+    res = ob.OracleModel(a).run_static()
+    assert res["n_steps"] == 11 and res["n_cutbacks"] == 0
+    u = res["dof_total"].reshape(-1, 3)
+    assert np.allclose(u[8], [-2.0, 2.01, 0.0], atol=1e-9)                 # node 9: (2.01, 0, 0) -> (0, 2.01, 0)
+    sv = res["state_variables"].reshape(2, 8, 15)
+    s_axial = 1.0e4 * 0.005 * (1.0 - 0.0025)                               # after step 1 (log-like strain of the rate form)
+    assert np.allclose(sv[..., 1], sv[0, 0, 1], rtol=1e-7) and abs(sv[0, 0, 1] - 49.875) < 1e-3 and abs(sv[0, 0, 1] - s_axial) < 0.1
+    assert np.abs(np.delete(sv[..., :6], 1, axis=-1)).max() < 1e-6 * sv[0, 0, 1]
+
+
 def test_parser_rules():
     # parse.f90: blanks stripped, case-insensitive prefix keywords, % comments, Fortran D exponents, 100-char lines
     txt = synthetic_block_input(2)

@@ -200,6 +200,14 @@ int en234host_gpu_create(en234host_model_t w, int device, en234gpu_handle* h) {
         if (m.element_flag[e] == EN234_FLAG_C3D8) {
             const int mi = e < (int)m.element_material.size() ? m.element_material[e] : 0;
             if (mi < 1 || mi > (int)m.materials.size()) { g_err = "C3D8 element without a MATERIAL"; return 1; }
+            // the input file does not say which UMAT the executable was linked with; the device has the linear-elastic one
+            // (user_codes/src/abaqus_umat_elastic.for: PROPS = E, nu, no state variables) and nothing else
+            if (m.materials[mi - 1].n_props != 2 || m.materials[mi - 1].n_states != 0) {
+                g_err = "material '" + m.materials[mi - 1].name + "' has " + std::to_string(m.materials[mi - 1].n_props) +
+                        " properties and " + std::to_string(m.materials[mi - 1].n_states) + " state variables: only the "
+                        "linear-elastic UMAT (E, nu; no state variables) is available on the device";
+                return 1;
+            }
             pidx[e] = (int)m.element_properties.size() + m.materials[mi - 1].prop_index;
         }
     int rc = en234gpu_create(h, device, m.n_nodes, m.n_elements, m.coords.data(), m.connectivity.data(),

@@ -384,6 +384,18 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(api.host_lib(), s), s
 
 
+@pytest.mark.skipif(not HAVE_REF, reason="reference input files not present")
+def test_other_umat_inputs_are_rejected_not_misread():
+    """C3D8 inputs written for other UMATs (hyperelastic, porous elastic, viscoplastic: 4-7 properties, extra state
+    variables) parse, but the device path refuses them instead of running them with the elastic UMAT."""
+    import ctypes as C
+    for name in ("Abaqus_umat_hyperelastic2.in", "Abaqus_umat_porous_elastic.in", "Abaqus_umat_viscoplastic.in"):
+        m = Model.read(os.path.join(REF_INPUTS, name))
+        h = C.c_void_p()
+        assert api.host_lib().en234host_gpu_create(m.h, 0, C.byref(h)) != 0
+        assert b"only the linear-elastic UMAT" in api.host_lib().en234host_last_error()
+
+
 def test_no_device_means_loud_failure():
     import ctypes as C
     if api.gpu_lib().en234gpu_device_count() > 0:

@@ -76,11 +76,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A) {
             y1 += __ldcs(v + L + q) * xv;
             y2 += __ldcs(v + 2 * L + q) * xv;
         }
-        y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2);
-        if (lane < 3) {
-            const double yv = lane == 0 ? y0 : (lane == 1 ? y1 : y2);
-            A.y[3 * (size_t)i + lane] = yv;
-            dot += yv * A.x[3 * (size_t)i + lane];
+        const double yv = warp_sum3(y0, y1, y2, lane);          // y_r in lanes 8r..8r+7
+        if ((lane & 7) == 0 && lane < 24) {
+            const int r = lane >> 3;
+            A.y[3 * (size_t)i + r] = yv;
+            dot += yv * A.x[3 * (size_t)i + r];
         }
         rb = rbn; re = ren; rbn = rb2; ren = re2; c0 = cn0; c1 = cn1; c2 = cn2;
     }

@@ -63,6 +63,20 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Sum of three values over the warp in 6 shuffle steps instead of 15: the first two steps halve what a lane carries
+// (xor 16: keep (y0,y1) or y2; xor 8: keep one of the pair), the last three are an ordinary butterfly.  The sum of y_r ends
+// up in lanes 8r .. 8r+7 (fixed tree: deterministic).
+__device__ __forceinline__ double warp_sum3(double y0, double y1, double y2, int lane) {
+    const bool hi16 = lane & 16, hi8 = lane & 8;
+    const double sa = hi16 ? y0 : y2, sb = hi16 ? y1 : 0.0;          // what the partner keeps
+    double ka = (hi16 ? y2 : y0) + __shfl_xor_sync(0xffffffffu, sa, 16);
+    double kb = (hi16 ? 0.0 : y1) + __shfl_xor_sync(0xffffffffu, sb, 16);
+    double v = (hi8 ? kb : ka) + __shfl_xor_sync(0xffffffffu, hi8 ? ka : kb, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
 // deterministic CTA sum (fixed tree); result valid in every thread
 template <int NT>
 __device__ __forceinline__ double block_sum(double v, double* sm /*NT/32 + 1*/) {

@@ -86,6 +86,7 @@ struct en234gpu_ctx {
     std::vector<int> h_fixdof;   // last prescribed-DOF list (the row subset is rebuilt only when it changes)
     bool diag_valid = false;
     int spmv_occ = 4;
+    int max_row_blocks = 0;      // longest block row (k_spmv drops its tail loop when <= 32)
     bool any_neo = false;
     bool any_c3d8 = false;       // built-in C3D8 continuum elements (all elements of the mesh)
     DevBuf<double> sv0, sv1;     // initial / updated element state variables
@@ -230,6 +231,7 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
         browptr[i + 1] = (int)bcol.size();
     }
     c->nnzb = (long long)bcol.size();
+    for (int i = 0; i < N; ++i) c->max_row_blocks = std::max(c->max_row_blocks, browptr[i + 1] - browptr[i]);
     // inverse slot map: for block (row i, slot s) nibble k = local node b of the row's k-th adjacent element on column s
     std::vector<unsigned> inv(bcol.size(), 0xffffffffu);
     for (int i = 0; i < N; ++i) {
@@ -612,6 +614,7 @@ static int launch_spmv_rows(en234gpu_ctx* c, const double* x, double* y, int row
     A.row0 = row0; A.N = row1; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
     A.partials = c->part.p + part_off; A.S = c->S.p; A.check_stop = check_stop;
     if (c->spmv_occ == 5) k_spmv<5><<<grid, THREADS, 0, c->stream>>>(A);
+    else if (c->max_row_blocks <= 32) k_spmv<4, false><<<grid, THREADS, 0, c->stream>>>(A);
     else k_spmv<4><<<grid, THREADS, 0, c->stream>>>(A);
     c->st.kernel_launches++;
     *n_part = grid;

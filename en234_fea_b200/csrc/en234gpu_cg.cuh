@@ -29,7 +29,9 @@ struct SpmvArgs {
 // ahead), so every load issued for a row is independent of the others: one memory latency per row instead of the
 // pointer -> column -> x chain.  Rows are interleaved over all warps of the (single-wave, persistent) grid so that the
 // rows in flight at any time are neighbours and their x entries hit in L2/L1.
-template <int MINB>
+// WIDE = false: no block row has more than 32 blocks (every hex8 mesh with at most 8 elements per node), the tail loop
+// over further blocks is compiled out.
+template <int MINB, bool WIDE = true>
 __global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A) {
     __shared__ double red[WARPS + 1];
     if (A.check_stop && A.S->stop) return;
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A) {
         y0 = a00 * x0 + a01 * x1 + a02 * x2;
         y1 = a10 * x0 + a11 * x1 + a12 * x2;
         y2 = a20 * x0 + a21 * x1 + a22 * x2;
+        if (WIDE)
         for (int q = lane + 96; q < L; q += 32) {            // rows with more than 32 blocks (unstructured meshes)
             const int j = 3 * __ldg(A.bcol + rb + q / 3) + q % 3;
             const double xv = __ldg(A.x + j);

@@ -37,6 +37,9 @@ CG_MAXIT = 20000
 
 
 def workload(n_gpus, name):
+    if os.environ.get("EN234_BENCH_DIMS"):                 # test hook: a small block instead of the BASELINE sizes
+        d = tuple(int(x) for x in os.environ["EN234_BENCH_DIMS"].split(","))
+        return d, "test: %dx%dx%d hex8 block (EN234_BENCH_DIMS)" % d
     if name == "c4":
         return (96, 96, 96), "c4: synthetic 96^3 hex8 neo-Hookean block, 4 increments, Newton-Raphson with re-assembly (BASELINE configs[3])"
     if name == "c5":

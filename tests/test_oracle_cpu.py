@@ -396,6 +396,29 @@ def test_other_umat_inputs_are_rejected_not_misread():
         assert b"only the linear-elastic UMAT" in api.host_lib().en234host_last_error()
 
 
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside the CUDA arm) on a small block: one JSON line with the
+    contract keys, on rank 0 only."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, EN234_BENCH_DIMS="8,8,8")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "MDOF-CG-iters/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    env["RANK"] = "1"                                          # other ranks exit 0 without work or output
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"], env=env, stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
 def test_no_device_means_loud_failure():
     import ctypes as C
     if api.gpu_lib().en234gpu_device_count() > 0:

@@ -49,6 +49,7 @@ GPU_SYMBOLS = [
     "en234gpu_get_unique_id", "en234gpu_comm_init", "en234gpu_set_partition", "en234gpu_get_stats",
     "en234gpu_bench_operator", "en234gpu_comm_arena", "en234gpu_comm_connect",
     "en234gpu_measure_fp64_peak", "en234gpu_n_state_variables", "en234gpu_commit_state", "en234gpu_get_state_variables", "en234gpu_set_state_variables",
+    "en234gpu_project_fields",
 ]
 HOST_SYMBOLS = [
     "en234host_model_read", "en234host_model_from_text", "en234host_model_free", "en234host_last_error",
@@ -56,6 +57,7 @@ HOST_SYMBOLS = [
     "en234host_model_write_text", "en234host_evaluate_loads", "en234host_gpu_create", "en234host_run_static",
     "en234host_partition", "en234host_part_free", "en234host_part_int", "en234host_part_owned",
     "en234host_part_gpu_create", "en234host_run_static_part", "en234host_check_stiffness",
+    "en234host_model_get_state_print", "en234host_model_set_state_print", "en234host_project_fields", "en234host_print_state",
 ]
 # Fortran-linkage twins of the reference plugin entry points (include/en234host.h)
 PLUGIN_SYMBOLS = ["user_element_static_", "uel_"]
@@ -190,6 +192,31 @@ class Model:
         if rc:
             raise RuntimeError("check_stiffness failed: " + host_lib().en234host_last_error().decode())
         return err.value, nu.value, nnu.value
+
+    def state_print(self):
+        """The PRINT STATE block as parsed (read_input_file.f90:1772-1866)."""
+        flags, steps, scale = C.c_int(), C.c_int(), C.c_double()
+        names, fname = C.create_string_buffer(4096), C.create_string_buffer(1024)
+        host_lib().en234host_model_get_state_print(self.h, C.byref(flags), C.byref(steps), C.byref(scale), names, C.c_int(4096),
+                                                   fname, C.c_int(1024))
+        f = flags.value
+        return {"stateprint": bool(f & 1), "print_dof": bool(f & 2), "displaced_mesh": bool(f & 4), "lumped": bool(f & 8),
+                "state_print_steps": steps.value, "displacement_scale_factor": scale.value,
+                "field_variables": [n for n in names.value.decode().split(",") if n], "file_name": fname.value.decode()}
+
+    def set_state_print(self, path, field_variables=None, print_dof=None, displaced_mesh=None, lumped=None,
+                        state_print_steps=0, displacement_scale_factor=None, enabled=True):
+        """Turn the state prints of run_static on (path) or off (path=None); unspecified options keep their parsed values."""
+        cur = self.state_print()
+        pick = lambda v, k: cur[k] if v is None else v
+        flags = (1 if enabled else 0) | (2 if pick(print_dof, "print_dof") else 0) | (4 if pick(displaced_mesh, "displaced_mesh") else 0) \
+            | (8 if pick(lumped, "lumped") else 0)
+        names = None if field_variables is None else ",".join(field_variables).encode()
+        rc = host_lib().en234host_model_set_state_print(self.h, C.c_int(flags), C.c_int(state_print_steps),
+                                                        C.c_double(pick(displacement_scale_factor, "displacement_scale_factor")),
+                                                        names, os.fsencode(path) if path else None)
+        if rc:
+            raise RuntimeError(host_lib().en234host_last_error().decode())
 
     def evaluate_loads(self, time, dtime, dof_total=None, dof_increment=None):
         nd = 3 * self.n_nodes
@@ -335,6 +362,29 @@ class GpuSystem:
     def commit_state(self):
         self._ck(gpu_lib().en234gpu_commit_state(self.h))
 
+    def project_fields(self, names, dof_total=None, dof_increment=None, lumped=False):
+        """Nodal projection of integration-point fields (print_state, src/printing.f90:457-490) on the device:
+        (n_nodes, n_fields).  dof arrays None: the device-resident state of the last step."""
+        out = np.zeros((len(names), self.model.n_nodes))
+        ut = None if dof_total is None else _f64(dof_total)
+        du = None if dof_increment is None else _f64(dof_increment)
+        if ut is not None and du is None:
+            du = np.zeros_like(ut)
+        rc = host_lib().en234host_project_fields(self.model.h, self.h, ",".join(names).encode(), C.c_int(1 if lumped else 0),
+                                                 _dp(ut), _dp(du), _dp(out))
+        if rc:
+            raise RuntimeError("project_fields failed: " + host_lib().en234host_last_error().decode())
+        return out.T.copy()
+
+    def print_state(self, path, dof_total, dof_increment=None, time_end=1.0, append=False):
+        """One Tecplot zone of the current PRINT STATE options for the given state."""
+        ut = _f64(dof_total)
+        du = None if dof_increment is None else _f64(dof_increment)
+        rc = host_lib().en234host_print_state(self.model.h, self.h, C.c_double(time_end), _dp(ut), _dp(du), os.fsencode(path),
+                                              C.c_int(1 if append else 0))
+        if rc:
+            raise RuntimeError("print_state failed: " + host_lib().en234host_last_error().decode())
+
     def csr(self):
         import scipy.sparse as sp
         nnz = 9 * self.nnz_blocks()
@@ -430,7 +480,7 @@ class GpuSystem:
         if rc:
             raise RuntimeError("static step failed: " + host_lib().en234host_last_error().decode())
         return {"dof_total": u, "rforce": rf, "newton": newton[:info[2]].copy(), "cg_iterations": cg[:info[3]].copy(),
-                "n_steps": int(info[0]), "n_cutbacks": int(info[1])}
+                "n_steps": int(info[0]), "n_cutbacks": int(info[1]), "n_state_prints": int(info[4])}
 
 
 

@@ -18,6 +18,7 @@
 #include "en234gpu_elem.cuh"
 #include "en234gpu_cg.cuh"
 #include "en234gpu_mf.cuh"
+#include "en234gpu_project.cuh"
 #include "en234gpu_comm.h"
 
 using namespace en234k;
@@ -828,16 +829,10 @@ static int bicgstab_solve(en234gpu_ctx* c, double tol, int maxit, double* correc
     return phase_end(c, &c->st.solve_ms);
 }
 
-int en234gpu_solve_dev(en234gpu_handle c, int method, double cg_tolerance, int max_cg_iterations,
-                       double* correction_norm, int* cg_iterations, int* fail) {
-    if (method == EN234_SOLVE_BICGSTAB_BSR) return bicgstab_solve(c, cg_tolerance, max_cg_iterations, correction_norm, cg_iterations, fail);
-    if (method != EN234_SOLVE_PCG_BSR && method != EN234_SOLVE_PCG_MATRIXFREE) return set_err("unknown solve method");
-    if (method == EN234_SOLVE_PCG_BSR && !c->matrix_valid) return set_err("solve called before assemble");
-    if (method != c->mode) return set_err("solve method differs from the operator mode (en234gpu_set_operator_mode)");
-    if (c->any_c3d8) return set_err("C3D8 continuum elements have an unsymmetric tangent: use EN234_SOLVE_BICGSTAB_BSR");
-    if (method == EN234_SOLVE_PCG_MATRIXFREE && c->any_neo)
-        return set_err("the matrix-free operator covers the linear-elastic elements only (1001 / U1)");
-    if (phase_begin(c)) return 1;
+// PCG on (val | matrix-free operator, rhs, minv) -> sol: initialisation, then chunks of CG_CHUNK captured iterations; the
+// stop flag is read back after each chunk (iterations after convergence inside a chunk return immediately).  Leaves the
+// final scalars in c->hS.
+static int pcg_run(en234gpu_ctx* c, int method, double cg_tolerance, int max_cg_iterations) {
     if (!c->graph[method] && build_graph(c, method)) return 1;
     // tolerance / iteration cap are run-time values in device memory (compile-time in modules/Stiffness.f90:35-37)
     CgScalars init{};
@@ -864,14 +859,26 @@ int en234gpu_solve_dev(en234gpu_handle c, int method, double cg_tolerance, int m
     c->st.kernel_launches++;
     CK(cudaGetLastError());
     const long long per_graph = c->graph_launches[method];
-    // chunks of CG_CHUNK iterations; the stop flag is read back after each chunk (iterations after convergence
-    // inside a chunk return immediately)
     for (;;) {
         if (read_scalars(c)) return 1;
         if (c->hS->stop || c->hS->iter >= max_cg_iterations) break;
         CK(cudaGraphLaunch(c->graph[method], c->stream));
         c->st.kernel_launches += per_graph;
     }
+    return 0;
+}
+
+int en234gpu_solve_dev(en234gpu_handle c, int method, double cg_tolerance, int max_cg_iterations,
+                       double* correction_norm, int* cg_iterations, int* fail) {
+    if (method == EN234_SOLVE_BICGSTAB_BSR) return bicgstab_solve(c, cg_tolerance, max_cg_iterations, correction_norm, cg_iterations, fail);
+    if (method != EN234_SOLVE_PCG_BSR && method != EN234_SOLVE_PCG_MATRIXFREE) return set_err("unknown solve method");
+    if (method == EN234_SOLVE_PCG_BSR && !c->matrix_valid) return set_err("solve called before assemble");
+    if (method != c->mode) return set_err("solve method differs from the operator mode (en234gpu_set_operator_mode)");
+    if (c->any_c3d8) return set_err("C3D8 continuum elements have an unsymmetric tangent: use EN234_SOLVE_BICGSTAB_BSR");
+    if (method == EN234_SOLVE_PCG_MATRIXFREE && c->any_neo)
+        return set_err("the matrix-free operator covers the linear-elastic elements only (1001 / U1)");
+    if (phase_begin(c)) return 1;
+    if (pcg_run(c, method, cg_tolerance, max_cg_iterations)) return 1;
     if (comm_p2p_error(c->comm)) return set_err("peer-memory collective timed out (a rank stopped responding)");
     *fail = c->hS->fail ? 1 : 0;
     *cg_iterations = c->hS->iter;
@@ -1026,6 +1033,95 @@ int en234gpu_get_svars(en234gpu_handle c, const double* dof_total, const double*
     CK(cudaMemcpyAsync(svars, d_sv.p, (size_t)c->E * 48 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+// print_state's projection of integration-point fields to the nodes (src/printing.f90:457-490): right-hand sides, the
+// 27-point mass matrix written as diag(m,m,m) blocks over the stiffness storage, three fields per Jacobi-PCG pass (or the
+// row-sum lumped matrix).  The stiffness values are overwritten: the next solve needs a fresh assembly.
+int en234gpu_project_fields(en234gpu_handle c, int n_fields, const int* field_codes, int lumped, double tolerance,
+                            int max_iterations, const double* dof_total, const double* dof_increment, double* fields,
+                            int* iterations) {
+    CK(cudaSetDevice(c->device));
+    // post-processing, not a timed path: every stage is synchronised so that a failure names the stage
+#define STAGE(name)                                                                                              \
+    do {                                                                                                         \
+        cudaError_t e_ = cudaGetLastError();                                                                     \
+        if (e_ == cudaSuccess) e_ = cudaStreamSynchronize(c->stream);                                            \
+        if (e_ != cudaSuccess) return set_err(std::string("project_fields, ") + name + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+    if (iterations) *iterations = 0;
+    if (c->comm.active) return set_err("field projection is single-device post-processing: run it on an unpartitioned context");
+    if (n_fields < 0 || n_fields > PROJ_MAXF) return set_err("project_fields: between 0 and " + std::to_string(PROJ_MAXF) + " field variables");
+    if (c->any_neo)   // user_element_fieldvariables knows element 1001 only (user_codes/src/user_element.f90:233-266)
+        return set_err("project_fields: no field variables are defined for the neo-Hookean element (1002 / U2)");
+    if (n_fields == 0) return 0;
+    const int N = c->N;
+    const size_t b = (size_t)c->ndof * sizeof(double);
+    if (dof_total) CK(cudaMemcpyAsync(c->ut.p, dof_total, b, cudaMemcpyHostToDevice, c->stream));
+    if (dof_increment) CK(cudaMemcpyAsync(c->du.p, dof_increment, b, cudaMemcpyHostToDevice, c->stream));
+    DevBuf<double> F, lump;
+    CK(F.alloc((size_t)n_fields * N));
+    CK(lump.alloc(N));
+    ProjArgs A{};
+    A.M = mesh_of(c);
+    A.ut = c->ut.p; A.du = c->du.p;
+    A.source = c->any_c3d8 ? 1 : 0;
+    A.sv = c->any_c3d8 ? c->sv1.p : nullptr;
+    A.nsp = C3D8_NSV_POINT;
+    A.nf = n_fields;
+    A.F = F.p;
+    for (int k = 0; k < n_fields; ++k) {
+        int code = field_codes[k];
+        bool ok;
+        if (A.source == 0) ok = code >= 0 && code <= FIELD_MISES;                       // el_linelast_3Dbasic.f90:392-408
+        else ok = (code >= 0 && code < 6) || (code >= FIELD_STRAIN0 && code < FIELD_STRAIN0 + 6) ||
+                  (code >= FIELD_STATE0 && code < FIELD_STATE0 + A.nsp);                // continuum_elements.f90:1291-1345
+        A.code[k] = ok ? code : FIELD_ZERO;                                             // unknown names stay zero fields
+    }
+    const int grid = (N + PROJ_THREADS - 1) / PROJ_THREADS;
+    STAGE("state upload");
+    k_project_rhs<<<grid, PROJ_THREADS, 0, c->stream>>>(A);
+    c->st.kernel_launches++;
+    STAGE("k_project_rhs");
+    // the PCG graph is wired to rhs / minv / val: keep the step's rhs and preconditioner aside
+    CK(cudaMemcpyAsync(c->tmpvec.p, c->rhs.p, b, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->tmpvec2.p, c->minv.p, b, cudaMemcpyDeviceToDevice, c->stream));
+    MassArgs Ma{};
+    Ma.M = mesh_of(c); Ma.val = c->val.p; Ma.minv = c->minv.p; Ma.lump = lump.p;
+    c->matrix_valid = false;
+    c->diag_valid = false;
+    STAGE("save rhs / preconditioner");
+    k_project_mass<<<grid, PROJ_THREADS, 0, c->stream>>>(Ma);
+    c->st.kernel_launches++;
+    STAGE("k_project_mass");
+    int rc = 0, its = 0;
+    if (lumped) {
+        k_project_lumped<<<(N + 255) / 256, 256, 0, c->stream>>>(N, n_fields, lump.p, F.p);
+        c->st.kernel_launches++;
+        STAGE("k_project_lumped");
+    } else {
+        for (int k0 = 0; k0 < n_fields && !rc; k0 += 3) {
+            k_project_pack<<<(N + 255) / 256, 256, 0, c->stream>>>(N, n_fields, k0, F.p, c->rhs.p);
+            c->st.kernel_launches++;
+            STAGE("k_project_pack");
+            rc = pcg_run(c, EN234_SOLVE_PCG_BSR, tolerance > 0 ? tolerance : 1e-28, max_iterations > 0 ? max_iterations : 500);
+            if (rc) break;
+            if (c->hS->fail) { rc = set_err("project_fields: the projection solve did not converge"); break; }
+            its += c->hS->iter;
+            k_project_unpack<<<(N + 255) / 256, 256, 0, c->stream>>>(N, n_fields, k0, c->sol.p, F.p);
+            c->st.kernel_launches++;
+            STAGE("k_project_unpack");
+        }
+    }
+    CK(cudaMemcpyAsync(c->rhs.p, c->tmpvec.p, b, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->minv.p, c->tmpvec2.p, b, cudaMemcpyDeviceToDevice, c->stream));
+    if (rc) { cudaStreamSynchronize(c->stream); return 1; }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(fields, F.p, (size_t)n_fields * N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (iterations) *iterations = its;
+    return 0;
+#undef STAGE
 }
 
 // Single-element evaluation on the device for the host-callable twins of the reference's element routines

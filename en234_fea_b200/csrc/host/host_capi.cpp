@@ -7,6 +7,7 @@
 #include "../../../include/en234host.h"
 #include "loads.h"
 #include "model.h"
+#include "print_state.h"
 #include "staticstep.h"
 
 using namespace en234;
@@ -216,6 +217,70 @@ int en234host_gpu_create(en234host_model_t w, int device, en234gpu_handle* h) {
     return rc;
 }
 
+// ---- state print ---------------------------------------------------------------------------------------
+static std::vector<std::string> split_csv(const char* csv) {
+    std::vector<std::string> v;
+    std::string cur;
+    for (const char* p = csv ? csv : "";; ++p) {
+        if (*p == ',' || *p == 0) { if (!cur.empty()) v.push_back(cur); cur.clear(); if (!*p) break; }
+        else if (*p != ' ') cur += *p;
+    }
+    return v;
+}
+static void copy_text(const std::string& s, char* dst, int cap) {
+    if (!dst || cap <= 0) return;
+    std::strncpy(dst, s.c_str(), (size_t)cap - 1);
+    dst[cap - 1] = 0;
+}
+
+int en234host_model_get_state_print(en234host_model_t w, int* flags, int* state_print_steps, double* scale_factor,
+                                    char* field_names_csv, int cap_names, char* file_name, int cap_file) {
+    const Model& m = w->m;
+    if (flags) *flags = (m.stateprint ? 1 : 0) | (m.print_dof ? 2 : 0) | (m.print_displacedmesh ? 4 : 0) | (m.use_lumped_projection_matrix ? 8 : 0);
+    if (state_print_steps) *state_print_steps = m.state_print_steps;
+    if (scale_factor) *scale_factor = m.displacementscalefactor;
+    std::string names;
+    for (size_t i = 0; i < m.field_variable_names.size(); ++i) names += (i ? "," : "") + m.field_variable_names[i];
+    copy_text(names, field_names_csv, cap_names);
+    copy_text(m.state_print_filename, file_name, cap_file);
+    return 0;
+}
+
+int en234host_model_set_state_print(en234host_model_t w, int flags, int state_print_steps, double scale_factor,
+                                    const char* field_names_csv, const char* path) {
+    Model& m = w->m;
+    m.stateprint = flags & 1; m.print_dof = flags & 2; m.print_displacedmesh = flags & 4; m.use_lumped_projection_matrix = flags & 8;
+    if (state_print_steps > 0) m.state_print_steps = state_print_steps;
+    m.displacementscalefactor = scale_factor;
+    if (field_names_csv) m.field_variable_names = split_csv(field_names_csv);
+    if ((int)m.field_variable_names.size() > EN234_MAX_FIELDS) { g_err = "too many field variables"; return 1; }
+    m.state_print_path = path ? normalise_path(path) : std::string();
+    return 0;
+}
+
+int en234host_project_fields(en234host_model_t w, en234gpu_handle h, const char* field_names_csv, int lumped,
+                             const double* dof_total, const double* dof_increment, double* fields) {
+    std::vector<double> f;
+    std::string err;
+    if (project_fields(w->m, h, split_csv(field_names_csv), lumped != 0, dof_total, dof_increment, f, err)) { g_err = err; return 1; }
+    if (!f.empty()) std::memcpy(fields, f.data(), f.size() * sizeof(double));
+    return 0;
+}
+
+int en234host_print_state(en234host_model_t w, en234gpu_handle h, double time_end, const double* dof_total,
+                          const double* dof_increment, const char* path, int append) {
+    std::vector<double> zero;
+    if (!dof_increment) { zero.assign((size_t)w->m.ndof(), 0.0); dof_increment = zero.data(); }
+    if (!dof_total) { g_err = "print_state needs dof_total"; return 1; }
+    FILE* f = std::fopen(normalise_path(path).c_str(), append ? "a" : "w");
+    if (!f) { g_err = std::string("cannot open state print file ") + path; return 1; }
+    std::string err;
+    const int rc = print_state(w->m, h, time_end, dof_total, dof_increment, f, err);
+    std::fclose(f);
+    if (rc) g_err = err;
+    return rc;
+}
+
 int en234host_run_static(en234host_model_t w, en234gpu_handle h, int method, double cg_tolerance,
                          int max_cg_iterations, int check_linear_cg, int use_host_api, double* dof_total,
                          double* rforce, double* newton, int max_rows, int* cg_iterations, int max_cg_rows,
@@ -225,9 +290,15 @@ int en234host_run_static(en234host_model_t w, en234gpu_handle h, int method, dou
     o.check_linear_cg = check_linear_cg != 0; o.use_host_api = use_host_api != 0;
     StepResult r;
     FILE* log = log_path ? std::fopen(log_path, "w") : nullptr;
+    if (w->m.stateprint && !w->m.state_print_path.empty()) {
+        o.state_print = std::fopen(w->m.state_print_path.c_str(), "w");
+        if (!o.state_print) { if (log) std::fclose(log); g_err = "cannot open state print file " + w->m.state_print_path; return -1; }
+    }
     int rc = compute_static_step(w->m, h, o, r, log);
     if (log) std::fclose(log);
+    if (o.state_print) std::fclose(o.state_print);
     if (rc) g_err = r.error;
+    if (info) info[4] = r.n_state_prints;
     const size_t nd = (size_t)w->m.ndof();
     if (dof_total && r.dof_total.size() == nd) std::memcpy(dof_total, r.dof_total.data(), nd * sizeof(double));
     if (rforce && r.rforce.size() == nd) std::memcpy(rforce, r.rforce.data(), nd * sizeof(double));

@@ -1,5 +1,5 @@
 // en234_run — command-line static analysis on the GPU path:  en234_run <file.in> [--matrix-free] [--cg-tol x]
-//             [--cg-maxit n] [--host-api] [--log file.out] [--device d]
+//             [--cg-maxit n] [--host-api] [--log file.out] [--device d] [--state-print file | --no-state-print]
 // Plays the role of `program en234fea` (src/main.f90:127-143) for the static step: read the input file, run
 // compute_static_step, report the convergence history.  (The reference hard-codes its input path, main.f90:11-35.)
 #include <cstdio>
@@ -11,10 +11,12 @@
 #include "../../../include/en234host.h"
 
 int main(int argc, char** argv) {
-    if (argc < 2) { std::fprintf(stderr, "usage: en234_run <file.in> [--matrix-free] [--cg-tol x] [--cg-maxit n] [--host-api] [--log f] [--device d]\n"); return 2; }
+    if (argc < 2) { std::fprintf(stderr, "usage: en234_run <file.in> [--matrix-free] [--cg-tol x] [--cg-maxit n] [--host-api] [--log f] [--device d] [--state-print f | --no-state-print]\n"); return 2; }
     int method = EN234_SOLVE_PCG_BSR, host_api = 0, device = 0, maxit = 0;
     double tol = 0.0;
     const char* log = nullptr;
+    const char* state_print = nullptr;
+    bool no_state_print = false;
     for (int i = 2; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--matrix-free")) method = EN234_SOLVE_PCG_MATRIXFREE;
         else if (!std::strcmp(argv[i], "--host-api")) host_api = 1;
@@ -22,6 +24,8 @@ int main(int argc, char** argv) {
         else if (!std::strcmp(argv[i], "--cg-maxit") && i + 1 < argc) maxit = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--log") && i + 1 < argc) log = argv[++i];
         else if (!std::strcmp(argv[i], "--device") && i + 1 < argc) device = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--state-print") && i + 1 < argc) state_print = argv[++i];
+        else if (!std::strcmp(argv[i], "--no-state-print")) no_state_print = true;
     }
     en234host_model_t m = en234host_model_read(argv[1]);
     if (!m) { std::fprintf(stderr, "input error: %s\n", en234host_last_error()); return 1; }
@@ -42,12 +46,23 @@ int main(int argc, char** argv) {
             std::printf(" STIFFNESS CHECK element %d: normalized difference %.3e (%s), unsymmetric entries %d / %d\n", p[0], err,
                         err > 1e-6 ? "NOT consistent" : "consistent with residual", nu, nnu);
     }
+    {   // PRINT STATE block: written to the file the input names (print_state, src/printing.f90) unless overridden
+        int flags = 0, steps = 1;
+        double scale = 1.0;
+        char fname[512] = {0};
+        en234host_model_get_state_print(m, &flags, &steps, &scale, nullptr, 0, fname, (int)sizeof fname);
+        if ((flags & 1) && !no_state_print) {
+            const char* path = state_print ? state_print : fname;
+            if (en234host_model_set_state_print(m, flags, steps, scale, nullptr, path)) { std::fprintf(stderr, "%s\n", en234host_last_error()); return 1; }
+            std::printf(" state prints -> %s\n", path);
+        }
+    }
     std::vector<double> u(3 * (size_t)nn), rf(3 * (size_t)nn), newton(8 * 4096);
     std::vector<int> cg(4096);
     long long info[8] = {0};
     int rc = en234host_run_static(m, h, method, tol, maxit, 1, host_api, u.data(), rf.data(), newton.data(), 4096, cg.data(), 4096, info, log);
     if (rc) { std::fprintf(stderr, "static step failed: %s\n", en234host_last_error()); return 1; }
-    std::printf(" steps completed %lld, cutbacks %lld\n", info[0], info[1]);
+    std::printf(" steps completed %lld, cutbacks %lld, state prints %lld\n", info[0], info[1], info[4]);
     for (int i = 0; i < info[2]; ++i)
         std::printf(" step %3d it %2d  correction %12.5e  force %12.5e  unbalanced %12.5e  ratio %12.5e  %s\n",
                     (int)newton[8 * i], (int)newton[8 * i + 1], newton[8 * i + 2], newton[8 * i + 3], newton[8 * i + 4],

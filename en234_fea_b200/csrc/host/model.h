@@ -74,6 +74,14 @@ struct Model {
     int max_newton_iterations = 1;
     bool unsymmetric_stiffness = false;
     int checkstiffness_flag = 0;           // element flag named by CHECK STIFFNESS (0 = none)
+    // PRINT STATE block of the static step (read_input_file.f90:1772-1866; defaults :136-149, modules/Printparameters.f90)
+    bool stateprint = false;
+    std::string state_print_filename;      // as written in the input (backslashes kept; normalised when opened)
+    int state_print_steps = 1;             // STATE PRINT STEPS (:1715-1726)
+    bool print_dof = false, print_displacedmesh = false, use_lumped_projection_matrix = false;
+    double displacementscalefactor = 1.0;
+    std::vector<std::string> field_variable_names;
+    std::string state_print_path;          // run-time: where run_static writes the state prints ("" = state prints off)
     // run-time solver options that are compile-time parameters in modules/Stiffness.f90:35-37
     double cg_tolerance = 1e-17;
     int max_cg_iterations = 1000;

@@ -478,7 +478,10 @@ bool parse_static_step(Reader& r) {
         } else if (kw(L.tok[0], "STOPT")) {                            // :1704-1714
             m.max_total_time = to_real(L.tok[1]);
             if (m.max_no_steps == 0) m.max_no_steps = (int)(m.max_total_time / m.timestep_min);
-        } else if (kw(L.tok[0], "STATEPRINTS") || kw(L.tok[0], "USERPRINTST")) {
+        } else if (kw(L.tok[0], "STATEPRINTS")) {                      // :1715-1726
+            if (L.n() != 2 || L.typ[1] != 0) return r.fail("expecting value for STATE PRINT STEPS", &L);
+            m.state_print_steps = to_int(L.tok[1]);
+        } else if (kw(L.tok[0], "USERPRINTST")) {
         } else if (kw(L.tok[0], "SOLVER")) {                           // :1735-1771
             if (L.n() < 3) return r.fail("SOLVER needs a type and LINEAR/NONLINEAR", &L);
             m.unsymmetric_stiffness = false;
@@ -500,7 +503,33 @@ bool parse_static_step(Reader& r) {
             m.cg_tolerance = to_real(L.tok[1]);
         } else if (kw(L.tok[0], "CGMAXIT")) {                          // extension: run-time max_cg_iterations (Stiffness.f90:37)
             m.max_cg_iterations = to_int(L.tok[1]);
-        } else if (kw(L.tok[0], "PRINTST")) { if (!skip_block(r, "ENDPRINTS")) return false; }
+        } else if (kw(L.tok[0], "PRINTST")) {                          // :1772-1866
+            if (L.n() != 2 || L.typ[1] != 2) return r.fail("expecting a file name following PRINT STATE key", &L);
+            m.stateprint = true;
+            m.state_print_filename = L.tok[1];
+            while (true) {
+                if (!r.next(L)) return r.fail("PRINT STATE block not terminated");
+                if (kw(L.tok[0], "ENDPRINTS")) break;
+                if (L.typ[0] < 2) return r.fail("unrecognized option in PRINT STATE in a STATIC STEP", &L);
+                if (kw(L.tok[0], "DEGREE")) m.print_dof = true;
+                if (kw(L.tok[0], "DISPLACEDM")) m.print_displacedmesh = true;
+                if (kw(L.tok[0], "DISPLACEMENTS")) {
+                    if (L.n() < 2 || L.typ[1] == 2) return r.fail("expecting value for displacement scale factor", &L);
+                    m.displacementscalefactor = to_real(L.tok[1]);
+                }
+                if (kw(L.tok[0], "FIELD")) {
+                    if (L.n() < 2) return r.fail("expecting names of field variables", &L);
+                    // names are stored from slot 1 on every FIELD VARIABLES line (field_variable_names(k-1), :1830-1833)
+                    for (int k = 1; k < L.n(); ++k) {
+                        if ((int)m.field_variable_names.size() < k) m.field_variable_names.resize(k);
+                        m.field_variable_names[k - 1] = L.tok[k];
+                    }
+                }
+                if (kw(L.tok[0], "ZONES")) {                           // single-zone meshes: the list is read and ignored
+                    if (!skip_block(r, "ENDZ")) return false;
+                }
+            }
+        }
         else if (kw(L.tok[0], "USERPRINTPA") || kw(L.tok[0], "USERPRINTFI")) { if (!skip_block(r, "ENDU")) return false; }
         else return r.fail("unknown key in STATIC STEP block", &L);
     }

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 
+#include "print_state.h"
 #include "staticstep.h"
 
 namespace en234 {
@@ -166,6 +167,13 @@ int compute_static_step(const Model& m, en234gpu_handle h, const StepOptions& op
         }
         if (!opt.use_host_api &&
             en234gpu_download_state(h, dof_increment.data(), res.rforce.data())) { res.error = en234gpu_last_error(); return -1; }
+        // state print: first step, every state_print_steps-th step, last step (staticstep.f90:227-231), before the
+        // increment is added to dof_total (:81-86); one device only
+        if (m.stateprint && opt.state_print && !g2l &&
+            (t.current_step_number == 1 || (m.state_print_steps > 0 && t.current_step_number % m.state_print_steps == 0) || !cont)) {
+            if (print_state(m, h, t.TIME + t.DTIME, res.dof_total.data(), dof_increment.data(), opt.state_print, res.error)) return -1;
+            res.n_state_prints++;
+        }
         t.current_step_number++;
         for (size_t d = 0; d < ndof; ++d) res.dof_total[d] += dof_increment[d];
         if (en234gpu_commit_state(h)) { res.error = en234gpu_last_error(); return -1; }   // staticstep.f90:87

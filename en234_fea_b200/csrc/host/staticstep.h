@@ -21,6 +21,7 @@ struct StepOptions {
     int max_cg_iterations = 0;        // <= 0: reference value / 100000
     bool check_linear_cg = false;     // run the re-assemble + convergencecheck loop for LINEAR + CG too
     bool use_host_api = false;        // true: host-buffer entry points (what a Fortran driver binds) each call
+    FILE* state_print = nullptr;      // open Tecplot file for the PRINT STATE block (null: state prints are skipped)
 };
 
 struct StepResult {
@@ -28,7 +29,7 @@ struct StepResult {
     std::vector<NewtonRecord> newton;
     std::vector<int> cg_iterations;
     std::vector<double> step_time;
-    int n_steps_completed = 0, n_cutbacks = 0;
+    int n_steps_completed = 0, n_cutbacks = 0, n_state_prints = 0;
     std::string error;
 };
 

@@ -212,7 +212,19 @@ std::string write_input_text(const Model& m) {
         if (m.nonlinear) o << "NONLINEAR, " << m.newtonraphson_tolerance << ", " << m.max_newton_iterations;
         else o << "LINEAR";
         if (m.unsymmetric_stiffness) o << ", UNSYMMETRIC";
-        o << "\n CG TOLERANCE, " << m.cg_tolerance << "\n CG MAX ITERATIONS, " << m.max_cg_iterations << "\nEND STATIC STEP\n";
+        o << "\n CG TOLERANCE, " << m.cg_tolerance << "\n CG MAX ITERATIONS, " << m.max_cg_iterations << "\n";
+        if (m.stateprint) {
+            o << " STATE PRINT STEPS, " << m.state_print_steps << "\n PRINT STATE, " << m.state_print_filename << "\n";
+            if (m.print_dof) o << "  DEGREES OF FREEDOM\n";
+            if (!m.field_variable_names.empty()) {
+                o << "  FIELD VARIABLES";
+                for (const std::string& nm : m.field_variable_names) o << ", " << nm;
+                o << "\n";
+            }
+            if (m.print_displacedmesh) o << "  DISPLACED MESH\n";
+            o << "  DISPLACEMENT SCALE FACTOR, " << m.displacementscalefactor << "\n END PRINT STATE\n";
+        }
+        o << "END STATIC STEP\n";
     }
     o << "STOP\n";
     return o.str();

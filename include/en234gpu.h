@@ -138,6 +138,26 @@ int en234gpu_element_single(int element_flag, const double* coords24, const doub
 int en234gpu_get_svars(en234gpu_handle h, const double* dof_total, const double* dof_increment,
                        double* svars /*48*n_elements*/);
 
+/* Field projection of print_state (src/printing.f90:457-490; the step after the hot path): nodal least-squares fit of
+ * integration-point fields.  Right-hand sides int f N dV per node in the reference's element order (assemble_field_projection,
+ * :1386-1668), the consistent projection matrix int N N dV with the 27-point rule (:1214-1383) solved by Jacobi-PCG on the
+ * device, three fields per pass (the reference LU-factorises a skyline copy: agreement to the solver tolerance), or the
+ * row-sum lumped matrix (:1096-1212) when lumped != 0.
+ * field_codes[k]: EN234_FIELD_S11..S23 (0..5), EN234_FIELD_SMISES (6; elements 1001 / U1), EN234_FIELD_E11..E23 (7..12;
+ * C3D8), EN234_FIELD_STATE0 + i (state variable i of the point; C3D8); anything else projects to a zero field, as an
+ * unknown name does in the reference.  dof_total / dof_increment: host arrays, or NULL to use the device-resident state.
+ * fields: host, [k * n_nodes + n].  tolerance <= 0: 1e-28 on r.r / b.b; max_iterations <= 0: 500.
+ * Overwrites the assembled stiffness values (a new en234gpu_assemble* must precede the next solve).  Single device. */
+#define EN234_FIELD_S11 0
+#define EN234_FIELD_SMISES 6
+#define EN234_FIELD_E11 7
+#define EN234_FIELD_STATE0 100
+#define EN234_FIELD_NONE (-1)
+#define EN234_MAX_FIELDS 24
+int en234gpu_project_fields(en234gpu_handle h, int n_fields, const int* field_codes, int lumped, double tolerance,
+                            int max_iterations, const double* dof_total, const double* dof_increment, double* fields,
+                            int* iterations);
+
 /* ---- inspection (parity tests, reports) */
 long long en234gpu_nnz_blocks(en234gpu_handle h);
 /* Scalar CSR view of the current system matrix: rowptr[3N+1] (64-bit), col[9*nnzb] (0-based), val[9*nnzb] */

@@ -54,7 +54,7 @@ int en234host_gpu_create(en234host_model_t m, int device, en234gpu_handle* h);
 
 /* compute_static_step (src/staticstep.f90:1-162) on the device path.
  *   newton[8*max_rows]: step, iteration, correction, force, unbalanced, ratio, tolerance, converged per row
- *   info[8]: n_steps_completed, n_cutbacks, n_newton_rows, n_cg_solves, 0...
+ *   info[8]: n_steps_completed, n_cutbacks, n_newton_rows, n_cg_solves, n_state_prints, 0...
  *   log_path: optional file receiving the reference-format convergence lines (NULL = none) */
 int en234host_run_static(en234host_model_t m, en234gpu_handle h, int method, double cg_tolerance,
                          int max_cg_iterations, int check_linear_cg, int use_host_api, double* dof_total,
@@ -80,6 +80,29 @@ int en234host_run_static_part(en234host_model_t m, en234host_part_t p, en234gpu_
                               double cg_tolerance, int max_cg_iterations, int check_linear_cg, int use_host_api,
                               double* dof_total_local, double* rforce_local, double* newton, int max_rows,
                               int* cg_iterations, int max_cg_rows, long long* info, const char* log_path);
+
+/* ---- state print: the step after the hot path (print_state, src/printing.f90:249-1093; 3-D hex8 zones).
+ * The PRINT STATE block of the static step is parsed (read_input_file.f90:1772-1866); en234host_run_static writes a
+ * Tecplot FEPOINT zone at the first, every STATE PRINT STEPS-th and the last step (staticstep.f90:227-231) once a path
+ * has been set with en234host_model_set_state_print (library default: off, so that running an input never writes files
+ * the caller did not ask for; the en234_run driver turns it on with the input's own file name).
+ * flags: bit 0 PRINT STATE present / enabled, bit 1 DEGREES OF FREEDOM, bit 2 DISPLACED MESH, bit 3 lumped projection
+ * matrix (printing.f90:464-471; the static step default is the consistent matrix, read_input_file.f90:144). */
+int en234host_model_get_state_print(en234host_model_t m, int* flags, int* state_print_steps, double* scale_factor,
+                                    char* field_names_csv, int cap_names, char* file_name, int cap_file);
+int en234host_model_set_state_print(en234host_model_t m, int flags, int state_print_steps, double scale_factor,
+                                    const char* field_names_csv /*NULL: keep*/, const char* path /*NULL: off*/);
+/* Nodal projection of the named integration-point fields on the device (en234gpu_project_fields): S11 S22 S33 S12 S13 S23
+ * SMISES for elements 1001 / U1 (el_linelast_3Dbasic.f90:392-408, abaqus_tecplot_interface.f90:163-179), S.., E11..E23,
+ * U<n> for C3D8 (continuum_elements.f90:1291-1345); names are matched by prefix like the reference's strcmp, unknown
+ * names give zero fields.  fields[k * n_nodes + n].  dof arrays: host, or NULL for the device-resident state. */
+int en234host_project_fields(en234host_model_t m, en234gpu_handle h, const char* field_names_csv, int lumped,
+                             const double* dof_total, const double* dof_increment, double* fields);
+/* One zone of the Tecplot file for the given state: VARIABLES line, ZONE header (A10,D12.4,A15,I5,A3,I5,A9), one
+ * (n(1X,E18.10)) line per node in order of first appearance in the element list, (8(1x,i5)) connectivity.  Node / element
+ * counts above 99999 are written in full (the reference's I5 prints asterisks). */
+int en234host_print_state(en234host_model_t m, en234gpu_handle h, double time_end, const double* dof_total,
+                          const double* dof_increment /*NULL: zero*/, const char* path, int append);
 
 /* check_stiffness (src/checkstiffness.f90): the reference's self-test of an element routine, run through the device twins
  * below — coded stiffness against the numerical derivative of the residual (h = 1e-7), err = sum (K_num - K)^2 / sum K^2

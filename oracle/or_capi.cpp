@@ -140,6 +140,50 @@ int or_projection_mass_lu(void* model, const int* order, double* out) {
     return 0;
 }
 
+// ---- state print (or_print.cpp) ----------------------------------------------------------------
+static std::vector<std::string> split_names(const char* csv) {
+    std::vector<std::string> v;
+    std::string cur;
+    for (const char* p = csv ? csv : ""; ; ++p) {
+        if (*p == ',' || *p == 0) { if (!cur.empty()) v.push_back(cur); cur.clear(); if (!*p) break; }
+        else cur += *p;
+    }
+    return v;
+}
+// raw = 1: the assembled right-hand sides int f N dV only; else the projected nodal fields.  out[k + nf*n]
+int or_project_fields(void* model, const double* dof_total, const double* dof_increment, const double* svars,
+                      const char* names_csv, int lumped, int raw, double* out) {
+    const Model& m = *(Model*)model;
+    std::vector<std::string> names = split_names(names_csv);
+    std::vector<double> f;
+    int rc = raw ? assemble_field_projection(m, dof_total, dof_increment, svars, names, f)
+                 : project_fields(m, dof_total, dof_increment, svars, names, lumped != 0, f);
+    if (rc) return rc;
+    std::memcpy(out, f.data(), sizeof(double) * f.size());
+    return 0;
+}
+int or_lumped_projection_mass(void* model, double* out) {
+    std::vector<double> l;
+    lumped_projection_mass(*(Model*)model, l);
+    std::memcpy(out, l.data(), sizeof(double) * l.size());
+    return 0;
+}
+// flags: bit 0 DEGREES OF FREEDOM, bit 1 DISPLACED MESH, bit 2 lumped projection matrix
+int or_print_state(void* model, const double* dof_total, const double* dof_increment, const double* svars,
+                   const char* names_csv, int flags, double scale_factor, double time_end, const char* path) {
+    PrintOptions o;
+    o.field_names = split_names(names_csv);
+    o.print_dof = flags & 1; o.displaced_mesh = flags & 2; o.lumped = flags & 4;
+    o.displacement_scale_factor = scale_factor;
+    std::string text;
+    if (int rc = print_state(*(Model*)model, o, time_end, dof_total, dof_increment, svars, text)) return rc;
+    FILE* f = std::fopen(path, "w");
+    if (!f) return -1;
+    std::fwrite(text.data(), 1, text.size(), f);
+    std::fclose(f);
+    return 0;
+}
+
 // ---- assembled systems ------------------------------------------------------------------------
 void* or_system_new(void* model, int kind) {
     System* s = new System();

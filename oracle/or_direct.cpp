@@ -338,10 +338,15 @@ static void lu_decomposition(Skyline& s, StepLog* log) {
 // with the node numbering given, factorised by the same LDU routine (printing.f90:475-488).  Only the conditioning line
 // the reference prints for it is of interest here: the golden log carries it once per printed step.
 void projection_mass_lu(const Model& m, const std::vector<int>& node_order, StepLog* log) {
+    Skyline s;
+    projection_mass_factor(m, node_order, s, log);
+}
+// the factorised matrix itself (print_state then back-substitutes one right-hand side per field variable, :480-488)
+void projection_mass_factor(const Model& m, const std::vector<int>& node_order, Skyline& s, StepLog* log) {
     const int N = m.n_nodes;
     std::vector<int> num(N, 0);                       // node -> equation (0-based)
     for (int i = 0; i < N; ++i) num[node_order[i]] = i;
-    Skyline s;
+    s = Skyline();
     s.neq = N;
     std::vector<long long> h(N, 0);
     for (int lmn = 0; lmn < m.n_elements; ++lmn) {
@@ -427,6 +432,8 @@ static void backsubstitution(Skyline& s) {
         }
     }
 }
+
+void skyline_backsubstitution(Skyline& s) { backsubstitution(s); }
 
 // solve_direct (solver_direct.f90:916-973)
 void solve_direct(const Model& m, Skyline& s, double* dof_increment, AsmOut& out, StepLog* log) {

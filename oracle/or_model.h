@@ -125,6 +125,8 @@ void compute_profile(const Model& m, const std::vector<int>& node_order, Skyline
 void gps_node_order(const Model& m, std::vector<int>& node_order);   // bandwidth_minimizer.f90
 struct StepLog;
 void projection_mass_lu(const Model& m, const std::vector<int>& node_order, StepLog* log);   // printing.f90:1214-1383, :475-488
+void projection_mass_factor(const Model& m, const std::vector<int>& node_order, Skyline& s, StepLog* log);
+void skyline_backsubstitution(Skyline& s);   // solver_direct.f90:976-1032 on s.rhs
 struct AsmOut {
     std::vector<double> rforce;
     double nodal_force_norm = 0, unbalanced_force_norm = 0, correction_norm = 0;
@@ -156,5 +158,21 @@ int solve_conjugategradient(const Model& m, CooUpper& c, double* dof_increment, 
 // ---- static step driver (or_step.cpp) -------------------------------------------------------
 int compute_static_step(const Model& m, std::vector<double>& dof_total, std::vector<double>& rforce,
                         std::vector<double>& svars, StepLog& log);
+
+
+// ---- state print (or_print.cpp): nodal projection of Gauss-point fields + Tecplot file, src/printing.f90:249-1093 ----
+struct PrintOptions {
+    std::vector<std::string> field_names;   // FIELD VARIABLES of the PRINT STATE block (read_input_file.f90:1822-1834)
+    bool print_dof = false, displaced_mesh = false, lumped = false;
+    double displacement_scale_factor = 1.0;
+};
+// field[k + nf*n]: int_V f_k N^n dV summed over the elements in element order (printing.f90:1386-1668)
+int assemble_field_projection(const Model& m, const double* dof_total, const double* dof_increment, const double* svars,
+                              const std::vector<std::string>& names, std::vector<double>& field);
+void lumped_projection_mass(const Model& m, std::vector<double>& lump);                       // printing.f90:1096-1212
+int project_fields(const Model& m, const double* dof_total, const double* dof_increment, const double* svars,
+                   const std::vector<std::string>& names, bool lumped, std::vector<double>& field);
+int print_state(const Model& m, const PrintOptions& o, double time_end, const double* dof_total,
+                const double* dof_increment, const double* svars, std::string& out);
 
 }  // namespace oracle

@@ -84,6 +84,35 @@ class OracleModel:
         lib().or_projection_mass_lu(self.h, _i(np.ascontiguousarray(order, np.int32)), _d(out))
         return out
 
+    def project_fields(self, names, dof_total, dof_increment=None, svars=None, lumped=False, raw=False):
+        """Nodal projection of the named integration-point fields (src/printing.f90:457-490): (n_nodes, n_fields).
+        raw=True returns the assembled right-hand sides int f N dV instead."""
+        out = np.zeros((self.n_nodes, len(names)))
+        du = np.zeros(self.ndof) if dof_increment is None else np.ascontiguousarray(dof_increment, np.float64)
+        ut = np.ascontiguousarray(dof_total, np.float64)
+        sv = None if svars is None else np.ascontiguousarray(svars, np.float64)
+        rc = lib().or_project_fields(self.h, _d(ut), _d(du), _d(sv) if sv is not None else None, ",".join(names).encode(),
+                                     C.c_int(int(lumped)), C.c_int(int(raw)), _d(out))
+        if rc:
+            raise RuntimeError("oracle field projection failed rc=%d" % rc)
+        return out
+
+    def lumped_projection_mass(self):
+        out = np.zeros(self.n_nodes)
+        lib().or_lumped_projection_mass(self.h, _d(out))
+        return out
+
+    def print_state(self, path, names, dof_total, dof_increment=None, svars=None, print_dof=False, displaced_mesh=False,
+                    lumped=False, scale_factor=1.0, time_end=1.0):
+        du = np.zeros(self.ndof) if dof_increment is None else np.ascontiguousarray(dof_increment, np.float64)
+        ut = np.ascontiguousarray(dof_total, np.float64)
+        sv = None if svars is None else np.ascontiguousarray(svars, np.float64)
+        flags = int(print_dof) | 2 * int(displaced_mesh) | 4 * int(lumped)
+        rc = lib().or_print_state(self.h, _d(ut), _d(du), _d(sv) if sv is not None else None, ",".join(names).encode(),
+                                  C.c_int(flags), C.c_double(scale_factor), C.c_double(time_end), str(path).encode())
+        if rc:
+            raise RuntimeError("oracle print_state failed rc=%d" % rc)
+
     def run_static(self):
         L = lib()
         u, rf = np.zeros(self.ndof), np.zeros(self.ndof)

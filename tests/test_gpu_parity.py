@@ -542,3 +542,91 @@ def test_stretch_rotate_reference_input_with_subroutine_bcs():
     assert np.abs(sv - svo).max() <= 1e-8 * np.abs(svo).max()
     assert np.allclose(sv[..., 1], 49.875, atol=1e-3) and np.abs(np.delete(sv[..., :6], 1, axis=-1)).max() < 1e-4
     g.close()
+
+
+# ---------------------------------------------------------------------------------------------- state print
+def test_field_projection_matches_oracle_linear_elastic_elements(cube8):
+    """print_state's nodal projection (src/printing.f90:457-490) on the device against the oracle's restatement (skyline
+    LDU of the 27-point matrix): element 1001 on the jittered 8^3 block, consistent and lumped matrices.  The device
+    solves the consistent system by Jacobi-PCG to r.r/b.b <= 1e-28, so the bar is 1e-10 of the largest nodal value."""
+    m, g, om = cube8
+    names = ["S11", "S22", "S33", "S12", "S13", "S23", "SMISES", "nonsense"]
+    rng = np.random.default_rng(11)
+    ut, du = 0.01 * rng.uniform(-1, 1, g.ndof), 0.002 * rng.uniform(-1, 1, g.ndof)
+    for lumped in (False, True):
+        got = g.project_fields(names, ut, du, lumped=lumped)
+        want = om.project_fields(names, ut, du, lumped=lumped)
+        assert got.shape == want.shape == (m.n_nodes, 8)
+        assert np.abs(got[:, :7] - want[:, :7]).max() < 1e-10 * np.abs(want).max(), lumped
+        assert not got[:, 7].any() and not want[:, 7].any()             # unknown names project to zero
+    # the stiffness storage was used for the projection matrix: solving without a new assembly is refused ...
+    with pytest.raises(RuntimeError):
+        g.solve_dev(method=0)
+    # ... and a fresh static step on the same handle still reproduces the oracle
+    res = g.run_static(method=0)
+    ref = om.run_static()
+    assert relmax(res["dof_total"], ref["dof_total"]) < TOL_U
+
+
+def test_state_print_file_of_the_uel_reference_input(tmp_path):
+    """input_files/Abaqus_uel_linear_elastic_3d.in with its PRINT STATE block (DEGREES OF FREEDOM, six stresses, DISPLACED
+    MESH): run_static writes one Tecplot zone per step (STATE PRINT STEPS 1, 3 steps); the last zone against the oracle's
+    print_state of the same state, number by number, and against the analytic uniaxial stress of 2."""
+    m = golden_model("linear_elastic_3d_uel.in")
+    names = ["S11", "S22", "S33", "S12", "S13", "S23"]
+    out = tmp_path / "contourplots.dat"
+    m.set_state_print(str(out), field_variables=names, print_dof=True, displaced_mesh=True, displacement_scale_factor=1.0)
+    g = GpuSystem(m)
+    res = g.run_static(method=0)
+    assert res["n_steps"] == 3 and res["n_state_prints"] == 3
+    lines = out.read_text().splitlines()
+    per_zone = 2 + 12 + 2
+    assert len(lines) == 3 * per_zone
+    assert [l for l in lines if l.startswith(" ZONE")] == [' ZONE, T="  0.%d000D+01" F=FEPOINT, I=   12 J=    2 ET=BRICK' % k for k in (1, 2, 3)]
+    # the load is constant in time (dload_history), so step 1 carries the whole displacement and the increments of steps
+    # 2 and 3 are zero to rounding: the state printed at step 3 is (dof_total, 0)
+    om = ob.OracleModel(m.arrays())
+    ref = om.run_static()
+    u3 = ref["dof_total"]
+    want = tmp_path / "oracle.dat"
+    om.print_state(want, names, u3, None, svars=ref["state_variables"], print_dof=True, displaced_mesh=True, time_end=3.0)
+    wl = want.read_text().splitlines()
+    gl = lines[2 * per_zone:]
+    assert gl[0] == wl[0] and gl[1] == wl[1] and gl[14:] == wl[14:]
+    for a_, b_ in zip(gl[2:14], wl[2:14]):
+        va = np.array([float(a_[19 * k:19 * k + 19]) for k in range(15)])
+        vb = np.array([float(b_[19 * k:19 * k + 19]) for k in range(15)])
+        assert np.allclose(va, vb, rtol=1e-9, atol=1e-11)
+        assert abs(va[9] - 2.0) < 1e-7 and np.abs(va[10:]).max() < 1e-11
+    # one more zone through the direct entry point, appended
+    g.print_state(str(out), u3, None, time_end=4.0, append=True)
+    assert len(out.read_text().splitlines()) == 4 * per_zone
+    g.close()
+
+
+def test_field_projection_c3d8_state_variables_golden_model():
+    """The golden-log model (3075 C3D8 B-bar elements, elastic UMAT): stresses and strains of the converged state are read
+    from the device state variables (continuum_elements.f90:1206-1351) and projected; against the oracle's projection of
+    its own converged state.  The two runs differ by their linear solvers (1e-9 on the state), the projection adds 1e-10."""
+    m = golden_model("holeplate_3d_umat.in.gz")
+    g = GpuSystem(m)
+    res = g.run_static(method=0)
+    names = ["S11", "S22", "S33", "S12", "S13", "S23", "E11", "E22", "E33", "E12", "E13", "E23", "U1", "SMISES"]
+    got = g.project_fields(names)                                        # device-resident state of the last step
+    a = dict(np.load(os.path.join(GOLDEN, "holeplate_3d_umat_model.npz")))
+    om = ob.OracleModel(a, node_order=ob.OracleModel(a).gps_node_order())
+    ref = om.run_static()
+    assert relmax(res["dof_total"], ref["dof_total"]) < 1e-9
+    want = om.project_fields(names, ref["dof_total"], svars=ref["state_variables"])
+    for k in range(12):
+        assert np.abs(got[:, k] - want[:, k]).max() < 1e-7 * np.abs(want[:, k]).max(), names[k]
+    assert not got[:, 12:].any() and not want[:, 12:].any()             # U1: the elastic UMAT has no state; SMISES: not a C3D8 field
+    # stress concentration at the hole: the projected S11 peaks at about three times the remote stress (Kirsch), here a
+    # finite-width plate, so between 2.5 and 4.5
+    s11 = got[:, 0]
+    far = np.median(s11)
+    assert 2.5 < s11.max() / far < 4.5
+    lum = g.project_fields(names[:6], lumped=True)
+    wl = om.project_fields(names[:6], ref["dof_total"], svars=ref["state_variables"], lumped=True)
+    assert np.abs(lum - wl).max() < 1e-7 * np.abs(wl).max()
+    g.close()

@@ -396,6 +396,156 @@ def test_other_umat_inputs_are_rejected_not_misread():
         assert b"only the linear-elastic UMAT" in api.host_lib().en234host_last_error()
 
 
+# ---------------------------------------------------------------------------------------------- state print
+FIELDS7 = ["S11", "S22", "S33", "S12", "S13", "S23", "SMISES"]
+
+
+def _hex8_shape(xi):
+    sg = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], float)
+    f = 1 + sg * xi
+    N = f[:, 0] * f[:, 1] * f[:, 2] / 8
+    dN = np.stack([sg[:, 0] * f[:, 1] * f[:, 2], sg[:, 1] * f[:, 0] * f[:, 2], sg[:, 2] * f[:, 0] * f[:, 1]], 1) / 8
+    return N, dN
+
+
+def test_field_projection_right_hand_sides_and_matrices_against_numpy():
+    """print_state's projection (src/printing.f90:457-490) restated in numpy on a jittered 1001 block: right-hand sides
+    int sigma_k N dV with the 2x2x2 rule and the single-precision abscissa (el_linelast_3Dbasic.f90:369-408), consistent
+    and lumped projection matrices with the 27-point rule and the reference's truncated weights (Element_Utilities.f90:651-656),
+    dense solve instead of the skyline LDU."""
+    m = Model.from_text(synthetic_block_input(3, jitter=0.25))
+    a = m.arrays()
+    om = ob.OracleModel(a)
+    N = m.n_nodes
+    X = a["coords"].reshape(-1, 3)
+    conn = a["connectivity"].reshape(-1, 8) - 1
+    rng = np.random.default_rng(5)
+    ut, du = 0.01 * rng.uniform(-1, 1, 3 * N), 0.002 * rng.uniform(-1, 1, 3 * N)
+    E, nu = a["element_properties"][:2]
+    D = np.zeros((6, 6))
+    D[:3, :3] = nu * E / ((1 + nu) * (1 - 2 * nu))
+    np.fill_diagonal(D[:3, :3], (1 - nu) * E / ((1 + nu) * (1 - 2 * nu)))
+    D[3, 3] = D[4, 4] = D[5, 5] = 0.5 * E / (1 + nu)
+    g = float(np.float32(0.5773502692))
+    g3 = float(np.float32(0.7745966692))
+    x1, w1 = [-g3, 0.0, g3], [0.5555555555, 0.888888888, 0.55555555555]
+    F = np.zeros((N, 7))
+    M = np.zeros((N, N))
+    for c in conn:
+        xc = X[c]
+        u = (ut + du).reshape(-1, 3)[c].ravel()
+        for k in (-1, 1):
+            for j in (-1, 1):
+                for i in (-1, 1):
+                    Nn, dN = _hex8_shape(np.array([i, j, k]) * g)
+                    J = xc.T @ dN
+                    dNdx = dN @ np.linalg.inv(J)
+                    B = np.zeros((6, 24))
+                    B[0, 0::3] = dNdx[:, 0]; B[1, 1::3] = dNdx[:, 1]; B[2, 2::3] = dNdx[:, 2]
+                    B[3, 0::3] = dNdx[:, 1]; B[3, 1::3] = dNdx[:, 0]
+                    B[4, 0::3] = dNdx[:, 2]; B[4, 2::3] = dNdx[:, 0]
+                    B[5, 1::3] = dNdx[:, 2]; B[5, 2::3] = dNdx[:, 1]
+                    s = D @ (B @ u)
+                    dev = s.copy(); dev[:3] -= s[:3].mean()
+                    mises = np.sqrt(dev[:3] @ dev[:3] + 2 * dev[3:] @ dev[3:]) * np.sqrt(1.5)
+                    F[c] += np.outer(Nn, np.append(s, mises)) * np.linalg.det(J)
+        for k in range(3):
+            for j in range(3):
+                for i in range(3):
+                    Nn, dN = _hex8_shape(np.array([x1[i], x1[j], x1[k]]))
+                    M[np.ix_(c, c)] += np.outer(Nn, Nn) * np.linalg.det(xc.T @ dN) * w1[i] * w1[j] * w1[k]
+    rel = lambda A, B: np.abs(A - B).max() / np.abs(B).max()
+    raw = om.project_fields(FIELDS7, ut, du, raw=True)
+    assert rel(raw, F) < 1e-13
+    assert rel(om.lumped_projection_mass(), M.sum(1)) < 1e-13
+    assert rel(om.project_fields(FIELDS7, ut, du), np.linalg.solve(M, F)) < 1e-11
+    assert rel(om.project_fields(FIELDS7, ut, du, lumped=True), F / M.sum(1)[:, None]) < 1e-13
+    # names are matched on their first characters, either case (src/parse.f90:155-176); unknown names give zero fields
+    odd = om.project_fields(["s11", "S22xyz", "SMISESfoo", "E11", "nonsense"], ut, du, raw=True)
+    assert np.array_equal(odd[:, 0], raw[:, 0]) and np.array_equal(odd[:, 1], raw[:, 1]) and np.array_equal(odd[:, 2], raw[:, 6])
+    assert not odd[:, 3:].any()
+
+
+def test_field_projection_reproduces_fields_of_the_finite_element_space():
+    """A least-squares projection returns any field that is itself trilinear: SVARS of the U1 elements set to a linear
+    function of position at the integration points must come back as that function at the nodes (to the 1e-8 the
+    reference's rounded quadrature constants allow), with the consistent matrix; uniform fields with both matrices."""
+    m = golden_model("holeplate_3d.in.gz") if os.path.exists(os.path.join(GOLDEN, "holeplate_3d.in.gz")) else None
+    m = m or Model.from_text(synthetic_block_input(4, jitter=0.0))
+    a = m.arrays()
+    a["element_flag"] = np.full(m.n_elements, 100000, np.int32)          # U1: stress read from SVARS
+    a["element_n_states"] = np.full(m.n_elements, 48, np.int32)
+    om = ob.OracleModel(a)
+    X = a["coords"].reshape(-1, 3)
+    conn = a["connectivity"].reshape(-1, 8) - 1
+    g = float(np.float32(0.5773502692))
+    lin = lambda P: 1.0 + 2.0 * P[..., 0] - 1.0 * P[..., 1] + 0.5 * P[..., 2]
+    sv = np.zeros((m.n_elements, 8, 6))
+    for kint in range(8):
+        xi = np.array([g if kint & 1 else -g, g if kint & 2 else -g, g if kint & 4 else -g])
+        Nn, _ = _hex8_shape(xi)
+        P = np.einsum("a,eai->ei", Nn, X[conn])
+        sv[:, kint, 0] = lin(P)
+        sv[:, kint, 1] = 3.0
+    f = om.project_fields(["S11", "S22"], np.zeros(3 * m.n_nodes), svars=sv.ravel())
+    assert np.abs(f[:, 0] - lin(X)).max() < 2e-7 * np.abs(lin(X)).max()
+    assert np.abs(f[:, 1] - 3.0).max() < 3e-8
+    fl = om.project_fields(["S11", "S22"], np.zeros(3 * m.n_nodes), svars=sv.ravel(), lumped=True)
+    assert np.abs(fl[:, 1] - 3.0).max() < 3e-8
+    assert np.abs(fl[:, 0] - lin(X)).max() > 1e-3                          # lumping smears a non-uniform field
+
+
+def test_print_state_file_layout(tmp_path):
+    """The Tecplot zone print_state writes (src/printing.f90:425-431, :494-548, :742-744): list-directed VARIABLES line,
+    (A10,D12.4,A15,I5,A3,I5,A9) zone header, one (n(1X,E18.10)) record per node in order of first appearance in the element
+    list, (8(1x,i5)) connectivity in the new numbering."""
+    m = golden_model("linear_elastic_3d_uel.in")
+    a = m.arrays()
+    om = ob.OracleModel(a)
+    res = om.run_static()
+    p = tmp_path / "state.dat"
+    om.print_state(p, ["S11", "S22", "S33", "S12", "S13", "S23"], res["dof_total"], svars=res["state_variables"], print_dof=True,
+                   displaced_mesh=True, scale_factor=2.0, time_end=3.0)
+    lines = p.read_text().splitlines()
+    assert lines[0] == " VARIABLES = X,Y,Z,DU1,DU2,DU3,U1,U2,U3,S11,S22,S33,S12,S13,S23"
+    assert lines[1] == ' ZONE, T="  0.3000D+01" F=FEPOINT, I=   12 J=    2 ET=BRICK'
+    assert len(lines) == 2 + 12 + 2
+    conn = a["connectivity"].reshape(-1, 8)
+    order = list(dict.fromkeys(conn.ravel().tolist()))                     # first appearance
+    X = a["coords"].reshape(-1, 3)
+    U = res["dof_total"].reshape(-1, 3)
+    for line, node in zip(lines[2:14], order):
+        assert len(line) == 15 * 19 and all(line[19 * k] == " " for k in range(15))
+        v = np.array([float(line[19 * k:19 * k + 19]) for k in range(15)])
+        assert re.fullmatch(r" *-?0\.\d{10}E[+-]\d\d", line[:19])
+        assert np.allclose(v[:3], X[node - 1] + 2.0 * U[node - 1], rtol=1e-9, atol=1e-12)
+        assert np.allclose(v[3:6], 0.0) and np.allclose(v[6:9], U[node - 1], rtol=1e-9, atol=1e-12)
+        assert abs(v[9] - 2.0) < 1e-7 and np.abs(v[10:]).max() < 1e-12      # uniaxial tension of 2 (SURVEY section 4)
+    renum = {n: i + 1 for i, n in enumerate(order)}
+    for line, c in zip(lines[14:], conn):
+        assert line == "".join(" %5d" % renum[n] for n in c)
+
+
+def test_parser_reads_the_print_state_block():
+    text = synthetic_block_input(2).replace("END STATIC STEP", """ STATE PRINT STEPS, 2
+  PRINT STATE, Output_files\\contour.dat
+     DEGREES OF FREEDOM
+     FIELD VARIABLES, S11, smises, Q9
+     DISPLACED MESH
+     DISPLACEMENT SCALE FACTOR, 2.5d0
+  END PRINT STATE
+END STATIC STEP""")
+    m = Model.from_text(text)
+    sp = m.state_print()
+    assert sp == {"stateprint": True, "print_dof": True, "displaced_mesh": True, "lumped": False, "state_print_steps": 2,
+                  "displacement_scale_factor": 2.5, "field_variables": ["S11", "smises", "Q9"],
+                  "file_name": "Output_files\\contour.dat"}
+    assert Model.from_text(m.text()).state_print() == sp                   # the writer re-emits the block
+    assert not Model.from_text(synthetic_block_input(2)).state_print()["stateprint"]
+    with pytest.raises(Exception):
+        Model.from_text(text.replace("PRINT STATE, Output_files\\contour.dat", "PRINT STATE"))
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """bench.py --impl reference (the CPU arm the driver runs beside the CUDA arm) on a small block: one JSON line with the
     contract keys, on rank 0 only."""

@@ -74,6 +74,22 @@ module en234_gpu_iface
             type(c_ptr), value :: h
             integer(c_int)     :: en234gpu_commit_state
         end function
+        ! print_state's field projection on the device (src/printing.f90:457-490): replaces assemble_field_projection +
+        ! assemble_projection_mass_matrix + LU_decomposition + backsubstitution (or the lumped division);
+        ! fields(n_nodes, n_fields) in Fortran order = fields[k*n_nodes + n] (transpose of field_variables(k,n));
+        ! field_codes: 0..5 S11 S22 S33 S12 S13 S23, 6 SMISES, 7..12 E11..E23, -1 for a name no element routine knows
+        function en234gpu_project_fields(h, n_fields, field_codes, lumped, tolerance, max_iterations, dof_total, &
+                                         dof_increment, fields, iterations) bind(C, name='en234gpu_project_fields')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value            :: h
+            integer(c_int), value         :: n_fields, lumped, max_iterations
+            integer(c_int), intent(in)    :: field_codes(*)
+            real(c_double), value         :: tolerance
+            real(c_double), intent(in)    :: dof_total(*), dof_increment(*)
+            real(c_double), intent(out)   :: fields(*)
+            integer(c_int), intent(out)   :: iterations
+            integer(c_int)                :: en234gpu_project_fields
+        end function
         function en234gpu_last_error() bind(C, name='en234gpu_last_error')
             import :: c_ptr
             type(c_ptr) :: en234gpu_last_error

@@ -49,7 +49,8 @@ GPU_SYMBOLS = [
     "en234gpu_get_unique_id", "en234gpu_comm_init", "en234gpu_set_partition", "en234gpu_get_stats",
     "en234gpu_bench_operator", "en234gpu_comm_arena", "en234gpu_comm_connect",
     "en234gpu_measure_fp64_peak", "en234gpu_n_state_variables", "en234gpu_commit_state", "en234gpu_get_state_variables", "en234gpu_set_state_variables",
-    "en234gpu_project_fields",
+    "en234gpu_project_fields", "en234gpu_dynamic_setup", "en234gpu_dynamic_set_state", "en234gpu_dynamic_steps",
+    "en234gpu_dynamic_half_step", "en234gpu_dynamic_get_state",
 ]
 HOST_SYMBOLS = [
     "en234host_model_read", "en234host_model_from_text", "en234host_model_free", "en234host_last_error",
@@ -58,6 +59,7 @@ HOST_SYMBOLS = [
     "en234host_partition", "en234host_part_free", "en234host_part_int", "en234host_part_owned",
     "en234host_part_gpu_create", "en234host_run_static_part", "en234host_check_stiffness",
     "en234host_model_get_state_print", "en234host_model_set_state_print", "en234host_project_fields", "en234host_print_state",
+    "en234host_run_dynamic",
 ]
 # Fortran-linkage twins of the reference plugin entry points (include/en234host.h)
 PLUGIN_SYMBOLS = ["user_element_static_", "uel_"]
@@ -110,11 +112,11 @@ INT_ARRAYS = ["connectivity", "element_flag", "element_prop_index", "element_n_p
               "pforce_flag", "pforce_dof", "pforce_node", "pforce_nodeset", "pforce_history",
               "dload_flag", "dload_elset", "dload_face", "dload_history", "dload_val_ptr"]
 INT_SCALARS = ["n_nodes", "n_elements", "max_no_steps", "solvertype", "nonlinear", "max_newton_iterations",
-               "unsymmetric", "abaqusformat", "max_cg_iterations", "checkstiffness_flag"]
+               "unsymmetric", "abaqusformat", "max_cg_iterations", "checkstiffness_flag", "explicitdynamicstep", "no_dynamic_steps"]
 DBL_ARRAYS = ["coords", "element_properties", "material_properties", "history_time", "history_value", "pdof_value", "pforce_value",
-              "dload_values", "subparam_values"]
+              "dload_values", "subparam_values", "element_density"]
 DBL_SCALARS = ["timestep_initial", "timestep_min", "timestep_max", "max_total_time", "newtonraphson_tolerance",
-               "cg_tolerance"]
+               "cg_tolerance", "dynamic_timestep"]
 
 
 class Model:
@@ -376,6 +378,38 @@ class GpuSystem:
             raise RuntimeError("project_fields failed: " + host_lib().en234host_last_error().decode())
         return out.T.copy()
 
+    def run_dynamic(self, n_steps=0, initial_velocity=None):
+        """explicit_dynamic_step (src/explicit_dynamic_step.f90) for an input with an EXPLICIT DYNAMIC STEP block; n_steps=0
+        runs the input's NUMBER OF STEPS.  State prints go to the path set with Model.set_state_print."""
+        nd = self.ndof
+        out = {k: np.zeros(nd) for k in ("dof_total", "velocity", "acceleration", "rforce", "lumped_mass")}
+        info = (C.c_longlong * 8)()
+        ms = C.c_double()
+        v0 = None if initial_velocity is None else _f64(initial_velocity)
+        rc = host_lib().en234host_run_dynamic(self.model.h, self.h, C.c_int(n_steps), _dp(v0), _dp(out["dof_total"]),
+                                              _dp(out["velocity"]), _dp(out["acceleration"]), _dp(out["rforce"]),
+                                              _dp(out["lumped_mass"]), info, C.byref(ms))
+        if rc:
+            raise RuntimeError("explicit dynamic step failed: " + host_lib().en234host_last_error().decode())
+        out.update(steps=int(info[0]), n_state_prints=int(info[1]), kernel_launches=int(info[2]), device_ms=ms.value)
+        return out
+
+    def dynamic_steps(self, dt, n_steps):
+        """n_steps more central-difference steps from the device-resident state (after run_dynamic / dynamic set-up)."""
+        fail, ms = C.c_int(), C.c_double()
+        self._ck(gpu_lib().en234gpu_dynamic_steps(self.h, C.c_double(dt), C.c_int(n_steps), C.byref(fail), C.byref(ms)))
+        return fail.value, ms.value
+
+    def dynamic_state(self):
+        nd = self.ndof
+        out = {k: np.zeros(nd) for k in ("dof_total", "dof_increment", "velocity", "acceleration", "rforce", "lumped_mass")}
+        t = C.c_double()
+        self._ck(gpu_lib().en234gpu_dynamic_get_state(self.h, _dp(out["dof_total"]), _dp(out["dof_increment"]), _dp(out["velocity"]),
+                                                      _dp(out["acceleration"]), _dp(out["rforce"]), _dp(out["lumped_mass"]),
+                                                      C.byref(t)))
+        out["time"] = t.value
+        return out
+
     def print_state(self, path, dof_total, dof_increment=None, time_end=1.0, append=False):
         """One Tecplot zone of the current PRINT STATE options for the given state."""
         ut = _f64(dof_total)
@@ -561,7 +595,7 @@ class Partition:
 
 def synthetic_block_input(nx, ny=None, nz=None, jitter=0.2, seed=1234, element="1001", E=100.0, nu=0.3,
                           solver="CONJUGATE GRADIENT", cg_tolerance=1e-17, cg_maxit=1000, load="traction",
-                          nonlinear=None, steps=1, props=None, dt=1.0):
+                          nonlinear=None, steps=1, props=None, dt=1.0, dynamic=None):
     """`.in` text of the synthetic structured hex8 blocks of BASELINE.json: face x=0 clamped,
     face x=max loaded by the traction (0,0,-1) ("traction") or a prescribed u_x ramp ("stretch")."""
     ny = nx if ny is None else ny
@@ -579,6 +613,10 @@ def synthetic_block_input(nx, ny=None, nz=None, jitter=0.2, seed=1234, element="
     t += [" END DEGREES OF FREEDOM"]
     if load == "traction":
         t += [" DISTRIBUTED LOADS", "  xmax_el, 4, VALUE, 0.d0, 0.d0, -1.d0", " END DISTRIBUTED LOADS"]
+    if dynamic:          # (time step, number of steps): EXPLICIT DYNAMIC STEP instead of the static step
+        t += ["END BOUNDARY CONDITIONS", "EXPLICIT DYNAMIC STEP", " TIME STEP, %.17g" % dynamic[0], " NUMBER OF STEPS, %d" % dynamic[1],
+              "END EXPLICIT DYNAMIC STEP", "STOP", ""]
+        return "\n".join(t)
     t += ["END BOUNDARY CONDITIONS", "STATIC STEP", " INITIAL TIME STEP, %.17g" % dt, " MAX TIME STEP, %.17g" % dt,
           " MIN TIME STEP, %.17g" % (dt / 1024.0), " MAX NUMBER OF STEPS, %d" % steps, " STOP TIME, %.17g" % (steps * dt)]
     if nonlinear:

@@ -16,7 +16,7 @@ ORACLE = os.path.join(ROOT, "oracle")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
-HOST_SRCS = ["read_input_file.cpp", "user_mesh.cpp", "loads.cpp", "staticstep.cpp", "host_capi.cpp", "user_element.cpp", "checkstiffness.cpp", "print_state.cpp"]
+HOST_SRCS = ["read_input_file.cpp", "user_mesh.cpp", "loads.cpp", "staticstep.cpp", "host_capi.cpp", "user_element.cpp", "checkstiffness.cpp", "print_state.cpp", "explicit_dynamic_step.cpp"]
 
 
 def _newer(target, sources):

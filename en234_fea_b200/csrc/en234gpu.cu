@@ -19,6 +19,7 @@
 #include "en234gpu_cg.cuh"
 #include "en234gpu_mf.cuh"
 #include "en234gpu_project.cuh"
+#include "en234gpu_dyn.cuh"
 #include "en234gpu_comm.h"
 
 using namespace en234k;
@@ -96,6 +97,18 @@ struct en234gpu_ctx {
     BiScalars* h_bi_S = nullptr;              // pinned mirror
     cudaGraphExec_t bi_graph = nullptr;       // BI_CHUNK iterations
     long long bi_graph_launches = 0;
+    // explicit dynamics (en234gpu_dyn.cuh)
+    struct Dyn {
+        bool ready = false;
+        DevBuf<double> v, a, mass, f, density, hist_t, hist_v, load_val, pd_value, time;
+        DevBuf<int> hist_ptr, load_dof, pd_dof, pd_hist, pd_mode;
+        std::vector<int> load_ptr, load_hist;
+        std::vector<double> load_const;
+        int n_pd = 0;
+        cudaGraphExec_t graph = nullptr;       // DYN_CHUNK steps at time step graph_dt
+        double graph_dt = 0.0;
+        long long graph_launches = 0;
+    } dyn;
     // host copies needed for inspection
     std::vector<int> h_browptr, h_bcol;
     // multi-GPU
@@ -354,6 +367,7 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
 }
 
 int en234gpu_destroy(en234gpu_handle c) {
+    if (c && c->dyn.graph) { cudaGraphExecDestroy(c->dyn.graph); c->dyn.graph = nullptr; }
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
@@ -1122,6 +1136,194 @@ int en234gpu_project_fields(en234gpu_handle c, int n_fields, const int* field_co
     if (iterations) *iterations = its;
     return 0;
 #undef STAGE
+}
+
+// ---- explicit dynamic step (src/explicit_dynamic_step.f90) ---------------------------------------------------
+constexpr int DYN_CHUNK = 16;      // time steps per CUDA-graph launch
+
+int en234gpu_dynamic_setup(en234gpu_handle c, const double* element_density, int n_histories, const int* history_ptr,
+                           const double* history_time, const double* history_value, int n_loads, const int* load_ptr,
+                           const int* load_dof, const double* load_val, const int* load_history, const double* load_constant,
+                           int n_pdof, const int* pdof_dof, const int* pdof_history, const double* pdof_value,
+                           const int* pdof_mode) {
+    CK(cudaSetDevice(c->device));
+    if (c->comm.active) return set_err("explicit dynamics runs on one device in this version");
+    if (c->any_neo || c->any_c3d8)   // user_element_dynamic knows element 1001 only (user_element.f90:152-181); VUMAT is out of scope
+        return set_err("explicit dynamics covers the linear elastic hex8 elements (1001 / VU1) only");
+    auto& D = c->dyn;
+    const size_t nd = (size_t)c->ndof;
+#define UPD(buf, ptr, count)                                                                          \
+    do {                                                                                              \
+        CK(D.buf.alloc(std::max<size_t>((count), 1)));                                                \
+        if ((count) > 0) CK(cudaMemcpy(D.buf.p, (ptr), (size_t)(count) * sizeof(*(ptr)), cudaMemcpyHostToDevice)); \
+    } while (0)
+    UPD(density, element_density, (size_t)c->E);
+    const int nh = std::max(n_histories, 0);
+    std::vector<int> hp(1, 0);
+    if (nh > 0) hp.assign(history_ptr, history_ptr + nh + 1);
+    UPD(hist_ptr, hp.data(), hp.size());
+    UPD(hist_t, history_time, (size_t)hp.back());
+    UPD(hist_v, history_value, (size_t)hp.back());
+    D.load_ptr.assign(1, 0); D.load_hist.clear(); D.load_const.clear();
+    if (n_loads > 0) {
+        D.load_ptr.assign(load_ptr, load_ptr + n_loads + 1);
+        D.load_hist.assign(load_history, load_history + n_loads);
+        D.load_const.assign(load_constant, load_constant + n_loads);
+        for (int l = 0; l < n_loads; ++l)
+            if (D.load_hist[l] < 0 || D.load_hist[l] > nh) return set_err("dynamic_setup: load refers to a history that does not exist");
+        for (int k = 0; k < D.load_ptr.back(); ++k)
+            if (load_dof[k] < 0 || (size_t)load_dof[k] >= nd) return set_err("dynamic_setup: load DOF out of range");
+    }
+    UPD(load_dof, load_dof, (size_t)D.load_ptr.back());
+    UPD(load_val, load_val, (size_t)D.load_ptr.back());
+    for (int k = 0; k < n_pdof; ++k) {
+        if (pdof_dof[k] < 0 || (size_t)pdof_dof[k] >= nd) return set_err("dynamic_setup: prescribed DOF out of range");
+        if (pdof_history[k] < 0 || pdof_history[k] > nh) return set_err("dynamic_setup: prescribed DOF refers to a history that does not exist");
+    }
+    D.n_pd = n_pdof;
+    UPD(pd_dof, pdof_dof, (size_t)n_pdof); UPD(pd_hist, pdof_history, (size_t)n_pdof);
+    UPD(pd_value, pdof_value, (size_t)n_pdof); UPD(pd_mode, pdof_mode, (size_t)n_pdof);
+#undef UPD
+    for (DevBuf<double>* b : {&D.v, &D.a, &D.mass, &D.f}) {
+        CK(b->alloc(nd));
+        CK(cudaMemsetAsync(b->p, 0, nd * sizeof(double), c->stream));
+    }
+    CK(D.time.alloc(1));
+    CK(cudaMemsetAsync(D.time.p, 0, sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->ut.p, 0, nd * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->du.p, 0, nd * sizeof(double), c->stream));
+    k_dyn_lumped_mass<<<(c->N + 127) / 128, 128, 0, c->stream>>>(mesh_of(c), D.density.p, D.mass.p);
+    c->st.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->Re.n < (size_t)c->E * 24) CK(c->Re.alloc((size_t)c->E * 24));
+    if (D.graph) { cudaGraphExecDestroy(D.graph); D.graph = nullptr; }
+    D.ready = true;
+    c->matrix_valid = false;
+    c->rhs_valid = false;
+    return 0;
+}
+
+int en234gpu_dynamic_set_state(en234gpu_handle c, const double* dof_total, const double* velocity, const double* acceleration,
+                               double time) {
+    CK(cudaSetDevice(c->device));
+    if (!c->dyn.ready) return set_err("dynamic_set_state called before dynamic_setup");
+    const size_t b = (size_t)c->ndof * sizeof(double);
+    auto put = [&](double* dst, const double* src) -> cudaError_t {
+        return src ? cudaMemcpyAsync(dst, src, b, cudaMemcpyHostToDevice, c->stream) : cudaMemsetAsync(dst, 0, b, c->stream);
+    };
+    CK(put(c->ut.p, dof_total)); CK(put(c->dyn.v.p, velocity)); CK(put(c->dyn.a.p, acceleration));
+    CK(cudaMemcpyAsync(c->dyn.time.p, &time, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// phases: 1 = predictor + boundary conditions, 2 = element forces + update, 3 = both (one whole step)
+static void dyn_enqueue_step(en234gpu_ctx* c, double dt, int phases = 3) {
+    auto& D = c->dyn;
+    const int n = c->ndof;
+    const DynTables T{D.hist_ptr.p, D.hist_t.p, D.hist_v.p};
+    if (phases & 1) {
+    k_dyn_predict<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(n, dt, D.v.p, D.a.p, c->du.p, D.f.p);
+    const int n_loads = (int)D.load_hist.size();
+    for (int l = 0; l < n_loads; ++l) {
+        const int cnt = D.load_ptr[l + 1] - D.load_ptr[l];
+        if (cnt == 0) continue;
+        k_dyn_load<<<(cnt + 255) / 256, 256, 0, c->stream>>>(cnt, D.load_dof.p + D.load_ptr[l], D.load_val.p + D.load_ptr[l],
+                                                             D.load_hist[l], D.load_const[l], T, D.time.p, dt, D.f.p);
+        c->st.kernel_launches++;
+    }
+    if (D.n_pd > 0) {
+        k_dyn_pdof<<<(D.n_pd + 255) / 256, 256, 0, c->stream>>>(D.n_pd, D.pd_dof.p, D.pd_hist.p, D.pd_value.p, D.pd_mode.p, T,
+                                                                D.time.p, dt, c->ut.p, c->du.p);
+        c->st.kernel_launches++;
+    }
+    c->st.kernel_launches++;
+    }
+    if (!(phases & 2)) return;
+    ElemArgs EA;
+    EA.M = mesh_of(c);
+    EA.Ke = nullptr; EA.Re = c->Re.p; EA.S = c->S.p;
+    k_element_forces<LoadSum><<<c->grid_elem0, 256, 0, c->stream>>>(EA, LoadSum{c->ut.p, c->du.p});
+    DynUpdateArgs U;
+    U.M = EA.M; U.Re = c->Re.p; U.f = D.f.p; U.mass = D.mass.p; U.a = D.a.p; U.v = D.v.p; U.ut = c->ut.p; U.rforce = c->rforce.p;
+    U.du = c->du.p; U.time = D.time.p; U.dt = dt; U.S = c->S.p;
+    k_dyn_gather_update<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(U);
+    c->st.kernel_launches += 2;
+}
+
+// One step in two halves, so that the caller can read (dof_total, dof_increment) where the reference prints the state:
+// after the boundary conditions, before the element forces (explicit_dynamic_step.f90:40-64).  phase 1, then phase 2.
+int en234gpu_dynamic_half_step(en234gpu_handle c, double dt, int phase, int* fail) {
+    CK(cudaSetDevice(c->device));
+    if (!c->dyn.ready) return set_err("dynamic_half_step called before dynamic_setup");
+    if (phase != 1 && phase != 2) return set_err("dynamic_half_step: phase is 1 (predictor + boundary conditions) or 2 (forces + update)");
+    if (!(dt > 0.0)) return set_err("dynamic_half_step: dt must be positive");
+    if (phase == 1) CK(cudaMemsetAsync(&c->S.p->nanflag, 0, sizeof(int), c->stream));
+    dyn_enqueue_step(c, dt, phase);
+    CK(cudaGetLastError());
+    if (read_scalars(c)) return 1;
+    if (fail) *fail = c->hS->nanflag ? 1 : 0;
+    return 0;
+}
+
+// n_steps central-difference steps of size dt from the device-resident state; fail = 1 when a non-finite acceleration or
+// a non-positive Jacobian appeared.  device_ms (may be NULL): CUDA-event time of the steps.
+int en234gpu_dynamic_steps(en234gpu_handle c, double dt, int n_steps, int* fail, double* device_ms) {
+    CK(cudaSetDevice(c->device));
+    auto& D = c->dyn;
+    if (!D.ready) return set_err("dynamic_steps called before dynamic_setup");
+    if (!(dt > 0.0) || n_steps < 0) return set_err("dynamic_steps: dt must be positive");
+    CK(cudaMemsetAsync(&c->S.p->nanflag, 0, sizeof(int), c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    int left = n_steps;
+    if (left >= 2 * DYN_CHUNK) {
+        if (D.graph && D.graph_dt != dt) { cudaGraphExecDestroy(D.graph); D.graph = nullptr; }
+        if (!D.graph) {
+            cudaGraph_t g = nullptr;
+            const long long before = c->st.kernel_launches;
+            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            for (int s = 0; s < DYN_CHUNK; ++s) dyn_enqueue_step(c, dt);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            D.graph_launches = c->st.kernel_launches - before;
+            c->st.kernel_launches = before;
+            if (e != cudaSuccess) return set_err(std::string("dynamic_steps: cudaStreamEndCapture: ") + cudaGetErrorString(e));
+            CK(cudaGraphInstantiate(&D.graph, g, 0));
+            CK(cudaGraphDestroy(g));
+            D.graph_dt = dt;
+        }
+        for (; left >= DYN_CHUNK; left -= DYN_CHUNK) {
+            CK(cudaGraphLaunch(D.graph, c->stream));
+            c->st.kernel_launches += D.graph_launches;
+        }
+    }
+    for (; left > 0; --left) dyn_enqueue_step(c, dt);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if (read_scalars(c)) return 1;
+    if (fail) *fail = c->hS->nanflag ? 1 : 0;
+    if (device_ms) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        *device_ms = ms;
+    }
+    return 0;
+}
+
+int en234gpu_dynamic_get_state(en234gpu_handle c, double* dof_total, double* dof_increment, double* velocity,
+                               double* acceleration, double* rforce, double* lumped_mass, double* time) {
+    CK(cudaSetDevice(c->device));
+    auto& D = c->dyn;
+    if (!D.ready) return set_err("dynamic_get_state called before dynamic_setup");
+    const size_t b = (size_t)c->ndof * sizeof(double);
+    auto get = [&](double* dst, const double* src) -> cudaError_t {
+        return dst ? cudaMemcpyAsync(dst, src, b, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
+    };
+    CK(get(dof_total, c->ut.p)); CK(get(dof_increment, c->du.p)); CK(get(velocity, D.v.p)); CK(get(acceleration, D.a.p));
+    CK(get(rforce, c->rforce.p)); CK(get(lumped_mass, D.mass.p));
+    if (time) CK(cudaMemcpyAsync(time, D.time.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 // Single-element evaluation on the device for the host-callable twins of the reference's element routines

@@ -7,6 +7,7 @@
 #include "../../../include/en234host.h"
 #include "loads.h"
 #include "model.h"
+#include "explicit_dynamic_step.h"
 #include "print_state.h"
 #include "staticstep.h"
 
@@ -97,6 +98,10 @@ static void flatten(en234host_model& w) {
     I["max_newton_iterations"] = {m.max_newton_iterations}; I["unsymmetric"] = {m.unsymmetric_stiffness ? 1 : 0};
     I["abaqusformat"] = {m.abaqusformat ? 1 : 0}; I["max_cg_iterations"] = {m.max_cg_iterations};
     I["checkstiffness_flag"] = {m.checkstiffness_flag};
+    D["element_density"] = m.element_density;
+    D["element_density"].resize(m.n_elements, 0.0);
+    I["explicitdynamicstep"] = {m.explicitdynamicstep ? 1 : 0}; I["no_dynamic_steps"] = {m.no_dynamic_steps};
+    D["dynamic_timestep"] = {m.dynamic_timestep};
     D["timestep_initial"] = {m.timestep_initial}; D["timestep_min"] = {m.timestep_min};
     D["timestep_max"] = {m.timestep_max}; D["max_total_time"] = {m.max_total_time};
     D["newtonraphson_tolerance"] = {m.newtonraphson_tolerance}; D["cg_tolerance"] = {m.cg_tolerance};
@@ -279,6 +284,32 @@ int en234host_print_state(en234host_model_t w, en234gpu_handle h, double time_en
     std::fclose(f);
     if (rc) g_err = err;
     return rc;
+}
+
+int en234host_run_dynamic(en234host_model_t w, en234gpu_handle h, int n_steps, const double* initial_velocity,
+                          double* dof_total, double* velocity, double* acceleration, double* rforce, double* lumped_mass,
+                          long long* info, double* device_ms) {
+    FILE* sp = nullptr;
+    if (w->m.stateprint && !w->m.state_print_path.empty()) {
+        sp = std::fopen(w->m.state_print_path.c_str(), "w");
+        if (!sp) { g_err = "cannot open state print file " + w->m.state_print_path; return -1; }
+    }
+    en234gpu_stats st0{}, st1{};
+    en234gpu_get_stats(h, &st0);
+    DynamicResult r;
+    const int rc = explicit_dynamic_step(w->m, h, n_steps, initial_velocity, sp, r);
+    if (sp) std::fclose(sp);
+    if (rc) { g_err = r.error; return rc; }
+    en234gpu_get_stats(h, &st1);
+    const size_t b = (size_t)w->m.ndof() * sizeof(double);
+    if (dof_total) std::memcpy(dof_total, r.dof_total.data(), b);
+    if (velocity) std::memcpy(velocity, r.velocity.data(), b);
+    if (acceleration) std::memcpy(acceleration, r.acceleration.data(), b);
+    if (rforce) std::memcpy(rforce, r.rforce.data(), b);
+    if (lumped_mass) std::memcpy(lumped_mass, r.lumped_mass.data(), b);
+    if (info) { info[0] = r.steps; info[1] = r.n_state_prints; info[2] = st1.kernel_launches - st0.kernel_launches; }
+    if (device_ms) *device_ms = r.device_ms;
+    return 0;
 }
 
 int en234host_run_static(en234host_model_t w, en234gpu_handle h, int method, double cg_tolerance,

@@ -205,4 +205,110 @@ void evaluate_loads(const Model& m, double time, double dtime, const double* dof
     }
 }
 
+bool dynamic_load_tables(const Model& m, DynamicLoads& out) {
+    out = DynamicLoads();
+    const size_t nd = (size_t)m.ndof();
+    for (const History& h : m.histories) {
+        out.history_time.insert(out.history_time.end(), h.t.begin(), h.t.end());
+        out.history_value.insert(out.history_value.end(), h.v.begin(), h.v.end());
+        out.history_ptr.push_back((int)out.history_time.size());
+    }
+    out.element_density.assign(m.n_elements, 0.0);
+    for (int e = 0; e < m.n_elements; ++e) {
+        if (m.element_flag[e] > 99999) {                              // VUEL: amass = amass*props(3) (abaqus_vuel.for:208)
+            if (m.element_n_props[e] < 3) { out.error = "a VUEL element needs three properties (E, nu, density)"; return false; }
+            out.element_density[e] = m.element_properties[m.element_prop_index[e] + 2];
+        } else {
+            out.element_density[e] = e < (int)m.element_density.size() ? m.element_density[e] : 0.0;
+            if (out.element_density[e] == 0.0) { out.error = "a density has not been defined for element number " + std::to_string(e + 1); return false; }
+        }
+    }
+    std::vector<double> dense(nd);
+    auto push_load = [&](int history, double constant) {
+        for (size_t d = 0; d < nd; ++d)
+            if (dense[d] != 0.0) { out.load_dof.push_back((int)d); out.load_val.push_back(dense[d]); }
+        out.load_ptr.push_back((int)out.load_dof.size());
+        out.load_history.push_back(history);
+        out.load_constant.push_back(constant);
+    };
+    const bool last_has_history = !m.distributed_loads.empty() && m.distributed_loads.back().history_number > 0;
+    for (const auto& d : m.distributed_loads) {
+        std::fill(dense.begin(), dense.end(), 0.0);
+        const NamedSet& es = m.elementsets[d.element_set - 1];
+        int history = 0;
+        double constant = 1.0;
+        for (int e1 : es.items) {
+            const int lmn = e1 - 1;
+            int nodes[4];
+            double fc[4][3];
+            if (m.element_flag[lmn] > 99999) {
+                // VUEL, lflags(3) = 3 (:806-905): RHS -= N2(i) adlmag norm(1:3) w; adlmag = history(TIME+DTIME) when the LAST
+                // load of the list has a history (:880), else the load's value
+                if (!d.uel_format) { out.error = "a native distributed load was applied to a VUEL element"; return false; }
+                if (last_has_history) {
+                    if (d.history_number <= 0) { out.error = "distributed load without a history while the last load has one (explicit_dynamic_step.f90:880)"; return false; }
+                    history = d.history_number;
+                } else constant = d.values.empty() ? 0.0 : d.values[0];
+                face_coords(m, lmn, d.flag < 0 ? -d.flag : d.flag, nodes, fc);
+                for (int kint = 0; kint < 4; ++kint) {
+                    FacePoint fp;
+                    face_point(fc, kint, fp);
+                    for (int i = 0; i < 4; ++i)
+                        for (int c = 0; c < 3; ++c) dense[3 * (size_t)nodes[i] + c] -= fp.N[i] * fp.norm[c];
+                }
+            } else {
+                if (d.uel_format) { out.error = "an ABAQUS-format distributed load was applied to a native element"; return false; }
+                if (d.flag >= 4) { out.error = "SUBROUTINE distributed loads are not supported in explicit dynamics"; return false; }
+                double tr[3] = {0, 0, 0};
+                if (d.flag < 3) for (size_t i = 0; i < d.values.size() && i < 3; ++i) tr[i] = d.values[i];
+                else tr[0] = 1.0;
+                if (d.flag == 2) {
+                    const double nr = std::sqrt(tr[0] * tr[0] + tr[1] * tr[1] + tr[2] * tr[2]);
+                    for (double& t : tr) t /= nr;
+                }
+                if (d.flag > 1) history = d.history_number;
+                face_coords(m, lmn, d.face, nodes, fc);
+                for (int kint = 0; kint < 4; ++kint) {
+                    FacePoint fp;
+                    face_point(fc, kint, fp);
+                    const double det = std::sqrt(fp.norm[0] * fp.norm[0] + fp.norm[1] * fp.norm[1] + fp.norm[2] * fp.norm[2]);
+                    for (int a = 0; a < 4; ++a) {
+                        if (d.flag < 3) for (int c = 0; c < 3; ++c) dense[3 * (size_t)nodes[a] + c] += fp.N[a] * tr[c] * det;
+                        // normal load as traction_boundarycondition_dynamic writes it (traction_boundarycondition.f90:186-192)
+                        // with the caller's traction = (value, 0, 0): only the first component receives a force
+                        else dense[3 * (size_t)nodes[a]] += fp.N[a] * tr[0] * fp.norm[0];
+                    }
+                }
+            }
+        }
+        push_load(history, constant);
+    }
+    for (const auto& p : m.prescribed_forces) {                       // :1029-1063
+        if (p.flag == 3) { out.error = "SUBROUTINE prescribed forces are not supported in explicit dynamics"; return false; }
+        std::fill(dense.begin(), dense.end(), 0.0);
+        auto addf = [&](int n) { dense[3 * (size_t)(n - 1) + p.dof - 1] += 1.0; };
+        if (p.node_set == 0) addf(p.node_number);
+        else for (int n : m.nodesets[p.node_set - 1].items) addf(n);
+        push_load(p.flag == 2 ? p.history_number : 0, p.flag == 1 ? p.value : 1.0);
+    }
+    std::vector<int> slot(nd, -1);                                    // :1064-1110, later entries overwrite earlier ones
+    for (const auto& p : m.prescribed_dofs) {
+        if (p.flag == 3) { out.error = "SUBROUTINE prescribed DOFs are not supported in explicit dynamics"; return false; }
+        auto one = [&](int n, int mode) {
+            const size_t d = 3 * (size_t)(n - 1) + p.dof - 1;
+            if (slot[d] < 0) {
+                slot[d] = (int)out.pdof_dof.size();
+                out.pdof_dof.push_back((int)d); out.pdof_history.push_back(0); out.pdof_value.push_back(0.0); out.pdof_mode.push_back(0);
+            }
+            const int k = slot[d];
+            out.pdof_history[k] = p.flag == 2 ? p.history_number : 0;
+            out.pdof_value[k] = p.flag == 1 ? p.value : 0.0;
+            out.pdof_mode[k] = mode;
+        };
+        if (p.node_set == 0) one(p.node_number, p.rate_flag == 0 ? 0 : 2);     // single node, rate: du = value (:1073-1088)
+        else for (int n : m.nodesets[p.node_set - 1].items) one(n, p.rate_flag == 0 ? 0 : 1);
+    }
+    return true;
+}
+
 }  // namespace en234

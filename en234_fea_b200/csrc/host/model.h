@@ -48,6 +48,7 @@ struct Model {
     std::vector<int> element_flag, element_prop_index, element_n_props, element_n_states;
     std::vector<double> element_properties;
     std::vector<ElementGroup> groups;
+    std::vector<double> element_density;   // DENSITY of the ELEMENTS block in force when the element was read (0: none)
     // MATERIAL blocks + ELEMENTS, INTERNAL (C3D8 + UMAT, element flag 10003): parsed so that the reference's golden
     // input can be read, but not part of the GPU hot path — en234gpu_create rejects flag 10003.
     struct MaterialDef { std::string name; int n_states = 0, prop_index = 0, n_props = 0; };
@@ -82,6 +83,10 @@ struct Model {
     double displacementscalefactor = 1.0;
     std::vector<std::string> field_variable_names;
     std::string state_print_path;          // run-time: where run_static writes the state prints ("" = state prints off)
+    // EXPLICIT DYNAMIC STEP (read_input_file.f90:1920-1966, modules/Dynamicstepparameters.f90)
+    bool explicitdynamicstep = false;
+    double dynamic_timestep = 0.0;
+    int no_dynamic_steps = 0;
     // run-time solver options that are compile-time parameters in modules/Stiffness.f90:35-37
     double cg_tolerance = 1e-17;
     int max_cg_iterations = 1000;

@@ -144,6 +144,7 @@ bool parse_elements_user(Reader& r) {
     Model& m = r.m;
     Line L;
     int nnod = 0, nsvar = 0, lmntyp = 0, prop_index = 0, nprops = 0;
+    double density = 0.0;
     while (r.next(L)) {
         if (kw(L.tok[0], "PARAM")) {                                   // :530-564
             if (L.n() != 4 || L.typ[1] != 0 || L.typ[2] != 0)
@@ -151,11 +152,13 @@ bool parse_elements_user(Reader& r) {
             nnod = to_int(L.tok[1]);
             nsvar = to_int(L.tok[2]);
             if (L.typ[3] == 0) lmntyp = to_int(L.tok[3]);
-            else if (kw(L.tok[3], "VU")) return r.fail("ABAQUS VUEL (explicit dynamics) is outside the hot path", &L);
+            else if (kw(L.tok[3], "VU")) { m.abaqusformat = true; lmntyp = to_int(L.tok[3].substr(2)) + 99999; }   // :551-555
             else if (kw(L.tok[3], "U")) { m.abaqusformat = true; lmntyp = to_int(L.tok[3].substr(1)) + 99999; }
             else return r.fail("element identifier must be an integer or Un", &L);
             if (nnod != 8) return r.fail("only 8-node brick elements are supported on the GPU hot path", &L);
-        } else if (kw(L.tok[0], "DENS")) {
+        } else if (kw(L.tok[0], "DENS")) {                             // :565-574
+            if (L.n() < 2 || L.typ[1] > 1) return r.fail("expecting density value following DENSITY key", &L);
+            density = to_real(L.tok[1]);
         } else if (kw(L.tok[0], "PROP")) {                             // :575-607
             prop_index = (int)m.element_properties.size();
             nprops = 0;
@@ -189,6 +192,8 @@ bool parse_elements_user(Reader& r) {
                 m.element_prop_index.push_back(prop_index);
                 m.element_n_props.push_back(nprops);
                 m.element_n_states.push_back(nsvar);
+                m.element_density.resize(m.n_elements, 0.0);
+                m.element_density.push_back(density);
                 m.n_elements++;
             }
             g.n_elements = m.n_elements - g.first_element;
@@ -459,6 +464,70 @@ bool parse_boundary(Reader& r) {
     return r.fail("BOUNDARY CONDITIONS block not terminated");
 }
 
+// PRINT STATE block (read_input_file.f90:1772-1866 in a static step, :1987-2080 in an explicit dynamic step); L holds the
+// PRINT STATE line
+bool parse_print_state(Reader& r, Line& L) {
+    Model& m = r.m;
+    if (L.n() != 2 || L.typ[1] != 2) return r.fail("expecting a file name following PRINT STATE key", &L);
+    m.stateprint = true;
+    m.state_print_filename = L.tok[1];
+    while (true) {
+        if (!r.next(L)) return r.fail("PRINT STATE block not terminated");
+        if (kw(L.tok[0], "ENDPRINTS")) return true;
+        if (L.typ[0] < 2) return r.fail("unrecognized option in PRINT STATE", &L);
+        if (kw(L.tok[0], "DEGREE")) m.print_dof = true;
+        if (kw(L.tok[0], "DISPLACEDM")) m.print_displacedmesh = true;
+        if (kw(L.tok[0], "DISPLACEMENTS")) {
+            if (L.n() < 2 || L.typ[1] == 2) return r.fail("expecting value for displacement scale factor", &L);
+            m.displacementscalefactor = to_real(L.tok[1]);
+        }
+        if (kw(L.tok[0], "FIELD")) {
+            if (L.n() < 2) return r.fail("expecting names of field variables", &L);
+            // names are stored from slot 1 on every FIELD VARIABLES line (field_variable_names(k-1), :1830-1833)
+            for (int k = 1; k < L.n(); ++k) {
+                if ((int)m.field_variable_names.size() < k) m.field_variable_names.resize(k);
+                m.field_variable_names[k - 1] = L.tok[k];
+            }
+        }
+        if (kw(L.tok[0], "ZONES")) {                           // single-zone meshes: the list is read and ignored
+            if (!skip_block(r, "ENDZ")) return false;
+        }
+    }
+}
+
+// EXPLICIT DYNAMIC STEP block (read_input_file.f90:1920-2103)
+bool parse_explicit_dynamic_step(Reader& r) {
+    Model& m = r.m;
+    Line L;
+    m.explicitdynamicstep = true;
+    m.use_lumped_projection_matrix = true;                             // :1922
+    while (r.next(L)) {
+        if (kw(L.tok[0], "ENDEXP")) {
+            if (m.dynamic_timestep == 0.0) return r.fail("a value must be provided for the TIME STEP in an explicit dynamic analysis");
+            if (m.no_dynamic_steps == 0) return r.fail("a value must be provided for the NUMBER OF STEPS in an explicit dynamic analysis");
+            for (int f : m.element_flag)
+                if (f == 10003) return r.fail("explicit dynamics with built-in continuum elements (VUMAT) is outside the supported subset");
+            if (!m.abaqusformat)
+                for (double d : m.element_density)
+                    if (d == 0.0) return r.fail("densities must be specified for an explicit dynamic analysis");
+            return true;
+        } else if (kw(L.tok[0], "TIMESTEP")) {
+            if (L.n() != 2 || L.typ[1] > 1) return r.fail("expecting value for a TIME STEP", &L);
+            m.dynamic_timestep = to_real(L.tok[1]);
+        } else if (kw(L.tok[0], "NUMB")) {
+            if (L.n() != 2 || L.typ[1] != 0) return r.fail("expecting value for NUMBER OF STEPS", &L);
+            m.no_dynamic_steps = to_int(L.tok[1]);
+        } else if (kw(L.tok[0], "STATEPRINTS")) {
+            if (L.n() != 2 || L.typ[1] != 0) return r.fail("expecting value for STATE PRINT STEPS", &L);
+            m.state_print_steps = to_int(L.tok[1]);
+        } else if (kw(L.tok[0], "USERPRINTST")) {
+        } else if (kw(L.tok[0], "PRINTST")) { if (!parse_print_state(r, L)) return false; }
+        else if (kw(L.tok[0], "USERPRINTPA") || kw(L.tok[0], "USERPRINTFI")) { if (!skip_block(r, "ENDU")) return false; }
+        else return r.fail("unknown key in EXPLICIT DYNAMIC STEP block", &L);
+    }
+    return r.fail("EXPLICIT DYNAMIC STEP block not terminated");
+}
+
 bool parse_static_step(Reader& r) {
     Model& m = r.m;
     Line L;
@@ -503,33 +572,7 @@ bool parse_static_step(Reader& r) {
             m.cg_tolerance = to_real(L.tok[1]);
         } else if (kw(L.tok[0], "CGMAXIT")) {                          // extension: run-time max_cg_iterations (Stiffness.f90:37)
             m.max_cg_iterations = to_int(L.tok[1]);
-        } else if (kw(L.tok[0], "PRINTST")) {                          // :1772-1866
-            if (L.n() != 2 || L.typ[1] != 2) return r.fail("expecting a file name following PRINT STATE key", &L);
-            m.stateprint = true;
-            m.state_print_filename = L.tok[1];
-            while (true) {
-                if (!r.next(L)) return r.fail("PRINT STATE block not terminated");
-                if (kw(L.tok[0], "ENDPRINTS")) break;
-                if (L.typ[0] < 2) return r.fail("unrecognized option in PRINT STATE in a STATIC STEP", &L);
-                if (kw(L.tok[0], "DEGREE")) m.print_dof = true;
-                if (kw(L.tok[0], "DISPLACEDM")) m.print_displacedmesh = true;
-                if (kw(L.tok[0], "DISPLACEMENTS")) {
-                    if (L.n() < 2 || L.typ[1] == 2) return r.fail("expecting value for displacement scale factor", &L);
-                    m.displacementscalefactor = to_real(L.tok[1]);
-                }
-                if (kw(L.tok[0], "FIELD")) {
-                    if (L.n() < 2) return r.fail("expecting names of field variables", &L);
-                    // names are stored from slot 1 on every FIELD VARIABLES line (field_variable_names(k-1), :1830-1833)
-                    for (int k = 1; k < L.n(); ++k) {
-                        if ((int)m.field_variable_names.size() < k) m.field_variable_names.resize(k);
-                        m.field_variable_names[k - 1] = L.tok[k];
-                    }
-                }
-                if (kw(L.tok[0], "ZONES")) {                           // single-zone meshes: the list is read and ignored
-                    if (!skip_block(r, "ENDZ")) return false;
-                }
-            }
-        }
+        } else if (kw(L.tok[0], "PRINTST")) { if (!parse_print_state(r, L)) return false; }
         else if (kw(L.tok[0], "USERPRINTPA") || kw(L.tok[0], "USERPRINTFI")) { if (!skip_block(r, "ENDU")) return false; }
         else return r.fail("unknown key in STATIC STEP block", &L);
     }
@@ -549,11 +592,12 @@ bool parse_stream(std::istream& in, Model& m) {
                 else if (kw(L.tok[1], "U")) m.checkstiffness_flag = to_int(L.tok[1].substr(1)) + 99999;
             }
         } else if (kw(L.tok[0], "STATICSTEP")) { if (!parse_static_step(r)) return false; }
-        else if (kw(L.tok[0], "EXPLICITDYNAMICSTEP")) return r.fail("EXPLICIT DYNAMIC STEP is outside the hot path", &L);
+        else if (kw(L.tok[0], "EXPLICITDYNAMICSTEP")) { if (!parse_explicit_dynamic_step(r)) return false; }
         else if (kw(L.tok[0], "STOP")) break;
         else return r.fail("unknown top-level key", &L);
     }
     if (m.n_nodes == 0 || m.n_elements == 0) return r.fail("no mesh was defined");
+    m.element_density.resize(m.n_elements, 0.0);
     for (int c : m.connectivity)
         if (c < 1 || c > m.n_nodes) return r.fail("connectivity refers to a node that does not exist");
     return true;

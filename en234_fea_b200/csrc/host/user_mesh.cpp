@@ -135,8 +135,11 @@ std::string write_input_text(const Model& m) {
     for (const auto& g : m.groups) {
         if (g.flag == 10003) continue;
         o << "  PARAMETERS, 8, " << g.n_states << ", ";
-        if (g.flag > 99999) o << "U" << g.flag - 99999; else o << g.flag;
-        o << "\n  PROPERTIES\n";
+        if (g.flag > 99999) o << (m.explicitdynamicstep ? "VU" : "U") << g.flag - 99999; else o << g.flag;
+        o << "\n";
+        if (g.first_element < (int)m.element_density.size() && m.element_density[g.first_element] != 0.0)
+            o << "  DENSITY, " << m.element_density[g.first_element] << "\n";
+        o << "  PROPERTIES\n";
         for (int k = 0; k < g.n_props; ++k) o << "   " << m.element_properties[g.prop_index + k] << "\n";
         o << "  END PROPERTIES\n  CONNECTIVITY, " << (g.zone.empty() ? "zone" : g.zone) << "\n";
         for (int e = g.first_element; e < g.first_element + g.n_elements; ++e) {
@@ -204,6 +207,17 @@ std::string write_input_text(const Model& m) {
         o << " END DISTRIBUTED LOADS\n";
     }
     o << "END BOUNDARY CONDITIONS\n";
+    auto put_print_state = [&]() {
+        o << " PRINT STATE, " << m.state_print_filename << "\n";
+        if (m.print_dof) o << "  DEGREES OF FREEDOM\n";
+        if (!m.field_variable_names.empty()) {
+            o << "  FIELD VARIABLES";
+            for (const std::string& nm : m.field_variable_names) o << ", " << nm;
+            o << "\n";
+        }
+        if (m.print_displacedmesh) o << "  DISPLACED MESH\n";
+        o << "  DISPLACEMENT SCALE FACTOR, " << m.displacementscalefactor << "\n END PRINT STATE\n";
+    };
     if (m.staticstep) {
         o << "STATIC STEP\n INITIAL TIME STEP, " << m.timestep_initial << "\n MAX TIME STEP, " << m.timestep_max
           << "\n MIN TIME STEP, " << m.timestep_min << "\n MAX NUMBER OF STEPS, " << m.max_no_steps
@@ -214,17 +228,18 @@ std::string write_input_text(const Model& m) {
         if (m.unsymmetric_stiffness) o << ", UNSYMMETRIC";
         o << "\n CG TOLERANCE, " << m.cg_tolerance << "\n CG MAX ITERATIONS, " << m.max_cg_iterations << "\n";
         if (m.stateprint) {
-            o << " STATE PRINT STEPS, " << m.state_print_steps << "\n PRINT STATE, " << m.state_print_filename << "\n";
-            if (m.print_dof) o << "  DEGREES OF FREEDOM\n";
-            if (!m.field_variable_names.empty()) {
-                o << "  FIELD VARIABLES";
-                for (const std::string& nm : m.field_variable_names) o << ", " << nm;
-                o << "\n";
-            }
-            if (m.print_displacedmesh) o << "  DISPLACED MESH\n";
-            o << "  DISPLACEMENT SCALE FACTOR, " << m.displacementscalefactor << "\n END PRINT STATE\n";
+            o << " STATE PRINT STEPS, " << m.state_print_steps << "\n";
+            put_print_state();
         }
         o << "END STATIC STEP\n";
+    }
+    if (m.explicitdynamicstep) {
+        o << "EXPLICIT DYNAMIC STEP\n TIME STEP, " << m.dynamic_timestep << "\n NUMBER OF STEPS, " << m.no_dynamic_steps << "\n";
+        if (m.stateprint) {
+            o << " STATE PRINT STEPS, " << m.state_print_steps << "\n";
+            put_print_state();
+        }
+        o << "END EXPLICIT DYNAMIC STEP\n";
     }
     o << "STOP\n";
     return o.str();

@@ -158,6 +158,39 @@ int en234gpu_project_fields(en234gpu_handle h, int n_fields, const int* field_co
                             int max_iterations, const double* dof_total, const double* dof_increment, double* fields,
                             int* iterations);
 
+/* ---- explicit dynamic step (src/explicit_dynamic_step.f90:1-83): central differences with the row-sum lumped mass matrix.
+ * The element loop of assemble_dynamic_force (:394-718) is the residual half of the static element loop, so the device path
+ * reuses the residual-only element kernel; time, displacement, velocity, acceleration stay on the device and a chunk of
+ * steps runs without a host round trip (16 steps per CUDA graph).  Linear elastic hex8 elements (1001 with a DENSITY, or the
+ * VUEL of user_codes/src/abaqus_vuel.for whose third property is the density); one device.
+ * en234gpu_dynamic_setup replaces assemble_lumped_mass (:85-392; computed once: it depends on geometry and density only)
+ * and takes the time-independent part of apply_dynamic_boundaryconditions (:720-1128):
+ *   element_density[n_elements];
+ *   history tables as CSR (history_ptr[n_histories + 1], time / value pairs; Boundaryconditions.f90:4-20), 1-based ids;
+ *   loads: CSR of (0-based DOF, nodal force of a unit magnitude) with DISTINCT DOFs inside one load, applied in order as
+ *          f[dof] += scale * value with scale = history(TIME + DTIME) when load_history[l] > 0, else load_constant[l];
+ *   prescribed DOFs (distinct): value = history(TIME + DTIME) when pdof_history[k] > 0 else pdof_value[k];
+ *          pdof_mode 0: dof_increment = value - dof_total (:1086, :1102), 1: dof_increment = DTIME * value (:1104),
+ *          2: dof_increment = value (rate flag on a single node, :1080-1086).
+ * The state starts at zero; en234gpu_dynamic_set_state overrides it (NULL = zeros; velocity is what the reference takes from
+ * dof_increment at :30). */
+int en234gpu_dynamic_setup(en234gpu_handle h, const double* element_density, int n_histories, const int* history_ptr,
+                           const double* history_time, const double* history_value, int n_loads, const int* load_ptr,
+                           const int* load_dof, const double* load_val, const int* load_history, const double* load_constant,
+                           int n_pdof, const int* pdof_dof, const int* pdof_history, const double* pdof_value,
+                           const int* pdof_mode);
+int en234gpu_dynamic_set_state(en234gpu_handle h, const double* dof_total, const double* velocity, const double* acceleration,
+                               double time);
+/* n_steps whole steps (:36-70 without the prints); fail = 1: non-finite acceleration or non-positive Jacobian;
+ * device_ms (may be NULL): CUDA-event time of the steps */
+int en234gpu_dynamic_steps(en234gpu_handle h, double dt, int n_steps, int* fail, double* device_ms);
+/* one step in two halves — phase 1: predictor + boundary conditions (:38-43), phase 2: element forces + update (:64-70) —
+ * so that the state can be read where the reference prints it (:45-53) */
+int en234gpu_dynamic_half_step(en234gpu_handle h, double dt, int phase, int* fail);
+/* any pointer may be NULL; rforce is the last step's total nodal force (external + internal) */
+int en234gpu_dynamic_get_state(en234gpu_handle h, double* dof_total, double* dof_increment, double* velocity,
+                               double* acceleration, double* rforce, double* lumped_mass, double* time);
+
 /* ---- inspection (parity tests, reports) */
 long long en234gpu_nnz_blocks(en234gpu_handle h);
 /* Scalar CSR view of the current system matrix: rowptr[3N+1] (64-bit), col[9*nnzb] (0-based), val[9*nnzb] */

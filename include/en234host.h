@@ -104,6 +104,17 @@ int en234host_project_fields(en234host_model_t m, en234gpu_handle h, const char*
 int en234host_print_state(en234host_model_t m, en234gpu_handle h, double time_end, const double* dof_total,
                           const double* dof_increment /*NULL: zero*/, const char* path, int append);
 
+/* explicit_dynamic_step (src/explicit_dynamic_step.f90:1-83) for an input with an EXPLICIT DYNAMIC STEP block (TIME STEP,
+ * NUMBER OF STEPS, STATE PRINT STEPS, PRINT STATE; read_input_file.f90:1920-2103): builds the load tables
+ * (apply_dynamic_boundaryconditions), runs no_dynamic_steps steps on the device and writes a state print every
+ * STATE PRINT STEPS-th step at the point of the step where the reference prints (after the boundary conditions, before the
+ * element forces) when a path has been set with en234host_model_set_state_print.  n_steps <= 0: the input's
+ * NUMBER OF STEPS.  initial_velocity may be NULL (the reference starts from velocity = dof_increment = 0).  Outputs may be
+ * NULL.  info[8]: steps done, state prints, kernels launched, 0...; device_ms: CUDA-event time of the steps. */
+int en234host_run_dynamic(en234host_model_t m, en234gpu_handle h, int n_steps, const double* initial_velocity,
+                          double* dof_total, double* velocity, double* acceleration, double* rforce, double* lumped_mass,
+                          long long* info, double* device_ms);
+
 /* check_stiffness (src/checkstiffness.f90): the reference's self-test of an element routine, run through the device twins
  * below — coded stiffness against the numerical derivative of the residual (h = 1e-7), err = sum (K_num - K)^2 / sum K^2
  * (consistent when <= 1e-6), plus the counts of entries the symmetry report flags.  element_flag: as parsed from the

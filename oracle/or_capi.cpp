@@ -39,7 +39,7 @@ int or_model_set_int(void* h, const char* name, const int* p, long n) {
     VI(node_order) VI(dload_flag) VI(dload_elset) VI(dload_face) VI(dload_history) VI(dload_val_ptr)
     SI(n_nodes) SI(n_elements) SI(max_no_steps) SI(solvertype) SI(nonlinear) SI(max_newton_iterations)
     SI(unsymmetric) SI(abaqusformat) SI(max_cg_iterations) SI(gps_renumber) SI(cg_apply_nodal_forces)
-    SI(cg_check_linear)
+    SI(cg_check_linear) SI(explicitdynamicstep) SI(no_dynamic_steps)
 #undef VI
 #undef SI
     return 1;
@@ -51,9 +51,9 @@ int or_model_set_double(void* h, const char* name, const double* p, long n) {
 #define VD(f) if (k == #f) { assign(m.f, p, n); return 0; }
 #define SD(f) if (k == #f) { m.f = p[0]; return 0; }
     VD(coords) VD(element_properties) VD(material_properties) VD(history_time) VD(history_value)
-    VD(pdof_value) VD(pforce_value) VD(dload_values) VD(subparam_values)
+    VD(pdof_value) VD(pforce_value) VD(dload_values) VD(subparam_values) VD(element_density)
     SD(timestep_initial) SD(timestep_min) SD(timestep_max) SD(max_total_time) SD(newtonraphson_tolerance)
-    SD(cg_tolerance)
+    SD(cg_tolerance) SD(dynamic_timestep)
 #undef VD
 #undef SD
     return 1;
@@ -69,6 +69,7 @@ int or_model_finalize(void* h) {
     if (m.element_n_props.empty()) m.element_n_props.assign(E, (int)m.element_properties.size());
     if (m.element_n_states.empty()) m.element_n_states.assign(E, 0);
     if (m.element_material.empty()) m.element_material.assign(E, 0);
+    if (m.element_density.empty()) m.element_density.assign(E, 0.0);
     if (m.history_ptr.empty()) m.history_ptr.assign(1, 0);
     if (m.nodeset_ptr.empty()) m.nodeset_ptr.assign(1, 0);
     if (m.elementset_ptr.empty()) m.elementset_ptr.assign(1, 0);
@@ -181,6 +182,36 @@ int or_print_state(void* model, const double* dof_total, const double* dof_incre
     if (!f) return -1;
     std::fwrite(text.data(), 1, text.size(), f);
     std::fclose(f);
+    return 0;
+}
+
+// ---- explicit dynamics (or_dynamic.cpp) -----------------------------------------------------------
+namespace { struct Dyn { const Model* m; DynamicState s; }; }
+void* or_dynamic_new(void* model, const double* dof_total0, const double* velocity0) {
+    Dyn* d = new Dyn();
+    d->m = (Model*)model;
+    const size_t nd = (size_t)d->m->ndof();
+    d->s.dof_total.assign(nd, 0.0);
+    d->s.dof_increment.assign(nd, 0.0);
+    if (dof_total0) d->s.dof_total.assign(dof_total0, dof_total0 + nd);
+    if (velocity0) d->s.dof_increment.assign(velocity0, velocity0 + nd);     // velocity(1:neq) = dof_increment(1:neq), :30
+    return d;
+}
+void or_dynamic_free(void* h) { delete (Dyn*)h; }
+int or_dynamic_steps(void* h, int n) { Dyn* d = (Dyn*)h; return explicit_dynamic_steps(*d->m, d->s, n); }
+// any pointer may be NULL; time_steps = {TIME, steps done}
+void or_dynamic_get(void* h, double* dof_total, double* dof_increment, double* velocity, double* acceleration, double* rforce,
+                    double* lumped_mass, double* time_steps) {
+    Dyn* d = (Dyn*)h;
+    auto cp = [](double* dst, const std::vector<double>& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(double)); };
+    cp(dof_total, d->s.dof_total); cp(dof_increment, d->s.dof_increment); cp(velocity, d->s.velocity);
+    cp(acceleration, d->s.acceleration); cp(rforce, d->s.rforce); cp(lumped_mass, d->s.lumped_mass);
+    if (time_steps) { time_steps[0] = d->s.time; time_steps[1] = d->s.steps_done; }
+}
+int or_lumped_mass(void* model, double* out) {
+    std::vector<double> l;
+    assemble_lumped_mass(*(Model*)model, l);
+    std::memcpy(out, l.data(), l.size() * sizeof(double));
     return 0;
 }
 

@@ -283,6 +283,52 @@ void traction_boundarycondition_static_3d(int flag, const double* fc12, const do
     }
 }
 
+// traction_boundarycondition_dynamic (src/traction_boundarycondition.f90:102-198), 3-D 4-node face.  flag 1/2 as the static
+// routine; flag 3 (normal) as written there: + traction(1) norm(1), - traction(2) norm(2), - traction(3) norm(3), with the
+// caller's traction vector (explicit_dynamic_step.f90:905-920 passes (dloadvalue, 0, 0): only the first term survives).
+void traction_boundarycondition_dynamic_3d(int flag, const double* fc12, const double* traction3, int ntract, double* R12) {
+    std::memset(R12, 0, sizeof(double) * 12);
+    for (int kint = 0; kint < 4; ++kint) {
+        double xi2[2], N2[4], dN2[4][2], norm[3];
+        face_gauss(kint, xi2);
+        shape_quad4(xi2, N2, dN2);
+        face_normal(fc12, dN2, norm);
+        double det = std::sqrt(norm[0] * norm[0] + norm[1] * norm[1] + norm[2] * norm[2]);
+        if (flag < 3) {
+            for (int k = 0; k < 3; ++k) {
+                double t = k < ntract ? traction3[k] : 0.0;
+                for (int a = 0; a < 4; ++a) R12[3 * a + k] = R12[3 * a + k] + N2[a] * t * 1.0 * det;
+            }
+        } else {
+            for (int a = 0; a < 4; ++a) {
+                R12[3 * a] = R12[3 * a] + N2[a] * traction3[0] * norm[0] * 1.0;
+                R12[3 * a + 1] = R12[3 * a + 1] - N2[a] * traction3[1] * norm[1] * 1.0;
+                R12[3 * a + 2] = R12[3 * a + 2] - N2[a] * traction3[2] * norm[2] * 1.0;
+            }
+        }
+    }
+}
+
+// VUEL distributed load (user_codes/src/abaqus_vuel.for:274-320): RHS(ipoin:ipoin+2) -= N2(i) adlmag norm(1:3) w
+void vuel_pressure_3d(const double* coords24, int face, double adlmag, double* R24) {
+    std::memset(R24, 0, sizeof(double) * 24);
+    int list[4];
+    facenodes_hex8(face < 0 ? -face : face, list);
+    double fc[12];
+    for (int i = 0; i < 4; ++i)
+        for (int c = 0; c < 3; ++c) fc[3 * i + c] = coords24[3 * (list[i] - 1) + c];
+    for (int kint = 0; kint < 4; ++kint) {
+        double xi2[2], N2[4], dN2[4][2], norm[3];
+        face_gauss(kint, xi2);
+        shape_quad4(xi2, N2, dN2);
+        face_normal(fc, dN2, norm);
+        for (int i = 0; i < 4; ++i) {
+            int ip = 3 * (list[i] - 1);
+            for (int c = 0; c < 3; ++c) R24[ip + c] = R24[ip + c] - N2[i] * adlmag * norm[c] * 1.0;
+        }
+    }
+}
+
 // History table interpolation (modules/Boundaryconditions.f90:161-221)
 double interpolate_history_table(const double* t, const double* v, int n, double time) {
     if (n == 1) return v[0];

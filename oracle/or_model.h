@@ -36,6 +36,10 @@ struct Model {
     std::vector<int> material_prop_index, material_n_props;
     std::vector<double> material_properties;
 
+    std::vector<double> element_density;    // densities(element%density_index), 0 if none (explicit dynamics, native elements)
+    int explicitdynamicstep = 0, no_dynamic_steps = 0;   // modules/Dynamicstepparameters.f90
+    double dynamic_timestep = 0.0;
+
     // Boundary conditions (Boundaryconditions.f90:34-66)
     std::vector<int> history_ptr;           // nh+1
     std::vector<double> history_time, history_value;
@@ -107,6 +111,8 @@ int element_static(const Model& m, int lmn /*0-based*/, const double* dof_total,
                    double* svars /*n_states or null*/);
 void traction_boundarycondition_static_3d(int flag, const double* face_coords12,
                                           const double* traction, int ntract, double* R12);
+void traction_boundarycondition_dynamic_3d(int flag, const double* face_coords12, const double* traction3, int ntract, double* R12);
+void vuel_pressure_3d(const double* coords24, int face, double adlmag, double* R24);
 void facenodes_hex8(int face, int list[4]);
 double interpolate_history_table(const double* t, const double* v, int n, double time);
 // Element ids understood by the oracle
@@ -159,6 +165,16 @@ int solve_conjugategradient(const Model& m, CooUpper& c, double* dof_increment, 
 int compute_static_step(const Model& m, std::vector<double>& dof_total, std::vector<double>& rforce,
                         std::vector<double>& svars, StepLog& log);
 
+
+// ---- explicit dynamics (or_dynamic.cpp): src/explicit_dynamic_step.f90 -------------------------------------------
+struct DynamicState {
+    std::vector<double> dof_total, dof_increment, velocity, acceleration, rforce, lumped_mass;
+    double time = 0.0;
+    int steps_done = 0;
+};
+void assemble_lumped_mass(const Model& m, std::vector<double>& lumped_mass);                         // :85-392
+// runs steps [s.steps_done, s.steps_done + n_steps); the first call initialises velocity = dof_increment, acceleration = 0
+int explicit_dynamic_steps(const Model& m, DynamicState& s, int n_steps);
 
 // ---- state print (or_print.cpp): nodal projection of Gauss-point fields + Tecplot file, src/printing.f90:249-1093 ----
 struct PrintOptions {

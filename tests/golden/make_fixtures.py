@@ -69,3 +69,17 @@ open(os.path.join(HERE, "linear_elastic_3d_umat.in"), "w").write(m2.text())
 # (user_prescribeddof): input_files/Abaqus_umat_stretch_rotate.in
 m3 = Model.read(os.path.join(REF, "Abaqus_umat_stretch_rotate.in"))
 open(os.path.join(HERE, "stretch_rotate_3d_umat.in"), "w").write(m3.text())
+# explicit dynamics: the two VUEL inputs (user_codes/src/abaqus_vuel.for), EXPLICIT DYNAMIC STEP blocks with their PRINT STATE
+for src, dst in [("Abaqus_vuel_linear_elastic_3d.in", "linear_elastic_3d_vuel.in"), ("Abaqus_vuel_holeplate_3d.in", "holeplate_3d_vuel.in.gz")]:
+    mv = Model.read(os.path.join(REF, src))
+    text = mv.text()
+    if dst.endswith(".gz"):
+        with gzip.GzipFile(os.path.join(HERE, dst), "wb", mtime=0) as f:
+            f.write(text.encode())
+    else:
+        open(os.path.join(HERE, dst), "w").write(text)
+    a, b = mv.arrays(), Model.from_text(text).arrays()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert mv.state_print() == Model.from_text(text).state_print()
+    print(dst, "nodes", mv.n_nodes, "elements", mv.n_elements, "dt", a["dynamic_timestep"][0], "steps", a["no_dynamic_steps"][0])

@@ -29,6 +29,11 @@ def lib():
         L.or_system_free.argtypes = [C.c_void_p]
         L.or_system_nnz_upper.restype = C.c_long
         L.or_system_nnz_upper.argtypes = [C.c_void_p]
+        L.or_dynamic_new.restype = C.c_void_p
+        L.or_dynamic_new.argtypes = [C.c_void_p, dp, dp]
+        L.or_dynamic_free.argtypes = [C.c_void_p]
+        L.or_dynamic_steps.argtypes = [C.c_void_p, C.c_int]
+        L.or_dynamic_get.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, dp, dp]
         _lib = L
     return _lib
 
@@ -112,6 +117,15 @@ class OracleModel:
                                   C.c_int(flags), C.c_double(scale_factor), C.c_double(time_end), str(path).encode())
         if rc:
             raise RuntimeError("oracle print_state failed rc=%d" % rc)
+
+    def lumped_mass(self):
+        out = np.zeros(self.ndof)
+        lib().or_lumped_mass(self.h, _d(out))
+        return out
+
+    def dynamic(self, dof_total0=None, velocity0=None):
+        """Explicit dynamic step state (src/explicit_dynamic_step.f90); advance with .steps(n), read with .get()."""
+        return OracleDynamic(self, dof_total0, velocity0)
 
     def run_static(self):
         L = lib()
@@ -199,3 +213,31 @@ def check_stiffness(flag, coords24, dof_increment24, dof_total24, props):
     if rc:
         raise RuntimeError("oracle element failed")
     return err.value, asym.value
+
+
+class OracleDynamic:
+    def __init__(self, model, dof_total0=None, velocity0=None):
+        self.model = model
+        u0 = None if dof_total0 is None else np.ascontiguousarray(dof_total0, np.float64)
+        v0 = None if velocity0 is None else np.ascontiguousarray(velocity0, np.float64)
+        self.h = C.c_void_p(lib().or_dynamic_new(model.h, _d(u0), _d(v0)))
+
+    def steps(self, n):
+        rc = lib().or_dynamic_steps(self.h, C.c_int(n))
+        if rc:
+            raise RuntimeError("oracle explicit dynamic step failed rc=%d" % rc)
+        return self
+
+    def get(self):
+        nd = self.model.ndof
+        out = {k: np.zeros(nd) for k in ("dof_total", "dof_increment", "velocity", "acceleration", "rforce", "lumped_mass")}
+        ts = np.zeros(2)
+        lib().or_dynamic_get(self.h, _d(out["dof_total"]), _d(out["dof_increment"]), _d(out["velocity"]), _d(out["acceleration"]),
+                             _d(out["rforce"]), _d(out["lumped_mass"]), _d(ts))
+        out["time"], out["steps"] = float(ts[0]), int(ts[1])
+        return out
+
+    def close(self):
+        if self.h:
+            lib().or_dynamic_free(self.h)
+            self.h = None

@@ -189,8 +189,9 @@ def test_parser_on_reference_files():
     assert set(au["element_flag"]) == {10003} and set(au["element_n_states"]) == {120} and au["unsymmetric"][0] == 1
     assert au["material_properties"].tolist() == [10000.0, 0.3] and au["abaqusformat"][0] == 0
     fx = np.load(os.path.join(GOLDEN, "holeplate_3d_umat_model.npz"))
-    for k in au:
+    for k in fx.files:
         assert np.array_equal(au[k], fx[k]), k
+    assert au["explicitdynamicstep"][0] == 0 and not au["element_density"].any()      # keys added after the fixture was written
     # unsupported paths are rejected with a message, never silently misread
     with pytest.raises(ValueError):
         Model.read(os.path.join(REF_INPUTS, "Abaqus_vumat_linear_elastic_3d.in"))
@@ -544,6 +545,123 @@ END STATIC STEP""")
     assert not Model.from_text(synthetic_block_input(2)).state_print()["stateprint"]
     with pytest.raises(Exception):
         Model.from_text(text.replace("PRINT STATE, Output_files\\contour.dat", "PRINT STATE"))
+
+
+# ---------------------------------------------------------------------------------------------- explicit dynamics
+def dynamic_bar(nx, dt, steps, E=100.0, nu=0.0, rho=1.0, fixed=False, force=0.0):
+    """A bar of nx x 1 x 1 VU1 elements (cubes of side h = 1 / nx: length 1, cross-section h^2), optional end force on x = 1,
+    optional clamp of u_x on x = 0."""
+    t = synthetic_block_input(nx, 1, 1, jitter=0.0, element="U1", props=[E, nu, rho], dynamic=(dt, steps))
+    bc = [" DEGREES OF FREEDOM", "  xmin, 1, VALUE, 0.d0", " END DEGREES OF FREEDOM"] if fixed else []
+    if force:
+        bc += [" FORCES", "  xmax, 1, VALUE, %.17g" % (force / 4.0), " END FORCES"]
+    i0, i1 = t.index("\n DEGREES OF FREEDOM") + 1, t.index("END BOUNDARY CONDITIONS")
+    return t[:i0] + "".join(l + "\n" for l in bc) + t[i1:]
+
+
+def test_explicit_dynamics_oracle_against_an_independent_central_difference_loop():
+    """explicit_dynamic_step.f90:36-70 restated (oracle/or_dynamic.cpp) against a numpy loop built from independent pieces:
+    the stiffness matrix of the static CG path (K u = -internal force for the linear element), the numpy 27-point lumped
+    mass, the history interpolation; prescribed DOF ramp (value - u), nodal force with a history, jittered 3-D block."""
+    text = synthetic_block_input(3, 2, 2, jitter=0.2, element="U1", props=[100.0, 0.3, 2.5], load="stretch", steps=4, dt=0.5,
+                                 dynamic=(2e-3, 40))
+    text = text.replace(" END DEGREES OF FREEDOM", " END DEGREES OF FREEDOM\n FORCES\n  xmax, 3, HISTORY, ramp\n END FORCES")
+    m = Model.from_text(text)
+    a = m.arrays()
+    assert a["explicitdynamicstep"][0] == 1 and a["no_dynamic_steps"][0] == 40 and a["dynamic_timestep"][0] == 2e-3
+    om = ob.OracleModel(a)
+    N, nd = m.n_nodes, 3 * m.n_nodes
+    # independent pieces
+    sys_ = ob.OracleSystem(ob.OracleModel(a, solvertype=2), 2)
+    sys_.assemble(np.zeros(nd), np.zeros(nd), 0.0, 1.0)
+    K, _ = sys_.matrix()
+    X = a["coords"].reshape(-1, 3)
+    conn = a["connectivity"].reshape(-1, 8) - 1
+    g3 = float(np.float32(0.7745966692))
+    x1, w1 = [-g3, 0.0, g3], [0.5555555555, 0.888888888, 0.55555555555]
+    mass = np.zeros(N)
+    for c in conn:
+        for k in range(3):
+            for j in range(3):
+                for i in range(3):
+                    Nn, dN = _hex8_shape(np.array([x1[i], x1[j], x1[k]]))
+                    mass[c] += Nn * Nn.sum() * np.linalg.det(X[c].T @ dN) * w1[i] * w1[j] * w1[k] * 2.5
+    mass = np.repeat(mass, 3)
+    assert np.abs(om.lumped_mass() - mass).max() < 1e-13 * mass.max()
+    ht, hv = a["history_time"], a["history_value"]
+    ramp = lambda t: np.interp(t, ht, hv)
+    xmin = a["nodeset_nodes"][a["nodeset_ptr"][m.find_set("xmin") - 1]:a["nodeset_ptr"][m.find_set("xmin")]] - 1
+    xmax = a["nodeset_nodes"][a["nodeset_ptr"][m.find_set("xmax") - 1]:a["nodeset_ptr"][m.find_set("xmax")]] - 1
+    u, v, acc, t, dt = np.zeros(nd), np.zeros(nd), np.zeros(nd), 0.0, 2e-3
+    for _ in range(40):
+        du = dt * (v + 0.5 * dt * acc)
+        f = np.zeros(nd)
+        f[3 * xmax + 2] += ramp(t + dt)
+        for c in range(3):
+            du[3 * xmin + c] = 0.0 - u[3 * xmin + c]
+        du[3 * xmax] = ramp(t + dt) - u[3 * xmax]
+        f -= K @ (u + du)
+        acc = f / mass
+        v = v + dt * acc
+        u = u + du
+        t += dt
+    got = om.dynamic().steps(25).steps(15).get()                                  # in two batches: the state carries over
+    assert got["steps"] == 40 and abs(got["time"] - t) < 1e-15
+    for k, want in (("dof_total", u), ("velocity", v), ("acceleration", acc)):
+        assert np.abs(got[k] - want).max() < 1e-11 * np.abs(want).max(), k
+
+
+def test_explicit_dynamics_oracle_momentum_and_wave_front():
+    """Physics the central-difference scheme keeps exactly or nearly so: a free bar under a constant end force gains momentum
+    F t (internal forces sum to zero) and no part of it moves ahead of the elastic wave front x = c t, c = sqrt(E / rho);
+    a free bar with a uniform initial velocity translates rigidly."""
+    nx, dt, steps, F = 40, 1e-3, 50, 3.0                                            # h / c = 2.5e-3: dt is 0.4 of the stability limit
+    m = Model.from_text(dynamic_bar(nx, dt, steps, E=100.0, nu=0.0, rho=1.0, force=F))
+    a = m.arrays()
+    om = ob.OracleModel(a)
+    got = om.dynamic().steps(steps).get()
+    mass = got["lumped_mass"]
+    vol = 1.0 / nx ** 2
+    assert abs(mass[0::3].sum() - vol) < 1e-6 * vol                                # volume x density (27-point weights: 1e-9)
+    px = (mass[0::3] * got["velocity"][0::3]).sum()
+    assert abs(px - F * got["time"]) < 1e-11 * F * got["time"]
+    X = a["coords"].reshape(-1, 3)[:, 0]
+    ux = got["dof_total"][0::3]
+    c, t, h = 10.0, got["time"], 1.0 / nx                                         # the force acts on x = 1; front at 1 - c t = 0.5
+    assert np.abs(ux[X > 1.0 - 0.5 * c * t]).min() > 1e-3 * np.abs(ux).max()
+    # ahead of the front only the exponentially small precursor of the discrete scheme (a factor ~7 per element)
+    assert np.abs(ux[X < 1.0 - c * t - 12 * h]).max() < 1e-8 * np.abs(ux).max()
+    m2 = Model.from_text(dynamic_bar(6, 0.01, 50))
+    om2 = ob.OracleModel(m2.arrays())
+    v0 = np.tile([0.3, -0.1, 0.2], m2.n_nodes)
+    g2 = om2.dynamic(velocity0=v0).steps(50).get()
+    assert np.abs(g2["dof_total"] - 0.5 * v0).max() < 1e-13 and np.abs(g2["velocity"] - v0).max() < 1e-13
+
+
+def test_parser_explicit_dynamic_step_and_density():
+    m = golden_model("linear_elastic_3d_vuel.in")
+    a = m.arrays()
+    assert a["explicitdynamicstep"][0] == 1 and a["dynamic_timestep"][0] == 0.01 and a["no_dynamic_steps"][0] == 5
+    assert a["element_flag"].tolist() == [100000, 100000] and a["element_properties"].tolist() == [1000.0, 0.3, 10.0]
+    sp_ = m.state_print()
+    assert sp_["stateprint"] and sp_["lumped"] and sp_["state_print_steps"] == 1       # read_input_file.f90:1922: lumped projection
+    if HAVE_REF:                                                                     # the fixture is a faithful re-emission
+        r = Model.read(os.path.join(REF_INPUTS, "Abaqus_vuel_linear_elastic_3d.in"))
+        for k, v in r.arrays().items():
+            assert np.array_equal(v, a[k]), k
+    # native element with a DENSITY key (read_input_file.f90:565-574): the density in force when the elements are read
+    text = Model.from_text(synthetic_block_input(2, 1, 1, jitter=0.0)).text()
+    text = text.replace("  PARAMETERS, 8, 0, 1001\n", "  PARAMETERS, 8, 0, 1001\n  DENSITY, 2.5d0\n")
+    text = text[:text.index("STATIC STEP")] + "EXPLICIT DYNAMIC STEP\n TIME STEP, 0.01\n NUMBER OF STEPS, 3\nEND EXPLICIT DYNAMIC STEP\nSTOP\n"
+    md = Model.from_text(text)
+    assert md.arrays()["element_density"].tolist() == [2.5, 2.5]
+    assert Model.from_text(md.text()).arrays()["element_density"].tolist() == [2.5, 2.5]
+    om = ob.OracleModel(md.arrays())
+    assert abs(om.lumped_mass()[0::3].sum() - 2 * 0.5 ** 3 * 2.5) < 1e-8                 # two cubes of side 1/2
+    with pytest.raises(ValueError):                                                  # no density: "Densities must be specified" (:1928-1932)
+        Model.from_text(text.replace("  DENSITY, 2.5d0\n", ""))
+    with pytest.raises(ValueError):
+        Model.from_text(text.replace(" TIME STEP, 0.01\n", ""))
 
 
 def test_bench_reference_arm_prints_the_contract_line():

@@ -630,3 +630,83 @@ def test_field_projection_c3d8_state_variables_golden_model():
     wl = om.project_fields(names[:6], ref["dof_total"], svars=ref["state_variables"], lumped=True)
     assert np.abs(lum - wl).max() < 1e-7 * np.abs(wl).max()
     g.close()
+
+
+# ---------------------------------------------------------------------------------------------- explicit dynamics
+def test_explicit_dynamics_matches_oracle_on_a_jittered_block():
+    """explicit_dynamic_step (src/explicit_dynamic_step.f90:1-83) on the device against the oracle's restatement: VUEL
+    elements (density = third property), a prescribed-displacement ramp on x = max, a nodal force history, clamped x = 0;
+    70 steps = four 16-step CUDA graphs + 6 single steps.  The two differ by roundoff only (fused multiply-adds, the scale of a
+    load applied after instead of inside the face integral): 1e-10 of the field maximum."""
+    text = synthetic_block_input(6, 5, 4, jitter=0.2, element="U1", props=[100.0, 0.3, 2.5], load="stretch", steps=4, dt=0.5,
+                                 dynamic=(1e-3, 70))
+    text = text.replace(" END DEGREES OF FREEDOM", " END DEGREES OF FREEDOM\n FORCES\n  xmax, 3, HISTORY, ramp\n END FORCES")
+    m = Model.from_text(text)
+    g = GpuSystem(m)
+    res = g.run_dynamic()
+    ref = ob.OracleModel(m.arrays()).dynamic().steps(70).get()
+    assert res["steps"] == 70 and res["n_state_prints"] == 0
+    assert relmax(res["lumped_mass"], ref["lumped_mass"]) < 1e-13
+    for k in ("dof_total", "velocity", "acceleration"):
+        assert relmax(res[k], ref[k]) < 1e-10, k
+    st = g.dynamic_state()
+    assert abs(st["time"] - ref["time"]) < 1e-15 and relmax(st["dof_increment"], ref["dof_increment"]) < 1e-10
+    # 30 more steps from the device-resident state (single launches: below the graph threshold)
+    fail, ms = g.dynamic_steps(1e-3, 30)
+    assert fail == 0 and ms > 0
+    ref2 = ob.OracleModel(m.arrays()).dynamic().steps(100).get()
+    assert relmax(g.dynamic_state()["dof_total"], ref2["dof_total"]) < 1e-10
+    g.close()
+
+
+def test_explicit_dynamics_vuel_reference_input_with_state_prints(tmp_path):
+    """input_files/Abaqus_vuel_linear_elastic_3d.in as shipped (two VUEL elements, pressure history on face 4 of the end
+    element, u_x = 0 on the left face, 5 steps of 0.01, STATE PRINT STEPS 1 with the lumped projection matrix): final state
+    against the oracle, one Tecplot zone per step written where the reference prints (after the boundary conditions of the
+    step), header time TIME + DTIME."""
+    m = golden_model("linear_elastic_3d_vuel.in")
+    out = tmp_path / "contourplots.dat"
+    sp = m.state_print()
+    m.set_state_print(str(out))
+    g = GpuSystem(m)
+    res = g.run_dynamic()
+    ref = ob.OracleModel(m.arrays()).dynamic().steps(5).get()
+    assert res["steps"] == 5 and res["n_state_prints"] == 5
+    for k in ("dof_total", "velocity", "acceleration", "lumped_mass"):
+        assert relmax(res[k], ref[k]) < 1e-11, k
+    assert abs(res["lumped_mass"][0::3].sum() - 20.0) < 1e-6                       # two unit cubes of density 10
+    lines = out.read_text().splitlines()
+    assert len(lines) == 5 * (2 + 12 + 2)
+    zones = [l for l in lines if l.startswith(" ZONE")]
+    assert zones == [' ZONE, T="  0.%d000D-01" F=FEPOINT, I=   12 J=    2 ET=BRICK' % k for k in (1, 2, 3, 4, 5)]
+    assert lines[0] == " VARIABLES = X,Y,Z,DU1,DU2,DU3,U1,U2,U3," + ",".join(sp["field_variables"])
+    # last zone: printed with (dof_total after 4 steps, predicted increment of step 5); U + DU of every node is the final state
+    last = lines[4 * 16 + 2:4 * 16 + 14]
+    order = list(dict.fromkeys((m.arrays()["connectivity"]).tolist()))
+    for line, node in zip(last, order):
+        v = np.array([float(line[19 * k:19 * k + 19]) for k in range(15)])
+        assert np.allclose(v[3:6] + v[6:9], ref["dof_total"][3 * (node - 1):3 * node], rtol=1e-8, atol=1e-14)
+    g.close()
+
+
+def test_explicit_dynamics_native_element_with_density_and_tractions():
+    """Element 1001 with a DENSITY key (user_element_lumped_mass, el_linelast_3dbasic_dynamic) under the three native
+    distributed-load types of traction_boundarycondition_dynamic — VALUE, HISTORY (normalised direction x history) and NORMAL
+    (as that routine writes it) — against the oracle."""
+    base = Model.from_text(synthetic_block_input(4, 3, 3, jitter=0.15)).text()
+    base = base.replace("  PARAMETERS, 8, 0, 1001\n", "  PARAMETERS, 8, 0, 1001\n  DENSITY, 3.d0\n")
+    head = base[:base.index(" DISTRIBUTED LOADS")]
+    loads = (" HISTORY, pulse\n  0.d0, 0.d0\n  0.02d0, 4.d0\n  1.d0, 4.d0\n END HISTORY\n"
+             " DISTRIBUTED LOADS\n  xmax_el, 4, VALUE, 0.d0, 0.5d0, -1.d0\n  ymax_el, 5, HISTORY, pulse, 1.d0, 1.d0, 0.d0\n"
+             "  zmax_el, 2, NORMAL, pulse\n END DISTRIBUTED LOADS\nEND BOUNDARY CONDITIONS\n")
+    text = head + loads + "EXPLICIT DYNAMIC STEP\n TIME STEP, 5.d-4\n NUMBER OF STEPS, 40\nEND EXPLICIT DYNAMIC STEP\nSTOP\n"
+    m = Model.from_text(text)
+    a = m.arrays()
+    assert a["dload_flag"].tolist() == [1, 2, 3] and a["element_density"].min() == 3.0
+    g = GpuSystem(m)
+    res = g.run_dynamic()
+    ref = ob.OracleModel(a).dynamic().steps(40).get()
+    for k in ("dof_total", "velocity", "acceleration", "lumped_mass"):
+        assert relmax(res[k], ref[k]) < 1e-10, k
+    assert np.abs(res["dof_total"]).max() > 0
+    g.close()

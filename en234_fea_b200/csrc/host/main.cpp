@@ -2,6 +2,7 @@
 //             [--cg-maxit n] [--host-api] [--log file.out] [--device d] [--state-print file | --no-state-print]
 // Plays the role of `program en234fea` (src/main.f90:127-143) for the static step: read the input file, run
 // compute_static_step, report the convergence history.  (The reference hard-codes its input path, main.f90:11-35.)
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -56,6 +57,23 @@ int main(int argc, char** argv) {
             if (en234host_model_set_state_print(m, flags, steps, scale, nullptr, path)) { std::fprintf(stderr, "%s\n", en234host_last_error()); return 1; }
             std::printf(" state prints -> %s\n", path);
         }
+    }
+    en234host_model_int(m, "explicitdynamicstep", &p, &n);
+    if (p[0]) {                                         // EXPLICIT DYNAMIC STEP (main.f90:139 explicit_dynamic_step)
+        std::vector<double> u(3 * (size_t)nn), v(3 * (size_t)nn);
+        long long dinfo[8] = {0};
+        double ms = 0.0;
+        if (en234host_run_dynamic(m, h, 0, nullptr, u.data(), v.data(), nullptr, nullptr, nullptr, dinfo, &ms)) {
+            std::fprintf(stderr, "explicit dynamic step failed: %s\n", en234host_last_error());
+            return 1;
+        }
+        double umax = 0.0, vmax = 0.0;
+        for (size_t d = 0; d < u.size(); ++d) { umax = std::fmax(umax, std::fabs(u[d])); vmax = std::fmax(vmax, std::fabs(v[d])); }
+        std::printf(" explicit dynamic steps %lld, state prints %lld, kernels launched %lld, device ms %.3f\n max |u| %.6e  max |v| %.6e\n",
+                    dinfo[0], dinfo[1], dinfo[2], ms, umax, vmax);
+        en234gpu_destroy(h);
+        en234host_model_free(m);
+        return 0;
     }
     std::vector<double> u(3 * (size_t)nn), rf(3 * (size_t)nn), newton(8 * 4096);
     std::vector<int> cg(4096);

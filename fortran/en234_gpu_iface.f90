@@ -90,6 +90,25 @@ module en234_gpu_iface
             integer(c_int), intent(out)   :: iterations
             integer(c_int)                :: en234gpu_project_fields
         end function
+        ! explicit dynamics (src/explicit_dynamic_step.f90:36-70): n_steps whole central-difference steps on the device after
+        ! en234gpu_dynamic_setup; replaces assemble_lumped_mass / apply_dynamic_boundaryconditions / assemble_dynamic_force
+        function en234gpu_dynamic_steps(h, dt, n_steps, fail, device_ms) bind(C, name='en234gpu_dynamic_steps')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value          :: h
+            real(c_double), value       :: dt
+            integer(c_int), value       :: n_steps
+            integer(c_int), intent(out) :: fail
+            real(c_double), intent(out) :: device_ms
+            integer(c_int)              :: en234gpu_dynamic_steps
+        end function
+        function en234gpu_dynamic_get_state(h, dof_total, dof_increment, velocity, acceleration, rforce, lumped_mass, time) &
+                bind(C, name='en234gpu_dynamic_get_state')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value          :: h
+            real(c_double), intent(out) :: dof_total(*), dof_increment(*), velocity(*), acceleration(*), rforce(*), lumped_mass(*)
+            real(c_double), intent(out) :: time
+            integer(c_int)              :: en234gpu_dynamic_get_state
+        end function
         function en234gpu_last_error() bind(C, name='en234gpu_last_error')
             import :: c_ptr
             type(c_ptr) :: en234gpu_last_error

@@ -59,7 +59,7 @@ HOST_SYMBOLS = [
     "en234host_partition", "en234host_part_free", "en234host_part_int", "en234host_part_owned",
     "en234host_part_gpu_create", "en234host_run_static_part", "en234host_check_stiffness",
     "en234host_model_get_state_print", "en234host_model_set_state_print", "en234host_project_fields", "en234host_print_state",
-    "en234host_run_dynamic",
+    "en234host_run_dynamic", "en234host_run_dynamic_part",
 ]
 # Fortran-linkage twins of the reference plugin entry points (include/en234host.h)
 PLUGIN_SYMBOLS = ["user_element_static_", "uel_"]
@@ -386,9 +386,14 @@ class GpuSystem:
         info = (C.c_longlong * 8)()
         ms = C.c_double()
         v0 = None if initial_velocity is None else _f64(initial_velocity)
-        rc = host_lib().en234host_run_dynamic(self.model.h, self.h, C.c_int(n_steps), _dp(v0), _dp(out["dof_total"]),
-                                              _dp(out["velocity"]), _dp(out["acceleration"]), _dp(out["rforce"]),
-                                              _dp(out["lumped_mass"]), info, C.byref(ms))
+        if self.part is not None:      # rank-local arrays; collective over all ranks
+            rc = host_lib().en234host_run_dynamic_part(self.model.h, self.part.h, self.h, C.c_int(n_steps), _dp(v0),
+                                                       _dp(out["dof_total"]), _dp(out["velocity"]), _dp(out["acceleration"]),
+                                                       _dp(out["rforce"]), _dp(out["lumped_mass"]), info, C.byref(ms))
+        else:
+            rc = host_lib().en234host_run_dynamic(self.model.h, self.h, C.c_int(n_steps), _dp(v0), _dp(out["dof_total"]),
+                                                  _dp(out["velocity"]), _dp(out["acceleration"]), _dp(out["rforce"]),
+                                                  _dp(out["lumped_mass"]), info, C.byref(ms))
         if rc:
             raise RuntimeError("explicit dynamic step failed: " + host_lib().en234host_last_error().decode())
         out.update(steps=int(info[0]), n_state_prints=int(info[1]), kernel_launches=int(info[2]), device_ms=ms.value)

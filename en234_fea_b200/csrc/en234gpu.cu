@@ -1147,7 +1147,6 @@ int en234gpu_dynamic_setup(en234gpu_handle c, const double* element_density, int
                            int n_pdof, const int* pdof_dof, const int* pdof_history, const double* pdof_value,
                            const int* pdof_mode) {
     CK(cudaSetDevice(c->device));
-    if (c->comm.active) return set_err("explicit dynamics runs on one device in this version");
     if (c->any_neo || c->any_c3d8)   // user_element_dynamic knows element 1001 only (user_element.f90:152-181); VUMAT is out of scope
         return set_err("explicit dynamics covers the linear elastic hex8 elements (1001 / VU1) only");
     auto& D = c->dyn;
@@ -1195,6 +1194,8 @@ int en234gpu_dynamic_setup(en234gpu_handle c, const double* element_density, int
     k_dyn_lumped_mass<<<(c->N + 127) / 128, 128, 0, c->stream>>>(mesh_of(c), D.density.p, D.mass.p);
     c->st.kernel_launches++;
     CK(cudaGetLastError());
+    // partitioned runs: interface nodes hold the mass of the local elements only
+    if (c->comm.active && comm_halo_sum(c->comm, D.mass.p, c->stream)) return set_err(comm_error());
     CK(cudaStreamSynchronize(c->stream));
     if (c->Re.n < (size_t)c->E * 24) CK(c->Re.alloc((size_t)c->E * 24));
     if (D.graph) { cudaGraphExecDestroy(D.graph); D.graph = nullptr; }
@@ -1219,7 +1220,7 @@ int en234gpu_dynamic_set_state(en234gpu_handle c, const double* dof_total, const
 }
 
 // phases: 1 = predictor + boundary conditions, 2 = element forces + update, 3 = both (one whole step)
-static void dyn_enqueue_step(en234gpu_ctx* c, double dt, int phases = 3) {
+static int dyn_enqueue_step(en234gpu_ctx* c, double dt, int phases = 3) {
     auto& D = c->dyn;
     const int n = c->ndof;
     const DynTables T{D.hist_ptr.p, D.hist_t.p, D.hist_v.p};
@@ -1240,16 +1241,29 @@ static void dyn_enqueue_step(en234gpu_ctx* c, double dt, int phases = 3) {
     }
     c->st.kernel_launches++;
     }
-    if (!(phases & 2)) return;
+    if (!(phases & 2)) return 0;
     ElemArgs EA;
     EA.M = mesh_of(c);
     EA.Ke = nullptr; EA.Re = c->Re.p; EA.S = c->S.p;
     k_element_forces<LoadSum><<<c->grid_elem0, 256, 0, c->stream>>>(EA, LoadSum{c->ut.p, c->du.p});
+    if (c->comm.active) {
+        // partial element-force sums -> halo sum -> update (the one exchange of a step)
+        GatherArgs G{};
+        G.M = EA.M; G.Re = c->Re.p; G.rhs = c->rhs.p; G.rforce = c->rforce.p; G.partials = c->part.p; G.S = c->S.p;
+        const int np = std::min(MAX_PARTIALS, std::max(1, (c->N + VEC_THREADS - 1) / VEC_THREADS));
+        k_gather_residual<<<np, VEC_THREADS, 0, c->stream>>>(G);
+        if (comm_halo_sum(c->comm, c->rhs.p, c->stream)) return 1;
+        k_dyn_update<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(n, dt, D.f.p, c->rhs.p, D.mass.p, D.a.p, D.v.p, c->ut.p, c->du.p,
+                                                                 c->rforce.p, D.time.p, c->S.p);
+        c->st.kernel_launches += 3 + c->comm.launches_per_halo;
+        return 0;
+    }
     DynUpdateArgs U;
     U.M = EA.M; U.Re = c->Re.p; U.f = D.f.p; U.mass = D.mass.p; U.a = D.a.p; U.v = D.v.p; U.ut = c->ut.p; U.rforce = c->rforce.p;
     U.du = c->du.p; U.time = D.time.p; U.dt = dt; U.S = c->S.p;
     k_dyn_gather_update<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(U);
     c->st.kernel_launches += 2;
+    return 0;
 }
 
 // One step in two halves, so that the caller can read (dof_total, dof_increment) where the reference prints the state:
@@ -1260,10 +1274,12 @@ int en234gpu_dynamic_half_step(en234gpu_handle c, double dt, int phase, int* fai
     if (phase != 1 && phase != 2) return set_err("dynamic_half_step: phase is 1 (predictor + boundary conditions) or 2 (forces + update)");
     if (!(dt > 0.0)) return set_err("dynamic_half_step: dt must be positive");
     if (phase == 1) CK(cudaMemsetAsync(&c->S.p->nanflag, 0, sizeof(int), c->stream));
-    dyn_enqueue_step(c, dt, phase);
+    if (dyn_enqueue_step(c, dt, phase)) return set_err(comm_error());
     CK(cudaGetLastError());
     if (read_scalars(c)) return 1;
-    if (fail) *fail = c->hS->nanflag ? 1 : 0;
+    int bad = c->hS->nanflag;
+    if (c->comm.active && comm_host_max(c->comm, &bad)) return set_err(comm_error());
+    if (fail) *fail = bad ? 1 : 0;
     return 0;
 }
 
@@ -1283,10 +1299,12 @@ int en234gpu_dynamic_steps(en234gpu_handle c, double dt, int n_steps, int* fail,
             cudaGraph_t g = nullptr;
             const long long before = c->st.kernel_launches;
             CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-            for (int s = 0; s < DYN_CHUNK; ++s) dyn_enqueue_step(c, dt);
+            int rc = 0;
+            for (int s = 0; s < DYN_CHUNK && !rc; ++s) rc = dyn_enqueue_step(c, dt);
             cudaError_t e = cudaStreamEndCapture(c->stream, &g);
             D.graph_launches = c->st.kernel_launches - before;
             c->st.kernel_launches = before;
+            if (rc) return set_err(std::string("dynamic_steps: graph capture: ") + comm_error());
             if (e != cudaSuccess) return set_err(std::string("dynamic_steps: cudaStreamEndCapture: ") + cudaGetErrorString(e));
             CK(cudaGraphInstantiate(&D.graph, g, 0));
             CK(cudaGraphDestroy(g));
@@ -1297,11 +1315,14 @@ int en234gpu_dynamic_steps(en234gpu_handle c, double dt, int n_steps, int* fail,
             c->st.kernel_launches += D.graph_launches;
         }
     }
-    for (; left > 0; --left) dyn_enqueue_step(c, dt);
+    for (; left > 0; --left)
+        if (dyn_enqueue_step(c, dt)) return set_err(comm_error());
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev1, c->stream));
     if (read_scalars(c)) return 1;
-    if (fail) *fail = c->hS->nanflag ? 1 : 0;
+    int bad = c->hS->nanflag;
+    if (c->comm.active && comm_host_max(c->comm, &bad)) return set_err(comm_error());
+    if (fail) *fail = bad ? 1 : 0;
     if (device_ms) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));

@@ -105,6 +105,28 @@ __global__ void __launch_bounds__(VEC_THREADS) k_dyn_gather_update(DynUpdateArgs
     if (blockIdx.x == 0 && threadIdx.x == 0) A.time[0] = A.time[0] + A.dt;
 }
 
+// Partitioned runs: the element forces of interface nodes are partial sums, so the gather (k_gather_residual), the halo sum and
+// this update are separate launches.  r = internal forces (halo-summed), f = external forces (full-valued on every copy).
+__global__ void __launch_bounds__(VEC_THREADS) k_dyn_update(int n, double dt, const double* __restrict__ f, const double* __restrict__ r,
+                                                             const double* __restrict__ mass, double* __restrict__ a,
+                                                             double* __restrict__ v, double* __restrict__ ut,
+                                                             const double* __restrict__ du, double* __restrict__ rforce,
+                                                             double* time, CgScalars* S) {
+    bool bad = false;
+    for (int d = blockIdx.x * VEC_THREADS + threadIdx.x; d < n; d += gridDim.x * VEC_THREADS) {
+        const double rf = f[d] + r[d];
+        const double m = mass[d];
+        const double acc = m != 0.0 ? rf / m : 0.0;
+        rforce[d] = rf;
+        a[d] = acc;
+        v[d] = v[d] + dt * acc;
+        ut[d] = ut[d] + du[d];
+        if (acc != acc || acc == acc + 1.0) bad = true;
+    }
+    if (bad) atomicOr(&S->nanflag, 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) time[0] = time[0] + dt;
+}
+
 // assemble_lumped_mass (:85-392): per element the row sums of the 27-point consistent matrix (user_element.f90:380-410 =
 // abaqus_vuel.for:164-208) times the element's density, added per node in ascending element order.  One thread per node.
 __global__ void __launch_bounds__(128) k_dyn_lumped_mass(Mesh M, const double* __restrict__ density, double* __restrict__ mass) {

@@ -2,6 +2,7 @@
 // apply_dynamic_boundaryconditions and assemble_dynamic_force replaced by the en234gpu_dynamic_* entry points
 // (include/en234gpu.h).  No numerical work happens here: the host builds the time-independent load tables once and decides
 // which steps print.
+#include <algorithm>
 #include <cstdio>
 
 #include "explicit_dynamic_step.h"
@@ -11,10 +12,10 @@
 namespace en234 {
 
 int explicit_dynamic_step(const Model& m, en234gpu_handle h, int n_steps, const double* initial_velocity, FILE* state_print,
-                          DynamicResult& res) {
+                          DynamicResult& res, const std::vector<int>* g2l, size_t n_local, const std::vector<int>* local_elements) {
     if (!m.explicitdynamicstep) { res.error = "the input has no EXPLICIT DYNAMIC STEP block"; return 1; }
     DynamicLoads L;
-    if (!dynamic_load_tables(m, L)) { res.error = L.error; return 1; }
+    if (!dynamic_load_tables(m, L, g2l, local_elements)) { res.error = L.error; return 1; }
     auto ip = [](const std::vector<int>& v) { return v.empty() ? nullptr : v.data(); };
     auto dp = [](const std::vector<double>& v) { return v.empty() ? nullptr : v.data(); };
     if (en234gpu_dynamic_setup(h, L.element_density.data(), (int)L.history_ptr.size() - 1, L.history_ptr.data(), dp(L.history_time),
@@ -24,8 +25,8 @@ int explicit_dynamic_step(const Model& m, en234gpu_handle h, int n_steps, const 
     if (initial_velocity && en234gpu_dynamic_set_state(h, nullptr, initial_velocity, nullptr, 0.0)) { res.error = en234gpu_last_error(); return -1; }
     const int total = n_steps > 0 ? n_steps : m.no_dynamic_steps;
     const double dt = m.dynamic_timestep;
-    const size_t nd = (size_t)m.ndof();
-    const bool printing = m.stateprint && state_print != nullptr && m.state_print_steps > 0;
+    const size_t nd = g2l ? n_local : (size_t)m.ndof();
+    const bool printing = m.stateprint && state_print != nullptr && m.state_print_steps > 0 && !g2l;
     std::vector<double> ut, du;
     int done = 0, fail = 0;
     double ms = 0.0;

@@ -16,7 +16,10 @@ struct DynamicResult {
 };
 
 // src/explicit_dynamic_step.f90:1-83 on the device; n_steps <= 0: the input's NUMBER OF STEPS
+// partitioned runs (g2l / local_elements as in dynamic_load_tables): every rank runs this loop on its rank-local arrays of
+// n_local DOFs; state prints are single-device and skipped
 int explicit_dynamic_step(const Model& m, en234gpu_handle h, int n_steps, const double* initial_velocity, FILE* state_print,
-                          DynamicResult& res);
+                          DynamicResult& res, const std::vector<int>* g2l = nullptr, size_t n_local = 0,
+                          const std::vector<int>* local_elements = nullptr);
 
 }  // namespace en234

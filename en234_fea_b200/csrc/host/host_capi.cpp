@@ -312,6 +312,30 @@ int en234host_run_dynamic(en234host_model_t w, en234gpu_handle h, int n_steps, c
     return 0;
 }
 
+// the same on one rank of a partitioned run (collective over all ranks): arrays are rank-local (3 * part n_nodes)
+int en234host_run_dynamic_part(en234host_model_t w, en234host_part_t p, en234gpu_handle h, int n_steps,
+                               const double* initial_velocity_local, double* dof_total_local, double* velocity_local,
+                               double* acceleration_local, double* rforce_local, double* lumped_mass_local, long long* info,
+                               double* device_ms) {
+    const auto& l2g = p->I["local_to_global_node"];
+    std::vector<int> g2l((size_t)w->m.ndof(), -1);
+    for (size_t i = 0; i < l2g.size(); ++i)
+        for (int c = 0; c < 3; ++c) g2l[3 * (size_t)l2g[i] + c] = (int)(3 * i + c);
+    const size_t nd = 3 * l2g.size();
+    DynamicResult r;
+    const int rc = explicit_dynamic_step(w->m, h, n_steps, initial_velocity_local, nullptr, r, &g2l, nd, &p->I["local_elements"]);
+    if (rc) { g_err = r.error; return rc; }
+    const size_t b = nd * sizeof(double);
+    if (dof_total_local) std::memcpy(dof_total_local, r.dof_total.data(), b);
+    if (velocity_local) std::memcpy(velocity_local, r.velocity.data(), b);
+    if (acceleration_local) std::memcpy(acceleration_local, r.acceleration.data(), b);
+    if (rforce_local) std::memcpy(rforce_local, r.rforce.data(), b);
+    if (lumped_mass_local) std::memcpy(lumped_mass_local, r.lumped_mass.data(), b);
+    if (info) { info[0] = r.steps; info[1] = 0; info[2] = 0; }
+    if (device_ms) *device_ms = r.device_ms;
+    return 0;
+}
+
 int en234host_run_static(en234host_model_t w, en234gpu_handle h, int method, double cg_tolerance,
                          int max_cg_iterations, int check_linear_cg, int use_host_api, double* dof_total,
                          double* rforce, double* newton, int max_rows, int* cg_iterations, int max_cg_rows,

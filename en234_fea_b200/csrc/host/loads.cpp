@@ -205,28 +205,31 @@ void evaluate_loads(const Model& m, double time, double dtime, const double* dof
     }
 }
 
-bool dynamic_load_tables(const Model& m, DynamicLoads& out) {
+bool dynamic_load_tables(const Model& m, DynamicLoads& out, const std::vector<int>* g2l, const std::vector<int>* local_elements) {
     out = DynamicLoads();
     const size_t nd = (size_t)m.ndof();
+    auto loc = [&](size_t gd) -> long { return g2l ? (long)(*g2l)[gd] : (long)gd; };
     for (const History& h : m.histories) {
         out.history_time.insert(out.history_time.end(), h.t.begin(), h.t.end());
         out.history_value.insert(out.history_value.end(), h.v.begin(), h.v.end());
         out.history_ptr.push_back((int)out.history_time.size());
     }
-    out.element_density.assign(m.n_elements, 0.0);
-    for (int e = 0; e < m.n_elements; ++e) {
+    const int n_el = local_elements ? (int)local_elements->size() : m.n_elements;
+    out.element_density.assign(n_el, 0.0);
+    for (int le = 0; le < n_el; ++le) {
+        const int e = local_elements ? (*local_elements)[le] : le;
         if (m.element_flag[e] > 99999) {                              // VUEL: amass = amass*props(3) (abaqus_vuel.for:208)
             if (m.element_n_props[e] < 3) { out.error = "a VUEL element needs three properties (E, nu, density)"; return false; }
-            out.element_density[e] = m.element_properties[m.element_prop_index[e] + 2];
+            out.element_density[le] = m.element_properties[m.element_prop_index[e] + 2];
         } else {
-            out.element_density[e] = e < (int)m.element_density.size() ? m.element_density[e] : 0.0;
-            if (out.element_density[e] == 0.0) { out.error = "a density has not been defined for element number " + std::to_string(e + 1); return false; }
+            out.element_density[le] = e < (int)m.element_density.size() ? m.element_density[e] : 0.0;
+            if (out.element_density[le] == 0.0) { out.error = "a density has not been defined for element number " + std::to_string(e + 1); return false; }
         }
     }
     std::vector<double> dense(nd);
     auto push_load = [&](int history, double constant) {
         for (size_t d = 0; d < nd; ++d)
-            if (dense[d] != 0.0) { out.load_dof.push_back((int)d); out.load_val.push_back(dense[d]); }
+            if (dense[d] != 0.0 && loc(d) >= 0) { out.load_dof.push_back((int)loc(d)); out.load_val.push_back(dense[d]); }
         out.load_ptr.push_back((int)out.load_dof.size());
         out.load_history.push_back(history);
         out.load_constant.push_back(constant);
@@ -296,9 +299,10 @@ bool dynamic_load_tables(const Model& m, DynamicLoads& out) {
         if (p.flag == 3) { out.error = "SUBROUTINE prescribed DOFs are not supported in explicit dynamics"; return false; }
         auto one = [&](int n, int mode) {
             const size_t d = 3 * (size_t)(n - 1) + p.dof - 1;
+            if (loc(d) < 0) return;
             if (slot[d] < 0) {
                 slot[d] = (int)out.pdof_dof.size();
-                out.pdof_dof.push_back((int)d); out.pdof_history.push_back(0); out.pdof_value.push_back(0.0); out.pdof_mode.push_back(0);
+                out.pdof_dof.push_back((int)loc(d)); out.pdof_history.push_back(0); out.pdof_value.push_back(0.0); out.pdof_mode.push_back(0);
             }
             const int k = slot[d];
             out.pdof_history[k] = p.flag == 2 ? p.history_number : 0;

@@ -34,6 +34,10 @@ struct DynamicLoads {
     std::vector<double> element_density;                    // DENSITY, or the third property of a VUEL element
     std::string error;
 };
-bool dynamic_load_tables(const Model& m, DynamicLoads& out);
+// partitioned runs: g2l maps a global DOF to the rank-local DOF (-1: not on this rank), local_elements lists the rank's
+// elements (0-based global numbers); loads and prescribed DOFs are then restricted to the rank's DOFs with their FULL values
+// (every copy of an interface DOF receives the whole external force, like the element load vector of the static step)
+bool dynamic_load_tables(const Model& m, DynamicLoads& out, const std::vector<int>* g2l = nullptr,
+                         const std::vector<int>* local_elements = nullptr);
 
 }  // namespace en234

@@ -115,6 +115,13 @@ int en234host_run_dynamic(en234host_model_t m, en234gpu_handle h, int n_steps, c
                           double* dof_total, double* velocity, double* acceleration, double* rforce, double* lumped_mass,
                           long long* info, double* device_ms);
 
+/* one rank of a partitioned explicit dynamic run (collective; one halo sum of the element forces per step); arrays are
+ * rank-local, 3 * (part n_nodes); no state prints */
+int en234host_run_dynamic_part(en234host_model_t m, en234host_part_t p, en234gpu_handle h, int n_steps,
+                               const double* initial_velocity_local, double* dof_total_local, double* velocity_local,
+                               double* acceleration_local, double* rforce_local, double* lumped_mass_local, long long* info,
+                               double* device_ms);
+
 /* check_stiffness (src/checkstiffness.f90): the reference's self-test of an element routine, run through the device twins
  * below — coded stiffness against the numerical derivative of the residual (h = 1e-7), err = sum (K_num - K)^2 / sum K^2
  * (consistent when <= 1e-6), plus the counts of entries the symmetry report flags.  element_flag: as parsed from the

@@ -18,10 +18,13 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dynamics_only = "--dynamics-only" in sys.argv
+    if dynamics_only:
+        sys.argv.remove("--dynamics-only")
     dims = tuple(int(x) for x in (sys.argv[1:4] if len(sys.argv) >= 4 else (12, 10, 8 * world)))
     jitter = float(sys.argv[4]) if len(sys.argv) >= 5 else 0.2      # 0 with power-of-two dims: congruent-mesh operator
     ok = True
-    for method in (0, 1):
+    for method in (() if dynamics_only else (0, 1)):
         for load in ("traction", "stretch"):
             m = Model.from_text(synthetic_block_input(*dims, jitter=jitter, cg_tolerance=1e-26, cg_maxit=20000, load=load,
                                                       steps=2 if load == "stretch" else 1))
@@ -57,6 +60,40 @@ def main():
                 g1.close()
             dist.barrier()
             g.close()
+    # explicit dynamic step on the partitioned mesh: one halo sum of the element forces per step (and of the lumped mass once)
+    text = synthetic_block_input(*dims, jitter=jitter, element="U1", props=[100.0, 0.3, 2.5], load="stretch", steps=4, dt=0.5,
+                                 dynamic=(1e-3 * 8.0 / max(dims), 70))
+    text = text.replace(" END DEGREES OF FREEDOM", " END DEGREES OF FREEDOM\n FORCES\n  xmax, 3, HISTORY, ramp\n END FORCES")
+    m = Model.from_text(text)
+    part = Partition(m, world, rank)
+    g = GpuSystem(m, device=local, part=part)
+    comm_kind = g.setup_distributed()
+    res = g.run_dynamic()
+    l2g = part.ints("local_to_global_node").astype(np.int64)
+    ldof = (3 * l2g[:, None] + np.arange(3)).ravel()
+    idx = torch.from_numpy(ldof).cuda()
+    fields = {}
+    for k in ("dof_total", "velocity", "lumped_mass"):
+        acc = torch.zeros(3 * m.n_nodes, dtype=torch.float64, device="cuda")
+        cnt = torch.zeros_like(acc)
+        acc[idx] = torch.from_numpy(res[k]).cuda()
+        cnt[idx] = 1.0
+        dist.all_reduce(acc); dist.all_reduce(cnt)
+        fields[k] = (acc / cnt).cpu().numpy()
+    agree = np.abs(fields["dof_total"][ldof] - res["dof_total"]).max() <= 1e-15 * np.abs(fields["dof_total"]).max()
+    if rank == 0:
+        g1 = GpuSystem(m, device=local)
+        ref = g1.run_dynamic()
+        errs = {k: np.abs(fields[k] - ref[k]).max() / np.abs(ref[k]).max() for k in fields}
+        good = all(e < 1e-10 for e in errs.values()) and agree and res["steps"] == ref["steps"] == 70
+        print("mgpu_check [%s] world=%d mesh=%s explicit dynamics 70 steps: u err %.2e, v err %.2e, mass err %.2e, copies agree %s, "
+              "%.1f us/step on %d GPUs vs %.1f us/step on one -> %s"
+              % (comm_kind, world, dims, errs["dof_total"], errs["velocity"], errs["lumped_mass"], agree,
+                 1e3 * res["device_ms"] / 70, world, 1e3 * ref["device_ms"] / 70, "OK" if good else "FAIL"), flush=True)
+        ok = ok and good
+        g1.close()
+    dist.barrier()
+    g.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()

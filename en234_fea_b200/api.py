@@ -59,7 +59,7 @@ HOST_SYMBOLS = [
     "en234host_partition", "en234host_part_free", "en234host_part_int", "en234host_part_owned",
     "en234host_part_gpu_create", "en234host_run_static_part", "en234host_check_stiffness",
     "en234host_model_get_state_print", "en234host_model_set_state_print", "en234host_project_fields", "en234host_print_state",
-    "en234host_run_dynamic", "en234host_run_dynamic_part",
+    "en234host_run_dynamic", "en234host_run_dynamic_part", "en234host_dynamic_tables",
 ]
 # Fortran-linkage twins of the reference plugin entry points (include/en234host.h)
 PLUGIN_SYMBOLS = ["user_element_static_", "uel_"]
@@ -219,6 +219,29 @@ class Model:
                                                         names, os.fsencode(path) if path else None)
         if rc:
             raise RuntimeError(host_lib().en234host_last_error().decode())
+
+    def dynamic_tables(self, part=None):
+        """The explicit-dynamics load tables (apply_dynamic_boundaryconditions, time-independent part) as handed to the device:
+        list of (dense unit nodal forces, history id, constant), prescribed DOFs (dof, history, value, mode), element densities."""
+        L = host_lib()
+        nd = 3 * (part.ints("n_nodes")[0] if part is not None else self.n_nodes)
+        ne = part.ints("n_elements")[0] if part is not None else self.n_elements
+        ph = part.h if part is not None else None
+        cap = int(nd)
+        n_pd = C.c_int()
+        pd, phs, pm, pv, dens = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap), np.zeros(ne)
+        n_loads = L.en234host_dynamic_tables(self.h, ph, C.c_int(-1), None, None, None, C.byref(n_pd), _ip(pd), _ip(phs), _dp(pv),
+                                             _ip(pm), C.c_int(cap), _dp(dens))
+        if n_loads < 0:
+            raise RuntimeError(L.en234host_last_error().decode())
+        loads = []
+        for l in range(n_loads):
+            dense, h, c = np.zeros(nd), C.c_int(), C.c_double()
+            L.en234host_dynamic_tables(self.h, ph, C.c_int(l), _dp(dense), C.byref(h), C.byref(c), None, None, None, None, None,
+                                       C.c_int(0), None)
+            loads.append((dense, h.value, c.value))
+        k = n_pd.value
+        return {"loads": loads, "pdof": (pd[:k].copy(), phs[:k].copy(), pv[:k].copy(), pm[:k].copy()), "element_density": dens}
 
     def evaluate_loads(self, time, dtime, dof_total=None, dof_increment=None):
         nd = 3 * self.n_nodes

@@ -336,6 +336,45 @@ int en234host_run_dynamic_part(en234host_model_t w, en234host_part_t p, en234gpu
     return 0;
 }
 
+// Inspection of the explicit-dynamics load tables (tests): dense nodal forces of a unit magnitude of load `load_index`
+// (distributed loads first, then prescribed forces), its history id / constant; prescribed DOFs as (dof, history, value, mode).
+// p == NULL: whole mesh; else rank-local numbering.  Returns the number of loads, or -1.
+int en234host_dynamic_tables(en234host_model_t w, en234host_part_t p, int load_index, double* dense, int* history,
+                             double* constant, int* n_pdof, int* pdof_dof, int* pdof_history, double* pdof_value, int* pdof_mode,
+                             int cap_pdof, double* element_density) {
+    DynamicLoads L;
+    std::vector<int> g2l;
+    size_t nd = (size_t)w->m.ndof();
+    bool ok;
+    if (p) {
+        const auto& l2g = p->I["local_to_global_node"];
+        g2l.assign((size_t)w->m.ndof(), -1);
+        for (size_t i = 0; i < l2g.size(); ++i)
+            for (int c = 0; c < 3; ++c) g2l[3 * (size_t)l2g[i] + c] = (int)(3 * i + c);
+        nd = 3 * l2g.size();
+        ok = dynamic_load_tables(w->m, L, &g2l, &p->I["local_elements"]);
+    } else ok = dynamic_load_tables(w->m, L);
+    if (!ok) { g_err = L.error; return -1; }
+    const int n_loads = (int)L.load_history.size();
+    if (load_index >= 0 && load_index < n_loads) {
+        if (dense) {
+            std::fill(dense, dense + nd, 0.0);
+            for (int k = L.load_ptr[load_index]; k < L.load_ptr[load_index + 1]; ++k) dense[L.load_dof[k]] = L.load_val[k];
+        }
+        if (history) *history = L.load_history[load_index];
+        if (constant) *constant = L.load_constant[load_index];
+    }
+    if (n_pdof) *n_pdof = (int)L.pdof_dof.size();
+    for (int k = 0; k < (int)L.pdof_dof.size() && k < cap_pdof; ++k) {
+        if (pdof_dof) pdof_dof[k] = L.pdof_dof[k];
+        if (pdof_history) pdof_history[k] = L.pdof_history[k];
+        if (pdof_value) pdof_value[k] = L.pdof_value[k];
+        if (pdof_mode) pdof_mode[k] = L.pdof_mode[k];
+    }
+    if (element_density) std::copy(L.element_density.begin(), L.element_density.end(), element_density);
+    return n_loads;
+}
+
 int en234host_run_static(en234host_model_t w, en234gpu_handle h, int method, double cg_tolerance,
                          int max_cg_iterations, int check_linear_cg, int use_host_api, double* dof_total,
                          double* rforce, double* newton, int max_rows, int* cg_iterations, int max_cg_rows,

@@ -122,6 +122,14 @@ int en234host_run_dynamic_part(en234host_model_t m, en234host_part_t p, en234gpu
                                double* acceleration_local, double* rforce_local, double* lumped_mass_local, long long* info,
                                double* device_ms);
 
+/* inspection of the load tables en234host_run_dynamic hands to en234gpu_dynamic_setup (tests): load `load_index` as a dense
+ * vector of nodal forces for a unit magnitude (distributed loads first, then prescribed forces) with its history id /
+ * constant scale, the prescribed-DOF list, the element densities; p == NULL: whole mesh, else rank-local numbering.
+ * Returns the number of loads, -1 on error. */
+int en234host_dynamic_tables(en234host_model_t m, en234host_part_t p, int load_index, double* dense, int* history,
+                             double* constant, int* n_pdof, int* pdof_dof, int* pdof_history, double* pdof_value, int* pdof_mode,
+                             int cap_pdof, double* element_density);
+
 /* check_stiffness (src/checkstiffness.f90): the reference's self-test of an element routine, run through the device twins
  * below — coded stiffness against the numerical derivative of the residual (h = 1e-7), err = sum (K_num - K)^2 / sum K^2
  * (consistent when <= 1e-6), plus the counts of entries the symmetry report flags.  element_flag: as parsed from the

@@ -664,6 +664,42 @@ def test_parser_explicit_dynamic_step_and_density():
         Model.from_text(text.replace(" TIME STEP, 0.01\n", ""))
 
 
+def test_explicit_dynamics_load_tables_whole_mesh_and_partitioned():
+    """The time-independent half of apply_dynamic_boundaryconditions as the host hands it to the device: unit nodal forces per
+    load against the oracle's first-step external force, and the rank-local tables of a 3-way partition against the whole-mesh
+    ones (every copy of an interface DOF gets the full value)."""
+    base = Model.from_text(synthetic_block_input(3, 3, 6, jitter=0.15)).text()
+    base = base.replace("  PARAMETERS, 8, 0, 1001\n", "  PARAMETERS, 8, 0, 1001\n  DENSITY, 3.d0\n")
+    head = base[:base.index(" DISTRIBUTED LOADS")]
+    loads = (" HISTORY, pulse\n  0.d0, 0.d0\n  0.02d0, 4.d0\n  1.d0, 4.d0\n END HISTORY\n"
+             " DISTRIBUTED LOADS\n  xmax_el, 4, VALUE, 0.d0, 0.5d0, -1.d0\n  ymax_el, 5, HISTORY, pulse, 1.d0, 1.d0, 0.d0\n"
+             "  zmax_el, 2, NORMAL, pulse\n END DISTRIBUTED LOADS\n FORCES\n  zmin, 2, HISTORY, pulse\n END FORCES\nEND BOUNDARY CONDITIONS\n")
+    m = Model.from_text(head + loads + "EXPLICIT DYNAMIC STEP\n TIME STEP, 5.d-3\n NUMBER OF STEPS, 4\nEND EXPLICIT DYNAMIC STEP\nSTOP\n")
+    a = m.arrays()
+    T = m.dynamic_tables()
+    assert [(h, c) for _, h, c in T["loads"]] == [(0, 1.0), (1, 1.0), (1, 1.0), (1, 1.0)]
+    assert np.all(T["element_density"] == 3.0)
+    # first step of the oracle: rforce = external + internal, internal = 0 at u = 0 except through the prescribed DOFs (none move)
+    d = ob.OracleModel(a).dynamic().steps(1).get()
+    hist = np.interp(5e-3, [0.0, 0.02, 1.0], [0.0, 4.0, 4.0])
+    fext = sum(dense * (hist if h else c) for dense, h, c in T["loads"])
+    assert np.abs(d["rforce"] - fext).max() < 1e-13 * np.abs(fext).max()
+    pd, ph, pv, pm = T["pdof"]
+    assert len(pd) == len(set(pd.tolist())) and not ph.any() and not pv.any() and not pm.any()
+    owners = np.zeros(3 * m.n_nodes, int)
+    for rank in range(3):
+        part = Partition(m, 3, rank)
+        l2g = part.ints("local_to_global_node").astype(np.int64)
+        ldof = (3 * l2g[:, None] + np.arange(3)).ravel()
+        P = m.dynamic_tables(part)
+        for (dl, hl, cl), (dg, hg, cg) in zip(P["loads"], T["loads"]):
+            assert (hl, cl) == (hg, cg) and np.array_equal(dl, dg[ldof])
+        assert sorted(ldof[P["pdof"][0]].tolist()) == sorted(set(pd.tolist()) & set(ldof.tolist()))
+        assert np.all(P["element_density"] == 3.0) and P["element_density"].size == part.ints("n_elements")[0]
+        owners[ldof] += 1
+    assert owners.min() >= 1 and owners.max() >= 2                                    # interface DOFs live on two ranks
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """bench.py --impl reference (the CPU arm the driver runs beside the CUDA arm) on a small block: one JSON line with the
     contract keys, on rank 0 only."""

@@ -438,6 +438,20 @@ class GpuSystem:
         out["time"] = t.value
         return out
 
+    def project_field_codes(self, codes, dof_total=None, dof_increment=None, lumped=False):
+        """en234gpu_project_fields with numeric field codes (include/en234gpu.h) on this handle's own (rank-local when
+        partitioned) numbering: (n_local_nodes, n_fields).  Collective on partitioned handles."""
+        n = self.ndof // 3
+        out = np.zeros((len(codes), n))
+        ut = None if dof_total is None else _f64(dof_total)
+        du = None if dof_increment is None else _f64(dof_increment)
+        if ut is not None and du is None:
+            du = np.zeros_like(ut)
+        its = C.c_int()
+        self._ck(gpu_lib().en234gpu_project_fields(self.h, C.c_int(len(codes)), _ip(_i32(codes)), C.c_int(1 if lumped else 0),
+                                                   C.c_double(0.0), C.c_int(0), _dp(ut), _dp(du), _dp(out), C.byref(its)))
+        return out.T.copy()
+
     def print_state(self, path, dof_total, dof_increment=None, time_end=1.0, append=False):
         """One Tecplot zone of the current PRINT STATE options for the given state."""
         ut = _f64(dof_total)

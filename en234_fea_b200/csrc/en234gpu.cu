@@ -1064,7 +1064,6 @@ int en234gpu_project_fields(en234gpu_handle c, int n_fields, const int* field_co
         if (e_ != cudaSuccess) return set_err(std::string("project_fields, ") + name + ": " + cudaGetErrorString(e_)); \
     } while (0)
     if (iterations) *iterations = 0;
-    if (c->comm.active) return set_err("field projection is single-device post-processing: run it on an unpartitioned context");
     if (n_fields < 0 || n_fields > PROJ_MAXF) return set_err("project_fields: between 0 and " + std::to_string(PROJ_MAXF) + " field variables");
     if (c->any_neo)   // user_element_fieldvariables knows element 1001 only (user_codes/src/user_element.f90:233-266)
         return set_err("project_fields: no field variables are defined for the neo-Hookean element (1002 / U2)");
@@ -1073,9 +1072,13 @@ int en234gpu_project_fields(en234gpu_handle c, int n_fields, const int* field_co
     const size_t b = (size_t)c->ndof * sizeof(double);
     if (dof_total) CK(cudaMemcpyAsync(c->ut.p, dof_total, b, cudaMemcpyHostToDevice, c->stream));
     if (dof_increment) CK(cudaMemcpyAsync(c->du.p, dof_increment, b, cudaMemcpyHostToDevice, c->stream));
+    // partitioned runs: right-hand sides, matrix diagonal and lumped entries of interface nodes are partial sums over the
+    // rank's elements; they are halo-summed as DOF-shaped vectors, the PCG loop is the partitioned one of the static step
+    const bool part = c->comm.active;
+    const int ls = part ? 3 : 1;
     DevBuf<double> F, lump;
     CK(F.alloc((size_t)n_fields * N));
-    CK(lump.alloc(N));
+    CK(lump.alloc((size_t)ls * N));
     ProjArgs A{};
     A.M = mesh_of(c);
     A.ut = c->ut.p; A.du = c->du.p;
@@ -1102,22 +1105,33 @@ int en234gpu_project_fields(en234gpu_handle c, int n_fields, const int* field_co
     CK(cudaMemcpyAsync(c->tmpvec2.p, c->minv.p, b, cudaMemcpyDeviceToDevice, c->stream));
     MassArgs Ma{};
     Ma.M = mesh_of(c); Ma.val = c->val.p; Ma.minv = c->minv.p; Ma.lump = lump.p;
+    Ma.raw_diag = part ? 1 : 0; Ma.lump_stride = ls;
     c->matrix_valid = false;
     c->diag_valid = false;
     STAGE("save rhs / preconditioner");
     k_project_mass<<<grid, PROJ_THREADS, 0, c->stream>>>(Ma);
     c->st.kernel_launches++;
     STAGE("k_project_mass");
+    if (part) {
+        if (comm_halo_sum(c->comm, c->minv.p, c->stream) || comm_halo_sum(c->comm, lump.p, c->stream)) return set_err(comm_error());
+        k_project_invert<<<(c->ndof + 255) / 256, 256, 0, c->stream>>>(c->ndof, c->minv.p);
+        c->st.kernel_launches += 1 + 2 * c->comm.launches_per_halo;
+        STAGE("halo sums of the projection matrix diagonal");
+    }
     int rc = 0, its = 0;
-    if (lumped) {
-        k_project_lumped<<<(N + 255) / 256, 256, 0, c->stream>>>(N, n_fields, lump.p, F.p);
-        c->st.kernel_launches++;
-        STAGE("k_project_lumped");
-    } else {
+    if (!lumped || part) {
         for (int k0 = 0; k0 < n_fields && !rc; k0 += 3) {
             k_project_pack<<<(N + 255) / 256, 256, 0, c->stream>>>(N, n_fields, k0, F.p, c->rhs.p);
             c->st.kernel_launches++;
+            if (part && comm_halo_sum(c->comm, c->rhs.p, c->stream)) { rc = set_err(comm_error()); break; }
             STAGE("k_project_pack");
+            if (lumped) {                     // lumped: only the (halo-summed) right-hand sides are needed
+                if (part) {
+                    k_project_unpack<<<(N + 255) / 256, 256, 0, c->stream>>>(N, n_fields, k0, c->rhs.p, F.p);
+                    c->st.kernel_launches++;
+                }
+                continue;
+            }
             rc = pcg_run(c, EN234_SOLVE_PCG_BSR, tolerance > 0 ? tolerance : 1e-28, max_iterations > 0 ? max_iterations : 500);
             if (rc) break;
             if (c->hS->fail) { rc = set_err("project_fields: the projection solve did not converge"); break; }
@@ -1126,6 +1140,11 @@ int en234gpu_project_fields(en234gpu_handle c, int n_fields, const int* field_co
             c->st.kernel_launches++;
             STAGE("k_project_unpack");
         }
+    }
+    if (lumped && !rc) {
+        k_project_lumped<<<(N + 255) / 256, 256, 0, c->stream>>>(N, n_fields, lump.p, ls, F.p);
+        c->st.kernel_launches++;
+        STAGE("k_project_lumped");
     }
     CK(cudaMemcpyAsync(c->rhs.p, c->tmpvec.p, b, cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaMemcpyAsync(c->minv.p, c->tmpvec2.p, b, cudaMemcpyDeviceToDevice, c->stream));

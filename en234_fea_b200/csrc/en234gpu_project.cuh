@@ -116,8 +116,10 @@ __global__ void __launch_bounds__(PROJ_THREADS) k_project_rhs(ProjArgs A) {
 struct MassArgs {
     Mesh M;
     double* val;            // block-CSR values, [r][block][c] per block row: receives diag(m, m, m) blocks
-    double* minv;           // 1 / M(n,n) for the three DOF slots of node n
-    double* lump;           // row-sum lumped projection matrix
+    double* minv;           // 1 / M(n,n) for the three DOF slots of node n (raw_diag: M(n,n) itself)
+    double* lump;           // row-sum lumped projection matrix, lump[lump_stride * n] (+1, +2 filled too when the stride is 3)
+    int raw_diag;           // partitioned runs: diagonal and lumped entries of interface nodes are partial sums, the caller
+    int lump_stride;        // halo-sums them (DOF-shaped vectors) and inverts afterwards
 };
 
 __global__ void __launch_bounds__(PROJ_THREADS) k_project_mass(MassArgs A) {
@@ -172,10 +174,15 @@ __global__ void __launch_bounds__(PROJ_THREADS) k_project_mass(MassArgs A) {
         row[3 * self] = 1.0; row[L + 3 * self + 1] = 1.0; row[2 * L + 3 * self + 2] = 1.0;
         lump = 1.0;
     }
-    A.minv[3 * (size_t)n] = 1.0 / d;
-    A.minv[3 * (size_t)n + 1] = 1.0 / d;
-    A.minv[3 * (size_t)n + 2] = 1.0 / d;
-    A.lump[n] = lump;
+    const double dv = A.raw_diag ? d : 1.0 / d;
+    A.minv[3 * (size_t)n] = dv;
+    A.minv[3 * (size_t)n + 1] = dv;
+    A.minv[3 * (size_t)n + 2] = dv;
+    for (int c = 0; c < A.lump_stride; ++c) A.lump[(size_t)A.lump_stride * n + c] = lump;
+}
+__global__ void k_project_invert(int n, double* v) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) v[d] = 1.0 / v[d];
 }
 
 // rhs[3n + r] = F[(k0 + r)*N + n] for the fields that exist (zero otherwise)
@@ -192,10 +199,10 @@ __global__ void k_project_unpack(int N, int nf, int k0, const double* sol, doubl
     for (int r = 0; r < 3; ++r)
         if (k0 + r < nf) F[(size_t)(k0 + r) * N + n] = sol[3 * (size_t)n + r];
 }
-__global__ void k_project_lumped(int N, int nf, const double* lump, double* F) {
+__global__ void k_project_lumped(int N, int nf, const double* lump, int lump_stride, double* F) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
-    const double l = lump[n];
+    const double l = lump[(size_t)lump_stride * n];
     for (int k = 0; k < nf; ++k) F[(size_t)k * N + n] = F[(size_t)k * N + n] / l;
 }
 

@@ -147,7 +147,9 @@ int en234gpu_get_svars(en234gpu_handle h, const double* dof_total, const double*
  * C3D8), EN234_FIELD_STATE0 + i (state variable i of the point; C3D8); anything else projects to a zero field, as an
  * unknown name does in the reference.  dof_total / dof_increment: host arrays, or NULL to use the device-resident state.
  * fields: host, [k * n_nodes + n].  tolerance <= 0: 1e-28 on r.r / b.b; max_iterations <= 0: 500.
- * Overwrites the assembled stiffness values (a new en234gpu_assemble* must precede the next solve).  Single device. */
+ * Overwrites the assembled stiffness values (a new en234gpu_assemble* must precede the next solve).
+ * Partitioned contexts: collective over the ranks; arrays are rank-local; right-hand sides, matrix diagonal and lumped entries
+ * of interface nodes are halo-summed, the solve is the partitioned PCG loop of the static step. */
 #define EN234_FIELD_S11 0
 #define EN234_FIELD_SMISES 6
 #define EN234_FIELD_E11 7

@@ -18,13 +18,15 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dynamics_only = "--dynamics-only" in sys.argv
-    if dynamics_only:
-        sys.argv.remove("--dynamics-only")
+    only = None                                   # --dynamics-only / --project-only: one section (GPU-minute budget)
+    for flag in ("--dynamics-only", "--project-only"):
+        if flag in sys.argv:
+            sys.argv.remove(flag)
+            only = flag[2:-5]
     dims = tuple(int(x) for x in (sys.argv[1:4] if len(sys.argv) >= 4 else (12, 10, 8 * world)))
     jitter = float(sys.argv[4]) if len(sys.argv) >= 5 else 0.2      # 0 with power-of-two dims: congruent-mesh operator
     ok = True
-    for method in (() if dynamics_only else (0, 1)):
+    for method in (() if only else (0, 1)):
         for load in ("traction", "stretch"):
             m = Model.from_text(synthetic_block_input(*dims, jitter=jitter, cg_tolerance=1e-26, cg_maxit=20000, load=load,
                                                       steps=2 if load == "stretch" else 1))
@@ -61,6 +63,18 @@ def main():
             dist.barrier()
             g.close()
     # explicit dynamic step on the partitioned mesh: one halo sum of the element forces per step (and of the lumped mass once)
+    if only in (None, "dynamics"):
+        ok = dynamics_section(rank, world, local, dims, jitter) and ok
+    if only in (None, "project"):
+        ok = project_section(rank, world, local, dims, jitter) and ok
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+def dynamics_section(rank, world, local, dims, jitter):
+    ok = True
     text = synthetic_block_input(*dims, jitter=jitter, element="U1", props=[100.0, 0.3, 2.5], load="stretch", steps=4, dt=0.5,
                                  dynamic=(1e-3 * 8.0 / max(dims), 70))
     text = text.replace(" END DEGREES OF FREEDOM", " END DEGREES OF FREEDOM\n FORCES\n  xmax, 3, HISTORY, ramp\n END FORCES")
@@ -94,10 +108,46 @@ def main():
         g1.close()
     dist.barrier()
     g.close()
-    flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.broadcast(flag, src=0)
-    dist.destroy_process_group()
-    sys.exit(0 if flag.item() else 1)
+    return ok
+
+
+def project_section(rank, world, local, dims, jitter):
+    # state print projection on the partitioned mesh (rank-local numbering), consistent and lumped, against one GPU
+    ok = True
+    m = Model.from_text(synthetic_block_input(*dims, jitter=jitter))
+    part = Partition(m, world, rank)
+    g = GpuSystem(m, device=local, part=part)
+    comm_kind = g.setup_distributed()
+    l2g = part.ints("local_to_global_node").astype(np.int64)
+    ldof = (3 * l2g[:, None] + np.arange(3)).ravel()
+    ug = 0.01 * np.random.default_rng(7).uniform(-1, 1, 3 * m.n_nodes)
+    codes = [0, 1, 2, 3, 4, 5, 6]
+    proj = {}
+    for lumped in (False, True):
+        f = g.project_field_codes(codes, ug[ldof], lumped=lumped)
+        acc = torch.zeros((m.n_nodes, len(codes)), dtype=torch.float64, device="cuda")
+        cnt = torch.zeros(m.n_nodes, dtype=torch.float64, device="cuda")
+        nidx = torch.from_numpy(l2g).cuda()
+        acc[nidx] = torch.from_numpy(f).cuda()
+        cnt[nidx] = 1.0
+        dist.all_reduce(acc); dist.all_reduce(cnt)
+        proj[lumped] = ((acc / cnt[:, None]).cpu().numpy(), np.abs((acc / cnt[:, None]).cpu().numpy()[l2g] - f).max())
+    if rank == 0:
+        g1 = GpuSystem(m, device=local)
+        good = True
+        msg = []
+        for lumped in (False, True):
+            ref = g1.project_field_codes(codes, ug, lumped=lumped)
+            err = np.abs(proj[lumped][0] - ref).max() / np.abs(ref).max()
+            good = good and err < 1e-10 and proj[lumped][1] <= 1e-12 * np.abs(ref).max()
+            msg.append("%s err %.2e (copies differ by %.1e)" % ("lumped" if lumped else "consistent", err, proj[lumped][1]))
+        print("mgpu_check [%s] world=%d mesh=%s state-print projection of 7 fields: %s -> %s"
+              % (comm_kind, world, dims, ", ".join(msg), "OK" if good else "FAIL"), flush=True)
+        ok = ok and good
+        g1.close()
+    dist.barrier()
+    g.close()
+    return ok
 
 
 if __name__ == "__main__":

@@ -60,6 +60,7 @@ HOST_SYMBOLS = [
     "en234host_part_gpu_create", "en234host_run_static_part", "en234host_check_stiffness",
     "en234host_model_get_state_print", "en234host_model_set_state_print", "en234host_project_fields", "en234host_print_state",
     "en234host_run_dynamic", "en234host_run_dynamic_part", "en234host_dynamic_tables",
+    "en234host_model_device_support",
 ]
 # Fortran-linkage twins of the reference plugin entry points (include/en234host.h)
 PLUGIN_SYMBOLS = ["user_element_static_", "uel_"]
@@ -219,6 +220,12 @@ class Model:
                                                         names, os.fsencode(path) if path else None)
         if rc:
             raise RuntimeError(host_lib().en234host_last_error().decode())
+
+    def device_support(self):
+        """None when the device implements every element of the model, else the reason (en234host_model_device_support)."""
+        if host_lib().en234host_model_device_support(self.h) == 0:
+            return None
+        return host_lib().en234host_last_error().decode()
 
     def dynamic_tables(self, part=None):
         """The explicit-dynamics load tables (apply_dynamic_boundaryconditions, time-independent part) as handed to the device:

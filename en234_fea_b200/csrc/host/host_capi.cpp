@@ -195,8 +195,36 @@ int en234host_check_stiffness(en234host_model_t w, int element_flag, const doubl
     return rc;
 }
 
+// An input file names element routines only by an id ("U1", a MATERIAL block): which Fortran source stood behind the id is
+// decided when the reference is linked.  The device implements the shipped ones and nothing else, so models whose property /
+// state counts do not fit those routines are refused instead of being run with the wrong physics.
+static bool device_supports(const Model& m, std::string& err) {
+    for (int e = 0; e < m.n_elements; ++e) {
+        const int flag = m.element_flag[e], np = m.element_n_props[e];
+        if (flag == 100000 && np != 2 && np != 3) {
+            // abaqus_uel_linelastic_3d.for: PROPS = E, nu; abaqus_vuel.for: E, nu, density
+            err = "element " + std::to_string(e + 1) + " is a U1 / VU1 user element with " + std::to_string(np) +
+                  " properties: the device has the shipped linear-elastic UEL (E, nu) and VUEL (E, nu, density) only";
+            return false;
+        }
+        if ((flag == 1001 || flag == 1002 || flag == 100001) && np < 2) {
+            err = "element " + std::to_string(e + 1) + " (type " + std::to_string(flag) + ") needs two properties";
+            return false;
+        }
+    }
+    return true;
+}
+
+int en234host_model_device_support(en234host_model_t w) {
+    std::string err;
+    if (device_supports(w->m, err)) return 0;
+    g_err = err;
+    return 1;
+}
+
 int en234host_gpu_create(en234host_model_t w, int device, en234gpu_handle* h) {
     const Model& m = w->m;
+    if (!device_supports(m, g_err)) return 1;
     // built-in continuum elements (flag 10003) take their properties from their MATERIAL (read_input_file.f90:433-509,
     // :756-960): one combined property array, element property index pointing into the material's section
     std::vector<double> props = m.element_properties;
@@ -555,6 +583,7 @@ const unsigned char* en234host_part_owned(en234host_part_t p) { return p->owned.
 
 int en234host_part_gpu_create(en234host_model_t w, en234host_part_t p, int device, en234gpu_handle* h) {
     const Model& m = w->m;
+    if (!device_supports(m, g_err)) return 1;
     const auto& lel = p->I["local_elements"];
     std::vector<int> flag(lel.size()), pidx(lel.size());
     for (size_t i = 0; i < lel.size(); ++i) { flag[i] = m.element_flag[lel[i]]; pidx[i] = m.element_prop_index[lel[i]]; }

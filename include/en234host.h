@@ -130,6 +130,12 @@ int en234host_dynamic_tables(en234host_model_t m, en234host_part_t p, int load_i
                              double* constant, int* n_pdof, int* pdof_dof, int* pdof_history, double* pdof_value, int* pdof_mode,
                              int cap_pdof, double* element_density);
 
+/* 0 when every element of the model is one the device implements; else 1 with the reason in en234host_last_error — e.g. a
+ * "U1" element whose property count fits neither the shipped linear-elastic UEL (E, nu) nor the VUEL (E, nu, density): an
+ * input file names element routines by id only, so a model written for another UEL source would otherwise run with the
+ * wrong physics.  en234host_gpu_create / en234host_part_gpu_create apply the same test. */
+int en234host_model_device_support(en234host_model_t m);
+
 /* check_stiffness (src/checkstiffness.f90): the reference's self-test of an element routine, run through the device twins
  * below — coded stiffness against the numerical derivative of the residual (h = 1e-7), err = sum (K_num - K)^2 / sum K^2
  * (consistent when <= 1e-6), plus the counts of entries the symmetry report flags.  element_flag: as parsed from the

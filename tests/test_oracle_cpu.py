@@ -700,6 +700,25 @@ def test_explicit_dynamics_load_tables_whole_mesh_and_partitioned():
     assert owners.min() >= 1 and owners.max() >= 2                                    # interface DOFs live on two ranks
 
 
+def test_models_written_for_other_element_routines_are_refused():
+    """"U1" only names a routine: input_files/Abaqus_uel_hyperelastic.in expects a six-property hyperelastic UEL the reference does
+    not ship; the device has the shipped linear-elastic UEL / VUEL, so that model is refused, never run as linear elastic.  Every
+    model the tests and the bench run on the device passes the same check."""
+    bad = synthetic_block_input(2, element="U1", props=[1.0, 200.0, 2.0, 2.0, 2.0, 1.0])
+    why = Model.from_text(bad).device_support()
+    assert why is not None and "6 properties" in why
+    if HAVE_REF:
+        assert Model.read(os.path.join(REF_INPUTS, "Abaqus_uel_hyperelastic.in")).device_support() is not None
+    good = [synthetic_block_input(2), synthetic_block_input(2, element="U1"), synthetic_block_input(2, element="1002", props=[1.0, 200.0]),
+            synthetic_block_input(2, element="U2", props=[1.0, 200.0]),
+            synthetic_block_input(2, element="U1", props=[100.0, 0.3, 2.5], dynamic=(1e-3, 4))]
+    for text in good:
+        assert Model.from_text(text).device_support() is None
+    for name in ("linear_elastic_3d_uel.in", "holeplate_3d_uel.in.gz", "linear_elastic_3d_vuel.in", "holeplate_3d_vuel.in.gz",
+                 "linear_elastic_3d_umat.in", "stretch_rotate_3d_umat.in", "holeplate_3d_umat.in.gz"):
+        assert golden_model(name).device_support() is None, name
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """bench.py --impl reference (the CPU arm the driver runs beside the CUDA arm) on a small block: one JSON line with the
     contract keys, on rank 0 only."""

@@ -527,6 +527,30 @@ def test_print_state_file_layout(tmp_path):
         assert line == "".join(" %5d" % renum[n] for n in c)
 
 
+def test_product_tecplot_writer_equals_the_oracle_writer_without_field_variables(tmp_path):
+    """The product's print_state (host/print_state.cpp) and the oracle's (oracle/or_print.cpp) are written independently; with no
+    FIELD VARIABLES no device is needed, so the two files can be compared here byte for byte: VARIABLES line, zone header,
+    (n(1X,E18.10)) node records incl. negative, tiny and three-digit-exponent values, (8(1x,i5)) connectivity."""
+    import ctypes as C
+    m = Model.from_text(synthetic_block_input(3, 2, 2, jitter=0.2))
+    m.set_state_print("unused", field_variables=[], print_dof=True, displaced_mesh=True, displacement_scale_factor=3.0)
+    a = m.arrays()
+    rng = np.random.default_rng(2)
+    ut = rng.uniform(-1, 1, 3 * m.n_nodes) * 10.0 ** rng.integers(-120, 5, 3 * m.n_nodes)
+    du = rng.uniform(-1e-3, 1e-3, 3 * m.n_nodes)
+    ut[:4] = [0.0, -0.0, 1e-310, 9.9999999999e99]
+    got, want = tmp_path / "product.dat", tmp_path / "oracle.dat"
+    L = api.host_lib()
+    dp = lambda v: v.ctypes.data_as(C.POINTER(C.c_double))
+    rc = L.en234host_print_state(m.h, None, C.c_double(0.125), dp(ut), dp(du), str(got).encode(), C.c_int(0))
+    assert rc == 0, L.en234host_last_error()
+    ob.OracleModel(a).print_state(want, [], ut, du, print_dof=True, displaced_mesh=True, scale_factor=3.0, time_end=0.125)
+    assert got.read_text() == want.read_text()
+    lines = got.read_text().splitlines()
+    assert lines[1] == ' ZONE, T="  0.1250D+00" F=FEPOINT, I=%5d J=%5d ET=BRICK' % (m.n_nodes, m.n_elements)
+    assert len(lines) == 2 + m.n_nodes + m.n_elements and all(len(l) == 9 * 19 for l in lines[2:2 + m.n_nodes])
+
+
 def test_parser_reads_the_print_state_block():
     text = synthetic_block_input(2).replace("END STATIC STEP", """ STATE PRINT STEPS, 2
   PRINT STATE, Output_files\\contour.dat

@@ -743,6 +743,98 @@ def test_models_written_for_other_element_routines_are_refused():
         assert golden_model(name).device_support() is None, name
 
 
+# ---------------------------------------------------------------------------------------------- device kernels compiled for the host
+@pytest.fixture(scope="module")
+def emul_kernels(tmp_path_factory):
+    """tests/emul/emul_kernels.cpp: the thread-per-node device kernels (state-print projection, lumped mass) compiled for the host
+    with the address and undefined-behaviour sanitisers."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++") or "/opt/gcc/bin/g++"
+    exe = tmp_path_factory.mktemp("emul") / "emul_kernels"
+    src = os.path.join(ROOT, "tests", "emul")
+    r = subprocess.run([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                        "-I" + os.path.join(src, "stub"), "-I" + os.path.join(ROOT, "en234_fea_b200", "csrc"),
+                        os.path.join(src, "emul_kernels.cpp"), "-o", str(exe)], capture_output=True, text=True)
+    if r.returncode:
+        pytest.skip("host compiler cannot build the emulation harness: " + r.stderr[-300:])
+    return str(exe)
+
+
+def _run_emul(exe, tmp_path, a, codes, ut, du, source=0, nsp=15, sv=None, density=None):
+    import subprocess
+    N, E = int(a["n_nodes"][0]), int(a["n_elements"][0])
+    pr = a["element_properties"]
+    if source == 0:
+        Ey, nu = pr[0], pr[1]
+        d = [(1 - nu) * Ey / ((1 + nu) * (1 - 2 * nu)), nu * Ey / ((1 + nu) * (1 - 2 * nu)), 0.5 * Ey / (1 + nu)]
+    else:
+        d = [0.0, 0.0, 0.0]
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        np.array([N, E, len(codes), source, nsp], np.int32).tofile(f)
+        np.array(codes, np.int32).tofile(f)
+        a["coords"].astype(np.float64).tofile(f)
+        a["connectivity"].astype(np.int32).tofile(f)
+        np.array(d, np.float64).tofile(f)
+        np.asarray(ut, np.float64).tofile(f)
+        np.asarray(du, np.float64).tofile(f)
+        (np.ones(E) if density is None else np.asarray(density, np.float64)).tofile(f)
+        if source == 1:
+            np.asarray(sv, np.float64).tofile(f)
+    r = subprocess.run([exe, str(inp), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    raw = np.fromfile(out)
+    nf = len(codes)
+    o = 0
+    res = {}
+    for k, n in (("F", nf * N), ("mdiag", N), ("lump", N), ("rowsum", N), ("mass", 3 * N)):
+        res[k] = raw[o:o + n]
+        o += n
+    res["F"] = res["F"].reshape(nf, N).T
+    return res
+
+
+def test_device_projection_and_mass_kernels_compiled_for_the_host_match_the_oracle(emul_kernels, tmp_path):
+    """k_project_rhs, k_project_mass and k_dyn_lumped_mass — the source nvcc compiles, run thread by thread on the host under the
+    sanitisers — against the oracle: right-hand sides of the seven linear-elastic fields (+ an unknown name), the 27-point
+    projection matrix (row sums = lumped entries, diagonal), the lumped dynamic mass with a density per element."""
+    m = Model.from_text(synthetic_block_input(4, 3, 2, jitter=0.25))
+    a = m.arrays()
+    om = ob.OracleModel(a)
+    rng = np.random.default_rng(3)
+    ut, du = 0.01 * rng.uniform(-1, 1, 3 * m.n_nodes), 0.003 * rng.uniform(-1, 1, 3 * m.n_nodes)
+    dens = rng.uniform(1.0, 4.0, m.n_elements)
+    got = _run_emul(emul_kernels, tmp_path, a, [0, 1, 2, 3, 4, 5, 6, -1], ut, du, density=dens)
+    want = om.project_fields(FIELDS7 + ["nonsense"], ut, du, raw=True)
+    assert np.abs(got["F"] - want).max() < 1e-13 * np.abs(want).max() and not got["F"][:, 7].any()
+    lump = om.lumped_projection_mass()
+    assert np.abs(got["lump"] - lump).max() < 1e-14 * lump.max()
+    assert np.abs(got["rowsum"] - lump).max() < 1e-13 * lump.max()            # rows of the consistent matrix sum to the lumped one
+    assert np.all(got["mdiag"] > 0) and np.all(got["mdiag"] < got["rowsum"])
+    a2 = dict(a)
+    a2["element_density"] = dens
+    mass = ob.OracleModel(a2).lumped_mass()
+    assert np.abs(got["mass"] - mass).max() < 1e-14 * mass.max()
+
+
+def test_device_projection_kernel_c3d8_source_compiled_for_the_host(emul_kernels, tmp_path):
+    """The state-variable branch of k_project_rhs (C3D8: stress, strain, material state per integration point) on the golden
+    two-element UMAT model, with made-up state values and 18 state variables per point so that U1 / U2 select real entries
+    (U<n> is honoured for n < 18 - 15 only, continuum_elements.f90:1340: the last material state cannot be plotted)."""
+    m = golden_model("linear_elastic_3d_umat.in")
+    a = m.arrays()
+    nsp = 18
+    a["element_n_states"] = np.full(m.n_elements, 8 * nsp, np.int32)
+    sv = np.random.default_rng(4).uniform(-1, 1, m.n_elements * 8 * nsp)
+    names = ["S11", "S23", "E11", "E13", "U1", "U2", "U3", "SMISES"]
+    codes = [0, 5, 7, 11, 100 + 15, 100 + 16, -1, -1]                         # U3: no such state variable; SMISES: not a C3D8 field
+    got = _run_emul(emul_kernels, tmp_path, a, codes, np.zeros(3 * m.n_nodes), np.zeros(3 * m.n_nodes), source=1, nsp=nsp, sv=sv)
+    want = ob.OracleModel(a).project_fields(names, np.zeros(3 * m.n_nodes), svars=sv, raw=True)
+    assert np.abs(got["F"] - want).max() < 1e-14 * np.abs(want).max()
+    assert not want[:, 6:].any() and want[:, 4].any() and want[:, 5].any()
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """bench.py --impl reference (the CPU arm the driver runs beside the CUDA arm) on a small block: one JSON line with the
     contract keys, on rank 0 only."""

@@ -51,6 +51,12 @@ GPU_SYMBOLS = [
     "en234gpu_measure_fp64_peak", "en234gpu_n_state_variables", "en234gpu_commit_state", "en234gpu_get_state_variables", "en234gpu_set_state_variables",
     "en234gpu_project_fields", "en234gpu_dynamic_setup", "en234gpu_dynamic_set_state", "en234gpu_dynamic_steps",
     "en234gpu_dynamic_half_step", "en234gpu_dynamic_get_state",
+    "en234gpu_create_multi", "en234gpu_multi_destroy", "en234gpu_multi_set_operator_mode", "en234gpu_multi_assemble",
+    "en234gpu_multi_apply_boundaryconditions", "en234gpu_multi_solve", "en234gpu_multi_upload_state",
+    "en234gpu_multi_assemble_dev", "en234gpu_multi_apply_boundaryconditions_dev", "en234gpu_multi_solve_dev",
+    "en234gpu_multi_zero_increment_dev", "en234gpu_multi_download_state", "en234gpu_multi_n_parts",
+    "en234gpu_multi_part_handle", "en234gpu_multi_part_info", "en234gpu_multi_get_stats",
+    "en234gpu_partition_sizes", "en234gpu_partition_arrays",
 ]
 HOST_SYMBOLS = [
     "en234host_model_read", "en234host_model_from_text", "en234host_model_free", "en234host_last_error",
@@ -565,6 +571,124 @@ class GpuSystem:
         return {"dof_total": u, "rforce": rf, "newton": newton[:info[2]].copy(), "cg_iterations": cg[:info[3]].copy(),
                 "n_steps": int(info[0]), "n_cutbacks": int(info[1]), "n_state_prints": int(info[4])}
 
+
+
+def library_partition(connectivity, n_nodes, n_parts, part):
+    """The element partition en234gpu_create_multi builds (host code of liben234gpu.so; no device needed)."""
+    L = gpu_lib()
+    cn = _i32(connectivity)
+    ne = cn.size // 8
+    sizes = np.zeros(6, np.int32)
+    if L.en234gpu_partition_sizes(C.c_int(n_parts), C.c_int(part), C.c_int(n_nodes), C.c_int(ne), _ip(cn), _ip(sizes)):
+        raise RuntimeError(L.en234gpu_last_error().decode())
+    nl, el, e0, nif, nn, ns = (int(x) for x in sizes)
+    out = {"local_to_global_node": np.zeros(nl, np.int32), "connectivity": np.zeros(8 * el, np.int32),
+           "neighbour_rank": np.zeros(nn, np.int32), "shared_ptr": np.zeros(nn + 1, np.int32),
+           "shared_nodes": np.zeros(ns, np.int32), "owned": np.zeros(nl, np.uint8)}
+    if L.en234gpu_partition_arrays(C.c_int(n_parts), C.c_int(part), C.c_int(n_nodes), C.c_int(ne), _ip(cn),
+                                   _ip(out["local_to_global_node"]), _ip(out["connectivity"]), _ip(out["neighbour_rank"]),
+                                   _ip(out["shared_ptr"]), _ip(out["shared_nodes"]),
+                                   out["owned"].ctypes.data_as(C.POINTER(C.c_ubyte))):
+        raise RuntimeError(L.en234gpu_last_error().decode())
+    out.update(first_element=e0, n_interface=nif, local_elements=np.arange(e0, e0 + el, dtype=np.int32))
+    return out
+
+
+class MultiGpuSystem:
+    """Several GPUs behind one handle in one process (en234gpu_create_multi): whole-mesh arrays in, whole-mesh arrays out.
+    devices may repeat a device (several parts co-scheduled on one GPU: tests on a one-GPU box)."""
+
+    def __init__(self, model=None, devices=(0, 1), arrays=None):
+        L = gpu_lib()
+        self.h = C.c_void_p()
+        a = arrays if arrays is not None else model.arrays()
+        co, cn = _f64(a["coords"]), _i32(a["connectivity"])
+        fl, pi, pr = _i32(a["element_flag"]), _i32(a["element_prop_index"]), _f64(a["element_properties"])
+        self.n_nodes = co.size // 3
+        self.ndof = 3 * self.n_nodes
+        dv = _i32(list(devices))
+        rc = L.en234gpu_create_multi(C.byref(self.h), C.c_int(dv.size), _ip(dv), C.c_int(self.n_nodes), C.c_int(fl.size), _dp(co),
+                                     _ip(cn), _ip(fl), _ip(pi), _dp(pr), C.c_int(pr.size))
+        if rc:
+            self.h = None
+            raise RuntimeError("en234gpu_create_multi failed: " + L.en234gpu_last_error().decode())
+        self.n_parts = dv.size
+
+    def _ck(self, rc):
+        if rc:
+            raise RuntimeError(gpu_lib().en234gpu_last_error().decode())
+
+    def close(self):
+        if self.h:
+            gpu_lib().en234gpu_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_operator_mode(self, method):
+        self._ck(gpu_lib().en234gpu_multi_set_operator_mode(self.h, C.c_int(method)))
+
+    def assemble(self, dof_total, dof_increment, f_element_ext=None):
+        rf, nrm, fail = np.zeros(self.ndof), C.c_double(), C.c_int()
+        self._ck(gpu_lib().en234gpu_multi_assemble(self.h, _dp(_f64(dof_total)), _dp(_f64(dof_increment)), _dp(_f64(f_element_ext)),
+                                                   _dp(rf), C.byref(nrm), C.byref(fail)))
+        return rf, nrm.value, fail.value
+
+    def apply_boundaryconditions(self, f_ext, fixed_dof, fixed_correction):
+        fd, nrm = _i32(fixed_dof), C.c_double()
+        self._ck(gpu_lib().en234gpu_multi_apply_boundaryconditions(self.h, _dp(_f64(f_ext)), C.c_int(fd.size), _ip(fd),
+                                                                   _dp(_f64(fixed_correction)), C.byref(nrm)))
+        return nrm.value
+
+    def solve(self, dof_increment, method=0, cg_tolerance=1e-17, max_cg_iterations=1000):
+        du = _f64(dof_increment).copy()
+        nrm, its, fail = C.c_double(), C.c_int(), C.c_int()
+        self._ck(gpu_lib().en234gpu_multi_solve(self.h, C.c_int(method), C.c_double(cg_tolerance), C.c_int(max_cg_iterations),
+                                                _dp(du), C.byref(nrm), C.byref(its), C.byref(fail)))
+        return du, nrm.value, its.value, fail.value
+
+    def upload_state(self, dof_total, dof_increment, f_element_ext, f_ext, fixed_dof, fixed_value):
+        fd = _i32(fixed_dof)
+        self._ck(gpu_lib().en234gpu_multi_upload_state(self.h, _dp(_f64(dof_total)), _dp(_f64(dof_increment)), _dp(_f64(f_element_ext)),
+                                                       _dp(_f64(f_ext)), C.c_int(fd.size), _ip(fd), _dp(_f64(fixed_value))))
+
+    def zero_increment_dev(self):
+        self._ck(gpu_lib().en234gpu_multi_zero_increment_dev(self.h))
+
+    def assemble_dev(self):
+        nrm, fail = C.c_double(), C.c_int()
+        self._ck(gpu_lib().en234gpu_multi_assemble_dev(self.h, C.byref(nrm), C.byref(fail)))
+        return nrm.value, fail.value
+
+    def apply_boundaryconditions_dev(self):
+        nrm = C.c_double()
+        self._ck(gpu_lib().en234gpu_multi_apply_boundaryconditions_dev(self.h, C.byref(nrm)))
+        return nrm.value
+
+    def solve_dev(self, method=0, cg_tolerance=1e-17, max_cg_iterations=1000):
+        nrm, its, fail = C.c_double(), C.c_int(), C.c_int()
+        self._ck(gpu_lib().en234gpu_multi_solve_dev(self.h, C.c_int(method), C.c_double(cg_tolerance), C.c_int(max_cg_iterations),
+                                                    C.byref(nrm), C.byref(its), C.byref(fail)))
+        return nrm.value, its.value, fail.value
+
+    def download_state(self):
+        du, rf = np.zeros(self.ndof), np.zeros(self.ndof)
+        self._ck(gpu_lib().en234gpu_multi_download_state(self.h, _dp(du), _dp(rf)))
+        return du, rf
+
+    def stats(self):
+        s = Stats()
+        self._ck(gpu_lib().en234gpu_multi_get_stats(self.h, C.byref(s)))
+        return s
+
+    def part_info(self, part):
+        v = [C.c_int() for _ in range(5)]
+        self._ck(gpu_lib().en234gpu_multi_part_info(self.h, C.c_int(part), *[C.byref(x) for x in v]))
+        return dict(zip(("device", "n_nodes", "n_elements", "n_interface", "n_neighbours"), (x.value for x in v)))
 
 
 # ---- the reference's plugin entry points, called the way a gfortran-compiled driver would (everything by reference)

@@ -67,10 +67,21 @@ def build_oracle(force=False):
     return out
 
 
+def build_ctests(force=False):
+    """tests/c/multi_check: plain-C driver of the multi-GPU entry points, linked against liben234gpu.so only."""
+    src = os.path.join(ROOT, "tests", "c", "multi_check.c")
+    out = os.path.join(ROOT, "tests", "c", "multi_check")
+    if os.path.exists(src) and (force or _newer(out, [src, os.path.join(CSRC, "liben234gpu.so"), os.path.join(ROOT, "include", "en234gpu.h")])):
+        _run([os.environ.get("CC", "gcc"), "-O2", "-Wall", "-o", out, src, "-I" + os.path.join(ROOT, "include"), "-L" + CSRC, "-len234gpu",
+              "-lm", "-Wl,-rpath,$ORIGIN/../../en234_fea_b200/csrc"], ROOT)
+    return out
+
+
 def build_all(force=False):
     build_gpu(force)
     build_host(force)
     build_oracle(force)
+    build_ctests(force)
 
 
 if __name__ == "__main__":

@@ -25,6 +25,7 @@
 using namespace en234k;
 
 static thread_local std::string g_err;
+static thread_local int g_sm_share = 1;   // parts that share the creating thread's device (en234gpu_create_multi)
 static int set_err(const std::string& s) { g_err = s; return 1; }
 #define CK(call)                                                                                     \
     do {                                                                                             \
@@ -48,7 +49,10 @@ template <class T> struct DevBuf {
     ~DevBuf() { release(); }
 };
 
-constexpr int CG_CHUNK = 16;   // PCG iterations per CUDA-graph launch (even: iteration parity is baked into the graph)
+constexpr int CG_CHUNK = 32;   // PCG iterations per CUDA-graph launch (even: iteration parity is baked into the graph)
+
+// what the host reads back after every chunk of captured iterations (pinned; two slots: one chunk is always in flight)
+struct CgPoll { en234k::CgScalars S; int p2p_error; int pad; };
 
 struct en234gpu_ctx {
     int device = 0;
@@ -70,6 +74,8 @@ struct en234gpu_ctx {
     bool have_felem = false, have_fext = false, have_owned = false;
     DevBuf<CgScalars> S;
     CgScalars* hS = nullptr;     // pinned mirror
+    CgPoll* hPoll = nullptr;     // pinned, 2 slots
+    cudaEvent_t evPoll[2] = {nullptr, nullptr};
     // matrix-free
     MfData mf;
     // graphs
@@ -157,6 +163,9 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->n_sm = prop.multiProcessorCount;
+    // several parts of one mesh on this device (tests on a one-GPU box): their kernels wait for one another and must be
+    // co-resident, so each part sizes its persistent grids for its share of half the SMs
+    if (g_sm_share > 1) c->n_sm = std::max(1, c->n_sm / (2 * g_sm_share));
     const int N = n_nodes, E = n_elements;
 
     // ---- materials: one table entry per distinct (flag, property offset)
@@ -285,6 +294,10 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
     CK(cudaMemset(c->S.p, 0, sizeof(CgScalars)));
     CK(cudaMallocHost((void**)&c->hS, sizeof(CgScalars)));
     std::memset(c->hS, 0, sizeof(CgScalars));
+    CK(cudaMallocHost((void**)&c->hPoll, 2 * sizeof(CgPoll)));
+    std::memset(c->hPoll, 0, 2 * sizeof(CgPoll));
+    CK(cudaEventCreateWithFlags(&c->evPoll[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->evPoll[1], cudaEventDisableTiming));
 
     // ---- launch geometry: persistent grids sized from the SM count (148 on B200)
     c->any_neo = any_neo;
@@ -377,6 +390,8 @@ int en234gpu_destroy(en234gpu_handle c) {
     comm_destroy(c->comm);
     mf_release(c->mf);
     if (c->hS) cudaFreeHost(c->hS);
+    if (c->hPoll) cudaFreeHost(c->hPoll);
+    for (auto& e : c->evPoll) if (e) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -491,7 +506,7 @@ int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail
     }
     if (finish_norm(c, part, npart, nodal_force_norm)) return 1;
     int bad = c->hS->nanflag;
-    if (c->comm.active && comm_host_max(c->comm, &bad)) return set_err(comm_error());
+    if (c->comm.active && comm_host_max(c->comm, &bad, c->stream)) return set_err(comm_error());
     *fail = bad ? 1 : 0;
     return phase_end(c, &c->st.assemble_ms);
 }
@@ -617,6 +632,10 @@ static CgVecArgs vec_args(en234gpu_ctx* c, int method, int parity) {
     V.n_part = c->comm.active ? 1 : c->grid_vec;
     V.S = c->S.p;
     V.parity = parity;
+    if (c->comm.active && c->comm.p2p && c->comm.fused) {
+        V.F = c->comm.F;
+        V.F.halo_in_spmv = method == EN234_SOLVE_PCG_BSR ? 1 : 0;
+    }
     return V;
 }
 
@@ -647,6 +666,36 @@ static int launch_operator(en234gpu_ctx* c, int method, const double* x, double*
     return 0;
 }
 
+// assembled operator of a partitioned run with the collectives folded in: one launch over all local rows that also pushes
+// the interface rows to the neighbours and the rank's p.Ap to all ranks
+static void launch_spmv_fused(en234gpu_ctx* c, const double* x, double* y) {
+    const int need = (c->N + WARPS - 1) / WARPS;
+    const int grid = std::max(1, std::min(need, c->grid_spmv));
+    SpmvArgs A;
+    A.row0 = 0; A.N = c->N; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
+    A.partials = c->part.p; A.S = c->S.p; A.check_stop = 1;
+    FusedComm F = c->comm.F;
+    F.halo_in_spmv = 1;
+    if (c->max_row_blocks <= 32) k_spmv<4, false, true><<<grid, THREADS, 0, c->stream>>>(A, F);
+    else k_spmv<4, true, true><<<grid, THREADS, 0, c->stream>>>(A, F);
+    c->st.kernel_launches++;
+}
+
+// peer-memory halo PUSH only (the consumer k_cg_update adds what arrived), forked to the side stream
+static void p2p_halo_push_fork(en234gpu_ctx* c, double* vec) {
+    Comm& cm = c->comm;
+    cudaEventRecord(cm.ev_fork, c->stream);
+    cudaStreamWaitEvent(cm.side, cm.ev_fork, 0);
+    if (cm.n_nbr > 0) {
+        int mx = 0;
+        for (int k = 0; k < cm.n_nbr; ++k) mx = std::max(mx, 3 * (cm.shared_ptr[k + 1] - cm.shared_ptr[k]));
+        const int nblk = std::max(1, std::min(32, (mx + 255) / 256));
+        k_halo_push<<<dim3(nblk, cm.n_nbr), 256, 0, cm.side>>>(cm.peers, cm.halo, vec, c->S.p, 1);
+        c->st.kernel_launches += 1;
+    }
+    cudaEventRecord(cm.ev_join, cm.side);
+}
+
 // number of p.Ap partials the operator leaves in part[]
 static int operator_partials(en234gpu_ctx* c, int method) {
     if (method == EN234_SOLVE_PCG_MATRIXFREE) return c->mf.n_partials;
@@ -674,6 +723,30 @@ static void p2p_halo_join(en234gpu_ctx* c) { cudaStreamWaitEvent(c->stream, c->c
 // one PCG iteration on the stream (captured into the graph)
 static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
     Comm& cm = c->comm;
+    if (cm.active && cm.p2p && cm.fused) {
+        // collectives folded into the kernels: three launches per iteration on the assembled operator, like one GPU
+        if (method == EN234_SOLVE_PCG_BSR) {
+            launch_spmv_fused(c, c->p.p, c->Ap.p);
+        } else {
+            const uint8_t* owned = c->have_owned ? c->owned.p : nullptr;
+            if (c->mf.congruent) {
+                mf_stencil(c->mf, mesh_of(c), c->cflag.p, owned, c->p.p, c->Ap.p, c->part.p, c->S.p, c->stream, &c->st.kernel_launches, 0);
+                p2p_halo_push_fork(c, c->Ap.p);
+                mf_stencil(c->mf, mesh_of(c), c->cflag.p, owned, c->p.p, c->Ap.p, c->part.p, c->S.p, c->stream, &c->st.kernel_launches, 1);
+            } else {
+                launch_operator(c, method, c->p.p, c->Ap.p, 1);
+                p2p_halo_push_fork(c, c->Ap.p);
+            }
+            k_p2p_push<<<1, VEC_THREADS, 0, c->stream>>>(cm.peers, c->part.p, operator_partials(c, method), c->S.p);
+            p2p_halo_join(c);
+            c->st.kernel_launches++;
+        }
+        CgVecArgs V = vec_args(c, method, parity);
+        k_cg_update<true><<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+        k_cg_pupdate<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+        c->st.kernel_launches += 2;
+        return 0;
+    }
     if (cm.active && cm.p2p) {
         // interface rows first; their halo exchange (peer-memory stores + flags, side stream) overlaps the interior
         // rows; p.Ap is the all-reduced sum of local partial products over ALL local rows, which needs no halo first
@@ -700,7 +773,7 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
         k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(cm.peers, c->part.p, np, nullptr, 0, c->part.p, nullptr, c->S.p, 1);
         p2p_halo_join(c);
         CgVecArgs V = vec_args(c, method, parity);
-        k_cg_update<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+        k_cg_update<false><<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
         k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(cm.peers, c->part2.p, c->grid_vec, c->part3.p, c->grid_vec,
                                                           c->part2.p, c->part3.p, c->S.p, 1);
         k_cg_pupdate<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
@@ -717,7 +790,7 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
         c->st.kernel_launches += 1 + c->comm.launches_per_halo;
     }
     CgVecArgs V = vec_args(c, method, parity);
-    k_cg_update<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+    k_cg_update<false><<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
     c->st.kernel_launches++;
     if (cm.active) {
         k_reduce2_to<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, c->grid_vec, c->part2.p, c->part3.p);
@@ -873,12 +946,40 @@ static int pcg_run(en234gpu_ctx* c, int method, double cg_tolerance, int max_cg_
     c->st.kernel_launches++;
     CK(cudaGetLastError());
     const long long per_graph = c->graph_launches[method];
-    for (;;) {
-        if (read_scalars(c)) return 1;
-        if (c->hS->stop || c->hS->iter >= max_cg_iterations) break;
+    // Chunks of CG_CHUNK captured iterations; the stop flag (and the peer-memory error flag) is copied to a pinned slot
+    // after every chunk.  The next chunk is launched BEFORE the host looks at the previous one's flags, so the device never
+    // waits for the host; once stopped, the kernels of a chunk return immediately.
+    auto poll = [&](int slot) -> int {
+        CK(cudaMemcpyAsync(&c->hPoll[slot].S, c->S.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+        if (c->comm.p2p)
+            CK(cudaMemcpyAsync(&c->hPoll[slot].p2p_error, &((ArenaHdr*)c->comm.arena)->error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        else c->hPoll[slot].p2p_error = 0;
+        CK(cudaEventRecord(c->evPoll[slot], c->stream));
+        return 0;
+    };
+    int cur = 0;
+    if (poll(cur)) return 1;
+    CK(cudaEventSynchronize(c->evPoll[cur]));
+    if (!c->hPoll[cur].S.stop) {
         CK(cudaGraphLaunch(c->graph[method], c->stream));
         c->st.kernel_launches += per_graph;
+        cur ^= 1;
+        if (poll(cur)) return 1;
+        for (;;) {
+            // one chunk (slot cur) is in flight: queue the next one, then look at the flags of the one in flight
+            CK(cudaGraphLaunch(c->graph[method], c->stream));
+            c->st.kernel_launches += per_graph;
+            const int nxt = cur ^ 1;
+            if (poll(nxt)) return 1;
+            CK(cudaEventSynchronize(c->evPoll[cur]));
+            const bool done = c->hPoll[cur].S.stop || c->hPoll[cur].p2p_error || c->hPoll[cur].S.iter >= max_cg_iterations;
+            cur = nxt;
+            if (done) break;
+        }
+        CK(cudaEventSynchronize(c->evPoll[cur]));
     }
+    *c->hS = c->hPoll[cur].S;
+    if (c->hPoll[cur].p2p_error) return set_err("peer-memory collective timed out (a rank stopped responding); the communicator must be rebuilt");
     return 0;
 }
 
@@ -893,7 +994,6 @@ int en234gpu_solve_dev(en234gpu_handle c, int method, double cg_tolerance, int m
         return set_err("the matrix-free operator covers the linear-elastic elements only (1001 / U1)");
     if (phase_begin(c)) return 1;
     if (pcg_run(c, method, cg_tolerance, max_cg_iterations)) return 1;
-    if (comm_p2p_error(c->comm)) return set_err("peer-memory collective timed out (a rank stopped responding)");
     *fail = c->hS->fail ? 1 : 0;
     *cg_iterations = c->hS->iter;
     c->st.last_cg_iterations = c->hS->iter;
@@ -1297,7 +1397,7 @@ int en234gpu_dynamic_half_step(en234gpu_handle c, double dt, int phase, int* fai
     CK(cudaGetLastError());
     if (read_scalars(c)) return 1;
     int bad = c->hS->nanflag;
-    if (c->comm.active && comm_host_max(c->comm, &bad)) return set_err(comm_error());
+    if (c->comm.active && comm_host_max(c->comm, &bad, c->stream)) return set_err(comm_error());
     if (fail) *fail = bad ? 1 : 0;
     return 0;
 }
@@ -1340,7 +1440,7 @@ int en234gpu_dynamic_steps(en234gpu_handle c, double dt, int n_steps, int* fail,
     CK(cudaEventRecord(c->ev1, c->stream));
     if (read_scalars(c)) return 1;
     int bad = c->hS->nanflag;
-    if (c->comm.active && comm_host_max(c->comm, &bad)) return set_err(comm_error());
+    if (c->comm.active && comm_host_max(c->comm, &bad, c->stream)) return set_err(comm_error());
     if (fail) *fail = bad ? 1 : 0;
     if (device_ms) {
         float ms = 0.f;
@@ -1450,6 +1550,7 @@ int en234gpu_apply_operator(en234gpu_handle c, int method, const double* x, doub
     else if (c->comm.active && comm_halo_sum(c->comm, c->tmpvec2.p, c->stream)) return set_err(comm_error());
     CK(cudaMemcpyAsync(y, c->tmpvec2.p, b, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (comm_p2p_error(c->comm)) return set_err("peer-memory halo exchange timed out (a rank stopped responding); the communicator must be rebuilt");
     return 0;
 }
 
@@ -1532,3 +1633,5 @@ int en234gpu_bench_operator(en234gpu_handle c, int method, int warm, int reps, d
 }
 
 }  // extern "C"
+
+#include "en234gpu_multi.h"

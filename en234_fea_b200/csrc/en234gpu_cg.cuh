@@ -5,6 +5,7 @@
 // iteration has no host round trip, no atomics and is bitwise run-to-run deterministic.
 #pragma once
 #include "en234gpu_kernels.cuh"
+#include "en234gpu_p2p.cuh"
 
 namespace en234k {
 
@@ -21,6 +22,14 @@ struct SpmvArgs {
     int check_stop;
 };
 
+// reduce_partials for partials written by OTHER CTAs of the same launch (last-CTA tails): loads bypass L1
+template <int NT>
+__device__ __forceinline__ double reduce_partials_cg(const double* part, int n, double* sm) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += NT) s += __ldcg(part + i);
+    return block_sum<NT>(s, sm);
+}
+
 // y = A x for the 3x3-block CSR matrix stored per block row as [r][block][c]; one warp per block row.
 // Lane q < 3*nb owns scalar column q of the block row: it gathers x_q once and reuses it for the three scalar
 // rows, whose values are read as three fully coalesced streams (streaming loads: the matrix is read once per
@@ -31,11 +40,39 @@ struct SpmvArgs {
 // rows in flight at any time are neighbours and their x entries hit in L2/L1.
 // WIDE = false: no block row has more than 32 blocks (every hex8 mesh with at most 8 elements per node), the tail loop
 // over further blocks is compiled out.
-template <int MINB, bool WIDE = true>
-__global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A) {
+// FUSED (partitioned runs, peer-memory arenas): the launch covers all local rows; interface rows (the first F.n_if) also
+// store their result into the neighbours' halo receive areas, every warp counts itself off when its interface rows are
+// done and the last one raises the neighbours' flags; the last CTA of the launch reduces the p.Ap partials and pushes the
+// rank's sum to all ranks (see en234gpu_p2p.cuh).
+template <int MINB, bool WIDE = true, bool FUSED = false>
+__global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A, FusedComm F = FusedComm{}) {
     __shared__ double red[WARPS + 1];
     if (A.check_stop && A.S->stop) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ArenaHdr* mine = nullptr;
+    unsigned long long hseq = 0ULL;
+    bool arrived = true;
+    if (FUSED) {
+        mine = F.P.arena[F.P.me];
+        hseq = ld_volatile_u64(&mine->halo_seq) + 1ULL;
+        arrived = F.halo_in_spmv == 0;
+    }
+    auto arrive = [&]() {
+        // this warp's interface rows are stored (locally and in the neighbours' arenas): count it off; the last warp
+        // of the grid raises the flags
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned t = atomicAdd(&mine->arrive, 1u);
+            if (t == gridDim.x * WARPS - 1) {
+                mine->arrive = 0;
+                __threadfence_system();
+                for (int k = 0; k < F.n_nbr; ++k)
+                    *(volatile unsigned long long*)&F.P.arena[F.nbr_rank[k]]->halo_flag[F.P.me] = hseq;
+            }
+        }
+        arrived = true;
+    };
     const int W = gridDim.x * WARPS, N = A.N;          // rows [A.row0, A.N) are processed by this launch
     const int d0 = lane / 3, m0 = lane % 3;                  // q = lane      -> block d0, component m0
     const int d1 = (lane + 32) / 3, m1 = (lane + 32) % 3;    // q = lane + 32
@@ -52,6 +89,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A) {
         if (d2 < nb) c2 = __ldg(A.bcol + rb + d2);
     }
     for (; i < N; i += W) {
+        if (FUSED && !arrived && i >= F.n_if) arrive();
         const int nb = re - rb, L = 3 * nb;
         const double* v = A.val + 9 * (size_t)rb;
         double y0 = 0.0, y1 = 0.0, y2 = 0.0;
@@ -84,11 +122,31 @@ __global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A) {
             const int r = lane >> 3;
             A.y[3 * (size_t)i + r] = yv;
             dot += yv * A.x[3 * (size_t)i + r];
+            if (FUSED && !arrived && i < F.n_if) {
+                const int par = (int)(hseq & 1ULL);
+                for (int j = F.if_ptr[i]; j < F.if_ptr[i + 1]; ++j)
+                    halo_send_area(F, F.if_nbr[j], par)[3 * (size_t)F.if_pos[j] + r] = yv;
+            }
         }
         rb = rbn; re = ren; rbn = rb2; ren = re2; c0 = cn0; c1 = cn1; c2 = cn2;
     }
+    if (FUSED && !arrived) arrive();
     const double t = block_sum<THREADS>(dot, red);
     if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
+    if (FUSED) {
+        __shared__ int s_last;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(&mine->tk_spmv, 1u) == gridDim.x - 1 ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const double pAp = reduce_partials_cg<THREADS>(A.partials, (int)gridDim.x, red);
+            if (threadIdx.x == 0) mine->tk_spmv = 0;
+            p2p_push2(F.P, ld_volatile_u64(&mine->ar_seq) + 1ULL, pAp, 0.0);
+        }
+    }
 }
 
 struct CgVecArgs {
@@ -101,7 +159,7 @@ struct CgVecArgs {
     double* part_a; double* part_b; int n_part; // partials written by this family (grid size of the vector kernels)
     CgScalars* S;
     int parity;                    // iteration parity (selects S->rz slot)
-    double pAp_allreduced;         // unused on one GPU
+    FusedComm F;                   // collectives folded into the vector kernels (F.active; en234gpu_p2p.cuh)
 };
 
 __device__ __forceinline__ bool dof_owned(const uint8_t* owned, int d) { return owned == nullptr || owned[d / 3] != 0; }
@@ -143,26 +201,52 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_init_finish(CgVecArgs A) {
 // Each thread handles VEC_ILP strided entries with all loads issued before the first use (the vectors are far smaller
 // than the matrix, so these kernels are latency-bound unless several loads per thread are in flight).
 constexpr int VEC_ILP = 4;
-__global__ void __launch_bounds__(VEC_THREADS) k_cg_update(CgVecArgs A) {
+template <bool FUSED>
+__global__ void __launch_bounds__(VEC_THREADS, FUSED ? 3 : 4) k_cg_update(CgVecArgs A) {
     __shared__ double red[VEC_THREADS / 32 + 1];
+    __shared__ double sh2[2];
     if (A.S->stop) return;
-    const double pAp = reduce_partials<VEC_THREADS>(A.part_pAp, A.n_part_pAp, red);
-    const double ak = A.S->rz[A.parity] / pAp;
-    double rr = 0.0, rz = 0.0;
+    const FusedComm& F = A.F;
     const int T = gridDim.x * VEC_THREADS;
-    for (int d0 = blockIdx.x * VEC_THREADS + threadIdx.x; d0 < A.n; d0 += VEC_ILP * T) {
-        double pv[VEC_ILP], sv[VEC_ILP], rv[VEC_ILP], av[VEC_ILP], mv[VEC_ILP];
+    const int dfirst = blockIdx.x * VEC_THREADS + threadIdx.x;
+    double pv[VEC_ILP], sv[VEC_ILP], rv[VEC_ILP], av[VEC_ILP], mv[VEC_ILP];
+    // the vector loads of the first chunk are in flight while the scalar arrives (partials / peers' arena slots)
 #pragma unroll
-        for (int k = 0; k < VEC_ILP; ++k) {
-            const int d = d0 + k * T;
-            if (d < A.n) { pv[k] = A.p[d]; sv[k] = A.sol[d]; rv[k] = A.r[d]; av[k] = A.Ap[d]; mv[k] = A.minv[d]; }
+    for (int k = 0; k < VEC_ILP; ++k) {
+        const int d = dfirst + k * T;
+        if (d < A.n) { pv[k] = A.p[d]; sv[k] = A.sol[d]; rv[k] = A.r[d]; av[k] = A.Ap[d]; mv[k] = A.minv[d]; }
+    }
+    double pAp;
+    unsigned long long seq = 0ULL, hseq = 0ULL;
+    ArenaHdr* mine = nullptr;
+    if (FUSED) {
+        mine = F.P.arena[F.P.me];
+        seq = ld_volatile_u64(&mine->ar_seq) + 1ULL;
+        hseq = F.n_nbr > 0 ? ld_volatile_u64(&mine->halo_seq) + 1ULL : 0ULL;
+        double unused;
+        p2p_wait2(F, seq, hseq, A.S, sh2, pAp, unused);
+    } else {
+        pAp = reduce_partials<VEC_THREADS>(A.part_pAp, A.n_part_pAp, red);
+    }
+    const double ak = A.S->rz[A.parity] / pAp;
+    const int nif3 = FUSED ? 3 * F.n_if : 0, hpar = (int)(hseq & 1ULL);
+    double rr = 0.0, rz = 0.0;
+    for (int d0 = dfirst; d0 < A.n; d0 += VEC_ILP * T) {
+        if (d0 != dfirst) {
+#pragma unroll
+            for (int k = 0; k < VEC_ILP; ++k) {
+                const int d = d0 + k * T;
+                if (d < A.n) { pv[k] = A.p[d]; sv[k] = A.sol[d]; rv[k] = A.r[d]; av[k] = A.Ap[d]; mv[k] = A.minv[d]; }
+            }
         }
 #pragma unroll
         for (int k = 0; k < VEC_ILP; ++k) {
             const int d = d0 + k * T;
             if (d < A.n) {
+                double ap = av[k];
+                if (FUSED && d < nif3) ap = halo_total(F, hpar, d, ap);          // interface row: add the neighbours' partial sums
                 A.sol[d] = sv[k] + ak * pv[k];
-                const double r = rv[k] - ak * av[k];
+                const double r = rv[k] - ak * ap;
                 A.r[d] = r;
                 if (dof_owned(A.owned, d)) { rr += r * r; rz += (r * mv[k]) * r; }
             }
@@ -171,6 +255,27 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_update(CgVecArgs A) {
     const double s0 = block_sum<VEC_THREADS>(rr, red);
     const double s1 = block_sum<VEC_THREADS>(rz, red);
     if (threadIdx.x == 0) { A.part_a[blockIdx.x] = s0; A.part_b[blockIdx.x] = s1; }
+    if (FUSED) {
+        // last CTA: this all-reduce and halo exchange are consumed by every CTA -> advance the counters, then reduce the
+        // r.r / r.z partials and push them to all ranks
+        __shared__ int s_last;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(&mine->tk_upd, 1u) == gridDim.x - 1 ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const double a = reduce_partials_cg<VEC_THREADS>(A.part_a, (int)gridDim.x, red);
+            const double b = reduce_partials_cg<VEC_THREADS>(A.part_b, (int)gridDim.x, red);
+            if (threadIdx.x == 0) {
+                mine->tk_upd = 0;
+                mine->ar_seq = seq;
+                if (hseq != 0ULL) mine->halo_seq = hseq;
+            }
+            p2p_push2(F.P, seq + 1ULL, a, b);
+        }
+    }
 }
 
 // err = r.r/b.b; stop if !(err > tol) (:849, :900) or after maxit iterations (:854-860);
@@ -188,8 +293,16 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_pupdate(CgVecArgs A) {
         const int d = dfirst + k * T;
         if (d < A.n) { pv[k] = A.p[d]; rv[k] = A.r[d]; mv[k] = A.minv[d]; }
     }
-    const double rr = reduce_partials<VEC_THREADS>(A.part_a, A.n_part, red);
-    const double rz = reduce_partials<VEC_THREADS>(A.part_b, A.n_part, red);
+    double rr, rz;
+    unsigned long long seq = 0ULL;
+    if (A.F.active) {
+        __shared__ double sh2[2];
+        seq = ld_volatile_u64(&A.F.P.arena[A.F.P.me]->ar_seq) + 1ULL;
+        p2p_wait2(A.F, seq, 0ULL, S, sh2, rr, rz);
+    } else {
+        rr = reduce_partials<VEC_THREADS>(A.part_a, A.n_part, red);
+        rz = reduce_partials<VEC_THREADS>(A.part_b, A.n_part, red);
+    }
     const double err = rr / S->bnrm;
     const bool more = err > S->tol;
     const int iter = S->iter + 1;
@@ -224,6 +337,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_pupdate(CgVecArgs A) {
     __syncthreads();
     if (ticket == gridDim.x - 1 && threadIdx.x == 0) {
         S->pad0 = 0;
+        if (A.F.active) A.F.P.arena[A.F.P.me]->ar_seq = seq;
         S->rz[A.parity ^ 1] = rz;
         S->err = err;
         S->iter = iter;

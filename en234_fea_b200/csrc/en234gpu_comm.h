@@ -71,6 +71,15 @@ struct Comm {
     HaloSet halo{};
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // collectives folded into the PCG kernels (FusedComm, en234gpu_p2p.cuh): per interface node the (neighbour, position)
+    // entries in ascending neighbour rank; EN234_P2P_FUSED=0 keeps the separate push / wait-add / all-reduce kernels
+    bool fused = false;
+    bool inproc = false;                      // ranks are threads of one process (en234gpu_create_multi): no NCCL at all
+    double* d_scratch = nullptr;              // 4 doubles: operand of the peer-memory scalar all-reduces
+    std::vector<int> h_shared;                // host copy of the shared-node lists
+    int *d_if_ptr = nullptr, *d_if_nbr = nullptr, *d_if_pos = nullptr;
+    unsigned char* d_if_before = nullptr;
+    FusedComm F{};
 };
 
 constexpr size_t P2P_HDR_BYTES = (sizeof(ArenaHdr) + 255) / 256 * 256;
@@ -82,6 +91,8 @@ inline int comm_arena_create(Comm& c, int max_shared_nodes, char* handle64) {
     c.arena_bytes = P2P_HDR_BYTES + (size_t)c.n_ranks * 2 * (size_t)c.peers.cap * sizeof(double);
     if (cudaMalloc(&c.arena, c.arena_bytes) != cudaSuccess) { comm_err_ref() = "cudaMalloc failed for the peer arena"; return 1; }
     cudaMemset(c.arena, 0, c.arena_bytes);
+    if (!c.d_scratch && cudaMalloc((void**)&c.d_scratch, 4 * sizeof(double)) != cudaSuccess) { comm_err_ref() = "cudaMalloc failed"; return 1; }
+    if (c.inproc) return 0;
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, c.arena);
     if (e != cudaSuccess) { comm_err_ref() = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); return 1; }
@@ -90,6 +101,8 @@ inline int comm_arena_create(Comm& c, int max_shared_nodes, char* handle64) {
     return 0;
 }
 
+inline int comm_arena_finish(Comm& c);
+// ranks in different processes: the peers' arenas are opened through their CUDA-IPC handles
 inline int comm_arena_connect(Comm& c, const char* handles /* n_ranks x 64 */) {
     if (!c.arena) { comm_err_ref() = "comm_arena_connect: no arena"; return 1; }
     c.peers.n_ranks = c.n_ranks;
@@ -106,6 +119,20 @@ inline int comm_arena_connect(Comm& c, const char* handles /* n_ranks x 64 */) {
         c.peers.arena[r] = (ArenaHdr*)base;
         c.peers.halo[r] = (double*)((char*)base + P2P_HDR_BYTES);
     }
+    return comm_arena_finish(c);
+}
+// ranks are threads of one process: the peers' arenas are plain device pointers (peer access enabled by the caller)
+inline int comm_arena_connect_inproc(Comm& c, void* const* bases /* n_ranks */) {
+    if (!c.arena) { comm_err_ref() = "comm_arena_connect: no arena"; return 1; }
+    c.peers.n_ranks = c.n_ranks;
+    c.peers.me = c.rank;
+    for (int r = 0; r < c.n_ranks; ++r) {
+        c.peers.arena[r] = (ArenaHdr*)bases[r];
+        c.peers.halo[r] = (double*)((char*)bases[r] + P2P_HDR_BYTES);
+    }
+    return comm_arena_finish(c);
+}
+inline int comm_arena_finish(Comm& c) {
     if (c.n_nbr > P2P_MAXR) { comm_err_ref() = "too many neighbours"; return 1; }
     c.halo.n_nbr = c.n_nbr;
     for (int k = 0; k < c.n_nbr; ++k) { c.halo.nbr_rank[k] = c.nbr_rank[k]; c.halo.ptr[k] = c.shared_ptr[k]; }
@@ -113,6 +140,56 @@ inline int comm_arena_connect(Comm& c, const char* handles /* n_ranks x 64 */) {
     c.halo.nodes = c.d_shared;
     for (int k = 0; k < c.n_nbr; ++k)
         if (3LL * (c.shared_ptr[k + 1] - c.shared_ptr[k]) > c.peers.cap) { comm_err_ref() = "halo capacity too small"; return 1; }
+    {
+        // spin time-out of the peer-memory collectives (default ~2 s; a debugger or profiler may need more)
+        c.peers.timeout = P2P_TIMEOUT_CYCLES;
+        if (const char* e = getenv("EN234_P2P_TIMEOUT_MS")) {
+            const double ms = atof(e);
+            if (ms > 0.0) c.peers.timeout = (long long)(ms * 2.0e6);
+        }
+    }
+    // fused collectives: possible when the interface nodes are exactly the first local rows
+    c.fused = false;
+    c.F = FusedComm{};
+    {
+        const char* e = getenv("EN234_P2P_FUSED");
+        const bool want = !(e && atoi(e) == 0);
+        if (want && (c.n_nbr == 0 || c.n_interface > 0)) {
+            const int nif = c.n_interface;
+            std::vector<int> cnt(nif + 1, 0);
+            for (int k = 0; k < c.n_nbr; ++k)
+                for (int q = c.shared_ptr[k]; q < c.shared_ptr[k + 1]; ++q) cnt[c.h_shared[q] + 1]++;
+            for (int i = 0; i < nif; ++i) cnt[i + 1] += cnt[i];
+            std::vector<int> fill(cnt.begin(), cnt.end() - 1), ifn(cnt[nif]), ifp(cnt[nif]);
+            std::vector<unsigned char> before(nif > 0 ? nif : 1, 0);
+            for (int k = 0; k < c.n_nbr; ++k)                     // neighbours are listed in ascending rank
+                for (int q = c.shared_ptr[k]; q < c.shared_ptr[k + 1]; ++q) {
+                    const int i = c.h_shared[q];
+                    ifn[fill[i]] = k; ifp[fill[i]] = q - c.shared_ptr[k]; fill[i]++;
+                    if (c.nbr_rank[k] < c.rank) before[i]++;
+                }
+            bool ascending = true;
+            for (int k = 1; k < c.n_nbr; ++k) ascending = ascending && c.nbr_rank[k] > c.nbr_rank[k - 1];
+            auto up = [](void** d, const void* h, size_t bytes) {
+                if (cudaMalloc(d, bytes > 0 ? bytes : 4) != cudaSuccess) return 1;
+                return bytes == 0 || cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : 1;
+            };
+            if (ascending) {
+                if (up((void**)&c.d_if_ptr, cnt.data(), cnt.size() * sizeof(int)) || up((void**)&c.d_if_nbr, ifn.data(), ifn.size() * sizeof(int)) ||
+                    up((void**)&c.d_if_pos, ifp.data(), ifp.size() * sizeof(int)) || up((void**)&c.d_if_before, before.data(), before.size())) {
+                    comm_err_ref() = "cudaMalloc failed for the interface tables";
+                    return 1;
+                }
+                c.F.active = 1;
+                c.F.P = c.peers;
+                c.F.n_nbr = c.n_nbr;
+                for (int k = 0; k < c.n_nbr; ++k) c.F.nbr_rank[k] = c.nbr_rank[k];
+                c.F.n_if = nif;
+                c.F.if_ptr = c.d_if_ptr; c.F.if_nbr = c.d_if_nbr; c.F.if_pos = c.d_if_pos; c.F.if_before = c.d_if_before;
+                c.fused = true;
+            }
+        }
+    }
     if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming) != cudaSuccess) {
@@ -158,6 +235,13 @@ inline int comm_init(Comm& c, int n_ranks, int rank, const char* id128, cudaStre
     return 0;
 }
 
+inline int comm_init_inproc(Comm& c, int n_ranks, int rank) {
+    c.n_ranks = n_ranks; c.rank = rank;
+    c.inproc = true;
+    c.active = n_ranks > 1;
+    return 0;
+}
+
 inline void comm_destroy(Comm& c) {
     if (c.nccl) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(c.nccl); c.nccl = nullptr; }
     if (c.d_shared) cudaFree(c.d_shared);
@@ -165,6 +249,13 @@ inline void comm_destroy(Comm& c) {
     if (c.recvbuf) cudaFree(c.recvbuf);
     for (int r = 0; r < P2P_MAXR; ++r) if (c.peer_base[r]) { cudaIpcCloseMemHandle(c.peer_base[r]); c.peer_base[r] = nullptr; }
     if (c.arena) cudaFree(c.arena);
+    if (c.d_scratch) cudaFree(c.d_scratch);
+    c.d_scratch = nullptr;
+    if (c.d_if_ptr) cudaFree(c.d_if_ptr);
+    if (c.d_if_nbr) cudaFree(c.d_if_nbr);
+    if (c.d_if_pos) cudaFree(c.d_if_pos);
+    if (c.d_if_before) cudaFree(c.d_if_before);
+    c.d_if_ptr = c.d_if_nbr = c.d_if_pos = nullptr; c.d_if_before = nullptr; c.fused = false; c.F = FusedComm{};
     if (c.side) cudaStreamDestroy(c.side);
     if (c.ev_fork) cudaEventDestroy(c.ev_fork);
     if (c.ev_join) cudaEventDestroy(c.ev_join);
@@ -177,6 +268,7 @@ inline int comm_set_halo(Comm& c, int n_nbr, const int* nbr_rank, const int* sha
     c.nbr_rank.assign(nbr_rank, nbr_rank + n_nbr);
     c.shared_ptr.assign(shared_ptr, shared_ptr + n_nbr + 1);
     c.n_shared = n_nbr > 0 ? shared_ptr[n_nbr] : 0;
+    c.h_shared.assign(shared_nodes, shared_nodes + c.n_shared);
     c.launches_per_halo = n_nbr > 0 ? 1 + n_nbr : 0;
     // interface rows are separable when the shared nodes are exactly the local nodes [0, n_interface)
     {
@@ -212,8 +304,28 @@ __global__ void k_halo_add(int n, const int* nodes, const double* buf, double* v
 
 // vec[shared nodes] += sum over neighbours of their partial values.  Both sides add the same two numbers
 // (a+b == b+a), so the copies of an interface value stay bitwise identical on 1-D slab partitions.
+// peer-memory halo sum on stream s (used where NCCL is not available: ranks that are threads of one process)
+inline int comm_halo_sum_p2p(Comm& c, double* vec, cudaStream_t s) {
+    if (c.n_nbr == 0) return 0;
+    int mx = 0;
+    for (int k = 0; k < c.n_nbr; ++k) mx = std::max(mx, 3 * (c.shared_ptr[k + 1] - c.shared_ptr[k]));
+    const int nblk = std::max(1, std::min(32, (mx + 255) / 256));
+    k_halo_push<<<dim3(nblk, c.n_nbr), 256, 0, s>>>(c.peers, c.halo, vec, nullptr, 0);
+    if (c.fused) {
+        k_halo_wait_total<<<std::max(1, std::min(64, (3 * c.n_interface + 255) / 256)), 256, 0, s>>>(c.F, vec);
+    } else {
+        for (int k = 0; k < c.n_nbr; ++k)
+            k_halo_wait_add<<<nblk, 256, 0, s>>>(c.peers, c.halo, k, k == c.n_nbr - 1 ? 1 : 0, vec, nullptr, 0);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : (comm_err_ref() = "peer-memory halo sum: launch failed", 1);
+}
+
 inline int comm_halo_sum(Comm& c, double* vec, cudaStream_t s) {
     if (!c.active || c.n_shared == 0) return 0;
+    if (!c.nccl) {
+        if (!c.p2p) { comm_err_ref() = "halo sum: no communicator"; return 1; }
+        return comm_halo_sum_p2p(c, vec, s);
+    }
     NcclApi* api = nccl_api();
     if (!api) return 1;
     k_halo_pack<<<(3 * c.n_shared + 255) / 256, 256, 0, s>>>(c.n_shared, c.d_shared, vec, c.sendbuf);
@@ -233,6 +345,11 @@ inline int comm_halo_sum(Comm& c, double* vec, cudaStream_t s) {
 
 inline int comm_allreduce_sum(Comm& c, double* dev, int n, cudaStream_t s) {
     if (!c.active) return 0;
+    if (!c.nccl) {
+        if (!c.p2p || n > 2) { comm_err_ref() = "all-reduce: no communicator"; return 1; }
+        k_p2p_allreduce_vals<<<1, 32, 0, s>>>(c.peers, dev, n);
+        return 0;
+    }
     NcclApi* api = nccl_api();
     if (!api) return 1;
     NCK(api->AllReduce(dev, dev, (size_t)n, ncclDouble, ncclSum, c.nccl, s));
@@ -240,8 +357,19 @@ inline int comm_allreduce_sum(Comm& c, double* dev, int n, cudaStream_t s) {
 }
 
 // host int max across ranks (fail flags); uses a tiny device buffer
-inline int comm_host_max(Comm& c, int* v) {
+inline int comm_host_max(Comm& c, int* v, cudaStream_t s = nullptr) {
     if (!c.active) return 0;
+    if (!c.nccl) {
+        if (!c.p2p) { comm_err_ref() = "all-reduce: no communicator"; return 1; }
+        const double x = *v != 0 ? 1.0 : 0.0;                       // sum of 0 / 1 flags: non-zero iff any rank raised one
+        double y = 0.0;
+        if (cudaMemcpyAsync(c.d_scratch, &x, sizeof(double), cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
+        k_p2p_allreduce_vals<<<1, 32, 0, s>>>(c.peers, c.d_scratch, 1);
+        if (cudaMemcpyAsync(&y, c.d_scratch, sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) return 1;
+        if (cudaStreamSynchronize(s) != cudaSuccess) { comm_err_ref() = "all-reduce failed"; return 1; }
+        *v = y != 0.0 ? 1 : 0;
+        return 0;
+    }
     NcclApi* api = nccl_api();
     if (!api) return 1;
     int* d = nullptr;

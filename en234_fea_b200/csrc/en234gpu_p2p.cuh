@@ -17,7 +17,7 @@
 namespace en234k {
 
 constexpr int P2P_MAXR = 16;
-constexpr long long P2P_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s at 2 GHz
+constexpr long long P2P_TIMEOUT_CYCLES = 4000000000LL;   // default ~2 s at 2 GHz (EN234_P2P_TIMEOUT_MS overrides)
 
 struct ArenaHdr {
     unsigned long long ar_flag[2][P2P_MAXR];   // all-reduce: sequence number per (parity, source rank)
@@ -27,7 +27,9 @@ struct ArenaHdr {
     unsigned int ticket[P2P_MAXR];             // per-neighbour CTA tickets of k_halo_push
     unsigned int ticket_wait;
     int error;
-    int pad[2];
+    unsigned int tk_spmv, tk_upd;              // last-CTA tickets of the fused PCG kernels (k_spmv tail, k_cg_update tail)
+    unsigned int arrive;                       // warps of the fused k_spmv that have finished their interface rows
+    int pad[3];
 };
 
 struct PeerSet {
@@ -35,6 +37,7 @@ struct PeerSet {
     ArenaHdr* arena[P2P_MAXR];     // arena[me] is local
     double* halo[P2P_MAXR];        // halo receive area of each rank: [source rank][parity][cap]
     long long cap;                 // doubles per (source, parity)
+    long long timeout;             // spin time-out in SM clock cycles
 };
 
 struct HaloSet {
@@ -47,10 +50,18 @@ struct HaloSet {
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     return *(const volatile unsigned long long*)p;
 }
-__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long seq, int* error) {
+// A time-out (a peer stopped responding) raises arena->error AND the solver's stop / fail flags, so every later kernel of
+// the captured iterations returns at once instead of spinning again; the communicator must be rebuilt afterwards (the
+// sequence counters of the ranks no longer agree).
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long seq, int* error,
+                                           long long timeout = P2P_TIMEOUT_CYCLES, CgScalars* S = nullptr) {
     const long long t0 = clock64();
     while (ld_volatile_u64(flag) < seq) {
-        if (clock64() - t0 > P2P_TIMEOUT_CYCLES) { *(volatile int*)error = 1; return false; }
+        if (clock64() - t0 > timeout) {
+            *(volatile int*)error = 1;
+            if (S) { *(volatile int*)&S->fail = 1; *(volatile int*)&S->stop = 1; }
+            return false;
+        }
         __nanosleep(20);
     }
     return true;
@@ -77,7 +88,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_p2p_allreduce(PeerSet P, const 
         *(volatile double*)&dst->ar_val[par][P.me][1] = b;
         __threadfence_system();
         *(volatile unsigned long long*)&dst->ar_flag[par][P.me] = seq;
-        spin_until(&mine->ar_flag[par][r], seq, &mine->error);
+        spin_until(&mine->ar_flag[par][r], seq, &mine->error, P.timeout, check_stop ? const_cast<CgScalars*>(S) : nullptr);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -128,7 +139,7 @@ __global__ void __launch_bounds__(256) k_halo_wait_add(PeerSet P, HaloSet H, int
     const unsigned long long seq = mine->halo_seq + 1;
     const int par = (int)(seq & 1ULL);
     const int nb = H.nbr_rank[k];
-    if (threadIdx.x == 0) spin_until(&mine->halo_flag[nb], seq, &mine->error);
+    if (threadIdx.x == 0) spin_until(&mine->halo_flag[nb], seq, &mine->error, P.timeout, check_stop ? const_cast<CgScalars*>(S) : nullptr);
     __syncthreads();
     __threadfence_system();
     const int off = H.ptr[k], cnt = 3 * (H.ptr[k + 1] - H.ptr[k]);
@@ -145,6 +156,152 @@ __global__ void __launch_bounds__(256) k_halo_wait_add(PeerSet P, HaloSet H, int
             if (tk == gridDim.x - 1) { mine->ticket_wait = 0; mine->halo_seq = seq; }
         }
     }
+}
+
+// ---- collectives folded into the PCG kernels (no kernel of their own) ---------------------------------------------------
+// The producer of a dot product (k_spmv for p.Ap, k_cg_update for r.r / r.z) ends with a last-CTA ticket: that CTA reduces
+// the kernel's per-CTA partials in the fixed order and stores the rank's sum into every rank's arena slot, then the flag.
+// The consumer kernel (k_cg_update / k_cg_pupdate) issues its first vector loads, then every CTA spins on the LOCAL
+// arena flags and adds the slots in rank order: bitwise identical sums on all ranks, no single-CTA all-reduce launch on
+// the critical path.  Sequence numbers: arena->ar_seq counts completed all-reduces; producers use ar_seq + 1, the
+// consumer's last CTA (ticket) advances it after every CTA has read it.  Two parity slots suffice: a rank can only push
+// sequence s + 2 after it consumed s + 1, which its peers pushed after they had consumed s.
+// Halo sums: the warps of k_spmv store the A p values of interface rows straight into the neighbours' receive areas and
+// count themselves off once their interface rows are done (interface rows are the first local rows); the last warp
+// raises the neighbours' flags.  The consumer k_cg_update adds what arrived to its own partial value in ascending RANK
+// order (its own contribution inserted at its rank), so every copy of an interface value is the bitwise identical sum on
+// every rank that holds it, also for nodes shared by more than two ranks.
+struct FusedComm {
+    int active;                       // 0: one GPU, NCCL path or the unfused peer-memory path
+    int halo_in_spmv;                 // 1: k_spmv pushes the interface rows itself (assembled operator)
+    PeerSet P;
+    int n_nbr;
+    int nbr_rank[P2P_MAXR];
+    int n_if;                         // interface nodes are the local rows [0, n_if)
+    const int* if_ptr;                // n_if + 1: entries of interface node i
+    const int* if_nbr;                // neighbour slot k of the entry; a node's entries are in ascending neighbour rank
+    const int* if_pos;                // position of the node in the list shared with that neighbour
+    const unsigned char* if_before;   // per interface node: number of its entries whose rank is below this rank
+};
+
+__device__ __forceinline__ double* halo_send_area(const FusedComm& F, int k, int par) {
+    return F.P.halo[F.nbr_rank[k]] + ((long long)F.P.me * 2 + par) * F.P.cap;
+}
+__device__ __forceinline__ const double* halo_recv_area(const FusedComm& F, int k, int par) {
+    return F.P.halo[F.P.me] + ((long long)F.nbr_rank[k] * 2 + par) * F.P.cap;
+}
+
+// all threads of the CTA; a and b are CTA-uniform
+__device__ __forceinline__ void p2p_push2(const PeerSet& P, unsigned long long seq, double a, double b) {
+    const int par = (int)(seq & 1ULL);
+    const int r = threadIdx.x;
+    if (r < P.n_ranks) {
+        ArenaHdr* dst = P.arena[r];
+        *(volatile double*)&dst->ar_val[par][P.me][0] = a;
+        *(volatile double*)&dst->ar_val[par][P.me][1] = b;
+        __threadfence_system();
+        *(volatile unsigned long long*)&dst->ar_flag[par][P.me] = seq;
+    }
+}
+
+// all threads of the CTA (>= 64 threads): waits for all-reduce `seq` (and, when hseq != 0, for the halo pushes of all
+// neighbours), returns the two sums in every thread.  sh: 2 doubles of shared memory.
+__device__ __forceinline__ void p2p_wait2(const FusedComm& F, unsigned long long seq, unsigned long long hseq, CgScalars* S,
+                                          double* sh, double& a, double& b) {
+    ArenaHdr* mine = F.P.arena[F.P.me];
+    const int par = (int)(seq & 1ULL);
+    const int t = threadIdx.x;
+    if (t < F.P.n_ranks) spin_until(&mine->ar_flag[par][t], seq, &mine->error, F.P.timeout, S);
+    else if (hseq != 0ULL && t >= 32 && t < 32 + F.n_nbr)
+        spin_until(&mine->halo_flag[F.nbr_rank[t - 32]], hseq, &mine->error, F.P.timeout, S);
+    __syncthreads();
+    if (t == 0) {
+        __threadfence_system();
+        double sa = 0.0, sb = 0.0;
+        for (int q = 0; q < F.P.n_ranks; ++q) {                    // fixed rank order => identical sums on all ranks
+            sa += *(volatile double*)&mine->ar_val[par][q][0];
+            sb += *(volatile double*)&mine->ar_val[par][q][1];
+        }
+        sh[0] = sa; sh[1] = sb;
+    }
+    __syncthreads();
+    __threadfence_system();
+    a = sh[0]; b = sh[1];
+}
+
+// value of interface DOF d (= 3 * node + c, node < n_if): own partial value and the neighbours' in ascending rank order
+__device__ __forceinline__ double halo_total(const FusedComm& F, int hpar, int d, double own) {
+    const int i = d / 3, c = d - 3 * i;
+    const int e0 = F.if_ptr[i], cnt = F.if_ptr[i + 1] - e0, before = F.if_before[i];
+    double s = 0.0;
+    for (int t = 0; t <= cnt; ++t) {
+        double v;
+        if (t == before) v = own;
+        else {
+            const int j = e0 + (t > before ? t - 1 : t);
+            v = __ldcv(halo_recv_area(F, F.if_nbr[j], hpar) + 3 * (size_t)F.if_pos[j] + c);
+        }
+        s = t == 0 ? v : s + v;
+    }
+    return s;
+}
+
+// vec[interface DOFs] = own partial value + what the neighbours pushed, in ascending rank order (halo_total); waits for all
+// neighbours' flags first; the last CTA advances the halo sequence counter.  Replaces the per-neighbour k_halo_wait_add
+// launches where the interface tables exist.
+__global__ void __launch_bounds__(256) k_halo_wait_total(FusedComm F, double* __restrict__ vec) {
+    ArenaHdr* mine = F.P.arena[F.P.me];
+    const unsigned long long hseq = ld_volatile_u64(&mine->halo_seq) + 1ULL;
+    const int hpar = (int)(hseq & 1ULL);
+    if (threadIdx.x < F.n_nbr) spin_until(&mine->halo_flag[F.nbr_rank[threadIdx.x]], hseq, &mine->error, F.P.timeout);
+    __syncthreads();
+    __threadfence_system();
+    const int n3 = 3 * F.n_if;
+    for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n3; d += gridDim.x * blockDim.x) vec[d] = halo_total(F, hpar, d, vec[d]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int tk = atomicAdd(&mine->ticket_wait, 1u);
+        if (tk == gridDim.x - 1) { mine->ticket_wait = 0; mine->halo_seq = hseq; }
+    }
+}
+
+// one warp: all-reduce (sum) of n <= 2 device scalars in place, through the arenas, added in rank order
+__global__ void k_p2p_allreduce_vals(PeerSet P, double* vals, int n) {
+    ArenaHdr* mine = P.arena[P.me];
+    const unsigned long long seq = ld_volatile_u64(&mine->ar_seq) + 1ULL;
+    const int par = (int)(seq & 1ULL);
+    const double a = vals[0], b = n > 1 ? vals[1] : 0.0;
+    __syncwarp();
+    const int r = threadIdx.x;
+    if (r < P.n_ranks) {
+        ArenaHdr* dst = P.arena[r];
+        *(volatile double*)&dst->ar_val[par][P.me][0] = a;
+        *(volatile double*)&dst->ar_val[par][P.me][1] = b;
+        __threadfence_system();
+        *(volatile unsigned long long*)&dst->ar_flag[par][P.me] = seq;
+        spin_until(&mine->ar_flag[par][r], seq, &mine->error, P.timeout);
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        double sa = 0.0, sb = 0.0;
+        for (int q = 0; q < P.n_ranks; ++q) {
+            sa += *(volatile double*)&mine->ar_val[par][q][0];
+            sb += *(volatile double*)&mine->ar_val[par][q][1];
+        }
+        vals[0] = sa;
+        if (n > 1) vals[1] = sb;
+        mine->ar_seq = seq;
+    }
+}
+
+// single CTA: reduce the partials of an operator kernel that has no tail of its own (matrix-free operators) and push
+__global__ void __launch_bounds__(VEC_THREADS) k_p2p_push(PeerSet P, const double* partA, int nA, const CgScalars* S) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    if (S->stop) return;
+    const double a = reduce_partials<VEC_THREADS>(partA, nA, red);
+    p2p_push2(P, ld_volatile_u64(&P.arena[P.me]->ar_seq) + 1ULL, a, 0.0);
 }
 
 }  // namespace en234k

@@ -497,6 +497,17 @@ en234host_part_t en234host_partition(en234host_model_t w, int n_ranks, int rank)
         long long lf = nl * r / n_ranks;
         return lf * layer;
     };
+    // every rank validates the whole split, so an impossible one (more ranks than layers / elements) is refused on all
+    // ranks alike instead of leaving one rank with an empty mesh while the others wait in the communicator set-up
+    for (int r = 0; r < n_ranks; ++r) {
+        const long long a = first_of(r), b = r + 1 == n_ranks ? E : first_of(r + 1);
+        if (b <= a) {
+            g_err = "partition: rank " + std::to_string(r) + " of " + std::to_string(n_ranks) + " would get no elements (" +
+                    std::to_string(E) + " elements; structured blocks are split on whole z-layers)";
+            delete p;
+            return nullptr;
+        }
+    }
     const long long e0 = first_of(rank), e1 = rank + 1 == n_ranks ? E : first_of(rank + 1);
     // which ranks touch each node: since ranges are contiguous, compute min/max rank per node
     std::vector<int> rmin(m.n_nodes, n_ranks), rmax(m.n_nodes, -1);

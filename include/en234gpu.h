@@ -218,6 +218,54 @@ int en234gpu_set_partition(en234gpu_handle h, int n_neighbours, const int* neigh
 int en234gpu_comm_arena(en234gpu_handle h, int max_shared_nodes, char* handle64);
 int en234gpu_comm_connect(en234gpu_handle h, const char* handles);
 
+/* ---- several GPUs behind one handle, in one process (no MPI / torchrun / NCCL needed by the caller).
+ * The reference's driver is one serial program (src/main.f90 -> src/staticstep.f90:93-160); this is the entry a Fortran
+ * driver binds to use all GPUs of a node without changing its structure: en234gpu_create_multi takes the WHOLE mesh (same
+ * arrays as en234gpu_create), splits the elements into n_parts contiguous ranges (whole layers of a structured block),
+ * creates one context per part on devices[part] (NULL: part p on device p mod device count) — each driven by its own host
+ * thread inside the library — and connects them through peer memory (cudaDeviceEnablePeerAccess).  The en234gpu_multi_*
+ * calls below have the argument lists of their single-GPU namesakes, with whole-mesh arrays in the reference's layouts;
+ * the norms, iteration counts and fail flags they return are the global ones.  The collectives of the PCG loop (halo sums
+ * of A p on shared nodes, the three dot products) are folded into the kernels (peer-memory stores + flags).
+ * devices[] may repeat a device (tests on a one-GPU box; the parts' kernels are then co-scheduled on it).
+ * Element types: the symmetric ones (1001, U1, 1002, U2); methods EN234_SOLVE_PCG_BSR / _MATRIXFREE. */
+typedef struct en234gpu_multi_ctx* en234gpu_multi_handle;
+int en234gpu_create_multi(en234gpu_multi_handle* h, int n_parts, const int* devices, int n_nodes, int n_elements,
+                          const double* coords, const int* connectivity, const int* element_flag,
+                          const int* element_prop_index, const double* element_properties, int n_element_properties);
+int en234gpu_multi_destroy(en234gpu_multi_handle h);
+int en234gpu_multi_set_operator_mode(en234gpu_multi_handle h, int method);
+int en234gpu_multi_assemble(en234gpu_multi_handle h, const double* dof_total, const double* dof_increment,
+                            const double* f_element_ext, double* rforce, double* nodal_force_norm, int* fail);
+int en234gpu_multi_apply_boundaryconditions(en234gpu_multi_handle h, const double* f_ext, int n_fixed, const int* fixed_dof,
+                                            const double* fixed_correction, double* unbalanced_force_norm);
+int en234gpu_multi_solve(en234gpu_multi_handle h, int method, double cg_tolerance, int max_cg_iterations,
+                         double* dof_increment, double* correction_norm, int* cg_iterations, int* fail);
+/* device-resident variants (see en234gpu_upload_state ... above) */
+int en234gpu_multi_upload_state(en234gpu_multi_handle h, const double* dof_total, const double* dof_increment,
+                                const double* f_element_ext, const double* f_ext, int n_fixed, const int* fixed_dof,
+                                const double* fixed_value);
+int en234gpu_multi_assemble_dev(en234gpu_multi_handle h, double* nodal_force_norm, int* fail);
+int en234gpu_multi_apply_boundaryconditions_dev(en234gpu_multi_handle h, double* unbalanced_force_norm);
+int en234gpu_multi_solve_dev(en234gpu_multi_handle h, int method, double cg_tolerance, int max_cg_iterations,
+                             double* correction_norm, int* cg_iterations, int* fail);
+int en234gpu_multi_zero_increment_dev(en234gpu_multi_handle h);
+int en234gpu_multi_download_state(en234gpu_multi_handle h, double* dof_increment, double* rforce);
+/* inspection */
+/* The element partition en234gpu_create_multi builds (host code, no device needed): contiguous element ranges (whole layers
+ * of a layer-numbered block), local nodes = interface nodes first then interior, each in ascending global order.
+ * sizes[6] = local nodes, local elements, first element (0-based), interface nodes, neighbours, total shared entries;
+ * arrays: local_to_global[nodes] (0-based), local_connectivity[8*elements] (1-based local), neighbour_rank[neighbours],
+ * shared_ptr[neighbours+1], shared_nodes[shared] (local, same order on both sides), owned[nodes]. */
+int en234gpu_partition_sizes(int n_parts, int part, int n_nodes, int n_elements, const int* connectivity, int* sizes);
+int en234gpu_partition_arrays(int n_parts, int part, int n_nodes, int n_elements, const int* connectivity,
+                              int* local_to_global, int* local_connectivity, int* neighbour_rank, int* shared_ptr,
+                              int* shared_nodes, unsigned char* owned);
+int en234gpu_multi_n_parts(en234gpu_multi_handle h);
+en234gpu_handle en234gpu_multi_part_handle(en234gpu_multi_handle h, int part);
+int en234gpu_multi_part_info(en234gpu_multi_handle h, int part, int* device, int* n_nodes, int* n_elements,
+                             int* n_interface, int* n_neighbours);
+
 /* ---- measurement: device time (ms, CUDA events on the handle's stream) of the last call of each phase,
  * kernel-launch counter, and per-iteration SpMV time of the last solve */
 struct en234gpu_stats {
@@ -229,6 +277,8 @@ struct en234gpu_stats {
                                     matrix-free operator multiplies by that single K_e */
 };
 int en234gpu_get_stats(en234gpu_handle h, struct en234gpu_stats* s);
+/* slowest part's phase times, launch counters summed over the parts */
+int en234gpu_multi_get_stats(en234gpu_multi_handle h, struct en234gpu_stats* s);
 /* average device time (ms, CUDA events on the handle's stream) of `reps` back-to-back launches of the operator
  * kernel y = A p (method 0: block-CSR SpMV; 1: matrix-free apply) after `warm` untimed ones — the per-launch
  * duration the roofline figures are computed from */

@@ -710,3 +710,62 @@ def test_explicit_dynamics_native_element_with_density_and_tractions():
         assert relmax(res[k], ref[k]) < 1e-10, k
     assert np.abs(res["dof_total"]).max() > 0
     g.close()
+
+
+# ------------------------------------------------------------------------------------------- several parts behind one handle
+def _devices(n_parts):
+    """Distinct GPUs when the box has them, else all parts co-scheduled on device 0 (the library sizes the grids for that)."""
+    import ctypes as C
+    from en234_fea_b200 import api
+    nd = api.gpu_lib().en234gpu_device_count()
+    return [p % nd for p in range(n_parts)] if nd >= n_parts else [0] * n_parts
+
+
+@pytest.mark.parametrize("dims,n_parts,method", [((6, 5, 8), 2, 0), ((5, 4, 9), 3, 0), ((6, 5, 8), 2, 1), ((4, 4, 8), 4, 0)])
+def test_multi_handle_from_plain_c_matches_one_device(dims, n_parts, method):
+    """tests/c/multi_check.c: a C program that includes include/en234gpu.h only drives en234gpu_create_multi (partition
+    inside the library, peer-memory collectives folded into the PCG kernels, one host thread per part) and compares the
+    static step with the one-device handle."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(__file__), "c", "multi_check")
+    assert os.path.exists(exe), "tests/c/multi_check is built by __graft_entry__.build()"
+    env = dict(os.environ, EN234_P2P_TIMEOUT_MS="20000")
+    out = subprocess.run([exe] + [str(d) for d in dims] + [str(n_parts), ",".join(str(d) for d in _devices(n_parts)), str(method)],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
+    print(out.stdout)
+    assert out.returncode == 0, out.stdout
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_multi_handle_static_step_matches_oracle(fused, monkeypatch):
+    """The whole-mesh C ABI over 3 parts against the oracle (skyline LDU) on the same model: u and rforce within 1e-10,
+    PCG iteration count within 2 of the CPU recurrences; collectives folded into the kernels (default) and as separate
+    kernels (EN234_P2P_FUSED=0)."""
+    from en234_fea_b200 import MultiGpuSystem
+    monkeypatch.setenv("EN234_P2P_FUSED", fused)
+    monkeypatch.setenv("EN234_P2P_TIMEOUT_MS", "20000")
+    m = Model.from_text(synthetic_block_input(6, 5, 9, jitter=0.2, cg_tolerance=1e-26, cg_maxit=5000))
+    fe, fx, fd, fv, fc = m.evaluate_loads(0.0, 1.0)
+    g = MultiGpuSystem(m, devices=_devices(3))
+    z = np.zeros(g.ndof)
+    rf, nrm, fail = g.assemble(z, z)
+    assert not fail
+    g.apply_boundaryconditions(fx, fd, fc)
+    du, corr, its, sfail = g.solve(z, 0, 1e-26, 5000)
+    assert not sfail
+    rf, nrm2, fail = g.assemble(z, du)
+    unb = g.apply_boundaryconditions(fx, fd, fv - du[fd])
+    ref = ob.OracleModel(m.arrays(), solvertype=1).run_static()
+    refcg = ob.OracleModel(m.arrays(), solvertype=2, cg_check_linear=1).run_static()
+    assert relmax(du, ref["dof_total"]) < TOL_U
+    assert relmax(rf, ref["rforce"]) < TOL_U
+    assert abs(its - int(refcg["cg_iterations"][0])) <= 2
+    assert unb / nrm2 < 1e-9
+    # device-resident variants
+    g.upload_state(z, z, None, fx, fd, fv)
+    g.zero_increment_dev()
+    g.assemble_dev(); g.apply_boundaryconditions_dev()
+    _, its2, sfail = g.solve_dev(0, 1e-26, 5000)
+    du2, rf2 = g.download_state()
+    assert its2 == its and np.array_equal(du2, du)
+    g.close()

@@ -371,6 +371,26 @@ def test_partition_maps():
     assert sorted(seen_elems) == list(range(m.n_elements))
 
 
+def test_library_partition_equals_host_partition_and_refuses_empty_parts():
+    """en234gpu_create_multi partitions inside liben234gpu.so (en234gpu_partition.h); the one-process-per-GPU mode uses
+    en234host_partition: both must produce the same numbering, shared lists and ownership."""
+    from en234_fea_b200 import library_partition
+    for dims, P in (((4, 4, 8), 4), ((5, 3, 6), 3), ((3, 3, 3), 2), ((6, 5, 7), 2)):
+        m = Model.from_text(synthetic_block_input(*dims, jitter=0.1))
+        a = m.arrays()
+        for r in range(P):
+            hp, lp = Partition(m, P, r), library_partition(a["connectivity"], m.n_nodes, P, r)
+            for k in ("local_to_global_node", "connectivity", "neighbour_rank", "shared_ptr", "shared_nodes", "local_elements"):
+                assert np.array_equal(hp.ints(k), lp[k]), (dims, P, r, k)
+            assert np.array_equal(hp.owned(), lp["owned"]) and hp.ints("n_interface")[0] == lp["n_interface"]
+    m = Model.from_text(synthetic_block_input(3, 3, 2))
+    for r in range(4):                                            # every rank refuses alike: no rank is left waiting
+        with pytest.raises(RuntimeError, match="would get no elements"):
+            Partition(m, 4, r)
+    with pytest.raises(RuntimeError, match="fewer elements"):
+        library_partition(m.arrays()["connectivity"], m.n_nodes, 40, 0)
+
+
 # ------------------------------------------------------------------------------------------- C ABI
 def test_c_abi_exports_every_declared_symbol():
     for header, lib, expected in (("en234gpu.h", api.gpu_lib(), api.GPU_SYMBOLS), ("en234host.h", api.host_lib(), api.HOST_SYMBOLS)):

@@ -91,6 +91,7 @@ struct en234gpu_ctx {
     DevBuf<int> bc_rows;         // block rows touched by the prescribed DOFs (prescribed nodes and their neighbours)
     DevBuf<uint8_t> bc_affected; // the same set as a per-node flag
     int n_bc_rows = 0;
+    bool bc_rows_valid = false;  // bc_rows / bc_affected describe h_fixdof
     std::vector<int> h_fixdof;   // last prescribed-DOF list (the row subset is rebuilt only when it changes)
     bool diag_valid = false;
     int spmv_occ = 4;
@@ -138,6 +139,7 @@ static Mesh mesh_of(en234gpu_ctx* c) {
 
 extern "C" {
 
+static int preallocate_for_shared_device(en234gpu_ctx* c);
 const char* en234gpu_last_error(void) { return g_err.c_str(); }
 
 int en234gpu_device_count(void) {
@@ -375,6 +377,7 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
         const int rcs = mf_set_congruent(c->mf, K0.data(), N, adj_ptr, adj, slot, browptr, bcol);
         if (rcs == 1) { delete c; return set_err("matrix-free set-up failed (congruent mesh row table)"); }
     }
+    if (g_sm_share > 1 && preallocate_for_shared_device(c)) { delete c; return 1; }
     *out = c;
     return 0;
 }
@@ -411,7 +414,30 @@ int en234gpu_set_stream(en234gpu_handle c, void* s) {
 // ---------------------------------------------------------------------------------------------------------
 static int read_scalars(en234gpu_ctx* c) {
     CK(cudaMemcpyAsync(c->hS, c->S.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+    // a peer-memory collective that timed out anywhere before this point (halo sums and all-reduces of the assembly /
+    // boundary-condition phases included) is reported here, not at some later solve
+    if (c->comm.p2p)
+        CK(cudaMemcpyAsync(&c->hPoll[0].p2p_error, &((ArenaHdr*)c->comm.arena)->error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->comm.p2p && c->hPoll[0].p2p_error)
+        return set_err("peer-memory collective timed out (a rank stopped responding); the communicator must be rebuilt");
+    return 0;
+}
+
+// Several parts of one mesh on ONE device (en234gpu_create_multi with a repeated device): a device memory allocation is an
+// implicit synchronisation point of the whole device, and a part whose kernel is waiting for another part's push must
+// never sit behind one — so everything the steady-state calls would allocate lazily is allocated at creation.
+static int preallocate_for_shared_device(en234gpu_ctx* c) {
+    const size_t need_ke = (size_t)((c->E + 3) / 4) * 4 * 576;
+    if (!c->asm_rows) { CK(c->Ke.alloc(need_ke)); }
+    CK(c->Re.alloc((size_t)c->E * 24));
+    CK(c->diag.alloc((size_t)c->ndof));
+    CK(c->bc_affected.alloc(c->N));
+    CK(cudaMemset(c->bc_affected.p, 0, c->N));
+    CK(c->bc_rows.alloc(c->N));
+    CK(c->fixdof.alloc((size_t)c->ndof));
+    CK(c->fixval.alloc((size_t)c->ndof));
+    c->mf.affected = c->bc_affected.p;
     return 0;
 }
 
@@ -474,7 +500,7 @@ int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail
         } else if (c->any_neo && with_matrix) k_element_blocks<true, true, LoadSum><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
         else if (c->any_neo) k_element_blocks<true, false, LoadSum><<<c->grid_elem0, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
         else if (with_matrix) k_element_blocks<false, true, LoadSum><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
-        else k_element_forces<LoadSum><<<c->grid_elem0, 256, 0, c->stream>>>(EA, ld);
+        else launch_element_forces(c->mf, EA, ld, c->grid_elem0, c->stream);
         GatherArgs G;
         G.M = EA.M; G.Ke = c->Ke.p; G.Re = c->Re.p; G.felem = felem;
         G.val = c->val.p; G.rhs = c->rhs.p; G.rforce = c->rforce.p; G.partials = c->part.p; G.S = c->S.p;
@@ -524,7 +550,8 @@ static int upload_fixed(en234gpu_ctx* c, int n_fixed, const int* fixed_dof, cons
         else v[it->second] = fixed_value[i];
     }
     c->n_fixed = (int)d.size();
-    if (d != c->h_fixdof || c->bc_affected.n == 0) {
+    if (d != c->h_fixdof || !c->bc_rows_valid) {
+        c->bc_rows_valid = true;
         // rows changed by fixdof: the prescribed nodes and every node coupled to one (the pattern is symmetric)
         std::vector<uint8_t> aff(c->N, 0);
         for (int dof : d) {
@@ -536,7 +563,7 @@ static int upload_fixed(en234gpu_ctx* c, int n_fixed, const int* fixed_dof, cons
         for (int i = 0; i < c->N; ++i) if (aff[i]) rows.push_back(i);
         c->n_bc_rows = (int)rows.size();
         if (c->bc_affected.n == 0) CK(c->bc_affected.alloc(c->N));
-        if (c->bc_rows.n < rows.size()) CK(c->bc_rows.alloc(rows.size()));
+        if (c->bc_rows.n < rows.size()) CK(c->bc_rows.alloc(std::max(rows.size(), (size_t)1)));
         CK(cudaMemcpyAsync(c->bc_affected.p, aff.data(), aff.size(), cudaMemcpyHostToDevice, c->stream));
         if (!rows.empty()) CK(cudaMemcpyAsync(c->bc_rows.p, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
@@ -567,7 +594,7 @@ static int apply_bc_common(en234gpu_ctx* c, int values_are_corrections, double* 
     B.cflag = c->cflag.p; B.cval = c->cval.p; B.minv = c->minv.p; B.partials = c->part.p;
     const double* part = c->part.p;
     int npart = c->grid_bc;
-    const bool subset = c->mode == EN234_SOLVE_PCG_BSR && c->diag_valid && c->bc_affected.n > 0;
+    const bool subset = c->mode == EN234_SOLVE_PCG_BSR && c->diag_valid && c->bc_rows_valid;
     int grid_bc = c->grid_bc;
     if (subset) {
         B.rows = c->bc_rows.p; B.n_rows = c->n_bc_rows;
@@ -824,41 +851,79 @@ static int build_graph(en234gpu_ctx* c, int method) {
 // ---- BiCGSTAB (unsymmetric stiffness) ---------------------------------------------------------------------
 constexpr int BI_CHUNK = 8;     // BiCGSTAB iterations per CUDA-graph launch
 
-static void bicg_enqueue_iteration(en234gpu_ctx* c) {
+// partitioned runs: the two partial arrays become global sums in partA[0], partB[0] (the single-CTA consumers then read
+// one entry); returns the number of partials the consumers read
+static int bicg_allreduce2(en234gpu_ctx* c, double* partA, double* partB, int n) {
+    if (!c->comm.active) return n;
+    k_reduce2_to<<<1, VEC_THREADS, 0, c->stream>>>(partA, partB, n, partA, partB);
+    k_pack2<<<1, 1, 0, c->stream>>>(partA, partB);
+    if (comm_allreduce_sum(c->comm, partA, 2, c->stream)) return -1;
+    k_unpack2<<<1, 1, 0, c->stream>>>(partA, partB);
+    c->st.kernel_launches += 3;
+    return 1;
+}
+// y = A x on all local rows, interface rows halo-summed on partitioned runs
+static int bicg_operator(en234gpu_ctx* c, const double* x, double* y) {
+    int np = 0;
+    launch_spmv_rows(c, x, y, 0, c->N, 0, 0, &np);
+    if (c->comm.active) {
+        if (comm_halo_sum(c->comm, y, c->stream)) return 1;
+        c->st.kernel_launches += c->comm.launches_per_halo;
+    }
+    return 0;
+}
+
+static int bicg_enqueue_iteration(en234gpu_ctx* c) {
     const int n = c->ndof, gv = c->grid_vec, nb = (n + 255) / 256;
     double *x = c->sol.p, *r = c->r.p, *rhat = c->tmpvec.p, *p = c->p.p, *v = c->Ap.p, *y = c->tmpvec2.p, *z = c->bi_z.p, *t = c->bi_t.p;
+    const uint8_t* owned = c->have_owned ? c->owned.p : nullptr;
     BiScalars* S = c->bi_S.p;
-    int np = 0;
     k_bi_p<<<nb, 256, 0, c->stream>>>(n, S, r, v, c->minv.p, p, y);
-    launch_spmv_rows(c, y, v, 0, c->N, 0, 0, &np);
-    k_bi_dot2<<<gv, VEC_THREADS, 0, c->stream>>>(n, S, rhat, v, rhat, v, c->part2.p, c->part3.p);
-    k_bi_alpha<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, gv, S);
+    if (bicg_operator(c, y, v)) return 1;
+    k_bi_dot2<<<gv, VEC_THREADS, 0, c->stream>>>(n, S, rhat, v, rhat, v, c->part2.p, c->part3.p, owned);
+    int np = bicg_allreduce2(c, c->part2.p, c->part3.p, gv);
+    if (np < 0) return 1;
+    k_bi_alpha<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, np, S);
     k_bi_s<<<nb, 256, 0, c->stream>>>(n, S, v, c->minv.p, r, z);
-    launch_spmv_rows(c, z, t, 0, c->N, 0, 0, &np);
-    k_bi_dot2<<<gv, VEC_THREADS, 0, c->stream>>>(n, S, t, r, t, t, c->part2.p, c->part3.p);
-    k_bi_omega<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, S);
-    k_bi_x<<<gv, VEC_THREADS, 0, c->stream>>>(n, S, y, z, t, rhat, x, r, c->part2.p, c->part3.p);
-    k_bi_finish<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, S);
+    if (bicg_operator(c, z, t)) return 1;
+    k_bi_dot2<<<gv, VEC_THREADS, 0, c->stream>>>(n, S, t, r, t, t, c->part2.p, c->part3.p, owned);
+    np = bicg_allreduce2(c, c->part2.p, c->part3.p, gv);
+    if (np < 0) return 1;
+    k_bi_omega<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, np, S);
+    k_bi_x<<<gv, VEC_THREADS, 0, c->stream>>>(n, S, y, z, t, rhat, x, r, c->part2.p, c->part3.p, owned);
+    np = bicg_allreduce2(c, c->part2.p, c->part3.p, gv);
+    if (np < 0) return 1;
+    k_bi_finish<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, np, S);
     c->st.kernel_launches += 8;
+    return 0;
 }
 
 // One BiCGSTAB run for A d = b from d = 0 (recurrence residual driven to (r.r)/(b.b) <= tol), result in c->sol; returns
 // the iteration count, -1 on breakdown / iteration cap, -2 on a CUDA error
 static int bicgstab_run(en234gpu_ctx* c, const double* b, double tol, int maxit) {
     const int n = c->ndof, gv = c->grid_vec;
+    const uint8_t* owned = c->have_owned ? c->owned.p : nullptr;
     if (!c->bi_graph) {
         cudaGraph_t g = nullptr;
         const long long before = c->st.kernel_launches;
         if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return -2;
-        for (int it = 0; it < BI_CHUNK; ++it) bicg_enqueue_iteration(c);
-        if (cudaStreamEndCapture(c->stream, &g) != cudaSuccess) return -2;
+        int rc = 0;
+        for (int it = 0; it < BI_CHUNK && !rc; ++it) rc = bicg_enqueue_iteration(c);
+        if (cudaStreamEndCapture(c->stream, &g) != cudaSuccess || rc) return -2;
         c->bi_graph_launches = c->st.kernel_launches - before;
         c->st.kernel_launches = before;
         if (cudaGraphInstantiate(&c->bi_graph, g, 0) != cudaSuccess) return -2;
         cudaGraphDestroy(g);
     }
-    k_bi_init<<<gv, VEC_THREADS, 0, c->stream>>>(n, b, c->sol.p, c->r.p, c->tmpvec.p, c->p.p, c->Ap.p, c->part2.p);
-    k_bi_init_finish<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, gv, c->bi_S.p, tol, maxit);
+    k_bi_init<<<gv, VEC_THREADS, 0, c->stream>>>(n, b, c->sol.p, c->r.p, c->tmpvec.p, c->p.p, c->Ap.p, c->part2.p, owned);
+    int np = gv;
+    if (c->comm.active) {
+        k_reduce_to<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, gv, c->part2.p);
+        if (comm_allreduce_sum(c->comm, c->part2.p, 1, c->stream)) return -2;
+        c->st.kernel_launches += 1;
+        np = 1;
+    }
+    k_bi_init_finish<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, np, c->bi_S.p, tol, maxit);
     c->st.kernel_launches += 2;
     for (;;) {
         if (cudaMemcpyAsync(c->h_bi_S, c->bi_S.p, sizeof(BiScalars), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -2;
@@ -873,29 +938,33 @@ static int bicgstab_run(en234gpu_ctx* c, const double* b, double tol, int maxit)
 // A x = rhs to a TRUE residual (b - A x).(b - A x)/(b.b) <= tol: BiCGSTAB runs on the current true residual, the
 // corrections are accumulated (iterative refinement).  The Newton history of the reference's golden log needs solves of
 // direct-solver quality (6 printed digits of a 1e-4 second correction), which a single recurrence-residual stop misses.
+// Partitioned runs: halo sums of A y / A z on interface rows, owned-only dot products all-reduced over the ranks (every
+// rank carries bitwise identical recurrence scalars, so all ranks stop in the same iteration).
 static int bicgstab_solve(en234gpu_ctx* c, double tol, int maxit, double* correction_norm, int* iterations, int* fail) {
     if (c->mode != EN234_SOLVE_PCG_BSR || !c->matrix_valid) return set_err("BiCGSTAB needs the assembled matrix (solve called before assemble?)");
-    if (c->comm.active) return set_err("BiCGSTAB is a single-GPU solver");
     if (phase_begin(c)) return 1;
     const int n = c->ndof, gv = c->grid_vec, nb = (n + 255) / 256;
+    const uint8_t* owned = c->have_owned ? c->owned.p : nullptr;
     if (c->bi_z.n < (size_t)n) {
         CK(c->bi_z.alloc(n)); CK(c->bi_t.alloc(n)); CK(c->bi_xt.alloc(n)); CK(c->bi_b.alloc(n)); CK(c->bi_S.alloc(1));
         CK(cudaMallocHost((void**)&c->h_bi_S, sizeof(BiScalars)));
     }
     const double tol_run = std::max(tol, 1e-24);
-    int total = 0, np = 0;
+    int total = 0;
     *fail = 0;
     double bb = 0.0, rr_prev = 0.0;
     for (int pass = 0; pass < 6; ++pass) {
         const double* b = pass == 0 ? c->rhs.p : c->bi_b.p;
         const int it = bicgstab_run(c, b, pass == 0 ? tol_run : 1e-12, std::max(1, maxit - total));
-        if (it == -2) return set_err("BiCGSTAB: CUDA error");
+        if (it == -2) return set_err(std::string("BiCGSTAB: CUDA / communicator error ") + comm_error());
         if (it < 0) { *fail = 1; break; }
         total += it;
         k_bi_accumulate<<<nb, 256, 0, c->stream>>>(n, c->sol.p, c->bi_xt.p, pass == 0);
-        launch_spmv_rows(c, c->bi_xt.p, c->bi_t.p, 0, c->N, 0, 0, &np);
-        k_bi_residual<<<gv, VEC_THREADS, 0, c->stream>>>(n, c->rhs.p, c->bi_t.p, c->bi_b.p, c->part2.p, c->part3.p);
-        k_bi_reduce2<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, gv, &c->S.p->rz[0]);
+        if (bicg_operator(c, c->bi_xt.p, c->bi_t.p)) return set_err(comm_error());
+        k_bi_residual<<<gv, VEC_THREADS, 0, c->stream>>>(n, c->rhs.p, c->bi_t.p, c->bi_b.p, c->part2.p, c->part3.p, owned);
+        const int np = bicg_allreduce2(c, c->part2.p, c->part3.p, gv);
+        if (np < 0) return set_err(comm_error());
+        k_bi_reduce2<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, np, &c->S.p->rz[0]);
         c->st.kernel_launches += 4;
         if (read_scalars(c)) return 1;
         const double rr = c->hS->rz[0];
@@ -909,7 +978,7 @@ static int bicgstab_solve(en234gpu_ctx* c, double tol, int maxit, double* correc
     *iterations = total;
     c->st.last_cg_iterations = total;
     if (!*fail) {
-        k_add_solution<<<gv, VEC_THREADS, 0, c->stream>>>(n, c->bi_xt.p, c->du.p, nullptr, c->part2.p);
+        k_add_solution<<<gv, VEC_THREADS, 0, c->stream>>>(n, c->bi_xt.p, c->du.p, owned, c->part2.p);
         c->st.kernel_launches++;
         if (finish_norm(c, c->part2.p, gv, correction_norm)) return 1;
     } else *correction_norm = 0.0;
@@ -1364,7 +1433,7 @@ static int dyn_enqueue_step(en234gpu_ctx* c, double dt, int phases = 3) {
     ElemArgs EA;
     EA.M = mesh_of(c);
     EA.Ke = nullptr; EA.Re = c->Re.p; EA.S = c->S.p;
-    k_element_forces<LoadSum><<<c->grid_elem0, 256, 0, c->stream>>>(EA, LoadSum{c->ut.p, c->du.p});
+    launch_element_forces(c->mf, EA, LoadSum{c->ut.p, c->du.p}, c->grid_elem0, c->stream);
     if (c->comm.active) {
         // partial element-force sums -> halo sum -> update (the one exchange of a step)
         GatherArgs G{};
@@ -1549,9 +1618,7 @@ int en234gpu_apply_operator(en234gpu_handle c, int method, const double* x, doub
     if (c->comm.active && c->comm.p2p) { p2p_halo_fork(c, c->tmpvec2.p, 0); p2p_halo_join(c); }
     else if (c->comm.active && comm_halo_sum(c->comm, c->tmpvec2.p, c->stream)) return set_err(comm_error());
     CK(cudaMemcpyAsync(y, c->tmpvec2.p, b, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (comm_p2p_error(c->comm)) return set_err("peer-memory halo exchange timed out (a rank stopped responding); the communicator must be rebuilt");
-    return 0;
+    return read_scalars(c);        // synchronises and reports a timed-out halo exchange
 }
 
 // ---- multi-GPU ----------------------------------------------------------------------------------------------

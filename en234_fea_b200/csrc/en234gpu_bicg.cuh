@@ -17,14 +17,16 @@ struct BiScalars {
 };
 
 // x = 0, r = rhat = b, p = v = 0 ; partial of b.b
+// (owned: per-NODE ownership mask of partitioned runs — every dot product counts each global DOF once; null = all)
+__device__ __forceinline__ bool bi_owned(const uint8_t* owned, int i) { return owned == nullptr || owned[i / 3] != 0; }
 __global__ void __launch_bounds__(VEC_THREADS) k_bi_init(int n, const double* b, double* x, double* r, double* rhat, double* p,
-                                                          double* v, double* part) {
+                                                          double* v, double* part, const uint8_t* owned = nullptr) {
     __shared__ double red[VEC_THREADS / 32 + 1];
     double s = 0.0;
     for (int i = blockIdx.x * VEC_THREADS + threadIdx.x; i < n; i += gridDim.x * VEC_THREADS) {
         const double bi = b[i];
         x[i] = 0.0; r[i] = bi; rhat[i] = bi; p[i] = 0.0; v[i] = 0.0;
-        s += bi * bi;
+        if (bi_owned(owned, i)) s += bi * bi;
     }
     const double t = block_sum<VEC_THREADS>(s, red);
     if (threadIdx.x == 0) part[blockIdx.x] = t;
@@ -51,13 +53,16 @@ __global__ void k_bi_p(int n, const BiScalars* S, const double* r, const double*
 }
 // partials of a.b and c.d
 __global__ void __launch_bounds__(VEC_THREADS) k_bi_dot2(int n, const BiScalars* S, const double* a, const double* b,
-                                                          const double* c, const double* d, double* part_ab, double* part_cd) {
+                                                          const double* c, const double* d, double* part_ab, double* part_cd,
+                                                          const uint8_t* owned = nullptr) {
     __shared__ double red[VEC_THREADS / 32 + 1];
     if (S && S->stop) return;
     double s0 = 0.0, s1 = 0.0;
     for (int i = blockIdx.x * VEC_THREADS + threadIdx.x; i < n; i += gridDim.x * VEC_THREADS) {
-        s0 += a[i] * b[i];
-        s1 += c[i] * d[i];
+        if (bi_owned(owned, i)) {
+            s0 += a[i] * b[i];
+            s1 += c[i] * d[i];
+        }
     }
     const double t0 = block_sum<VEC_THREADS>(s0, red);
     const double t1 = block_sum<VEC_THREADS>(s1, red);
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_bi_omega(const double* part_ts,
 // x += alpha y + omega z ; r = s - omega t ; partials of r.r and rhat.r
 __global__ void __launch_bounds__(VEC_THREADS) k_bi_x(int n, const BiScalars* S, const double* y, const double* z,
                                                        const double* t, const double* rhat, double* x, double* r,
-                                                       double* part_rr, double* part_rho) {
+                                                       double* part_rr, double* part_rho, const uint8_t* owned = nullptr) {
     __shared__ double red[VEC_THREADS / 32 + 1];
     if (S->stop) return;
     const double alpha = S->alpha, omega = S->omega;
@@ -105,8 +110,10 @@ __global__ void __launch_bounds__(VEC_THREADS) k_bi_x(int n, const BiScalars* S,
         x[i] = x[i] + alpha * y[i] + omega * z[i];
         const double ri = r[i] - omega * t[i];
         r[i] = ri;
-        s0 += ri * ri;
-        s1 += rhat[i] * ri;
+        if (bi_owned(owned, i)) {
+            s0 += ri * ri;
+            s1 += rhat[i] * ri;
+        }
     }
     const double t0 = block_sum<VEC_THREADS>(s0, red);
     const double t1 = block_sum<VEC_THREADS>(s1, red);
@@ -132,14 +139,16 @@ __global__ void __launch_bounds__(VEC_THREADS) k_bi_finish(const double* part_rr
 // iterative refinement: xt += d ; r_true = b0 - A xt is formed by the caller's SpMV into `Axt`; this kernel writes
 // rnew = b0 - Axt and the partials of rnew.rnew and b0.b0
 __global__ void __launch_bounds__(VEC_THREADS) k_bi_residual(int n, const double* b0, const double* Axt, double* rnew,
-                                                              double* part_rr, double* part_bb) {
+                                                              double* part_rr, double* part_bb, const uint8_t* owned = nullptr) {
     __shared__ double red[VEC_THREADS / 32 + 1];
     double s = 0.0, sb = 0.0;
     for (int i = blockIdx.x * VEC_THREADS + threadIdx.x; i < n; i += gridDim.x * VEC_THREADS) {
         const double bi = b0[i], ri = bi - Axt[i];
         rnew[i] = ri;
-        s += ri * ri;
-        sb += bi * bi;
+        if (bi_owned(owned, i)) {
+            s += ri * ri;
+            sb += bi * bi;
+        }
     }
     const double t = block_sum<VEC_THREADS>(s, red);
     const double tb = block_sum<VEC_THREADS>(sb, red);

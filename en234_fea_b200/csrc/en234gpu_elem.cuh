@@ -23,6 +23,8 @@ struct ElemArgs {
     double* Re;             // element residual entries in NODE-MAJOR order: the three components of (element e, local node
                             // a) at 3 * adj_pos[8e + a], so a node's contributions are contiguous, ascending element order
     CgScalars* S;           // nanflag (may be null)
+    double* geom = nullptr; // cached Gauss-point geometry of k_element_forces: per group of 4 elements 10 rows of 32 lanes
+                            // (lane = 8 * element-in-group + Gauss point): J^-1 (9 values) and w|J|; 640 B per element
 };
 
 template <bool NEO>
@@ -64,7 +66,25 @@ __device__ __forceinline__ void grad_acc_sm(const double* nb, const double fp[3]
         for (int j = 0; j < 3; ++j) H[3 * i + j] += u * d[j];
     }
 }
-__device__ __forceinline__ void gauss_point_eval_sm(const double* nb, int gp, double* g, GpOut& o) {
+// the second half of gauss_point_eval_sm: dN/dx and grad u from a given inverse Jacobian (same operations, same order)
+__device__ __forceinline__ void gauss_point_grad_sm(const double* nb, int gp, const Jac& jc, double* g, GpOut& o) {
+    double fp[3], fm[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const double xi = ((gp >> j) & 1) ? EN234_GP : -EN234_GP;
+        fp[j] = 1.0 + xi;
+        fm[j] = 1.0 - xi;
+    }
+    o.det = jc.det;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) o.H[q] = 0.0;
+    grad_acc_sm<0>(nb, fp, fm, jc.Ji, g, o.H); grad_acc_sm<1>(nb, fp, fm, jc.Ji, g, o.H);
+    grad_acc_sm<2>(nb, fp, fm, jc.Ji, g, o.H); grad_acc_sm<3>(nb, fp, fm, jc.Ji, g, o.H);
+    grad_acc_sm<4>(nb, fp, fm, jc.Ji, g, o.H); grad_acc_sm<5>(nb, fp, fm, jc.Ji, g, o.H);
+    grad_acc_sm<6>(nb, fp, fm, jc.Ji, g, o.H); grad_acc_sm<7>(nb, fp, fm, jc.Ji, g, o.H);
+    g[24] = jc.det;   // w = 1 for the 2x2x2 rule
+}
+__device__ __forceinline__ void gauss_point_eval_sm(const double* nb, int gp, double* g, GpOut& o, Jac* jc_out = nullptr) {
     double fp[3], fm[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -79,6 +99,7 @@ __device__ __forceinline__ void gauss_point_eval_sm(const double* nb, int gp, do
     jac_acc_sm<4>(nb, fp, fm, J); jac_acc_sm<5>(nb, fp, fm, J); jac_acc_sm<6>(nb, fp, fm, J); jac_acc_sm<7>(nb, fp, fm, J);
     Jac jc;
     invert3(J, jc);
+    if (jc_out) *jc_out = jc;
     o.det = jc.det;
 #pragma unroll
     for (int q = 0; q < 9; ++q) o.H[q] = 0.0;
@@ -260,7 +281,11 @@ __global__ void __launch_bounds__(ElemCfg<NEO>::NW * 32, 2) k_element_blocks(Ele
 #ifndef FORCES_OCC
 #define FORCES_OCC 2
 #endif
-template <class Load>
+// GEOM = 0: the Gauss-point geometry (Jacobian, cofactor inverse) is evaluated from the node coordinates;
+// GEOM = 1: the same, and J^-1, w|J| are stored in A.geom;  GEOM = 2: they are read from A.geom (streamed one group ahead) —
+// the node coordinates are then not touched at all and 40 % of the arithmetic of an element application is gone; the
+// results are bitwise those of GEOM = 0 (the stored values are the ones it computes, the remaining operations are the same).
+template <class Load, int GEOM = 0>
 __global__ void __launch_bounds__(256, FORCES_OCC) k_element_forces(ElemArgs A, Load ld) {
     constexpr int NW = 8, NS = ElemCfg<false>::NSTRIDE;
     __shared__ double nbuf_all[NW * 4 * NS];
@@ -277,20 +302,32 @@ __global__ void __launch_bounds__(256, FORCES_OCC) k_element_forces(ElemArgs A, 
         return M.conn[(size_t)p * M.E + min(4 * grp + g, M.E - 1)];
     };
     auto stage = [&](int n) {
-        nd[0] = __ldg(M.x + n); nd[1] = __ldg(M.y + n); nd[2] = __ldg(M.z + n);
+        if (GEOM != 2) { nd[0] = __ldg(M.x + n); nd[1] = __ldg(M.y + n); nd[2] = __ldg(M.z + n); }
         nd[3] = ld(3 * (size_t)n); nd[4] = ld(3 * (size_t)n + 1); nd[5] = ld(3 * (size_t)n + 2);
+    };
+    Jac jn;                                                           // GEOM = 2: geometry of the NEXT group, in flight
+    auto fetch_geom = [&](int gr) {
+        if (GEOM == 2 && gr < ngroups) {
+            const double* src = A.geom + (size_t)gr * 320 + lane;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) jn.Ji[q] = __ldcs(src + 32 * q);
+            jn.det = __ldcs(src + 32 * 9);
+        }
     };
     int grp = blockIdx.x * NW + warp;
     stage(node_of(grp));
+    fetch_geom(grp);
     int n_next = node_of(grp + W);
     for (; grp < ngroups; grp += W) {
         {
             double* dst = nbuf + g * NS + p * 6;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) dst[q] = nd[q];
+            for (int q = (GEOM == 2 ? 3 : 0); q < 6; ++q) dst[q] = nd[q];
         }
         __syncwarp();
+        Jac jc = jn;
         stage(n_next);
+        fetch_geom(grp + W);
         n_next = node_of(grp + 2 * W);
         const int e = 4 * grp + g;
         const bool valid = e < M.E;
@@ -298,7 +335,14 @@ __global__ void __launch_bounds__(256, FORCES_OCC) k_element_forces(ElemArgs A, 
         const Material mat = M.n_mats == 1 ? mat0 : M.mats[M.mat[valid ? e : M.E - 1]];
         double gg[GEOM_STRIDE];
         GpOut gp;
-        gauss_point_eval_sm(nbuf + g * NS, p, gg, gp);
+        if (GEOM == 2) gauss_point_grad_sm(nbuf + g * NS, p, jc, gg, gp);
+        else gauss_point_eval_sm(nbuf + g * NS, p, gg, gp, &jc);
+        if (GEOM == 1) {
+            double* dst = A.geom + (size_t)grp * 320 + lane;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) dst[32 * q] = jc.Ji[q];
+            dst[32 * 9] = jc.det;
+        }
         if (valid && !(gp.det != 0.0)) bad = true;
         double s[9];
         stress_linear(mat, gp.H, s);

@@ -163,6 +163,7 @@ struct LoadSum {                       // u = dof_total + dof_increment         
     const double* __restrict__ du;
     __device__ __forceinline__ double operator()(size_t d) const { return ut[d] + du[d]; }
     __device__ __forceinline__ bool stopped() const { return false; }
+    bool may_skip() const { return false; }
 };
 struct LoadMasked {                    // x with prescribed DOFs zeroed (operator P A P of the matrix-free solve)
     const double* __restrict__ x;
@@ -175,6 +176,7 @@ struct LoadMasked {                    // x with prescribed DOFs zeroed (operato
         return f ? 0.0 : v;
     }
     __device__ __forceinline__ bool stopped() const { return stop != nullptr && stop->stop != 0; }
+    bool may_skip() const { return stop != nullptr; }
 };
 
 template <int C, class Load>

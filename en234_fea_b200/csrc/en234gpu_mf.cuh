@@ -26,6 +26,10 @@ struct DominantRow { double v[243]; };
 
 struct MfData {
     double* d_fe = nullptr;         // element force scratch, node-major (3 per adjacency entry)
+    // Gauss-point geometry cache of k_element_forces (J^-1 and w|J|: 640 B per element).  The mesh never moves, so it is
+    // written by the first launch of the kernel and read by all later ones.  EN234_MF_GEOM=0 disables it (A/B).
+    double* d_geom = nullptr;
+    int geom_state = 0;             // 0 not allocated yet, 1 allocated and to be written, 2 valid, -1 disabled / no memory
     // congruent-mesh fast path: every element is a translate of element 0 (bitwise equal node offsets, same material),
     // so one 24x24 K_e serves the whole mesh and a block row is determined by WHICH local nodes of its adjacent elements
     // the node is (and where their columns sit in the row): a few dozen distinct rows on a structured block.  The
@@ -422,7 +426,29 @@ inline int mf_set_congruent(MfData& mf, const double* Ke_colmajor, int N, const 
     mf.congruent = true;
     return 0;
 }
+// Launch of the residual-only element kernel with the geometry cache in the right state.
+template <class Load>
+inline void launch_element_forces(MfData& mf, ElemArgs EA, const Load& ld, int grid, cudaStream_t s) {
+    if (mf.geom_state == 0) {
+        const char* e = getenv("EN234_MF_GEOM");
+        const size_t bytes = (size_t)((EA.M.E + 3) / 4) * 320 * sizeof(double);
+        if ((e && atoi(e) == 0) || cudaMalloc((void**)&mf.d_geom, bytes) != cudaSuccess) { cudaGetLastError(); mf.geom_state = -1; }
+        else mf.geom_state = 1;
+    }
+    EA.geom = mf.d_geom;
+    if (mf.geom_state == 2) k_element_forces<Load, 2><<<grid, 256, 0, s>>>(EA, ld);
+    else if (mf.geom_state == 1) {
+        k_element_forces<Load, 1><<<grid, 256, 0, s>>>(EA, ld);
+        // a kernel whose Load can make it return at once (PCG stop flag) may not have written the cache
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s, &cs);
+        if (cs == cudaStreamCaptureStatusNone && !ld.may_skip()) mf.geom_state = 2;
+    } else k_element_forces<Load, 0><<<grid, 256, 0, s>>>(EA, ld);
+}
+
 inline void mf_release(MfData& mf) {
+    if (mf.d_geom) cudaFree(mf.d_geom);
+    mf.d_geom = nullptr; mf.geom_state = 0;
     if (mf.d_elist) cudaFree(mf.d_elist);
     if (mf.d_fe) cudaFree(mf.d_fe);
     if (mf.d_st_val) cudaFree(mf.d_st_val);
@@ -457,7 +483,7 @@ inline void mf_stencil(const MfData& mf, const Mesh& M, const uint8_t* cflag, co
 }
 
 // y = P A P x + (I-P) x ; partials of x.y.  (cflag == null: plain A x)
-inline void mf_apply(const MfData& mf, const Mesh& M, int ndof, const uint8_t* cflag, const uint8_t* owned, const double* x,
+inline void mf_apply(MfData& mf, const Mesh& M, int ndof, const uint8_t* cflag, const uint8_t* owned, const double* x,
                      double* y, double* partials, const CgScalars* S, cudaStream_t s, long long* launches) {
     (void)ndof;
     ElemArgs EA;
@@ -467,7 +493,7 @@ inline void mf_apply(const MfData& mf, const Mesh& M, int ndof, const uint8_t* c
         mf_stencil(mf, M, cflag, owned, x, y, partials, S, s, launches, 1);
         return;
     }
-    k_element_forces<LoadMasked><<<mf.grid_elem, mf.elem_threads, 0, s>>>(EA, LoadMasked{x, cflag, S});
+    launch_element_forces(mf, EA, LoadMasked{x, cflag, S}, mf.grid_elem, s);
     k_mf_gather<<<mf.grid_gather, VEC_THREADS, 0, s>>>(M.N, M.adj_ptr, M.adj, mf.d_fe, cflag, owned, x, y, partials, S);
     *launches += 2;
 }

@@ -103,6 +103,31 @@ inline void localize_fixed(const std::vector<int>& g2l, int n_fixed, const int* 
 }
 }  // namespace
 
+// With CUDA's lazy module loading a kernel is loaded at its first launch, and loading may need a synchronisation of the
+// whole context: a part that launches some kernel for the first time would then wait for another part's kernel on the
+// same device — which may be spinning for exactly this part.  Every kernel a partitioned static step can launch is
+// therefore loaded before the parts start to depend on one another.
+static int preload_partitioned_kernels() {
+    cudaFuncAttributes a;
+#define PRELOAD(...)                                                                                          \
+    if (cudaFuncGetAttributes(&a, __VA_ARGS__) != cudaSuccess) return set_err("cannot load kernel " #__VA_ARGS__)
+    PRELOAD(k_element_blocks<false, true, LoadSum>); PRELOAD(k_element_blocks<true, true, LoadSum>);
+    PRELOAD(k_element_blocks<true, false, LoadSum>); PRELOAD(k_assemble_rows<false>); PRELOAD(k_assemble_rows<true>);
+    PRELOAD(k_element_forces<LoadSum, 0>); PRELOAD(k_element_forces<LoadSum, 1>); PRELOAD(k_element_forces<LoadSum, 2>);
+    PRELOAD(k_element_forces<LoadMasked, 0>); PRELOAD(k_element_forces<LoadMasked, 1>); PRELOAD(k_element_forces<LoadMasked, 2>);
+    PRELOAD(k_gather_rows); PRELOAD(k_gather_residual); PRELOAD(k_negate_norm); PRELOAD(k_reduce_to); PRELOAD(k_reduce2_to);
+    PRELOAD(k_pack2); PRELOAD(k_unpack2); PRELOAD(k_set_corrections); PRELOAD(k_apply_bc); PRELOAD(k_bc_rest); PRELOAD(k_bc_finalize);
+    PRELOAD(k_mask_values); PRELOAD(k_mf_color<1>); PRELOAD(k_fix_diag); PRELOAD(k_mf_gather); PRELOAD(k_mask_soa);
+    PRELOAD(k_stencil_nodes); PRELOAD(k_element_batch);
+    PRELOAD(k_halo_push); PRELOAD(k_halo_wait_add); PRELOAD(k_halo_wait_total); PRELOAD(k_p2p_allreduce);
+    PRELOAD(k_p2p_allreduce_vals); PRELOAD(k_p2p_push);
+    PRELOAD(k_cg_init); PRELOAD(k_cg_init_finish); PRELOAD(k_cg_update<true>); PRELOAD(k_cg_update<false>); PRELOAD(k_cg_pupdate);
+    PRELOAD(k_add_solution); PRELOAD(k_spmv<4, false, true>); PRELOAD(k_spmv<4, true, true>); PRELOAD(k_spmv<4, false>);
+    PRELOAD(k_spmv<4>); PRELOAD(k_spmv<5>);
+#undef PRELOAD
+    return 0;
+}
+
 extern "C" {
 
 int en234gpu_multi_destroy(en234gpu_multi_handle m) {
@@ -169,6 +194,7 @@ int en234gpu_create_multi(en234gpu_multi_handle* out, int n_parts, const int* de
             g2l[P.l2g[i]] = i;
             for (int c = 0; c < 3; ++c) xl[3 * (size_t)i + c] = coords[3 * (size_t)P.l2g[i] + c];
         }
+        if (preload_partitioned_kernels()) return 1;
         int share = 0;
         for (int q = 0; q < n_parts; ++q) share += m->dev[q] == m->dev[p] ? 1 : 0;
         g_sm_share = share;

@@ -222,28 +222,36 @@ int en234host_model_device_support(en234host_model_t w) {
     return 1;
 }
 
-int en234host_gpu_create(en234host_model_t w, int device, en234gpu_handle* h) {
-    const Model& m = w->m;
-    if (!device_supports(m, g_err)) return 1;
-    // built-in continuum elements (flag 10003) take their properties from their MATERIAL (read_input_file.f90:433-509,
-    // :756-960): one combined property array, element property index pointing into the material's section
-    std::vector<double> props = m.element_properties;
-    std::vector<int> pidx = m.element_prop_index;
+// Property table handed to en234gpu_create: the element properties followed by the material properties; built-in continuum
+// elements (flag 10003) take their properties from their MATERIAL (read_input_file.f90:433-509, :756-960), so their
+// property index points into the material's section.  Shared by the whole-mesh and the partitioned creators.
+static bool device_property_table(const Model& m, std::vector<double>& props, std::vector<int>& pidx, std::string& err) {
+    props = m.element_properties;
+    pidx = m.element_prop_index;
     props.insert(props.end(), m.material_properties.begin(), m.material_properties.end());
     for (int e = 0; e < m.n_elements; ++e)
         if (m.element_flag[e] == EN234_FLAG_C3D8) {
             const int mi = e < (int)m.element_material.size() ? m.element_material[e] : 0;
-            if (mi < 1 || mi > (int)m.materials.size()) { g_err = "C3D8 element without a MATERIAL"; return 1; }
+            if (mi < 1 || mi > (int)m.materials.size()) { err = "C3D8 element without a MATERIAL"; return false; }
             // the input file does not say which UMAT the executable was linked with; the device has the linear-elastic one
             // (user_codes/src/abaqus_umat_elastic.for: PROPS = E, nu, no state variables) and nothing else
             if (m.materials[mi - 1].n_props != 2 || m.materials[mi - 1].n_states != 0) {
-                g_err = "material '" + m.materials[mi - 1].name + "' has " + std::to_string(m.materials[mi - 1].n_props) +
-                        " properties and " + std::to_string(m.materials[mi - 1].n_states) + " state variables: only the "
-                        "linear-elastic UMAT (E, nu; no state variables) is available on the device";
-                return 1;
+                err = "material '" + m.materials[mi - 1].name + "' has " + std::to_string(m.materials[mi - 1].n_props) +
+                      " properties and " + std::to_string(m.materials[mi - 1].n_states) + " state variables: only the "
+                      "linear-elastic UMAT (E, nu; no state variables) is available on the device";
+                return false;
             }
             pidx[e] = (int)m.element_properties.size() + m.materials[mi - 1].prop_index;
         }
+    return true;
+}
+
+int en234host_gpu_create(en234host_model_t w, int device, en234gpu_handle* h) {
+    const Model& m = w->m;
+    if (!device_supports(m, g_err)) return 1;
+    std::vector<double> props;
+    std::vector<int> pidx;
+    if (!device_property_table(m, props, pidx, g_err)) return 1;
     int rc = en234gpu_create(h, device, m.n_nodes, m.n_elements, m.coords.data(), m.connectivity.data(),
                              m.element_flag.data(), pidx.data(), props.data(), (int)props.size());
     if (rc) g_err = en234gpu_last_error();
@@ -596,10 +604,13 @@ int en234host_part_gpu_create(en234host_model_t w, en234host_part_t p, int devic
     const Model& m = w->m;
     if (!device_supports(m, g_err)) return 1;
     const auto& lel = p->I["local_elements"];
+    std::vector<double> props;
+    std::vector<int> gidx;
+    if (!device_property_table(m, props, gidx, g_err)) return 1;
     std::vector<int> flag(lel.size()), pidx(lel.size());
-    for (size_t i = 0; i < lel.size(); ++i) { flag[i] = m.element_flag[lel[i]]; pidx[i] = m.element_prop_index[lel[i]]; }
+    for (size_t i = 0; i < lel.size(); ++i) { flag[i] = m.element_flag[lel[i]]; pidx[i] = gidx[lel[i]]; }
     int rc = en234gpu_create(h, device, p->I["n_nodes"][0], (int)lel.size(), p->coords.data(), p->I["connectivity"].data(),
-                             flag.data(), pidx.data(), m.element_properties.data(), (int)m.element_properties.size());
+                             flag.data(), pidx.data(), props.data(), (int)props.size());
     if (rc) { g_err = en234gpu_last_error(); return rc; }
     rc = en234gpu_set_partition(*h, p->I["n_neighbours"][0], p->I["neighbour_rank"].data(), p->I["shared_ptr"].data(),
                                 p->I["shared_nodes"].data(), p->owned.data());

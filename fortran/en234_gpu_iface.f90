@@ -14,8 +14,13 @@ module en234_gpu_iface
 
     integer(c_int), parameter :: EN234_SOLVE_PCG_BSR = 0
     integer(c_int), parameter :: EN234_SOLVE_PCG_MATRIXFREE = 1
+    integer(c_int), parameter :: EN234_SOLVE_BICGSTAB_BSR = 2      ! unsymmetric stiffness (SOLVER, ..., UNSYMMETRIC)
 
     type(c_ptr), save :: gpu_handle = c_null_ptr
+    ! several GPUs behind one handle (en234gpu_create_multi): the driver stays one serial program, the library partitions
+    ! the mesh, runs one host thread per GPU and takes / returns the whole-mesh module arrays
+    type(c_ptr), save :: gpu_multi_handle = c_null_ptr
+    integer, save     :: gpu_count = 1
 
     interface
         ! replaces initialize_cg_solver (src/solver_conjugate_gradient.f90:1039-1244; call site src/staticstep.f90:95)
@@ -109,6 +114,74 @@ module en234_gpu_iface
             real(c_double), intent(out) :: time
             integer(c_int)              :: en234gpu_dynamic_get_state
         end function
+        ! time-independent part of assemble_lumped_mass / apply_dynamic_boundaryconditions (src/explicit_dynamic_step.f90:85-392,
+        ! :720-1128): densities, history tables (CSR), unit nodal forces of every load, prescribed DOFs (include/en234gpu.h)
+        function en234gpu_dynamic_setup(h, element_density, n_histories, history_ptr, history_time, history_value, n_loads, &
+                                        load_ptr, load_dof, load_val, load_history, load_constant, n_pdof, pdof_dof, &
+                                        pdof_history, pdof_value, pdof_mode) bind(C, name='en234gpu_dynamic_setup')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value          :: h
+            integer(c_int), value       :: n_histories, n_loads, n_pdof
+            real(c_double), intent(in)  :: element_density(*), history_time(*), history_value(*), load_val(*), load_constant(*), &
+                                           pdof_value(*)
+            integer(c_int), intent(in)  :: history_ptr(*), load_ptr(*), load_dof(*), load_history(*), pdof_dof(*), &
+                                           pdof_history(*), pdof_mode(*)
+            integer(c_int)              :: en234gpu_dynamic_setup
+        end function
+        function en234gpu_device_count() bind(C, name='en234gpu_device_count')
+            import :: c_int
+            integer(c_int) :: en234gpu_device_count
+        end function
+        ! ---- several GPUs, one process: same argument lists as the single-GPU calls, whole-mesh arrays
+        function en234gpu_create_multi(h, n_parts, devices, n_nodes, n_elements, coords, connectivity, element_flag, &
+                                       element_prop_index, element_properties, n_element_properties) &
+                bind(C, name='en234gpu_create_multi')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), intent(out)          :: h
+            integer(c_int), value             :: n_parts, n_nodes, n_elements, n_element_properties
+            type(c_ptr), value                :: devices              ! c_loc(integer array) or c_null_ptr: part p on GPU p
+            real(c_double), intent(in)        :: coords(*), element_properties(*)
+            integer(c_int), intent(in)        :: connectivity(*), element_flag(*), element_prop_index(*)
+            integer(c_int)                    :: en234gpu_create_multi
+        end function
+        function en234gpu_multi_destroy(h) bind(C, name='en234gpu_multi_destroy')
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h
+            integer(c_int)     :: en234gpu_multi_destroy
+        end function
+        function en234gpu_multi_assemble(h, dof_total, dof_increment, f_element_ext, rforce, nodal_force_norm, fail) &
+                bind(C, name='en234gpu_multi_assemble')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value          :: h
+            real(c_double), intent(in)  :: dof_total(*), dof_increment(*)
+            type(c_ptr), value          :: f_element_ext
+            real(c_double), intent(out) :: rforce(*), nodal_force_norm
+            integer(c_int), intent(out) :: fail
+            integer(c_int)              :: en234gpu_multi_assemble
+        end function
+        function en234gpu_multi_apply_boundaryconditions(h, f_ext, n_fixed, fixed_dof, fixed_correction, &
+                                                         unbalanced_force_norm) &
+                bind(C, name='en234gpu_multi_apply_boundaryconditions')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value          :: h
+            type(c_ptr), value          :: f_ext
+            integer(c_int), value       :: n_fixed
+            integer(c_int), intent(in)  :: fixed_dof(*)
+            real(c_double), intent(in)  :: fixed_correction(*)
+            real(c_double), intent(out) :: unbalanced_force_norm
+            integer(c_int)              :: en234gpu_multi_apply_boundaryconditions
+        end function
+        function en234gpu_multi_solve(h, method, cg_tolerance, max_cg_iterations, dof_increment, correction_norm, &
+                                      cg_iterations, fail) bind(C, name='en234gpu_multi_solve')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value            :: h
+            integer(c_int), value         :: method, max_cg_iterations
+            real(c_double), value         :: cg_tolerance
+            real(c_double), intent(inout) :: dof_increment(*)
+            real(c_double), intent(out)   :: correction_norm
+            integer(c_int), intent(out)   :: cg_iterations, fail
+            integer(c_int)                :: en234gpu_multi_solve
+        end function
         function en234gpu_last_error() bind(C, name='en234gpu_last_error')
             import :: c_ptr
             type(c_ptr) :: en234gpu_last_error
@@ -131,13 +204,68 @@ contains
             flags(lmn) = element_list(lmn)%flag
             propidx(lmn) = element_list(lmn)%element_property_index - 1      ! 0-based offset
         end do
-        status = en234gpu_create(gpu_handle, 0_c_int, int(n_nodes, c_int), int(n_elements, c_int), coords, connectivity, &
-                                 flags, propidx, element_properties, int(length_element_properties, c_int))
+        ! all GPUs of the node behind one handle when there are several (the static step then calls the en234gpu_multi_*
+        ! twins with the same module arrays), else the single-GPU handle
+        gpu_count = en234gpu_device_count()
+        if (gpu_count > 1) then
+            status = en234gpu_create_multi(gpu_multi_handle, int(gpu_count, c_int), c_null_ptr, int(n_nodes, c_int), &
+                                           int(n_elements, c_int), coords, connectivity, flags, propidx, element_properties, &
+                                           int(length_element_properties, c_int))
+        else
+            status = en234gpu_create(gpu_handle, 0_c_int, int(n_nodes, c_int), int(n_elements, c_int), coords, connectivity, &
+                                     flags, propidx, element_properties, int(length_element_properties, c_int))
+        end if
         if (status /= 0) then
             write(IOW, *) ' *** Error creating the GPU solver (en234gpu_create) *** '
             stop
         end if
         deallocate(flags, propidx)
     end subroutine initialize_gpu_solver
+
+    ! The three calls of the static step, on one GPU or on all GPUs of the node (same arguments: whole-mesh module arrays)
+    function gpu_assemble(dof_total, dof_increment, f_element_ext, rforce, nodal_force_norm, fail) result(status)
+        real(c_double), intent(in)  :: dof_total(*), dof_increment(*)
+        type(c_ptr), value          :: f_element_ext
+        real(c_double), intent(out) :: rforce(*), nodal_force_norm
+        integer(c_int), intent(out) :: fail
+        integer(c_int)              :: status
+        if (gpu_count > 1) then
+            status = en234gpu_multi_assemble(gpu_multi_handle, dof_total, dof_increment, f_element_ext, rforce, nodal_force_norm, fail)
+        else
+            status = en234gpu_assemble(gpu_handle, dof_total, dof_increment, f_element_ext, rforce, nodal_force_norm, fail)
+        end if
+    end function gpu_assemble
+
+    function gpu_apply_boundaryconditions(f_ext, n_fixed, fixed_dof, fixed_correction, unbalanced_force_norm) result(status)
+        type(c_ptr), value          :: f_ext
+        integer(c_int), value       :: n_fixed
+        integer(c_int), intent(in)  :: fixed_dof(*)
+        real(c_double), intent(in)  :: fixed_correction(*)
+        real(c_double), intent(out) :: unbalanced_force_norm
+        integer(c_int)              :: status
+        if (gpu_count > 1) then
+            status = en234gpu_multi_apply_boundaryconditions(gpu_multi_handle, f_ext, n_fixed, fixed_dof, fixed_correction, &
+                                                             unbalanced_force_norm)
+        else
+            status = en234gpu_apply_boundaryconditions(gpu_handle, f_ext, n_fixed, fixed_dof, fixed_correction, &
+                                                       unbalanced_force_norm)
+        end if
+    end function gpu_apply_boundaryconditions
+
+    function gpu_solve(method, cg_tolerance, max_cg_iterations, dof_increment, correction_norm, cg_iterations, fail) result(status)
+        integer(c_int), value         :: method, max_cg_iterations
+        real(c_double), value         :: cg_tolerance
+        real(c_double), intent(inout) :: dof_increment(*)
+        real(c_double), intent(out)   :: correction_norm
+        integer(c_int), intent(out)   :: cg_iterations, fail
+        integer(c_int)                :: status
+        if (gpu_count > 1) then
+            status = en234gpu_multi_solve(gpu_multi_handle, method, cg_tolerance, max_cg_iterations, dof_increment, &
+                                          correction_norm, cg_iterations, fail)
+        else
+            status = en234gpu_solve(gpu_handle, method, cg_tolerance, max_cg_iterations, dof_increment, correction_norm, &
+                                    cg_iterations, fail)
+        end if
+    end function gpu_solve
 
 end module en234_gpu_iface

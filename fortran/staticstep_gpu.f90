@@ -2,7 +2,8 @@
 !
 !  compute_static_step_gpu is the CG branch of compute_static_step (src/staticstep.f90:93-160) with the three
 !  module-global calls replaced by the C ABI of liben234gpu.so:
-!      assemble_conjugate_gradient_stiffness(fail)      -> en234gpu_assemble
+!      assemble_conjugate_gradient_stiffness(fail)      -> en234gpu_assemble   (gpu_assemble etc. below dispatch to the
+!                                                          en234gpu_multi_* twins when the node has several GPUs)
 !      apply_cojugategradient_boundaryconditions        -> gpu_collect_boundaryconditions + en234gpu_apply_boundaryconditions
 !      solve_conjugategradient(fail)                    -> en234gpu_solve
 !  convergencecheck, compute_static_time_increment, print_state and the state update are the reference's own routines,
@@ -43,13 +44,13 @@ subroutine compute_static_step_gpu
 
     do while (continue_timesteps)
         call gpu_collect_boundaryconditions(f_ext, f_element_ext, n_fixed, fixed_dof, fixed_correction)
-        status = en234gpu_assemble(gpu_handle, dof_total, dof_increment, c_loc(f_element_ext), rforce, &
+        status = gpu_assemble(dof_total, dof_increment, c_loc(f_element_ext), rforce, &
                                    nodal_force_norm, cfail)
         fail = (status /= 0) .or. (cfail /= 0)
         if (.not.fail) then
-            status = en234gpu_apply_boundaryconditions(gpu_handle, c_loc(f_ext), int(n_fixed, c_int), fixed_dof, &
+            status = gpu_apply_boundaryconditions(c_loc(f_ext), int(n_fixed, c_int), fixed_dof, &
                                                        fixed_correction, unbalanced_force_norm)
-            status = en234gpu_solve(gpu_handle, EN234_SOLVE_PCG_BSR, cg_tolerance, int(max_cg_iterations, c_int), &
+            status = gpu_solve(EN234_SOLVE_PCG_BSR, cg_tolerance, int(max_cg_iterations, c_int), &
                                     dof_increment, correction_norm, cg_its, cfail)
             fail = (status /= 0) .or. (cfail /= 0)
         endif
@@ -66,17 +67,17 @@ subroutine compute_static_step_gpu
 
         do iteration = 1, max_newton_iterations   ! also run for LINEAR problems, like the direct branch (:60-70)
             call gpu_collect_boundaryconditions(f_ext, f_element_ext, n_fixed, fixed_dof, fixed_correction)
-            status = en234gpu_assemble(gpu_handle, dof_total, dof_increment, c_loc(f_element_ext), rforce, &
+            status = gpu_assemble(dof_total, dof_increment, c_loc(f_element_ext), rforce, &
                                        nodal_force_norm, cfail)
             if (status /= 0 .or. cfail /= 0) then
                 converged = .false.
                 exit
             endif
-            status = en234gpu_apply_boundaryconditions(gpu_handle, c_loc(f_ext), int(n_fixed, c_int), fixed_dof, &
+            status = gpu_apply_boundaryconditions(c_loc(f_ext), int(n_fixed, c_int), fixed_dof, &
                                                        fixed_correction, unbalanced_force_norm)
             call convergencecheck(iteration, converged)
             if (converged) exit
-            status = en234gpu_solve(gpu_handle, EN234_SOLVE_PCG_BSR, cg_tolerance, int(max_cg_iterations, c_int), &
+            status = gpu_solve(EN234_SOLVE_PCG_BSR, cg_tolerance, int(max_cg_iterations, c_int), &
                                     dof_increment, correction_norm, cg_its, cfail)
         end do
 

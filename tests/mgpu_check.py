@@ -19,14 +19,14 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     only = None                                   # --dynamics-only / --project-only: one section (GPU-minute budget)
-    for flag in ("--dynamics-only", "--project-only"):
+    for flag in ("--dynamics-only", "--project-only", "--c3d8-only", "--static-only"):
         if flag in sys.argv:
             sys.argv.remove(flag)
             only = flag[2:-5]
     dims = tuple(int(x) for x in (sys.argv[1:4] if len(sys.argv) >= 4 else (12, 10, 8 * world)))
     jitter = float(sys.argv[4]) if len(sys.argv) >= 5 else 0.2      # 0 with power-of-two dims: congruent-mesh operator
     ok = True
-    for method in (() if only else (0, 1)):
+    for method in ((0, 1) if only in (None, "static") else ()):
         for load in ("traction", "stretch"):
             m = Model.from_text(synthetic_block_input(*dims, jitter=jitter, cg_tolerance=1e-26, cg_maxit=20000, load=load,
                                                       steps=2 if load == "stretch" else 1))
@@ -67,6 +67,8 @@ def main():
         ok = dynamics_section(rank, world, local, dims, jitter) and ok
     if only in (None, "project"):
         ok = project_section(rank, world, local, dims, jitter) and ok
+    if only in (None, "c3d8"):
+        ok = c3d8_section(rank, world, local) and ok
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
@@ -105,6 +107,44 @@ def dynamics_section(rank, world, local, dims, jitter):
               % (comm_kind, world, dims, errs["dof_total"], errs["velocity"], errs["lumped_mass"], agree,
                  1e3 * res["device_ms"] / 70, world, 1e3 * ref["device_ms"] / 70, "OK" if good else "FAIL"), flush=True)
         ok = ok and good
+        g1.close()
+    dist.barrier()
+    g.close()
+    return ok
+
+
+def c3d8_section(rank, world, local):
+    """The reference's golden C3D8 + UMAT model (unsymmetric tangent -> Jacobi-BiCGSTAB with halo sums and all-reduced dot
+    products) on an element partition: same Newton history as one GPU, displacements within 1e-8 (the golden log's own
+    records are reproduced to their printed digits by the one-GPU path, tests/test_gpu_parity.py)."""
+    import gzip
+    golden = os.path.join(ROOT, "tests", "golden", "holeplate_3d_umat.in.gz")
+    m = Model.from_text(gzip.open(golden, "rb").read().decode())
+    part = Partition(m, world, rank)
+    g = GpuSystem(m, device=local, part=part)
+    comm_kind = g.setup_distributed()
+    res = g.run_static(method=0)
+    l2g = part.ints("local_to_global_node").astype(np.int64)
+    ldof = (3 * l2g[:, None] + np.arange(3)).ravel()
+    acc = torch.zeros(3 * m.n_nodes, dtype=torch.float64, device="cuda")
+    cnt = torch.zeros_like(acc)
+    idx = torch.from_numpy(ldof).cuda()
+    acc[idx] = torch.from_numpy(res["dof_total"]).cuda()
+    cnt[idx] = 1.0
+    dist.all_reduce(acc); dist.all_reduce(cnt)
+    ug = (acc / cnt).cpu().numpy()
+    ok = True
+    if rank == 0:
+        g1 = GpuSystem(m, device=local)
+        ref = g1.run_static(method=0)
+        eu = np.abs(ug - ref["dof_total"]).max() / np.abs(ref["dof_total"]).max()
+        same = res["newton"].shape == ref["newton"].shape
+        rel = np.abs(res["newton"][:, 2:5] - ref["newton"][:, 2:5]).max() / np.abs(ref["newton"][:, 2:5]).max() if same else np.inf
+        good = same and eu < 1e-8 and rel < 1e-5
+        print("mgpu_check [%s] world=%d golden C3D8 + UMAT hole plate (BiCGSTAB on partitions): %d Newton records, norms agree to %.1e, "
+              "u err %.2e, BiCGSTAB its %s vs %s -> %s" % (comm_kind, world, res["newton"].shape[0], rel, eu,
+                                                          res["cg_iterations"].tolist(), ref["cg_iterations"].tolist(), "OK" if good else "FAIL"), flush=True)
+        ok = good
         g1.close()
     dist.barrier()
     g.close()

@@ -241,3 +241,51 @@ class OracleDynamic:
         if self.h:
             lib().or_dynamic_free(self.h)
             self.h = None
+
+
+def synthetic_block_arrays(nx, ny=None, nz=None, jitter=0.2, seed=1234, E=100.0, nu=0.3, cg_tolerance=1e-17, cg_maxit=1000,
+                           solvertype=2):
+    """The oracle's own model of the synthetic hex8 block (oracle/or_mesh.cpp + the boundary-condition tables below): face
+    x = 0 clamped, traction (0, 0, -1) on face 4 of the elements at x = max, one LINEAR static step — the same arrays the
+    product's parser produces for synthetic_block_input(...) (tests/test_oracle_cpu.py checks the equality), built without
+    loading any product library."""
+    ny = nx if ny is None else ny
+    nz = nx if nz is None else nz
+    N, Ne = (nx + 1) * (ny + 1) * (nz + 1), nx * ny * nz
+    coords, conn = np.zeros(3 * N), np.zeros(8 * Ne, np.int32)
+    L = lib()
+    L.or_synthetic_block.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_ulonglong, dp, ip]
+    if L.or_synthetic_block(nx, ny, nz, float(jitter), int(seed), _d(coords), _i(conn)):
+        raise ValueError("bad block dimensions")
+    i32 = lambda v: np.asarray(v, np.int32)
+    node = (1 + np.arange(N)).reshape(nz + 1, ny + 1, nx + 1)
+    elem = (1 + np.arange(Ne)).reshape(nz, ny, nx)
+    nsets = [node[:, :, 0], node[:, :, nx], node[:, 0, :], node[:, ny, :], node[0], node[nz]]
+    esets = [elem[:, :, 0], elem[:, :, nx - 1], elem[:, 0, :], elem[:, ny - 1, :], elem[0], elem[nz - 1]]
+    z = i32([])
+    return {
+        "n_nodes": i32([N]), "n_elements": i32([Ne]), "coords": coords, "connectivity": conn,
+        "element_flag": np.full(Ne, 1001, np.int32), "element_prop_index": np.zeros(Ne, np.int32),
+        "element_n_props": np.full(Ne, 2, np.int32), "element_n_states": np.zeros(Ne, np.int32),
+        "element_material": np.zeros(Ne, np.int32), "material_prop_index": z, "material_n_props": z,
+        "element_properties": np.array([E, nu]), "material_properties": np.zeros(0), "element_density": np.zeros(Ne),
+        "history_ptr": i32([0]), "history_time": np.zeros(0), "history_value": np.zeros(0),
+        "nodeset_ptr": i32(np.concatenate([[0], np.cumsum([s.size for s in nsets])])),
+        "nodeset_nodes": i32(np.concatenate([s.ravel() for s in nsets])),
+        "elementset_ptr": i32(np.concatenate([[0], np.cumsum([s.size for s in esets])])),
+        "elementset_elements": i32(np.concatenate([s.ravel() for s in esets])),
+        # DEGREES OF FREEDOM: node set 1 (xmin), DOFs 1..3, VALUE 0
+        "pdof_flag": i32([1, 1, 1]), "pdof_dof": i32([1, 2, 3]), "pdof_node": i32([0, 0, 0]), "pdof_nodeset": i32([1, 1, 1]),
+        "pdof_history": i32([0, 0, 0]), "pdof_rate": i32([0, 0, 0]), "pdof_subparam": i32([0, 0, 0]), "subparam_ptr": i32([0]),
+        "pdof_value": np.zeros(3), "subparam_values": np.zeros(0),
+        "pforce_flag": z, "pforce_dof": z, "pforce_node": z, "pforce_nodeset": z, "pforce_history": z, "pforce_value": np.zeros(0),
+        # DISTRIBUTED LOADS: element set 2 (xmax_el), face 4, VALUE (0, 0, -1)
+        "dload_flag": i32([1]), "dload_elset": i32([2]), "dload_face": i32([4]), "dload_history": i32([0]),
+        "dload_val_ptr": i32([0, 3]), "dload_values": np.array([0.0, 0.0, -1.0]),
+        "max_no_steps": i32([1]), "solvertype": i32([solvertype]), "nonlinear": i32([0]), "max_newton_iterations": i32([1]),
+        "unsymmetric": i32([0]), "abaqusformat": i32([0]), "max_cg_iterations": i32([cg_maxit]), "checkstiffness_flag": i32([0]),
+        "explicitdynamicstep": i32([0]), "no_dynamic_steps": i32([0]),
+        "timestep_initial": np.array([1.0]), "timestep_min": np.array([1.0 / 1024.0]), "timestep_max": np.array([1.0]),
+        "max_total_time": np.array([1.0]), "newtonraphson_tolerance": np.array([1e-8]), "cg_tolerance": np.array([cg_tolerance]),
+        "dynamic_timestep": np.array([0.0]),
+    }

@@ -438,6 +438,7 @@ static int preallocate_for_shared_device(en234gpu_ctx* c) {
     CK(c->fixdof.alloc((size_t)c->ndof));
     CK(c->fixval.alloc((size_t)c->ndof));
     c->mf.affected = c->bc_affected.p;
+    mf_prepare_geom(c->mf, c->E);
     return 0;
 }
 
@@ -1386,6 +1387,7 @@ int en234gpu_dynamic_setup(en234gpu_handle c, const double* element_density, int
     if (c->comm.active && comm_halo_sum(c->comm, D.mass.p, c->stream)) return set_err(comm_error());
     CK(cudaStreamSynchronize(c->stream));
     if (c->Re.n < (size_t)c->E * 24) CK(c->Re.alloc((size_t)c->E * 24));
+    mf_prepare_geom(c->mf, c->E);
     if (D.graph) { cudaGraphExecDestroy(D.graph); D.graph = nullptr; }
     D.ready = true;
     c->matrix_valid = false;

@@ -426,23 +426,27 @@ inline int mf_set_congruent(MfData& mf, const double* Ke_colmajor, int N, const 
     mf.congruent = true;
     return 0;
 }
+// Allocation of the geometry cache (never inside a stream capture: callers that capture call this first).
+inline void mf_prepare_geom(MfData& mf, int E) {
+    if (mf.geom_state != 0) return;
+    const char* e = getenv("EN234_MF_GEOM");
+    const size_t bytes = (size_t)((E + 3) / 4) * 320 * sizeof(double);
+    if ((e && atoi(e) == 0) || cudaMalloc((void**)&mf.d_geom, bytes) != cudaSuccess) { cudaGetLastError(); mf.geom_state = -1; }
+    else mf.geom_state = 1;
+}
 // Launch of the residual-only element kernel with the geometry cache in the right state.
 template <class Load>
 inline void launch_element_forces(MfData& mf, ElemArgs EA, const Load& ld, int grid, cudaStream_t s) {
-    if (mf.geom_state == 0) {
-        const char* e = getenv("EN234_MF_GEOM");
-        const size_t bytes = (size_t)((EA.M.E + 3) / 4) * 320 * sizeof(double);
-        if ((e && atoi(e) == 0) || cudaMalloc((void**)&mf.d_geom, bytes) != cudaSuccess) { cudaGetLastError(); mf.geom_state = -1; }
-        else mf.geom_state = 1;
-    }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);
+    if (mf.geom_state == 0 && cap == cudaStreamCaptureStatusNone) mf_prepare_geom(mf, EA.M.E);
     EA.geom = mf.d_geom;
+    if (mf.geom_state == 0) { k_element_forces<Load, 0><<<grid, 256, 0, s>>>(EA, ld); return; }   // capturing, no cache yet
     if (mf.geom_state == 2) k_element_forces<Load, 2><<<grid, 256, 0, s>>>(EA, ld);
     else if (mf.geom_state == 1) {
         k_element_forces<Load, 1><<<grid, 256, 0, s>>>(EA, ld);
         // a kernel whose Load can make it return at once (PCG stop flag) may not have written the cache
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing(s, &cs);
-        if (cs == cudaStreamCaptureStatusNone && !ld.may_skip()) mf.geom_state = 2;
+        if (cap == cudaStreamCaptureStatusNone && !ld.may_skip()) mf.geom_state = 2;
     } else k_element_forces<Load, 0><<<grid, 256, 0, s>>>(EA, ld);
 }
 

@@ -161,6 +161,20 @@ int en234gpu_create_multi(en234gpu_multi_handle* out, int n_parts, const int* de
         if (d < 0 || d >= ndev) { delete m; return set_err("en234gpu_create_multi: bad device index"); }
         m->dev.push_back(d);
     }
+    // Parts that share a device wait for one another from separately launched kernels, and nothing in CUDA guarantees that
+    // those run at the same time (the library sizes the grids so that they can, preloads the kernels and preallocates, and
+    // every wait has a time-out) — a debugging aid for small meshes on a one-GPU box, refused unless asked for.
+    for (int p = 0; p < n_parts; ++p)
+        for (int q = 0; q < p; ++q)
+            if (m->dev[p] == m->dev[q]) {
+                const char* e = getenv("EN234_ALLOW_SHARED_DEVICE");
+                if (!(e && atoi(e) != 0)) {
+                    delete m;
+                    return set_err("en234gpu_create_multi: parts " + std::to_string(q) + " and " + std::to_string(p) +
+                                   " are both on device " + std::to_string(m->dev[p]) +
+                                   "; one part per GPU (set EN234_ALLOW_SHARED_DEVICE=1 to co-schedule parts on one device: small meshes, debugging only)");
+                }
+            }
     const std::string perr = en234part::partition(n_nodes, n_elements, connectivity, n_parts, m->part);
     if (!perr.empty()) { delete m; return set_err("en234gpu_create_multi: " + perr); }
     m->g2l.resize(n_parts);
@@ -215,7 +229,6 @@ int en234gpu_create_multi(en234gpu_multi_handle* out, int n_parts, const int* de
         rc = m->run([&](int p) {
             en234gpu_ctx* c = m->ctx[p];
             if (comm_arena_connect_inproc(c->comm, bases.data())) return set_err(comm_error());
-            if (!c->comm.fused) return set_err("en234gpu_create_multi: the interface rows of this partition are not separable");
             return 0;
         });
     }

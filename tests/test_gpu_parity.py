@@ -714,11 +714,19 @@ def test_explicit_dynamics_native_element_with_density_and_tractions():
 
 # ------------------------------------------------------------------------------------------- several parts behind one handle
 def _devices(n_parts):
-    """Distinct GPUs when the box has them, else all parts co-scheduled on device 0 (the library sizes the grids for that)."""
-    import ctypes as C
+    """One GPU per part.  On a box with fewer GPUs the test is skipped: parts sharing a device would wait for one another
+    from separately launched kernels, which nothing guarantees to run at the same time (B200_PROFILING.md) — the library
+    supports it as a debugging aid (EN234_ALLOW_SHARED_DEVICE=1, used here only when EN234_TEST_SHARED_DEVICE=1 asks for
+    it); the N > 1 host logic is covered on the CPU (tests/test_partition_gloo.py, the partition tests) and the multi-GPU
+    numerics by bench.py's parity gate at every N."""
     from en234_fea_b200 import api
     nd = api.gpu_lib().en234gpu_device_count()
-    return [p % nd for p in range(n_parts)] if nd >= n_parts else [0] * n_parts
+    if nd >= n_parts:
+        return list(range(n_parts))
+    if os.environ.get("EN234_TEST_SHARED_DEVICE") == "1":
+        os.environ["EN234_ALLOW_SHARED_DEVICE"] = "1"
+        return [0] * n_parts
+    pytest.skip("%d GPUs needed, %d present" % (n_parts, nd))
 
 
 @pytest.mark.parametrize("dims,n_parts,method", [((6, 5, 8), 2, 0), ((5, 4, 9), 3, 0), ((6, 5, 8), 2, 1), ((4, 4, 8), 4, 0)])
@@ -729,8 +737,9 @@ def test_multi_handle_from_plain_c_matches_one_device(dims, n_parts, method):
     import subprocess
     exe = os.path.join(os.path.dirname(__file__), "c", "multi_check")
     assert os.path.exists(exe), "tests/c/multi_check is built by __graft_entry__.build()"
+    devs = _devices(n_parts)
     env = dict(os.environ, EN234_P2P_TIMEOUT_MS="20000")
-    out = subprocess.run([exe] + [str(d) for d in dims] + [str(n_parts), ",".join(str(d) for d in _devices(n_parts)), str(method)],
+    out = subprocess.run([exe] + [str(d) for d in dims] + [str(n_parts), ",".join(str(d) for d in devs), str(method)],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     print(out.stdout)
     assert out.returncode == 0, out.stdout

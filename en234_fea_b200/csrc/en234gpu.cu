@@ -353,6 +353,7 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
         c->grid_gather = std::min(MAX_PARTIALS, std::max(1, std::min((N + WARPS - 1) / WARPS, c->n_sm * std::max(og, 1))));
         if (const char* e = getenv("EN234_ASM")) c->asm_rows = std::strcmp(e, "rows") == 0;
     }
+    c->mf.sm_share = g_sm_share > 1 ? 2 * g_sm_share : 1;
     int rc = mf_setup(c->mf, mesh_of(c), conn, N, E, c->n_sm, c->ndof);
     if (rc) { delete c; return set_err("matrix-free set-up failed"); }
     // congruent mesh (every element a translate of element 0, one linear-elastic material): the matrix-free operator

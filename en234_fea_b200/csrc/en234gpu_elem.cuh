@@ -25,6 +25,7 @@ struct ElemArgs {
     CgScalars* S;           // nanflag (may be null)
     double* geom = nullptr; // cached Gauss-point geometry of k_element_forces: per group of 4 elements 10 rows of 32 lanes
                             // (lane = 8 * element-in-group + Gauss point): J^-1 (9 values) and w|J|; 640 B per element
+    size_t geom_stride = 0; // != 0: transposed cache layout geomT[(10 * point + q) * geom_stride + e] (k_element_forces_tpe)
 };
 
 template <bool NEO>
@@ -338,10 +339,19 @@ __global__ void __launch_bounds__(256, FORCES_OCC) k_element_forces(ElemArgs A, 
         if (GEOM == 2) gauss_point_grad_sm(nbuf + g * NS, p, jc, gg, gp);
         else gauss_point_eval_sm(nbuf + g * NS, p, gg, gp, &jc);
         if (GEOM == 1) {
-            double* dst = A.geom + (size_t)grp * 320 + lane;
+            if (A.geom_stride != 0) {
+                if (valid) {
+                    double* dst = A.geom + (size_t)(10 * p) * A.geom_stride + e;
 #pragma unroll
-            for (int q = 0; q < 9; ++q) dst[32 * q] = jc.Ji[q];
-            dst[32 * 9] = jc.det;
+                    for (int q = 0; q < 9; ++q) dst[(size_t)q * A.geom_stride] = jc.Ji[q];
+                    dst[(size_t)9 * A.geom_stride] = jc.det;
+                }
+            } else {
+                double* dst = A.geom + (size_t)grp * 320 + lane;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) dst[32 * q] = jc.Ji[q];
+                dst[32 * 9] = jc.det;
+            }
         }
         if (valid && !(gp.det != 0.0)) bad = true;
         double s[9];
@@ -388,6 +398,241 @@ __global__ void __launch_bounds__(256, FORCES_OCC) k_element_forces(ElemArgs A, 
         __syncwarp();
     }
     if (bad && A.S) atomicOr(&A.S->nanflag, 1);
+}
+
+// Residual-only element kernel on the CACHED Gauss-point geometry (J^-1 = dxi/dx and w|J| per point, written once by
+// k_element_forces<Load, 1>): the same lane mapping and butterfly as k_element_forces, but the shape-function gradients in
+// physical space are never formed.  With d_a = dN_a/dxi at the point (three products of (1 +- xi_j), sign applied last):
+//   grad u = G J^-1,   G = sum_a u_a (x) d_a                 (72 + 27 FMA instead of 72 + 72)
+//   f_a    = T d_a,    T = -(w|J| sigma) J^-T                 (27 + 72 FMA instead of 72)
+// 24 registers of dN/dx disappear, which is what lets three CTAs share an SM (the kernel is latency-bound: ncu shows the
+// FP64 pipe 39 % busy at 16 warps per SM).  The element sums are the same numbers in a different association, so results
+// agree with k_element_forces to rounding (1e-15 relative), not bitwise.
+template <int C>
+__device__ __forceinline__ void xi_grad_acc(const double* nb, const double fp[3], const double fm[3], double* G) {
+    double dn[3];
+    dshape<C>(fp, fm, dn);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double u = nb[6 * C + 3 + i];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) G[3 * i + k] += u * dn[k];
+    }
+}
+// dN/dxi of node C4 + 4 * upper (the two nodes differ in the xi_3 factor and the sign of the third component only); same
+// operation order as dshape<C>
+template <int C4>
+__device__ __forceinline__ void dshape_half(const double fp[3], const double fm[3], bool upper, double dn[3]) {
+    const double f0 = sgn(C4, 0) > 0 ? fp[0] : fm[0];
+    const double f1 = sgn(C4, 1) > 0 ? fp[1] : fm[1];
+    const double f2 = upper ? fp[2] : fm[2];
+    dn[0] = sgn(C4, 0) * (f1 * f2 * 0.125);
+    dn[1] = sgn(C4, 1) * (f0 * f2 * 0.125);
+    const double d2 = f0 * f1 * 0.125;
+    dn[2] = upper ? d2 : -d2;
+}
+// forces of the four nodes C4 + 4 * upper: f[3 * C4 + i] = sum_k T[i][k] dN/dxi_k
+template <int C4>
+__device__ __forceinline__ void xi_force_half(const double fp[3], const double fm[3], bool upper, const double* T, double* f) {
+    double dn[3];
+    dshape_half<C4>(fp, fm, upper, dn);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) f[3 * C4 + i] = T[3 * i] * dn[0] + T[3 * i + 1] * dn[1] + T[3 * i + 2] * dn[2];
+}
+template <class Load, int OCC = 2>
+__global__ void __launch_bounds__(256, OCC) k_element_forces_cached(ElemArgs A, Load ld) {
+    constexpr int NW = 8, NS = ElemCfg<false>::NSTRIDE;
+    __shared__ double nbuf_all[NW * 4 * NS];
+    if (ld.stopped()) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, p = lane & 7;
+    double* nbuf = nbuf_all + warp * 4 * NS;
+    const Mesh& M = A.M;
+    const int ngroups = (M.E + 3) >> 2, W = gridDim.x * NW;
+    const Material mat0 = M.mats[0];
+    double fp[3], fm[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const double xi = ((p >> j) & 1) ? EN234_GP : -EN234_GP;
+        fp[j] = 1.0 + xi;
+        fm[j] = 1.0 - xi;
+    }
+    double nd[3];
+    auto node_of = [&](int grp) -> int {
+        if (grp >= ngroups) return 0;
+        return M.conn[(size_t)p * M.E + min(4 * grp + g, M.E - 1)];
+    };
+    auto stage = [&](int n) { nd[0] = ld(3 * (size_t)n); nd[1] = ld(3 * (size_t)n + 1); nd[2] = ld(3 * (size_t)n + 2); };
+    int grp = blockIdx.x * NW + warp;
+    stage(node_of(grp));
+    int n_next = node_of(grp + W);
+    for (; grp < ngroups; grp += W) {
+        {
+            double* dst = nbuf + g * NS + p * 6 + 3;
+            dst[0] = nd[0]; dst[1] = nd[1]; dst[2] = nd[2];
+        }
+        __syncwarp();
+        // loads of this iteration: the group's cached geometry (used after G below), the next group's node values
+        double Ji[9], det;
+        {
+            const double* src = A.geom + (size_t)grp * 320 + lane;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) Ji[q] = __ldcs(src + 32 * q);
+            det = __ldcs(src + 32 * 9);
+        }
+        stage(n_next);
+        n_next = node_of(grp + 2 * W);
+        const int e = 4 * grp + g;
+        const bool valid = e < M.E;
+        const int pos = valid ? M.adj_pos[8 * (size_t)e + p] : 0;     // fetched now, used after the arithmetic
+        const Material mat = M.n_mats == 1 ? mat0 : M.mats[M.mat[valid ? e : M.E - 1]];
+        const double* nb = nbuf + g * NS;
+        double G[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) G[q] = 0.0;
+        xi_grad_acc<0>(nb, fp, fm, G); xi_grad_acc<1>(nb, fp, fm, G); xi_grad_acc<2>(nb, fp, fm, G); xi_grad_acc<3>(nb, fp, fm, G);
+        xi_grad_acc<4>(nb, fp, fm, G); xi_grad_acc<5>(nb, fp, fm, G); xi_grad_acc<6>(nb, fp, fm, G); xi_grad_acc<7>(nb, fp, fm, G);
+        double T[9];
+        {
+            double H[9], s[9];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) H[3 * i + j] = G[3 * i] * Ji[j] + G[3 * i + 1] * Ji[3 + j] + G[3 * i + 2] * Ji[6 + j];
+            stress_linear(mat, H, s);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) s[q] *= -det;                 // R = - sum_p w|J| sigma . grad N  (w = 1)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) T[3 * i + k] = s[3 * i] * Ji[3 * k] + s[3 * i + 1] * Ji[3 * k + 1] + s[3 * i + 2] * Ji[3 * k + 2];
+        }
+        // halving butterfly over the 8 Gauss-point lanes (lane a ends with the 3 components of node a); the half that is
+        // sent away is computed first, the half that is kept while the shuffles are in flight
+        double h[12], q6[6], r3[3];
+        {
+            const bool up = p & 4;                                    // this lane keeps nodes 4..7 when up, else 0..3
+            double snd[12];
+            xi_force_half<0>(fp, fm, !up, T, snd); xi_force_half<1>(fp, fm, !up, T, snd);
+            xi_force_half<2>(fp, fm, !up, T, snd); xi_force_half<3>(fp, fm, !up, T, snd);
+#pragma unroll
+            for (int j = 0; j < 12; ++j) snd[j] = __shfl_xor_sync(0xffffffffu, snd[j], 4);
+            xi_force_half<0>(fp, fm, up, T, h); xi_force_half<1>(fp, fm, up, T, h);
+            xi_force_half<2>(fp, fm, up, T, h); xi_force_half<3>(fp, fm, up, T, h);
+#pragma unroll
+            for (int j = 0; j < 12; ++j) h[j] += snd[j];
+        }
+        {
+            const bool up = p & 2;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const double send = up ? h[j] : h[6 + j], keep = up ? h[6 + j] : h[j];
+                q6[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+        }
+        {
+            const bool up = p & 1;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double send = up ? q6[j] : q6[3 + j], keep = up ? q6[3 + j] : q6[j];
+                r3[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+        }
+        if (valid) {
+            double* R = A.Re + 3 * (size_t)pos;
+            R[0] = r3[0]; R[1] = r3[1]; R[2] = r3[2];
+        }
+        __syncwarp();
+    }
+}
+
+// Thread-per-element form of the residual-only kernel on the cached geometry (the matrix-free operator's hot kernel).
+// ncu on the warp-cooperative forms above (k_element_forces, k_element_forces_cached): 750 warp instructions per group of
+// four elements of which 288 are FP64 — issue slots, not the FP64 pipe (39 %) or HBM (36 %), bound them: the lane = (element,
+// Gauss point) mapping pays for its butterflies, 64-bit selects and shared-memory hand-over.  Here one thread owns one
+// element: the Gauss-point loop is unrolled, so dN_a/dxi are literal constants (no dshape arithmetic, no selects), the 24
+// nodal values and the 24 force accumulators stay in registers, there is no shared memory, no shuffle and no divergence;
+// what is left per point is G (72 FMA), H = G J^-1 (27), the stress, T (27) and f += T d (72).
+// Geometry cache layout for this kernel: geomT[(10 * point + q) * Epad + e] (coalesced over e), written by
+// k_element_forces<Load, 1> when ElemArgs::geom_stride != 0.
+template <int P, int C>
+__device__ __forceinline__ void tpe_grad(const double (&u)[24], double* G) {
+    constexpr double A = 1.0 + EN234_GP, B = 1.0 - EN234_GP;
+    constexpr double f0 = (sgn(C, 0) > 0) == (((P >> 0) & 1) != 0) ? A : B;
+    constexpr double f1 = (sgn(C, 1) > 0) == (((P >> 1) & 1) != 0) ? A : B;
+    constexpr double f2 = (sgn(C, 2) > 0) == (((P >> 2) & 1) != 0) ? A : B;
+    constexpr double d0 = sgn(C, 0) * (f1 * f2 * 0.125), d1 = sgn(C, 1) * (f0 * f2 * 0.125), d2 = sgn(C, 2) * (f0 * f1 * 0.125);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        G[3 * i] += u[3 * C + i] * d0;
+        G[3 * i + 1] += u[3 * C + i] * d1;
+        G[3 * i + 2] += u[3 * C + i] * d2;
+    }
+}
+template <int P, int C>
+__device__ __forceinline__ void tpe_force(const double* T, double (&f)[24]) {
+    constexpr double A = 1.0 + EN234_GP, B = 1.0 - EN234_GP;
+    constexpr double f0 = (sgn(C, 0) > 0) == (((P >> 0) & 1) != 0) ? A : B;
+    constexpr double f1 = (sgn(C, 1) > 0) == (((P >> 1) & 1) != 0) ? A : B;
+    constexpr double f2 = (sgn(C, 2) > 0) == (((P >> 2) & 1) != 0) ? A : B;
+    constexpr double d0 = sgn(C, 0) * (f1 * f2 * 0.125), d1 = sgn(C, 1) * (f0 * f2 * 0.125), d2 = sgn(C, 2) * (f0 * f1 * 0.125);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) f[3 * C + i] += T[3 * i] * d0 + T[3 * i + 1] * d1 + T[3 * i + 2] * d2;
+}
+template <int P>
+__device__ __forceinline__ void tpe_point(const double* __restrict__ geomT, size_t stride, const Material& mat,
+                                          const double (&u)[24], double (&f)[24]) {
+    double Ji[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) Ji[q] = __ldcs(geomT + (size_t)(10 * P + q) * stride);
+    const double det = __ldcs(geomT + (size_t)(10 * P + 9) * stride);
+    double G[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) G[q] = 0.0;
+    tpe_grad<P, 0>(u, G); tpe_grad<P, 1>(u, G); tpe_grad<P, 2>(u, G); tpe_grad<P, 3>(u, G);
+    tpe_grad<P, 4>(u, G); tpe_grad<P, 5>(u, G); tpe_grad<P, 6>(u, G); tpe_grad<P, 7>(u, G);
+    double H[9], s[9], T[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) H[3 * i + j] = G[3 * i] * Ji[j] + G[3 * i + 1] * Ji[3 + j] + G[3 * i + 2] * Ji[6 + j];
+    stress_linear(mat, H, s);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) s[q] *= -det;                         // R = - sum_p w|J| sigma . grad N  (w = 1)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) T[3 * i + k] = s[3 * i] * Ji[3 * k] + s[3 * i + 1] * Ji[3 * k + 1] + s[3 * i + 2] * Ji[3 * k + 2];
+    tpe_force<P, 0>(T, f); tpe_force<P, 1>(T, f); tpe_force<P, 2>(T, f); tpe_force<P, 3>(T, f);
+    tpe_force<P, 4>(T, f); tpe_force<P, 5>(T, f); tpe_force<P, 6>(T, f); tpe_force<P, 7>(T, f);
+}
+constexpr int TPE_THREADS = 128;
+template <class Load>
+__global__ void __launch_bounds__(TPE_THREADS, 2) k_element_forces_tpe(ElemArgs A, Load ld) {
+    if (ld.stopped()) return;
+    const Mesh& M = A.M;
+    const Material mat0 = M.mats[0];
+    for (int e = blockIdx.x * TPE_THREADS + threadIdx.x; e < M.E; e += gridDim.x * TPE_THREADS) {
+        const Material mat = M.n_mats == 1 ? mat0 : M.mats[M.mat[e]];
+        double u[24], f[24];
+        int pos[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int n = M.conn[(size_t)a * M.E + e];
+            pos[a] = M.adj_pos[8 * (size_t)e + a];
+            u[3 * a] = ld(3 * (size_t)n); u[3 * a + 1] = ld(3 * (size_t)n + 1); u[3 * a + 2] = ld(3 * (size_t)n + 2);
+        }
+#pragma unroll
+        for (int q = 0; q < 24; ++q) f[q] = 0.0;
+        const double* gT = A.geom + e;
+        const size_t st = A.geom_stride;
+        tpe_point<0>(gT, st, mat, u, f); tpe_point<1>(gT, st, mat, u, f); tpe_point<2>(gT, st, mat, u, f); tpe_point<3>(gT, st, mat, u, f);
+        tpe_point<4>(gT, st, mat, u, f); tpe_point<5>(gT, st, mat, u, f); tpe_point<6>(gT, st, mat, u, f); tpe_point<7>(gT, st, mat, u, f);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            double* R = A.Re + 3 * (size_t)pos[a];
+            R[0] = f[3 * a]; R[1] = f[3 * a + 1]; R[2] = f[3 * a + 2];
+        }
+    }
 }
 
 struct GatherArgs {

@@ -164,6 +164,7 @@ struct LoadSum {                       // u = dof_total + dof_increment         
     __device__ __forceinline__ double operator()(size_t d) const { return ut[d] + du[d]; }
     __device__ __forceinline__ bool stopped() const { return false; }
     bool may_skip() const { return false; }
+    static constexpr bool use_geometry_cache = false;
 };
 struct LoadMasked {                    // x with prescribed DOFs zeroed (operator P A P of the matrix-free solve)
     const double* __restrict__ x;
@@ -177,6 +178,7 @@ struct LoadMasked {                    // x with prescribed DOFs zeroed (operato
     }
     __device__ __forceinline__ bool stopped() const { return stop != nullptr && stop->stop != 0; }
     bool may_skip() const { return stop != nullptr; }
+    static constexpr bool use_geometry_cache = true;
 };
 
 template <int C, class Load>

@@ -30,6 +30,10 @@ struct MfData {
     // written by the first launch of the kernel and read by all later ones.  EN234_MF_GEOM=0 disables it (A/B).
     double* d_geom = nullptr;
     int geom_state = 0;             // 0 not allocated yet, 1 allocated and to be written, 2 valid, -1 disabled / no memory
+    int grid_cached = 0, occ_cached = 2;   // persistent grid / CTAs per SM of k_element_forces_cached (EN234_MF_OCC=3: A/B)
+    int sm_share = 1;               // > 1: several parts of one mesh share the device (their kernels must be co-resident)
+    bool tpe = true;                // thread-per-element kernel on the transposed cache (EN234_MF_TPE=0: warp-cooperative forms)
+    size_t geom_stride = 0;
     // congruent-mesh fast path: every element is a translate of element 0 (bitwise equal node offsets, same material),
     // so one 24x24 K_e serves the whole mesh and a block row is determined by WHICH local nodes of its adjacent elements
     // the node is (and where their columns sit in the row): a few dozen distinct rows on a structured block.  The
@@ -430,6 +434,9 @@ inline int mf_set_congruent(MfData& mf, const double* Ke_colmajor, int N, const 
 inline void mf_prepare_geom(MfData& mf, int E) {
     if (mf.geom_state != 0) return;
     const char* e = getenv("EN234_MF_GEOM");
+    const char* t = getenv("EN234_MF_TPE");
+    mf.tpe = !(t && atoi(t) == 0);
+    mf.geom_stride = mf.tpe ? (size_t)((E + 3) / 4) * 4 : 0;
     const size_t bytes = (size_t)((E + 3) / 4) * 320 * sizeof(double);
     if ((e && atoi(e) == 0) || cudaMalloc((void**)&mf.d_geom, bytes) != cudaSuccess) { cudaGetLastError(); mf.geom_state = -1; }
     else mf.geom_state = 1;
@@ -437,12 +444,42 @@ inline void mf_prepare_geom(MfData& mf, int E) {
 // Launch of the residual-only element kernel with the geometry cache in the right state.
 template <class Load>
 inline void launch_element_forces(MfData& mf, ElemArgs EA, const Load& ld, int grid, cudaStream_t s) {
+    // the cache pays for the operator of the matrix-free solve (thousands of applications per step, measured 0.89 -> 0.75 ms
+    // at 128^3); the residual assembly and the explicit-dynamics step (LoadSum, once per assembly / time step) measured
+    // slower with it (64^3: 181 vs 128 us per dynamic step) and keep the coordinate-based kernel
+    if (!Load::use_geometry_cache) { k_element_forces<Load, 0><<<grid, 256, 0, s>>>(EA, ld); return; }
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(s, &cap);
     if (mf.geom_state == 0 && cap == cudaStreamCaptureStatusNone) mf_prepare_geom(mf, EA.M.E);
     EA.geom = mf.d_geom;
+    EA.geom_stride = mf.geom_stride;
     if (mf.geom_state == 0) { k_element_forces<Load, 0><<<grid, 256, 0, s>>>(EA, ld); return; }   // capturing, no cache yet
-    if (mf.geom_state == 2) k_element_forces<Load, 2><<<grid, 256, 0, s>>>(EA, ld);
+    if (mf.geom_state == 2 && mf.tpe) {
+        if (mf.grid_cached == 0) {
+            int occ = 1, dev = 0, n_sm = 148;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_element_forces_tpe<Load>, TPE_THREADS, 0);
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            mf.grid_cached = std::max(1, std::min((EA.M.E + TPE_THREADS - 1) / TPE_THREADS, std::max(1, n_sm / mf.sm_share) * std::max(occ, 1)));
+        }
+        k_element_forces_tpe<Load><<<mf.grid_cached, TPE_THREADS, 0, s>>>(EA, ld);
+    } else if (mf.geom_state == 2) {
+        if (mf.grid_cached == 0) {
+            const char* o = getenv("EN234_MF_OCC");
+            mf.occ_cached = (o && atoi(o) == 3) ? 3 : 2;
+            int occ = 1;
+            if (mf.occ_cached == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_element_forces_cached<Load, 3>, 256, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_element_forces_cached<Load, 2>, 256, 0);
+            int dev = 0, n_sm = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            mf.grid_cached = std::max(1, std::min(((EA.M.E + 3) / 4 + 7) / 8, std::max(1, n_sm / mf.sm_share) * std::max(occ, 1)));
+        }
+        const char* v = getenv("EN234_MF_XI");
+        if (v && atoi(v) == 0) k_element_forces<Load, 2><<<grid, 256, 0, s>>>(EA, ld);
+        else if (mf.occ_cached == 3) k_element_forces_cached<Load, 3><<<mf.grid_cached, 256, 0, s>>>(EA, ld);
+        else k_element_forces_cached<Load, 2><<<mf.grid_cached, 256, 0, s>>>(EA, ld);
+    }
     else if (mf.geom_state == 1) {
         k_element_forces<Load, 1><<<grid, 256, 0, s>>>(EA, ld);
         // a kernel whose Load can make it return at once (PCG stop flag) may not have written the cache

@@ -114,6 +114,7 @@ static int preload_partitioned_kernels() {
     PRELOAD(k_element_blocks<false, true, LoadSum>); PRELOAD(k_element_blocks<true, true, LoadSum>);
     PRELOAD(k_element_blocks<true, false, LoadSum>); PRELOAD(k_assemble_rows<false>); PRELOAD(k_assemble_rows<true>);
     PRELOAD(k_element_forces<LoadSum, 0>); PRELOAD(k_element_forces<LoadSum, 1>); PRELOAD(k_element_forces<LoadSum, 2>);
+    PRELOAD(k_element_forces_tpe<LoadSum>); PRELOAD(k_element_forces_tpe<LoadMasked>); PRELOAD(k_element_forces_cached<LoadSum, 2>); PRELOAD(k_element_forces_cached<LoadMasked, 2>);
     PRELOAD(k_element_forces<LoadMasked, 0>); PRELOAD(k_element_forces<LoadMasked, 1>); PRELOAD(k_element_forces<LoadMasked, 2>);
     PRELOAD(k_gather_rows); PRELOAD(k_gather_residual); PRELOAD(k_negate_norm); PRELOAD(k_reduce_to); PRELOAD(k_reduce2_to);
     PRELOAD(k_pack2); PRELOAD(k_unpack2); PRELOAD(k_set_corrections); PRELOAD(k_apply_bc); PRELOAD(k_bc_rest); PRELOAD(k_bc_finalize);

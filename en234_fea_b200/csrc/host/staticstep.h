@@ -30,6 +30,7 @@ struct StepResult {
     std::vector<int> cg_iterations;
     std::vector<double> step_time;
     int n_steps_completed = 0, n_cutbacks = 0, n_state_prints = 0;
+    bool warned_no_state_print = false;
     std::string error;
 };
 

@@ -76,7 +76,7 @@ def gpu_lib():
     """liben234gpu.so (raises if it was not built: the product never falls back to a CPU path)."""
     global _gpu
     if _gpu is None:
-        path = os.path.join(_CSRC, "liben234gpu.so")
+        path = os.environ.get("EN234_GPU_LIB") or os.path.join(_CSRC, "liben234gpu.so")   # override: A/B builds of kernel variants
         if not os.path.exists(path):
             raise RuntimeError("liben234gpu.so is not built (run python -c 'import __graft_entry__ as g; g.build()')")
         L = C.CDLL(path, mode=C.RTLD_GLOBAL)

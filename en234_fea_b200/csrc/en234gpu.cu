@@ -697,14 +697,14 @@ static int launch_operator(en234gpu_ctx* c, int method, const double* x, double*
 
 // assembled operator of a partitioned run with the collectives folded in: one launch over all local rows that also pushes
 // the interface rows to the neighbours and the rank's p.Ap to all ranks
-static void launch_spmv_fused(en234gpu_ctx* c, const double* x, double* y) {
+static void launch_spmv_fused(en234gpu_ctx* c, const double* x, double* y, int halo_in_spmv) {
     const int need = (c->N + WARPS - 1) / WARPS;
     const int grid = std::max(1, std::min(need, c->grid_spmv));
     SpmvArgs A;
     A.row0 = 0; A.N = c->N; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
     A.partials = c->part.p; A.S = c->S.p; A.check_stop = 1;
     FusedComm F = c->comm.F;
-    F.halo_in_spmv = 1;
+    F.halo_in_spmv = halo_in_spmv;
     if (c->max_row_blocks <= 32) k_spmv<4, false, true><<<grid, THREADS, 0, c->stream>>>(A, F);
     else k_spmv<4, true, true><<<grid, THREADS, 0, c->stream>>>(A, F);
     c->st.kernel_launches++;
@@ -754,8 +754,14 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
     Comm& cm = c->comm;
     if (cm.active && cm.p2p && cm.fused) {
         // collectives folded into the kernels: three launches per iteration on the assembled operator, like one GPU
-        if (method == EN234_SOLVE_PCG_BSR) {
-            launch_spmv_fused(c, c->p.p, c->Ap.p);
+        static const bool halo_in_spmv = !(getenv("EN234_FUSED_HALO") && atoi(getenv("EN234_FUSED_HALO")) == 0);
+        if (method == EN234_SOLVE_PCG_BSR && halo_in_spmv) {
+            launch_spmv_fused(c, c->p.p, c->Ap.p, 1);
+        } else if (method == EN234_SOLVE_PCG_BSR) {
+            // A/B: p.Ap pushed by the SpMV's last CTA, the interface rows by a separate push kernel afterwards
+            launch_spmv_fused(c, c->p.p, c->Ap.p, 0);
+            p2p_halo_push_fork(c, c->Ap.p);
+            p2p_halo_join(c);
         } else {
             const uint8_t* owned = c->have_owned ? c->owned.p : nullptr;
             if (c->mf.congruent) {

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_init_finish(CgVecArgs A) {
 // than the matrix, so these kernels are latency-bound unless several loads per thread are in flight).
 constexpr int VEC_ILP = 4;
 template <bool FUSED>
-__global__ void __launch_bounds__(VEC_THREADS, FUSED ? 3 : 4) k_cg_update(CgVecArgs A) {
+__global__ void __launch_bounds__(VEC_THREADS, 4) k_cg_update(CgVecArgs A) {
     __shared__ double red[VEC_THREADS / 32 + 1];
     __shared__ double sh2[2];
     if (A.S->stop) return;

@@ -211,12 +211,15 @@ __device__ __forceinline__ void p2p_wait2(const FusedComm& F, unsigned long long
     ArenaHdr* mine = F.P.arena[F.P.me];
     const int par = (int)(seq & 1ULL);
     const int t = threadIdx.x;
-    if (t < F.P.n_ranks) spin_until(&mine->ar_flag[par][t], seq, &mine->error, F.P.timeout, S);
-    else if (hseq != 0ULL && t >= 32 && t < 32 + F.n_nbr)
+    // acquire: each spinning thread fences after it has seen its flag; the barrier passes that on to the threads that read
+    // the data (volatile loads, which bypass L1) — no fence in the other threads
+    if (t < F.P.n_ranks) { spin_until(&mine->ar_flag[par][t], seq, &mine->error, F.P.timeout, S); __threadfence_system(); }
+    else if (hseq != 0ULL && t >= 32 && t < 32 + F.n_nbr) {
         spin_until(&mine->halo_flag[F.nbr_rank[t - 32]], hseq, &mine->error, F.P.timeout, S);
+        __threadfence_system();
+    }
     __syncthreads();
     if (t == 0) {
-        __threadfence_system();
         double sa = 0.0, sb = 0.0;
         for (int q = 0; q < F.P.n_ranks; ++q) {                    // fixed rank order => identical sums on all ranks
             sa += *(volatile double*)&mine->ar_val[par][q][0];
@@ -225,7 +228,6 @@ __device__ __forceinline__ void p2p_wait2(const FusedComm& F, unsigned long long
         sh[0] = sa; sh[1] = sb;
     }
     __syncthreads();
-    __threadfence_system();
     a = sh[0]; b = sh[1];
 }
 

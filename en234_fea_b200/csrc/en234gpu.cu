@@ -330,7 +330,7 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
         c->grid_bc = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(ob, 1))));
         c->grid_spmv = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(os, 1))));
     }
-    c->grid_vec = std::min(MAX_PARTIALS, std::max(1, std::min((int)((nd + VEC_THREADS - 1) / VEC_THREADS), c->n_sm * 4)));
+    c->grid_vec = std::min(std::min(MAX_PARTIALS, P2P_MAXCTA), std::max(1, std::min((int)((nd + VEC_THREADS - 1) / VEC_THREADS), c->n_sm * 4)));
     {
         // two-kernel assembly: element kernel (one warp per four elements) + row gather
         int oe = 1, oe0 = 1, og = 1;
@@ -656,9 +656,10 @@ static CgVecArgs vec_args(en234gpu_ctx* c, int method, int parity) {
     V.owned = c->have_owned ? c->owned.p : nullptr;
     V.sol = c->sol.p; V.r = c->r.p; V.p = c->p.p; V.Ap = c->Ap.p;
     V.part_pAp = c->part.p;
-    V.n_part_pAp = c->comm.active ? 1 : operator_partials(c, method);
+    const bool fused = c->comm.active && c->comm.p2p && c->comm.fused;
+    V.n_part_pAp = (c->comm.active && !fused) ? 1 : operator_partials(c, method);
     V.part_a = c->part2.p; V.part_b = c->part3.p;
-    V.n_part = c->comm.active ? 1 : c->grid_vec;
+    V.n_part = (c->comm.active && !fused) ? 1 : c->grid_vec;
     V.S = c->S.p;
     V.parity = parity;
     if (c->comm.active && c->comm.p2p && c->comm.fused) {
@@ -695,19 +696,21 @@ static int launch_operator(en234gpu_ctx* c, int method, const double* x, double*
     return 0;
 }
 
-// assembled operator of a partitioned run with the collectives folded in: one launch over all local rows that also pushes
-// the interface rows to the neighbours and the rank's p.Ap to all ranks
-static void launch_spmv_fused(en234gpu_ctx* c, const double* x, double* y, int halo_in_spmv) {
-    const int need = (c->N + WARPS - 1) / WARPS;
+// interface rows of the assembled operator on a partitioned run: the fused SpMV variant stores them into the neighbours'
+// arenas as it goes and raises the flags; partials go to part[0 ...)
+static int launch_spmv_interface(en234gpu_ctx* c, const double* x, double* y, cudaStream_t stream) {
+    const int n_if = c->comm.n_interface;
+    const int need = (n_if + WARPS - 1) / WARPS;
     const int grid = std::max(1, std::min(need, c->grid_spmv));
     SpmvArgs A;
-    A.row0 = 0; A.N = c->N; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
+    A.row0 = 0; A.N = n_if; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
     A.partials = c->part.p; A.S = c->S.p; A.check_stop = 1;
     FusedComm F = c->comm.F;
-    F.halo_in_spmv = halo_in_spmv;
-    if (c->max_row_blocks <= 32) k_spmv<4, false, true><<<grid, THREADS, 0, c->stream>>>(A, F);
-    else k_spmv<4, true, true><<<grid, THREADS, 0, c->stream>>>(A, F);
+    F.halo_in_spmv = 1;
+    if (c->max_row_blocks <= 32) k_spmv<4, false, true><<<grid, THREADS, 0, stream>>>(A, F);
+    else k_spmv<4, true, true><<<grid, THREADS, 0, stream>>>(A, F);
     c->st.kernel_launches++;
+    return grid;
 }
 
 // peer-memory halo PUSH only (the consumer k_cg_update adds what arrived), forked to the side stream
@@ -728,6 +731,13 @@ static void p2p_halo_push_fork(en234gpu_ctx* c, double* vec) {
 // number of p.Ap partials the operator leaves in part[]
 static int operator_partials(en234gpu_ctx* c, int method) {
     if (method == EN234_SOLVE_PCG_MATRIXFREE) return c->mf.n_partials;
+    if (c->comm.active && c->comm.p2p && c->comm.fused) {
+        // two launches: interface rows, interior rows
+        const int n_if = c->comm.n_interface;
+        const int n1 = n_if > 0 ? std::max(1, std::min((n_if + WARPS - 1) / WARPS, c->grid_spmv)) : 0;
+        const int n2 = n_if < c->N ? std::max(1, std::min((c->N - n_if + WARPS - 1) / WARPS, c->grid_spmv)) : 0;
+        return n1 + n2;
+    }
     return std::max(1, std::min((c->N + WARPS - 1) / WARPS, c->grid_spmv));
 }
 
@@ -753,15 +763,19 @@ static void p2p_halo_join(en234gpu_ctx* c) { cudaStreamWaitEvent(c->stream, c->c
 static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
     Comm& cm = c->comm;
     if (cm.active && cm.p2p && cm.fused) {
-        // collectives folded into the kernels: three launches per iteration on the assembled operator, like one GPU
-        static const bool halo_in_spmv = !(getenv("EN234_FUSED_HALO") && atoi(getenv("EN234_FUSED_HALO")) == 0);
-        if (method == EN234_SOLVE_PCG_BSR && halo_in_spmv) {
-            launch_spmv_fused(c, c->p.p, c->Ap.p, 1);
-        } else if (method == EN234_SOLVE_PCG_BSR) {
-            // A/B: p.Ap pushed by the SpMV's last CTA, the interface rows by a separate push kernel afterwards
-            launch_spmv_fused(c, c->p.p, c->Ap.p, 0);
-            p2p_halo_push_fork(c, c->Ap.p);
-            p2p_halo_join(c);
+        // collectives folded into the kernels: no collective has a launch of its own
+        if (method == EN234_SOLVE_PCG_BSR) {
+            // interface rows first (they push themselves to the neighbours), then the interior rows with the lean kernel
+            // (the few interface rows run on the side stream, concurrently with the interior rows)
+            int n1 = 0, n2 = 0;
+            if (cm.n_interface > 0) {
+                cudaEventRecord(cm.ev_fork, c->stream);
+                cudaStreamWaitEvent(cm.side, cm.ev_fork, 0);
+                n1 = launch_spmv_interface(c, c->p.p, c->Ap.p, cm.side);
+                cudaEventRecord(cm.ev_join, cm.side);
+            }
+            if (cm.n_interface < c->N) launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2);
+            if (cm.n_interface > 0) cudaStreamWaitEvent(c->stream, cm.ev_join, 0);
         } else {
             const uint8_t* owned = c->have_owned ? c->owned.p : nullptr;
             if (c->mf.congruent) {
@@ -772,9 +786,7 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
                 launch_operator(c, method, c->p.p, c->Ap.p, 1);
                 p2p_halo_push_fork(c, c->Ap.p);
             }
-            k_p2p_push<<<1, VEC_THREADS, 0, c->stream>>>(cm.peers, c->part.p, operator_partials(c, method), c->S.p);
             p2p_halo_join(c);
-            c->st.kernel_launches++;
         }
         CgVecArgs V = vec_args(c, method, parity);
         k_cg_update<true><<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);

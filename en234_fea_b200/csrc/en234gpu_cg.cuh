@@ -40,10 +40,10 @@ __device__ __forceinline__ double reduce_partials_cg(const double* part, int n, 
 // rows in flight at any time are neighbours and their x entries hit in L2/L1.
 // WIDE = false: no block row has more than 32 blocks (every hex8 mesh with at most 8 elements per node), the tail loop
 // over further blocks is compiled out.
-// FUSED (partitioned runs, peer-memory arenas): the launch covers all local rows; interface rows (the first F.n_if) also
-// store their result into the neighbours' halo receive areas, every warp counts itself off when its interface rows are
-// done and the last one raises the neighbours' flags; the last CTA of the launch reduces the p.Ap partials and pushes the
-// rank's sum to all ranks (see en234gpu_p2p.cuh).
+// FUSED (partitioned runs, peer-memory arenas; launched over the interface rows [0, F.n_if) only, the interior rows go
+// through the lean variant so that the hot loop carries nothing extra): every row also stores its result into the
+// neighbours' halo receive areas, every warp counts itself off when its rows are done and the last one raises the
+// neighbours' flags (see en234gpu_p2p.cuh).
 template <int MINB, bool WIDE = true, bool FUSED = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A, FusedComm F = FusedComm{}) {
     __shared__ double red[WARPS + 1];
@@ -133,20 +133,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A, FusedComm F 
     if (FUSED && !arrived) arrive();
     const double t = block_sum<THREADS>(dot, red);
     if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
-    if (FUSED) {
-        __shared__ int s_last;
-        if (threadIdx.x == 0) {
-            __threadfence();
-            s_last = atomicAdd(&mine->tk_spmv, 1u) == gridDim.x - 1 ? 1 : 0;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            const double pAp = reduce_partials_cg<THREADS>(A.partials, (int)gridDim.x, red);
-            if (threadIdx.x == 0) mine->tk_spmv = 0;
-            p2p_push2(F.P, ld_volatile_u64(&mine->ar_seq) + 1ULL, pAp, 0.0);
-        }
-    }
 }
 
 struct CgVecArgs {
@@ -210,21 +196,29 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_cg_update(CgVecArgs A) {
     const int T = gridDim.x * VEC_THREADS;
     const int dfirst = blockIdx.x * VEC_THREADS + threadIdx.x;
     double pv[VEC_ILP], sv[VEC_ILP], rv[VEC_ILP], av[VEC_ILP], mv[VEC_ILP];
-    // the vector loads of the first chunk are in flight while the scalar arrives (partials / peers' arena slots)
+    double pAp;
+    unsigned long long seq = 0ULL, hseq = 0ULL;
+    ArenaHdr* mine = nullptr;
+    if (FUSED) {
+        // sequence numbers of this iteration's p.Ap all-reduce and halo exchange
+        mine = F.P.arena[F.P.me];
+        seq = ld_volatile_u64(&mine->ar_seq) + 1ULL;
+        hseq = F.n_nbr > 0 ? ld_volatile_u64(&mine->halo_seq) + 1ULL : 0ULL;
+    }
+    // CTA 0 exchanges the rank's p.Ap with the peers (and waits for the neighbours' interface rows) before it has anything
+    // else in flight; the others pick the all-reduced value up from their local broadcast slot (p2p_allreduce_cta) with
+    // the vector loads of their first chunk already under way
+    double unused;
+    if (FUSED && blockIdx.x == 0)
+        p2p_allreduce_cta<VEC_THREADS>(F, seq, hseq, A.S, A.part_pAp, A.n_part_pAp, nullptr, 0, red, sh2, pAp, unused);
 #pragma unroll
     for (int k = 0; k < VEC_ILP; ++k) {
         const int d = dfirst + k * T;
         if (d < A.n) { pv[k] = A.p[d]; sv[k] = A.sol[d]; rv[k] = A.r[d]; av[k] = A.Ap[d]; mv[k] = A.minv[d]; }
     }
-    double pAp;
-    unsigned long long seq = 0ULL, hseq = 0ULL;
-    ArenaHdr* mine = nullptr;
     if (FUSED) {
-        mine = F.P.arena[F.P.me];
-        seq = ld_volatile_u64(&mine->ar_seq) + 1ULL;
-        hseq = F.n_nbr > 0 ? ld_volatile_u64(&mine->halo_seq) + 1ULL : 0ULL;
-        double unused;
-        p2p_wait2(F, seq, hseq, A.S, sh2, pAp, unused);
+        if (blockIdx.x != 0)
+            p2p_allreduce_cta<VEC_THREADS>(F, seq, hseq, A.S, A.part_pAp, A.n_part_pAp, nullptr, 0, red, sh2, pAp, unused);
     } else {
         pAp = reduce_partials<VEC_THREADS>(A.part_pAp, A.n_part_pAp, red);
     }
@@ -256,24 +250,15 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_cg_update(CgVecArgs A) {
     const double s1 = block_sum<VEC_THREADS>(rz, red);
     if (threadIdx.x == 0) { A.part_a[blockIdx.x] = s0; A.part_b[blockIdx.x] = s1; }
     if (FUSED) {
-        // last CTA: this all-reduce and halo exchange are consumed by every CTA -> advance the counters, then reduce the
-        // r.r / r.z partials and push them to all ranks
-        __shared__ int s_last;
+        // last CTA: this all-reduce and halo exchange have been consumed by every CTA -> advance the counters
         if (threadIdx.x == 0) {
             __threadfence();
-            s_last = atomicAdd(&mine->tk_upd, 1u) == gridDim.x - 1 ? 1 : 0;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            const double a = reduce_partials_cg<VEC_THREADS>(A.part_a, (int)gridDim.x, red);
-            const double b = reduce_partials_cg<VEC_THREADS>(A.part_b, (int)gridDim.x, red);
-            if (threadIdx.x == 0) {
+            if (atomicAdd(&mine->tk_upd, 1u) == gridDim.x - 1) {
                 mine->tk_upd = 0;
                 mine->ar_seq = seq;
                 if (hseq != 0ULL) mine->halo_seq = hseq;
+                __threadfence();
             }
-            p2p_push2(F.P, seq + 1ULL, a, b);
         }
     }
 }
@@ -284,21 +269,27 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_pupdate(CgVecArgs A) {
     __shared__ double red[VEC_THREADS / 32 + 1];
     CgScalars* S = A.S;
     if (S->stop) return;
-    // start the vector loads of the first chunk before the scalar reduction so their latency overlaps it
     const int T = gridDim.x * VEC_THREADS;
     const int dfirst = blockIdx.x * VEC_THREADS + threadIdx.x;
     double pv[VEC_ILP], rv[VEC_ILP], mv[VEC_ILP];
+    double rr, rz;
+    unsigned long long seq = 0ULL;
+    if (A.F.active) {
+        seq = ld_volatile_u64(&A.F.P.arena[A.F.P.me]->ar_seq) + 1ULL;
+    }
+    // CTA 0 of a partitioned run exchanges r.r / r.z with the peers first; everybody else starts the vector loads of the
+    // first chunk before the scalars arrive so their latency overlaps the wait
+    __shared__ double sh2[2];
+    if (A.F.active && blockIdx.x == 0)
+        p2p_allreduce_cta<VEC_THREADS>(A.F, seq, 0ULL, S, A.part_a, A.n_part, A.part_b, A.n_part, red, sh2, rr, rz);
 #pragma unroll
     for (int k = 0; k < VEC_ILP; ++k) {
         const int d = dfirst + k * T;
         if (d < A.n) { pv[k] = A.p[d]; rv[k] = A.r[d]; mv[k] = A.minv[d]; }
     }
-    double rr, rz;
-    unsigned long long seq = 0ULL;
     if (A.F.active) {
-        __shared__ double sh2[2];
-        seq = ld_volatile_u64(&A.F.P.arena[A.F.P.me]->ar_seq) + 1ULL;
-        p2p_wait2(A.F, seq, 0ULL, S, sh2, rr, rz);
+        if (blockIdx.x != 0)
+            p2p_allreduce_cta<VEC_THREADS>(A.F, seq, 0ULL, S, A.part_a, A.n_part, A.part_b, A.n_part, red, sh2, rr, rz);
     } else {
         rr = reduce_partials<VEC_THREADS>(A.part_a, A.n_part, red);
         rz = reduce_partials<VEC_THREADS>(A.part_b, A.n_part, red);

@@ -17,7 +17,10 @@
 namespace en234k {
 
 constexpr int P2P_MAXR = 16;
+constexpr int P2P_MAXCTA = 1024;          // CTAs of a consumer kernel that can be served by the local broadcast slots
 constexpr long long P2P_TIMEOUT_CYCLES = 4000000000LL;   // default ~2 s at 2 GHz (EN234_P2P_TIMEOUT_MS overrides)
+
+struct BcastSlot { double a, b; unsigned long long seq, pad; };     // one 32-byte sector per consumer CTA
 
 struct ArenaHdr {
     unsigned long long ar_flag[2][P2P_MAXR];   // all-reduce: sequence number per (parity, source rank)
@@ -30,6 +33,7 @@ struct ArenaHdr {
     unsigned int tk_spmv, tk_upd;              // last-CTA tickets of the fused PCG kernels (k_spmv tail, k_cg_update tail)
     unsigned int arrive;                       // warps of the fused k_spmv that have finished their interface rows
     int pad[3];
+    BcastSlot bc[2][P2P_MAXCTA];               // local re-broadcast of an all-reduced pair to the CTAs of the consumer kernel
 };
 
 struct PeerSet {
@@ -204,31 +208,58 @@ __device__ __forceinline__ void p2p_push2(const PeerSet& P, unsigned long long s
     }
 }
 
-// all threads of the CTA (>= 64 threads): waits for all-reduce `seq` (and, when hseq != 0, for the halo pushes of all
-// neighbours), returns the two sums in every thread.  sh: 2 doubles of shared memory.
-__device__ __forceinline__ void p2p_wait2(const FusedComm& F, unsigned long long seq, unsigned long long hseq, CgScalars* S,
-                                          double* sh, double& a, double& b) {
+// All-reduce of the pair (sum of partA, sum of partB) inside the consumer kernel, all threads of every CTA (>= 64 threads).
+// CTA 0 is the rank's agent: it reduces the producer's partials in the fixed order, stores the rank's pair into every rank's
+// arena, waits for the peers' pairs (and, when hseq != 0, for the neighbours' halo flags), adds the pairs in rank order and
+// re-broadcasts the result through one 32-byte slot per CTA in LOCAL memory.  Every other CTA polls only its own slot: no
+// flag is polled by more than a handful of threads (hundreds of CTAs spinning on the one line a peer is trying to write
+// cost 15-20 us per all-reduce on B200), and the peers' stores stay one per rank.
+// sh: 2 doubles of shared memory, red: scratch of reduce_partials.
+template <int NT>
+__device__ __forceinline__ void p2p_allreduce_cta(const FusedComm& F, unsigned long long seq, unsigned long long hseq, CgScalars* S,
+                                                  const double* partA, int nA, const double* partB, int nB, double* red,
+                                                  double* sh, double& a, double& b) {
     ArenaHdr* mine = F.P.arena[F.P.me];
     const int par = (int)(seq & 1ULL);
     const int t = threadIdx.x;
-    // acquire: each spinning thread fences after it has seen its flag; the barrier passes that on to the threads that read
-    // the data (volatile loads, which bypass L1) — no fence in the other threads
-    if (t < F.P.n_ranks) { spin_until(&mine->ar_flag[par][t], seq, &mine->error, F.P.timeout, S); __threadfence_system(); }
-    else if (hseq != 0ULL && t >= 32 && t < 32 + F.n_nbr) {
-        spin_until(&mine->halo_flag[F.nbr_rank[t - 32]], hseq, &mine->error, F.P.timeout, S);
-        __threadfence_system();
-    }
-    __syncthreads();
-    if (t == 0) {
-        double sa = 0.0, sb = 0.0;
-        for (int q = 0; q < F.P.n_ranks; ++q) {                    // fixed rank order => identical sums on all ranks
-            sa += *(volatile double*)&mine->ar_val[par][q][0];
-            sb += *(volatile double*)&mine->ar_val[par][q][1];
+    BcastSlot* bc = mine->bc[par];
+    if (blockIdx.x == 0) {
+        const double la = reduce_partials<NT>(partA, nA, red);
+        const double lb = partB ? reduce_partials<NT>(partB, nB, red) : 0.0;
+        p2p_push2(F.P, seq, la, lb);
+        // acquire: each spinning thread fences after it has seen its flag; the barrier passes that on
+        if (t < F.P.n_ranks) { spin_until(&mine->ar_flag[par][t], seq, &mine->error, F.P.timeout, S); __threadfence_system(); }
+        else if (hseq != 0ULL && t >= 32 && t < 32 + F.n_nbr) {
+            spin_until(&mine->halo_flag[F.nbr_rank[t - 32]], hseq, &mine->error, F.P.timeout, S);
+            __threadfence_system();
         }
-        sh[0] = sa; sh[1] = sb;
+        __syncthreads();
+        if (t == 0) {
+            double sa = 0.0, sb = 0.0;
+            for (int q = 0; q < F.P.n_ranks; ++q) {                    // fixed rank order => identical sums on all ranks
+                sa += *(volatile double*)&mine->ar_val[par][q][0];
+                sb += *(volatile double*)&mine->ar_val[par][q][1];
+            }
+            sh[0] = sa; sh[1] = sb;
+        }
+        __syncthreads();
+        a = sh[0]; b = sh[1];
+        for (int j = 1 + t; j < (int)gridDim.x; j += NT) {
+            *(volatile double*)&bc[j].a = a;
+            *(volatile double*)&bc[j].b = b;
+        }
+        __threadfence();
+        for (int j = 1 + t; j < (int)gridDim.x; j += NT) *(volatile unsigned long long*)&bc[j].seq = seq;
+    } else {
+        if (t == 0) {
+            spin_until(&bc[blockIdx.x].seq, seq, &mine->error, F.P.timeout, S);
+            __threadfence();
+            sh[0] = *(volatile double*)&bc[blockIdx.x].a;
+            sh[1] = *(volatile double*)&bc[blockIdx.x].b;
+        }
+        __syncthreads();
+        a = sh[0]; b = sh[1];
     }
-    __syncthreads();
-    a = sh[0]; b = sh[1];
 }
 
 // value of interface DOF d (= 3 * node + c, node < n_if): own partial value and the neighbours' in ascending rank order

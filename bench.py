@@ -174,8 +174,9 @@ class Block:
             self.part = Partition(self.model, D.world, D.rank)
             self.gpu = GpuSystem(self.model, device=D.local, part=self.part)
             self.comm_kind = self.gpu.setup_distributed()
-            if self.comm_kind == "peer-memory" and os.environ.get("EN234_P2P_FUSED", "1") != "0":
-                self.comm_kind = "peer-memory, folded into the PCG kernels"
+            if self.comm_kind == "peer-memory":
+                self.comm_kind = ("peer-memory, folded into the PCG kernels (EN234_P2P_FUSED=1)" if os.environ.get("EN234_P2P_FUSED") == "1"
+                                  else "peer-memory (single-CTA collective kernels; interface rows and their exchange on a side stream)")
             self.l2g = self.part.ints("local_to_global_node").astype(np.int64)
             self.ldof = (3 * self.l2g[:, None] + np.arange(3)).ravel()
             g2l = -np.ones(self.ndof_global, np.int64)

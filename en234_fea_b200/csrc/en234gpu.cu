@@ -656,30 +656,33 @@ static CgVecArgs vec_args(en234gpu_ctx* c, int method, int parity) {
     V.owned = c->have_owned ? c->owned.p : nullptr;
     V.sol = c->sol.p; V.r = c->r.p; V.p = c->p.p; V.Ap = c->Ap.p;
     V.part_pAp = c->part.p;
-    const bool fused = c->comm.active && c->comm.p2p && c->comm.fused;
+    const bool fused = c->comm.active && c->comm.p2p && c->comm.fused && c->comm.fused_loop;
     V.n_part_pAp = (c->comm.active && !fused) ? 1 : operator_partials(c, method);
     V.part_a = c->part2.p; V.part_b = c->part3.p;
     V.n_part = (c->comm.active && !fused) ? 1 : c->grid_vec;
     V.S = c->S.p;
     V.parity = parity;
-    if (c->comm.active && c->comm.p2p && c->comm.fused) {
+    if (c->comm.active && c->comm.p2p && c->comm.fused && c->comm.fused_loop) {
         V.F = c->comm.F;
         V.F.halo_in_spmv = method == EN234_SOLVE_PCG_BSR ? 1 : 0;
+        V.F.pAp_pushed = method == EN234_SOLVE_PCG_BSR ? 1 : 0;
     }
     return V;
 }
 
 // y = A x on block rows [row0, row1) (assembled operator); partials are written at part[part_off ...]
 static int launch_spmv_rows(en234gpu_ctx* c, const double* x, double* y, int row0, int row1, int part_off, int check_stop,
-                            int* n_part) {
+                            int* n_part, int tail_total = 0, cudaStream_t stream = nullptr) {
+    if (!stream) stream = c->stream;
     const int need = (row1 - row0 + WARPS - 1) / WARPS;
     const int grid = std::max(1, std::min(need, c->grid_spmv));
     SpmvArgs A;
     A.row0 = row0; A.N = row1; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
     A.partials = c->part.p + part_off; A.S = c->S.p; A.check_stop = check_stop;
-    if (c->spmv_occ == 5) k_spmv<5><<<grid, THREADS, 0, c->stream>>>(A);
-    else if (c->max_row_blocks <= 32) k_spmv<4, false><<<grid, THREADS, 0, c->stream>>>(A);
-    else k_spmv<4><<<grid, THREADS, 0, c->stream>>>(A);
+    if (tail_total > 0) { A.tail = (ArenaHdr*)c->comm.arena; A.tail_partials = c->part.p; A.tail_total = tail_total; }
+    if (c->spmv_occ == 5) k_spmv<5><<<grid, THREADS, 0, stream>>>(A);
+    else if (c->max_row_blocks <= 32) k_spmv<4, false><<<grid, THREADS, 0, stream>>>(A);
+    else k_spmv<4><<<grid, THREADS, 0, stream>>>(A);
     c->st.kernel_launches++;
     *n_part = grid;
     return 0;
@@ -698,13 +701,14 @@ static int launch_operator(en234gpu_ctx* c, int method, const double* x, double*
 
 // interface rows of the assembled operator on a partitioned run: the fused SpMV variant stores them into the neighbours'
 // arenas as it goes and raises the flags; partials go to part[0 ...)
-static int launch_spmv_interface(en234gpu_ctx* c, const double* x, double* y, cudaStream_t stream) {
+static int launch_spmv_interface(en234gpu_ctx* c, const double* x, double* y, cudaStream_t stream, int tail_total) {
     const int n_if = c->comm.n_interface;
     const int need = (n_if + WARPS - 1) / WARPS;
     const int grid = std::max(1, std::min(need, c->grid_spmv));
     SpmvArgs A;
     A.row0 = 0; A.N = n_if; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
     A.partials = c->part.p; A.S = c->S.p; A.check_stop = 1;
+    A.tail = (ArenaHdr*)c->comm.arena; A.tail_partials = c->part.p; A.tail_total = tail_total;
     FusedComm F = c->comm.F;
     F.halo_in_spmv = 1;
     if (c->max_row_blocks <= 32) k_spmv<4, false, true><<<grid, THREADS, 0, stream>>>(A, F);
@@ -731,7 +735,7 @@ static void p2p_halo_push_fork(en234gpu_ctx* c, double* vec) {
 // number of p.Ap partials the operator leaves in part[]
 static int operator_partials(en234gpu_ctx* c, int method) {
     if (method == EN234_SOLVE_PCG_MATRIXFREE) return c->mf.n_partials;
-    if (c->comm.active && c->comm.p2p && c->comm.fused) {
+    if (c->comm.active && c->comm.p2p && c->comm.fused && c->comm.fused_loop) {
         // two launches: interface rows, interior rows
         const int n_if = c->comm.n_interface;
         const int n1 = n_if > 0 ? std::max(1, std::min((n_if + WARPS - 1) / WARPS, c->grid_spmv)) : 0;
@@ -758,23 +762,39 @@ static void p2p_halo_fork(en234gpu_ctx* c, double* vec, int check_stop) {
     cudaEventRecord(cm.ev_join, cm.side);
 }
 static void p2p_halo_join(en234gpu_ctx* c) { cudaStreamWaitEvent(c->stream, c->comm.ev_join, 0); }
+// the same exchange for a caller that has already forked the side stream
+static void p2p_halo_exchange_on_side(en234gpu_ctx* c, double* vec, int check_stop) {
+    Comm& cm = c->comm;
+    if (cm.n_nbr > 0) {
+        int mx = 0;
+        for (int k = 0; k < cm.n_nbr; ++k) mx = std::max(mx, 3 * (cm.shared_ptr[k + 1] - cm.shared_ptr[k]));
+        const int nblk = std::max(1, std::min(32, (mx + 255) / 256));
+        k_halo_push<<<dim3(nblk, cm.n_nbr), 256, 0, cm.side>>>(cm.peers, cm.halo, vec, c->S.p, check_stop);
+        for (int k = 0; k < cm.n_nbr; ++k)
+            k_halo_wait_add<<<nblk, 256, 0, cm.side>>>(cm.peers, cm.halo, k, k == cm.n_nbr - 1 ? 1 : 0, vec, c->S.p, check_stop);
+        c->st.kernel_launches += 1 + cm.n_nbr;
+    }
+    cudaEventRecord(cm.ev_join, cm.side);
+}
 
 // one PCG iteration on the stream (captured into the graph)
 static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
     Comm& cm = c->comm;
-    if (cm.active && cm.p2p && cm.fused) {
+    if (cm.active && cm.p2p && cm.fused && cm.fused_loop) {
         // collectives folded into the kernels: no collective has a launch of its own
         if (method == EN234_SOLVE_PCG_BSR) {
             // interface rows first (they push themselves to the neighbours), then the interior rows with the lean kernel
             // (the few interface rows run on the side stream, concurrently with the interior rows)
+            // The CTA that finishes last over both launches reduces the p.Ap partials and pushes the rank's sum.
             int n1 = 0, n2 = 0;
+            const int total = operator_partials(c, method);
             if (cm.n_interface > 0) {
                 cudaEventRecord(cm.ev_fork, c->stream);
                 cudaStreamWaitEvent(cm.side, cm.ev_fork, 0);
-                n1 = launch_spmv_interface(c, c->p.p, c->Ap.p, cm.side);
+                n1 = launch_spmv_interface(c, c->p.p, c->Ap.p, cm.side, total);
                 cudaEventRecord(cm.ev_join, cm.side);
             }
-            if (cm.n_interface < c->N) launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2);
+            if (cm.n_interface < c->N) launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2, total);
             if (cm.n_interface > 0) cudaStreamWaitEvent(c->stream, cm.ev_join, 0);
         } else {
             const uint8_t* owned = c->have_owned ? c->owned.p : nullptr;
@@ -797,13 +817,28 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
     if (cm.active && cm.p2p) {
         // interface rows first; their halo exchange (peer-memory stores + flags, side stream) overlaps the interior
         // rows; p.Ap is the all-reduced sum of local partial products over ALL local rows, which needs no halo first
+        // EN234_P2P_TAIL (default 1): the producers' last CTAs reduce their partials and push the rank's sums (the stores cross
+        // NVLink during the kernel boundary), the collective kernels in between only wait and add
+        static const bool tail_push = !(getenv("EN234_P2P_TAIL") && atoi(getenv("EN234_P2P_TAIL")) == 0);
+        bool spmv_pushed = false;
         int np = 0;
         if (method == EN234_SOLVE_PCG_BSR && cm.n_interface > 0 && cm.n_interface < c->N) {
+            // side stream: the few interface rows, then their exchange (push, wait + add); main stream: the interior rows
+            // at the same time.  The all-reduce needs the partials of both launches (ev_if), k_cg_update the whole side
+            // stream (ev_join).
             int n1 = 0, n2 = 0;
-            launch_spmv_rows(c, c->p.p, c->Ap.p, 0, cm.n_interface, 0, 1, &n1);
-            p2p_halo_fork(c, c->Ap.p, 1);
-            launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2);
+            cudaEventRecord(cm.ev_fork, c->stream);
+            cudaStreamWaitEvent(cm.side, cm.ev_fork, 0);
+            const int g1 = std::max(1, std::min((cm.n_interface + WARPS - 1) / WARPS, c->grid_spmv));
+            const int g2 = std::max(1, std::min((c->N - cm.n_interface + WARPS - 1) / WARPS, c->grid_spmv));
+            const int tail_total = tail_push ? g1 + g2 : 0;
+            launch_spmv_rows(c, c->p.p, c->Ap.p, 0, cm.n_interface, 0, 1, &n1, tail_total, cm.side);
+            cudaEventRecord(cm.ev_if, cm.side);
+            p2p_halo_exchange_on_side(c, c->Ap.p, 1);
+            launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2, tail_total);
+            cudaStreamWaitEvent(c->stream, cm.ev_if, 0);
             np = n1 + n2;
+            spmv_pushed = tail_push;
         } else if (method == EN234_SOLVE_PCG_MATRIXFREE && c->mf.congruent) {
             // congruent-mesh operator: the non-dominant rows (all interface rows among them) first, their halo
             // exchange overlaps the dominant rows
@@ -817,12 +852,15 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
             np = operator_partials(c, method);
             p2p_halo_fork(c, c->Ap.p, 1);
         }
-        k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(cm.peers, c->part.p, np, nullptr, 0, c->part.p, nullptr, c->S.p, 1);
+        if (spmv_pushed) k_p2p_wait<<<1, 32, 0, c->stream>>>(cm.peers, c->part.p, nullptr, c->S.p);
+        else k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(cm.peers, c->part.p, np, nullptr, 0, c->part.p, nullptr, c->S.p, 1);
         p2p_halo_join(c);
         CgVecArgs V = vec_args(c, method, parity);
+        if (tail_push) V.tail = (ArenaHdr*)cm.arena;
         k_cg_update<false><<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
-        k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(cm.peers, c->part2.p, c->grid_vec, c->part3.p, c->grid_vec,
-                                                          c->part2.p, c->part3.p, c->S.p, 1);
+        if (tail_push) k_p2p_wait<<<1, 32, 0, c->stream>>>(cm.peers, c->part2.p, c->part3.p, c->S.p);
+        else k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(cm.peers, c->part2.p, c->grid_vec, c->part3.p, c->grid_vec,
+                                                               c->part2.p, c->part3.p, c->S.p, 1);
         k_cg_pupdate<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
         c->st.kernel_launches += 4;
         return 0;

@@ -20,6 +20,11 @@ struct SpmvArgs {
     double* partials;       // per-CTA sum of p.(A p) over the CTA's rows (all local rows, see DESIGN.md multi-GPU)
     const CgScalars* S;
     int check_stop;
+    // partitioned runs with folded collectives: the CTA that finishes last among tail_total CTAs (of the interface and the
+    // interior launch together) reduces tail_partials[0 .. tail_total) and pushes the rank's p.Ap (p2p_tail_push)
+    ArenaHdr* tail = nullptr;
+    const double* tail_partials = nullptr;
+    int tail_total = 0;
 };
 
 // reduce_partials for partials written by OTHER CTAs of the same launch (last-CTA tails): loads bypass L1
@@ -133,6 +138,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A, FusedComm F 
     if (FUSED && !arrived) arrive();
     const double t = block_sum<THREADS>(dot, red);
     if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
+    if (A.tail) p2p_tail_push<THREADS>(A.tail, &A.tail->tk_spmv, (unsigned)A.tail_total, A.tail_partials, nullptr, A.tail_total, red);
 }
 
 struct CgVecArgs {
@@ -146,6 +152,7 @@ struct CgVecArgs {
     CgScalars* S;
     int parity;                    // iteration parity (selects S->rz slot)
     FusedComm F;                   // collectives folded into the vector kernels (F.active; en234gpu_p2p.cuh)
+    ArenaHdr* tail = nullptr;      // separate-kernel collectives: k_cg_update's last CTA pushes the rank's r.r / r.z
 };
 
 __device__ __forceinline__ bool dof_owned(const uint8_t* owned, int d) { return owned == nullptr || owned[d / 3] != 0; }
@@ -209,8 +216,10 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_cg_update(CgVecArgs A) {
     // else in flight; the others pick the all-reduced value up from their local broadcast slot (p2p_allreduce_cta) with
     // the vector loads of their first chunk already under way
     double unused;
+    const int nif3 = FUSED ? 3 * F.n_if : 0, hpar = (int)(hseq & 1ULL);
+    const bool need_halo = (int)(blockIdx.x * VEC_THREADS) < nif3;     // this CTA's first chunk reaches into the interface DOFs
     if (FUSED && blockIdx.x == 0)
-        p2p_allreduce_cta<VEC_THREADS>(F, seq, hseq, A.S, A.part_pAp, A.n_part_pAp, nullptr, 0, red, sh2, pAp, unused);
+        p2p_allreduce_cta<VEC_THREADS>(F, seq, hseq, A.S, F.pAp_pushed, need_halo, A.part_pAp, A.n_part_pAp, nullptr, 0, red, sh2, pAp, unused);
 #pragma unroll
     for (int k = 0; k < VEC_ILP; ++k) {
         const int d = dfirst + k * T;
@@ -218,12 +227,11 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_cg_update(CgVecArgs A) {
     }
     if (FUSED) {
         if (blockIdx.x != 0)
-            p2p_allreduce_cta<VEC_THREADS>(F, seq, hseq, A.S, A.part_pAp, A.n_part_pAp, nullptr, 0, red, sh2, pAp, unused);
+            p2p_allreduce_cta<VEC_THREADS>(F, seq, hseq, A.S, F.pAp_pushed, need_halo, A.part_pAp, A.n_part_pAp, nullptr, 0, red, sh2, pAp, unused);
     } else {
         pAp = reduce_partials<VEC_THREADS>(A.part_pAp, A.n_part_pAp, red);
     }
     const double ak = A.S->rz[A.parity] / pAp;
-    const int nif3 = FUSED ? 3 * F.n_if : 0, hpar = (int)(hseq & 1ULL);
     double rr = 0.0, rz = 0.0;
     for (int d0 = dfirst; d0 < A.n; d0 += VEC_ILP * T) {
         if (d0 != dfirst) {
@@ -249,16 +257,27 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_cg_update(CgVecArgs A) {
     const double s0 = block_sum<VEC_THREADS>(rr, red);
     const double s1 = block_sum<VEC_THREADS>(rz, red);
     if (threadIdx.x == 0) { A.part_a[blockIdx.x] = s0; A.part_b[blockIdx.x] = s1; }
+    if (!FUSED && A.tail)
+        p2p_tail_push<VEC_THREADS>(A.tail, &A.tail->tk_upd, gridDim.x, A.part_a, A.part_b, (int)gridDim.x, red);
     if (FUSED) {
-        // last CTA: this all-reduce and halo exchange have been consumed by every CTA -> advance the counters
+        // last CTA: this all-reduce and halo exchange have been consumed by every CTA -> advance the counters, then reduce
+        // the r.r / r.z partials and push them to all ranks (they cross NVLink while k_cg_pupdate is being launched)
+        __shared__ int s_last;
         if (threadIdx.x == 0) {
             __threadfence();
-            if (atomicAdd(&mine->tk_upd, 1u) == gridDim.x - 1) {
+            s_last = atomicAdd(&mine->tk_upd, 1u) == gridDim.x - 1 ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const double a = reduce_partials_cg<VEC_THREADS>(A.part_a, (int)gridDim.x, red);
+            const double b = reduce_partials_cg<VEC_THREADS>(A.part_b, (int)gridDim.x, red);
+            if (threadIdx.x == 0) {
                 mine->tk_upd = 0;
                 mine->ar_seq = seq;
                 if (hseq != 0ULL) mine->halo_seq = hseq;
-                __threadfence();
             }
+            p2p_push2(F.P, seq + 1ULL, a, b);
         }
     }
 }
@@ -281,7 +300,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_pupdate(CgVecArgs A) {
     // first chunk before the scalars arrive so their latency overlaps the wait
     __shared__ double sh2[2];
     if (A.F.active && blockIdx.x == 0)
-        p2p_allreduce_cta<VEC_THREADS>(A.F, seq, 0ULL, S, A.part_a, A.n_part, A.part_b, A.n_part, red, sh2, rr, rz);
+        p2p_allreduce_cta<VEC_THREADS>(A.F, seq, 0ULL, S, 1, false, A.part_a, A.n_part, A.part_b, A.n_part, red, sh2, rr, rz);
 #pragma unroll
     for (int k = 0; k < VEC_ILP; ++k) {
         const int d = dfirst + k * T;
@@ -289,7 +308,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_pupdate(CgVecArgs A) {
     }
     if (A.F.active) {
         if (blockIdx.x != 0)
-            p2p_allreduce_cta<VEC_THREADS>(A.F, seq, 0ULL, S, A.part_a, A.n_part, A.part_b, A.n_part, red, sh2, rr, rz);
+            p2p_allreduce_cta<VEC_THREADS>(A.F, seq, 0ULL, S, 1, false, A.part_a, A.n_part, A.part_b, A.n_part, red, sh2, rr, rz);
     } else {
         rr = reduce_partials<VEC_THREADS>(A.part_a, A.n_part, red);
         rz = reduce_partials<VEC_THREADS>(A.part_b, A.n_part, red);

@@ -70,10 +70,11 @@ struct Comm {
     PeerSet peers{};
     HaloSet halo{};
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_if = nullptr;
     // collectives folded into the PCG kernels (FusedComm, en234gpu_p2p.cuh): per interface node the (neighbour, position)
     // entries in ascending neighbour rank; EN234_P2P_FUSED=0 keeps the separate push / wait-add / all-reduce kernels
-    bool fused = false;
+    bool fused = false;                       // interface tables built
+    bool fused_loop = false;                  // PCG loop with the collectives folded into the kernels (EN234_P2P_FUSED=1)
     bool inproc = false;                      // ranks are threads of one process (en234gpu_create_multi): no NCCL at all
     double* d_scratch = nullptr;              // 4 doubles: operand of the peer-memory scalar all-reduces
     std::vector<int> h_shared;                // host copy of the shared-node lists
@@ -148,12 +149,22 @@ inline int comm_arena_finish(Comm& c) {
             if (ms > 0.0) c.peers.timeout = (long long)(ms * 2.0e6);
         }
     }
+    // device copy of the peer table inside the local arena (producer tails reach it through one pointer)
+    if (cudaMemcpy(&((ArenaHdr*)c.arena)->peers, &c.peers, sizeof(PeerSet), cudaMemcpyHostToDevice) != cudaSuccess) {
+        comm_err_ref() = "cannot store the peer table";
+        return 1;
+    }
     // fused collectives: possible when the interface nodes are exactly the first local rows
     c.fused = false;
     c.F = FusedComm{};
     {
+        // The interface tables are always built (rank-ordered halo sums use them).  Whether the PCG loop folds its
+        // collectives into the kernels is c.fused_loop: measured on 2 and 8 B200 the folded forms were 4-13 % SLOWER than
+        // single-CTA collective kernels between the compute kernels, so it is opt-in
+        // (EN234_P2P_FUSED=1); ranks that are threads of one process use it too when asked.
         const char* e = getenv("EN234_P2P_FUSED");
-        const bool want = !(e && atoi(e) == 0);
+        c.fused_loop = e && atoi(e) == 1;
+        const bool want = true;
         if (want && (c.n_nbr == 0 || c.n_interface > 0)) {
             const int nif = c.n_interface;
             std::vector<int> cnt(nif + 1, 0);
@@ -192,7 +203,8 @@ inline int comm_arena_finish(Comm& c) {
     }
     if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.ev_if, cudaEventDisableTiming) != cudaSuccess) {
         comm_err_ref() = "cannot create the side stream";
         return 1;
     }
@@ -259,7 +271,8 @@ inline void comm_destroy(Comm& c) {
     if (c.side) cudaStreamDestroy(c.side);
     if (c.ev_fork) cudaEventDestroy(c.ev_fork);
     if (c.ev_join) cudaEventDestroy(c.ev_join);
-    c.arena = nullptr; c.side = nullptr; c.ev_fork = c.ev_join = nullptr; c.p2p = false;
+    if (c.ev_if) cudaEventDestroy(c.ev_if);
+    c.arena = nullptr; c.side = nullptr; c.ev_fork = c.ev_join = c.ev_if = nullptr; c.p2p = false;
     c.d_shared = nullptr; c.sendbuf = c.recvbuf = nullptr; c.active = false;
 }
 

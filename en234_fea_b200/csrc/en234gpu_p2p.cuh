@@ -21,6 +21,15 @@ constexpr int P2P_MAXCTA = 1024;          // CTAs of a consumer kernel that can 
 constexpr long long P2P_TIMEOUT_CYCLES = 4000000000LL;   // default ~2 s at 2 GHz (EN234_P2P_TIMEOUT_MS overrides)
 
 struct BcastSlot { double a, b; unsigned long long seq, pad; };     // one 32-byte sector per consumer CTA
+struct ArenaHdr;
+
+struct PeerSet {
+    int n_ranks, me;
+    ArenaHdr* arena[P2P_MAXR];     // arena[me] is local
+    double* halo[P2P_MAXR];        // halo receive area of each rank: [source rank][parity][cap]
+    long long cap;                 // doubles per (source, parity)
+    long long timeout;             // spin time-out in SM clock cycles
+};
 
 struct ArenaHdr {
     unsigned long long ar_flag[2][P2P_MAXR];   // all-reduce: sequence number per (parity, source rank)
@@ -34,14 +43,7 @@ struct ArenaHdr {
     unsigned int arrive;                       // warps of the fused k_spmv that have finished their interface rows
     int pad[3];
     BcastSlot bc[2][P2P_MAXCTA];               // local re-broadcast of an all-reduced pair to the CTAs of the consumer kernel
-};
-
-struct PeerSet {
-    int n_ranks, me;
-    ArenaHdr* arena[P2P_MAXR];     // arena[me] is local
-    double* halo[P2P_MAXR];        // halo receive area of each rank: [source rank][parity][cap]
-    long long cap;                 // doubles per (source, parity)
-    long long timeout;             // spin time-out in SM clock cycles
+    PeerSet peers;                             // device copy of the peer table (producer tails reach it through one pointer)
 };
 
 struct HaloSet {
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(256) k_halo_wait_add(PeerSet P, HaloSet H, int
 struct FusedComm {
     int active;                       // 0: one GPU, NCCL path or the unfused peer-memory path
     int halo_in_spmv;                 // 1: k_spmv pushes the interface rows itself (assembled operator)
+    int pAp_pushed;                   // 1: the operator kernel's tail has pushed the rank's p.Ap (assembled operator)
     PeerSet P;
     int n_nbr;
     int nbr_rank[P2P_MAXR];
@@ -208,32 +211,68 @@ __device__ __forceinline__ void p2p_push2(const PeerSet& P, unsigned long long s
     }
 }
 
+// Tail of a producer kernel (k_spmv, k_cg_update), all threads of every CTA: the CTA that finishes last — counted over
+// `total` CTAs, which may belong to two concurrent launches — reduces the kernel's per-CTA partials in the fixed order and
+// stores the rank's pair into every rank's arena.  The peers' stores cross NVLink while the consumer kernel is being
+// launched.  `arena` is the local arena (its device copy of the peer table is used), `ticket` one of its counters.
+template <int NT>
+__device__ __forceinline__ void p2p_tail_push(ArenaHdr* arena, unsigned int* ticket, unsigned int total, const double* partA,
+                                              const double* partB, int n, double* red) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == total - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double a = 0.0, b = 0.0;
+        for (int i = threadIdx.x; i < n; i += NT) { a += __ldcg(partA + i); if (partB) b += __ldcg(partB + i); }
+        a = block_sum<NT>(a, red);
+        b = block_sum<NT>(b, red);
+        if (threadIdx.x == 0) *ticket = 0;
+        p2p_push2(arena->peers, ld_volatile_u64(&arena->ar_seq) + 1ULL, a, b);
+    }
+}
+
 // All-reduce of the pair (sum of partA, sum of partB) inside the consumer kernel, all threads of every CTA (>= 64 threads).
-// CTA 0 is the rank's agent: it reduces the producer's partials in the fixed order, stores the rank's pair into every rank's
-// arena, waits for the peers' pairs (and, when hseq != 0, for the neighbours' halo flags), adds the pairs in rank order and
-// re-broadcasts the result through one 32-byte slot per CTA in LOCAL memory.  Every other CTA polls only its own slot: no
-// flag is polled by more than a handful of threads (hundreds of CTAs spinning on the one line a peer is trying to write
-// cost 15-20 us per all-reduce on B200), and the peers' stores stay one per rank.
+// The rank's pair normally arrives from the producer's tail (pushed != 0); otherwise CTA 0 reduces the partials and pushes.
+// Every CTA first looks ONCE at the peers' flags (and, when it handles interface DOFs, at the neighbours' halo flags): if
+// everything has arrived — the usual case, the stores crossed NVLink during the kernel launch — it adds the pairs in rank
+// order itself.  Otherwise it waits for CTA 0, the rank's agent, which spins on the flags and re-broadcasts the result
+// through one 32-byte slot per CTA in LOCAL memory: no flag is polled by more than a handful of threads (hundreds of CTAs
+// spinning on the one line a peer is trying to write cost 15-20 us per all-reduce on B200).
 // sh: 2 doubles of shared memory, red: scratch of reduce_partials.
 template <int NT>
 __device__ __forceinline__ void p2p_allreduce_cta(const FusedComm& F, unsigned long long seq, unsigned long long hseq, CgScalars* S,
-                                                  const double* partA, int nA, const double* partB, int nB, double* red,
-                                                  double* sh, double& a, double& b) {
+                                                  int pushed, bool need_halo, const double* partA, int nA, const double* partB,
+                                                  int nB, double* red, double* sh, double& a, double& b) {
     ArenaHdr* mine = F.P.arena[F.P.me];
     const int par = (int)(seq & 1ULL);
     const int t = threadIdx.x;
     BcastSlot* bc = mine->bc[par];
-    if (blockIdx.x == 0) {
+    const bool agent = blockIdx.x == 0;
+    if (agent && !pushed) {
         const double la = reduce_partials<NT>(partA, nA, red);
         const double lb = partB ? reduce_partials<NT>(partB, nB, red) : 0.0;
         p2p_push2(F.P, seq, la, lb);
-        // acquire: each spinning thread fences after it has seen its flag; the barrier passes that on
+    }
+    // one look at the flags this CTA depends on
+    int here = 1;
+    if (t < F.P.n_ranks) here = ld_volatile_u64(&mine->ar_flag[par][t]) >= seq;
+    else if ((need_halo || agent) && hseq != 0ULL && t >= 32 && t < 32 + F.n_nbr)
+        here = ld_volatile_u64(&mine->halo_flag[F.nbr_rank[t - 32]]) >= hseq;
+    if (here) __threadfence_system();                              // acquire (passed on by the barrier)
+    const int all_here = __syncthreads_and(here);
+    if (!all_here && agent) {
         if (t < F.P.n_ranks) { spin_until(&mine->ar_flag[par][t], seq, &mine->error, F.P.timeout, S); __threadfence_system(); }
         else if (hseq != 0ULL && t >= 32 && t < 32 + F.n_nbr) {
             spin_until(&mine->halo_flag[F.nbr_rank[t - 32]], hseq, &mine->error, F.P.timeout, S);
             __threadfence_system();
         }
         __syncthreads();
+    }
+    if (all_here || agent) {
         if (t == 0) {
             double sa = 0.0, sb = 0.0;
             for (int q = 0; q < F.P.n_ranks; ++q) {                    // fixed rank order => identical sums on all ranks
@@ -244,12 +283,14 @@ __device__ __forceinline__ void p2p_allreduce_cta(const FusedComm& F, unsigned l
         }
         __syncthreads();
         a = sh[0]; b = sh[1];
-        for (int j = 1 + t; j < (int)gridDim.x; j += NT) {
-            *(volatile double*)&bc[j].a = a;
-            *(volatile double*)&bc[j].b = b;
+        if (agent) {                                                    // always: some CTA may have looked too early
+            for (int j = 1 + t; j < (int)gridDim.x; j += NT) {
+                *(volatile double*)&bc[j].a = a;
+                *(volatile double*)&bc[j].b = b;
+            }
+            __threadfence();
+            for (int j = 1 + t; j < (int)gridDim.x; j += NT) *(volatile unsigned long long*)&bc[j].seq = seq;
         }
-        __threadfence();
-        for (int j = 1 + t; j < (int)gridDim.x; j += NT) *(volatile unsigned long long*)&bc[j].seq = seq;
     } else {
         if (t == 0) {
             spin_until(&bc[blockIdx.x].seq, seq, &mine->error, F.P.timeout, S);
@@ -325,6 +366,28 @@ __global__ void k_p2p_allreduce_vals(PeerSet P, double* vals, int n) {
         }
         vals[0] = sa;
         if (n > 1) vals[1] = sb;
+        mine->ar_seq = seq;
+    }
+}
+
+// one warp: the consumer half of an all-reduce whose pairs were pushed by the producers' tails (p2p_tail_push): wait for
+// all ranks' flags, add the pairs in rank order, store the sums, advance the counter
+__global__ void k_p2p_wait(PeerSet P, double* outA, double* outB, CgScalars* S) {
+    if (S->stop) return;
+    ArenaHdr* mine = P.arena[P.me];
+    const unsigned long long seq = ld_volatile_u64(&mine->ar_seq) + 1ULL;
+    const int par = (int)(seq & 1ULL);
+    const int r = threadIdx.x;
+    if (r < P.n_ranks) { spin_until(&mine->ar_flag[par][r], seq, &mine->error, P.timeout, S); __threadfence_system(); }
+    __syncwarp();
+    if (r == 0) {
+        double sa = 0.0, sb = 0.0;
+        for (int q = 0; q < P.n_ranks; ++q) {
+            sa += *(volatile double*)&mine->ar_val[par][q][0];
+            sb += *(volatile double*)&mine->ar_val[par][q][1];
+        }
+        *outA = sa;
+        if (outB) *outB = sb;
         mine->ar_seq = seq;
     }
 }

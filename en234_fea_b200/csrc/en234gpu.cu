@@ -137,6 +137,24 @@ static Mesh mesh_of(en234gpu_ctx* c) {
     return M;
 }
 
+// Kernel launch with the programmatic-dependent-launch attribute (the kernel calls pdl_wait() before it touches what its
+// predecessor in the stream wrote); opt-in with EN234_PDL=1 (64^3: 101.4 us per PCG iteration with and without it).
+static bool use_pdl() {
+    static const bool on = getenv("EN234_PDL") && atoi(getenv("EN234_PDL")) == 1;   // measured: no gain inside CUDA graphs on B200
+    return on;
+}
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = use_pdl() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 extern "C" {
 
 static int preallocate_for_shared_device(en234gpu_ctx* c);
@@ -672,7 +690,7 @@ static CgVecArgs vec_args(en234gpu_ctx* c, int method, int parity) {
 
 // y = A x on block rows [row0, row1) (assembled operator); partials are written at part[part_off ...]
 static int launch_spmv_rows(en234gpu_ctx* c, const double* x, double* y, int row0, int row1, int part_off, int check_stop,
-                            int* n_part, int tail_total = 0, cudaStream_t stream = nullptr) {
+                            int* n_part, int tail_total = 0, cudaStream_t stream = nullptr, bool pdl = false) {
     if (!stream) stream = c->stream;
     const int need = (row1 - row0 + WARPS - 1) / WARPS;
     const int grid = std::max(1, std::min(need, c->grid_spmv));
@@ -681,6 +699,8 @@ static int launch_spmv_rows(en234gpu_ctx* c, const double* x, double* y, int row
     A.partials = c->part.p + part_off; A.S = c->S.p; A.check_stop = check_stop;
     if (tail_total > 0) { A.tail = (ArenaHdr*)c->comm.arena; A.tail_partials = c->part.p; A.tail_total = tail_total; }
     if (c->spmv_occ == 5) k_spmv<5><<<grid, THREADS, 0, stream>>>(A);
+    else if (pdl && c->max_row_blocks <= 32) launch_pdl(k_spmv<4, false, false>, grid, THREADS, stream, A, FusedComm{});
+    else if (pdl) launch_pdl(k_spmv<4, true, false>, grid, THREADS, stream, A, FusedComm{});
     else if (c->max_row_blocks <= 32) k_spmv<4, false><<<grid, THREADS, 0, stream>>>(A);
     else k_spmv<4><<<grid, THREADS, 0, stream>>>(A);
     c->st.kernel_launches++;
@@ -694,7 +714,7 @@ static int launch_operator(en234gpu_ctx* c, int method, const double* x, double*
                  check_stop ? c->S.p : nullptr, c->stream, &c->st.kernel_launches);
     } else {
         int np = 0;
-        launch_spmv_rows(c, x, y, 0, c->N, 0, check_stop, &np);
+        launch_spmv_rows(c, x, y, 0, c->N, 0, check_stop, &np, 0, nullptr, check_stop != 0);
     }
     return 0;
 }
@@ -817,9 +837,10 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
     if (cm.active && cm.p2p) {
         // interface rows first; their halo exchange (peer-memory stores + flags, side stream) overlaps the interior
         // rows; p.Ap is the all-reduced sum of local partial products over ALL local rows, which needs no halo first
-        // EN234_P2P_TAIL (default 1): the producers' last CTAs reduce their partials and push the rank's sums (the stores cross
-        // NVLink during the kernel boundary), the collective kernels in between only wait and add
-        static const bool tail_push = !(getenv("EN234_P2P_TAIL") && atoi(getenv("EN234_P2P_TAIL")) == 0);
+        // EN234_P2P_TAIL=1 (A/B; measured 3 us per iteration slower on 2 B200): the producers' last CTAs reduce their partials
+        // and push the rank's sums (the stores cross NVLink during the kernel boundary), the collective kernels in between
+        // only wait and add.  Default: single-CTA all-reduce kernels (reduce, push, wait, add).
+        static const bool tail_push = getenv("EN234_P2P_TAIL") && atoi(getenv("EN234_P2P_TAIL")) == 1;
         bool spmv_pushed = false;
         int np = 0;
         if (method == EN234_SOLVE_PCG_BSR && cm.n_interface > 0 && cm.n_interface < c->N) {
@@ -835,7 +856,7 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
             launch_spmv_rows(c, c->p.p, c->Ap.p, 0, cm.n_interface, 0, 1, &n1, tail_total, cm.side);
             cudaEventRecord(cm.ev_if, cm.side);
             p2p_halo_exchange_on_side(c, c->Ap.p, 1);
-            launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2, tail_total);
+            launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2, tail_total, nullptr, true);
             cudaStreamWaitEvent(c->stream, cm.ev_if, 0);
             np = n1 + n2;
             spmv_pushed = tail_push;
@@ -853,15 +874,16 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
             p2p_halo_fork(c, c->Ap.p, 1);
         }
         if (spmv_pushed) k_p2p_wait<<<1, 32, 0, c->stream>>>(cm.peers, c->part.p, nullptr, c->S.p);
-        else k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(cm.peers, c->part.p, np, nullptr, 0, c->part.p, nullptr, c->S.p, 1);
+        else launch_pdl(k_p2p_allreduce, 1, VEC_THREADS, c->stream, cm.peers, (const double*)c->part.p, np, (const double*)nullptr, 0,
+                        c->part.p, (double*)nullptr, (const CgScalars*)c->S.p, 1);
         p2p_halo_join(c);
         CgVecArgs V = vec_args(c, method, parity);
         if (tail_push) V.tail = (ArenaHdr*)cm.arena;
-        k_cg_update<false><<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+        launch_pdl(k_cg_update<false>, c->grid_vec, VEC_THREADS, c->stream, V);
         if (tail_push) k_p2p_wait<<<1, 32, 0, c->stream>>>(cm.peers, c->part2.p, c->part3.p, c->S.p);
-        else k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(cm.peers, c->part2.p, c->grid_vec, c->part3.p, c->grid_vec,
-                                                               c->part2.p, c->part3.p, c->S.p, 1);
-        k_cg_pupdate<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+        else launch_pdl(k_p2p_allreduce, 1, VEC_THREADS, c->stream, cm.peers, (const double*)c->part2.p, c->grid_vec,
+                        (const double*)c->part3.p, c->grid_vec, c->part2.p, c->part3.p, (const CgScalars*)c->S.p, 1);
+        launch_pdl(k_cg_pupdate, c->grid_vec, VEC_THREADS, c->stream, V);
         c->st.kernel_launches += 4;
         return 0;
     }
@@ -875,7 +897,7 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
         c->st.kernel_launches += 1 + c->comm.launches_per_halo;
     }
     CgVecArgs V = vec_args(c, method, parity);
-    k_cg_update<false><<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+    launch_pdl(k_cg_update<false>, c->grid_vec, VEC_THREADS, c->stream, V);
     c->st.kernel_launches++;
     if (cm.active) {
         k_reduce2_to<<<1, VEC_THREADS, 0, c->stream>>>(c->part2.p, c->part3.p, c->grid_vec, c->part2.p, c->part3.p);
@@ -885,7 +907,7 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
         k_unpack2<<<1, 1, 0, c->stream>>>(c->part2.p, c->part3.p);
         c->st.kernel_launches += 3;
     }
-    k_cg_pupdate<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(V);
+    launch_pdl(k_cg_pupdate, c->grid_vec, VEC_THREADS, c->stream, V);
     c->st.kernel_launches++;
     return 0;
 }

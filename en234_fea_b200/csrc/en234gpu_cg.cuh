@@ -52,7 +52,6 @@ __device__ __forceinline__ double reduce_partials_cg(const double* part, int n, 
 template <int MINB, bool WIDE = true, bool FUSED = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A, FusedComm F = FusedComm{}) {
     __shared__ double red[WARPS + 1];
-    if (A.check_stop && A.S->stop) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     ArenaHdr* mine = nullptr;
     unsigned long long hseq = 0ULL;
@@ -93,6 +92,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A, FusedComm F 
         if (d1 < nb) c1 = __ldg(A.bcol + rb + d1);
         if (d2 < nb) c2 = __ldg(A.bcol + rb + d2);
     }
+    // the index loads above touch nothing the previous kernel writes: with a programmatic launch they overlap its tail
+    pdl_wait();
+    pdl_trigger();
+    if (A.check_stop && A.S->stop) return;
     for (; i < N; i += W) {
         if (FUSED && !arrived && i >= F.n_if) arrive();
         const int nb = re - rb, L = 3 * nb;
@@ -198,11 +201,22 @@ template <bool FUSED>
 __global__ void __launch_bounds__(VEC_THREADS, 4) k_cg_update(CgVecArgs A) {
     __shared__ double red[VEC_THREADS / 32 + 1];
     __shared__ double sh2[2];
-    if (A.S->stop) return;
     const FusedComm& F = A.F;
     const int T = gridDim.x * VEC_THREADS;
     const int dfirst = blockIdx.x * VEC_THREADS + threadIdx.x;
     double pv[VEC_ILP], sv[VEC_ILP], rv[VEC_ILP], av[VEC_ILP], mv[VEC_ILP];
+    if (!FUSED) {
+        // p, sol, r and the preconditioner were last written at least two kernels ago: with a programmatic launch these
+        // loads overlap the tail of the operator kernel; A p and its partial sums are read after pdl_wait()
+#pragma unroll
+        for (int k = 0; k < VEC_ILP; ++k) {
+            const int d = dfirst + k * T;
+            if (d < A.n) { pv[k] = A.p[d]; sv[k] = A.sol[d]; rv[k] = A.r[d]; mv[k] = A.minv[d]; }
+        }
+    }
+    pdl_wait();
+    pdl_trigger();
+    if (A.S->stop) return;
     double pAp;
     unsigned long long seq = 0ULL, hseq = 0ULL;
     ArenaHdr* mine = nullptr;
@@ -223,7 +237,10 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_cg_update(CgVecArgs A) {
 #pragma unroll
     for (int k = 0; k < VEC_ILP; ++k) {
         const int d = dfirst + k * T;
-        if (d < A.n) { pv[k] = A.p[d]; sv[k] = A.sol[d]; rv[k] = A.r[d]; av[k] = A.Ap[d]; mv[k] = A.minv[d]; }
+        if (d < A.n) {
+            if (FUSED) { pv[k] = A.p[d]; sv[k] = A.sol[d]; rv[k] = A.r[d]; mv[k] = A.minv[d]; }
+            av[k] = A.Ap[d];
+        }
     }
     if (FUSED) {
         if (blockIdx.x != 0)
@@ -287,10 +304,19 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_cg_update(CgVecArgs A) {
 __global__ void __launch_bounds__(VEC_THREADS) k_cg_pupdate(CgVecArgs A) {
     __shared__ double red[VEC_THREADS / 32 + 1];
     CgScalars* S = A.S;
-    if (S->stop) return;
     const int T = gridDim.x * VEC_THREADS;
     const int dfirst = blockIdx.x * VEC_THREADS + threadIdx.x;
     double pv[VEC_ILP], rv[VEC_ILP], mv[VEC_ILP];
+    // p (this kernel's own output of the previous iteration) and the preconditioner are not touched by the predecessor:
+    // with a programmatic launch these loads overlap its tail; r and the partial sums are read after pdl_wait()
+#pragma unroll
+    for (int k = 0; k < VEC_ILP; ++k) {
+        const int d = dfirst + k * T;
+        if (d < A.n) { pv[k] = A.p[d]; mv[k] = A.minv[d]; }
+    }
+    pdl_wait();
+    pdl_trigger();
+    if (S->stop) return;
     double rr, rz;
     unsigned long long seq = 0ULL;
     if (A.F.active) {
@@ -304,7 +330,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_pupdate(CgVecArgs A) {
 #pragma unroll
     for (int k = 0; k < VEC_ILP; ++k) {
         const int d = dfirst + k * T;
-        if (d < A.n) { pv[k] = A.p[d]; rv[k] = A.r[d]; mv[k] = A.minv[d]; }
+        if (d < A.n) rv[k] = A.r[d];
     }
     if (A.F.active) {
         if (blockIdx.x != 0)

@@ -57,6 +57,13 @@ struct Mesh {
     const int* bcol;                   // block columns, ascending within a row
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may start while
+// its predecessor in the stream is still draining; pdl_wait() blocks until the predecessor grid has completed and its
+// writes are visible (a no-op for ordinary launches), pdl_trigger() lets the successor start launching.  Everything a
+// kernel reads before pdl_wait() must not be written by its immediate predecessor.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

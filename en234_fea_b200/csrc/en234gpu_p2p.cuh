@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(VEC_THREADS) k_p2p_allreduce(PeerSet P, const 
                                                                int check_stop) {
     __shared__ double red[VEC_THREADS / 32 + 1];
     __shared__ unsigned long long s_seq;
+    pdl_wait();
+    pdl_trigger();
     if (check_stop && S->stop) return;
     ArenaHdr* mine = P.arena[P.me];
     const double a = reduce_partials<VEC_THREADS>(partA, nA, red);

@@ -44,7 +44,8 @@ struct Model {
     int n_nodes = 0, n_elements = 0;
     int n_coords = 3, n_dof = 3;
     std::vector<double> coords;            // 3 per node
-    std::vector<int> connectivity;         // 8 per element, 1-based
+    int nodes_per_element = 8;             // 8 (hex8), or 4 / 10 / 20: meshes of tet4 / tet10 / hex20 elements of type 1001
+    std::vector<int> connectivity;         // nodes_per_element per element, 1-based
     std::vector<int> element_flag, element_prop_index, element_n_props, element_n_states;
     std::vector<double> element_properties;
     std::vector<ElementGroup> groups;

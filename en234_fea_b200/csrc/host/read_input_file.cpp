@@ -155,7 +155,14 @@ bool parse_elements_user(Reader& r) {
             else if (kw(L.tok[3], "VU")) { m.abaqusformat = true; lmntyp = to_int(L.tok[3].substr(2)) + 99999; }   // :551-555
             else if (kw(L.tok[3], "U")) { m.abaqusformat = true; lmntyp = to_int(L.tok[3].substr(1)) + 99999; }
             else return r.fail("element identifier must be an integer or Un", &L);
-            if (nnod != 8) return r.fail("only 8-node brick elements are supported on the GPU hot path", &L);
+            // el_linelast_3Dbasic.f90:82-85 integrates 4-, 10-, 8- and 20-node elements; a mesh has one shape throughout
+            if (nnod != 8 && nnod != 4 && nnod != 10 && nnod != 20)
+                return r.fail("3-D elements have 4, 10, 8 or 20 nodes", &L);
+            if (nnod != 8 && lmntyp != 1001)
+                return r.fail("4-, 10- and 20-node elements are implemented for element type 1001 only", &L);
+            if (m.n_elements > 0 && nnod != m.nodes_per_element)
+                return r.fail("all elements of a mesh must have the same number of nodes on the device path", &L);
+            m.nodes_per_element = nnod;
         } else if (kw(L.tok[0], "DENS")) {                             // :565-574
             if (L.n() < 2 || L.typ[1] > 1) return r.fail("expecting density value following DENSITY key", &L);
             density = to_real(L.tok[1]);
@@ -186,7 +193,7 @@ bool parse_elements_user(Reader& r) {
                 if (!r.next(L)) return r.fail("CONNECTIVITY not terminated");
                 if (kw(L.tok[0], "ENDCONN")) break;
                 if (L.typ[0] == 2) return r.fail("CONNECTIVITY key must be terminated by an END CONNECTIVITY", &L);
-                if (L.n() < nnod || L.n() > nnod + 1) return r.fail("expecting element number (optional) and 8 nodes", &L);
+                if (L.n() < nnod || L.n() > nnod + 1) return r.fail("expecting element number (optional) and the element's nodes", &L);
                 for (int k = L.n() - nnod; k < L.n(); ++k) m.connectivity.push_back(to_int(L.tok[k]));
                 m.element_flag.push_back(lmntyp);
                 m.element_prop_index.push_back(prop_index);

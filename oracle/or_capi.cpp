@@ -37,7 +37,7 @@ int or_model_set_int(void* h, const char* name, const int* p, long n) {
     VI(pdof_flag) VI(pdof_dof) VI(pdof_node) VI(pdof_nodeset) VI(pdof_history) VI(pdof_rate) VI(pdof_subparam) VI(subparam_ptr)
     VI(pforce_flag) VI(pforce_dof) VI(pforce_node) VI(pforce_nodeset) VI(pforce_history)
     VI(node_order) VI(dload_flag) VI(dload_elset) VI(dload_face) VI(dload_history) VI(dload_val_ptr)
-    SI(n_nodes) SI(n_elements) SI(max_no_steps) SI(solvertype) SI(nonlinear) SI(max_newton_iterations)
+    SI(n_nodes) SI(n_elements) SI(nodes_per_element) SI(max_no_steps) SI(solvertype) SI(nonlinear) SI(max_newton_iterations)
     SI(unsymmetric) SI(abaqusformat) SI(max_cg_iterations) SI(gps_renumber) SI(cg_apply_nodal_forces)
     SI(cg_check_linear) SI(explicitdynamicstep) SI(no_dynamic_steps)
 #undef VI
@@ -63,7 +63,12 @@ int or_model_set_double(void* h, const char* name, const double* p, long n) {
 int or_model_finalize(void* h) {
     Model& m = *(Model*)h;
     const int E = m.n_elements, N = m.n_nodes;
-    if ((long)m.coords.size() != 3L * N || (long)m.connectivity.size() != 8L * E) return 1;
+    if ((long)m.coords.size() != 3L * N || (long)m.connectivity.size() != (long)m.nodes_per_element * E) return 1;
+    if (m.nodes_per_element != 8 && m.nodes_per_element != 4 && m.nodes_per_element != 10 && m.nodes_per_element != 20) return 4;
+    if (m.nodes_per_element != 8) {                       // other element shapes: element 1001 only, no face loads
+        for (int f : m.element_flag) if (f != ID_LINELAST) return 5;
+        if (!m.dload_flag.empty()) return 6;
+    }
     if ((int)m.element_flag.size() != E) return 2;
     if (m.element_prop_index.empty()) m.element_prop_index.assign(E, 0);
     if (m.element_n_props.empty()) m.element_n_props.assign(E, (int)m.element_properties.size());
@@ -94,6 +99,25 @@ int or_element(int flag, const double* coords24, const double* dof_increment24, 
     } else if (flag == ID_NEOHOOKE || flag == FLAG_UEL_BASE + 2) el_neohooke_3d(coords24, U, props, K, R, svars48, &fail);
     else return -1;
     return fail;
+}
+
+// ---- the other 3-D element shapes of element 1001 (tet4, tet10, hex20): shape-function table, integration rule, element
+int or_shapefunctions_3d(int n_nodes, const double* xi, double* f, double* df /*n_nodes x 3*/) {
+    double d[20][3];
+    if (n_nodes != 4 && n_nodes != 10 && n_nodes != 8 && n_nodes != 20) return 1;
+    shapefunctions_3d(n_nodes, xi, f, d);
+    for (int a = 0; a < n_nodes; ++a) for (int j = 0; j < 3; ++j) df[3 * a + j] = d[a][j];
+    return 0;
+}
+int or_integration_points_3d(int n_nodes, double* xi /*27 x 3*/, double* w /*27*/) {
+    double x[27][3];
+    const int n = integration_points_3d(n_nodes, x, w);
+    for (int k = 0; k < n; ++k) for (int j = 0; j < 3; ++j) xi[3 * k + j] = x[k][j];
+    return n;
+}
+int or_element_general(int n_nodes, const double* coords, const double* dof_increment, const double* dof_total,
+                       const double* props, double* K, double* R) {
+    return el_linelast_3d_general(n_nodes, coords, dof_increment, dof_total, props, K, R);
 }
 
 // CHECK STIFFNESS (src/checkstiffness.f90:481-532): forward difference of the residual, h = 1e-7,

@@ -45,7 +45,9 @@ int assemble_conjugate_gradient_stiffness(const Model& m, CooUpper& c, const dou
     std::fill(c.aupp.begin(), c.aupp.end(), 0.0);
     std::fill(c.rhs.begin(), c.rhs.end(), 0.0);
     std::fill(c.diag.begin(), c.diag.end(), 0.0);
-    double K[576], R[24];
+    const int npe = m.nodes_per_element, nd = 3 * npe;
+    std::vector<double> Kbuf((size_t)nd * nd), Rbuf(nd);
+    double *K = Kbuf.data(), *R = Rbuf.data();
     const double thresh = 0.0;
     long long sv_off = 0;
     for (int lmn = 0; lmn < m.n_elements; ++lmn) {
@@ -53,19 +55,19 @@ int assemble_conjugate_gradient_stiffness(const Model& m, CooUpper& c, const dou
         if (svars && m.element_n_states[lmn] > 0) sv = svars->data() + sv_off;
         sv_off += m.element_n_states[lmn];
         if (element_static(m, lmn, dof_total, dof_increment, time, dtime, K, R, sv)) return 1;
-        for (int i1 = 0; i1 < 8; ++i1) {                        // :233-258
-            int node1 = m.connectivity[8 * lmn + i1] - 1;
+        for (int i1 = 0; i1 < npe; ++i1) {                      // :233-258
+            int node1 = m.connectivity[(size_t)npe * lmn + i1] - 1;
             for (int j1 = 0; j1 < 3; ++j1) {
                 int irow = 3 * node1 + j1, nsr = 3 * i1 + j1;
                 c.rhs[irow] += R[nsr];
-                for (int i2 = 0; i2 < 8; ++i2) {
-                    int node2 = m.connectivity[8 * lmn + i2] - 1;
+                for (int i2 = 0; i2 < npe; ++i2) {
+                    int node2 = m.connectivity[(size_t)npe * lmn + i2] - 1;
                     for (int j2 = 0; j2 < 3; ++j2) {
                         int icol = 3 * node2 + j2, nsc = 3 * i2 + j2;
-                        if (icol == irow) c.diag[irow] += K[nsr + 24 * nsc];
+                        if (icol == irow) c.diag[irow] += K[nsr + nd * nsc];
                         else if (icol > irow) {
-                            if (std::fabs(K[nsr + 24 * nsc]) + std::fabs(K[nsc + 24 * nsr]) > thresh)
-                                c.aupp[getindex(c, irow, icol)] += K[nsr + 24 * nsc];
+                            if (std::fabs(K[nsr + nd * nsc]) + std::fabs(K[nsc + nd * nsr]) > thresh)
+                                c.aupp[getindex(c, irow, icol)] += K[nsr + nd * nsc];
                         }
                     }
                 }

@@ -25,14 +25,15 @@ void compute_profile(const Model& m, const std::vector<int>& node_order, Skyline
         for (int j = 0; j < 3; ++j) s.ieqs[3 * n + j] = e++;
     }
     std::vector<long long> h(neq, 0);
+    const int npe = m.nodes_per_element;
     for (int lmn = 0; lmn < m.n_elements; ++lmn) {
         int mineq = neq - 1;
-        for (int i = 0; i < 8; ++i) {
-            int n = m.connectivity[8 * lmn + i] - 1;
+        for (int i = 0; i < npe; ++i) {
+            int n = m.connectivity[(size_t)npe * lmn + i] - 1;
             for (int j = 0; j < 3; ++j) mineq = std::min(mineq, s.ieqs[3 * n + j]);
         }
-        for (int i = 0; i < 8; ++i) {
-            int n = m.connectivity[8 * lmn + i] - 1;
+        for (int i = 0; i < npe; ++i) {
+            int n = m.connectivity[(size_t)npe * lmn + i] - 1;
             for (int j = 0; j < 3; ++j) {
                 int q = s.ieqs[3 * n + j];
                 h[q] = std::max<long long>(h[q], q - mineq);
@@ -72,7 +73,9 @@ int assemble_direct_stiffness(const Model& m, Skyline& s, const double* dof_tota
     std::fill(s.alow.begin(), s.alow.end(), 0.0);
     std::fill(s.rhs.begin(), s.rhs.end(), 0.0);
     std::fill(s.diag.begin(), s.diag.end(), 0.0);
-    double K[576], R[24];
+    const int npe = m.nodes_per_element, nd = 3 * npe;
+    std::vector<double> Kbuf((size_t)nd * nd), Rbuf(nd);
+    double *K = Kbuf.data(), *R = Rbuf.data();
     long long sv_off = 0;
     for (int lmn = 0; lmn < m.n_elements; ++lmn) {
         double* sv = nullptr;
@@ -80,20 +83,20 @@ int assemble_direct_stiffness(const Model& m, Skyline& s, const double* dof_tota
         sv_off += m.element_n_states[lmn];
         if (element_static(m, lmn, dof_total, dof_increment, time, dtime, K, R, sv)) return 1;
         // scatter :264-287
-        for (int i1 = 0; i1 < 8; ++i1) {
-            int node1 = m.connectivity[8 * lmn + i1] - 1;
+        for (int i1 = 0; i1 < npe; ++i1) {
+            int node1 = m.connectivity[(size_t)npe * lmn + i1] - 1;
             for (int j1 = 0; j1 < 3; ++j1) {
                 int irow = s.ieqs[3 * node1 + j1], nsr = 3 * i1 + j1;
                 s.rhs[irow] += R[nsr];
-                for (int i2 = 0; i2 < 8; ++i2) {
-                    int node2 = m.connectivity[8 * lmn + i2] - 1;
+                for (int i2 = 0; i2 < npe; ++i2) {
+                    int node2 = m.connectivity[(size_t)npe * lmn + i2] - 1;
                     for (int j2 = 0; j2 < 3; ++j2) {
                         int icol = s.ieqs[3 * node2 + j2], nsc = 3 * i2 + j2;
-                        if (icol == irow) s.diag[irow] += K[nsr + 24 * nsc];
+                        if (icol == irow) s.diag[irow] += K[nsr + nd * nsc];
                         else if (icol > irow) {
                             const size_t nn = (size_t)(s.jp[icol] - (icol - irow));
-                            s.aupp[nn] += K[nsr + 24 * nsc];
-                            if (s.unsym) s.alow[nn] += K[nsc + 24 * nsr];          // :282
+                            s.aupp[nn] += K[nsr + nd * nsc];
+                            if (s.unsym) s.alow[nn] += K[nsc + nd * nsr];          // :282
                         }
                     }
                 }

@@ -423,8 +423,188 @@ void el_neohooke_3d(const double* coords24, const double* U24, const double* pro
 
 // Element dispatch + gather, mirroring solver_direct.f90:104-258 (gather :104-121, UEL :174-247,
 // native :250-256).  UEL distributed loads are generated as in generate_abaqus_dloads :798-912.
+// ---- integration rules and shape functions of the other 3-D element shapes, AS THE REFERENCE WRITES THEM -----------------
+// initialize_integration_points (Element_Utilities.f90:586-689): literals without a D exponent are single precision
+// there (0.58541020, 0.13819660, 0.7745966692, ...) and are reproduced as (double)(float) values.
+int integration_points_3d(int n_nodes, double xi[][3], double* w) {
+    if (n_nodes == 4) {                                   // 1 point (el_linelast_3Dbasic.f90:82)
+        xi[0][0] = xi[0][1] = xi[0][2] = 0.25;
+        w[0] = 1.0 / 6.0;
+        return 1;
+    }
+    if (n_nodes == 10) {                                  // 4 points (:83)
+        const double a = (double)0.58541020f, b = (double)0.13819660f;
+        const double p[4][3] = {{a, b, b}, {b, a, b}, {b, b, a}, {b, b, b}};
+        for (int k = 0; k < 4; ++k) { for (int j = 0; j < 3; ++j) xi[k][j] = p[k][j]; w[k] = 1.0 / 24.0; }
+        return 4;
+    }
+    if (n_nodes == 8) {
+        const double x1[2] = {(double)-0.5773502692f, (double)0.5773502692f};
+        for (int k = 0; k < 2; ++k) for (int j = 0; j < 2; ++j) for (int i = 0; i < 2; ++i) {
+            const int n = 4 * k + 2 * j + i;
+            xi[n][0] = x1[i]; xi[n][1] = x1[j]; xi[n][2] = x1[k]; w[n] = 1.0;
+        }
+        return 8;
+    }
+    if (n_nodes == 20) {                                  // 27 points (:85)
+        const double x1[3] = {(double)-0.7745966692f, 0.0, (double)0.7745966692f};
+        const double w1[3] = {0.5555555555, 0.888888888, 0.55555555555};
+        for (int k = 0; k < 3; ++k) for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) {
+            const int n = 9 * k + 3 * j + i;
+            xi[n][0] = x1[i]; xi[n][1] = x1[j]; xi[n][2] = x1[k]; w[n] = w1[i] * w1[j] * w1[k];
+        }
+        return 27;
+    }
+    return 0;
+}
+
+// calculate_shapefunctions, 3-D branch (Element_Utilities.f90:863-1025), statement by statement.  The reference's table
+// has three entries that are not the derivatives of its own shape functions — tet10 df(10,1) = -4 xi3 xi4 (:902) and
+// hex20 df(11,1), df(11,2) (copies of node 9's, :991-992): they are reproduced, because "the same results as the
+// reference on the same input" is the bar; tests/test_oracle_cpu.py pins this table against the Fortran text itself.
+void shapefunctions_3d(int n_nodes, const double* xi, double* f, double df[][3]) {
+    for (int a = 0; a < n_nodes; ++a) { f[a] = 0.0; df[a][0] = df[a][1] = df[a][2] = 0.0; }
+    const double x = xi[0], y = xi[1], z = xi[2];
+    if (n_nodes == 4) {
+        f[0] = x; f[1] = y; f[2] = z; f[3] = 1. - x - y - z;
+        df[0][0] = 1.; df[1][1] = 1.; df[2][2] = 1.;
+        df[3][0] = -1.; df[3][1] = -1.; df[3][2] = -1.;
+    } else if (n_nodes == 10) {
+        const double x4 = 1. - x - y - z;
+        f[0] = (2. * x - 1.) * x; f[1] = (2. * y - 1.) * y; f[2] = (2. * z - 1.) * z; f[3] = (2. * x4 - 1.) * x4;
+        f[4] = 4. * x * y; f[5] = 4. * y * z; f[6] = 4. * z * x; f[7] = 4. * x * x4; f[8] = 4. * y * x4; f[9] = 4. * z * x4;
+        df[0][0] = (4. * x - 1.); df[1][1] = (4. * y - 1.); df[2][2] = (4. * z - 1.);
+        df[3][0] = -(4. * x4 - 1.); df[3][1] = -(4. * x4 - 1.); df[3][2] = -(4. * x4 - 1.);
+        df[4][0] = 4. * y; df[4][1] = 4. * x;
+        df[5][1] = 4. * z; df[5][2] = 4. * y;
+        df[6][0] = 4. * z; df[6][2] = 4. * x;
+        df[7][0] = 4. * (x4 - x); df[7][1] = -4. * x; df[7][2] = -4. * x;
+        df[8][0] = -4. * y; df[8][1] = 4. * (x4 - y); df[8][2] = -4. * y;
+        df[9][0] = -4. * z * x4;                           // sic (:902)
+        df[9][1] = -4. * z; df[9][2] = 4. * (x4 - z);
+    } else if (n_nodes == 8) {
+        const int sx[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, sy[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, sz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+        for (int a = 0; a < 8; ++a) {
+            const double fx = 1. + sx[a] * x, fy = 1. + sy[a] * y, fz = 1. + sz[a] * z;
+            f[a] = fx * fy * fz / 8.;
+            df[a][0] = sx[a] * (fy * fz / 8.); df[a][1] = sy[a] * (fx * fz / 8.); df[a][2] = sz[a] * (fx * fy / 8.);
+        }
+    } else if (n_nodes == 20) {
+        const int sx[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, sy[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, sz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+        for (int a = 0; a < 8; ++a) {                      // corner nodes (:926-933, :946-973)
+            const double fx = 1. + sx[a] * x, fy = 1. + sy[a] * y, fz = 1. + sz[a] * z;
+            const double g = sx[a] * x + sy[a] * y + sz[a] * z - 2.;
+            f[a] = fx * fy * fz * g / 8.;
+            df[a][0] = (sx[a] * (fy * fz * g) + sx[a] * (fx * fy * fz)) / 8.;
+            df[a][1] = (sy[a] * (fx * fz * g) + sy[a] * (fx * fy * fz)) / 8.;
+            df[a][2] = (sz[a] * (fx * fy * g) + sz[a] * (fx * fy * fz)) / 8.;
+        }
+        const double xm = 1. - x, xp = 1. + x, ym = 1. - y, yp = 1. + y, zm = 1. - z, zp = 1. + z;
+        const double x2 = 1. - x * x, y2 = 1. - y * y, z2 = 1. - z * z;
+        f[8] = x2 * ym * zm / 4.;  f[9] = xp * y2 * zm / 4.;  f[10] = x2 * yp * zm / 4.; f[11] = xm * y2 * zm / 4.;
+        f[12] = x2 * ym * zp / 4.; f[13] = xp * y2 * zp / 4.; f[14] = x2 * yp * zp / 4.; f[15] = xm * y2 * zp / 4.;
+        f[16] = xm * ym * z2 / 4.; f[17] = xp * ym * z2 / 4.; f[18] = xp * yp * z2 / 4.; f[19] = xm * yp * z2 / 4.;
+        df[8][0] = -2. * x * ym * zm / 4.;  df[8][1] = -x2 * zm / 4.;            df[8][2] = -x2 * ym / 4.;
+        df[9][0] = y2 * zm / 4.;            df[9][1] = -2. * y * xp * zm / 4.;   df[9][2] = -y2 * xp / 4.;
+        df[10][0] = -2. * x * ym * zm / 4.; df[10][1] = -x2 * zm / 4.;           df[10][2] = -x2 * ym / 4.;   // sic (:991-993)
+        df[11][0] = -y2 * zm / 4.;          df[11][1] = -2. * y * xm * zm / 4.;  df[11][2] = -y2 * xm / 4.;
+        df[12][0] = -2. * x * ym * zp / 4.; df[12][1] = -x2 * zp / 4.;           df[12][2] = x2 * ym / 4.;
+        df[13][0] = y2 * zp / 4.;           df[13][1] = -2. * y * xp * zp / 4.;  df[13][2] = y2 * xp / 4.;
+        df[14][0] = 2. * x * yp * zp / 4.;  df[14][1] = x2 * zp / 4.;            df[14][2] = x2 * yp / 4.;    // sic (:1003): + 2 xi1
+        df[15][0] = -y2 * zp / 4.;          df[15][1] = -2. * y * xm * zp / 4.;  df[15][2] = y2 * xm / 4.;
+        df[16][0] = -ym * z2 / 4.;          df[16][1] = -xm * z2 / 4.;           df[16][2] = -z * xm * ym / 2.;
+        df[17][0] = ym * z2 / 4.;           df[17][1] = -xp * z2 / 4.;           df[17][2] = -z * xp * ym / 2.;
+        df[18][0] = yp * z2 / 4.;           df[18][1] = xp * z2 / 4.;            df[18][2] = -z * xp * yp / 2.;
+        df[19][0] = -yp * z2 / 4.;          df[19][1] = xm * z2 / 4.;            df[19][2] = -z * xm * yp / 2.;
+    }
+}
+
+// el_linelast_3dbasic for any of the four shapes (el_linelast_3Dbasic.f90:79-133): B^T D B and B^T sigma summed over the
+// integration points in the reference's order.
+int el_linelast_3d_general(int nn, const double* coords, const double* du, const double* utot, const double* props,
+                           double* K, double* R) {
+    const int nd = 3 * nn;
+    double xi[27][3], w[27];
+    const int npts = integration_points_3d(nn, xi, w);
+    if (npts == 0) return 1;
+    for (int q = 0; q < nd * nd; ++q) K[q] = 0.0;
+    for (int q = 0; q < nd; ++q) R[q] = 0.0;
+    const double E = props[0], xnu = props[1];
+    const double d44 = 0.5 * E / (1 + xnu), d11 = (1. - xnu) * E / ((1 + xnu) * (1 - 2. * xnu)), d12 = xnu * E / ((1 + xnu) * (1 - 2. * xnu));
+    double D[6][6] = {{0}};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) D[i][j] = d12;
+    D[0][0] = D[1][1] = D[2][2] = d11;
+    D[3][3] = D[4][4] = D[5][5] = d44;
+    int fail = 0;
+    for (int k = 0; k < npts; ++k) {
+        double f[20], df[20][3], dxdxi[3][3], dxidx[3][3], dNdx[20][3], B[6][60];
+        shapefunctions_3d(nn, xi[k], f, df);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double t = 0.0;
+                for (int a = 0; a < nn; ++a) t += coords[3 * a + i] * df[a][j];
+                dxdxi[i][j] = t;
+            }
+        const double (*A)[3] = dxdxi;                                   // invert_small, Element_Utilities.f90:99-123
+        const double det = A[0][0] * A[1][1] * A[2][2] - A[0][0] * A[1][2] * A[2][1] - A[0][1] * A[1][0] * A[2][2] +
+                           A[0][1] * A[1][2] * A[2][0] + A[0][2] * A[1][0] * A[2][1] - A[0][2] * A[1][1] * A[2][0];
+        if (det == 0.0) fail = 1;
+        const double r = 1.0 / det;
+        dxidx[0][0] = (A[1][1] * A[2][2] - A[1][2] * A[2][1]) * r;  dxidx[0][1] = -(A[0][1] * A[2][2] - A[0][2] * A[2][1]) * r;
+        dxidx[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * r;  dxidx[1][0] = -(A[1][0] * A[2][2] - A[1][2] * A[2][0]) * r;
+        dxidx[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * r;  dxidx[1][2] = -(A[0][0] * A[1][2] - A[0][2] * A[1][0]) * r;
+        dxidx[2][0] = (A[1][0] * A[2][1] - A[1][1] * A[2][0]) * r;  dxidx[2][1] = -(A[0][0] * A[2][1] - A[0][1] * A[2][0]) * r;
+        dxidx[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * r;
+        for (int a = 0; a < nn; ++a)
+            for (int j = 0; j < 3; ++j) dNdx[a][j] = df[a][0] * dxidx[0][j] + df[a][1] * dxidx[1][j] + df[a][2] * dxidx[2][j];
+        for (int r6 = 0; r6 < 6; ++r6) for (int q = 0; q < nd; ++q) B[r6][q] = 0.0;
+        for (int a = 0; a < nn; ++a) {
+            B[0][3 * a] = dNdx[a][0]; B[1][3 * a + 1] = dNdx[a][1]; B[2][3 * a + 2] = dNdx[a][2];
+            B[3][3 * a] = dNdx[a][1]; B[3][3 * a + 1] = dNdx[a][0];
+            B[4][3 * a] = dNdx[a][2]; B[4][3 * a + 2] = dNdx[a][0];
+            B[5][3 * a + 1] = dNdx[a][2]; B[5][3 * a + 2] = dNdx[a][1];
+        }
+        double strain[6], stress[6], DB[6][60];
+        for (int r6 = 0; r6 < 6; ++r6) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int q = 0; q < nd; ++q) { s0 += B[r6][q] * utot[q]; s1 += B[r6][q] * du[q]; }
+            strain[r6] = s0 + s1;
+        }
+        for (int r6 = 0; r6 < 6; ++r6) { double t = 0.0; for (int c = 0; c < 6; ++c) t += D[r6][c] * strain[c]; stress[r6] = t; }
+        const double wd = w[k] * det;
+        for (int q = 0; q < nd; ++q) {
+            double t = 0.0;
+            for (int r6 = 0; r6 < 6; ++r6) t += B[r6][q] * stress[r6];
+            R[q] = R[q] - t * wd;
+        }
+        for (int r6 = 0; r6 < 6; ++r6)
+            for (int q = 0; q < nd; ++q) { double t = 0.0; for (int c = 0; c < 6; ++c) t += D[r6][c] * B[c][q]; DB[r6][q] = t; }
+        for (int i = 0; i < nd; ++i)
+            for (int j = 0; j < nd; ++j) {
+                double t = 0.0;
+                for (int r6 = 0; r6 < 6; ++r6) t += B[r6][i] * DB[r6][j];
+                K[i + nd * j] += t * wd;
+            }
+    }
+    return fail;
+}
+
 int element_static(const Model& m, int lmn, const double* dof_total, const double* dof_increment,
                    double time, double dtime, double* K, double* R, double* svars) {
+    if (m.nodes_per_element != 8) {                      // tet4 / tet10 / hex20 meshes: element 1001 only
+        const int npe = m.nodes_per_element;
+        double gx[60], gdu[60], gut[60];
+        for (int j = 0; j < npe; ++j) {
+            int n = m.connectivity[(size_t)npe * lmn + j] - 1;
+            for (int k = 0; k < 3; ++k) {
+                gx[3 * j + k] = m.coords[3 * n + k];
+                gdu[3 * j + k] = dof_increment[3 * n + k];
+                gut[3 * j + k] = dof_total[3 * n + k];
+            }
+        }
+        if (m.element_flag[lmn] != ID_LINELAST) return 1;
+        return el_linelast_3d_general(npe, gx, gdu, gut, m.element_properties.data() + m.element_prop_index[lmn], K, R);
+    }
     double xc[24], du[24], ut[24];
     for (int j = 0; j < 8; ++j) {
         int n = m.connectivity[8 * lmn + j] - 1;

@@ -25,8 +25,10 @@ namespace oracle {
 // modules/Boundaryconditions.f90:4-76, restricted to 3-coordinate / 3-DOF nodes and 8-node elements.
 struct Model {
     int n_nodes = 0, n_elements = 0;
+    int nodes_per_element = 8;              // 8 (hex8: every element type of the path), or 4 / 10 / 20 for meshes of
+                                            // tet4 / tet10 / hex20 elements of type 1001 (el_linelast_3Dbasic.f90:82-85)
     std::vector<double> coords;             // 3*n_nodes, xyz per node            (Mesh.f90:84)
-    std::vector<int> connectivity;          // 8*n_elements, 1-based node numbers (Mesh.f90:69)
+    std::vector<int> connectivity;          // nodes_per_element*n_elements, 1-based node numbers (Mesh.f90:69)
     std::vector<int> element_flag;          // element_list%flag                  (Mesh.f90:16-29)
     std::vector<int> element_prop_index;    // 0-based offset into element_properties
     std::vector<int> element_n_props;
@@ -97,6 +99,12 @@ struct StepLog {
 // K is column-major 24x24 (K[row + 24*col]), matching element_stiffness(ROW,COL).
 void el_linelast_3dbasic(const double* coords24, const double* du24, const double* utot24,
                          const double* props, double* K, double* R);
+// the same routine for n_nodes = 4, 10, 8, 20 with the reference's integration rules and shape functions
+// (Element_Utilities.f90:586-689, :863-1025) as written there; K column-major (3 n_nodes)^2.  Returns 1 when det == 0.
+int el_linelast_3d_general(int n_nodes, const double* coords, const double* du, const double* utot, const double* props,
+                           double* K, double* R);
+int integration_points_3d(int n_nodes, double xi[][3], double* w);                       // number of points
+void shapefunctions_3d(int n_nodes, const double* xi, double* f, double dfdxi[][3]);
 void uel_linelastic_3d(const double* coords24, const double* U24, const double* props, int nsvars,
                        int ndload, const int* jdltyp, const double* adlmag, double* K, double* R,
                        double* svars, double* energy8, double* pnewdt);

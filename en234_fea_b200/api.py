@@ -41,7 +41,7 @@ _gpu = None
 _host = None
 
 GPU_SYMBOLS = [
-    "en234gpu_last_error", "en234gpu_device_count", "en234gpu_create", "en234gpu_destroy", "en234gpu_set_stream",
+    "en234gpu_last_error", "en234gpu_device_count", "en234gpu_create", "en234gpu_create_nodes", "en234gpu_destroy", "en234gpu_set_stream",
     "en234gpu_assemble", "en234gpu_apply_boundaryconditions", "en234gpu_solve", "en234gpu_set_operator_mode",
     "en234gpu_upload_state", "en234gpu_assemble_dev", "en234gpu_apply_boundaryconditions_dev", "en234gpu_solve_dev",
     "en234gpu_download_state", "en234gpu_zero_increment_dev", "en234gpu_element_batch", "en234gpu_element_single", "en234gpu_get_svars",
@@ -118,7 +118,7 @@ INT_ARRAYS = ["connectivity", "element_flag", "element_prop_index", "element_n_p
               "pdof_flag", "pdof_dof", "pdof_node", "pdof_nodeset", "pdof_history", "pdof_rate", "pdof_subparam", "subparam_ptr",
               "pforce_flag", "pforce_dof", "pforce_node", "pforce_nodeset", "pforce_history",
               "dload_flag", "dload_elset", "dload_face", "dload_history", "dload_val_ptr"]
-INT_SCALARS = ["n_nodes", "n_elements", "max_no_steps", "solvertype", "nonlinear", "max_newton_iterations",
+INT_SCALARS = ["n_nodes", "n_elements", "nodes_per_element", "max_no_steps", "solvertype", "nonlinear", "max_newton_iterations",
                "unsymmetric", "abaqusformat", "max_cg_iterations", "checkstiffness_flag", "explicitdynamicstep", "no_dynamic_steps"]
 DBL_ARRAYS = ["coords", "element_properties", "material_properties", "history_time", "history_value", "pdof_value", "pforce_value",
               "dload_values", "subparam_values", "element_density"]

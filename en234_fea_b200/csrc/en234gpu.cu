@@ -20,6 +20,7 @@
 #include "en234gpu_mf.cuh"
 #include "en234gpu_project.cuh"
 #include "en234gpu_dyn.cuh"
+#include "en234gpu_generic.cuh"
 #include "en234gpu_comm.h"
 
 using namespace en234k;
@@ -58,6 +59,9 @@ struct en234gpu_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int N = 0, E = 0, ndof = 0, n_sm = 148;
+    int npe = 8;                 // nodes per element: 8 = the hex8 path; 4 / 10 / 20 = general path (en234gpu_generic.cuh)
+    DevBuf<int> gconn, gadj;     // general path: conn[e * npe + a], adjacency entries e * 32 + a
+    DevBuf<uint8_t> gslot;
     long long nnzb = 0;
     // mesh
     DevBuf<double> x, y, z;
@@ -401,6 +405,149 @@ int en234gpu_create(en234gpu_handle* out, int device, int n_nodes, int n_element
     return 0;
 }
 
+static GenMesh gen_mesh_of(en234gpu_ctx* c) {
+    GenMesh M;
+    M.N = c->N; M.E = c->E; M.npe = c->npe;
+    M.x = c->x.p; M.y = c->y.p; M.z = c->z.p;
+    M.conn = c->gconn.p; M.mat = c->mat.p; M.mats = c->mats.p;
+    M.adj_ptr = c->adj_ptr.p; M.adj = c->gadj.p; M.slot = c->gslot.p;
+    M.browptr = c->browptr.p; M.bcol = c->bcol.p;
+    return M;
+}
+
+// Meshes of 4-, 10- or 20-node elements of type 1001 (8 nodes: en234gpu_create and the hex8 kernels).
+int en234gpu_create_nodes(en234gpu_handle* out, int device, int nodes_per_element, int n_nodes, int n_elements,
+                          const double* coords, const int* connectivity, const int* element_flag,
+                          const int* element_prop_index, const double* element_properties, int n_element_properties) {
+    const int npe = nodes_per_element;
+    if (npe == 8)
+        return en234gpu_create(out, device, n_nodes, n_elements, coords, connectivity, element_flag, element_prop_index,
+                               element_properties, n_element_properties);
+    *out = nullptr;
+    if (npe != 4 && npe != 10 && npe != 20) return set_err("en234gpu_create_nodes: 3-D elements have 4, 10, 8 or 20 nodes");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err("en234gpu_create_nodes: no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return set_err("en234gpu_create_nodes: bad device index");
+    if (n_nodes <= 0 || n_elements <= 0) return set_err("en234gpu_create_nodes: empty mesh");
+    if ((long long)n_nodes * 3 >= 2147483647LL || (long long)n_elements * 32 >= 2147483647LL)
+        return set_err("en234gpu_create_nodes: mesh too large for 32-bit indices");
+    CK(cudaSetDevice(device));
+    auto* c = new en234gpu_ctx();
+    c->device = device;
+    c->npe = npe;
+    c->N = n_nodes; c->E = n_elements; c->ndof = 3 * n_nodes;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->n_sm = prop.multiProcessorCount;
+    const int N = n_nodes, E = n_elements;
+    std::map<int, int> matmap;
+    std::vector<Material> mats;
+    std::vector<int> mat(E);
+    for (int e = 0; e < E; ++e) {
+        if (element_flag[e] != EN234_ID_LINELAST) {
+            delete c;
+            return set_err("4-, 10- and 20-node elements are implemented for element type 1001 only (element " + std::to_string(e + 1) + ")");
+        }
+        const int pi = element_prop_index ? element_prop_index[e] : 0;
+        auto it = matmap.find(pi);
+        if (it == matmap.end()) {
+            if (pi + 2 > n_element_properties) { delete c; return set_err("element needs 2 properties (E, nu)"); }
+            Material m{};
+            const double Em = element_properties[pi], xnu = element_properties[pi + 1];
+            m.kind = 0;                                               // el_linelast_3Dbasic.f90:93-98
+            m.d44 = 0.5 * Em / (1 + xnu);
+            m.d11 = (1.0 - xnu) * Em / ((1 + xnu) * (1 - 2.0 * xnu));
+            m.d12 = xnu * Em / ((1 + xnu) * (1 - 2.0 * xnu));
+            it = matmap.emplace(pi, (int)mats.size()).first;
+            mats.push_back(m);
+        }
+        mat[e] = it->second;
+    }
+    std::vector<double> xs(N), ys(N), zs(N);
+    for (int n = 0; n < N; ++n) { xs[n] = coords[3 * (size_t)n]; ys[n] = coords[3 * (size_t)n + 1]; zs[n] = coords[3 * (size_t)n + 2]; }
+    std::vector<int> conn((size_t)npe * E), adj_ptr(N + 1, 0);
+    for (size_t q = 0; q < conn.size(); ++q) {
+        const int n = connectivity[q] - 1;
+        if (n < 0 || n >= N) { delete c; return set_err("connectivity refers to a node that does not exist"); }
+        conn[q] = n;
+        adj_ptr[n + 1]++;
+    }
+    for (int n = 0; n < N; ++n) adj_ptr[n + 1] += adj_ptr[n];
+    std::vector<int> adj(conn.size()), fill(adj_ptr.begin(), adj_ptr.end() - 1);
+    for (int e = 0; e < E; ++e)
+        for (int a = 0; a < npe; ++a) adj[fill[conn[(size_t)e * npe + a]]++] = e * 32 + a;
+    std::vector<int>& browptr = c->h_browptr;
+    std::vector<int>& bcol = c->h_bcol;
+    browptr.assign(N + 1, 0);
+    bcol.clear();
+    std::vector<uint8_t> slot((size_t)npe * adj.size());
+    std::vector<int> cols;
+    for (int i = 0; i < N; ++i) {
+        cols.clear();
+        for (int k = adj_ptr[i]; k < adj_ptr[i + 1]; ++k) {
+            const int e = adj[k] >> 5;
+            for (int b = 0; b < npe; ++b) cols.push_back(conn[(size_t)e * npe + b]);
+        }
+        if (cols.empty()) cols.push_back(i);
+        std::sort(cols.begin(), cols.end());
+        cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+        if (cols.size() > 255) { delete c; return set_err("a node couples to more than 255 nodes"); }
+        for (int k = adj_ptr[i]; k < adj_ptr[i + 1]; ++k) {
+            const int e = adj[k] >> 5;
+            for (int b = 0; b < npe; ++b)
+                slot[(size_t)k * npe + b] = (uint8_t)(std::lower_bound(cols.begin(), cols.end(), conn[(size_t)e * npe + b]) - cols.begin());
+        }
+        bcol.insert(bcol.end(), cols.begin(), cols.end());
+        if (bcol.size() > 2000000000ULL) { delete c; return set_err("too many matrix blocks for one GPU"); }
+        browptr[i + 1] = (int)bcol.size();
+    }
+    c->nnzb = (long long)bcol.size();
+    for (int i = 0; i < N; ++i) c->max_row_blocks = std::max(c->max_row_blocks, browptr[i + 1] - browptr[i]);
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+#define UP(buf, vec)                                                                                  \
+    CK(c->buf.alloc((vec).size()));                                                                    \
+    CK(cudaMemcpy(c->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice))
+    UP(x, xs); UP(y, ys); UP(z, zs); UP(gconn, conn); UP(mat, mat); UP(mats, mats);
+    UP(adj_ptr, adj_ptr); UP(gadj, adj); UP(gslot, slot); UP(browptr, browptr); UP(bcol, bcol);
+#undef UP
+    const size_t nd = (size_t)c->ndof;
+    CK(c->val.alloc(9 * (size_t)c->nnzb));
+    for (DevBuf<double>* b : {&c->rhs, &c->rforce, &c->minv, &c->ut, &c->du, &c->felem, &c->fext, &c->cval, &c->sol, &c->r,
+                              &c->p, &c->Ap, &c->tmpvec, &c->tmpvec2, &c->diag}) {
+        CK(b->alloc(nd));
+        CK(cudaMemset(b->p, 0, nd * sizeof(double)));
+    }
+    CK(c->cflag.alloc(nd));
+    CK(cudaMemset(c->cflag.p, 0, nd));
+    CK(c->part.alloc(MAX_PARTIALS)); CK(c->part2.alloc(MAX_PARTIALS)); CK(c->part3.alloc(MAX_PARTIALS));
+    CK(c->S.alloc(1));
+    CK(cudaMemset(c->S.p, 0, sizeof(CgScalars)));
+    CK(cudaMallocHost((void**)&c->hS, sizeof(CgScalars)));
+    std::memset(c->hS, 0, sizeof(CgScalars));
+    CK(cudaMallocHost((void**)&c->hPoll, 2 * sizeof(CgPoll)));
+    std::memset(c->hPoll, 0, 2 * sizeof(CgPoll));
+    CK(cudaEventCreateWithFlags(&c->evPoll[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->evPoll[1], cudaEventDisableTiming));
+    CK(c->Ke.alloc((size_t)E * 9 * npe * npe));
+    CK(c->Re.alloc((size_t)E * 3 * npe));
+    {
+        int ob = 1, os = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ob, k_apply_bc, THREADS, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&os, k_spmv<4>, THREADS, 0));
+        const int need = (N + WARPS - 1) / WARPS;
+        c->grid_bc = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(ob, 1))));
+        c->grid_spmv = std::min(MAX_PARTIALS, std::max(1, std::min(need, c->n_sm * std::max(os, 1))));
+        c->grid_gather = c->grid_bc;
+    }
+    c->grid_vec = std::min(std::min(MAX_PARTIALS, P2P_MAXCTA), std::max(1, std::min((int)((nd + VEC_THREADS - 1) / VEC_THREADS), c->n_sm * 4)));
+    *out = c;
+    return 0;
+}
+
 int en234gpu_destroy(en234gpu_handle c) {
     if (c && c->dyn.graph) { cudaGraphExecDestroy(c->dyn.graph); c->dyn.graph = nullptr; }
     if (!c) return 0;
@@ -481,9 +628,31 @@ static int finish_norm(en234gpu_ctx* c, const double* part, int n, double* out) 
     return 0;
 }
 
+static int assemble_generic(en234gpu_ctx* c, double* nodal_force_norm, int* fail) {
+    if (c->mode != EN234_SOLVE_PCG_BSR) return set_err("4-, 10- and 20-node elements: assembled operator only");
+    if (c->comm.active) return set_err("4-, 10- and 20-node elements: one device only");
+    const GenMesh M = gen_mesh_of(c);
+    const long long nb = (long long)c->E * c->npe * c->npe, nr = (long long)c->E * c->npe;
+    k_gen_blocks<<<(unsigned)std::min<long long>((nb + 127) / 128, 65535LL * 16), 128, 0, c->stream>>>(M, c->Ke.p, c->S.p);
+    k_gen_residual<<<(unsigned)std::min<long long>((nr + 127) / 128, 65535LL * 16), 128, 0, c->stream>>>(M, c->ut.p, c->du.p, c->Re.p, c->S.p);
+    GenGatherArgs G;
+    G.M = M; G.Ke = c->Ke.p; G.Re = c->Re.p; G.val = c->val.p; G.rhs = c->rhs.p; G.rforce = c->rforce.p;
+    G.partials = c->part.p; G.diag = c->diag.p; G.S = c->S.p;
+    k_gen_gather<<<c->grid_gather, THREADS, 0, c->stream>>>(G);
+    c->st.kernel_launches += 3;
+    CK(cudaGetLastError());
+    c->diag_valid = true;
+    c->matrix_valid = true;
+    c->rhs_valid = true;
+    if (finish_norm(c, c->part.p, c->grid_gather, nodal_force_norm)) return 1;
+    *fail = c->hS->nanflag ? 1 : 0;
+    return phase_end(c, &c->st.assemble_ms);
+}
+
 int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail) {
     if (phase_begin(c)) return 1;
     CK(cudaMemsetAsync(&c->S.p->nanflag, 0, sizeof(int), c->stream));
+    if (c->npe != 8) return assemble_generic(c, nodal_force_norm, fail);
     const int with_matrix = c->mode == EN234_SOLVE_PCG_BSR ? 1 : 0;
     // partitioned runs add the (full-valued) element load vector after the halo sum of the partial residuals
     const double* felem = (c->have_felem && !c->comm.active) ? c->felem.p : nullptr;
@@ -1258,6 +1427,7 @@ int en234gpu_solve(en234gpu_handle c, int method, double cg_tolerance, int max_c
 // ---- element plugin surface / inspection --------------------------------------------------------------------
 int en234gpu_element_batch(en234gpu_handle c, int n, const int* element_numbers, const double* dof_total,
                            const double* dof_increment, double* element_stiffness, double* element_residual, int* fail) {
+    if (c->npe != 8) return set_err("en234gpu_element_batch: hex8 meshes only");
     CK(cudaSetDevice(c->device));
     std::vector<int> el(n);
     for (int i = 0; i < n; ++i) {
@@ -1283,6 +1453,7 @@ int en234gpu_element_batch(en234gpu_handle c, int n, const int* element_numbers,
 }
 
 int en234gpu_get_svars(en234gpu_handle c, const double* dof_total, const double* dof_increment, double* svars) {
+    if (c->npe != 8) return set_err("en234gpu_get_svars: hex8 meshes only");
     CK(cudaSetDevice(c->device));
     DevBuf<double> d_sv;
     CK(d_sv.alloc((size_t)c->E * 48));
@@ -1304,6 +1475,7 @@ int en234gpu_get_svars(en234gpu_handle c, const double* dof_total, const double*
 int en234gpu_project_fields(en234gpu_handle c, int n_fields, const int* field_codes, int lumped, double tolerance,
                             int max_iterations, const double* dof_total, const double* dof_increment, double* fields,
                             int* iterations) {
+    if (c->npe != 8) return set_err("en234gpu_project_fields: hex8 meshes only");
     CK(cudaSetDevice(c->device));
     // post-processing, not a timed path: every stage is synchronised so that a failure names the stage
 #define STAGE(name)                                                                                              \
@@ -1414,6 +1586,7 @@ int en234gpu_dynamic_setup(en234gpu_handle c, const double* element_density, int
                            const int* load_dof, const double* load_val, const int* load_history, const double* load_constant,
                            int n_pdof, const int* pdof_dof, const int* pdof_history, const double* pdof_value,
                            const int* pdof_mode) {
+    if (c->npe != 8) return set_err("explicit dynamics: hex8 meshes only");
     CK(cudaSetDevice(c->device));
     if (c->any_neo || c->any_c3d8)   // user_element_dynamic knows element 1001 only (user_element.f90:152-181); VUMAT is out of scope
         return set_err("explicit dynamics covers the linear elastic hex8 elements (1001 / VU1) only");
@@ -1706,6 +1879,7 @@ int en234gpu_apply_operator(en234gpu_handle c, int method, const double* x, doub
 int en234gpu_get_unique_id(char* id128) { return comm_unique_id(id128) ? set_err(comm_error()) : 0; }
 
 int en234gpu_comm_init(en234gpu_handle c, int n_ranks, int rank, const char* id128) {
+    if (c->npe != 8) return set_err("element partitions: hex8 meshes only");
     CK(cudaSetDevice(c->device));
     if (comm_init(c->comm, n_ranks, rank, id128, c->stream)) return set_err(comm_error());
     for (auto& g : c->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
@@ -1739,6 +1913,7 @@ int en234gpu_comm_connect(en234gpu_handle c, const char* handles) {
 
 int en234gpu_set_operator_mode(en234gpu_handle c, int method) {
     if (method != EN234_SOLVE_PCG_BSR && method != EN234_SOLVE_PCG_MATRIXFREE) return set_err("unknown operator mode");
+    if (c->npe != 8 && method != EN234_SOLVE_PCG_BSR) return set_err("the matrix-free operators are hex8 kernels");
     c->mode = method;
     c->matrix_valid = false;
     c->rhs_valid = false;

@@ -40,7 +40,7 @@ static void flatten(en234host_model& w) {
     auto& I = w.I;
     auto& D = w.D;
     I.clear(); D.clear();
-    I["n_nodes"] = {m.n_nodes}; I["n_elements"] = {m.n_elements};
+    I["n_nodes"] = {m.n_nodes}; I["n_elements"] = {m.n_elements}; I["nodes_per_element"] = {m.nodes_per_element};
     I["connectivity"] = m.connectivity; I["element_flag"] = m.element_flag;
     I["element_prop_index"] = m.element_prop_index; I["element_n_props"] = m.element_n_props;
     I["element_n_states"] = m.element_n_states;
@@ -252,8 +252,8 @@ int en234host_gpu_create(en234host_model_t w, int device, en234gpu_handle* h) {
     std::vector<double> props;
     std::vector<int> pidx;
     if (!device_property_table(m, props, pidx, g_err)) return 1;
-    int rc = en234gpu_create(h, device, m.n_nodes, m.n_elements, m.coords.data(), m.connectivity.data(),
-                             m.element_flag.data(), pidx.data(), props.data(), (int)props.size());
+    int rc = en234gpu_create_nodes(h, device, m.nodes_per_element, m.n_nodes, m.n_elements, m.coords.data(), m.connectivity.data(),
+                                   m.element_flag.data(), pidx.data(), props.data(), (int)props.size());
     if (rc) g_err = en234gpu_last_error();
     return rc;
 }
@@ -486,6 +486,7 @@ int en234host_run_static_part(en234host_model_t w, en234host_part_t p, en234gpu_
 en234host_part_t en234host_partition(en234host_model_t w, int n_ranks, int rank) {
     const Model& m = w->m;
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks) { g_err = "bad rank"; return nullptr; }
+    if (m.nodes_per_element != 8) { g_err = "element partitions are implemented for 8-node elements only"; return nullptr; }
     auto* p = new en234host_part();
     p->n_ranks = n_ranks; p->rank = rank;
     const long long E = m.n_elements;

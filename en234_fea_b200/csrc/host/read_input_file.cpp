@@ -607,6 +607,11 @@ bool parse_stream(std::istream& in, Model& m) {
     m.element_density.resize(m.n_elements, 0.0);
     for (int c : m.connectivity)
         if (c < 1 || c > m.n_nodes) return r.fail("connectivity refers to a node that does not exist");
+    // the face tables of the load routines are the hex8 ones (Element_Utilities.f90:1102-1109)
+    if (m.nodes_per_element != 8 && !m.distributed_loads.empty())
+        return r.fail("DISTRIBUTED LOADS are implemented for 8-node elements only (use FORCES / DEGREES OF FREEDOM on 4-, 10- and 20-node meshes)");
+    if (m.nodes_per_element != 8 && (m.stateprint || m.explicitdynamicstep))
+        return r.fail("PRINT STATE and EXPLICIT DYNAMIC STEP are implemented for 8-node elements only");
     return true;
 }
 

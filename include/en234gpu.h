@@ -57,6 +57,14 @@ int en234gpu_device_count(void);
 int en234gpu_create(en234gpu_handle* h, int device, int n_nodes, int n_elements, const double* coords,
                     const int* connectivity, const int* element_flag, const int* element_prop_index,
                     const double* element_properties, int n_element_properties);
+/* The same for meshes of 4-node / 10-node tetrahedra or 20-node bricks of element type 1001 (el_linelast_3Dbasic.f90:82-85:
+ * 1, 4, 27 integration points; shape functions Element_Utilities.f90:863-1025 as written there); connectivity holds
+ * nodes_per_element entries per element; nodes_per_element = 8 is en234gpu_create.  These meshes run the assembled-operator
+ * path on one device (assemble / apply_boundaryconditions / solve, host-buffer and device-resident forms); the matrix-free
+ * operators, state prints, explicit dynamics and partitions are hex8 paths. */
+int en234gpu_create_nodes(en234gpu_handle* h, int device, int nodes_per_element, int n_nodes, int n_elements,
+                          const double* coords, const int* connectivity, const int* element_flag,
+                          const int* element_prop_index, const double* element_properties, int n_element_properties);
 int en234gpu_destroy(en234gpu_handle h);
 
 /* Run all work of this handle on an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's

@@ -778,3 +778,59 @@ def test_multi_handle_static_step_matches_oracle(fused, monkeypatch):
     du2, rf2 = g.download_state()
     assert its2 == its and np.array_equal(du2, du)
     g.close()
+
+
+# ------------------------------------------------------------------------------------------- other 3-D element shapes (1001)
+def _assembled(g):
+    return g.csr().toarray()
+
+
+@pytest.mark.parametrize("shape,dims,jitter", [("tet4", (3, 2, 2), 0.15), ("tet10", (2, 2, 1), 0.15), ("hex20", (2, 2, 2), 0.2)])
+def test_other_element_shapes_assembly_matches_oracle(shape, dims, jitter):
+    """4-node / 10-node tetrahedra and 20-node bricks of element 1001 through the general device path: assembled matrix,
+    residual and reaction forces against the oracle (which carries the reference's shape-function table, quirks included)."""
+    import meshes
+    m = Model.from_text(meshes.input_text(shape, *dims, jitter=jitter))
+    a = m.arrays()
+    g = GpuSystem(m)
+    rng = np.random.default_rng(5)
+    ut, du = 1e-2 * rng.standard_normal(g.ndof), 1e-3 * rng.standard_normal(g.ndof)
+    rf, nrm, fail = g.assemble(ut, du)
+    s = ob.OracleSystem(ob.OracleModel(a, solvertype=2), 2)
+    rfo, nrmo, failo = s.assemble(ut, du)
+    assert fail == failo == 0
+    A, _ = s.matrix()
+    K = _assembled(g)
+    assert np.abs(K - A.toarray()).max() <= 1e-13 * np.abs(A.toarray()).max()
+    assert relmax(rf, rfo) < 1e-12 and abs(nrm - nrmo) <= 1e-12 * nrmo
+    g.close()
+
+
+def test_tet4_static_step_matches_oracle():
+    """A tet4 mesh (the one shape besides hex8 whose reference table is right) through the whole device step — parser,
+    general assembly, boundary conditions, PCG — against the oracle's skyline LDU: u and rforce within 1e-10."""
+    import meshes
+    m = Model.from_text(meshes.input_text("tet4", 5, 4, 4))
+    g = GpuSystem(m)
+    res = g.run_static(method=0)
+    ref = ob.OracleModel(m.arrays(), solvertype=1).run_static()
+    refcg = ob.OracleModel(m.arrays(), solvertype=2, cg_check_linear=1).run_static()
+    assert relmax(res["dof_total"], ref["dof_total"]) < TOL_U
+    assert relmax(res["rforce"], ref["rforce"]) < TOL_U
+    assert abs(int(res["cg_iterations"][0]) - int(refcg["cg_iterations"][0])) <= 2
+    with pytest.raises(RuntimeError, match="hex8"):
+        g.set_operator_mode(1)
+    g.close()
+
+
+def test_regular_hex20_fails_like_the_reference():
+    """Undistorted 20-node bricks: the reference's derivative table makes the Jacobian singular at an integration point, where
+    its invert_small stops the program; the device path and the oracle report fail instead."""
+    import meshes
+    m = Model.from_text(meshes.input_text("hex20", 2, 1, 1, jitter=0.0))
+    g = GpuSystem(m)
+    z = np.zeros(g.ndof)
+    assert g.assemble(z, z)[2] == 1
+    s = ob.OracleSystem(ob.OracleModel(m.arrays(), solvertype=2), 2)
+    assert s.assemble(z, z)[2] == 1
+    g.close()

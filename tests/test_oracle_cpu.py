@@ -3,6 +3,7 @@
 import gzip
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -369,6 +370,71 @@ def test_partition_maps():
             assert np.array_equal(mine, theirs) and mine.size == 25      # same nodes, same order, one 5x5 interface
     assert np.all(owners == 1)
     assert sorted(seen_elems) == list(range(m.n_elements))
+
+
+# ------------------------------------------------------------------------------------------- other 3-D element shapes
+def test_shape_function_table_equals_the_fortran_text_bit_for_bit():
+    """tet4 / tet10 / hex8 / hex20 shape functions and derivatives of the oracle against golden vectors evaluated from the
+    reference's Fortran text (tests/golden/make_shape3d_fixture.py) — including the entries of that table which are not
+    the derivatives of its own shape functions.  Regenerated from /root/reference when it is present."""
+    import ctypes as C
+    L = ob.lib()
+    g = np.load(os.path.join(GOLDEN, "shape3d_reference.npz"))
+    if HAVE_REF:
+        sys.path.insert(0, GOLDEN)
+        import make_shape3d_fixture as mk
+        blocks = mk.table_blocks()
+    for nn in (4, 10, 8, 20):
+        for k, xi in enumerate(g["xi_%d" % nn]):
+            f, df = np.zeros(nn), np.zeros(3 * nn)
+            assert L.or_shapefunctions_3d(nn, np.ascontiguousarray(xi).ctypes.data_as(ob.dp), f.ctypes.data_as(ob.dp), df.ctypes.data_as(ob.dp)) == 0
+            assert np.array_equal(f, g["f_%d" % nn][k]) and np.array_equal(df.reshape(nn, 3), g["df_%d" % nn][k]), nn
+            if HAVE_REF:
+                fr, dfr = mk.evaluate(blocks, nn, xi)
+                assert np.array_equal(fr, g["f_%d" % nn][k]) and np.array_equal(dfr, g["df_%d" % nn][k])
+    # the integration rules: single-precision literals of the reference (Element_Utilities.f90:586-689)
+    xi, w = np.zeros(81), np.zeros(27)
+    assert L.or_integration_points_3d(10, xi.ctypes.data_as(ob.dp), w.ctypes.data_as(ob.dp)) == 4
+    assert xi[0] == float(np.float32(0.58541020)) and xi[1] == float(np.float32(0.13819660)) and w[0] == 1.0 / 24.0
+    assert L.or_integration_points_3d(20, xi.ctypes.data_as(ob.dp), w.ctypes.data_as(ob.dp)) == 27
+    assert xi[0] == float(np.float32(-0.7745966692)) and w[13] == 0.888888888 ** 3
+    assert L.or_integration_points_3d(4, xi.ctypes.data_as(ob.dp), w.ctypes.data_as(ob.dp)) == 1 and w[0] == 1.0 / 6.0
+
+
+def test_tet4_mesh_on_the_oracle_and_what_the_reference_tables_do_to_tet10_and_hex20():
+    """tet4 (a correct table): patch test — a linear displacement field gives zero nodal residuals inside the mesh —, and
+    the skyline and CG paths agree.  tet10 / hex20: with the reference's table the assembled matrix is indefinite (tet10)
+    and regular 20-node bricks have a singular Jacobian at an integration point (the reference stops in invert_small): the
+    oracle reproduces both, which is what 'the same results as the reference' means for these two shapes."""
+    import meshes
+    m = Model.from_text(meshes.input_text("tet4", 3, 2, 2))
+    a = m.arrays()
+    assert a["nodes_per_element"][0] == 4 and m.n_elements == 72
+    rd = ob.OracleModel(a, solvertype=1).run_static()
+    rc = ob.OracleModel(a, solvertype=2, cg_check_linear=1).run_static()
+    assert np.abs(rd["dof_total"] - rc["dof_total"]).max() / np.abs(rd["dof_total"]).max() < 1e-11
+    om = ob.OracleModel(a, solvertype=2)
+    s = ob.OracleSystem(om, 2)
+    X = a["coords"].reshape(-1, 3)
+    G = np.array([[0.01, 0.002, 0.0], [0.0, -0.004, 0.003], [0.001, 0.0, 0.005]])
+    u = (X @ G.T).ravel()
+    rf, nrm, fail = s.assemble(u, np.zeros_like(u))
+    interior = np.all((X > 1e-9) & (X < np.array([3, 2, 2]) - 1e-9), axis=1)
+    assert not fail and interior.any() and np.abs(rf.reshape(-1, 3)[interior]).max() < 1e-13 * np.abs(rf).max()
+    A, _ = s.matrix()
+    assert np.linalg.eigvalsh(A.toarray())[0] > -1e-10 * abs(A).max()
+    # tet10: indefinite with the reference's df(10,1)
+    a10 = Model.from_text(meshes.input_text("tet10", 2, 1, 1)).arrays()
+    s10 = ob.OracleSystem(ob.OracleModel(a10, solvertype=2), 2)
+    z = np.zeros(3 * a10["n_nodes"][0])
+    assert s10.assemble(z, z)[2] == 0
+    A10, _ = s10.matrix()
+    assert np.linalg.eigvalsh(A10.toarray())[0] < -1.0
+    # hex20: regular bricks -> det == 0 at an integration point -> fail (the reference's invert_small stops)
+    a20 = Model.from_text(meshes.input_text("hex20", 2, 1, 1, jitter=0.0)).arrays()
+    s20 = ob.OracleSystem(ob.OracleModel(a20, solvertype=2), 2)
+    z = np.zeros(3 * a20["n_nodes"][0])
+    assert s20.assemble(z, z)[2] == 1
 
 
 def test_library_partition_equals_host_partition_and_refuses_empty_parts():

@@ -120,8 +120,9 @@ def measured_traffic(kernel, elements_per_gpu):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
+    first = lambda name: name.replace("void ", "").split("<")[0].split("(")[0].split(" ")[0]
     for row in json.load(open(p)):
-        if kernel.startswith(row["kernel"]) and row["elements_per_gpu"] == elements_per_gpu:
+        if first(kernel) == first(row["kernel"]) and row["elements_per_gpu"] == elements_per_gpu:
             return row["dram_bytes_per_launch"]
     return None
 

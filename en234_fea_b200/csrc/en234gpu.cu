@@ -944,9 +944,15 @@ static void p2p_halo_fork(en234gpu_ctx* c, double* vec, int check_stop) {
         for (int k = 0; k < cm.n_nbr; ++k) mx = std::max(mx, 3 * (cm.shared_ptr[k + 1] - cm.shared_ptr[k]));
         const int nblk = std::max(1, std::min(32, (mx + 255) / 256));
         k_halo_push<<<dim3(nblk, cm.n_nbr), 256, 0, cm.side>>>(cm.peers, cm.halo, vec, c->S.p, check_stop);
-        for (int k = 0; k < cm.n_nbr; ++k)
-            k_halo_wait_add<<<nblk, 256, 0, cm.side>>>(cm.peers, cm.halo, k, k == cm.n_nbr - 1 ? 1 : 0, vec, c->S.p, check_stop);
-        c->st.kernel_launches += 1 + cm.n_nbr;
+        if (cm.fused) {
+            // one launch: wait for all neighbours, add own and received values in ascending rank order
+            k_halo_wait_total<<<std::max(1, std::min(64, (3 * cm.n_interface + 255) / 256)), 256, 0, cm.side>>>(cm.F, vec, c->S.p, check_stop);
+            c->st.kernel_launches += 2;
+        } else {
+            for (int k = 0; k < cm.n_nbr; ++k)
+                k_halo_wait_add<<<nblk, 256, 0, cm.side>>>(cm.peers, cm.halo, k, k == cm.n_nbr - 1 ? 1 : 0, vec, c->S.p, check_stop);
+            c->st.kernel_launches += 1 + cm.n_nbr;
+        }
     }
     cudaEventRecord(cm.ev_join, cm.side);
 }
@@ -959,9 +965,15 @@ static void p2p_halo_exchange_on_side(en234gpu_ctx* c, double* vec, int check_st
         for (int k = 0; k < cm.n_nbr; ++k) mx = std::max(mx, 3 * (cm.shared_ptr[k + 1] - cm.shared_ptr[k]));
         const int nblk = std::max(1, std::min(32, (mx + 255) / 256));
         k_halo_push<<<dim3(nblk, cm.n_nbr), 256, 0, cm.side>>>(cm.peers, cm.halo, vec, c->S.p, check_stop);
-        for (int k = 0; k < cm.n_nbr; ++k)
-            k_halo_wait_add<<<nblk, 256, 0, cm.side>>>(cm.peers, cm.halo, k, k == cm.n_nbr - 1 ? 1 : 0, vec, c->S.p, check_stop);
-        c->st.kernel_launches += 1 + cm.n_nbr;
+        if (cm.fused) {
+            // one launch: wait for all neighbours, add own and received values in ascending rank order
+            k_halo_wait_total<<<std::max(1, std::min(64, (3 * cm.n_interface + 255) / 256)), 256, 0, cm.side>>>(cm.F, vec, c->S.p, check_stop);
+            c->st.kernel_launches += 2;
+        } else {
+            for (int k = 0; k < cm.n_nbr; ++k)
+                k_halo_wait_add<<<nblk, 256, 0, cm.side>>>(cm.peers, cm.halo, k, k == cm.n_nbr - 1 ? 1 : 0, vec, c->S.p, check_stop);
+            c->st.kernel_launches += 1 + cm.n_nbr;
+        }
     }
     cudaEventRecord(cm.ev_join, cm.side);
 }

@@ -606,8 +606,11 @@ __device__ __forceinline__ void tpe_point(const double* __restrict__ geomT, size
     tpe_force<P, 4>(T, f); tpe_force<P, 5>(T, f); tpe_force<P, 6>(T, f); tpe_force<P, 7>(T, f);
 }
 constexpr int TPE_THREADS = 128;
+#ifndef TPE_OCC
+#define TPE_OCC 2
+#endif
 template <class Load>
-__global__ void __launch_bounds__(TPE_THREADS, 2) k_element_forces_tpe(ElemArgs A, Load ld) {
+__global__ void __launch_bounds__(TPE_THREADS, TPE_OCC) k_element_forces_tpe(ElemArgs A, Load ld) {
     if (ld.stopped()) return;
     const Mesh& M = A.M;
     const Material mat0 = M.mats[0];

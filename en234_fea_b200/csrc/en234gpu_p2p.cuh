@@ -325,11 +325,14 @@ __device__ __forceinline__ double halo_total(const FusedComm& F, int hpar, int d
 // vec[interface DOFs] = own partial value + what the neighbours pushed, in ascending rank order (halo_total); waits for all
 // neighbours' flags first; the last CTA advances the halo sequence counter.  Replaces the per-neighbour k_halo_wait_add
 // launches where the interface tables exist.
-__global__ void __launch_bounds__(256) k_halo_wait_total(FusedComm F, double* __restrict__ vec) {
+__global__ void __launch_bounds__(256) k_halo_wait_total(FusedComm F, double* __restrict__ vec, CgScalars* S = nullptr,
+                                                         int check_stop = 0) {
+    if (check_stop && S->stop) return;
     ArenaHdr* mine = F.P.arena[F.P.me];
     const unsigned long long hseq = ld_volatile_u64(&mine->halo_seq) + 1ULL;
     const int hpar = (int)(hseq & 1ULL);
-    if (threadIdx.x < F.n_nbr) spin_until(&mine->halo_flag[F.nbr_rank[threadIdx.x]], hseq, &mine->error, F.P.timeout);
+    if (threadIdx.x < F.n_nbr)
+        spin_until(&mine->halo_flag[F.nbr_rank[threadIdx.x]], hseq, &mine->error, F.P.timeout, check_stop ? S : nullptr);
     __syncthreads();
     __threadfence_system();
     const int n3 = 3 * F.n_if;

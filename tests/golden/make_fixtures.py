@@ -6,7 +6,7 @@
   stretch_rotate_3d_umat.in  the same for input_files/Abaqus_umat_stretch_rotate.in (SUBROUTINE-type prescribed DOFs)
   linear_elastic_3d_umat.in  the same for input_files/Abaqus_umat_linear_elastic_3d.in (two C3D8 + UMAT elements)
   holeplate_3d_umat.in.gz    the same for input_files/Abaqus_umat_holeplate_3d.in (C3D8 + UMAT, the golden-log case)
-  *_oracle.npz               displacements, reaction forces and Newton history of the CPU oracle (skyline direct
+  *_oracle_output.npz        OUTPUTS OF THE REPO'S ORACLE (not of the reference, which cannot run here): displacements, reaction forces and Newton history of the CPU oracle (skyline direct
                              solver path) on those inputs
 """
 import gzip
@@ -42,7 +42,7 @@ for src, dst in [("Abaqus_uel_linear_elastic_3d.in", "linear_elastic_3d_uel.in")
         assert np.array_equal(a[k], b[k]), k
     om = ob.OracleModel(a)
     res = om.run_static()
-    np.savez_compressed(os.path.join(HERE, dst.split(".")[0] + "_oracle.npz"), dof_total=res["dof_total"],
+    np.savez_compressed(os.path.join(HERE, dst.split(".")[0] + "_oracle_output.npz"), dof_total=res["dof_total"],
                         rforce=res["rforce"], newton=res["newton"], profile=np.array(res["profile"]), lu=res["lu"])
     print(dst, "nodes", m.n_nodes, "elements", m.n_elements, "steps", res["n_steps"], "newton rows", len(res["newton"]))
     print(res["newton"])

@@ -154,7 +154,7 @@ def test_config1_reference_input_analytic_and_oracle():
     X = a["coords"].reshape(-1, 3)
     exact = np.stack([0.02 * X[:, 0], -0.006 * X[:, 1], -0.006 * X[:, 2]], 1).ravel()
     assert np.abs(res["dof_total"] - exact).max() < 1e-14
-    gold = np.load(os.path.join(GOLDEN, "linear_elastic_3d_uel_oracle.npz"))
+    gold = np.load(os.path.join(GOLDEN, "linear_elastic_3d_uel_oracle_output.npz"))
     assert relmax(res["dof_total"], gold["dof_total"]) < TOL_U
     assert relmax(res["rforce"], gold["rforce"]) < TOL_U
     assert res["n_steps"] == 3 and np.array_equal(res["newton"][:, [0, 1, 7]], gold["newton"][:, [0, 1, 7]])
@@ -167,7 +167,7 @@ def test_holeplate_reference_input_matches_golden_direct_solution():
     m = golden_model("holeplate_3d_uel.in.gz")
     g = GpuSystem(m)
     res = g.run_static(method=0)
-    gold = np.load(os.path.join(GOLDEN, "holeplate_3d_uel_oracle.npz"))
+    gold = np.load(os.path.join(GOLDEN, "holeplate_3d_uel_oracle_output.npz"))
     assert res["n_steps"] == 3
     assert relmax(res["dof_total"], gold["dof_total"]) < TOL_U
     assert relmax(res["rforce"], gold["rforce"]) < TOL_U

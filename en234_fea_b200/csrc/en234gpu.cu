@@ -685,7 +685,15 @@ int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail
             C3d8Args CA;
             CA.M = EA.M; CA.ut = c->ut.p; CA.du = c->du.p; CA.sv0 = c->sv0.p; CA.sv1 = c->sv1.p;
             CA.Ke = with_matrix ? c->Ke.p : nullptr; CA.Re = c->Re.p; CA.S = c->S.p;
-            k_element_c3d8<<<(c->E + 63) / 64, 64, 0, c->stream>>>(CA);
+            static const bool tpe = getenv("EN234_C3D8_TPE") && atoi(getenv("EN234_C3D8_TPE")) == 1;   // A/B: thread per element
+            if (tpe) k_element_c3d8<<<(c->E + 63) / 64, 64, 0, c->stream>>>(CA);
+            else {
+                // per device (several handles on different GPUs may live in one process): set on every launch, it is cheap
+                cudaFuncSetAttribute(k_element_c3d8_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(C3D8_WARPS * sizeof(C3d8Warp)));
+                const int per_cta = C3D8_WARPS * C3D8_GROUP;
+                const int grid = std::min((c->E + per_cta - 1) / per_cta, 148 * 12);
+                k_element_c3d8_warp<<<grid, 32 * C3D8_WARPS, C3D8_WARPS * sizeof(C3d8Warp), c->stream>>>(CA);
+            }
         } else if (c->any_neo && with_matrix) k_element_blocks<true, true, LoadSum><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
         else if (c->any_neo) k_element_blocks<true, false, LoadSum><<<c->grid_elem0, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);
         else if (with_matrix) k_element_blocks<false, true, LoadSum><<<c->grid_elem, c->elem_threads, c->elem_smem, c->stream>>>(EA, ld);

@@ -57,6 +57,7 @@ GPU_SYMBOLS = [
     "en234gpu_multi_zero_increment_dev", "en234gpu_multi_download_state", "en234gpu_multi_n_parts",
     "en234gpu_multi_part_handle", "en234gpu_multi_part_info", "en234gpu_multi_get_stats",
     "en234gpu_partition_sizes", "en234gpu_partition_arrays",
+    "en234gpu_set_ties", "en234gpu_get_lagrange_multipliers",
 ]
 HOST_SYMBOLS = [
     "en234host_model_read", "en234host_model_from_text", "en234host_model_free", "en234host_last_error",
@@ -117,7 +118,8 @@ INT_ARRAYS = ["connectivity", "element_flag", "element_prop_index", "element_n_p
               "history_ptr", "nodeset_ptr", "nodeset_nodes", "elementset_ptr", "elementset_elements",
               "pdof_flag", "pdof_dof", "pdof_node", "pdof_nodeset", "pdof_history", "pdof_rate", "pdof_subparam", "subparam_ptr",
               "pforce_flag", "pforce_dof", "pforce_node", "pforce_nodeset", "pforce_history",
-              "dload_flag", "dload_elset", "dload_face", "dload_history", "dload_val_ptr"]
+              "dload_flag", "dload_elset", "dload_face", "dload_history", "dload_val_ptr",
+              "con_node1", "con_dof1", "con_node2", "con_dof2"]
 INT_SCALARS = ["n_nodes", "n_elements", "nodes_per_element", "max_no_steps", "solvertype", "nonlinear", "max_newton_iterations",
                "unsymmetric", "abaqusformat", "max_cg_iterations", "checkstiffness_flag", "explicitdynamicstep", "no_dynamic_steps"]
 DBL_ARRAYS = ["coords", "element_properties", "material_properties", "history_time", "history_value", "pdof_value", "pforce_value",
@@ -568,8 +570,22 @@ class GpuSystem:
                                                  _ip(cg), C.c_int(4096), info, os.fsencode(log_path) if log_path else None)
         if rc:
             raise RuntimeError("static step failed: " + host_lib().en234host_last_error().decode())
-        return {"dof_total": u, "rforce": rf, "newton": newton[:info[2]].copy(), "cg_iterations": cg[:info[3]].copy(),
-                "n_steps": int(info[0]), "n_cutbacks": int(info[1]), "n_state_prints": int(info[4])}
+        out = {"dof_total": u, "rforce": rf, "newton": newton[:info[2]].copy(), "cg_iterations": cg[:info[3]].copy(),
+               "n_steps": int(info[0]), "n_cutbacks": int(info[1]), "n_state_prints": int(info[4])}
+        ncon = self.model.ints("con_node1").size if self.model is not None and self.part is None else 0
+        if ncon:                       # two-node tie constraints: the Lagrange multipliers the reference keeps in module Boundaryconditions
+            out["lagrange_multipliers"] = self.lagrange_multipliers(ncon)
+        return out
+
+    def set_ties(self, dof1, dof2):
+        """u[dof1[k]] = u[dof2[k]] (0-based DOFs): en234gpu_set_ties."""
+        a, b = _i32(dof1), _i32(dof2)
+        self._ck(gpu_lib().en234gpu_set_ties(self.h, C.c_int(a.size), _ip(a), _ip(b)))
+
+    def lagrange_multipliers(self, n):
+        lam = np.zeros(n)
+        self._ck(gpu_lib().en234gpu_get_lagrange_multipliers(self.h, C.c_int(n), _dp(lam)))
+        return lam
 
 
 

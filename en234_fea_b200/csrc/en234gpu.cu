@@ -22,6 +22,7 @@
 #include "en234gpu_dyn.cuh"
 #include "en234gpu_generic.cuh"
 #include "en234gpu_comm.h"
+#include "en234gpu_ties.cuh"
 
 using namespace en234k;
 
@@ -54,6 +55,31 @@ constexpr int CG_CHUNK = 32;   // PCG iterations per CUDA-graph launch (even: it
 
 // what the host reads back after every chunk of captured iterations (pinned; two slots: one chunk is always in flight)
 struct CgPoll { en234k::CgScalars S; int p2p_error; int pad; };
+
+// two-node tie constraints (en234gpu_ties.cuh, en234gpu_ties_host.h)
+struct Ties {
+    int n = 0;                               // constraints
+    std::vector<int> d1, d2;                 // u[d1] = u[d2], 0-based DOFs
+    std::vector<double> lambda, h_gap;       // Lagrange multipliers (host copy is the master), gaps of the last norm
+    std::vector<int> h_tdof, idx1, idx2;     // touched DOFs (sorted), index of d1 / d2 in that list
+    int n_tdof = 0, n_groups = 0, n_members = 0;
+    double eps = 0.0;                        // compliance of the multiplier rows: 1e-12 |diag| / neq
+    DevBuf<int> dd1, dd2, tdof, tptr, tent, counts, g_root, g_ptr, m_dof, m_root;
+    DevBuf<uint8_t> g_fixed, m_fixed;
+    DevBuf<double> dlambda, gap, trow, mgap, rhs0, vec, d0;
+    std::vector<int> peel_tie, peel_leaf;    // recovery order of the multiplier corrections
+    bool groups_valid = false;
+    std::vector<int> groups_fixdof;          // prescribed set the groups were built for
+    void reset() {
+        for (DevBuf<int>* b : {&dd1, &dd2, &tdof, &tptr, &tent, &counts, &g_root, &g_ptr, &m_dof, &m_root}) b->release();
+        g_fixed.release(); m_fixed.release();
+        for (DevBuf<double>* b : {&dlambda, &gap, &trow, &mgap, &rhs0, &vec, &d0}) b->release();
+        n = n_tdof = n_groups = n_members = 0;
+        d1.clear(); d2.clear(); lambda.clear(); h_gap.clear(); h_tdof.clear(); idx1.clear(); idx2.clear();
+        peel_tie.clear(); peel_leaf.clear(); groups_fixdof.clear();
+        groups_valid = false; eps = 0.0;
+    }
+};
 
 struct en234gpu_ctx {
     int device = 0;
@@ -124,6 +150,7 @@ struct en234gpu_ctx {
     std::vector<int> h_browptr, h_bcol;
     // multi-GPU
     Comm comm;
+    Ties ties;
     // stats
     en234gpu_stats st{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -619,6 +646,12 @@ static int phase_end(en234gpu_ctx* c, double* ms) {
 }
 
 // sum a per-node-owned norm^2 partial array into S->norm2, all-reduce across ranks, return sqrt
+static TieTables tie_tables(en234gpu_ctx* c);
+static int ties_after_assemble(en234gpu_ctx* c, double* nodal_force_norm);
+static int ties_after_bc(en234gpu_ctx* c, double* unbalanced);
+static int ties_before_solve(en234gpu_ctx* c);
+static int ties_after_solve(en234gpu_ctx* c, double* dl2);
+
 static int finish_norm(en234gpu_ctx* c, const double* part, int n, double* out) {
     k_reduce_to<<<1, VEC_THREADS, 0, c->stream>>>(part, n, &c->S.p->norm2);
     c->st.kernel_launches++;
@@ -646,6 +679,7 @@ static int assemble_generic(en234gpu_ctx* c, double* nodal_force_norm, int* fail
     c->rhs_valid = true;
     if (finish_norm(c, c->part.p, c->grid_gather, nodal_force_norm)) return 1;
     *fail = c->hS->nanflag ? 1 : 0;
+    if (c->ties.n && !*fail && ties_after_assemble(c, nodal_force_norm)) return 1;
     return phase_end(c, &c->st.assemble_ms);
 }
 
@@ -731,6 +765,7 @@ int en234gpu_assemble_dev(en234gpu_handle c, double* nodal_force_norm, int* fail
     int bad = c->hS->nanflag;
     if (c->comm.active && comm_host_max(c->comm, &bad, c->stream)) return set_err(comm_error());
     *fail = bad ? 1 : 0;
+    if (c->ties.n && !bad && ties_after_assemble(c, nodal_force_norm)) return 1;
     return phase_end(c, &c->st.assemble_ms);
 }
 
@@ -834,7 +869,9 @@ static int apply_bc_common(en234gpu_ctx* c, int values_are_corrections, double* 
         c->st.kernel_launches++;
     }
     CK(cudaGetLastError());
-    return finish_norm(c, part, npart, unbalanced);
+    if (finish_norm(c, part, npart, unbalanced)) return 1;
+    if (c->ties.n && ties_after_bc(c, unbalanced)) return 1;
+    return 0;
 }
 
 int en234gpu_apply_boundaryconditions_dev(en234gpu_handle c, double* unbalanced_force_norm) {
@@ -1076,7 +1113,15 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
         c->st.kernel_launches += 4;
         return 0;
     }
+    if (c->ties.n) {
+        k_tie_expand<<<std::max(1, (c->ties.n_tdof + 255) / 256), 256, 0, c->stream>>>(tie_tables(c), c->p.p, c->S.p);
+        c->st.kernel_launches++;
+    }
     launch_operator(c, method, c->p.p, c->Ap.p, 1);
+    if (c->ties.n) {
+        k_tie_reduce<<<std::max(1, (c->ties.n_tdof + 255) / 256), 256, 0, c->stream>>>(tie_tables(c), c->Ap.p, c->p.p, c->S.p);
+        c->st.kernel_launches++;
+    }
     if (cm.active) {
         // NCCL path (EN234_COMM=nccl or no peer arena)
         const int np = operator_partials(c, method);
@@ -1331,17 +1376,24 @@ int en234gpu_solve_dev(en234gpu_handle c, int method, double cg_tolerance, int m
     if (method == EN234_SOLVE_PCG_MATRIXFREE && c->any_neo)
         return set_err("the matrix-free operator covers the linear-elastic elements only (1001 / U1)");
     if (phase_begin(c)) return 1;
+    if (c->ties.n && ties_before_solve(c)) return 1;
     if (pcg_run(c, method, cg_tolerance, max_cg_iterations)) return 1;
     *fail = c->hS->fail ? 1 : 0;
     *cg_iterations = c->hS->iter;
     c->st.last_cg_iterations = c->hS->iter;
     c->st.last_cg_err = c->hS->err;
+    const int cg_iter = c->hS->iter;
+    const double cg_err = c->hS->err;
     if (!*fail) {
+        double dl2 = 0.0;
+        if (c->ties.n && ties_after_solve(c, &dl2)) return 1;
         k_add_solution<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(c->ndof, c->sol.p, c->du.p,
                                                                   c->have_owned ? c->owned.p : nullptr, c->part2.p);
         c->st.kernel_launches++;
         if (finish_norm(c, c->part2.p, c->grid_vec, correction_norm)) return 1;
+        if (c->ties.n) *correction_norm = std::sqrt(*correction_norm * *correction_norm + dl2);   // multiplier corrections count (:971)
     } else *correction_norm = 0.0;
+    c->hS->iter = cg_iter; c->hS->err = cg_err;
     if (phase_end(c, &c->st.solve_ms)) return 1;
     c->st.spmv_ms_avg = c->hS->iter > 0 ? c->st.solve_ms / c->hS->iter : 0.0;
     return 0;
@@ -1977,4 +2029,5 @@ int en234gpu_bench_operator(en234gpu_handle c, int method, int warm, int reps, d
 
 }  // extern "C"
 
+#include "en234gpu_ties_host.h"
 #include "en234gpu_multi.h"

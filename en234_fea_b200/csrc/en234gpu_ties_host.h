@@ -1,0 +1,241 @@
+// Host side of the tie-constraint layer (kernels and the method: en234gpu_ties.cuh).  Included by en234gpu.cu.
+#pragma once
+
+static TieTables tie_tables(en234gpu_ctx* c) {
+    Ties& t = c->ties;
+    TieTables T;
+    T.counts = t.counts.p; T.g_root = t.g_root.p; T.g_ptr = t.g_ptr.p; T.g_fixed = t.g_fixed.p;
+    T.m_dof = t.m_dof.p; T.m_root = t.m_root.p; T.m_fixed = t.m_fixed.p;
+    return T;
+}
+
+// Groups of tied DOFs for the current prescribed set: a group with a prescribed member follows that member (its root), every
+// other group is reduced to its smallest DOF.  Also the order in which the multiplier corrections are recovered after a solve.
+static int ties_rebuild_groups(en234gpu_ctx* c) {
+    Ties& t = c->ties;
+    const int nt = t.n_tdof;
+    std::vector<int> parent(nt);
+    for (int i = 0; i < nt; ++i) parent[i] = i;
+    auto find = [&](int i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; };
+    for (int k = 0; k < t.n; ++k) {
+        const int a = find(t.idx1[k]), b = find(t.idx2[k]);
+        if (a == b) return set_err("tie constraints: constraint " + std::to_string(k + 1) + " closes a loop (redundant constraint)");
+        parent[std::max(a, b)] = std::min(a, b);       // the smallest touched DOF is the representative
+    }
+    std::vector<uint8_t> fixed(nt, 0);
+    for (int d : c->h_fixdof) {
+        auto it = std::lower_bound(t.h_tdof.begin(), t.h_tdof.end(), d);
+        if (it != t.h_tdof.end() && *it == d) fixed[it - t.h_tdof.begin()] = 1;
+    }
+    std::vector<int> root_of(nt, -1);                  // representative -> root index
+    for (int i = 0; i < nt; ++i) {
+        const int r = find(i);
+        if (fixed[i]) {
+            if (root_of[r] >= 0 && fixed[root_of[r]])
+                return set_err("tie constraints: two prescribed DOFs are tied together (DOFs " + std::to_string(t.h_tdof[root_of[r]]) +
+                               " and " + std::to_string(t.h_tdof[i]) + ", 0-based)");
+            root_of[r] = i;
+        } else if (root_of[r] < 0) root_of[r] = i;
+    }
+    std::vector<int> g_root, g_ptr{0}, m_dof, m_root, gid(nt, -1);
+    std::vector<uint8_t> g_fixed, m_fixed;
+    for (int i = 0; i < nt; ++i) {
+        const int r = find(i);
+        if (gid[r] < 0) { gid[r] = (int)g_root.size(); g_root.push_back(t.h_tdof[root_of[r]]); g_fixed.push_back(fixed[root_of[r]]); }
+    }
+    std::vector<std::vector<int>> mem(g_root.size());
+    for (int i = 0; i < nt; ++i) { const int r = find(i); if (root_of[r] != i) mem[gid[r]].push_back(t.h_tdof[i]); }
+    for (size_t g = 0; g < g_root.size(); ++g) {
+        for (int d : mem[g]) { m_dof.push_back(d); m_root.push_back(g_root[g]); m_fixed.push_back(g_fixed[g]); }
+        g_ptr.push_back((int)m_dof.size());
+    }
+    const int counts[2] = {(int)g_root.size(), (int)m_dof.size()};
+    t.n_groups = counts[0]; t.n_members = counts[1];
+    CK(cudaMemcpyAsync(t.counts.p, counts, sizeof(counts), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(t.g_root.p, g_root.data(), g_root.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(t.g_ptr.p, g_ptr.data(), g_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(t.g_fixed.p, g_fixed.data(), g_fixed.size(), cudaMemcpyHostToDevice, c->stream));
+    if (!m_dof.empty()) {
+        CK(cudaMemcpyAsync(t.m_dof.p, m_dof.data(), m_dof.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(t.m_root.p, m_root.data(), m_root.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(t.m_fixed.p, m_fixed.data(), m_fixed.size(), cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    // recovery order of the multiplier corrections: peel the leaves of every tree (a prescribed DOF's row carries no information)
+    std::vector<int> deg(nt, 0);
+    std::vector<std::vector<int>> at(nt);
+    for (int k = 0; k < t.n; ++k) { at[t.idx1[k]].push_back(k); at[t.idx2[k]].push_back(k); deg[t.idx1[k]]++; deg[t.idx2[k]]++; }
+    std::vector<uint8_t> done(t.n, 0);
+    std::vector<int> queue;
+    for (int i = 0; i < nt; ++i) if (deg[i] == 1 && !fixed[i]) queue.push_back(i);
+    t.peel_tie.clear(); t.peel_leaf.clear();
+    for (size_t q = 0; q < queue.size(); ++q) {
+        const int i = queue[q];
+        if (deg[i] != 1) continue;
+        int k = -1;
+        for (int kk : at[i]) if (!done[kk]) { k = kk; break; }
+        if (k < 0) continue;
+        done[k] = 1;
+        t.peel_tie.push_back(k); t.peel_leaf.push_back(i);
+        const int o = t.idx1[k] == i ? t.idx2[k] : t.idx1[k];
+        deg[i]--; deg[o]--;
+        if (deg[o] == 1 && !fixed[o]) queue.push_back(o);
+    }
+    if ((int)t.peel_tie.size() != t.n) return set_err("tie constraints: the multipliers cannot be recovered (inconsistent constraint graph)");
+    t.groups_valid = true;
+    t.groups_fixdof = c->h_fixdof;
+    return 0;
+}
+
+extern "C" int en234gpu_set_ties(en234gpu_handle c, int n_ties, const int* dof1, const int* dof2) {
+    CK(cudaSetDevice(c->device));
+    if (n_ties < 0 || (n_ties > 0 && (!dof1 || !dof2))) return set_err("en234gpu_set_ties: bad arguments");
+    if (c->comm.active) return set_err("en234gpu_set_ties: tie constraints are implemented for one device (unpartitioned handle)");
+    Ties& t = c->ties;
+    for (auto& g : c->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }      // the PCG iteration changes shape
+    t.reset();
+    if (n_ties == 0) return 0;
+    for (int k = 0; k < n_ties; ++k) {
+        if (dof1[k] < 0 || dof1[k] >= c->ndof || dof2[k] < 0 || dof2[k] >= c->ndof) return set_err("en234gpu_set_ties: DOF out of range");
+        if (dof1[k] == dof2[k]) return set_err("en234gpu_set_ties: a DOF is tied to itself");
+    }
+    t.n = n_ties;
+    t.d1.assign(dof1, dof1 + n_ties); t.d2.assign(dof2, dof2 + n_ties);
+    t.lambda.assign(n_ties, 0.0);
+    t.h_tdof = t.d1;
+    t.h_tdof.insert(t.h_tdof.end(), t.d2.begin(), t.d2.end());
+    std::sort(t.h_tdof.begin(), t.h_tdof.end());
+    t.h_tdof.erase(std::unique(t.h_tdof.begin(), t.h_tdof.end()), t.h_tdof.end());
+    t.n_tdof = (int)t.h_tdof.size();
+    auto index_of = [&](int d) { return (int)(std::lower_bound(t.h_tdof.begin(), t.h_tdof.end(), d) - t.h_tdof.begin()); };
+    t.idx1.resize(n_ties); t.idx2.resize(n_ties);
+    std::vector<std::vector<int>> ent(t.n_tdof);
+    for (int k = 0; k < n_ties; ++k) {
+        t.idx1[k] = index_of(t.d1[k]); t.idx2[k] = index_of(t.d2[k]);
+        ent[t.idx1[k]].push_back(2 * k);            // row of dof1: - lambda
+        ent[t.idx2[k]].push_back(2 * k + 1);        // row of dof2: + lambda
+    }
+    std::vector<int> tptr{0}, tent;
+    for (auto& e : ent) { tent.insert(tent.end(), e.begin(), e.end()); tptr.push_back((int)tent.size()); }
+    const size_t nt = (size_t)t.n_tdof, nd = (size_t)c->ndof;
+    CK(t.dd1.alloc(n_ties)); CK(t.dd2.alloc(n_ties)); CK(t.dlambda.alloc(n_ties)); CK(t.gap.alloc(n_ties));
+    CK(t.tdof.alloc(nt)); CK(t.tptr.alloc(nt + 1)); CK(t.tent.alloc(tent.size())); CK(t.trow.alloc(nt));
+    CK(t.counts.alloc(2)); CK(t.g_root.alloc(nt)); CK(t.g_ptr.alloc(nt + 1)); CK(t.g_fixed.alloc(nt));
+    CK(t.m_dof.alloc(nt)); CK(t.m_root.alloc(nt)); CK(t.m_fixed.alloc(nt)); CK(t.mgap.alloc(nt));
+    CK(t.rhs0.alloc(nd)); CK(t.vec.alloc(nd)); CK(t.d0.alloc(nd));
+    CK(cudaMemcpy(t.dd1.p, t.d1.data(), n_ties * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t.dd2.p, t.d2.data(), n_ties * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemset(t.dlambda.p, 0, n_ties * sizeof(double)));
+    CK(cudaMemcpy(t.tdof.p, t.h_tdof.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t.tptr.p, tptr.data(), tptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(t.tent.p, tent.data(), tent.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (ties_rebuild_groups(c)) { t.reset(); return 1; }
+    return 0;
+}
+
+extern "C" int en234gpu_get_lagrange_multipliers(en234gpu_handle c, int n, double* out) {
+    if (n != c->ties.n) return set_err("en234gpu_get_lagrange_multipliers: the handle has " + std::to_string(c->ties.n) + " tie constraints");
+    for (int k = 0; k < n; ++k) out[k] = c->ties.lambda[k];
+    return 0;
+}
+
+static int ties_check_mode(en234gpu_ctx* c) {
+    if (c->mode != EN234_SOLVE_PCG_BSR) return set_err("tie constraints: assembled operator only (EN234_SOLVE_PCG_BSR)");
+    if (c->any_c3d8) return set_err("tie constraints: symmetric stiffness (PCG) only; C3D8 elements use BiCGSTAB");
+    if (!c->diag_valid) return set_err("tie constraints need the two-kernel assembly (unset EN234_ASM=rows)");
+    return 0;
+}
+
+// sum of (gap - eps lambda)^2 over the multiplier rows (their right-hand side, solver_direct.f90:325-326)
+static int ties_row_norm2(en234gpu_ctx* c, bool after_bc, double* out) {
+    Ties& t = c->ties;
+    k_tie_gap<<<(t.n + 255) / 256, 256, 0, c->stream>>>(t.n, t.dd1.p, t.dd2.p, c->ut.p, c->du.p, after_bc ? c->cflag.p : nullptr, c->cval.p, t.gap.p);
+    c->st.kernel_launches++;
+    t.h_gap.resize(t.n);
+    CK(cudaMemcpyAsync(t.h_gap.data(), t.gap.p, t.n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    double s = 0.0;
+    for (int k = 0; k < t.n; ++k) { const double g = t.h_gap[k] - t.lambda[k] * t.eps; s += g * g; }
+    *out = s;
+    return 0;
+}
+
+// after the element assembly: multiplier terms of the tied rows, reaction forces, generalized force norm over all equations
+static int ties_after_assemble(en234gpu_ctx* c, double* nodal_force_norm) {
+    Ties& t = c->ties;
+    if (ties_check_mode(c)) return 1;
+    // eps = 1e-12 |diag| / neq over the assembled diagonal (multiplier rows are still zero there), solver_direct.f90:292
+    k_sumsq<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(c->ndof, c->diag.p, c->part2.p);
+    double dn = 0.0;
+    if (finish_norm(c, c->part2.p, c->grid_vec, &dn)) return 1;
+    t.eps = 1.e-12 * dn / (double)(c->ndof + t.n);
+    k_tie_rhs<<<(t.n_tdof + 255) / 256, 256, 0, c->stream>>>(t.n_tdof, t.tdof.p, t.tptr.p, t.tent.p, t.dlambda.p, c->rhs.p, c->rforce.p);
+    k_sumsq<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(c->ndof, c->rhs.p, c->part2.p);
+    c->st.kernel_launches += 3;
+    double rn = 0.0, g2 = 0.0;
+    if (finish_norm(c, c->part2.p, c->grid_vec, &rn)) return 1;
+    if (ties_row_norm2(c, false, &g2)) return 1;
+    *nodal_force_norm = std::sqrt(rn * rn + g2);
+    return 0;
+}
+
+static int ties_after_bc(en234gpu_ctx* c, double* unbalanced) {
+    double g2 = 0.0;
+    if (ties_row_norm2(c, true, &g2)) return 1;
+    *unbalanced = std::sqrt(*unbalanced * *unbalanced + g2);
+    return 0;
+}
+
+// before the PCG loop: keep the reference-form right-hand side, move the known member corrections to the right-hand side,
+// reduce right-hand side and Jacobi diagonal to the roots
+static int ties_before_solve(en234gpu_ctx* c) {
+    Ties& t = c->ties;
+    if (ties_check_mode(c)) return 1;
+    if (!t.groups_valid || t.groups_fixdof != c->h_fixdof) {
+        if (ties_rebuild_groups(c)) return 1;
+    }
+    const TieTables T = tie_tables(c);
+    const size_t b = (size_t)c->ndof * sizeof(double);
+    CK(cudaMemcpyAsync(t.rhs0.p, c->rhs.p, b, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemsetAsync(t.d0.p, 0, b, c->stream));
+    const int gm = std::max(1, (t.n_tdof + 255) / 256);
+    k_tie_d0<<<gm, 256, 0, c->stream>>>(T, c->ut.p, c->du.p, c->cval.p, t.d0.p, t.mgap.p);
+    int np = 0;
+    launch_spmv_rows(c, t.d0.p, t.vec.p, 0, c->N, 0, 0, &np, 0, nullptr, false);
+    k_vec_sub<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(c->ndof, t.vec.p, c->rhs.p);
+    k_tie_reduce_rhs<<<gm, 256, 0, c->stream>>>(T, c->rhs.p, c->minv.p);
+    c->st.kernel_launches += 3;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// after the PCG loop: corrections of the members, multiplier corrections from the tied rows of rhs - K sol; *dl2 = their sum of squares
+static int ties_after_solve(en234gpu_ctx* c, double* dl2) {
+    Ties& t = c->ties;
+    const TieTables T = tie_tables(c);
+    const int gm = std::max(1, (t.n_tdof + 255) / 256);
+    k_tie_expand_sol<<<gm, 256, 0, c->stream>>>(T, t.mgap.p, c->sol.p);
+    int np = 0;
+    launch_spmv_rows(c, c->sol.p, t.vec.p, 0, c->N, 0, 0, &np, 0, nullptr, false);
+    k_tie_rows<<<gm, 256, 0, c->stream>>>(t.n_tdof, t.tdof.p, t.rhs0.p, t.vec.p, t.trow.p);
+    c->st.kernel_launches += 2;
+    std::vector<double> row(t.n_tdof);
+    CK(cudaMemcpyAsync(row.data(), t.trow.p, row.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    // row of dof1: K du + dlambda = rhs;  row of dof2: K du - dlambda = rhs.  Leaves first; a resolved multiplier is moved to the
+    // other end's row.
+    double s = 0.0;
+    for (size_t q = 0; q < t.peel_tie.size(); ++q) {
+        const int k = t.peel_tie[q], leaf = t.peel_leaf[q];
+        const bool first = t.idx1[k] == leaf;
+        const double dl = first ? row[leaf] : -row[leaf];
+        const int other = first ? t.idx2[k] : t.idx1[k];
+        row[other] += first ? dl : -dl;          // remove this multiplier from the other row: (-dl) there if other is dof2, (+dl) if dof1
+        t.lambda[k] += dl;
+        s += dl * dl;
+    }
+    CK(cudaMemcpyAsync(t.dlambda.p, t.lambda.data(), t.n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *dl2 = s;
+    return 0;
+}

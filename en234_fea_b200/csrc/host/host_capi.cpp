@@ -85,6 +85,11 @@ static void flatten(en234host_model& w) {
         D["subparam_values"].insert(D["subparam_values"].end(), sp.values.begin(), sp.values.end());
         I["subparam_ptr"].push_back((int)D["subparam_values"].size());
     }
+    for (const char* k : {"con_node1", "con_dof1", "con_node2", "con_dof2"}) I[k];     // two-node tie constraints
+    for (auto& c : m.constraints) {
+        I["con_node1"].push_back(c.node1); I["con_dof1"].push_back(c.dof1);
+        I["con_node2"].push_back(c.node2); I["con_dof2"].push_back(c.dof2);
+    }
     for (const char* k : {"dload_flag", "dload_elset", "dload_face", "dload_history"}) I[k];
     I["dload_val_ptr"] = {0};
     D["dload_values"];
@@ -199,6 +204,7 @@ int en234host_check_stiffness(en234host_model_t w, int element_flag, const doubl
 // decided when the reference is linked.  The device implements the shipped ones and nothing else, so models whose property /
 // state counts do not fit those routines are refused instead of being run with the wrong physics.
 static bool device_supports(const Model& m, std::string& err) {
+    if (!m.constraints.empty() && m.explicitdynamicstep) { err = "CONSTRAINTS are implemented for the static step only"; return false; }
     for (int e = 0; e < m.n_elements; ++e) {
         const int flag = m.element_flag[e], np = m.element_n_props[e];
         if (flag == 100000 && np != 2 && np != 3) {
@@ -254,7 +260,17 @@ int en234host_gpu_create(en234host_model_t w, int device, en234gpu_handle* h) {
     if (!device_property_table(m, props, pidx, g_err)) return 1;
     int rc = en234gpu_create_nodes(h, device, m.nodes_per_element, m.n_nodes, m.n_elements, m.coords.data(), m.connectivity.data(),
                                    m.element_flag.data(), pidx.data(), props.data(), (int)props.size());
-    if (rc) g_err = en234gpu_last_error();
+    if (rc) { g_err = en234gpu_last_error(); return rc; }
+    if (!m.constraints.empty()) {
+        // two-node ties (CONSTRAIN NODE PAIRS / TIE NODES): 0-based DOF pairs, u[dof1] = u[dof2] (solver_direct.f90:294-328)
+        std::vector<int> d1, d2;
+        for (const Constraint& c : m.constraints) {
+            d1.push_back(3 * (c.node1 - 1) + c.dof1 - 1);
+            d2.push_back(3 * (c.node2 - 1) + c.dof2 - 1);
+        }
+        rc = en234gpu_set_ties(*h, (int)d1.size(), d1.data(), d2.data());
+        if (rc) { g_err = en234gpu_last_error(); en234gpu_destroy(*h); *h = nullptr; }
+    }
     return rc;
 }
 
@@ -604,6 +620,7 @@ const unsigned char* en234host_part_owned(en234host_part_t p) { return p->owned.
 int en234host_part_gpu_create(en234host_model_t w, en234host_part_t p, int device, en234gpu_handle* h) {
     const Model& m = w->m;
     if (!device_supports(m, g_err)) return 1;
+    if (!m.constraints.empty()) { g_err = "CONSTRAINTS (tied DOFs) are implemented for one device: run this model unpartitioned"; return 1; }
     const auto& lel = p->I["local_elements"];
     std::vector<double> props;
     std::vector<int> gidx;

@@ -32,6 +32,12 @@ struct DistributedLoad {      // distributedload_list (Boundaryconditions.f90:57
     bool uel_format = false;
 };
 
+struct Constraint {           // constraint_list (Boundaryconditions.f90; read_input_file.f90:1429-1541)
+    int flag = 1;             // 1 CONSTRAIN NODE PAIRS, 2 TIE NODES (two-node ties); 3 CONSTRAIN NODE SET (user_constraint code)
+    int node1 = 0, dof1 = 0, node2 = 0, dof2 = 0;   // 1-based; flag 3: node1 / node2 are the node set and the DOF-list set
+    int index_parameters = 0; // 1-based CONSTRAINT PARAMETERS block (0 = none)
+};
+
 struct ElementGroup {         // one PARAMETERS/PROPERTIES/CONNECTIVITY block of ELEMENTS, USER
     int flag = 0, n_nodes = 8, n_states = 0;
     int prop_index = 0, n_props = 0;
@@ -62,6 +68,8 @@ struct Model {
     std::vector<NamedSet> nodesets, elementsets;
     std::vector<PrescribedDof> prescribed_dofs, prescribed_forces;
     std::vector<SubroutineParameters> subroutine_parameters;
+    std::vector<Constraint> constraints;                        // CONSTRAINTS block
+    std::vector<SubroutineParameters> constraint_parameters;    // CONSTRAINT PARAMETERS blocks
     // current_step_number of module Staticstepparameters: the reference's user hooks read it as a global
     // (user_codes/src/user_prescribeddof.f90:7); set by compute_static_step before the loads are evaluated
     mutable int current_step_number = 1;

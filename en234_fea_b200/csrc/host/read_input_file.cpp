@@ -463,8 +463,72 @@ bool parse_boundary(Reader& r) {
                 }
             }
             m.subroutine_parameters.push_back(sp);
-        } else if (kw(L.tok[0], "CONSTRA")) {
-            return r.fail("CONSTRAINTS are outside the supported subset", &L);
+        } else if (kw(L.tok[0], "CONSTRAINTP")) {                      // read_input_file.f90:1067-1098 (tested before CONSTRA)
+            if (L.n() < 2) return r.fail("CONSTRAINT PARAMETERS key was used without a name", &L);
+            SubroutineParameters cp;
+            cp.name = L.tok[1];
+            while (true) {
+                if (!r.next(L)) return r.fail("CONSTRAINT PARAMETERS not terminated");
+                if (kw(L.tok[0], "ENDCONS")) break;
+                for (int k = 0; k < L.n(); ++k) {
+                    if (L.typ[k] == 2) return r.fail("expecting a list of parameters in a CONSTRAINT PARAMETERS block", &L);
+                    cp.values.push_back(to_real(L.tok[k]));
+                }
+            }
+            m.constraint_parameters.push_back(cp);
+        } else if (kw(L.tok[0], "CONSTRA")) {                          // :1429-1541
+            auto param_index = [&](const Line& Q) -> int {             // optional 7th field: name of a parameter block
+                if (Q.n() == 7 && Q.typ[6] == 2)
+                    for (size_t i = 0; i < m.constraint_parameters.size(); ++i)
+                        if (m.constraint_parameters[i].name == Q.tok[6]) return (int)i + 1;
+                return 0;
+            };
+            while (true) {
+                if (!r.next(L)) return r.fail("CONSTRAINTS block was not terminated by an END CONSTRAINTS");
+                if (kw(L.tok[0], "ENDCONS")) break;
+                if (kw(L.tok[0], "CONSTRAINNODEPA")) {                 // CONSTRAIN NODE PAIRS, n, node1|set1, dof1, node2|set2, dof2
+                    if (L.n() < 6) return r.fail("expecting n, node (set), dof, node (set), dof in CONSTRAIN NODE PAIRS", &L);
+                    if (L.typ[2] == 0) {
+                        Constraint c;
+                        c.flag = 1;
+                        c.node1 = to_int(L.tok[2]); c.dof1 = to_int(L.tok[3]); c.node2 = to_int(L.tok[4]); c.dof2 = to_int(L.tok[5]);
+                        m.constraints.push_back(c);
+                    } else {
+                        const int s1 = find_name(m.nodesets, L.tok[2]), s2 = find_name(m.nodesets, L.tok[4]);
+                        if (!s1 || !s2) return r.fail("unknown node set name in CONSTRAIN NODE PAIRS", &L);
+                        const size_t k = (size_t)to_int(L.tok[1]);
+                        if (m.nodesets[s1 - 1].items.size() != k || m.nodesets[s2 - 1].items.size() != k)
+                            return r.fail("the node sets in a CONSTRAIN NODE PAIRS constraint do not have the correct number of nodes", &L);
+                        for (size_t i = 0; i < k; ++i) {
+                            Constraint c;
+                            c.flag = 1;
+                            c.node1 = m.nodesets[s1 - 1].items[i]; c.dof1 = to_int(L.tok[3]);
+                            c.node2 = m.nodesets[s2 - 1].items[i]; c.dof2 = to_int(L.tok[5]);
+                            c.index_parameters = param_index(L);
+                            m.constraints.push_back(c);
+                        }
+                    }
+                } else if (kw(L.tok[0], "TIENO")) {                    // TIE NODES, n, node set, dof1, master node, dof2
+                    if (L.n() < 6) return r.fail("expecting n, node set, dof, master node, dof in TIE NODES", &L);
+                    const int s1 = find_name(m.nodesets, L.tok[2]);
+                    if (!s1) return r.fail("unknown node set name in TIE NODES", &L);
+                    if (m.nodesets[s1 - 1].items.size() != (size_t)to_int(L.tok[1]))
+                        return r.fail("the node set in a TIE NODES constraint does not have the correct number of nodes", &L);
+                    for (int n : m.nodesets[s1 - 1].items) {
+                        Constraint c;
+                        c.flag = 2;
+                        c.node1 = n; c.dof1 = to_int(L.tok[3]); c.node2 = to_int(L.tok[4]); c.dof2 = to_int(L.tok[5]);
+                        c.index_parameters = param_index(L);
+                        m.constraints.push_back(c);
+                    }
+                } else if (kw(L.tok[0], "CONSTRAINNODESET")) {
+                    return r.fail("CONSTRAIN NODE SET calls user code (user_constraint): outside the supported subset; two-node ties "
+                                  "(CONSTRAIN NODE PAIRS, TIE NODES) are supported", &L);
+                } else return r.fail("CONSTRAINTS block was not terminated by an END CONSTRAINTS", &L);
+            }
+            for (const Constraint& c : m.constraints)
+                if (c.node1 < 1 || c.node1 > m.n_nodes || c.node2 < 1 || c.node2 > m.n_nodes || c.dof1 < 1 || c.dof1 > 3 || c.dof2 < 1 ||
+                    c.dof2 > 3) return r.fail("constraint: node or DOF out of range");
         } else if (kw(L.tok[0], "ENDBOUN")) return true;
         else return r.fail("unknown key in BOUNDARY CONDITIONS block", &L);
     }

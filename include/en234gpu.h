@@ -209,6 +209,19 @@ int en234gpu_get_rhs(en234gpu_handle h, double* rhs /*3N*/, double* diag /*3N or
 /* y = A x with the assembled (method 0) or matrix-free (method 1) operator, for tests */
 int en234gpu_apply_operator(en234gpu_handle h, int method, const double* x, double* y);
 
+/* ---- two-node tie constraints (CONSTRAINTS block: CONSTRAIN NODE PAIRS / TIE NODES, constraint_list flag 1 / 2)
+ * Replaces the Lagrange-multiplier rows the reference appends to the equation system (src/solver_direct.f90:292-328; same
+ * block in src/solver_conjugate_gradient.f90:263-296) and their update after a solve (:967-969).  dof1 / dof2: 0-based DOF
+ * numbers, constraint k demands u[dof1[k]] = u[dof2[k]].  After this call, assemble / apply_boundaryconditions / solve treat
+ * the system exactly as the reference does — rows of tied DOFs carry -/+ lambda, rforce = -rhs, the three norms of the Newton
+ * log include the multiplier rows and the multiplier corrections — but the solve eliminates every tied group onto one unknown
+ * inside the PCG loop instead of factorising the indefinite saddle-point matrix (en234_fea_b200/csrc/en234gpu_ties.cuh).
+ * One device, assembled operator, symmetric stiffness; a group may contain one prescribed DOF (the others follow it).
+ * Returns non-zero for loops of constraints or two prescribed DOFs tied together.  n_ties = 0 removes the constraints. */
+int en234gpu_set_ties(en234gpu_handle h, int n_ties, const int* dof1, const int* dof2);
+/* lagrange_multipliers(1:n_constraints) of module Boundaryconditions after the last solve */
+int en234gpu_get_lagrange_multipliers(en234gpu_handle h, int n_ties, double* out);
+
 /* ---- multi-GPU (one handle per process/GPU; element partitions with shared-node halo sums)
  * neighbours: for each neighbour rank its shared nodes as LOCAL 0-based node indices, listed in the same
  * (global-node-number) order on both sides.  owned[n_nodes]: 1 if this rank owns the node (exactly one

@@ -19,6 +19,7 @@ struct System {
     StepLog log;
 };
 template <class T> void assign(std::vector<T>& v, const T* p, long n) { v.assign(p, p + n); }
+std::vector<double> g_last_lagrange;
 }  // namespace
 
 extern "C" {
@@ -36,6 +37,7 @@ int or_model_set_int(void* h, const char* name, const int* p, long n) {
     VI(history_ptr) VI(nodeset_ptr) VI(nodeset_nodes) VI(elementset_ptr) VI(elementset_elements)
     VI(pdof_flag) VI(pdof_dof) VI(pdof_node) VI(pdof_nodeset) VI(pdof_history) VI(pdof_rate) VI(pdof_subparam) VI(subparam_ptr)
     VI(pforce_flag) VI(pforce_dof) VI(pforce_node) VI(pforce_nodeset) VI(pforce_history)
+    VI(con_node1) VI(con_dof1) VI(con_node2) VI(con_dof2)
     VI(node_order) VI(dload_flag) VI(dload_elset) VI(dload_face) VI(dload_history) VI(dload_val_ptr)
     SI(n_nodes) SI(n_elements) SI(nodes_per_element) SI(max_no_steps) SI(solvertype) SI(nonlinear) SI(max_newton_iterations)
     SI(unsymmetric) SI(abaqusformat) SI(max_cg_iterations) SI(gps_renumber) SI(cg_apply_nodal_forces)
@@ -81,6 +83,11 @@ int or_model_finalize(void* h) {
     if (m.dload_val_ptr.empty()) m.dload_val_ptr.assign(m.dload_flag.size() + 1, 0);
     for (int c : m.connectivity)
         if (c < 1 || c > N) return 3;
+    const size_t nc = m.con_node1.size();
+    if (m.con_dof1.size() != nc || m.con_node2.size() != nc || m.con_dof2.size() != nc) return 7;
+    for (size_t k = 0; k < nc; ++k)
+        if (m.con_node1[k] < 1 || m.con_node1[k] > N || m.con_node2[k] < 1 || m.con_node2[k] > N || m.con_dof1[k] < 1 ||
+            m.con_dof1[k] > 3 || m.con_dof2[k] < 1 || m.con_dof2[k] > 3) return 7;
     return 0;
 }
 
@@ -359,7 +366,14 @@ int or_run_static(void* model, double* dof_total, double* rforce, double* svars,
     info[0] = log.n_steps_completed; info[1] = log.n_cutbacks; info[2] = nr; info[3] = nc;
     info[4] = log.profile_neq; info[5] = log.profile_bwmax; info[6] = log.profile_bwmean;
     info[7] = log.profile_bwrms; info[8] = log.profile_size; info[9] = nl;
+    g_last_lagrange = log.lagrange_multipliers;
     return rc;
+}
+// Lagrange multipliers of the two-node tie constraints after the last or_run_static (module Boundaryconditions keeps them)
+int or_last_lagrange(double* out, int n) {
+    if ((int)g_last_lagrange.size() != n) return 1;
+    for (int i = 0; i < n; ++i) out[i] = g_last_lagrange[i];
+    return 0;
 }
 
 }  // extern "C"

@@ -16,14 +16,22 @@ static inline int colheight(const Skyline& s, int j) { return (int)(s.jp[j] - co
 // compute_profile (solver_direct.f90:1252-1360): equations numbered in node_order, 3 per node;
 // column height = max over elements of (eq - smallest eq on the element).
 void compute_profile(const Model& m, const std::vector<int>& node_order, Skyline& s, StepLog* log) {
-    const int neq = m.ndof();
+    // constraints: one extra equation each, ieqs[length_dofs + nc] (:1252-1266).  The reference orders them with the nodes
+    // (the Gibbs-Poole-Stockmeyer pass treats a constraint as a node); here node_order may list n_nodes + n_constraints
+    // entries (an entry >= n_nodes is constraint entry - n_nodes), otherwise the constraint equations follow all DOFs.
+    const int ncon = m.n_constraints();
+    const int neq = m.ndof() + ncon;
     s.neq = neq;
     s.ieqs.assign(neq, 0);
+    s.lagrange_multipliers.assign(ncon, 0.0);
     int e = 0;
-    for (int i = 0; i < m.n_nodes; ++i) {
+    const bool with_con = (int)node_order.size() == m.n_nodes + ncon;
+    for (int i = 0; i < (with_con ? m.n_nodes + ncon : m.n_nodes); ++i) {
         int n = node_order[i];
-        for (int j = 0; j < 3; ++j) s.ieqs[3 * n + j] = e++;
+        if (n < m.n_nodes) for (int j = 0; j < 3; ++j) s.ieqs[3 * n + j] = e++;
+        else s.ieqs[m.ndof() + n - m.n_nodes] = e++;
     }
+    if (!with_con) for (int nc = 0; nc < ncon; ++nc) s.ieqs[m.ndof() + nc] = e++;
     std::vector<long long> h(neq, 0);
     const int npe = m.nodes_per_element;
     for (int lmn = 0; lmn < m.n_elements; ++lmn) {
@@ -39,6 +47,12 @@ void compute_profile(const Model& m, const std::vector<int>& node_order, Skyline
                 h[q] = std::max<long long>(h[q], q - mineq);
             }
         }
+    }
+    for (int nc = 0; nc < ncon; ++nc) {                       // two-node ties :1296-1317
+        const int q[3] = {s.ieqs[3 * (m.con_node1[nc] - 1) + m.con_dof1[nc] - 1], s.ieqs[3 * (m.con_node2[nc] - 1) + m.con_dof2[nc] - 1],
+                          s.ieqs[m.ndof() + nc]};
+        const int mineq = std::min(q[0], std::min(q[1], q[2]));
+        for (int k = 0; k < 3; ++k) h[q[k]] = std::max<long long>(h[q[k]], q[k] - mineq);
     }
     // statistics exactly as :1339-1351 (first column excluded from max/mean/rms sums, divided by neq)
     long long bwmax = 0;
@@ -101,6 +115,28 @@ int assemble_direct_stiffness(const Model& m, Skyline& s, const double* dof_tota
                     }
                 }
             }
+        }
+    }
+    // two-node tie constraints :292-328 (the multiplier's diagonal is a penalty-scaled compliance 1e-12 |diag| / neq)
+    if (m.n_constraints() > 0) {
+        double dd = 0.0;
+        for (int n = 0; n < s.neq; ++n) dd += s.diag[n] * s.diag[n];
+        const double diagnorm = std::sqrt(dd) / s.neq;
+        auto upper = [&](int a, int b) -> size_t { return a > b ? (size_t)(s.jp[a] - (a - b)) : (size_t)(s.jp[b] - (b - a)); };
+        for (int nc = 0; nc < m.n_constraints(); ++nc) {
+            const int icol = s.ieqs[m.ndof() + nc];
+            const int iof1 = 3 * (m.con_node1[nc] - 1) + m.con_dof1[nc] - 1, iof2 = 3 * (m.con_node2[nc] - 1) + m.con_dof2[nc] - 1;
+            const double lam = s.lagrange_multipliers[nc];
+            int irow = s.ieqs[iof1];
+            s.rhs[irow] -= lam;
+            s.aupp[upper(icol, irow)] += 1.0;
+            if (s.unsym) s.alow[upper(icol, irow)] += 1.0;
+            irow = s.ieqs[iof2];
+            s.rhs[irow] += lam;
+            s.aupp[upper(icol, irow)] -= 1.0;
+            if (s.unsym) s.alow[upper(icol, irow)] -= 1.0;
+            s.rhs[icol] = dof_total[iof2] + dof_increment[iof2] - dof_total[iof1] - dof_increment[iof1] - lam * 1.e-12 * diagnorm;
+            s.diag[icol] = 1.e-12 * diagnorm;
         }
     }
     // NaN scan :402-415
@@ -443,6 +479,7 @@ void solve_direct(const Model& m, Skyline& s, double* dof_increment, AsmOut& out
     lu_decomposition(s, log);
     backsubstitution(s);
     for (int d = 0; d < m.ndof(); ++d) dof_increment[d] += s.rhs[s.ieqs[d]];
+    for (int nc = 0; nc < m.n_constraints(); ++nc) s.lagrange_multipliers[nc] += s.rhs[s.ieqs[m.ndof() + nc]];   // :967-969
     double nn = 0.0;
     for (int n = 0; n < s.neq; ++n) nn += s.rhs[n] * s.rhs[n];
     out.correction_norm = std::sqrt(nn);

@@ -57,6 +57,12 @@ struct Model {
     std::vector<double> pforce_value;
     std::vector<int> dload_flag, dload_elset, dload_face, dload_history, dload_val_ptr;
     std::vector<double> dload_values;
+    // Two-node tie constraints (constraint_list with flag 1 / 2, Boundaryconditions.f90; CONSTRAIN NODE PAIRS / TIE NODES of the
+    // CONSTRAINTS block, read_input_file.f90:1429-1498): dof1 of node1 equals dof2 of node2, enforced by one Lagrange
+    // multiplier each (solver_direct.f90:294-328).  1-based nodes and DOFs.  General constraints (flag 3) call user code
+    // (user_constraint.f90) and are not restated.
+    std::vector<int> con_node1, con_dof1, con_node2, con_dof2;
+    int n_constraints() const { return (int)con_node1.size(); }
 
     // Static step parameters (Staticstepparameters.f90:5-18, defaults read_input_file.f90:120-129)
     double timestep_initial = 0, timestep_min = 0, timestep_max = 0, max_total_time = 0;
@@ -93,6 +99,7 @@ struct StepLog {
     long long profile_neq = 0, profile_bwmax = 0, profile_bwmean = 0, profile_bwrms = 0, profile_size = 0;
     std::vector<double> lu_dimx, lu_dimn;
     std::vector<int> lu_ifig;
+    std::vector<double> lagrange_multipliers;   // final values (two-node tie constraints)
 };
 
 // ---- elements (or_elements.cpp) -------------------------------------------------------------
@@ -134,6 +141,7 @@ struct Skyline {
     std::vector<double> aupp, diag, rhs;
     std::vector<double> alow;    // lower triangle stored row-wise (unsymmetric_stiffness only, Stiffness.f90:17-28)
     bool unsym = false;
+    std::vector<double> lagrange_multipliers;   // one per constraint (module Boundaryconditions), equation ieqs[ndof + nc]
 };
 void compute_profile(const Model& m, const std::vector<int>& node_order, Skyline& s, StepLog* log);
 void gps_node_order(const Model& m, std::vector<int>& node_order);   // bandwidth_minimizer.f90

@@ -68,10 +68,11 @@ int compute_static_step(const Model& m, std::vector<double>& dof_total, std::vec
     bool cont = true, converged = false;
     double newdt = 0;
     int guard = 0;
+    if (m.solvertype != 1 && m.n_constraints() > 0) return 4;       // constraints: skyline path only in this restatement
     if (m.solvertype == 1) {                                           // direct :31-91
         Skyline s;
         std::vector<int> order(m.n_nodes);
-        if ((int)m.node_order.size() == m.n_nodes) order = m.node_order;
+        if ((int)m.node_order.size() == m.n_nodes || (int)m.node_order.size() == m.n_nodes + m.n_constraints()) order = m.node_order;
         else for (int i = 0; i < m.n_nodes; ++i) order[i] = i;
         compute_profile(m, order, s, &log);
         while (cont) {
@@ -115,6 +116,7 @@ int compute_static_step(const Model& m, std::vector<double>& dof_total, std::vec
             t.DTIME = newdt;
             log.n_steps_completed++;
         }
+        log.lagrange_multipliers = s.lagrange_multipliers;
     } else {                                                           // conjugate gradient :93-160
         CooUpper c;
         initialize_cg_solver(m, c);

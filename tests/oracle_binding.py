@@ -139,7 +139,12 @@ class OracleModel:
                              info, _d(lu), C.c_int(256))
         if rc:
             raise RuntimeError("oracle static step failed rc=%d" % rc)
+        ncon = len(self.arrays.get("con_node1", ()))
+        lam = np.zeros(ncon)
+        if ncon and L.or_last_lagrange(_d(lam), C.c_int(ncon)):
+            raise RuntimeError("oracle: Lagrange multipliers unavailable")
         return {"dof_total": u, "rforce": rf, "newton": newton[:info[2]].copy(), "cg_iterations": cg[:info[3]].copy(),
+                "lagrange_multipliers": lam,
                 "n_steps": int(info[0]), "n_cutbacks": int(info[1]),
                 "profile": [int(info[k]) for k in range(4, 9)], "lu": lu[:info[9]].copy(), "state_variables": sv[:nsv].copy()}
 

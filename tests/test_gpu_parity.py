@@ -834,3 +834,95 @@ def test_regular_hex20_fails_like_the_reference():
     s = ob.OracleSystem(ob.OracleModel(m.arrays(), solvertype=2), 2)
     assert s.assemble(z, z)[2] == 1
     g.close()
+
+
+# ---- two-node tie constraints (CONSTRAINTS block): Lagrange multipliers in the reference, group elimination inside PCG here ----
+TOL_TIE = 2e-9     # the reference regularises every multiplier row with a compliance of 1e-12 |diag| / neq, which the device
+                   # path drops; on these meshes that moves the oracle's displacements by a few 1e-11 of their maximum
+
+
+def _tie_case(text, before_last_node=True):
+    """The oracle's skyline LDU has no pivoting, so the position of the multiplier equations matters to IT (not to the device
+    path): before the last of its two nodes where a body is held by its ties only, after all DOFs where the master is
+    prescribed (a multiplier row placed before its only free DOF would start with the bare 1e-12 compliance as its pivot)."""
+    import meshes
+    m = Model.from_text(text)
+    a = m.arrays()
+    ref = (ob.OracleModel(a, node_order=meshes.order_with_constraints(a)) if before_last_node else ob.OracleModel(a)).run_static()
+    return m, ref
+
+
+def _same_newton_history(res, ref, rtol=1e-6):
+    assert res["newton"].shape == ref["newton"].shape
+    k = ref["newton"][:, 7] == 0                               # records before convergence: norms well above round-off
+    assert np.allclose(res["newton"][k, 2:5], ref["newton"][k, 2:5], rtol=rtol, atol=0)
+    # every record: correction norm (it contains the multiplier corrections) and generalized force norm (multiplier rows)
+    assert np.allclose(res["newton"][:, 2:4], ref["newton"][:, 2:4], rtol=rtol, atol=0)
+    assert np.array_equal(res["newton"][:, 7], ref["newton"][:, 7])
+
+
+@pytest.mark.parametrize("use_host_api", [False, True])
+def test_tied_cut_block_equals_uncut_block_and_oracle(use_host_api):
+    """A block cut along a node plane, the two sides tied node to node in all three DOFs (CONSTRAIN NODE PAIRS over node sets):
+    the device path (tied groups reduced onto one unknown inside PCG) gives the displacements of the UNCUT block to solver
+    accuracy, and the oracle's Lagrange-multiplier solution (skyline LDU of the saddle-point system) within TOL_TIE; multipliers,
+    reaction forces and the Newton log (whose norms run over the multiplier rows too) agree with the oracle's."""
+    import meshes
+    text, info = meshes.tied_block_text(5, 4, 3, cut=2)
+    m, ref = _tie_case(text)
+    g = GpuSystem(m)
+    res = g.run_static(method=0, use_host_api=use_host_api)
+    m0 = Model.from_text(meshes.tied_block_text(5, 4, 3, cut=None)[0])
+    g0 = GpuSystem(m0)
+    res0 = g0.run_static(method=0)
+    n0 = 3 * info["n_orig"]
+    assert relmax(res["dof_total"][:n0], res0["dof_total"]) < 1e-12
+    for o, c in info["copy"].items():
+        assert np.abs(res["dof_total"][3 * (o - 1):3 * o] - res["dof_total"][3 * (c - 1):3 * c]).max() <= 1e-15 * np.abs(res0["dof_total"]).max()
+    assert relmax(res["dof_total"], ref["dof_total"]) < TOL_TIE
+    assert relmax(res["rforce"], ref["rforce"]) < TOL_TIE
+    assert relmax(res["lagrange_multipliers"], ref["lagrange_multipliers"]) < 1e-7
+    nc = len(info["copy"])
+    assert abs(res["lagrange_multipliers"][2 * nc:].sum() - 0.01 * len(info["xmax"])) < 1e-12     # the ties carry the whole load
+    _same_newton_history(res, ref)
+    with pytest.raises(RuntimeError, match="assembled operator"):
+        g.run_static(method=1)
+    g.close(); g0.close()
+
+
+def test_tie_nodes_face_follows_master_node_forces_and_prescribed_master():
+    """TIE NODES: DOF 1 of every node of the face x = max follows the first node of that face.  (a) nodal forces on the face;
+    (b) the master's DOF is PRESCRIBED over two steps (the tied group then follows a prescribed root: nothing is solved for it,
+    the multipliers carry the reactions).  Both against the oracle's multiplier solution."""
+    import meshes
+    for kw in ({"force": (0.02, 0.0, -0.01)}, {"pull": 0.05, "steps": 2}):
+        text, info = meshes.tied_block_text(4, 3, 3, tie_face_dof=1, **kw)
+        m, ref = _tie_case(text, before_last_node=False)
+        g = GpuSystem(m)
+        res = g.run_static(method=0)
+        u = res["dof_total"]
+        face = np.array(info["xmax"]) - 1
+        assert np.abs(u[3 * face] - u[3 * face[0]]).max() <= 1e-15 * np.abs(u).max()             # exactly tied
+        if "pull" in kw:
+            assert abs(u[3 * face[0]] - 0.05) < 1e-15
+        assert relmax(u, ref["dof_total"]) < TOL_TIE
+        assert relmax(res["rforce"], ref["rforce"]) < TOL_TIE
+        assert relmax(res["lagrange_multipliers"], ref["lagrange_multipliers"]) < 1e-7
+        assert res["n_steps"] == ref["n_steps"] == kw.get("steps", 1)
+        _same_newton_history(res, ref)
+        g.close()
+
+
+def test_tie_errors_loops_and_doubly_prescribed_groups():
+    m = Model.from_text(synthetic_block_input(3, jitter=0.1))
+    g = GpuSystem(m)
+    with pytest.raises(RuntimeError, match="loop"):
+        g.set_ties([40, 41, 40], [41, 44, 44])
+    with pytest.raises(RuntimeError, match="itself"):
+        g.set_ties([40], [40])
+    g.set_ties([0], [12])          # nodes 1 and 5 (DOFs 0 and 12) both lie on the clamped face x = 0
+    with pytest.raises(RuntimeError, match="two prescribed DOFs"):
+        g.run_static(method=0)
+    g.set_ties([], [])
+    g.run_static(method=0)
+    g.close()

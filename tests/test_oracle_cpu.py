@@ -921,6 +921,44 @@ def test_device_projection_kernel_c3d8_source_compiled_for_the_host(emul_kernels
     assert not want[:, 6:].any() and want[:, 4].any() and want[:, 5].any()
 
 
+def test_tie_constraints_oracle_cut_block_equals_uncut_block():
+    """CONSTRAINTS block (CONSTRAIN NODE PAIRS / TIE NODES, read_input_file.f90:1429-1498) through the product's parser, and the
+    oracle's Lagrange-multiplier rows (solver_direct.f90:292-328, :967-969): a block cut along a node plane and tied node to
+    node reproduces the uncut block (to the compliance the reference puts on the multiplier rows), the multipliers carry the
+    load across the cut, the correction norm counts the multiplier corrections.  No reference output exists for constraints
+    (no shipped input uses them): this property is what pins the restatement."""
+    import meshes
+    text, info = meshes.tied_block_text(4, 3, 3, cut=2)
+    m = Model.from_text(text)
+    a = m.arrays()
+    nc = len(info["copy"])
+    assert a["con_node1"].size == 3 * nc and set(a["con_dof1"]) == {1, 2, 3}
+    assert np.array_equal(a["con_node1"][:nc], sorted(info["copy"])) and np.array_equal(a["con_node2"][:nc], [info["copy"][n] for n in sorted(info["copy"])])
+    res = ob.OracleModel(a, node_order=meshes.order_with_constraints(a)).run_static()
+    res0 = ob.OracleModel(Model.from_text(meshes.tied_block_text(4, 3, 3, cut=None)[0]).arrays()).run_static()
+    u, u0 = res["dof_total"], res0["dof_total"]
+    assert np.abs(u[:u0.size] - u0).max() < 2e-10 * np.abs(u0).max()
+    for o, c in info["copy"].items():
+        assert np.abs(u[3 * (o - 1):3 * o] - u[3 * (c - 1):3 * c]).max() < 1e-10 * np.abs(u0).max()    # = compliance x multiplier
+    lam = res["lagrange_multipliers"]
+    assert abs(lam[2 * nc:].sum() - 0.01 * len(info["xmax"])) < 1e-10 and abs(lam[:nc].sum()) < 1e-10
+    assert res["newton"].shape == res0["newton"].shape == (1, 8) and res["newton"][0, 7] == 1
+    assert res["newton"][0, 2] > 2 * res0["newton"][0, 2]                    # |du, dlambda| against |du|
+    # TIE NODES: 15 followers of one master node; a prescribed master is allowed
+    text, info = meshes.tied_block_text(3, 3, 3, tie_face_dof=1, pull=0.05, steps=2)
+    m = Model.from_text(text)
+    a = m.arrays()
+    assert a["con_node1"].size == 15 and np.all(a["con_node2"] == info["master"])
+    res = ob.OracleModel(a).run_static()                 # multiplier equations after all DOFs (the followers are held by the mesh)
+    face = np.array(info["xmax"]) - 1
+    # the followers trail the master by compliance x multiplier = 1e-12 |diag| / neq x lambda (about 1e-11 here)
+    assert res["n_steps"] == 2 and np.abs(res["dof_total"][3 * face] - 0.05).max() < 5e-11 and res["newton"].shape[0] == 2
+    # general constraints call user code: refused by name
+    bad = text.replace("  TIE NODES, 15, followers, 1, %d, 1" % info["master"], "  CONSTRAIN NODE SET, 15, followers, followers")
+    with pytest.raises(ValueError, match="user_constraint"):
+        Model.from_text(bad)
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """bench.py --impl reference (the CPU arm the driver runs beside the CUDA arm) on a small block: one JSON line with the
     contract keys, on rank 0 only."""

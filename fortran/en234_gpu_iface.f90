@@ -132,6 +132,23 @@ module en234_gpu_iface
             import :: c_int
             integer(c_int) :: en234gpu_device_count
         end function
+        ! ---- two-node tie constraints (constraint_list%flag < 3): replaces the Lagrange-multiplier block of
+        ! assemble_direct_stiffness / assemble_conjugate_gradient_stiffness (solver_direct.f90:292-328) and the multiplier update
+        ! of the solve (:967-969).  dof1 / dof2: 0-based positions in dof_total.
+        function en234gpu_set_ties(h, n_ties, dof1, dof2) bind(C, name='en234gpu_set_ties')
+            import :: c_ptr, c_int
+            type(c_ptr), value         :: h
+            integer(c_int), value      :: n_ties
+            integer(c_int), intent(in) :: dof1(*), dof2(*)
+            integer(c_int)             :: en234gpu_set_ties
+        end function
+        function en234gpu_get_lagrange_multipliers(h, n_ties, lagrange_multipliers) bind(C, name='en234gpu_get_lagrange_multipliers')
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value          :: h
+            integer(c_int), value       :: n_ties
+            real(c_double), intent(out) :: lagrange_multipliers(*)
+            integer(c_int)              :: en234gpu_get_lagrange_multipliers
+        end function
         ! ---- several GPUs, one process: same argument lists as the single-GPU calls, whole-mesh arrays
         function en234gpu_create_multi(h, n_parts, devices, n_nodes, n_elements, coords, connectivity, element_flag, &
                                        element_prop_index, element_properties, n_element_properties) &
@@ -196,9 +213,10 @@ contains
         use Types
         use ParamIO
         use Mesh
+        use Boundaryconditions, only : n_constraints, constraint_list
         implicit none
-        integer(c_int), allocatable :: flags(:), propidx(:)
-        integer :: lmn, status
+        integer(c_int), allocatable :: flags(:), propidx(:), tie1(:), tie2(:)
+        integer :: lmn, status, nc
         allocate(flags(n_elements), propidx(n_elements))
         do lmn = 1, n_elements
             flags(lmn) = element_list(lmn)%flag
@@ -207,6 +225,7 @@ contains
         ! all GPUs of the node behind one handle when there are several (the static step then calls the en234gpu_multi_*
         ! twins with the same module arrays), else the single-GPU handle
         gpu_count = en234gpu_device_count()
+        if (n_constraints > 0) gpu_count = 1        ! tie constraints: one device
         if (gpu_count > 1) then
             status = en234gpu_create_multi(gpu_multi_handle, int(gpu_count, c_int), c_null_ptr, int(n_nodes, c_int), &
                                            int(n_elements, c_int), coords, connectivity, flags, propidx, element_properties, &
@@ -220,6 +239,24 @@ contains
             stop
         end if
         deallocate(flags, propidx)
+        if (n_constraints > 0) then
+            ! CONSTRAIN NODE PAIRS / TIE NODES (flag 1 / 2); general constraints (flag 3, user_constraint) stay on the CPU path
+            allocate(tie1(n_constraints), tie2(n_constraints))
+            do nc = 1, n_constraints
+                if (constraint_list(nc)%flag > 2) then
+                    write(IOW, *) ' *** CONSTRAIN NODE SET constraints are not available on the GPU solver *** '
+                    stop
+                end if
+                tie1(nc) = node_list(constraint_list(nc)%node1)%dof_index + constraint_list(nc)%dof1 - 2
+                tie2(nc) = node_list(constraint_list(nc)%node2)%dof_index + constraint_list(nc)%dof2 - 2
+            end do
+            status = en234gpu_set_ties(gpu_handle, int(n_constraints, c_int), tie1, tie2)
+            if (status /= 0) then
+                write(IOW, *) ' *** Error in the constraint definition (en234gpu_set_ties) *** '
+                stop
+            end if
+            deallocate(tie1, tie2)
+        end if
     end subroutine initialize_gpu_solver
 
     ! The three calls of the static step, on one GPU or on all GPUs of the node (same arguments: whole-mesh module arrays)
@@ -253,6 +290,7 @@ contains
     end function gpu_apply_boundaryconditions
 
     function gpu_solve(method, cg_tolerance, max_cg_iterations, dof_increment, correction_norm, cg_iterations, fail) result(status)
+        use Boundaryconditions, only : n_constraints, lagrange_multipliers
         integer(c_int), value         :: method, max_cg_iterations
         real(c_double), value         :: cg_tolerance
         real(c_double), intent(inout) :: dof_increment(*)
@@ -265,6 +303,9 @@ contains
         else
             status = en234gpu_solve(gpu_handle, method, cg_tolerance, max_cg_iterations, dof_increment, correction_norm, &
                                     cg_iterations, fail)
+            ! module Boundaryconditions keeps the multipliers (solver_direct.f90:967-969); the library owns them between calls
+            if (status == 0 .and. n_constraints > 0) &
+                status = en234gpu_get_lagrange_multipliers(gpu_handle, int(n_constraints, c_int), lagrange_multipliers)
         end if
     end function gpu_solve
 

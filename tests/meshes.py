@@ -86,7 +86,8 @@ def input_text(shape, nx, ny, nz, jitter=0.15, E=100.0, nu=0.3, solver="CONJUGAT
 
 
 def tied_block_text(nx, ny, nz, cut=None, jitter=0.15, E=100.0, nu=0.3, seed=11, solver="DIRECT, NONLINEAR, 1.d-10, 6",
-                    tie_face_dof=None, force=(0.0, 0.0, -0.01), steps=1, cg_tolerance=1e-26, cg_maxit=20000, pull=None):
+                    tie_face_dof=None, force=(0.0, 0.0, -0.01), steps=1, cg_tolerance=1e-26, cg_maxit=20000, pull=None,
+                    element="1001", props=None):
     """hex8 block as literal `.in` text with the CONSTRAINTS block of the reference's input format
     (read_input_file.f90:1429-1541).
     cut = i: the node plane x-index i is DUPLICATED — elements right of it use the copies — and the two sides are tied
@@ -126,8 +127,8 @@ def tied_block_text(nx, ny, nz, cut=None, jitter=0.15, E=100.0, nu=0.3, seed=11,
     xmax = [nid(nx, j, k) for k in range(nz + 1) for j in range(ny + 1)]
     t = ["MESH", " NODES", "  PARAMETERS, 3, 3, 1", "  DISPLACEMENT DOF, 1, 2, 3", "  COORDINATES"]
     t += ["   %d, %.17g, %.17g, %.17g" % (n + 1, p[0], p[1], p[2]) for n, p in enumerate(X)]
-    t += ["  END COORDINATES", " END NODES", " ELEMENTS, USER", "  PARAMETERS, 8, 0, 1001", "  PROPERTIES",
-          "   %.17g" % E, "   %.17g" % nu, "  END PROPERTIES", "  CONNECTIVITY"]
+    t += ["  END COORDINATES", " END NODES", " ELEMENTS, USER", "  PARAMETERS, 8, 0, %s" % element, "  PROPERTIES"]
+    t += ["   %.17g" % v for v in (props if props is not None else (E, nu))] + ["  END PROPERTIES", "  CONNECTIVITY"]
     t += ["   " + ", ".join([str(e + 1)] + [str(n) for n in c]) for e, c in enumerate(conn)]
     t += ["  END CONNECTIVITY", " END ELEMENTS", "END MESH", "BOUNDARY CONDITIONS", " HISTORY, ramp", "  0.d0, 0.d0",
           "  %d.d0, 1.d0" % steps, " END HISTORY"]

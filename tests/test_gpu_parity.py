@@ -926,3 +926,25 @@ def test_tie_errors_loops_and_doubly_prescribed_groups():
     g.set_ties([], [])
     g.run_static(method=0)
     g.close()
+
+
+def test_tied_face_on_neohookean_block_same_newton_history():
+    """Tie constraints inside a NONLINEAR analysis: neo-Hookean user elements (U2), the face x = max tied in DOF 1 to a master
+    node that is pulled by 8 % over two steps.  Every Newton iteration re-assembles the tangent, adds -/+ lambda to the tied
+    rows and solves the reduced system; the records (whose norms include the multiplier rows and corrections) follow the
+    oracle's Lagrange-multiplier solution."""
+    import meshes
+    text, info = meshes.tied_block_text(4, 3, 3, tie_face_dof=1, pull=0.32, steps=2, element="U2", props=[1.0, 200.0],
+                                        solver="DIRECT, NONLINEAR, 1.d-7, 15")
+    m, ref = _tie_case(text, before_last_node=False)
+    g = GpuSystem(m)
+    res = g.run_static(method=0)
+    assert res["n_steps"] == ref["n_steps"] == 2 and res["newton"].shape == ref["newton"].shape and res["newton"].shape[0] >= 6
+    assert np.array_equal(res["newton"][:, [0, 1, 7]], ref["newton"][:, [0, 1, 7]])
+    big = ref["newton"][:, 5] > 1e-6
+    assert np.allclose(res["newton"][big][:, 2:6], ref["newton"][big][:, 2:6], rtol=1e-5)
+    face = np.array(info["xmax"]) - 1
+    assert np.abs(res["dof_total"][3 * face] - 0.32).max() < 1e-15
+    assert relmax(res["dof_total"], ref["dof_total"]) < 1e-8
+    assert relmax(res["lagrange_multipliers"], ref["lagrange_multipliers"]) < 1e-6
+    g.close()

@@ -650,7 +650,7 @@ static TieTables tie_tables(en234gpu_ctx* c);
 static int ties_after_assemble(en234gpu_ctx* c, double* nodal_force_norm);
 static int ties_after_bc(en234gpu_ctx* c, double* unbalanced);
 static int ties_before_solve(en234gpu_ctx* c);
-static int ties_after_solve(en234gpu_ctx* c, double* dl2);
+static int ties_after_solve(en234gpu_ctx* c, double* sol, double* dl2);
 
 static int finish_norm(en234gpu_ctx* c, const double* part, int n, double* out) {
     k_reduce_to<<<1, VEC_THREADS, 0, c->stream>>>(part, n, &c->S.p->norm2);
@@ -1179,7 +1179,14 @@ static int bicg_allreduce2(en234gpu_ctx* c, double* partA, double* partB, int n)
 // y = A x on all local rows, interface rows halo-summed on partitioned runs
 static int bicg_operator(en234gpu_ctx* c, const double* x, double* y) {
     int np = 0;
+    const int gt = std::max(1, (c->ties.n_tdof + 255) / 256);
+    // tie constraints: the operator of the reduced system, T^T A T (x has zeros on the members of every tied group)
+    if (c->ties.n) k_tie_expand<<<gt, 256, 0, c->stream>>>(tie_tables(c), const_cast<double*>(x), nullptr);
     launch_spmv_rows(c, x, y, 0, c->N, 0, 0, &np);
+    if (c->ties.n) {
+        k_tie_reduce<<<gt, 256, 0, c->stream>>>(tie_tables(c), y, const_cast<double*>(x), nullptr);
+        c->st.kernel_launches += 2;
+    }
     if (c->comm.active) {
         if (comm_halo_sum(c->comm, y, c->stream)) return 1;
         c->st.kernel_launches += c->comm.launches_per_halo;
@@ -1263,6 +1270,7 @@ static int bicgstab_solve(en234gpu_ctx* c, double tol, int maxit, double* correc
         CK(c->bi_z.alloc(n)); CK(c->bi_t.alloc(n)); CK(c->bi_xt.alloc(n)); CK(c->bi_b.alloc(n)); CK(c->bi_S.alloc(1));
         CK(cudaMallocHost((void**)&c->h_bi_S, sizeof(BiScalars)));
     }
+    if (c->ties.n && ties_before_solve(c)) return 1;
     const double tol_run = std::max(tol, 1e-24);
     int total = 0;
     *fail = 0;
@@ -1292,9 +1300,12 @@ static int bicgstab_solve(en234gpu_ctx* c, double tol, int maxit, double* correc
     *iterations = total;
     c->st.last_cg_iterations = total;
     if (!*fail) {
+        double dl2 = 0.0;
+        if (c->ties.n && ties_after_solve(c, c->bi_xt.p, &dl2)) return 1;
         k_add_solution<<<gv, VEC_THREADS, 0, c->stream>>>(n, c->bi_xt.p, c->du.p, owned, c->part2.p);
         c->st.kernel_launches++;
         if (finish_norm(c, c->part2.p, gv, correction_norm)) return 1;
+        if (c->ties.n) *correction_norm = std::sqrt(*correction_norm * *correction_norm + dl2);
     } else *correction_norm = 0.0;
     return phase_end(c, &c->st.solve_ms);
 }
@@ -1386,7 +1397,7 @@ int en234gpu_solve_dev(en234gpu_handle c, int method, double cg_tolerance, int m
     const double cg_err = c->hS->err;
     if (!*fail) {
         double dl2 = 0.0;
-        if (c->ties.n && ties_after_solve(c, &dl2)) return 1;
+        if (c->ties.n && ties_after_solve(c, c->sol.p, &dl2)) return 1;
         k_add_solution<<<c->grid_vec, VEC_THREADS, 0, c->stream>>>(c->ndof, c->sol.p, c->du.p,
                                                                   c->have_owned ? c->owned.p : nullptr, c->part2.p);
         c->st.kernel_launches++;

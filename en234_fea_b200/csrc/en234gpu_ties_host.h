@@ -92,7 +92,8 @@ extern "C" int en234gpu_set_ties(en234gpu_handle c, int n_ties, const int* dof1,
     if (n_ties < 0 || (n_ties > 0 && (!dof1 || !dof2))) return set_err("en234gpu_set_ties: bad arguments");
     if (c->comm.active) return set_err("en234gpu_set_ties: tie constraints are implemented for one device (unpartitioned handle)");
     Ties& t = c->ties;
-    for (auto& g : c->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }      // the PCG iteration changes shape
+    for (auto& g : c->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }      // the PCG / BiCGSTAB iteration changes shape
+    if (c->bi_graph) { cudaGraphExecDestroy(c->bi_graph); c->bi_graph = nullptr; }
     t.reset();
     if (n_ties == 0) return 0;
     for (int k = 0; k < n_ties; ++k) {
@@ -140,8 +141,7 @@ extern "C" int en234gpu_get_lagrange_multipliers(en234gpu_handle c, int n, doubl
 }
 
 static int ties_check_mode(en234gpu_ctx* c) {
-    if (c->mode != EN234_SOLVE_PCG_BSR) return set_err("tie constraints: assembled operator only (EN234_SOLVE_PCG_BSR)");
-    if (c->any_c3d8) return set_err("tie constraints: symmetric stiffness (PCG) only; C3D8 elements use BiCGSTAB");
+    if (c->mode != EN234_SOLVE_PCG_BSR) return set_err("tie constraints: assembled operator only (EN234_SOLVE_PCG_BSR / EN234_SOLVE_BICGSTAB_BSR)");
     if (!c->diag_valid) return set_err("tie constraints need the two-kernel assembly (unset EN234_ASM=rows)");
     return 0;
 }
@@ -210,13 +210,13 @@ static int ties_before_solve(en234gpu_ctx* c) {
 }
 
 // after the PCG loop: corrections of the members, multiplier corrections from the tied rows of rhs - K sol; *dl2 = their sum of squares
-static int ties_after_solve(en234gpu_ctx* c, double* dl2) {
+static int ties_after_solve(en234gpu_ctx* c, double* sol, double* dl2) {
     Ties& t = c->ties;
     const TieTables T = tie_tables(c);
     const int gm = std::max(1, (t.n_tdof + 255) / 256);
-    k_tie_expand_sol<<<gm, 256, 0, c->stream>>>(T, t.mgap.p, c->sol.p);
+    k_tie_expand_sol<<<gm, 256, 0, c->stream>>>(T, t.mgap.p, sol);
     int np = 0;
-    launch_spmv_rows(c, c->sol.p, t.vec.p, 0, c->N, 0, 0, &np, 0, nullptr, false);
+    launch_spmv_rows(c, sol, t.vec.p, 0, c->N, 0, 0, &np, 0, nullptr, false);
     k_tie_rows<<<gm, 256, 0, c->stream>>>(t.n_tdof, t.tdof.p, t.rhs0.p, t.vec.p, t.trow.p);
     c->st.kernel_launches += 2;
     std::vector<double> row(t.n_tdof);

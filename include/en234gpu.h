@@ -216,7 +216,8 @@ int en234gpu_apply_operator(en234gpu_handle h, int method, const double* x, doub
  * the system exactly as the reference does — rows of tied DOFs carry -/+ lambda, rforce = -rhs, the three norms of the Newton
  * log include the multiplier rows and the multiplier corrections — but the solve eliminates every tied group onto one unknown
  * inside the PCG loop instead of factorising the indefinite saddle-point matrix (en234_fea_b200/csrc/en234gpu_ties.cuh).
- * One device, assembled operator, symmetric stiffness; a group may contain one prescribed DOF (the others follow it).
+ * One device, assembled operator (PCG, or BiCGSTAB for an unsymmetric stiffness: the same two wrapper kernels around its
+ * operator); a group may contain one prescribed DOF (the others follow it).
  * Returns non-zero for loops of constraints or two prescribed DOFs tied together.  n_ties = 0 removes the constraints. */
 int en234gpu_set_ties(en234gpu_handle h, int n_ties, const int* dof1, const int* dof2);
 /* lagrange_multipliers(1:n_constraints) of module Boundaryconditions after the last solve */

@@ -948,3 +948,37 @@ def test_tied_face_on_neohookean_block_same_newton_history():
     assert relmax(res["dof_total"], ref["dof_total"]) < 1e-8
     assert relmax(res["lagrange_multipliers"], ref["lagrange_multipliers"]) < 1e-6
     g.close()
+
+
+def test_tied_cut_block_of_c3d8_elements_bicgstab():
+    """Tie constraints with the UNSYMMETRIC solver: the cut-and-tied block made of built-in C3D8 B-bar + UMAT elements
+    (BiCGSTAB with the same expand / reduce wrappers around its operator) against the uncut block on the device and against
+    the oracle's unsymmetric skyline LDU with multiplier rows."""
+    import meshes
+    import re
+
+    def c3d8(text):
+        head = text[:text.index(" ELEMENTS, USER")]
+        conn = text[text.index("  CONNECTIVITY"):]
+        t = (head + " MATERIAL, elastic_umat\n  STATE VARIABLES, 0\n  PROPERTIES\n   100.d0\n   0.3d0\n  END PROPERTIES\n END MATERIAL\n"
+             " ELEMENTS, INTERNAL\n  TYPE, C3D8\n  PROPERTIES, elastic_umat\n" + conn)
+        return re.sub(r" SOLVER, [^\n]*", " SOLVER, DIRECT, NONLINEAR, 1.d-9, 15, UNSYMMETRIC", t)
+
+    text, info = meshes.tied_block_text(4, 3, 3, cut=2, force=(0.0, 0.0, -0.002))
+    m, ref = _tie_case(c3d8(text))
+    assert m.arrays()["unsymmetric"][0] == 1 and m.arrays()["element_flag"][0] == 10003
+    g = GpuSystem(m)
+    res = g.run_static(method=0)
+    m0 = Model.from_text(c3d8(meshes.tied_block_text(4, 3, 3, cut=None, force=(0.0, 0.0, -0.002))[0]))
+    g0 = GpuSystem(m0)
+    res0 = g0.run_static(method=0)
+    n0 = 3 * info["n_orig"]
+    assert relmax(res["dof_total"][:n0], res0["dof_total"]) < 1e-9
+    for o, c in info["copy"].items():
+        assert np.abs(res["dof_total"][3 * (o - 1):3 * o] - res["dof_total"][3 * (c - 1):3 * c]).max() <= 1e-15 * np.abs(res0["dof_total"]).max()
+    assert relmax(res["dof_total"], ref["dof_total"]) < 1e-8
+    assert relmax(res["lagrange_multipliers"], ref["lagrange_multipliers"]) < 1e-6
+    assert res["newton"].shape == ref["newton"].shape and np.array_equal(res["newton"][:, 7], ref["newton"][:, 7])
+    big = ref["newton"][:, 5] > 1e-6
+    assert np.allclose(res["newton"][big][:, 2:5], ref["newton"][big][:, 2:5], rtol=1e-5)
+    g.close(); g0.close()

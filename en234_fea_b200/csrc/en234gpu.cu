@@ -1552,6 +1552,25 @@ int en234gpu_get_svars(en234gpu_handle c, const double* dof_total, const double*
     return 0;
 }
 
+// sum of a host buffer over the ranks of the handle's communicator (post-processing: gathers rank-local nodal fields into
+// whole-mesh arrays for the Tecplot writer of a partitioned run); a handle without a communicator leaves the buffer unchanged
+int en234gpu_comm_allreduce_host(en234gpu_handle c, double* buf, long long n) {
+    if (!c->comm.active || n <= 0) return 0;
+    if (!c->comm.nccl) return set_err("en234gpu_comm_allreduce_host: needs the NCCL communicator (en234gpu_comm_init)");
+    CK(cudaSetDevice(c->device));
+    const long long chunk = std::min<long long>(n, 1LL << 24);
+    DevBuf<double> d;
+    CK(d.alloc((size_t)chunk));
+    for (long long o = 0; o < n; o += chunk) {
+        const long long m = std::min(chunk, n - o);
+        CK(cudaMemcpyAsync(d.p, buf + o, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        if (comm_allreduce_sum(c->comm, d.p, (int)m, c->stream)) return set_err(comm_error());
+        CK(cudaMemcpyAsync(buf + o, d.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
 // print_state's projection of integration-point fields to the nodes (src/printing.f90:457-490): right-hand sides, the
 // 27-point mass matrix written as diag(m,m,m) blocks over the stiffness storage, three fields per Jacobi-PCG pass (or the
 // row-sum lumped matrix).  The stiffness values are overwritten: the next solve needs a fresh assembly.

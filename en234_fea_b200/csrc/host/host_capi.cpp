@@ -476,9 +476,20 @@ int en234host_run_static_part(en234host_model_t w, en234host_part_t p, en234gpu_
     const size_t nd = 3 * l2g.size();
     StepResult r;
     FILE* log = (log_path && p->rank == 0) ? std::fopen(log_path, "w") : nullptr;
+    bool state_file_failed = false;
+    if (w->m.stateprint && !w->m.state_print_path.empty()) {       // every rank projects, rank 0 writes the Tecplot file
+        o.state_print_collective = true;
+        if (p->rank == 0) {
+            o.state_print = std::fopen(w->m.state_print_path.c_str(), "w");
+            state_file_failed = !o.state_print;        // reported after the run: the other ranks are already inside it
+        }
+    }
     int rc = compute_static_step(w->m, h, o, r, log, &g2l, nd);
     if (log) std::fclose(log);
+    if (o.state_print) std::fclose(o.state_print);
     if (rc) g_err = r.error;
+    else if (state_file_failed) { rc = -1; g_err = "cannot open state print file " + w->m.state_print_path; }
+    if (info) info[4] = r.n_state_prints;
     if (dof_total_local && r.dof_total.size() == nd) std::memcpy(dof_total_local, r.dof_total.data(), nd * sizeof(double));
     if (rforce_local && r.rforce.size() == nd) std::memcpy(rforce_local, r.rforce.data(), nd * sizeof(double));
     int nr = 0;

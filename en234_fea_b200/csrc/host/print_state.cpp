@@ -105,9 +105,62 @@ int project_fields(const Model& m, en234gpu_handle h, const std::vector<std::str
 
 int print_state(const Model& m, en234gpu_handle h, double time_end, const double* dof_total, const double* dof_increment,
                 FILE* f, std::string& err) {
-    const int N = m.n_nodes, nf = (int)m.field_variable_names.size();
     std::vector<double> fields;
     if (project_fields(m, h, m.field_variable_names, m.use_lumped_projection_matrix, dof_total, dof_increment, fields, err)) return 1;
+    write_state_zone(m, time_end, dof_total, dof_increment, fields, f);
+    return 0;
+}
+
+// Partitioned run: every rank projects the fields on its part (the projection's right-hand sides and matrix are halo-summed,
+// its solve is the partitioned PCG loop), the rank-local nodal values and DOFs are summed into whole-mesh arrays over the
+// communicator together with a copy count (copies of a shared node agree to rounding: the mean is written), and the rank
+// that holds the open file writes the zone.  Collective: every rank must call it.
+int print_state_partitioned(const Model& m, en234gpu_handle h, double time_end, const double* dof_total_local,
+                            const double* dof_increment_local, const std::vector<int>& g2l, size_t n_local_dof, FILE* f,
+                            std::string& err) {
+    const size_t N = (size_t)m.n_nodes, nloc = n_local_dof / 3;
+    const int nf = (int)m.field_variable_names.size();
+    if (nf > EN234_MAX_FIELDS) { err = "at most " + std::to_string(EN234_MAX_FIELDS) + " FIELD VARIABLES"; return 1; }
+    for (int fl : m.element_flag)
+        if (fl != 1001 && fl != 100000 && fl != EN234_FLAG_C3D8) { err = "no field variables are defined for element type " + std::to_string(fl); return 1; }
+    std::vector<double> local((size_t)nf * nloc, 0.0);
+    if (nf > 0) {
+        const std::vector<int> codes = field_codes(m, m.field_variable_names);
+        int its = 0;
+        if (en234gpu_project_fields(h, nf, codes.data(), m.use_lumped_projection_matrix ? 1 : 0, 0.0, 0, dof_total_local,
+                                    dof_increment_local, local.data(), &its)) { err = en234gpu_last_error(); return 1; }
+    }
+    // rows: nf fields, 3 dof_increment, 3 dof_total, 1 copy count
+    std::vector<double> G((size_t)(nf + 7) * N, 0.0);
+    for (size_t n = 0; n < N; ++n) {
+        const int l = g2l[3 * n];
+        if (l < 0) continue;
+        const size_t ln = (size_t)l / 3;
+        for (int k = 0; k < nf; ++k) G[(size_t)k * N + n] = local[(size_t)k * nloc + ln];
+        for (int i = 0; i < 3; ++i) {
+            G[(size_t)(nf + i) * N + n] = dof_increment_local[3 * ln + i];
+            G[(size_t)(nf + 3 + i) * N + n] = dof_total_local[3 * ln + i];
+        }
+        G[(size_t)(nf + 6) * N + n] = 1.0;
+    }
+    if (en234gpu_comm_allreduce_host(h, G.data(), (long long)G.size())) { err = en234gpu_last_error(); return 1; }
+    if (!f) return 0;
+    std::vector<double> fields((size_t)nf * N), du(3 * N), ut(3 * N);
+    for (size_t n = 0; n < N; ++n) {
+        const double cnt = G[(size_t)(nf + 6) * N + n] > 0.0 ? G[(size_t)(nf + 6) * N + n] : 1.0;
+        for (int k = 0; k < nf; ++k) fields[(size_t)k * N + n] = G[(size_t)k * N + n] / cnt;
+        for (int i = 0; i < 3; ++i) {
+            du[3 * n + i] = G[(size_t)(nf + i) * N + n] / cnt;
+            ut[3 * n + i] = G[(size_t)(nf + 3 + i) * N + n] / cnt;
+        }
+    }
+    write_state_zone(m, time_end, ut.data(), du.data(), fields, f);
+    return 0;
+}
+
+void write_state_zone(const Model& m, double time_end, const double* dof_total, const double* dof_increment,
+                      const std::vector<double>& fields, FILE* f) {
+    const int N = m.n_nodes, nf = (int)m.field_variable_names.size();
     std::string out = " VARIABLES = X,Y,Z";                           // :358-388 (list-directed write: leading blank)
     if (m.print_dof) {
         for (int i = 1; i <= 3; ++i) out += ",DU" + std::to_string(i);
@@ -151,7 +204,6 @@ int print_state(const Model& m, en234gpu_handle h, double time_end, const double
         std::fputs(out.c_str(), f);
     }
     std::fflush(f);
-    return 0;
 }
 
 }  // namespace en234

@@ -23,6 +23,14 @@ int project_fields(const Model& m, en234gpu_handle h, const std::vector<std::str
 int print_state(const Model& m, en234gpu_handle h, double time_end, const double* dof_total, const double* dof_increment,
                 FILE* f, std::string& err);
 
+// the writer alone: whole-mesh DOF arrays and fields[k * n_nodes + n]
+void write_state_zone(const Model& m, double time_end, const double* dof_total, const double* dof_increment,
+                      const std::vector<double>& fields, FILE* f);
+// element partitions (one process per GPU): collective over the ranks; `f` is the open file on the writing rank, null elsewhere
+int print_state_partitioned(const Model& m, en234gpu_handle h, double time_end, const double* dof_total_local,
+                            const double* dof_increment_local, const std::vector<int>& g2l, size_t n_local_dof, FILE* f,
+                            std::string& err);
+
 std::string normalise_path(const std::string& input_name);   // Fileparameters.f90:46-54: backslashes of the .in files
 
 }  // namespace en234

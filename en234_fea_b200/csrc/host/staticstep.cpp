@@ -169,17 +169,17 @@ int compute_static_step(const Model& m, en234gpu_handle h, const StepOptions& op
             en234gpu_download_state(h, dof_increment.data(), res.rforce.data())) { res.error = en234gpu_last_error(); return -1; }
         // state print: first step, every state_print_steps-th step, last step (staticstep.f90:227-231), before the
         // increment is added to dof_total (:81-86); one device only
-        if (m.stateprint && opt.state_print && g2l && !res.warned_no_state_print) {
-            // partitioned run: the field projection is partitioned, the Tecplot writer is not — say so once instead of
-            // silently producing no file (the caller sees n_state_prints = 0)
-            res.warned_no_state_print = true;
-            if (log) std::fprintf(log, "\n *** PRINT STATE is skipped on partitioned (multi-GPU) runs: no state file is written ***\n");
-            std::fprintf(stderr, "en234: PRINT STATE is skipped on partitioned (multi-GPU) runs: no state file is written\n");
+        const bool print_now = t.current_step_number == 1 || (m.state_print_steps > 0 && t.current_step_number % m.state_print_steps == 0) || !cont;
+        if (m.stateprint && opt.state_print_collective && g2l && print_now) {
+            // partitioned run: collective over the ranks (projection on the parts, fields gathered over the communicator);
+            // opt.state_print is the open file on the writing rank and null on the others
+            if (print_state_partitioned(m, h, t.TIME + t.DTIME, res.dof_total.data(), dof_increment.data(), *g2l, ndof, opt.state_print,
+                                        res.error)) return -1;
+            res.n_state_prints++;
         }
         // NB a linear solve that fails inside the Newton loop above forces a cutback here; the reference ignores the flag at
         // that point (staticstep.f90:130) — deliberate deviation, documented in INTEGRATION.md
-        if (m.stateprint && opt.state_print && !g2l &&
-            (t.current_step_number == 1 || (m.state_print_steps > 0 && t.current_step_number % m.state_print_steps == 0) || !cont)) {
+        if (m.stateprint && opt.state_print && !g2l && print_now) {
             if (print_state(m, h, t.TIME + t.DTIME, res.dof_total.data(), dof_increment.data(), opt.state_print, res.error)) return -1;
             res.n_state_prints++;
         }

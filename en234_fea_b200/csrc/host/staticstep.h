@@ -22,6 +22,7 @@ struct StepOptions {
     bool check_linear_cg = false;     // run the re-assemble + convergencecheck loop for LINEAR + CG too
     bool use_host_api = false;        // true: host-buffer entry points (what a Fortran driver binds) each call
     FILE* state_print = nullptr;      // open Tecplot file for the PRINT STATE block (null: state prints are skipped)
+    bool state_print_collective = false;   // partitioned runs: every rank takes part in the state prints, one rank holds the file
 };
 
 struct StepResult {
@@ -30,7 +31,6 @@ struct StepResult {
     std::vector<int> cg_iterations;
     std::vector<double> step_time;
     int n_steps_completed = 0, n_cutbacks = 0, n_state_prints = 0;
-    bool warned_no_state_print = false;
     std::string error;
 };
 

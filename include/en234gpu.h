@@ -229,6 +229,9 @@ int en234gpu_get_lagrange_multipliers(en234gpu_handle h, int n_ties, double* out
  * owner per global node) — dot products and norms count owned DOFs only. */
 int en234gpu_get_unique_id(char* id128);
 int en234gpu_comm_init(en234gpu_handle h, int n_ranks, int rank, const char* id128);
+/* buf[n] (host) becomes its sum over all ranks of the communicator, on every rank (post-processing helper: the Tecplot
+ * writer of a partitioned run gathers the rank-local nodal fields with it).  No-op on an unpartitioned handle. */
+int en234gpu_comm_allreduce_host(en234gpu_handle h, double* buf, long long n);
 int en234gpu_set_partition(en234gpu_handle h, int n_neighbours, const int* neighbour_rank, const int* shared_ptr,
                            const int* shared_nodes, const unsigned char* owned);
 /* Optional peer-memory path for the collectives inside the PCG loop (CUDA IPC over NVLink): halo sums become direct

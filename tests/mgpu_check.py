@@ -19,7 +19,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     only = None                                   # --dynamics-only / --project-only: one section (GPU-minute budget)
-    for flag in ("--dynamics-only", "--project-only", "--c3d8-only", "--static-only"):
+    for flag in ("--dynamics-only", "--project-only", "--c3d8-only", "--static-only", "--print-only"):
         if flag in sys.argv:
             sys.argv.remove(flag)
             only = flag[2:-5]
@@ -69,6 +69,8 @@ def main():
         ok = project_section(rank, world, local, dims, jitter) and ok
     if only in (None, "c3d8"):
         ok = c3d8_section(rank, world, local) and ok
+    if only in (None, "print"):
+        ok = print_section(rank, world, local, dims, jitter) and ok
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
@@ -146,6 +148,55 @@ def c3d8_section(rank, world, local):
                                                           res["cg_iterations"].tolist(), ref["cg_iterations"].tolist(), "OK" if good else "FAIL"), flush=True)
         ok = good
         g1.close()
+    dist.barrier()
+    g.close()
+    return ok
+
+
+def print_section(rank, world, local, dims, jitter):
+    """PRINT STATE on a partitioned run: every rank projects the fields on its part, rank 0 gathers them over the communicator
+    and writes ONE Tecplot file; compared number by number with the file of the same analysis on one GPU."""
+    import tempfile
+    names = ["S11", "S22", "S33", "S12", "S13", "S23", "SMISES"]
+    tmp = tempfile.gettempdir()
+    paths = [os.path.join(tmp, "en234_mgpu_state_%d_%s.dat" % (world, k)) for k in ("part", "one")]
+    m = Model.from_text(synthetic_block_input(*dims, jitter=jitter, cg_tolerance=1e-26, cg_maxit=20000, load="stretch", steps=2))
+    m.set_state_print(paths[0], field_variables=names, print_dof=True, displaced_mesh=True, displacement_scale_factor=2.0)
+    part = Partition(m, world, rank)
+    g = GpuSystem(m, device=local, part=part)
+    comm_kind = g.setup_distributed()
+    res = g.run_static(method=0)
+    ok = True
+    if rank == 0:
+        m.set_state_print(paths[1], field_variables=names, print_dof=True, displaced_mesh=True, displacement_scale_factor=2.0)
+        g1 = GpuSystem(m, device=local)
+        ref = g1.run_static(method=0)
+        a, b = open(paths[0]).read().splitlines(), open(paths[1]).read().splitlines()
+        same_shape = len(a) == len(b) and res["n_state_prints"] == ref["n_state_prints"] == 2
+        worst, text_same = 0.0, True
+        if same_shape:
+            ncol = 3 + 6 + len(names)
+            scale = None
+            rows_a, rows_b = [], []
+            for la, lb in zip(a, b):
+                if len(la) == 19 * ncol and la[1:19].strip()[0] in "-0123456789":
+                    rows_a.append([float(la[19 * k:19 * k + 19]) for k in range(ncol)])
+                    rows_b.append([float(lb[19 * k:19 * k + 19]) for k in range(ncol)])
+                else:
+                    text_same = text_same and la == lb
+            A, B = np.array(rows_a), np.array(rows_b)
+            scale = np.abs(B).max(axis=0)
+            worst = float((np.abs(A - B).max(axis=0) / np.where(scale > 0, scale, 1.0)).max())
+            same_shape = same_shape and A.shape[0] == 2 * m.n_nodes
+        good = same_shape and text_same and worst < 1e-9
+        print("mgpu_check [%s] world=%d mesh=%s PRINT STATE on the partitioned run: %d zones, %d lines, headers / connectivity identical %s, "
+              "worst column difference %.1e of the column maximum -> %s" % (comm_kind, world, dims, res["n_state_prints"], len(a), text_same, worst,
+                                                                            "OK" if good else "FAIL"), flush=True)
+        ok = good
+        g1.close()
+        for q in paths:
+            if os.path.exists(q):
+                os.remove(q)
     dist.barrier()
     g.close()
     return ok

@@ -209,6 +209,7 @@ inline int comm_arena_finish(Comm& c) {
         return 1;
     }
     c.p2p = true;
+    c.launches_per_halo = c.n_nbr > 0 ? (c.fused ? 2 : 1 + c.n_nbr) : 0;      // push + (one wait-and-total | one wait-and-add per neighbour)
     return 0;
 }
 
@@ -335,10 +336,10 @@ inline int comm_halo_sum_p2p(Comm& c, double* vec, cudaStream_t s) {
 
 inline int comm_halo_sum(Comm& c, double* vec, cudaStream_t s) {
     if (!c.active || c.n_shared == 0) return 0;
-    if (!c.nccl) {
-        if (!c.p2p) { comm_err_ref() = "halo sum: no communicator"; return 1; }
-        return comm_halo_sum_p2p(c, vec, s);
-    }
+    // peer-memory arenas connected: every halo sum goes through them (assembly, boundary conditions, BiCGSTAB, the explicit
+    // dynamic step), not only the PCG loop — two small kernels instead of pack + grouped send/recv + one add per neighbour
+    if (c.p2p) return comm_halo_sum_p2p(c, vec, s);
+    if (!c.nccl) { comm_err_ref() = "halo sum: no communicator"; return 1; }
     NcclApi* api = nccl_api();
     if (!api) return 1;
     k_halo_pack<<<(3 * c.n_shared + 255) / 256, 256, 0, s>>>(c.n_shared, c.d_shared, vec, c.sendbuf);

@@ -902,6 +902,13 @@ static CgVecArgs vec_args(en234gpu_ctx* c, int method, int parity) {
     return V;
 }
 
+// EN234_P2P_TAIL: 1 = the producers' last CTAs push the rank's sums, single-warp wait kernels consume them; 2 = the last
+// CTAs are producer AND consumer (push, wait for the peers, add): no collective kernel for the two all-reduces at all
+static int p2p_tail_mode() {
+    static const int mode = getenv("EN234_P2P_TAIL") ? atoi(getenv("EN234_P2P_TAIL")) : 0;
+    return (mode == 1 || mode == 2) ? mode : 0;
+}
+
 // y = A x on block rows [row0, row1) (assembled operator); partials are written at part[part_off ...]
 static int launch_spmv_rows(en234gpu_ctx* c, const double* x, double* y, int row0, int row1, int part_off, int check_stop,
                             int* n_part, int tail_total = 0, cudaStream_t stream = nullptr, bool pdl = false) {
@@ -911,7 +918,10 @@ static int launch_spmv_rows(en234gpu_ctx* c, const double* x, double* y, int row
     SpmvArgs A;
     A.row0 = row0; A.N = row1; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
     A.partials = c->part.p + part_off; A.S = c->S.p; A.check_stop = check_stop;
-    if (tail_total > 0) { A.tail = (ArenaHdr*)c->comm.arena; A.tail_partials = c->part.p; A.tail_total = tail_total; }
+    if (tail_total > 0) {
+        A.tail = (ArenaHdr*)c->comm.arena; A.tail_partials = c->part.p; A.tail_total = tail_total;
+        if (p2p_tail_mode() == 2) A.tail_out = c->part.p;
+    }
     if (c->spmv_occ == 5) k_spmv<5><<<grid, THREADS, 0, stream>>>(A);
     else if (pdl && c->max_row_blocks <= 32) launch_pdl(k_spmv<4, false, false>, grid, THREADS, stream, A, FusedComm{});
     else if (pdl) launch_pdl(k_spmv<4, true, false>, grid, THREADS, stream, A, FusedComm{});
@@ -1066,7 +1076,7 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
         // EN234_P2P_TAIL=1 (A/B; measured 3 us per iteration slower on 2 B200): the producers' last CTAs reduce their partials
         // and push the rank's sums (the stores cross NVLink during the kernel boundary), the collective kernels in between
         // only wait and add.  Default: single-CTA all-reduce kernels (reduce, push, wait, add).
-        static const bool tail_push = getenv("EN234_P2P_TAIL") && atoi(getenv("EN234_P2P_TAIL")) == 1;
+        const bool tail_push = p2p_tail_mode() != 0, tail_finish = p2p_tail_mode() == 2;
         bool spmv_pushed = false;
         int np = 0;
         if (method == EN234_SOLVE_PCG_BSR && cm.n_interface > 0 && cm.n_interface < c->N) {
@@ -1099,18 +1109,20 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
             np = operator_partials(c, method);
             p2p_halo_fork(c, c->Ap.p, 1);
         }
-        if (spmv_pushed) k_p2p_wait<<<1, 32, 0, c->stream>>>(cm.peers, c->part.p, nullptr, c->S.p);
+        if (spmv_pushed && tail_finish) { /* the last SpMV CTA left the total in part[0] */ }
+        else if (spmv_pushed) k_p2p_wait<<<1, 32, 0, c->stream>>>(cm.peers, c->part.p, nullptr, c->S.p);
         else launch_pdl(k_p2p_allreduce, 1, VEC_THREADS, c->stream, cm.peers, (const double*)c->part.p, np, (const double*)nullptr, 0,
                         c->part.p, (double*)nullptr, (const CgScalars*)c->S.p, 1);
         p2p_halo_join(c);
         CgVecArgs V = vec_args(c, method, parity);
-        if (tail_push) V.tail = (ArenaHdr*)cm.arena;
+        if (tail_push) { V.tail = (ArenaHdr*)cm.arena; V.tail_finish = tail_finish ? 1 : 0; }
         launch_pdl(k_cg_update<false>, c->grid_vec, VEC_THREADS, c->stream, V);
-        if (tail_push) k_p2p_wait<<<1, 32, 0, c->stream>>>(cm.peers, c->part2.p, c->part3.p, c->S.p);
+        if (tail_finish) { /* k_cg_update's last CTA left the totals in part2[0] / part3[0] */ }
+        else if (tail_push) k_p2p_wait<<<1, 32, 0, c->stream>>>(cm.peers, c->part2.p, c->part3.p, c->S.p);
         else launch_pdl(k_p2p_allreduce, 1, VEC_THREADS, c->stream, cm.peers, (const double*)c->part2.p, c->grid_vec,
                         (const double*)c->part3.p, c->grid_vec, c->part2.p, c->part3.p, (const CgScalars*)c->S.p, 1);
         launch_pdl(k_cg_pupdate, c->grid_vec, VEC_THREADS, c->stream, V);
-        c->st.kernel_launches += 4;
+        c->st.kernel_launches += tail_finish ? (spmv_pushed ? 2 : 3) : 4;
         return 0;
     }
     if (c->ties.n) {

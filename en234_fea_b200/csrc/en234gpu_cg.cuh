@@ -25,6 +25,7 @@ struct SpmvArgs {
     ArenaHdr* tail = nullptr;
     const double* tail_partials = nullptr;
     int tail_total = 0;
+    double* tail_out = nullptr;    // EN234_P2P_TAIL=2: the last CTA also waits for the peers' sums and stores the total here
 };
 
 // reduce_partials for partials written by OTHER CTAs of the same launch (last-CTA tails): loads bypass L1
@@ -141,7 +142,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A, FusedComm F 
     if (FUSED && !arrived) arrive();
     const double t = block_sum<THREADS>(dot, red);
     if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
-    if (A.tail) p2p_tail_push<THREADS>(A.tail, &A.tail->tk_spmv, (unsigned)A.tail_total, A.tail_partials, nullptr, A.tail_total, red);
+    if (A.tail) p2p_tail_push<THREADS>(A.tail, &A.tail->tk_spmv, (unsigned)A.tail_total, A.tail_partials, nullptr, A.tail_total, red,
+                                       A.tail_out, nullptr, const_cast<CgScalars*>(A.S));
 }
 
 struct CgVecArgs {
@@ -155,6 +157,7 @@ struct CgVecArgs {
     CgScalars* S;
     int parity;                    // iteration parity (selects S->rz slot)
     FusedComm F;                   // collectives folded into the vector kernels (F.active; en234gpu_p2p.cuh)
+    int tail_finish = 0;           // EN234_P2P_TAIL=2: that CTA also waits for the peers and leaves the totals in part_a[0] / part_b[0]
     ArenaHdr* tail = nullptr;      // separate-kernel collectives: k_cg_update's last CTA pushes the rank's r.r / r.z
 };
 
@@ -275,7 +278,8 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_cg_update(CgVecArgs A) {
     const double s1 = block_sum<VEC_THREADS>(rz, red);
     if (threadIdx.x == 0) { A.part_a[blockIdx.x] = s0; A.part_b[blockIdx.x] = s1; }
     if (!FUSED && A.tail)
-        p2p_tail_push<VEC_THREADS>(A.tail, &A.tail->tk_upd, gridDim.x, A.part_a, A.part_b, (int)gridDim.x, red);
+        p2p_tail_push<VEC_THREADS>(A.tail, &A.tail->tk_upd, gridDim.x, A.part_a, A.part_b, (int)gridDim.x, red,
+                                   A.tail_finish ? A.part_a : nullptr, A.tail_finish ? A.part_b : nullptr, A.S);
     if (FUSED) {
         // last CTA: this all-reduce and halo exchange have been consumed by every CTA -> advance the counters, then reduce
         // the r.r / r.z partials and push them to all ranks (they cross NVLink while k_cg_pupdate is being launched)

@@ -219,7 +219,8 @@ __device__ __forceinline__ void p2p_push2(const PeerSet& P, unsigned long long s
 // launched.  `arena` is the local arena (its device copy of the peer table is used), `ticket` one of its counters.
 template <int NT>
 __device__ __forceinline__ void p2p_tail_push(ArenaHdr* arena, unsigned int* ticket, unsigned int total, const double* partA,
-                                              const double* partB, int n, double* red) {
+                                              const double* partB, int n, double* red, double* outA = nullptr,
+                                              double* outB = nullptr, CgScalars* S = nullptr) {
     __shared__ int s_last;
     if (threadIdx.x == 0) {
         __threadfence();
@@ -233,7 +234,26 @@ __device__ __forceinline__ void p2p_tail_push(ArenaHdr* arena, unsigned int* tic
         a = block_sum<NT>(a, red);
         b = block_sum<NT>(b, red);
         if (threadIdx.x == 0) *ticket = 0;
-        p2p_push2(arena->peers, ld_volatile_u64(&arena->ar_seq) + 1ULL, a, b);
+        const unsigned long long seq = ld_volatile_u64(&arena->ar_seq) + 1ULL;
+        p2p_push2(arena->peers, seq, a, b);
+        if (outA) {
+            // EN234_P2P_TAIL=2: the same CTA is also the consumer half (no collective kernel at all): wait for every rank's
+            // pair, add in rank order, leave the sums where the next kernel reads its single partial
+            const int par = (int)(seq & 1ULL);
+            const int r = threadIdx.x;
+            if (r < arena->peers.n_ranks) { spin_until(&arena->ar_flag[par][r], seq, &arena->error, arena->peers.timeout, S); __threadfence_system(); }
+            __syncthreads();
+            if (r == 0) {
+                double sa = 0.0, sb = 0.0;
+                for (int q = 0; q < arena->peers.n_ranks; ++q) {
+                    sa += *(volatile double*)&arena->ar_val[par][q][0];
+                    sb += *(volatile double*)&arena->ar_val[par][q][1];
+                }
+                *outA = sa;
+                if (outB) *outB = sb;
+                arena->ar_seq = seq;
+            }
+        }
     }
 }
 

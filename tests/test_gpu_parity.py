@@ -689,6 +689,23 @@ def test_explicit_dynamics_vuel_reference_input_with_state_prints(tmp_path):
     g.close()
 
 
+def test_explicit_dynamics_vuel_holeplate_reference_input():
+    """input_files/Abaqus_vuel_holeplate_3d.in as shipped (3,075 VUEL elements, 1000 steps of 0.002, state prints every 20 steps
+    switched off here): the whole run on the device against the oracle's central-difference loop."""
+    m = golden_model("holeplate_3d_vuel.in.gz")
+    a = m.arrays()
+    assert a["explicitdynamicstep"][0] == 1 and a["no_dynamic_steps"][0] == 1000 and m.n_elements == 3075
+    g = GpuSystem(m)
+    res = g.run_dynamic()
+    ref = ob.OracleModel(a).dynamic().steps(1000).get()
+    assert res["steps"] == 1000
+    assert relmax(res["lumped_mass"], ref["lumped_mass"]) < 1e-13
+    for k in ("dof_total", "velocity", "acceleration"):
+        assert relmax(res[k], ref[k]) < 1e-9, k
+    assert np.abs(res["dof_total"]).max() > 0
+    g.close()
+
+
 def test_explicit_dynamics_native_element_with_density_and_tractions():
     """Element 1001 with a DENSITY key (user_element_lumped_mass, el_linelast_3dbasic_dynamic) under the three native
     distributed-load types of traction_boundarycondition_dynamic — VALUE, HISTORY (normalised direction x history) and NORMAL

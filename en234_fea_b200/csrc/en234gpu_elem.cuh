@@ -638,6 +638,9 @@ __global__ void __launch_bounds__(TPE_THREADS, TPE_OCC) k_element_forces_tpe(Ele
     }
 }
 
+#ifndef EN234_GATHER_MINB
+#define EN234_GATHER_MINB 2
+#endif
 struct GatherArgs {
     Mesh M;
     const double* Ke;
@@ -693,7 +696,7 @@ __device__ __forceinline__ void gather_row_generic(const GatherArgs& A, int i, i
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(THREADS, 2) k_gather_rows(GatherArgs A) {
+__global__ void __launch_bounds__(THREADS, EN234_GATHER_MINB) k_gather_rows(GatherArgs A) {
     __shared__ double accs[WARPS * ACC_PER_WARP];
     __shared__ double red[WARPS + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -1181,6 +1181,12 @@ constexpr int BI_CHUNK = 8;     // BiCGSTAB iterations per CUDA-graph launch
 // one entry); returns the number of partials the consumers read
 static int bicg_allreduce2(en234gpu_ctx* c, double* partA, double* partB, int n) {
     if (!c->comm.active) return n;
+    if (c->comm.p2p) {
+        // peer-memory arenas: one single-CTA kernel (reduce, store to every rank, wait, add in rank order)
+        k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(c->comm.peers, partA, n, partB, n, partA, partB, c->S.p, 0);
+        c->st.kernel_launches += 1;
+        return 1;
+    }
     k_reduce2_to<<<1, VEC_THREADS, 0, c->stream>>>(partA, partB, n, partA, partB);
     k_pack2<<<1, 1, 0, c->stream>>>(partA, partB);
     if (comm_allreduce_sum(c->comm, partA, 2, c->stream)) return -1;

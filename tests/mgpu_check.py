@@ -125,7 +125,12 @@ def c3d8_section(rank, world, local):
     part = Partition(m, world, rank)
     g = GpuSystem(m, device=local, part=part)
     comm_kind = g.setup_distributed()
+    import time
+    t0 = time.perf_counter()
     res = g.run_static(method=0)
+    t_part = time.perf_counter() - t0
+    st = g.stats()
+    last_part = 1e3 * st.solve_ms / max(1, st.last_cg_iterations)
     l2g = part.ints("local_to_global_node").astype(np.int64)
     ldof = (3 * l2g[:, None] + np.arange(3)).ravel()
     acc = torch.zeros(3 * m.n_nodes, dtype=torch.float64, device="cuda")
@@ -138,14 +143,21 @@ def c3d8_section(rank, world, local):
     ok = True
     if rank == 0:
         g1 = GpuSystem(m, device=local)
+        t0 = time.perf_counter()
         ref = g1.run_static(method=0)
+        t_one = time.perf_counter() - t0
+        st1 = g1.stats()
+        print("   last solve: %.1f us per BiCGSTAB iteration on %d GPUs (device time), %.1f on one" %
+              (last_part, world, 1e3 * st1.solve_ms / max(1, st1.last_cg_iterations)), flush=True)
         eu = np.abs(ug - ref["dof_total"]).max() / np.abs(ref["dof_total"]).max()
         same = res["newton"].shape == ref["newton"].shape
         rel = np.abs(res["newton"][:, 2:5] - ref["newton"][:, 2:5]).max() / np.abs(ref["newton"][:, 2:5]).max() if same else np.inf
         good = same and eu < 1e-8 and rel < 1e-5
         print("mgpu_check [%s] world=%d golden C3D8 + UMAT hole plate (BiCGSTAB on partitions): %d Newton records, norms agree to %.1e, "
-              "u err %.2e, BiCGSTAB its %s vs %s -> %s" % (comm_kind, world, res["newton"].shape[0], rel, eu,
-                                                          res["cg_iterations"].tolist(), ref["cg_iterations"].tolist(), "OK" if good else "FAIL"), flush=True)
+              "u err %.2e, BiCGSTAB its %s vs %s, %.0f us per iteration on %d GPUs vs %.0f on one (whole step / iterations) -> %s"
+              % (comm_kind, world, res["newton"].shape[0], rel, eu, res["cg_iterations"].tolist(), ref["cg_iterations"].tolist(),
+                 1e6 * t_part / max(1, int(res["cg_iterations"].sum())), world, 1e6 * t_one / max(1, int(ref["cg_iterations"].sum())),
+                 "OK" if good else "FAIL"), flush=True)
         ok = good
         g1.close()
     dist.barrier()

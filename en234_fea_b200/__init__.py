@@ -2,4 +2,4 @@
 
 Layout: csrc/ (CUDA kernels + C ABI, C++ host driver), api.py (ctypes glue for tests and bench).
 """
-from .api import GpuSystem, MultiGpuSystem, library_partition, Model, Partition, Stats, synthetic_block_input, gpu_lib, host_lib, user_element_static, uel  # noqa: F401
+from .api import GpuSystem, MultiGpuSystem, library_partition, tie_plan, Model, Partition, Stats, synthetic_block_input, gpu_lib, host_lib, user_element_static, uel  # noqa: F401

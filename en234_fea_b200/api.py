@@ -57,7 +57,7 @@ GPU_SYMBOLS = [
     "en234gpu_multi_zero_increment_dev", "en234gpu_multi_download_state", "en234gpu_multi_n_parts",
     "en234gpu_multi_part_handle", "en234gpu_multi_part_info", "en234gpu_multi_get_stats",
     "en234gpu_partition_sizes", "en234gpu_partition_arrays",
-    "en234gpu_set_ties", "en234gpu_get_lagrange_multipliers", "en234gpu_comm_allreduce_host",
+    "en234gpu_set_ties", "en234gpu_get_lagrange_multipliers", "en234gpu_comm_allreduce_host", "en234gpu_tie_plan",
 ]
 HOST_SYMBOLS = [
     "en234host_model_read", "en234host_model_from_text", "en234host_model_free", "en234host_last_error",
@@ -587,6 +587,22 @@ class GpuSystem:
         self._ck(gpu_lib().en234gpu_get_lagrange_multipliers(self.h, C.c_int(n), _dp(lam)))
         return lam
 
+
+
+def tie_plan(dof1, dof2, fixed_dof=()):
+    """Elimination plan of en234gpu_set_ties for a prescribed-DOF list (host code of liben234gpu.so; no device needed)."""
+    L = gpu_lib()
+    a, b, f = _i32(dof1), _i32(dof2), _i32(np.asarray(fixed_dof, np.int32))
+    n = a.size
+    sizes = np.zeros(4, np.int32)
+    groot, gptr, gfix, mem = np.zeros(2 * n, np.int32), np.zeros(2 * n + 1, np.int32), np.zeros(2 * n, np.int32), np.zeros(2 * n, np.int32)
+    ptie, pdof = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    if L.en234gpu_tie_plan(C.c_int(n), _ip(a), _ip(b), C.c_int(f.size), _ip(f) if f.size else None, _ip(sizes), _ip(groot), _ip(gptr),
+                           _ip(gfix), _ip(mem), _ip(ptie), _ip(pdof)):
+        raise RuntimeError(L.en234gpu_last_error().decode())
+    ng, nm = int(sizes[0]), int(sizes[1])
+    return {"group_root": groot[:ng].copy(), "group_ptr": gptr[:ng + 1].copy(), "group_fixed": gfix[:ng].copy(),
+            "member_dof": mem[:nm].copy(), "peel_tie": ptie.copy(), "peel_dof": pdof.copy(), "n_touched": int(sizes[2])}
 
 
 def library_partition(connectivity, n_nodes, n_parts, part):

@@ -9,66 +9,69 @@ static TieTables tie_tables(en234gpu_ctx* c) {
     return T;
 }
 
-// Groups of tied DOFs for the current prescribed set: a group with a prescribed member follows that member (its root), every
-// other group is reduced to its smallest DOF.  Also the order in which the multiplier corrections are recovered after a solve.
-static int ties_rebuild_groups(en234gpu_ctx* c) {
-    Ties& t = c->ties;
-    const int nt = t.n_tdof;
+// Groups of tied DOFs for a prescribed set — pure host logic (no device): a group with a prescribed member follows that member
+// (its root), every other group is reduced to its smallest DOF.  Also the order in which the multiplier corrections are
+// recovered after a solve (leaves of every constraint tree first; a prescribed DOF's row carries no information).
+struct TiePlan {
+    std::vector<int> tdof, idx1, idx2;                 // touched DOFs (sorted), index of each constraint's two DOFs in that list
+    std::vector<int> g_root, g_ptr{0}, m_dof, m_root;  // groups: root DOF, members (root excluded, ascending DOF order)
+    std::vector<uint8_t> g_fixed, m_fixed;
+    std::vector<int> peel_tie, peel_leaf;              // recovery order: constraint, index (in tdof) of its leaf end
+    std::string error;
+};
+
+static bool tie_plan(int n, const int* d1, const int* d2, const std::vector<int>& fixdof, TiePlan& P) {
+    P = TiePlan();
+    P.tdof.assign(d1, d1 + n);
+    P.tdof.insert(P.tdof.end(), d2, d2 + n);
+    std::sort(P.tdof.begin(), P.tdof.end());
+    P.tdof.erase(std::unique(P.tdof.begin(), P.tdof.end()), P.tdof.end());
+    const int nt = (int)P.tdof.size();
+    auto index_of = [&](int d) { return (int)(std::lower_bound(P.tdof.begin(), P.tdof.end(), d) - P.tdof.begin()); };
+    P.idx1.resize(n); P.idx2.resize(n);
+    for (int k = 0; k < n; ++k) { P.idx1[k] = index_of(d1[k]); P.idx2[k] = index_of(d2[k]); }
     std::vector<int> parent(nt);
     for (int i = 0; i < nt; ++i) parent[i] = i;
     auto find = [&](int i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; };
-    for (int k = 0; k < t.n; ++k) {
-        const int a = find(t.idx1[k]), b = find(t.idx2[k]);
-        if (a == b) return set_err("tie constraints: constraint " + std::to_string(k + 1) + " closes a loop (redundant constraint)");
+    for (int k = 0; k < n; ++k) {
+        const int a = find(P.idx1[k]), b = find(P.idx2[k]);
+        if (a == b) { P.error = "tie constraints: constraint " + std::to_string(k + 1) + " closes a loop (redundant constraint)"; return false; }
         parent[std::max(a, b)] = std::min(a, b);       // the smallest touched DOF is the representative
     }
     std::vector<uint8_t> fixed(nt, 0);
-    for (int d : c->h_fixdof) {
-        auto it = std::lower_bound(t.h_tdof.begin(), t.h_tdof.end(), d);
-        if (it != t.h_tdof.end() && *it == d) fixed[it - t.h_tdof.begin()] = 1;
+    for (int d : fixdof) {
+        auto it = std::lower_bound(P.tdof.begin(), P.tdof.end(), d);
+        if (it != P.tdof.end() && *it == d) fixed[it - P.tdof.begin()] = 1;
     }
     std::vector<int> root_of(nt, -1);                  // representative -> root index
     for (int i = 0; i < nt; ++i) {
         const int r = find(i);
         if (fixed[i]) {
-            if (root_of[r] >= 0 && fixed[root_of[r]])
-                return set_err("tie constraints: two prescribed DOFs are tied together (DOFs " + std::to_string(t.h_tdof[root_of[r]]) +
-                               " and " + std::to_string(t.h_tdof[i]) + ", 0-based)");
+            if (root_of[r] >= 0 && fixed[root_of[r]]) {
+                P.error = "tie constraints: two prescribed DOFs are tied together (DOFs " + std::to_string(P.tdof[root_of[r]]) + " and " +
+                          std::to_string(P.tdof[i]) + ", 0-based)";
+                return false;
+            }
             root_of[r] = i;
         } else if (root_of[r] < 0) root_of[r] = i;
     }
-    std::vector<int> g_root, g_ptr{0}, m_dof, m_root, gid(nt, -1);
-    std::vector<uint8_t> g_fixed, m_fixed;
+    std::vector<int> gid(nt, -1);
     for (int i = 0; i < nt; ++i) {
         const int r = find(i);
-        if (gid[r] < 0) { gid[r] = (int)g_root.size(); g_root.push_back(t.h_tdof[root_of[r]]); g_fixed.push_back(fixed[root_of[r]]); }
+        if (gid[r] < 0) { gid[r] = (int)P.g_root.size(); P.g_root.push_back(P.tdof[root_of[r]]); P.g_fixed.push_back(fixed[root_of[r]]); }
     }
-    std::vector<std::vector<int>> mem(g_root.size());
-    for (int i = 0; i < nt; ++i) { const int r = find(i); if (root_of[r] != i) mem[gid[r]].push_back(t.h_tdof[i]); }
-    for (size_t g = 0; g < g_root.size(); ++g) {
-        for (int d : mem[g]) { m_dof.push_back(d); m_root.push_back(g_root[g]); m_fixed.push_back(g_fixed[g]); }
-        g_ptr.push_back((int)m_dof.size());
+    std::vector<std::vector<int>> mem(P.g_root.size());
+    for (int i = 0; i < nt; ++i) { const int r = find(i); if (root_of[r] != i) mem[gid[r]].push_back(P.tdof[i]); }
+    for (size_t g = 0; g < P.g_root.size(); ++g) {
+        for (int d : mem[g]) { P.m_dof.push_back(d); P.m_root.push_back(P.g_root[g]); P.m_fixed.push_back(P.g_fixed[g]); }
+        P.g_ptr.push_back((int)P.m_dof.size());
     }
-    const int counts[2] = {(int)g_root.size(), (int)m_dof.size()};
-    t.n_groups = counts[0]; t.n_members = counts[1];
-    CK(cudaMemcpyAsync(t.counts.p, counts, sizeof(counts), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(t.g_root.p, g_root.data(), g_root.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(t.g_ptr.p, g_ptr.data(), g_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(t.g_fixed.p, g_fixed.data(), g_fixed.size(), cudaMemcpyHostToDevice, c->stream));
-    if (!m_dof.empty()) {
-        CK(cudaMemcpyAsync(t.m_dof.p, m_dof.data(), m_dof.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(t.m_root.p, m_root.data(), m_root.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(t.m_fixed.p, m_fixed.data(), m_fixed.size(), cudaMemcpyHostToDevice, c->stream));
-    }
-    CK(cudaStreamSynchronize(c->stream));
-    // recovery order of the multiplier corrections: peel the leaves of every tree (a prescribed DOF's row carries no information)
     std::vector<int> deg(nt, 0);
     std::vector<std::vector<int>> at(nt);
-    for (int k = 0; k < t.n; ++k) { at[t.idx1[k]].push_back(k); at[t.idx2[k]].push_back(k); deg[t.idx1[k]]++; deg[t.idx2[k]]++; }
-    std::vector<uint8_t> done(t.n, 0);
+    for (int k = 0; k < n; ++k) { at[P.idx1[k]].push_back(k); at[P.idx2[k]].push_back(k); deg[P.idx1[k]]++; deg[P.idx2[k]]++; }
+    std::vector<uint8_t> done(n, 0);
     std::vector<int> queue;
     for (int i = 0; i < nt; ++i) if (deg[i] == 1 && !fixed[i]) queue.push_back(i);
-    t.peel_tie.clear(); t.peel_leaf.clear();
     for (size_t q = 0; q < queue.size(); ++q) {
         const int i = queue[q];
         if (deg[i] != 1) continue;
@@ -76,12 +79,53 @@ static int ties_rebuild_groups(en234gpu_ctx* c) {
         for (int kk : at[i]) if (!done[kk]) { k = kk; break; }
         if (k < 0) continue;
         done[k] = 1;
-        t.peel_tie.push_back(k); t.peel_leaf.push_back(i);
-        const int o = t.idx1[k] == i ? t.idx2[k] : t.idx1[k];
+        P.peel_tie.push_back(k); P.peel_leaf.push_back(i);
+        const int o = P.idx1[k] == i ? P.idx2[k] : P.idx1[k];
         deg[i]--; deg[o]--;
         if (deg[o] == 1 && !fixed[o]) queue.push_back(o);
     }
-    if ((int)t.peel_tie.size() != t.n) return set_err("tie constraints: the multipliers cannot be recovered (inconsistent constraint graph)");
+    if ((int)P.peel_tie.size() != n) { P.error = "tie constraints: the multipliers cannot be recovered (inconsistent constraint graph)"; return false; }
+    return true;
+}
+
+// the plan without a device (tests of the host logic): sizes[4] = groups, members, touched DOFs, constraints; arrays may be null
+extern "C" int en234gpu_tie_plan(int n_ties, const int* dof1, const int* dof2, int n_fixed, const int* fixed_dof, int* sizes,
+                                 int* group_root, int* group_ptr, int* group_fixed, int* member_dof, int* peel_tie, int* peel_dof) {
+    if (n_ties <= 0 || !dof1 || !dof2 || !sizes) return set_err("en234gpu_tie_plan: bad arguments");
+    TiePlan P;
+    const std::vector<int> fx(fixed_dof, fixed_dof + (n_fixed > 0 ? n_fixed : 0));
+    if (!tie_plan(n_ties, dof1, dof2, fx, P)) return set_err(P.error);
+    sizes[0] = (int)P.g_root.size(); sizes[1] = (int)P.m_dof.size(); sizes[2] = (int)P.tdof.size(); sizes[3] = n_ties;
+    for (size_t g = 0; g < P.g_root.size(); ++g) {
+        if (group_root) group_root[g] = P.g_root[g];
+        if (group_fixed) group_fixed[g] = P.g_fixed[g];
+    }
+    if (group_ptr) for (size_t g = 0; g < P.g_ptr.size(); ++g) group_ptr[g] = P.g_ptr[g];
+    if (member_dof) for (size_t i = 0; i < P.m_dof.size(); ++i) member_dof[i] = P.m_dof[i];
+    for (int q = 0; q < n_ties; ++q) {
+        if (peel_tie) peel_tie[q] = P.peel_tie[q];
+        if (peel_dof) peel_dof[q] = P.tdof[P.peel_leaf[q]];
+    }
+    return 0;
+}
+
+static int ties_rebuild_groups(en234gpu_ctx* c) {
+    Ties& t = c->ties;
+    TiePlan P;
+    if (!tie_plan(t.n, t.d1.data(), t.d2.data(), c->h_fixdof, P)) return set_err(P.error);
+    const int counts[2] = {(int)P.g_root.size(), (int)P.m_dof.size()};
+    t.n_groups = counts[0]; t.n_members = counts[1];
+    CK(cudaMemcpyAsync(t.counts.p, counts, sizeof(counts), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(t.g_root.p, P.g_root.data(), P.g_root.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(t.g_ptr.p, P.g_ptr.data(), P.g_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(t.g_fixed.p, P.g_fixed.data(), P.g_fixed.size(), cudaMemcpyHostToDevice, c->stream));
+    if (!P.m_dof.empty()) {
+        CK(cudaMemcpyAsync(t.m_dof.p, P.m_dof.data(), P.m_dof.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(t.m_root.p, P.m_root.data(), P.m_root.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(t.m_fixed.p, P.m_fixed.data(), P.m_fixed.size(), cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    t.peel_tie = P.peel_tie; t.peel_leaf = P.peel_leaf;
     t.groups_valid = true;
     t.groups_fixdof = c->h_fixdof;
     return 0;

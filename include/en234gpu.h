@@ -220,6 +220,12 @@ int en234gpu_apply_operator(en234gpu_handle h, int method, const double* x, doub
  * operator); a group may contain one prescribed DOF (the others follow it).
  * Returns non-zero for loops of constraints or two prescribed DOFs tied together.  n_ties = 0 removes the constraints. */
 int en234gpu_set_ties(en234gpu_handle h, int n_ties, const int* dof1, const int* dof2);
+/* The elimination plan of a set of ties for a given prescribed-DOF list, without a device (host logic of en234gpu_set_ties;
+ * used by the CPU tests): sizes[4] = groups, members, touched DOFs, constraints; group_ptr has groups + 1 entries; peel_tie /
+ * peel_dof give, in recovery order, each constraint and the DOF whose equilibrium row yields its multiplier.  Output arrays
+ * may be NULL.  Non-zero (en234gpu_last_error) for loops and for two prescribed DOFs in one group. */
+int en234gpu_tie_plan(int n_ties, const int* dof1, const int* dof2, int n_fixed, const int* fixed_dof, int* sizes,
+                      int* group_root, int* group_ptr, int* group_fixed, int* member_dof, int* peel_tie, int* peel_dof);
 /* lagrange_multipliers(1:n_constraints) of module Boundaryconditions after the last solve */
 int en234gpu_get_lagrange_multipliers(en234gpu_handle h, int n_ties, double* out);
 

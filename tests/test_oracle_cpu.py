@@ -959,6 +959,61 @@ def test_tie_constraints_oracle_cut_block_equals_uncut_block():
         Model.from_text(bad)
 
 
+def test_tie_plan_host_logic_groups_roots_and_multiplier_recovery_order():
+    """Host logic of en234gpu_set_ties (no device): tied groups by union-find, the root of a group (its prescribed member, else
+    its smallest DOF), members in ascending order, and the order in which the multiplier corrections are recovered from the
+    equilibrium rows (row of dof1 = +dlambda, row of dof2 = -dlambda; leaves of every constraint tree first, prescribed DOFs
+    never).  Replays the recovery on a random forest."""
+    from en234_fea_b200 import tie_plan
+    # chain 7-3-9 and a star around 20 with a prescribed centre
+    d1, d2 = [7, 3, 21, 22, 23], [3, 9, 20, 20, 20]
+    P = tie_plan(d1, d2, fixed_dof=[20, 100])
+    assert P["group_root"].tolist() == [3, 20] and P["group_fixed"].tolist() == [0, 1]
+    assert P["group_ptr"].tolist() == [0, 2, 5] and P["member_dof"].tolist() == [7, 9, 21, 22, 23] and P["n_touched"] == 7
+    assert sorted(P["peel_tie"].tolist()) == [0, 1, 2, 3, 4] and 20 not in P["peel_dof"].tolist()
+    with pytest.raises(RuntimeError, match="loop"):
+        tie_plan([1, 2, 3], [2, 3, 1])
+    with pytest.raises(RuntimeError, match="two prescribed"):
+        tie_plan([1, 2], [2, 3], fixed_dof=[1, 3])
+    # random forest: trees grown by attaching new DOFs to existing ones, random orientation of every constraint
+    rng = np.random.default_rng(5)
+    dofs = rng.permutation(400)[:120]
+    a, b, fixed = [], [], []
+    for tree in range(8):
+        nodes = [int(dofs[15 * tree])]
+        for k in range(1, 15):
+            new, old = int(dofs[15 * tree + k]), nodes[rng.integers(len(nodes))]
+            if rng.random() < 0.5:
+                a.append(new); b.append(old)
+            else:
+                a.append(old); b.append(new)
+            nodes.append(new)
+        if tree % 2 == 0:
+            fixed.append(nodes[rng.integers(len(nodes))])
+    a, b = np.array(a), np.array(b)
+    P = tie_plan(a, b, fixed_dof=fixed)
+    assert len(P["group_root"]) == 8 and sorted(P["group_root"][P["group_fixed"] == 1].tolist()) == sorted(fixed)
+    for g in range(8):
+        mem = P["member_dof"][P["group_ptr"][g]:P["group_ptr"][g + 1]]
+        assert np.all(np.diff(mem) > 0) and len(mem) == 14
+        if not P["group_fixed"][g]:
+            assert P["group_root"][g] < mem.min()
+    dl = rng.standard_normal(a.size)
+    row = {}
+    for k in range(a.size):
+        row[int(a[k])] = row.get(int(a[k]), 0.0) + dl[k]
+        row[int(b[k])] = row.get(int(b[k]), 0.0) - dl[k]
+    for f in fixed:
+        row[f] = 0.0                                          # a prescribed row is replaced: no information
+    got = np.zeros(a.size)
+    for k, leaf in zip(P["peel_tie"], P["peel_dof"]):
+        first = int(a[k]) == int(leaf)
+        got[k] = row[int(leaf)] if first else -row[int(leaf)]
+        other = int(b[k]) if first else int(a[k])
+        row[other] += got[k] if first else -got[k]
+    assert np.abs(got - dl).max() < 1e-12
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """bench.py --impl reference (the CPU arm the driver runs beside the CUDA arm) on a small block: one JSON line with the
     contract keys, on rank 0 only."""

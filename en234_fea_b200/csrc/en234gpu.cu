@@ -125,6 +125,9 @@ struct en234gpu_ctx {
     std::vector<int> h_fixdof;   // last prescribed-DOF list (the row subset is rebuilt only when it changes)
     bool diag_valid = false;
     int spmv_occ = 4;
+    int spmv_sym = 0;            // EN234_SPMV_SYM=1: 0 untried, 1 on (index built), -1 not applicable to this matrix
+    DevBuf<unsigned> sym_base;   // per block: offset of the transposed block in val (0xffffffff: read in place)
+    DevBuf<uint8_t> sym_len;     // per block: scalar-row length of the row that stores the transposed block
     int max_row_blocks = 0;      // longest block row (k_spmv drops its tail loop when <= 32)
     bool any_neo = false;
     bool any_c3d8 = false;       // built-in C3D8 continuum elements (all elements of the mesh)
@@ -909,6 +912,33 @@ static int p2p_tail_mode() {
     return (mode == 1 || mode == 2) ? mode : 0;
 }
 
+// index of the symmetric-storage product (k_spmv_sym): built on first use
+static bool spmv_sym_ready(en234gpu_ctx* c) {
+    if (c->spmv_sym != 0) return c->spmv_sym > 0;
+    c->spmv_sym = -1;
+    const bool want = getenv("EN234_SPMV_SYM") && atoi(getenv("EN234_SPMV_SYM")) == 1;      // read once per handle
+    if (!want || c->any_c3d8 || c->max_row_blocks > 32 || c->h_browptr.empty() || 9ULL * (unsigned long long)c->nnzb >= 0xffffffffULL) return false;
+    const std::vector<int>& rp = c->h_browptr;
+    const std::vector<int>& bc = c->h_bcol;
+    std::vector<unsigned> base(bc.size(), 0xffffffffu);
+    std::vector<uint8_t> len(bc.size(), 0);
+    for (int i = 0; i < c->N; ++i)
+        for (int k = rp[i]; k < rp[i + 1] && bc[k] < i; ++k) {
+            const int j = bc[k];
+            const int* b0 = bc.data() + rp[j];
+            const int* b1 = bc.data() + rp[j + 1];
+            const int* it = std::lower_bound(b0, b1, i);
+            if (it == b1 || *it != i) return false;               // pattern not symmetric: keep the full product
+            base[k] = (unsigned)(9ULL * (unsigned long long)rp[j] + 3ULL * (unsigned long long)(it - b0));
+            len[k] = (uint8_t)(3 * (rp[j + 1] - rp[j]));
+        }
+    if (c->sym_base.alloc(base.size()) != cudaSuccess || c->sym_len.alloc(len.size()) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaMemcpy(c->sym_base.p, base.data(), base.size() * sizeof(unsigned), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->sym_len.p, len.data(), len.size(), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    c->spmv_sym = 1;
+    return true;
+}
+
 // y = A x on block rows [row0, row1) (assembled operator); partials are written at part[part_off ...]
 static int launch_spmv_rows(en234gpu_ctx* c, const double* x, double* y, int row0, int row1, int part_off, int check_stop,
                             int* n_part, int tail_total = 0, cudaStream_t stream = nullptr, bool pdl = false) {
@@ -922,7 +952,8 @@ static int launch_spmv_rows(en234gpu_ctx* c, const double* x, double* y, int row
         A.tail = (ArenaHdr*)c->comm.arena; A.tail_partials = c->part.p; A.tail_total = tail_total;
         if (p2p_tail_mode() == 2) A.tail_out = c->part.p;
     }
-    if (c->spmv_occ == 5) k_spmv<5><<<grid, THREADS, 0, stream>>>(A);
+    if (c->mode == EN234_SOLVE_PCG_BSR && check_stop && spmv_sym_ready(c)) k_spmv_sym<4><<<grid, THREADS, 0, stream>>>(A, c->sym_base.p, c->sym_len.p);
+    else if (c->spmv_occ == 5) k_spmv<5><<<grid, THREADS, 0, stream>>>(A);
     else if (pdl && c->max_row_blocks <= 32) launch_pdl(k_spmv<4, false, false>, grid, THREADS, stream, A, FusedComm{});
     else if (pdl) launch_pdl(k_spmv<4, true, false>, grid, THREADS, stream, A, FusedComm{});
     else if (c->max_row_blocks <= 32) k_spmv<4, false><<<grid, THREADS, 0, stream>>>(A);
@@ -1332,6 +1363,7 @@ static int bicgstab_solve(en234gpu_ctx* c, double tol, int maxit, double* correc
 // stop flag is read back after each chunk (iterations after convergence inside a chunk return immediately).  Leaves the
 // final scalars in c->hS.
 static int pcg_run(en234gpu_ctx* c, int method, double cg_tolerance, int max_cg_iterations) {
+    if (method == EN234_SOLVE_PCG_BSR) spmv_sym_ready(c);       // allocates on first use: must not happen inside the capture
     if (!c->graph[method] && build_graph(c, method)) return 1;
     // tolerance / iteration cap are run-time values in device memory (compile-time in modules/Stiffness.f90:35-37)
     CgScalars init{};

@@ -146,6 +146,85 @@ __global__ void __launch_bounds__(THREADS, MINB) k_spmv(SpmvArgs A, FusedComm F 
                                        A.tail_out, nullptr, const_cast<CgScalars*>(A.S));
 }
 
+// Symmetric-storage product (EN234_SPMV_SYM=1): the reference keeps the upper triangle only (modules/Stiffness.f90:17-28;
+// its product visits every stored entry twice, solver_conjugate_gradient.f90:878-883).  Here the assembled block rows stay as
+// they are, but a row READS only its diagonal and upper blocks from its own storage (the tail of each of its three scalar
+// rows); a lower block (i, j), j < i, is taken as the transpose of block (j, i) from row j's storage — 24 contiguous bytes per
+// lane — which row j streamed from HBM a few thousand rows earlier and which is still in L2 when the numbering has a bounded
+// front (structured blocks: one node layer).  HBM traffic per row drops from 27 to 14 blocks; every row still sums its own
+// terms in a fixed order (gather form, no atomics), so the product stays deterministic.  sym_base[block] = offset of the
+// transposed block's first entry (0xffffffff: diagonal / upper block, read in place), sym_len[block] = scalar-row length of
+// row j.  Rows of at most 32 blocks only.
+template <int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_spmv_sym(SpmvArgs A, const unsigned* __restrict__ sym_base,
+                                                            const uint8_t* __restrict__ sym_len) {
+    __shared__ double red[WARPS + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = gridDim.x * WARPS, N = A.N;
+    const int d0 = lane / 3, m0 = lane % 3;
+    const int d1 = (lane + 32) / 3, m1 = (lane + 32) % 3;
+    const int d2 = (lane + 64) / 3, m2 = (lane + 64) % 3;
+    double dot = 0.0;
+    int i = A.row0 + blockIdx.x * WARPS + warp;
+    int rb = 0, re = 0, rbn = 0, ren = 0, c0 = 0, c1 = 0, c2 = 0;
+    unsigned t0 = 0xffffffffu, t1 = 0xffffffffu, t2 = 0xffffffffu;
+    int l0 = 0, l1 = 0, l2 = 0;
+    if (i < N) { rb = __ldg(A.browptr + i); re = __ldg(A.browptr + i + 1); }
+    if (i + W < N) { rbn = __ldg(A.browptr + i + W); ren = __ldg(A.browptr + i + W + 1); }
+    {
+        const int nb = re - rb;
+        if (d0 < nb) { c0 = __ldg(A.bcol + rb + d0); t0 = __ldg(sym_base + rb + d0); l0 = __ldg(sym_len + rb + d0); }
+        if (d1 < nb) { c1 = __ldg(A.bcol + rb + d1); t1 = __ldg(sym_base + rb + d1); l1 = __ldg(sym_len + rb + d1); }
+        if (d2 < nb) { c2 = __ldg(A.bcol + rb + d2); t2 = __ldg(sym_base + rb + d2); l2 = __ldg(sym_len + rb + d2); }
+    }
+    pdl_wait();
+    pdl_trigger();
+    if (A.check_stop && A.S->stop) return;
+    for (; i < N; i += W) {
+        const int nb = re - rb, L = 3 * nb;
+        const double* v = A.val + 9 * (size_t)rb;
+        double x0 = 0.0, x1 = 0.0, x2 = 0.0, a00 = 0.0, a01 = 0.0, a02 = 0.0, a10 = 0.0, a11 = 0.0, a12 = 0.0, a20 = 0.0,
+               a21 = 0.0, a22 = 0.0;
+        if (d0 < nb) {
+            x0 = __ldg(A.x + 3 * c0 + m0);
+            if (t0 == 0xffffffffu) { a00 = __ldcg(v + lane); a10 = __ldcg(v + L + lane); a20 = __ldcg(v + 2 * L + lane); }
+            else { const double* w = A.val + (size_t)t0 + m0 * l0; a00 = __ldcg(w); a10 = __ldcg(w + 1); a20 = __ldcg(w + 2); }
+        }
+        if (d1 < nb) {
+            x1 = __ldg(A.x + 3 * c1 + m1);
+            if (t1 == 0xffffffffu) { a01 = __ldcg(v + lane + 32); a11 = __ldcg(v + L + lane + 32); a21 = __ldcg(v + 2 * L + lane + 32); }
+            else { const double* w = A.val + (size_t)t1 + m1 * l1; a01 = __ldcg(w); a11 = __ldcg(w + 1); a21 = __ldcg(w + 2); }
+        }
+        if (d2 < nb) {
+            x2 = __ldg(A.x + 3 * c2 + m2);
+            if (t2 == 0xffffffffu) { a02 = __ldcg(v + lane + 64); a12 = __ldcg(v + L + lane + 64); a22 = __ldcg(v + 2 * L + lane + 64); }
+            else { const double* w = A.val + (size_t)t2 + m2 * l2; a02 = __ldcg(w); a12 = __ldcg(w + 1); a22 = __ldcg(w + 2); }
+        }
+        const int nbn = ren - rbn;
+        int cn0 = 0, cn1 = 0, cn2 = 0, rb2 = 0, re2 = 0, ln0 = 0, ln1 = 0, ln2 = 0;
+        unsigned tn0 = 0xffffffffu, tn1 = 0xffffffffu, tn2 = 0xffffffffu;
+        if (d0 < nbn) { cn0 = __ldg(A.bcol + rbn + d0); tn0 = __ldg(sym_base + rbn + d0); ln0 = __ldg(sym_len + rbn + d0); }
+        if (d1 < nbn) { cn1 = __ldg(A.bcol + rbn + d1); tn1 = __ldg(sym_base + rbn + d1); ln1 = __ldg(sym_len + rbn + d1); }
+        if (d2 < nbn) { cn2 = __ldg(A.bcol + rbn + d2); tn2 = __ldg(sym_base + rbn + d2); ln2 = __ldg(sym_len + rbn + d2); }
+        if (i + 2 * W < N) { rb2 = __ldg(A.browptr + i + 2 * W); re2 = __ldg(A.browptr + i + 2 * W + 1); }
+        const double y0 = a00 * x0 + a01 * x1 + a02 * x2;
+        const double y1 = a10 * x0 + a11 * x1 + a12 * x2;
+        const double y2 = a20 * x0 + a21 * x1 + a22 * x2;
+        const double yv = warp_sum3(y0, y1, y2, lane);
+        if ((lane & 7) == 0 && lane < 24) {
+            const int r = lane >> 3;
+            A.y[3 * (size_t)i + r] = yv;
+            dot += yv * A.x[3 * (size_t)i + r];
+        }
+        rb = rbn; re = ren; rbn = rb2; ren = re2; c0 = cn0; c1 = cn1; c2 = cn2;
+        t0 = tn0; t1 = tn1; t2 = tn2; l0 = ln0; l1 = ln1; l2 = ln2;
+    }
+    const double t = block_sum<THREADS>(dot, red);
+    if (threadIdx.x == 0) A.partials[blockIdx.x] = t;
+    if (A.tail) p2p_tail_push<THREADS>(A.tail, &A.tail->tk_spmv, (unsigned)A.tail_total, A.tail_partials, nullptr, A.tail_total, red,
+                                       A.tail_out, nullptr, const_cast<CgScalars*>(A.S));
+}
+
 struct CgVecArgs {
     int n;                         // number of DOFs
     const double* rhs;

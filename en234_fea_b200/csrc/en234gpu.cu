@@ -940,11 +940,18 @@ static bool spmv_sym_ready(en234gpu_ctx* c) {
 }
 
 // y = A x on block rows [row0, row1) (assembled operator); partials are written at part[part_off ...]
+// CTA slots the interior-row SpMV of a partitioned run leaves free (EN234_P2P_RESERVE, default 0): its persistent grid
+// otherwise fills every SM until it ends, so the halo push / wait kernels of the side stream could only start after it
+static int p2p_reserve() {
+    static const int n = getenv("EN234_P2P_RESERVE") ? std::max(0, atoi(getenv("EN234_P2P_RESERVE"))) : 0;
+    return n;
+}
+
 static int launch_spmv_rows(en234gpu_ctx* c, const double* x, double* y, int row0, int row1, int part_off, int check_stop,
-                            int* n_part, int tail_total = 0, cudaStream_t stream = nullptr, bool pdl = false) {
+                            int* n_part, int tail_total = 0, cudaStream_t stream = nullptr, bool pdl = false, int reserve = 0) {
     if (!stream) stream = c->stream;
     const int need = (row1 - row0 + WARPS - 1) / WARPS;
-    const int grid = std::max(1, std::min(need, c->grid_spmv));
+    const int grid = std::max(1, std::min(need, std::max(1, c->grid_spmv - reserve)));
     SpmvArgs A;
     A.row0 = row0; A.N = row1; A.browptr = c->browptr.p; A.bcol = c->bcol.p; A.val = c->val.p; A.x = x; A.y = y;
     A.partials = c->part.p + part_off; A.S = c->S.p; A.check_stop = check_stop;
@@ -1118,12 +1125,12 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
             cudaEventRecord(cm.ev_fork, c->stream);
             cudaStreamWaitEvent(cm.side, cm.ev_fork, 0);
             const int g1 = std::max(1, std::min((cm.n_interface + WARPS - 1) / WARPS, c->grid_spmv));
-            const int g2 = std::max(1, std::min((c->N - cm.n_interface + WARPS - 1) / WARPS, c->grid_spmv));
+            const int g2 = std::max(1, std::min((c->N - cm.n_interface + WARPS - 1) / WARPS, std::max(1, c->grid_spmv - p2p_reserve())));
             const int tail_total = tail_push ? g1 + g2 : 0;
             launch_spmv_rows(c, c->p.p, c->Ap.p, 0, cm.n_interface, 0, 1, &n1, tail_total, cm.side);
             cudaEventRecord(cm.ev_if, cm.side);
             p2p_halo_exchange_on_side(c, c->Ap.p, 1);
-            launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2, tail_total, nullptr, true);
+            launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2, tail_total, nullptr, true, p2p_reserve());
             cudaStreamWaitEvent(c->stream, cm.ev_if, 0);
             np = n1 + n2;
             spmv_pushed = tail_push;

@@ -905,6 +905,12 @@ static CgVecArgs vec_args(en234gpu_ctx* c, int method, int parity) {
     return V;
 }
 
+// EN234_P2P_LL=0: the all-reduce kernels of the PCG loop in their first form (value, fence, flag) instead of self-validating packets
+static bool p2p_ll() {
+    static const bool on = !(getenv("EN234_P2P_LL") && atoi(getenv("EN234_P2P_LL")) == 0);
+    return on;
+}
+
 // EN234_P2P_TAIL: 1 = the producers' last CTAs push the rank's sums, single-warp wait kernels consume them; 2 = the last
 // CTAs are producer AND consumer (push, wait for the peers, add): no collective kernel for the two all-reduces at all
 static int p2p_tail_mode() {
@@ -940,10 +946,12 @@ static bool spmv_sym_ready(en234gpu_ctx* c) {
 }
 
 // y = A x on block rows [row0, row1) (assembled operator); partials are written at part[part_off ...]
-// CTA slots the interior-row SpMV of a partitioned run leaves free (EN234_P2P_RESERVE, default 0): its persistent grid
-// otherwise fills every SM until it ends, so the halo push / wait kernels of the side stream could only start after it
+// CTA slots the interior-row SpMV of a partitioned run leaves free (EN234_P2P_RESERVE, default 32): its persistent grid
+// otherwise fills every SM until it ends, so the halo push / wait kernels of the side stream (32-64 CTAs) start only after
+// it.  Measured on 2 B200 with the packet all-reduce (64^3 per GPU): 0 -> 116.4, 16 -> 112.6, 32 -> 113.0, 64 -> 113.5,
+// 96 -> 117.0 us per PCG iteration.
 static int p2p_reserve() {
-    static const int n = getenv("EN234_P2P_RESERVE") ? std::max(0, atoi(getenv("EN234_P2P_RESERVE"))) : 0;
+    static const int n = getenv("EN234_P2P_RESERVE") ? std::max(0, atoi(getenv("EN234_P2P_RESERVE"))) : 32;
     return n;
 }
 
@@ -1050,25 +1058,30 @@ static void p2p_halo_fork(en234gpu_ctx* c, double* vec, int check_stop) {
     cudaEventRecord(cm.ev_join, cm.side);
 }
 static void p2p_halo_join(en234gpu_ctx* c) { cudaStreamWaitEvent(c->stream, c->comm.ev_join, 0); }
-// the same exchange for a caller that has already forked the side stream
-static void p2p_halo_exchange_on_side(en234gpu_ctx* c, double* vec, int check_stop) {
+// the same exchange for a caller that has already forked the side stream; phase 1 = push only, 2 = wait + add only (the
+// single-stream form puts the interior rows between the two), 3 = both on the side stream + the join event
+static void p2p_halo_exchange_on_side(en234gpu_ctx* c, double* vec, int check_stop, int phase = 3, cudaStream_t stream = nullptr) {
     Comm& cm = c->comm;
+    if (!stream) stream = cm.side;
     if (cm.n_nbr > 0) {
         int mx = 0;
         for (int k = 0; k < cm.n_nbr; ++k) mx = std::max(mx, 3 * (cm.shared_ptr[k + 1] - cm.shared_ptr[k]));
         const int nblk = std::max(1, std::min(32, (mx + 255) / 256));
-        k_halo_push<<<dim3(nblk, cm.n_nbr), 256, 0, cm.side>>>(cm.peers, cm.halo, vec, c->S.p, check_stop);
-        if (cm.fused) {
+        if (phase & 1) {
+            k_halo_push<<<dim3(nblk, cm.n_nbr), 256, 0, stream>>>(cm.peers, cm.halo, vec, c->S.p, check_stop);
+            c->st.kernel_launches += 1;
+        }
+        if ((phase & 2) && cm.fused) {
             // one launch: wait for all neighbours, add own and received values in ascending rank order
-            k_halo_wait_total<<<std::max(1, std::min(64, (3 * cm.n_interface + 255) / 256)), 256, 0, cm.side>>>(cm.F, vec, c->S.p, check_stop);
-            c->st.kernel_launches += 2;
-        } else {
+            k_halo_wait_total<<<std::max(1, std::min(64, (3 * cm.n_interface + 255) / 256)), 256, 0, stream>>>(cm.F, vec, c->S.p, check_stop);
+            c->st.kernel_launches += 1;
+        } else if (phase & 2) {
             for (int k = 0; k < cm.n_nbr; ++k)
-                k_halo_wait_add<<<nblk, 256, 0, cm.side>>>(cm.peers, cm.halo, k, k == cm.n_nbr - 1 ? 1 : 0, vec, c->S.p, check_stop);
-            c->st.kernel_launches += 1 + cm.n_nbr;
+                k_halo_wait_add<<<nblk, 256, 0, stream>>>(cm.peers, cm.halo, k, k == cm.n_nbr - 1 ? 1 : 0, vec, c->S.p, check_stop);
+            c->st.kernel_launches += cm.n_nbr;
         }
     }
-    cudaEventRecord(cm.ev_join, cm.side);
+    if (phase == 3) cudaEventRecord(cm.ev_join, cm.side);
 }
 
 // one PCG iteration on the stream (captured into the graph)
@@ -1117,7 +1130,19 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
         const bool tail_push = p2p_tail_mode() != 0, tail_finish = p2p_tail_mode() == 2;
         bool spmv_pushed = false;
         int np = 0;
-        if (method == EN234_SOLVE_PCG_BSR && cm.n_interface > 0 && cm.n_interface < c->N) {
+        static const bool serial = getenv("EN234_P2P_SERIAL") && atoi(getenv("EN234_P2P_SERIAL")) == 1;
+        bool joined = false;
+        if (serial && method == EN234_SOLVE_PCG_BSR && cm.n_interface > 0 && cm.n_interface < c->N) {
+            // ONE stream: interface rows -> push -> interior rows -> wait + add.  The pushed values cross NVLink while the
+            // interior rows run; no fork / join edges between graph branches.
+            int n1 = 0, n2 = 0;
+            launch_spmv_rows(c, c->p.p, c->Ap.p, 0, cm.n_interface, 0, 1, &n1);
+            p2p_halo_exchange_on_side(c, c->Ap.p, 1, 1, c->stream);
+            launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2);
+            p2p_halo_exchange_on_side(c, c->Ap.p, 1, 2, c->stream);
+            np = n1 + n2;
+            joined = true;
+        } else if (method == EN234_SOLVE_PCG_BSR && cm.n_interface > 0 && cm.n_interface < c->N) {
             // side stream: the few interface rows, then their exchange (push, wait + add); main stream: the interior rows
             // at the same time.  The all-reduce needs the partials of both launches (ev_if), k_cg_update the whole side
             // stream (ev_join).
@@ -1149,16 +1174,16 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
         }
         if (spmv_pushed && tail_finish) { /* the last SpMV CTA left the total in part[0] */ }
         else if (spmv_pushed) k_p2p_wait<<<1, 32, 0, c->stream>>>(cm.peers, c->part.p, nullptr, c->S.p);
-        else launch_pdl(k_p2p_allreduce, 1, VEC_THREADS, c->stream, cm.peers, (const double*)c->part.p, np, (const double*)nullptr, 0,
-                        c->part.p, (double*)nullptr, (const CgScalars*)c->S.p, 1);
-        p2p_halo_join(c);
+        else launch_pdl(p2p_ll() ? k_p2p_allreduce : k_p2p_allreduce_fence, 1, VEC_THREADS, c->stream, cm.peers, (const double*)c->part.p, np,
+                        (const double*)nullptr, 0, c->part.p, (double*)nullptr, (const CgScalars*)c->S.p, 1);
+        if (!joined) p2p_halo_join(c);
         CgVecArgs V = vec_args(c, method, parity);
         if (tail_push) { V.tail = (ArenaHdr*)cm.arena; V.tail_finish = tail_finish ? 1 : 0; }
         launch_pdl(k_cg_update<false>, c->grid_vec, VEC_THREADS, c->stream, V);
         if (tail_finish) { /* k_cg_update's last CTA left the totals in part2[0] / part3[0] */ }
         else if (tail_push) k_p2p_wait<<<1, 32, 0, c->stream>>>(cm.peers, c->part2.p, c->part3.p, c->S.p);
-        else launch_pdl(k_p2p_allreduce, 1, VEC_THREADS, c->stream, cm.peers, (const double*)c->part2.p, c->grid_vec,
-                        (const double*)c->part3.p, c->grid_vec, c->part2.p, c->part3.p, (const CgScalars*)c->S.p, 1);
+        else launch_pdl(p2p_ll() ? k_p2p_allreduce : k_p2p_allreduce_fence, 1, VEC_THREADS, c->stream, cm.peers, (const double*)c->part2.p,
+                        c->grid_vec, (const double*)c->part3.p, c->grid_vec, c->part2.p, c->part3.p, (const CgScalars*)c->S.p, 1);
         launch_pdl(k_cg_pupdate, c->grid_vec, VEC_THREADS, c->stream, V);
         c->st.kernel_launches += tail_finish ? (spmv_pushed ? 2 : 3) : 4;
         return 0;
@@ -2096,6 +2121,42 @@ int en234gpu_measure_fp64_peak(en234gpu_handle c, double* tflops) {
         if (rep > 0) best = std::max(best, 2.0 * 16.0 * iters * (double)grid * 256.0 / (ms * 1e-3) / 1e12);
     }
     *tflops = best;
+    return 0;
+}
+
+// Latency of the collectives of the partitioned PCG loop in isolation (collective call: every rank, same arguments):
+// which = 0: scalar all-reduce kernel (k_p2p_allreduce over grid_vec partials), 1: halo sum of a DOF vector (push + wait),
+// 2: an empty single-thread kernel (launch floor).  Back-to-back launches inside one captured graph, like the loop.
+int en234gpu_bench_collective(en234gpu_handle c, int which, int reps, double* us_per_call) {
+    CK(cudaSetDevice(c->device));
+    if (!c->comm.active || !c->comm.p2p) return set_err("bench_collective: needs a partitioned handle with connected peer-memory arenas");
+    if (reps < 1) reps = 1;
+    CK(cudaMemsetAsync(c->part2.p, 0, c->part2.n * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->part3.p, 0, c->part3.n * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->S.p, 0, sizeof(CgScalars), c->stream));
+    CK(cudaMemsetAsync(c->Ap.p, 0, (size_t)c->ndof * sizeof(double), c->stream));
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < 64; ++i) {
+        if (which == 0) k_p2p_allreduce<<<1, VEC_THREADS, 0, c->stream>>>(c->comm.peers, c->part2.p, c->grid_vec, c->part3.p, c->grid_vec,
+                                                                         c->part2.p, c->part3.p, c->S.p, 0);
+        else if (which == 1) comm_halo_sum_p2p(c->comm, c->Ap.p, c->stream);
+        else k_pack2<<<1, 1, 0, c->stream>>>(c->part2.p, c->part3.p);
+    }
+    CK(cudaStreamEndCapture(c->stream, &g));
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    CK(cudaGraphDestroy(g));
+    CK(cudaGraphLaunch(ge, c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i) CK(cudaGraphLaunch(ge, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaGetLastError());
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    CK(cudaGraphExecDestroy(ge));
+    *us_per_call = 1e3 * (double)t / (64.0 * reps);
     return 0;
 }
 

@@ -42,6 +42,7 @@ struct ArenaHdr {
     unsigned int tk_spmv, tk_upd;              // last-CTA tickets of the fused PCG kernels (k_spmv tail, k_cg_update tail)
     unsigned int arrive;                       // warps of the fused k_spmv that have finished their interface rows
     int pad[3];
+    unsigned long long ll[2][P2P_MAXR][4];     // all-reduce packets (k_p2p_allreduce): 4 words of (sequence << 32 | half a double)
     BcastSlot bc[2][P2P_MAXCTA];               // local re-broadcast of an all-reduced pair to the CTAs of the consumer kernel
     PeerSet peers;                             // device copy of the peer table (producer tails reach it through one pointer)
 };
@@ -74,7 +75,76 @@ __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsig
 }
 
 // single CTA.  outA/outB receive the global sums; partB may be null.
+// The pair travels as four 8-byte packets, each carrying its own validity tag — (sequence number << 32) | half of a double,
+// one aligned 8-byte store each — so no fence separates "data" from "flag" (a system-scope fence between a remote store and
+// its flag costs an NVLink round trip): the receiver polls the four words of every source until all carry this operation's
+// sequence number.  Slots alternate with the sequence parity; a slot's previous content carries sequence - 2.
+// Measured on 2 B200 (tests/mgpu_check.py --latency-only): 8.0 us per call with value / fence / flag, see DESIGN.md section 5.
+__device__ __forceinline__ unsigned long long ll_pack(unsigned long long seq, unsigned int half) {
+    return (seq << 32) | (unsigned long long)half;
+}
 __global__ void __launch_bounds__(VEC_THREADS) k_p2p_allreduce(PeerSet P, const double* partA, int nA, const double* partB,
+                                                               int nB, double* outA, double* outB, const CgScalars* S,
+                                                               int check_stop) {
+    __shared__ double red[VEC_THREADS / 32 + 1];
+    __shared__ double red2[VEC_THREADS / 32 + 1];
+    __shared__ double got[P2P_MAXR][2];
+    pdl_wait();
+    pdl_trigger();
+    if (check_stop && S->stop) return;
+    ArenaHdr* mine = P.arena[P.me];
+    // both partial arrays in one pass; per value the same order as reduce_partials (strided sums, shuffle tree, warps in order)
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nA; i += VEC_THREADS) a += partA[i];
+    if (partB) for (int i = threadIdx.x; i < nB; i += VEC_THREADS) b += partB[i];
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = a; red2[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    const unsigned long long seq = ld_volatile_u64(&mine->ar_seq) + 1ULL;
+    const unsigned long long tag = seq & 0xffffffffULL;
+    const int par = (int)(seq & 1ULL);
+    const int r = threadIdx.x;
+    if (r < P.n_ranks) {
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int w = 0; w < VEC_THREADS / 32; ++w) { sa += red[w]; sb += red2[w]; }
+        const unsigned long long ua = (unsigned long long)__double_as_longlong(sa), ub = (unsigned long long)__double_as_longlong(sb);
+        volatile unsigned long long* dst = P.arena[r]->ll[par][P.me];
+        dst[0] = ll_pack(tag, (unsigned int)ua);
+        dst[1] = ll_pack(tag, (unsigned int)(ua >> 32));
+        dst[2] = ll_pack(tag, (unsigned int)ub);
+        dst[3] = ll_pack(tag, (unsigned int)(ub >> 32));
+        // wait for source rank r's four packets
+        const volatile unsigned long long* src = mine->ll[par][r];
+        const long long t0 = clock64();
+        unsigned long long w0, w1, w2, w3;
+        bool ok = true;
+        for (;;) {
+            w0 = src[0]; w1 = src[1]; w2 = src[2]; w3 = src[3];
+            if ((w0 >> 32) == tag && (w1 >> 32) == tag && (w2 >> 32) == tag && (w3 >> 32) == tag) break;
+            if (clock64() - t0 > P.timeout) {
+                *(volatile int*)&mine->error = 1;
+                if (check_stop) { CgScalars* Sw = const_cast<CgScalars*>(S); *(volatile int*)&Sw->fail = 1; *(volatile int*)&Sw->stop = 1; }
+                ok = false;
+                break;
+            }
+        }
+        got[r][0] = ok ? __longlong_as_double((long long)((w0 & 0xffffffffULL) | (w1 << 32))) : 0.0;
+        got[r][1] = ok ? __longlong_as_double((long long)((w2 & 0xffffffffULL) | (w3 << 32))) : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0.0, sb = 0.0;
+        for (int q = 0; q < P.n_ranks; ++q) { sa += got[q][0]; sb += got[q][1]; }      // fixed rank order => identical sums on all ranks
+        *outA = sa;
+        if (outB) *outB = sb;
+        mine->ar_seq = seq;
+    }
+}
+
+// the first form of the all-reduce kernel (value, system fence, flag): kept for A/B (EN234_P2P_LL=0)
+__global__ void __launch_bounds__(VEC_THREADS) k_p2p_allreduce_fence(PeerSet P, const double* partA, int nA, const double* partB,
                                                                int nB, double* outA, double* outB, const CgScalars* S,
                                                                int check_stop) {
     __shared__ double red[VEC_THREADS / 32 + 1];

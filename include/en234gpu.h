@@ -314,6 +314,9 @@ int en234gpu_multi_get_stats(en234gpu_multi_handle h, struct en234gpu_stats* s);
  * kernel y = A p (method 0: block-CSR SpMV; 1: matrix-free apply) after `warm` untimed ones — the per-launch
  * duration the roofline figures are computed from */
 int en234gpu_bench_operator(en234gpu_handle h, int method, int warm, int reps, double* ms_per_launch);
+/* measurement helper, collective over the ranks: microseconds per call of which = 0 the scalar all-reduce kernel of the PCG
+ * loop, 1 a peer-memory halo sum of a DOF vector, 2 an empty kernel (launch floor); 64 calls per captured graph x reps */
+int en234gpu_bench_collective(en234gpu_handle h, int which, int reps, double* us_per_call);
 /* measured FP64 FMA throughput of the handle's device in TFLOP/s (an FMA micro-kernel, best of 5): the roof of the
  * FP64-bound kernels (element kernel, general-mesh matrix-free operator), reported beside the HBM roof */
 int en234gpu_measure_fp64_peak(en234gpu_handle h, double* tflops);

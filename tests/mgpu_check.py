@@ -19,7 +19,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     only = None                                   # --dynamics-only / --project-only: one section (GPU-minute budget)
-    for flag in ("--dynamics-only", "--project-only", "--c3d8-only", "--static-only", "--print-only"):
+    for flag in ("--dynamics-only", "--project-only", "--c3d8-only", "--static-only", "--print-only", "--latency-only"):
         if flag in sys.argv:
             sys.argv.remove(flag)
             only = flag[2:-5]
@@ -71,6 +71,8 @@ def main():
         ok = c3d8_section(rank, world, local) and ok
     if only in (None, "print"):
         ok = print_section(rank, world, local, dims, jitter) and ok
+    if only == "latency":
+        latency_section(rank, world, local, dims, jitter)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
@@ -163,6 +165,32 @@ def c3d8_section(rank, world, local):
     dist.barrier()
     g.close()
     return ok
+
+
+def latency_section(rank, world, local, dims, jitter):
+    """Collectives of the PCG loop in isolation (en234gpu_bench_collective): us per all-reduce kernel, per halo sum, per empty
+    kernel, back to back inside a captured graph on every rank at once."""
+    import ctypes as C
+    from en234_fea_b200 import gpu_lib
+    m = Model.from_text(synthetic_block_input(*dims, jitter=jitter))
+    part = Partition(m, world, rank)
+    g = GpuSystem(m, device=local, part=part)
+    comm_kind = g.setup_distributed()
+    out = []
+    for which in (2, 0, 1):
+        us = C.c_double()
+        dist.barrier()
+        if gpu_lib().en234gpu_bench_collective(g.h, C.c_int(which), C.c_int(20), C.byref(us)):
+            raise RuntimeError(gpu_lib().en234gpu_last_error().decode())
+        t = torch.tensor([us.value], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out.append(float(t.item()))
+    if rank == 0:
+        print("mgpu_check [%s] world=%d mesh=%s collectives in isolation (max over ranks, 1280 back-to-back calls in graphs): empty kernel %.2f us, "
+              "scalar all-reduce kernel %.2f us, halo sum of %d interface nodes (push + wait) %.2f us"
+              % (comm_kind, world, dims, out[0], out[1], part.ints("shared_nodes").size, out[2]), flush=True)
+    dist.barrier()
+    g.close()
 
 
 def print_section(rank, world, local, dims, jitter):

@@ -173,9 +173,13 @@ static Mesh mesh_of(en234gpu_ctx* c) {
 
 // Kernel launch with the programmatic-dependent-launch attribute (the kernel calls pdl_wait() before it touches what its
 // predecessor in the stream wrote); opt-in with EN234_PDL=1 (64^3: 101.4 us per PCG iteration with and without it).
+// Programmatic dependent launch of the PCG kernels.  One GPU: no gain inside CUDA graphs (101.4 us at 64^3 with and without).
+// Partitioned loop over peer memory: its chain of short kernels gains 4.5 us per iteration on 2 B200 (116.6 -> 112.1), so it
+// is on there by default.  EN234_PDL=0 / 1 overrides both.
+static thread_local bool t_pdl_auto = false;      // set per captured iteration (one host thread per handle)
 static bool use_pdl() {
-    static const bool on = getenv("EN234_PDL") && atoi(getenv("EN234_PDL")) == 1;   // measured: no gain inside CUDA graphs on B200
-    return on;
+    static const int env = getenv("EN234_PDL") ? atoi(getenv("EN234_PDL")) : -1;
+    return env >= 0 ? env == 1 : t_pdl_auto;
 }
 template <class... KArgs, class... Args>
 static void launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, Args... args) {
@@ -1087,6 +1091,7 @@ static void p2p_halo_exchange_on_side(en234gpu_ctx* c, double* vec, int check_st
 // one PCG iteration on the stream (captured into the graph)
 static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
     Comm& cm = c->comm;
+    t_pdl_auto = cm.active && cm.p2p;
     if (cm.active && cm.p2p && cm.fused && cm.fused_loop) {
         // collectives folded into the kernels: no collective has a launch of its own
         if (method == EN234_SOLVE_PCG_BSR) {

@@ -1014,6 +1014,117 @@ def test_tie_plan_host_logic_groups_roots_and_multiplier_recovery_order():
     assert np.abs(got - dl).max() < 1e-12
 
 
+@pytest.fixture(scope="module")
+def emul_ties(tmp_path_factory):
+    """tests/emul/emul_ties.cpp: the tie-constraint device kernels compiled for the host with the address / UB sanitisers."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++") or "/opt/gcc/bin/g++"
+    exe = tmp_path_factory.mktemp("emul_ties") / "emul_ties"
+    src = os.path.join(ROOT, "tests", "emul")
+    r = subprocess.run([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                        "-I" + os.path.join(src, "stub"), "-I" + os.path.join(ROOT, "en234_fea_b200", "csrc"),
+                        os.path.join(src, "emul_ties.cpp"), "-o", str(exe)], capture_output=True, text=True)
+    if r.returncode:
+        pytest.skip("host compiler cannot build the emulation harness: " + r.stderr[-300:])
+    return str(exe)
+
+
+@pytest.mark.parametrize("case", ["cut", "pull"])
+def test_tie_device_kernels_compiled_for_the_host_solve_the_saddle_point_system(emul_ties, tmp_path, case):
+    """The device path's treatment of tie constraints, with the device kernels themselves (en234gpu_ties.cuh compiled for the
+    host), on a real finite-element matrix: the reduced PCG solve + member corrections equal the displacement part of a dense
+    solve of the reference's saddle-point system [[K, C^T], [C, 0]] (compliance 0), and the multiplier corrections recovered
+    from the tied rows of rhs - K du in the planned order equal its multiplier part.  'cut': a body held only by its ties, a
+    non-zero gap to close, non-zero multipliers; 'pull': a tied face whose master DOF is prescribed (members follow a known
+    correction)."""
+    import subprocess
+    import meshes
+    from en234_fea_b200 import tie_plan
+    if case == "cut":
+        text, info = meshes.tied_block_text(3, 2, 2, cut=1)
+    else:
+        text, info = meshes.tied_block_text(3, 2, 2, tie_face_dof=1, pull=0.05)
+    m = Model.from_text(text)
+    a = m.arrays()
+    n = 3 * m.n_nodes
+    rng = np.random.default_rng(3)
+    ut, du = np.zeros(n), 1e-3 * rng.standard_normal(n)           # an iterate that violates the ties: gaps to close
+    s = ob.OracleSystem(ob.OracleModel(a), 2)                      # K and rhs without constraint terms (CG path ignores them)
+    assert s.assemble(ut, du)[2] == 0
+    s.apply_bc(ut, du)
+    A, rhs = s.matrix()
+    K = A.toarray()
+    _, _, fd, fv, _ = m.evaluate_loads(0.0, 1.0, ut, du)
+    cflag, cval = np.zeros(n, np.int32), np.zeros(n)
+    cflag[fd] = 1
+    cval[fd] = fv - (ut + du)[fd]
+    assert np.allclose(rhs[fd], cval[fd], atol=1e-15) and np.allclose(K[fd, fd], 1.0)
+    d1 = 3 * (a["con_node1"] - 1) + a["con_dof1"] - 1
+    d2 = 3 * (a["con_node2"] - 1) + a["con_dof2"] - 1
+    nt = d1.size
+    lam = rng.standard_normal(nt)
+    free1, free2 = cflag[d1] == 0, cflag[d2] == 0
+    rhs_ref = rhs.copy()
+    np.subtract.at(rhs_ref, d1[free1], lam[free1])
+    np.add.at(rhs_ref, d2[free2], lam[free2])
+    # ---- dense reference: [[K, C^T], [C, 0]] [d; dl] = [rhs_ref; gap], prescribed columns of C moved to the right-hand side
+    Cm = np.zeros((nt, n))
+    Cm[np.arange(nt), d1] = 1.0
+    Cm[np.arange(nt), d2] = -1.0
+    w = ut + du
+    gap = w[d2] - w[d1] - Cm[:, fd] @ cval[fd]
+    Cb = Cm.copy()
+    Cb[:, fd] = 0.0
+    M = np.block([[K, Cb.T], [Cb, np.zeros((nt, nt))]])
+    M[fd, n:] = 0.0                                               # prescribed rows are identity rows
+    ref = np.linalg.solve(M, np.concatenate([rhs_ref, gap]))
+    d_ref, dl_ref = ref[:n], ref[n:]
+    # ---- device-kernel path
+    P = tie_plan(d1, d2, fixed_dof=fd)
+    ng, nm = len(P["group_root"]), len(P["member_dof"])
+    m_root = np.concatenate([np.full(P["group_ptr"][g + 1] - P["group_ptr"][g], P["group_root"][g]) for g in range(ng)]).astype(np.int32)
+    m_fixed = np.concatenate([np.full(P["group_ptr"][g + 1] - P["group_ptr"][g], P["group_fixed"][g]) for g in range(ng)]).astype(np.int32)
+    tdof = np.unique(np.concatenate([d1, d2])).astype(np.int32)
+    ent = [[] for _ in tdof]
+    pos = {int(d): i for i, d in enumerate(tdof)}
+    for k in range(nt):
+        ent[pos[int(d1[k])]].append(2 * k)
+        ent[pos[int(d2[k])]].append(2 * k + 1)
+    tptr = np.concatenate([[0], np.cumsum([len(e) for e in ent])]).astype(np.int32)
+    tent = np.array([x for e in ent for x in e], np.int32)
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        np.array([n, nt, ng, nm, tdof.size], np.int32).tofile(f)
+        for v in (K.ravel(), rhs_ref, 1.0 / np.diag(K), ut, du, cval):
+            np.asarray(v, np.float64).tofile(f)
+        cflag.tofile(f)
+        d1.astype(np.int32).tofile(f); d2.astype(np.int32).tofile(f); lam.tofile(f)
+        for v in (P["group_root"], P["group_ptr"], P["group_fixed"], P["member_dof"], m_root, m_fixed, tdof, tptr, tent):
+            np.asarray(v, np.int32).tofile(f)
+    r = subprocess.run([emul_ties, str(inp), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    raw = np.fromfile(out)
+    sol, trow, gap_k, rhs_tied, iters = raw[:n], raw[n:n + tdof.size], raw[n + tdof.size:n + tdof.size + nt], raw[n + tdof.size + nt:-1], raw[-1]
+    assert 0 < iters < 20 * n
+    assert np.abs(sol - d_ref).max() < 1e-9 * np.abs(d_ref).max()
+    new_w = w + sol
+    assert np.abs(new_w[d1] - new_w[d2]).max() < 1e-13                        # tied exactly after the correction
+    assert np.abs(gap_k - gap).max() < 1e-15                                   # k_tie_gap: the multiplier rows' right-hand side
+    want = rhs_ref.copy()
+    np.subtract.at(want, d1, lam)
+    np.add.at(want, d2, lam)
+    assert np.abs(rhs_tied - want).max() < 1e-14                               # k_tie_rhs: -/+ lambda per constraint, in order
+    row = {int(d): trow[i] for i, d in enumerate(tdof)}
+    got = np.zeros(nt)
+    for k, leaf in zip(P["peel_tie"], P["peel_dof"]):
+        first = int(d1[k]) == int(leaf)
+        got[k] = row[int(leaf)] if first else -row[int(leaf)]
+        other = int(d2[k]) if first else int(d1[k])
+        row[other] += got[k] if first else -got[k]
+    assert np.abs(got - dl_ref).max() < 1e-8 * max(1.0, np.abs(dl_ref).max())
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """bench.py --impl reference (the CPU arm the driver runs beside the CUDA arm) on a small block: one JSON line with the
     contract keys, on rank 0 only."""

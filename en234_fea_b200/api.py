@@ -57,7 +57,7 @@ GPU_SYMBOLS = [
     "en234gpu_multi_zero_increment_dev", "en234gpu_multi_download_state", "en234gpu_multi_n_parts",
     "en234gpu_multi_part_handle", "en234gpu_multi_part_info", "en234gpu_multi_get_stats",
     "en234gpu_partition_sizes", "en234gpu_partition_arrays",
-    "en234gpu_set_ties", "en234gpu_get_lagrange_multipliers", "en234gpu_comm_allreduce_host", "en234gpu_tie_plan", "en234gpu_bench_collective",
+    "en234gpu_set_ties", "en234gpu_get_lagrange_multipliers", "en234gpu_reset_lagrange_multipliers", "en234gpu_comm_allreduce_host", "en234gpu_tie_plan", "en234gpu_bench_collective",
 ]
 HOST_SYMBOLS = [
     "en234host_model_read", "en234host_model_from_text", "en234host_model_free", "en234host_last_error",

@@ -178,6 +178,15 @@ extern "C" int en234gpu_set_ties(en234gpu_handle c, int n_ties, const int* dof1,
     return 0;
 }
 
+// a new analysis on the same handle starts from zero multipliers (read_input_file.f90:139)
+extern "C" int en234gpu_reset_lagrange_multipliers(en234gpu_handle c) {
+    if (c->ties.n == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    std::fill(c->ties.lambda.begin(), c->ties.lambda.end(), 0.0);
+    CK(cudaMemsetAsync(c->ties.dlambda.p, 0, c->ties.n * sizeof(double), c->stream));
+    return 0;
+}
+
 extern "C" int en234gpu_get_lagrange_multipliers(en234gpu_handle c, int n, double* out) {
     if (n != c->ties.n) return set_err("en234gpu_get_lagrange_multipliers: the handle has " + std::to_string(c->ties.n) + " tie constraints");
     for (int k = 0; k < n; ++k) out[k] = c->ties.lambda[k];

@@ -99,6 +99,8 @@ int compute_static_step(const Model& m, en234gpu_handle h, const StepOptions& op
     res.dof_total.assign(ndof, 0.0);
     res.rforce.assign(ndof, 0.0);
     std::vector<double> dof_increment(ndof, 0.0);
+    // every analysis starts from zero Lagrange multipliers (read_input_file.f90:139); the handle keeps them between calls
+    if (!m.constraints.empty() && en234gpu_reset_lagrange_multipliers(h)) { res.error = en234gpu_last_error(); return -1; }
     TimeCtl t;
     t.DTIME = m.timestep_initial;
     bool cont = true, converged = false;

@@ -142,6 +142,11 @@ module en234_gpu_iface
             integer(c_int), intent(in) :: dof1(*), dof2(*)
             integer(c_int)             :: en234gpu_set_ties
         end function
+        function en234gpu_reset_lagrange_multipliers(h) bind(C, name='en234gpu_reset_lagrange_multipliers')
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h
+            integer(c_int)     :: en234gpu_reset_lagrange_multipliers
+        end function
         function en234gpu_get_lagrange_multipliers(h, n_ties, lagrange_multipliers) bind(C, name='en234gpu_get_lagrange_multipliers')
             import :: c_ptr, c_int, c_double
             type(c_ptr), value          :: h

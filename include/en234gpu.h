@@ -226,6 +226,8 @@ int en234gpu_set_ties(en234gpu_handle h, int n_ties, const int* dof1, const int*
  * may be NULL.  Non-zero (en234gpu_last_error) for loops and for two prescribed DOFs in one group. */
 int en234gpu_tie_plan(int n_ties, const int* dof1, const int* dof2, int n_fixed, const int* fixed_dof, int* sizes,
                       int* group_root, int* group_ptr, int* group_fixed, int* member_dof, int* peel_tie, int* peel_dof);
+/* lagrange_multipliers = 0 (read_input_file.f90:139): call before a new analysis on a handle that has already run one */
+int en234gpu_reset_lagrange_multipliers(en234gpu_handle h);
 /* lagrange_multipliers(1:n_constraints) of module Boundaryconditions after the last solve */
 int en234gpu_get_lagrange_multipliers(en234gpu_handle h, int n_ties, double* out);
 

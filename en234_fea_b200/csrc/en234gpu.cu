@@ -181,6 +181,13 @@ static bool use_pdl() {
     static const int env = getenv("EN234_PDL") ? atoi(getenv("EN234_PDL")) : -1;
     return env >= 0 ? env == 1 : t_pdl_auto;
 }
+// The interior-row SpMV of a partitioned run is launched programmatically only on request (EN234_PDL=1): launched early, its
+// persistent CTAs would take the SM slots before the interface-row SpMV of the side stream — which everything downstream
+// (halo push, the peers' waits) hangs on — has started; the short kernels of the chain have no such side effect.
+static bool use_pdl_interior_spmv() {
+    static const bool on = getenv("EN234_PDL") && atoi(getenv("EN234_PDL")) == 1;
+    return on;
+}
 template <class... KArgs, class... Args>
 static void launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -1160,7 +1167,7 @@ static int enqueue_iteration(en234gpu_ctx* c, int method, int parity) {
             launch_spmv_rows(c, c->p.p, c->Ap.p, 0, cm.n_interface, 0, 1, &n1, tail_total, cm.side);
             cudaEventRecord(cm.ev_if, cm.side);
             p2p_halo_exchange_on_side(c, c->Ap.p, 1);
-            launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2, tail_total, nullptr, true, p2p_reserve());
+            launch_spmv_rows(c, c->p.p, c->Ap.p, cm.n_interface, c->N, n1, 1, &n2, tail_total, nullptr, use_pdl_interior_spmv(), p2p_reserve());
             cudaStreamWaitEvent(c->stream, cm.ev_if, 0);
             np = n1 + n2;
             spmv_pushed = tail_push;

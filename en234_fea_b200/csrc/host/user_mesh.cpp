@@ -134,7 +134,7 @@ std::string write_input_text(const Model& m) {
     if (any_user || !any_internal) o << " ELEMENTS, USER\n";
     for (const auto& g : m.groups) {
         if (g.flag == 10003) continue;
-        o << "  PARAMETERS, 8, " << g.n_states << ", ";
+        o << "  PARAMETERS, " << m.nodes_per_element << ", " << g.n_states << ", ";
         if (g.flag > 99999) o << (m.explicitdynamicstep ? "VU" : "U") << g.flag - 99999; else o << g.flag;
         o << "\n";
         if (g.first_element < (int)m.element_density.size() && m.element_density[g.first_element] != 0.0)
@@ -142,9 +142,10 @@ std::string write_input_text(const Model& m) {
         o << "  PROPERTIES\n";
         for (int k = 0; k < g.n_props; ++k) o << "   " << m.element_properties[g.prop_index + k] << "\n";
         o << "  END PROPERTIES\n  CONNECTIVITY, " << (g.zone.empty() ? "zone" : g.zone) << "\n";
+        const int npe = m.nodes_per_element;
         for (int e = g.first_element; e < g.first_element + g.n_elements; ++e) {
             o << "   " << e + 1;
-            for (int a = 0; a < 8; ++a) o << ", " << m.connectivity[8 * (size_t)e + a];
+            for (int a = 0; a < npe; ++a) o << ", " << m.connectivity[(size_t)npe * e + a];
             o << "\n";
         }
         o << "  END CONNECTIVITY\n";
@@ -205,6 +206,17 @@ std::string write_input_text(const Model& m) {
             o << "\n";
         }
         o << " END DISTRIBUTED LOADS\n";
+    }
+    for (const auto& cp : m.constraint_parameters) {                  // read_input_file.f90:1067-1098
+        o << " CONSTRAINT PARAMETERS, " << cp.name << "\n";
+        for (double v : cp.values) o << "  " << v << "\n";
+        o << " END CONSTRAINT PARAMETERS\n";
+    }
+    if (!m.constraints.empty()) {                                     // two-node ties, written pair by pair (:1436-1444)
+        o << " CONSTRAINTS\n";
+        for (const auto& c : m.constraints)
+            o << "  CONSTRAIN NODE PAIRS, 1, " << c.node1 << ", " << c.dof1 << ", " << c.node2 << ", " << c.dof2 << "\n";
+        o << " END CONSTRAINTS\n";
     }
     o << "END BOUNDARY CONDITIONS\n";
     auto put_print_state = [&]() {

@@ -1125,6 +1125,25 @@ def test_tie_device_kernels_compiled_for_the_host_solve_the_saddle_point_system(
     assert np.abs(got - dl_ref).max() < 1e-8 * max(1.0, np.abs(dl_ref).max())
 
 
+def test_written_input_text_keeps_constraints_and_other_element_shapes():
+    """Model.text() (the literal .in text of a parsed model) round-trips the CONSTRAINTS block — as CONSTRAIN NODE PAIRS lines
+    with node numbers — and meshes of 4- / 10- / 20-node elements."""
+    import meshes
+    text, info = meshes.tied_block_text(3, 2, 2, cut=1, tie_face_dof=2)
+    a = Model.from_text(text).arrays()
+    b = Model.from_text(Model.from_text(text).text()).arrays()
+    assert a["con_node1"].size == 3 * len(info["copy"]) + len(info["xmax"]) - 1
+    for k in ("con_node1", "con_dof1", "con_node2", "con_dof2", "connectivity", "pdof_dof", "pforce_dof"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["coords"], b["coords"])
+    for shape in ("tet4", "tet10", "hex20"):
+        t = meshes.input_text(shape, 2, 2, 1)
+        a = Model.from_text(t).arrays()
+        b = Model.from_text(Model.from_text(t).text()).arrays()
+        assert a["nodes_per_element"][0] == b["nodes_per_element"][0] == {"tet4": 4, "tet10": 10, "hex20": 20}[shape]
+        assert np.array_equal(a["connectivity"], b["connectivity"]) and np.array_equal(a["coords"], b["coords"])
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """bench.py --impl reference (the CPU arm the driver runs beside the CUDA arm) on a small block: one JSON line with the
     contract keys, on rank 0 only."""
